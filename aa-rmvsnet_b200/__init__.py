@@ -1,2 +1,11 @@
-"""aarmvsnet_b200: B200-native (sm_100a) AA-RMVSNet per-depth-plane cost-volume pipeline."""
+"""aarmvsnet_b200: B200-native (sm_100a) AA-RMVSNet per-depth-plane cost-volume pipeline.
+
+Public API mirrors the reference (models/drmvsnet.py): ``EMVSNet(...)(imgs, proj_matrices, depth_values)``.
+The arithmetic lives in lib/libaarmvs_sm100.so (C ABI: include/aarmvs.h); there is no CPU path.
+"""
+from . import synth                                     # noqa: F401
+from .model import EMVSNet                              # noqa: F401
+from .ops import homo_warping_depthwise                 # noqa: F401
+
 __version__ = "0.1.0"
+__all__ = ["EMVSNet", "homo_warping_depthwise", "synth"]

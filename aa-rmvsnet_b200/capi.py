@@ -1,0 +1,92 @@
+"""ctypes binding of lib/libaarmvs_sm100.so (the C ABI declared in include/aarmvs.h).
+
+There is no fallback: if the library is missing or a call fails, RuntimeError is raised.
+"""
+import ctypes
+import os
+
+from . import build as _build
+
+ERR_ARG = 1000001
+SRC_PLAIN, SRC_GN_RELU, SRC_MAXPOOL2, SRC_NCHW = 0, 1, 2, 3
+
+c_float_p = ctypes.POINTER(ctypes.c_float)
+
+
+class ConvSrc(ctypes.Structure):
+    """struct aarmvs_conv_src (include/aarmvs.h)."""
+    _fields_ = [
+        ("ptr", ctypes.c_void_p),
+        ("channels", ctypes.c_int),
+        ("mode", ctypes.c_int),
+        ("planes", ctypes.c_int),
+        ("gn_groups", ctypes.c_int),
+        ("gn_sums", ctypes.c_void_p),
+        ("gn_weight", ctypes.c_void_p),
+        ("gn_bias", ctypes.c_void_p),
+        ("gn_count", ctypes.c_double),
+        ("pp_stride", ctypes.c_size_t),
+        ("pp_phase", ctypes.c_int),
+    ]
+
+
+_P, _I, _SZ, _F = ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t, ctypes.c_float
+_SRCP = ctypes.POINTER(ConvSrc)
+
+# name -> (restype, argtypes); must list every symbol include/aarmvs.h declares (tests/test_capi_symbols.py)
+PROTOTYPES = {
+    "aarmvs_version": (_I, []),
+    "aarmvs_sm_count": (_I, []),
+    "aarmvs_conv2d": (_I, [_SRCP, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _I, _P, _P]),
+    "aarmvs_deform_conv": (_I, [_SRCP, _I, _I, _P, _P, _P, _P, _P, _P]),
+    "aarmvs_feat_assemble": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P]),
+    "aarmvs_warp": (_I, [_P, _P, _I, _I, c_float_p, _F, _I, _P]),
+    "aarmvs_omega_stats_bytes": (_SZ, [_I]),
+    "aarmvs_omega_tail_floats": (_I, []),
+    "aarmvs_cost_stem": (_I, [_P, _P, _SZ, _I, _I, _I, _P, c_float_p, c_float_p, _P, _I, _P, _I, _P, _P, _P]),
+    "aarmvs_omega_stats": (_I, [_I, _P, _I, _I, _I, c_float_p, _P, _P]),
+    "aarmvs_aggregate": (_I, [_P, _P, _SZ, _I, _I, _I, _P, c_float_p, _P, _I, _P, _I, _P, _P, _P, _P, _P]),
+    "aarmvs_convlstm_cell": (_I, [_SRCP, _I, _I, _I, _I, _I, _P, _P, _P, _P, _I, _P, _P]),
+    "aarmvs_deconv2x": (_I, [_SRCP, _I, _I, _P, _P, _P, _P, _I, _P, _P]),
+    "aarmvs_head_wta": (_I, [_SRCP, _I, _I, c_float_p, c_float_p, _P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "aarmvs_next_plane": (_I, [_P, _P, _I, _P]),
+}
+
+_lib = None
+
+
+def library_path():
+    return _build.LIB
+
+
+def load(build_if_missing=True):
+    """Load (building first if the .so is absent and nvcc is present) and type every entry point."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = library_path()
+    if not os.path.exists(path):
+        if not build_if_missing:
+            raise RuntimeError(f"{path} is missing: run `python __graft_entry__.py build` (nvcc, sm_100a)")
+        _build.build_library()
+    lib = ctypes.CDLL(path)
+    for name, (res, args) in PROTOTYPES.items():
+        fn = getattr(lib, name)          # AttributeError here = ABI drift between the header and the library
+        fn.restype = res
+        fn.argtypes = args
+    if lib.aarmvs_version() != 1:
+        raise RuntimeError("libaarmvs_sm100.so: ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+def check(code, what):
+    if code != 0:
+        kind = "rejected argument" if code == ERR_ARG else f"cudaError {code}"
+        raise RuntimeError(f"{what} failed: {kind}")
+
+
+def host_floats(values):
+    """A ctypes float array (host memory) from a flat python/torch sequence."""
+    values = [float(v) for v in values]
+    return (ctypes.c_float * len(values))(*values)

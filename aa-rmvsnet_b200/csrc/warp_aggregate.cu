@@ -1,0 +1,355 @@
+// Plane-sweep warp + inter-view adaptive aggregation.
+//
+// Reference: models/module.py:6-38 (homo_warping_depthwise), models/drmvsnet.py:27-38 (InterViewAAModule),
+// models/drmvsnet.py:307-319 (per-plane aggregation).  The reference materialises, per plane and view, the warped
+// volume, its squared difference, every omega activation and three GroupNorm passes.  Here one plane is
+//   pass A  cost_stem_kernel   gather S views, (warp - ref)^2 into a shared-memory tile (+1 halo), 3x3 conv 32->4
+//                              -> t0 [S][P][4] (16 B/px/view) + GroupNorm-1 sums
+//   pass B  omega_stats_kernel<2>   t0 -> GN1/ReLU -> 1x1 -> GroupNorm-2 sums          (reads t0 only)
+//   pass C  omega_stats_kernel<3>   ... -> GN2/ReLU -> 1x1 -> GroupNorm-3 sums         (reads t0 only)
+//   pass D  aggregate_kernel   re-gather, omega tail from t0 + the three statistics, sum_v (1 + w_v) c_v, * -1/S
+// so the 5-D cost volume and the per-view 32-channel cost never reach HBM.  Layout: features NHWC fp32 (one pixel
+// = 128 B = one cache line per bilinear tap); 8 lanes x float4 cover one pixel, a warp covers 4 pixels per load.
+#include "common.cuh"
+#include <string.h>
+
+struct StemParams {            // omega.reweight_network.0.0 repacked [tap][cin][cout] + bias; lives in the
+    float w[9 * 32 * 4];       // kernel parameter (constant) bank, so the 1152 FMAs per pixel take their
+    float b[4];                // weight operand straight from c[0][...] with no load instruction
+};
+
+struct OmegaTail {             // the 1x1 layers and GroupNorm affines of omega (models/drmvsnet.py:31-34)
+    float g1[4], b1[4];        // reweight_network.0.1   GroupNorm(1, 4)
+    float w1[16], c1[4];       // reweight_network.1.stem.0.0  conv1x1 4->4  (w[o*4+i])
+    float g2[4], b2[4];        // reweight_network.1.stem.0.1
+    float w2[16], c2[4];       // reweight_network.1.stem.1
+    float g3[4], b3[4];        // reweight_network.1.stem.2
+    float w3[4], c3;           // reweight_network.2  conv1x1 4->1
+};
+
+// ------------------------------------------------------------------------------------------------ plain warp
+// The operator seam homo_warping_depthwise(src_fea, src_proj, ref_proj, depth_value): out [P][32].
+__global__ void __launch_bounds__(256) warp_kernel(const float* __restrict__ src, float* __restrict__ out, int H, int W,
+                                                   Cams cams, int view, float depth, int align_corners) {
+    const int chunk = threadIdx.x & 7;
+    const int P = H * W;
+    for (int p = blockIdx.x * 32 + (threadIdx.x >> 3); p < P; p += gridDim.x * 32) {
+        int y = p / W, x = p - y * W;
+        float ix, iy;
+        sweep_position(cams.m[view], (float)x, (float)y, depth, W, H, align_corners != 0, ix, iy);
+        Taps t = make_taps(ix, iy, W, H);
+        st4(out + (size_t)p * 32 + chunk * 4, gather_taps(src, t, chunk));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ pass A
+constexpr int TA_H = 16, TA_W = 32;                     // output tile
+constexpr int TA_HH = TA_H + 2, TA_WW = TA_W + 2;       // with the 3x3 halo
+constexpr int TA_NPOS = TA_HH * TA_WW;                  // 612 positions
+constexpr int TA_THREADS = 128;
+
+// swizzled shared-memory address (floats) of 16-byte chunk j of tile position i: consecutive positions read with
+// the same j land in distinct 16-byte bank groups, so both the gather stores and the conv LDS.128 are conflict-free
+__device__ __forceinline__ int tile_addr(int i, int j) { return i * 32 + ((j ^ (i & 7)) << 2); }
+
+__global__ void __launch_bounds__(TA_THREADS, 2)
+cost_stem_kernel(const float* __restrict__ ref, const float* __restrict__ src, size_t view_stride, int H, int W, int S,
+                 const float* __restrict__ cams, const __grid_constant__ StemParams sp,
+                 const float* __restrict__ depth_values, int d_host, const int* __restrict__ d_dev, int align_corners,
+                 float* __restrict__ t0, double* __restrict__ stats /* [S][3][2] */) {
+    extern __shared__ __align__(16) float tile[];        // TA_NPOS * 32 floats
+    __shared__ double red[2 * (TA_THREADS / 32)];
+    __shared__ float scam[AARMVS_MAX_SRC * 12];
+    for (int i = threadIdx.x; i < S * 12; i += TA_THREADS) scam[i] = cams[i];
+    __syncthreads();
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int chunk = tid & 7, grp = tid >> 3;           // 16 groups of 8 lanes
+    const int tx0 = blockIdx.x * TA_W, ty0 = blockIdx.y * TA_H;
+    const float depth = depth_values[plane_index(d_host, d_dev)];
+    const size_t P = (size_t)H * W;
+
+    for (int v = 0; v < S; ++v) {
+        const float* sv = src + v * view_stride;
+        // ---- phase 1: (warp - ref)^2 for the tile + halo; zero outside the image (the conv's zero padding)
+#pragma unroll 2
+        for (int i = grp; i < TA_NPOS; i += TA_THREADS / 8) {
+            int r = i / TA_WW, c = i - r * TA_WW;
+            int y = ty0 - 1 + r, x = tx0 - 1 + c;
+            float4 cv = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (y >= 0 && y < H && x >= 0 && x < W) {
+                float ix, iy;
+                sweep_position(scam + v * 12, (float)x, (float)y, depth, W, H, align_corners != 0, ix, iy);
+                Taps t = make_taps(ix, iy, W, H);
+                float4 wv = gather_taps(sv, t, chunk);
+                float4 rv = ldg4(ref + ((size_t)y * W + x) * 32 + chunk * 4);
+                float dx = wv.x - rv.x, dy = wv.y - rv.y, dz = wv.z - rv.z, dw = wv.w - rv.w;
+                cv = make_float4(dx * dx, dy * dy, dz * dz, dw * dw);
+            }
+            st4(tile + tile_addr(i, chunk), cv);
+        }
+        __syncthreads();
+        // ---- phase 2: 3x3 conv 32 -> 4 on the tile; this thread: column `lane`, output rows 4*warp .. 4*warp+3.
+        // Sliding window over the 6 input rows: row r feeds output rows r (ky=0), r-1 (ky=1) and r-2 (ky=2), so the
+        // loop body is identical for every r and all 1152 weights are compile-time offsets into the parameter bank.
+        float s = 0.f, ss = 0.f;
+        const int x = tx0 + lane;
+        float a0[4], a1[4] = {0.f, 0.f, 0.f, 0.f}, a2[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+        for (int r = 0; r < 6; ++r) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) a0[k] = sp.b[k];
+#pragma unroll
+            for (int cc = 0; cc < 3; ++cc) {
+                const int i = (warp * 4 + r) * TA_WW + lane + cc;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float4 a = ld4(tile + tile_addr(i, j));
+                    const float* w0 = sp.w + ((0 * 3 + cc) * 32 + j * 4) * 4;
+                    const float* w1 = sp.w + ((1 * 3 + cc) * 32 + j * 4) * 4;
+                    const float* w2 = sp.w + ((2 * 3 + cc) * 32 + j * 4) * 4;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        a0[k] = fmaf(a.x, w0[k], a0[k]); a0[k] = fmaf(a.y, w0[4 + k], a0[k]);
+                        a0[k] = fmaf(a.z, w0[8 + k], a0[k]); a0[k] = fmaf(a.w, w0[12 + k], a0[k]);
+                        a1[k] = fmaf(a.x, w1[k], a1[k]); a1[k] = fmaf(a.y, w1[4 + k], a1[k]);
+                        a1[k] = fmaf(a.z, w1[8 + k], a1[k]); a1[k] = fmaf(a.w, w1[12 + k], a1[k]);
+                        a2[k] = fmaf(a.x, w2[k], a2[k]); a2[k] = fmaf(a.y, w2[4 + k], a2[k]);
+                        a2[k] = fmaf(a.z, w2[8 + k], a2[k]); a2[k] = fmaf(a.w, w2[12 + k], a2[k]);
+                    }
+                }
+            }
+            if (r >= 2) {      // output row r - 2 is complete: write t0 and the GroupNorm-1 partial sums
+                const int y = ty0 + warp * 4 + r - 2;
+                if (y < H && x < W) {
+                    st4(t0 + ((size_t)v * P + (size_t)y * W + x) * 4, make_float4(a2[0], a2[1], a2[2], a2[3]));
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) { s += a2[k]; ss += a2[k] * a2[k]; }
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { a2[k] = a1[k]; a1[k] = a0[k]; }
+        }
+        double dv[2] = {(double)s, (double)ss}, tot[2];
+        block_sum<2, TA_THREADS / 32>(dv, red, tot);      // its barriers also protect the tile for the next view
+        if (tid == 0) {
+            atomicAdd(stats + (v * 3 + 0) * 2 + 0, tot[0]);
+            atomicAdd(stats + (v * 3 + 0) * 2 + 1, tot[1]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ omega tail
+struct OmegaNorm { float m1, r1, m2, r2, m3, r3; };
+
+// a1 = ReLU(GN1(t0));  u = conv1x1(a1)
+__device__ __forceinline__ void omega_u(const OmegaTail& q, const OmegaNorm& n, float4 t, float (&a1)[4], float (&u)[4]) {
+    const float tv[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) a1[k] = fmaxf((tv[k] - n.m1) * n.r1 * q.g1[k] + q.b1[k], 0.f);
+#pragma unroll
+    for (int o = 0; o < 4; ++o) {
+        float s = q.c1[o];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) s = fmaf(q.w1[o * 4 + i], a1[i], s);
+        u[o] = s;
+    }
+}
+// a2 = ReLU(GN2(u));  v = conv1x1(a2)
+__device__ __forceinline__ void omega_v(const OmegaTail& q, const OmegaNorm& n, const float (&u)[4], float (&vv)[4]) {
+    float a2[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) a2[k] = fmaxf((u[k] - n.m2) * n.r2 * q.g2[k] + q.b2[k], 0.f);
+#pragma unroll
+    for (int o = 0; o < 4; ++o) {
+        float s = q.c2[o];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) s = fmaf(q.w2[o * 4 + i], a2[i], s);
+        vv[o] = s;
+    }
+}
+// w = sigmoid(conv1x1(ReLU(GN3(v) + a1)))
+__device__ __forceinline__ float omega_w(const OmegaTail& q, const OmegaNorm& n, const float (&a1)[4], const float (&vv)[4]) {
+    float s = q.c3;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        float r = fmaxf(((vv[k] - n.m3) * n.r3 * q.g3[k] + q.b3[k]) + a1[k], 0.f);
+        s = fmaf(q.w3[k], r, s);
+    }
+    return sigmoidf_acc(s);
+}
+
+// STAGE 2: accumulate sums of u (GroupNorm-2);  STAGE 3: sums of v (GroupNorm-3).  grid = (blocks, S).
+template <int STAGE>
+__global__ void __launch_bounds__(256) omega_stats_kernel(const float* __restrict__ t0, size_t P, const __grid_constant__ OmegaTail q,
+                                                          double* __restrict__ stats) {
+    __shared__ double red[2 * 8];
+    const int v = blockIdx.y;
+    double* st = stats + v * 6;
+    const double cnt = 4.0 * (double)P;
+    OmegaNorm n;
+    gn_mean_rstd(st + 0, cnt, n.m1, n.r1);
+    if (STAGE == 3) gn_mean_rstd(st + 2, cnt, n.m2, n.r2);
+    const float* tv = t0 + (size_t)v * P * 4;
+    float s = 0.f, ss = 0.f;
+    double ds = 0.0, dss = 0.0;
+    int it = 0;
+    for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (size_t)gridDim.x * blockDim.x) {
+        float a1[4], u[4], vv[4];
+        omega_u(q, n, ldg4(tv + p * 4), a1, u);
+        if (STAGE == 2) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { s += u[k]; ss += u[k] * u[k]; }
+        } else {
+            omega_v(q, n, u, vv);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { s += vv[k]; ss += vv[k] * vv[k]; }
+        }
+        if (++it == 8) { ds += s; dss += ss; s = ss = 0.f; it = 0; }   // bound the fp32 partial sums
+    }
+    double dv[2] = {ds + s, dss + ss}, tot[2];
+    block_sum<2, 8>(dv, red, tot);
+    if (threadIdx.x == 0) {
+        atomicAdd(st + (STAGE - 1) * 2 + 0, tot[0]);
+        atomicAdd(st + (STAGE - 1) * 2 + 1, tot[1]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ pass D
+// cost[p][c] = -( sum_v (omega_v(p) + 1) * (warp_v(p)[c] - ref(p)[c])^2 ) / S      (drmvsnet.py:311-319)
+// optional outputs for the operator seam: reweight [S][P].
+__global__ void __launch_bounds__(256)
+aggregate_kernel(const float* __restrict__ ref, const float* __restrict__ src, size_t view_stride, int H, int W, int S,
+                 const float* __restrict__ cams, const __grid_constant__ OmegaTail q,
+                 const float* __restrict__ depth_values, int d_host, const int* __restrict__ d_dev, int align_corners,
+                 const float* __restrict__ t0, const double* __restrict__ stats, float* __restrict__ cost,
+                 float* __restrict__ reweight_out) {
+    __shared__ OmegaNorm norms[AARMVS_MAX_SRC];
+    __shared__ float scam[AARMVS_MAX_SRC * 12];
+    for (int i = threadIdx.x; i < S * 12; i += blockDim.x) scam[i] = cams[i];
+    const size_t P = (size_t)H * W;
+    if (threadIdx.x < S) {
+        OmegaNorm n;
+        const double cnt = 4.0 * (double)P;
+        gn_mean_rstd(stats + threadIdx.x * 6 + 0, cnt, n.m1, n.r1);
+        gn_mean_rstd(stats + threadIdx.x * 6 + 2, cnt, n.m2, n.r2);
+        gn_mean_rstd(stats + threadIdx.x * 6 + 4, cnt, n.m3, n.r3);
+        norms[threadIdx.x] = n;
+    }
+    __syncthreads();
+    const int chunk = threadIdx.x & 7;
+    const float depth = depth_values[plane_index(d_host, d_dev)];
+    const float inv_s_den = (float)S;
+    for (size_t p = (size_t)blockIdx.x * 32 + (threadIdx.x >> 3); p < P; p += (size_t)gridDim.x * 32) {
+        const int y = (int)(p / W), x = (int)(p - (size_t)y * W);
+        const float4 rv = ldg4(ref + p * 32 + chunk * 4);
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int v0 = 0; v0 < S; v0 += 8) {
+            // lane `chunk` of the 8-lane group evaluates the reweight of view v0 + chunk, then it is broadcast
+            float wmine = 0.f;
+            if (v0 + chunk < S) {
+                const int v = v0 + chunk;
+                float a1[4], u[4], vv[4];
+                omega_u(q, norms[v], ldg4(t0 + ((size_t)v * P + p) * 4), a1, u);
+                omega_v(q, norms[v], u, vv);
+                wmine = omega_w(q, norms[v], a1, vv);
+                if (reweight_out) reweight_out[(size_t)v * P + p] = wmine;
+            }
+            const int nv = min(8, S - v0);
+            for (int k = 0; k < nv; ++k) {
+                const int v = v0 + k;
+                const float wv = __shfl_sync(0xffffffffu, wmine, k, 8) + 1.0f;
+                float ix, iy;
+                sweep_position(scam + v * 12, (float)x, (float)y, depth, W, H, align_corners != 0, ix, iy);
+                Taps t = make_taps(ix, iy, W, H);
+                float4 g = gather_taps(src + v * view_stride, t, chunk);
+                float dx = g.x - rv.x, dy = g.y - rv.y, dz = g.z - rv.z, dw = g.w - rv.w;
+                float cx = __fmul_rn(dx, dx), cy = __fmul_rn(dy, dy), cz = __fmul_rn(dz, dz), cw = __fmul_rn(dw, dw);
+                if (v == 0) {
+                    acc = make_float4(__fmul_rn(wv, cx), __fmul_rn(wv, cy), __fmul_rn(wv, cz), __fmul_rn(wv, cw));
+                } else {   // reference adds the rounded product (two ATen ops): keep mul and add separate
+                    acc.x = __fadd_rn(acc.x, __fmul_rn(wv, cx)); acc.y = __fadd_rn(acc.y, __fmul_rn(wv, cy));
+                    acc.z = __fadd_rn(acc.z, __fmul_rn(wv, cz)); acc.w = __fadd_rn(acc.w, __fmul_rn(wv, cw));
+                }
+            }
+        }
+        float4 o = make_float4(-__fdiv_rn(acc.x, inv_s_den), -__fdiv_rn(acc.y, inv_s_den), -__fdiv_rn(acc.z, inv_s_den),
+                               -__fdiv_rn(acc.w, inv_s_den));
+        st4(cost + p * 32 + chunk * 4, o);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ C ABI
+#include "../../include/aarmvs.h"
+
+static int fill_cams(Cams& c, const float* cams_host, int S) {
+    if (!cams_host || S < 1 || S > AARMVS_MAX_SRC) return AARMVS_ERR_ARG;
+    for (int v = 0; v < S; ++v)
+        for (int k = 0; k < 12; ++k) c.m[v][k] = cams_host[v * 12 + k];
+    return AARMVS_OK;
+}
+
+extern "C" int aarmvs_warp(const float* src, float* out, int H, int W, const float* cam_host, float depth,
+                           int align_corners, void* stream) {
+    AARMVS_CHECK_ARG(src && out && H > 0 && W > 0);
+    Cams c;
+    if (int e = fill_cams(c, cam_host, 1)) return e;
+    int P = H * W;
+    int blocks = min((P + 31) / 32, 148 * 16);
+    warp_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, out, H, W, c, 0, depth, align_corners);
+    AARMVS_LAUNCH_RESULT();
+}
+
+extern "C" size_t aarmvs_omega_stats_bytes(int S) { return (size_t)S * 6 * sizeof(double); }
+
+extern "C" int aarmvs_cost_stem(const float* ref, const float* src, size_t view_stride, int H, int W, int S,
+                                const float* cams, const float* stem_w, const float* stem_b,
+                                const float* depth_values, int d_host, const int* d_dev, int align_corners, float* t0,
+                                double* stats, void* stream) {
+    AARMVS_CHECK_ARG(ref && src && t0 && stats && stem_w && stem_b && depth_values && cams && H > 0 && W > 0);
+    AARMVS_CHECK_ARG(S >= 1 && S <= AARMVS_MAX_SRC);
+    StemParams sp;
+    for (int i = 0; i < 9 * 32 * 4; ++i) sp.w[i] = stem_w[i];
+    for (int i = 0; i < 4; ++i) sp.b[i] = stem_b[i];
+    static bool attr_set = false;
+    const int smem = TA_NPOS * 32 * sizeof(float);
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(cost_stem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return (int)e;
+        attr_set = true;
+    }
+    dim3 grid((W + TA_W - 1) / TA_W, (H + TA_H - 1) / TA_H);
+    cost_stem_kernel<<<grid, TA_THREADS, smem, (cudaStream_t)stream>>>(ref, src, view_stride, H, W, S, cams, sp, depth_values,
+                                                                      d_host, d_dev, align_corners, t0, stats);
+    AARMVS_LAUNCH_RESULT();
+}
+
+static void fill_tail(OmegaTail& q, const float* t) { memcpy(&q, t, sizeof(OmegaTail)); }
+
+extern "C" int aarmvs_omega_tail_floats(void) { return (int)(sizeof(OmegaTail) / sizeof(float)); }
+
+extern "C" int aarmvs_omega_stats(int stage, const float* t0, int H, int W, int S, const float* tail_host, double* stats,
+                                  void* stream) {
+    AARMVS_CHECK_ARG(t0 && stats && tail_host && (stage == 2 || stage == 3) && S >= 1 && S <= AARMVS_MAX_SRC);
+    OmegaTail q;
+    fill_tail(q, tail_host);
+    size_t P = (size_t)H * W;
+    dim3 grid((unsigned)min((P + 255) / 256, (size_t)148 * 4), S);
+    if (stage == 2) omega_stats_kernel<2><<<grid, 256, 0, (cudaStream_t)stream>>>(t0, P, q, stats);
+    else omega_stats_kernel<3><<<grid, 256, 0, (cudaStream_t)stream>>>(t0, P, q, stats);
+    AARMVS_LAUNCH_RESULT();
+}
+
+extern "C" int aarmvs_aggregate(const float* ref, const float* src, size_t view_stride, int H, int W, int S,
+                                const float* cams, const float* tail_host, const float* depth_values, int d_host,
+                                const int* d_dev, int align_corners, const float* t0, const double* stats, float* cost,
+                                float* reweight_out, void* stream) {
+    AARMVS_CHECK_ARG(ref && src && t0 && stats && cost && tail_host && depth_values && cams && H > 0 && W > 0);
+    AARMVS_CHECK_ARG(S >= 1 && S <= AARMVS_MAX_SRC);
+    OmegaTail q;
+    fill_tail(q, tail_host);
+    size_t P = (size_t)H * W;
+    int blocks = (int)min((P + 31) / 32, (size_t)148 * 16);
+    aggregate_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(ref, src, view_stride, H, W, S, cams, q, depth_values, d_host,
+                                                              d_dev, align_corners, t0, stats, cost, reweight_out);
+    AARMVS_LAUNCH_RESULT();
+}

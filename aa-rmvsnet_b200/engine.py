@@ -1,0 +1,288 @@
+"""Host-side driver of the sm_100a kernels: owns the device workspace (NHWC fp32, sized once per shape), the packed
+weights, and the per-plane kernel chain, which is captured once into a CUDA graph and replayed for every depth
+plane (the plane index lives in device memory).  PyTorch is used for device memory and streams only.
+
+Per view (FeatNet, models/drmvsnet.py:41-63):   16 launches.
+Per depth plane (models/drmvsnet.py:306-334):   cost_stem, omega_stats x2, aggregate, cell0, cell1, cell2, deconv_0,
+                                                cell3, deconv_1, cell4, head_wta, next_plane = 13 launches, 0 host syncs
+                                                (the reference issues ~526 ATen ops and 12 host syncs).
+"""
+import ctypes
+
+import torch
+
+from . import capi, pack
+
+_HID = (16, 16, 16, 16, 8)            # hidden channels of the five cells (models/drmvsnet.py:242)
+_SCALE = (1, 2, 4, 2, 1)              # their resolution divisors (models/drmvsnet.py:91)
+
+
+def _ptr(t, offset_elems=0):
+    return ctypes.c_void_p(t.data_ptr() + offset_elems * t.element_size())
+
+
+def _src(t, channels, mode=capi.SRC_PLAIN, *, planes=0, sums=None, gn=None, groups=0, count=0.0, pp_stride=0, pp_phase=0):
+    s = capi.ConvSrc()
+    s.ptr = t.data_ptr()
+    s.channels, s.mode, s.planes = channels, mode, planes
+    s.gn_groups = groups
+    s.gn_sums = sums.data_ptr() if sums is not None else None
+    s.gn_weight = gn[0].data_ptr() if gn is not None else None
+    s.gn_bias = gn[1].data_ptr() if gn is not None else None
+    s.gn_count = float(count)
+    s.pp_stride, s.pp_phase = pp_stride, pp_phase
+    return s
+
+
+def _src_array(*srcs):
+    arr = (capi.ConvSrc * len(srcs))(*srcs)
+    return arr
+
+
+class Engine:
+    """Runs EMVSNet.forward's arithmetic for one model instance (weights are re-packed when they change)."""
+
+    def __init__(self, module, align_corners=False, use_graph=True):
+        self.module = module
+        self.align_corners = bool(align_corners)     # grid_sample default under torch >= 1.3 is False
+        self.use_graph = use_graph
+        self.lib = capi.load()
+        self._wkey = None
+        self._ws = {}
+
+    # ------------------------------------------------------------------------------------------ weights
+    def _weights(self, device):
+        params = list(self.module.parameters())
+        key = (str(device),) + tuple((p.data_ptr(), p._version) for p in params)
+        if key == self._wkey:
+            return self.w
+        sd = {k: v.detach().to(device=device, dtype=torch.float32) for k, v in self.module.state_dict().items()}
+        w = {}
+
+        def convgn(name, prefix, cin_pad=None):
+            w[name + ".w"] = pack.conv_taps(sd[prefix + ".0.weight"], cin_pad)
+            w[name + ".b"] = sd[prefix + ".0.bias"].contiguous()
+            w[name + ".gn"] = (sd[prefix + ".1.weight"].contiguous(), sd[prefix + ".1.bias"].contiguous())
+
+        convgn("init0", "feature.init_conv.0", cin_pad=4)
+        convgn("init1", "feature.init_conv.1")
+        convgn("conv0", "feature.conv0")
+        convgn("conv1", "feature.conv1")
+        convgn("conv2", "feature.conv2")
+        for l in range(3):
+            dc = f"feature.intraAA.deformconv{l}"
+            pm_w = torch.cat([sd[dc + ".0.p_conv.weight"], sd[dc + ".0.m_conv.weight"]], 0)
+            pm_b = torch.cat([sd[dc + ".0.p_conv.bias"], sd[dc + ".0.m_conv.bias"]], 0)
+            w[f"pm{l}.w"] = pack.conv_taps(pm_w, cout_pad=32)
+            w[f"pm{l}.b"] = pack.pad_vec(pm_b, 32)
+            w[f"dc{l}.w"] = pack.conv_taps(sd[dc + ".0.conv.weight"])
+            w[f"dc{l}.b"] = sd[dc + ".0.conv.bias"].contiguous()
+            w[f"dc{l}.gn"] = (sd[dc + ".1.weight"].contiguous(), sd[dc + ".1.bias"].contiguous())
+            convgn(f"head{l}", f"feature.intraAA.conv{l}")
+        cr = "cost_regularization"
+        for i in range(5):
+            w[f"cell{i}.w"], w[f"cell{i}.b"] = pack.lstm_gates(sd[f"{cr}.cell_list.{i}.conv.weight"],
+                                                                sd[f"{cr}.cell_list.{i}.conv.bias"])
+        for i in range(2):
+            w[f"deconv{i}.w"] = pack.deconv_taps(sd[f"{cr}.deconv_{i}.conv.weight"])
+            w[f"deconv{i}.b"] = sd[f"{cr}.deconv_{i}.conv.bias"].contiguous()
+            w[f"deconv{i}.gn"] = (sd[f"{cr}.deconv_{i}.gn.weight"].contiguous(), sd[f"{cr}.deconv_{i}.gn.bias"].contiguous())
+        # small layers whose parameters are baked into kernel parameter banks (host arrays)
+        om = "omega.reweight_network"
+        w["stem.w_host"] = capi.host_floats(pack.conv_taps(sd[om + ".0.0.weight"]).reshape(-1).cpu().tolist())
+        w["stem.b_host"] = capi.host_floats(sd[om + ".0.0.bias"].cpu().tolist())
+        tail = pack.omega_tail(sd)
+        assert tail.numel() == self.lib.aarmvs_omega_tail_floats()
+        w["tail_host"] = capi.host_floats(tail.tolist())
+        w["head.w_host"] = capi.host_floats(pack.conv_taps(sd[cr + ".conv_0.weight"]).reshape(-1).cpu().tolist())
+        w["head.b_host"] = capi.host_floats(sd[cr + ".conv_0.bias"].cpu().tolist())
+        self.w, self._wkey = w, key
+        self._ws.clear()                 # graphs bake host-side parameters: drop them with the old weights
+        return w
+
+    # ------------------------------------------------------------------------------------------ workspace
+    def _workspace(self, H, W, N, D, device, keep_cost):
+        key = (H, W, N, D, str(device), keep_cost)
+        ws = self._ws.get(key)
+        if ws is not None:
+            return ws
+        if H % 4 or W % 4:
+            raise RuntimeError(f"feature height and width must be multiples of 4, got {H}x{W} (models/drmvsnet.py:51-52, 148-160)")
+        if not 2 <= N <= 16:
+            raise RuntimeError(f"2..16 views supported, got {N}")
+        f32 = dict(device=device, dtype=torch.float32)
+        P, S = H * W, N - 1
+        ws = {"H": H, "W": W, "N": N, "D": D, "graph": None, "warm": False}
+        ws["feat"] = torch.empty(N, P, 32, **f32)
+        # FeatNet scratch (reused for every view)
+        ws["a1"] = torch.empty(P, 8, **f32)
+        ws["a2"] = torch.empty(P, 16, **f32)
+        for l, s in enumerate((1, 2, 4)):
+            pl = P // (s * s)
+            ws[f"x{l}"] = torch.empty(pl, 32, **f32)
+            ws[f"om{l}"] = torch.empty(pl, 32, **f32)
+            ws[f"dc{l}"] = torch.empty(pl, 32, **f32)
+            ws[f"m{l}"] = torch.empty(pl, 16 if l == 0 else 8, **f32)
+        ws["fsums"] = torch.zeros(64, device=device, dtype=torch.float64)
+        # plane sweep
+        ws["t0"] = torch.empty(S, P, 4, **f32)
+        ws["cost"] = torch.empty(P, 32, **f32)
+        ws["h"] = [torch.empty(2, P // (s * s), ch, **f32) for ch, s in zip(_HID, _SCALE)]
+        ws["c"] = [torch.empty(P // (s * s), ch, **f32) for ch, s in zip(_HID, _SCALE)]
+        ws["up0"] = torch.empty(P // 4, 16, **f32)
+        ws["up1"] = torch.empty(P, 16, **f32)
+        ws["psums"] = torch.zeros(S * 6 + 8, device=device, dtype=torch.float64)
+        ws["plane"] = torch.zeros(1, device=device, dtype=torch.int32)
+        ws["cams"] = torch.empty(S, 12, **f32)
+        ws["depths"] = torch.empty(D, **f32)
+        ws["max_prob"] = torch.empty(P, **f32)
+        ws["exp_sum"] = torch.empty(P, **f32)
+        ws["depth"] = torch.empty(P, **f32)
+        ws["conf"] = torch.empty(P, **f32)
+        ws["index"] = torch.empty(P, device=device, dtype=torch.int32)
+        ws["cost_volume"] = torch.empty(D, P, **f32) if keep_cost else None
+        self._ws[key] = ws
+        return ws
+
+    # ------------------------------------------------------------------------------------------ FeatNet
+    def feature_map(self, img, out, ws, w, stream):
+        """img: [3,H,W] fp32 contiguous (NCHW plane order); out: [P,32] NHWC feature map."""
+        lib, H, W = self.lib, ws["H"], ws["W"]
+        sums = ws["fsums"]
+        sums.zero_()
+        off = {"init0": 0, "init1": 2, "conv0": 6, "conv1": 14, "conv2": 22, "dc0": 30, "dc1": 38, "dc2": 46,
+               "head0": 54, "head1": 58, "head2": 60}
+
+        def sl(name):
+            return sums[off[name]:]
+
+        def conv(name, srcs, hin, win, cin, cout, k, stride, dst, stored, stat):
+            arr = _src_array(*srcs)
+            capi.check(lib.aarmvs_conv2d(arr, len(srcs), hin, win, cin, cout, k, stride, _ptr(w[name + ".w"]),
+                                         _ptr(w[name + ".b"]), _ptr(dst), stored,
+                                         _ptr(sl(stat)) if stat else None, stream), "aarmvs_conv2d:" + name)
+
+        def gn(t, ch, name, wname, npix):
+            groups = max(1, ch // 8)
+            return _src(t, ch, capi.SRC_GN_RELU, sums=sl(name), gn=w[wname + ".gn"], groups=groups,
+                        count=(ch // groups) * npix)
+
+        P = H * W
+        conv("init0", [_src(img, 4, capi.SRC_NCHW, planes=3)], H, W, 4, 8, 3, 1, ws["a1"], 8, "init0")
+        conv("init1", [gn(ws["a1"], 8, "init0", "init0", P)], H, W, 8, 16, 3, 1, ws["a2"], 16, "init1")
+        conv("conv0", [gn(ws["a2"], 16, "init1", "init1", P)], H, W, 16, 32, 3, 1, ws["x0"], 32, "conv0")
+        conv("conv1", [gn(ws["x0"], 32, "conv0", "conv0", P)], H, W, 32, 32, 3, 2, ws["x1"], 32, "conv1")
+        conv("conv2", [gn(ws["x1"], 32, "conv1", "conv1", P // 4)], H // 2, W // 2, 32, 32, 3, 2, ws["x2"], 32, "conv2")
+        for l, s in enumerate((1, 2, 4)):
+            hl, wl, pl = H // s, W // s, P // (s * s)
+            x = gn(ws[f"x{l}"], 32, f"conv{l}", f"conv{l}", pl)
+            conv(f"pm{l}", [x], hl, wl, 32, 32, 3, 1, ws[f"om{l}"], 32, None)
+            capi.check(lib.aarmvs_deform_conv(ctypes.byref(x), hl, wl, _ptr(ws[f"om{l}"]), _ptr(w[f"dc{l}.w"]),
+                                              _ptr(w[f"dc{l}.b"]), _ptr(ws[f"dc{l}"]), _ptr(sl(f"dc{l}")), stream),
+                       "aarmvs_deform_conv")
+            ch = 16 if l == 0 else 8
+            conv(f"head{l}", [gn(ws[f"dc{l}"], 32, f"dc{l}", f"dc{l}", pl)], hl, wl, 32, ch, 1, 1, ws[f"m{l}"], ch,
+                 f"head{l}")
+        g0, g1, g2 = w["head0.gn"], w["head1.gn"], w["head2.gn"]
+        capi.check(lib.aarmvs_feat_assemble(_ptr(ws["m0"]), _ptr(ws["m1"]), _ptr(ws["m2"]), _ptr(sl("head0")),
+                                            _ptr(sl("head1")), _ptr(sl("head2")), _ptr(g0[0]), _ptr(g0[1]),
+                                            _ptr(g1[0]), _ptr(g1[1]), _ptr(g2[0]), _ptr(g2[1]), H, W, _ptr(out), stream),
+                   "aarmvs_feat_assemble")
+
+    # ------------------------------------------------------------------------------------------ one plane
+    def _plane(self, ws, w, stream):
+        """Enqueue the kernel chain of one depth plane; the plane index is read from ws['plane'] on the device."""
+        lib, H, W, N = self.lib, ws["H"], ws["W"], ws["N"]
+        P, S = H * W, N - 1
+        feat, dptr, ac = ws["feat"], _ptr(ws["plane"]), int(self.align_corners)
+        ref, src = _ptr(feat), _ptr(feat, P * 32)
+        ps = ws["psums"]
+        capi.check(lib.aarmvs_cost_stem(ref, src, P * 32, H, W, S, _ptr(ws["cams"]), w["stem.w_host"], w["stem.b_host"],
+                                        _ptr(ws["depths"]), 0, dptr, ac, _ptr(ws["t0"]), _ptr(ps), stream), "aarmvs_cost_stem")
+        for stage in (2, 3):
+            capi.check(lib.aarmvs_omega_stats(stage, _ptr(ws["t0"]), H, W, S, w["tail_host"], _ptr(ps), stream),
+                       "aarmvs_omega_stats")
+        capi.check(lib.aarmvs_aggregate(ref, src, P * 32, H, W, S, _ptr(ws["cams"]), w["tail_host"], _ptr(ws["depths"]), 0,
+                                        dptr, ac, _ptr(ws["t0"]), _ptr(ps), _ptr(ws["cost"]), None, stream),
+                   "aarmvs_aggregate")
+        h, c = ws["h"], ws["c"]
+
+        def hsrc(i, mode=capi.SRC_PLAIN):          # h_i of the CURRENT plane (ping-pong half d & 1)
+            return _src(h[i], _HID[i], mode, pp_stride=h[i][0].numel(), pp_phase=0)
+
+        def cell(i, srcs, hh, ww, cin):
+            arr = _src_array(*srcs)
+            capi.check(lib.aarmvs_convlstm_cell(arr, len(srcs), hh, ww, cin, _HID[i], _ptr(w[f"cell{i}.w"]),
+                                                _ptr(w[f"cell{i}.b"]), _ptr(h[i]), _ptr(c[i]), 0, dptr, stream),
+                       f"aarmvs_convlstm_cell[{i}]")
+
+        def deconv(i, src, hin, win, dst, sums):
+            capi.check(lib.aarmvs_deconv2x(ctypes.byref(src), hin, win, _ptr(w[f"deconv{i}.w"]), _ptr(w[f"deconv{i}.b"]),
+                                           _ptr(dst), _ptr(sums), 0, dptr, stream), f"aarmvs_deconv2x[{i}]")
+
+        H2, W2, H4, W4 = H // 2, W // 2, H // 4, W // 4
+        s_up0, s_up1 = ps[S * 6:], ps[S * 6 + 4:]
+        cell(0, [_src(ws["cost"], 32)], H, W, 48)
+        cell(1, [hsrc(0, capi.SRC_MAXPOOL2)], H2, W2, 32)
+        cell(2, [hsrc(1, capi.SRC_MAXPOOL2)], H4, W4, 32)
+        deconv(0, hsrc(2), H4, W4, ws["up0"], s_up0)
+        up0 = _src(ws["up0"], 16, capi.SRC_GN_RELU, sums=s_up0, gn=w["deconv0.gn"], groups=2, count=8 * (P // 4))
+        cell(3, [up0, hsrc(1)], H2, W2, 48)
+        deconv(1, hsrc(3), H2, W2, ws["up1"], s_up1)
+        up1 = _src(ws["up1"], 16, capi.SRC_GN_RELU, sums=s_up1, gn=w["deconv1.gn"], groups=2, count=8 * P)
+        cell(4, [up1, hsrc(0)], H, W, 40)
+        h4 = hsrc(4)
+        cv = ws["cost_volume"]
+        capi.check(lib.aarmvs_head_wta(ctypes.byref(h4), H, W, w["head.w_host"], w["head.b_host"], _ptr(ws["depths"]),
+                                       ws["D"], 0, dptr, _ptr(ws["max_prob"]), _ptr(ws["depth"]), _ptr(ws["exp_sum"]),
+                                       _ptr(ws["index"]), _ptr(ws["conf"]), _ptr(cv) if cv is not None else None, stream),
+                   "aarmvs_head_wta")
+        capi.check(lib.aarmvs_next_plane(dptr, _ptr(ps), ps.numel(), stream), "aarmvs_next_plane")
+
+    # ------------------------------------------------------------------------------------------ one depth map
+    @staticmethod
+    def relative_cameras(proj_matrices):
+        """rot | trans of src_proj @ inverse(ref_proj) per source view (models/module.py:16-18), evaluated on the host
+        with the same torch ops as the reference so the fp32 values are the reference's.  [N,4,4] -> [N-1,12]."""
+        pm = proj_matrices.detach().to("cpu", torch.float32)
+        ref = pm[0:1]
+        proj = torch.matmul(pm[1:], torch.inverse(ref))
+        return torch.cat([proj[:, :3, :3].reshape(-1, 9), proj[:, :3, 3]], 1).contiguous()
+
+    def depth_map(self, imgs, proj_matrices, depth_values, keep_cost=False):
+        """imgs [N,3,H,W], proj_matrices [N,4,4], depth_values [D] -> dict of [H,W] maps (views of the workspace)."""
+        device = imgs.device
+        if device.type != "cuda":
+            raise RuntimeError("aarmvsnet_b200 has no CPU path: inputs must live on a CUDA device")
+        N, _, H, W = imgs.shape
+        D = depth_values.shape[0]
+        w = self._weights(device)
+        ws = self._workspace(H, W, N, D, device, keep_cost)
+        stream = ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+        imgs = imgs.to(torch.float32).contiguous()
+        for v in range(N):
+            self.feature_map(imgs[v], ws["feat"][v], ws, w, stream)
+        ws["cams"].copy_(self.relative_cameras(proj_matrices), non_blocking=True)
+        ws["depths"].copy_(depth_values.to(torch.float32), non_blocking=True)
+        ws["plane"].zero_()
+        ws["psums"].zero_()
+        start = 0
+        if self.use_graph and ws["graph"] is None:
+            self._plane(ws, w, stream)            # plane 0 eagerly: also sets the kernels' launch attributes
+            start = 1
+            torch.cuda.synchronize(device)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                cap = ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+                self._plane(ws, w, cap)
+            ws["graph"] = g
+        for _ in range(start, D):
+            if self.use_graph:
+                ws["graph"].replay()
+            else:
+                self._plane(ws, w, stream)
+        out = {"depth": ws["depth"].view(H, W), "photometric_confidence": ws["conf"].view(H, W),
+               "index": ws["index"].view(H, W)}
+        if keep_cost:
+            out["cost_reg"] = ws["cost_volume"].view(D, H, W)
+        return out

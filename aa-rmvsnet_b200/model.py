@@ -1,0 +1,143 @@
+"""Drop-in mirror of the reference's model API for the per-depth-plane cost-volume path.
+
+`EMVSNet` keeps the reference's constructor, `forward(imgs, proj_matrices, depth_values)` signature, output keys
+and parameter names (models/drmvsnet.py:234-345), so the shipped checkpoints load with strict=True; the arithmetic
+runs in the sm_100a kernels behind include/aarmvs.h.  The submodules below only HOLD parameters under the
+reference's names; they are never called layer by layer.
+
+Differences from the reference, all documented in DESIGN.md:
+  * the evidential head (evidential/models.py) is out of scope: it has no weights in the shipped checkpoints and
+    raises for D != 32, so `evidential_prediction` is None;
+  * no `.cuda()` calls are hard-coded: the module follows its inputs' device, and raises if that is not CUDA;
+  * the test-phase output has an extra key "index" (winning plane per pixel, int32).
+"""
+import torch
+import torch.nn as nn
+
+from .engine import Engine
+
+
+def _conv_gn(cin, cout, k, stride=1):
+    # parameter names "<prefix>.0.{weight,bias}" (conv) and "<prefix>.1.{weight,bias}" (GroupNorm) as produced by
+    # the reference's convgnrelu (models/module.py:98-103); groups = max(1, cout / 8)
+    return nn.Sequential(nn.Conv2d(cin, cout, k, stride=stride, padding=(k - 1) // 2),
+                         nn.GroupNorm(int(max(1, cout / 8)), cout))
+
+
+class DeformConv2d(nn.Module):
+    """Parameters of the modulated deformable conv (models/module.py:105-126): conv (k3, applied to the 9 gathered
+    taps), p_conv (18 offsets), m_conv (9 modulation logits); p_conv / m_conv start at zero like the reference."""
+
+    def __init__(self, inc=32, outc=32):
+        super().__init__()
+        self.conv = nn.Conv2d(inc, outc, 3, stride=3, bias=True)
+        self.p_conv = nn.Conv2d(inc, 18, 3, padding=1)
+        self.m_conv = nn.Conv2d(inc, 9, 3, padding=1)
+        nn.init.constant_(self.p_conv.weight, 0)
+        nn.init.constant_(self.m_conv.weight, 0)
+
+
+class IntraViewAAModule(nn.Module):
+    """models/drmvsnet.py:7-16."""
+
+    def __init__(self):
+        super().__init__()
+        for l, ch in enumerate((16, 8, 8)):
+            setattr(self, f"deformconv{l}", nn.Sequential(DeformConv2d(32, 32), nn.GroupNorm(4, 32)))
+            setattr(self, f"conv{l}", _conv_gn(32, ch, 1))
+
+
+class FeatNet(nn.Module):
+    """models/drmvsnet.py:41-53."""
+
+    def __init__(self):
+        super().__init__()
+        self.init_conv = nn.Sequential(_conv_gn(3, 8, 3), _conv_gn(8, 16, 3))
+        self.conv0 = _conv_gn(16, 32, 3)
+        self.conv1 = _conv_gn(32, 32, 3, stride=2)
+        self.conv2 = _conv_gn(32, 32, 3, stride=2)
+        self.intraAA = IntraViewAAModule()
+
+
+class _ResBlockParams(nn.Module):
+    def __init__(self, ch):
+        super().__init__()
+        self.stem = nn.Sequential(_conv_gn(ch, ch, 1), nn.Conv2d(ch, ch, 1), nn.GroupNorm(int(max(1, ch / 8)), ch))
+
+
+class InterViewAAModule(nn.Module):
+    """models/drmvsnet.py:27-35 (omega)."""
+
+    def __init__(self, in_channels=32):
+        super().__init__()
+        self.reweight_network = nn.Sequential(_conv_gn(in_channels, 4, 3), _ResBlockParams(4), nn.Conv2d(4, 1, 1))
+
+
+class ConvLSTMCell(nn.Module):
+    """models/module.py:40-74."""
+
+    def __init__(self, input_dim, hidden_dim):
+        super().__init__()
+        self.input_dim, self.hidden_dim = input_dim, hidden_dim
+        self.conv = nn.Conv2d(input_dim + hidden_dim, 4 * hidden_dim, 3, padding=1)
+
+
+class _DeconvGnParams(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.conv = nn.ConvTranspose2d(16, 16, 3, stride=2, padding=1, output_padding=1)
+        self.gn = nn.GroupNorm(2, 16)
+
+
+class UNetConvLSTM(nn.Module):
+    """models/drmvsnet.py:66-117."""
+
+    def __init__(self, input_dim=(32, 16, 16, 32, 32), hidden_dim=(16, 16, 16, 16, 8)):
+        super().__init__()
+        self.cell_list = nn.ModuleList([ConvLSTMCell(i, h) for i, h in zip(input_dim, hidden_dim)])
+        self.deconv_0 = _DeconvGnParams()
+        self.deconv_1 = _DeconvGnParams()
+        self.conv_0 = nn.Conv2d(8, 1, 3, 1, padding=1)
+
+
+class EMVSNet(nn.Module):
+    """Same constructor as models/drmvsnet.py:235.  `disparity_level` only parameterised the evidential head and is
+    accepted and ignored; `max_h * image_scale` x `max_w * image_scale` must equal the tensor size in the reference
+    (it sizes the zero hidden state, drmvsnet.py:239) -- here the state is sized from the input, and a mismatch with
+    a non-default max_h/max_w raises the same way the reference's torch.cat would."""
+
+    def __init__(self, disparity_level=32, image_scale=0.25, max_h=960, max_w=480, return_depth=False,
+                 align_corners=False, use_graph=True, strict_size=False):
+        super().__init__()
+        self.feature = FeatNet()
+        self.cost_regularization = UNetConvLSTM()
+        self.omega = InterViewAAModule(32)
+        self.return_depth = return_depth
+        self.input_size = (int(max_h * image_scale), int(max_w * image_scale))
+        self.strict_size = strict_size
+        self._engine = Engine(self, align_corners=align_corners, use_graph=use_graph)
+
+    def forward(self, imgs, proj_matrices, depth_values):
+        if imgs.dim() != 5 or imgs.shape[2] != 3:
+            raise RuntimeError(f"imgs must be [B,N,3,H,W], got {tuple(imgs.shape)}")
+        B, N, _, H, W = imgs.shape
+        if proj_matrices.shape[:2] != (B, N) or tuple(proj_matrices.shape[2:]) != (4, 4):
+            raise AssertionError("Different number of images and projection matrices")     # drmvsnet.py:258
+        if depth_values.dim() != 2 or depth_values.shape[0] != B:
+            raise RuntimeError(f"depth_values must be [B,D], got {tuple(depth_values.shape)}")
+        if self.strict_size and (H, W) != self.input_size:
+            raise RuntimeError(f"input {H}x{W} does not match max_h*image_scale x max_w*image_scale = {self.input_size}")
+        keep_cost = not self.return_depth
+        outs = []
+        with torch.no_grad():
+            for b in range(B):
+                o = self._engine.depth_map(imgs[b], proj_matrices[b], depth_values[b], keep_cost=keep_cost)
+                outs.append({k: v.clone() for k, v in o.items()})
+        if self.return_depth:        # test phase (drmvsnet.py:299-345)
+            return {"depth": torch.stack([o["depth"] for o in outs]),
+                    "photometric_confidence": torch.stack([o["photometric_confidence"] for o in outs]),
+                    "index": torch.stack([o["index"] for o in outs]),
+                    "evidential_prediction": None}
+        # training phase (drmvsnet.py:289-295): softmax over the D regularised cost maps
+        prob_volume = torch.softmax(torch.stack([o["cost_reg"] for o in outs]), dim=1)
+        return prob_volume, None, None

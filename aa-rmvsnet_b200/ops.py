@@ -1,0 +1,127 @@
+"""Operator seams with the reference's call signatures (NCHW tensors in and out), each running the CUDA kernels.
+
+These are the individual Python call sites a maintainer could hook: `homo_warping_depthwise`
+(models/module.py:6), `ConvLSTMCell.forward` (module.py:76), `FeatNet.forward` (drmvsnet.py:56), the per-plane
+aggregation (drmvsnet.py:307-318).  The fused forward in engine.py does not go through them; they exist so the
+kernels can be checked one at a time against the oracle.  Layout conversion NCHW <-> NHWC happens here.
+"""
+import ctypes
+
+import torch
+
+from . import capi
+from .engine import Engine, _ptr, _src, _src_array
+
+
+def _nhwc(x):          # [C,H,W] -> [H*W, C] contiguous
+    return x.permute(1, 2, 0).reshape(-1, x.shape[0]).contiguous()
+
+
+def _nchw(x, h, w):    # [H*W, C] -> [C,H,W]
+    return x.view(h, w, -1).permute(2, 0, 1).contiguous()
+
+
+def _stream(device):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _need_cuda(t):
+    if t.device.type != "cuda":
+        raise RuntimeError("aarmvsnet_b200 has no CPU path: tensors must live on a CUDA device")
+
+
+def homo_warping_depthwise(src_fea, src_proj, ref_proj, depth_value, align_corners=False):
+    """models/module.py:6-38.  src_fea [B,32,H,W], src_proj/ref_proj [B,4,4], depth_value [B] -> [B,32,H,W]."""
+    _need_cuda(src_fea)
+    lib = capi.load()
+    B, C, H, W = src_fea.shape
+    if C != 32:
+        raise RuntimeError("the warp kernel is specialised for the 32-channel feature maps of FeatNet")
+    out = torch.empty_like(src_fea)
+    for b in range(B):
+        cam = Engine.relative_cameras(torch.stack([ref_proj[b], src_proj[b]]))[0]
+        src = _nhwc(src_fea[b].float())
+        dst = torch.empty_like(src)
+        capi.check(lib.aarmvs_warp(_ptr(src), _ptr(dst), H, W, capi.host_floats(cam.tolist()), float(depth_value[b]),
+                                   int(align_corners), _stream(src.device)), "aarmvs_warp")
+        out[b] = _nchw(dst, H, W)
+    return out
+
+
+def feat_net(model, img):
+    """FeatNet.forward (models/drmvsnet.py:56-63).  img [B,3,H,W] -> [B,32,H,W]."""
+    _need_cuda(img)
+    eng = model._engine
+    B, _, H, W = img.shape
+    w = eng._weights(img.device)
+    ws = eng._workspace(H, W, 2, 1, img.device, False)
+    out = torch.empty(B, 32, H, W, device=img.device)
+    for b in range(B):
+        eng.feature_map(img[b].float().contiguous(), ws["feat"][0], ws, w, _stream(img.device))
+        out[b] = _nchw(ws["feat"][0], H, W)
+    return out
+
+
+def aggregate_plane(model, ref_fea, src_feas, ref_proj, src_projs, depth_value):
+    """models/drmvsnet.py:307-318 for one sample: ref_fea [32,H,W], src_feas list of [32,H,W], projections [4,4].
+    Returns (volume_variance [32,H,W], reweight maps [S,H,W])."""
+    _need_cuda(ref_fea)
+    eng = model._engine
+    lib, dev = eng.lib, ref_fea.device
+    w = eng._weights(dev)
+    _, H, W = ref_fea.shape
+    S, P = len(src_feas), H * W
+    feat = torch.stack([_nhwc(f.float()) for f in [ref_fea] + list(src_feas)])
+    cams = Engine.relative_cameras(torch.stack([ref_proj] + list(src_projs))).to(dev)
+    depths = torch.tensor([float(depth_value)], device=dev)
+    t0 = torch.empty(S, P, 4, device=dev)
+    sums = torch.zeros(S * 6, device=dev, dtype=torch.float64)
+    cost = torch.empty(P, 32, device=dev)
+    rew = torch.empty(S, P, device=dev)
+    st, ac = _stream(dev), int(eng.align_corners)
+    capi.check(lib.aarmvs_cost_stem(_ptr(feat), _ptr(feat, P * 32), P * 32, H, W, S, _ptr(cams), w["stem.w_host"],
+                                    w["stem.b_host"], _ptr(depths), 0, None, ac, _ptr(t0), _ptr(sums), st), "aarmvs_cost_stem")
+    for stage in (2, 3):
+        capi.check(lib.aarmvs_omega_stats(stage, _ptr(t0), H, W, S, w["tail_host"], _ptr(sums), st), "aarmvs_omega_stats")
+    capi.check(lib.aarmvs_aggregate(_ptr(feat), _ptr(feat, P * 32), P * 32, H, W, S, _ptr(cams), w["tail_host"],
+                                    _ptr(depths), 0, None, ac, _ptr(t0), _ptr(sums), _ptr(cost), _ptr(rew), st),
+               "aarmvs_aggregate")
+    return -_nchw(cost, H, W), rew.view(S, H, W)
+
+
+def convlstm_cell(model, cell_index, x, h, c):
+    """ConvLSTMCell.forward (models/module.py:76-92) of cost_regularization.cell_list[cell_index].
+    x [Cx,H,W], h, c [Ch,H,W] -> (h_next, c_next)."""
+    _need_cuda(x)
+    eng = model._engine
+    lib, dev = eng.lib, x.device
+    w = eng._weights(dev)
+    cx, H, W = x.shape
+    ch = h.shape[0]
+    xs = _nhwc(x.float())
+    h_pair = torch.empty(2, H * W, ch, device=dev)
+    h_pair[0] = _nhwc(h.float())                       # plane d=1 reads half 0 and writes half 1
+    cs = _nhwc(c.float())
+    capi.check(lib.aarmvs_convlstm_cell(_src_array(_src(xs, cx)), 1, H, W, cx + ch, ch, _ptr(w[f"cell{cell_index}.w"]),
+                                        _ptr(w[f"cell{cell_index}.b"]), _ptr(h_pair), _ptr(cs), 1, None, _stream(dev)),
+               "aarmvs_convlstm_cell")
+    return _nchw(h_pair[1], H, W), _nchw(cs, H, W)
+
+
+def deform_conv(model, level, x):
+    """DeformConv2d.forward (models/module.py:133-189) of feature.intraAA.deformconv{level}[0].  x [32,H,W] -> [32,H,W]."""
+    _need_cuda(x)
+    eng = model._engine
+    lib, dev = eng.lib, x.device
+    w = eng._weights(dev)
+    _, H, W = x.shape
+    xs = _nhwc(x.float())
+    om = torch.empty(H * W, 32, device=dev)
+    out = torch.empty(H * W, 32, device=dev)
+    src = _src(xs, 32)
+    st = _stream(dev)
+    capi.check(lib.aarmvs_conv2d(_src_array(src), 1, H, W, 32, 32, 3, 1, _ptr(w[f"pm{level}.w"]), _ptr(w[f"pm{level}.b"]),
+                                 _ptr(om), 32, None, st), "aarmvs_conv2d:pm")
+    capi.check(lib.aarmvs_deform_conv(ctypes.byref(src), H, W, _ptr(om), _ptr(w[f"dc{level}.w"]), _ptr(w[f"dc{level}.b"]),
+                                      _ptr(out), None, st), "aarmvs_deform_conv")
+    return _nchw(out, H, W)

@@ -1,0 +1,47 @@
+"""Repacks checkpoint tensors (nn.Conv2d / ConvTranspose2d / GroupNorm layouts) into the kernel-native layouts
+documented in include/aarmvs.h.  Pure tensor reshuffling; runs once per weight version."""
+import torch
+
+
+def conv_taps(w, cin_pad=None, cout_pad=None):
+    """nn.Conv2d weight [cout][cin][k][k] -> [k*k][cin_pad][cout_pad] (zero padded)."""
+    cout, cin, k, _ = w.shape
+    cin_pad = cin_pad or cin
+    cout_pad = cout_pad or cout
+    out = w.new_zeros(k * k, cin_pad, cout_pad)
+    out[:, :cin, :cout] = w.permute(2, 3, 1, 0).reshape(k * k, cin, cout)
+    return out.contiguous()
+
+
+def pad_vec(b, n):
+    out = b.new_zeros(n)
+    out[: b.numel()] = b
+    return out
+
+
+def lstm_gates(w, b):
+    """ConvLSTMCell conv: output channels [i | f | o | g] blocks of `hidden` (models/module.py:83) ->
+    [k*k][cin][hidden*4] with channel order [hidden channel][i,f,o,g], and the bias likewise."""
+    c4, cin, k, _ = w.shape
+    hidden = c4 // 4
+    perm = torch.arange(c4).view(4, hidden).t().reshape(-1)      # new index hc*4+g <- old g*hidden+hc
+    return conv_taps(w[perm]), b[perm].contiguous()
+
+
+def deconv_taps(w):
+    """nn.ConvTranspose2d weight [cin][cout][kh][kw] -> [kh][kw][cin][cout]."""
+    return w.permute(2, 3, 0, 1).contiguous()
+
+
+def omega_tail(sd, prefix="omega.reweight_network"):
+    """Flat parameter block in the order of struct OmegaTail (csrc/warp_aggregate.cu)."""
+    s = prefix + ".1.stem"
+    parts = [
+        sd[prefix + ".0.1.weight"], sd[prefix + ".0.1.bias"],
+        sd[s + ".0.0.weight"].reshape(16), sd[s + ".0.0.bias"],
+        sd[s + ".0.1.weight"], sd[s + ".0.1.bias"],
+        sd[s + ".1.weight"].reshape(16), sd[s + ".1.bias"],
+        sd[s + ".2.weight"], sd[s + ".2.bias"],
+        sd[prefix + ".2.weight"].reshape(4), sd[prefix + ".2.bias"],
+    ]
+    return torch.cat([p.reshape(-1).float().cpu() for p in parts])

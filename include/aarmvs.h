@@ -1,0 +1,137 @@
+/* aarmvs.h -- C ABI of libaarmvs_sm100.so: the sm_100a kernels of the AA-RMVSNet per-depth-plane cost-volume
+ * pipeline.  The reference (BuTTerK3ks/AA-RMVSNet) is pure PyTorch and has no FFI of its own; each entry point
+ * below replaces the reference Python call site cited next to it (paths relative to the reference root).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in _host;
+ *   - activations are fp32 NHWC ("pixel major": [H][W][C]); images arrive as planar NCHW;
+ *   - no allocation, no ownership transfer, no global mutable state: the caller owns every buffer and passes
+ *     the CUDA stream (cudaStream_t as void*) the work is enqueued on; calls are asynchronous;
+ *   - return value: 0 = enqueued; AARMVS_ERR_ARG = rejected argument; otherwise a cudaError_t value;
+ *   - plane index: kernels of the per-plane chain take (d_host, d_dev).  If d_dev is non-null the plane index
+ *     is read from device memory at run time, which lets one captured CUDA graph be replayed for every plane.
+ *     Hidden states h live in ping-pong pairs: plane d writes half (d & 1) and reads h_{d-1} from the other.
+ */
+#ifndef AARMVS_H
+#define AARMVS_H
+#include <stddef.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AARMVS_ERR_ARG 1000001
+#define AARMVS_MAX_SRC_VIEWS 15
+
+int aarmvs_version(void);          /* ABI version, currently 1 */
+int aarmvs_sm_count(void);         /* multiprocessors of the current device (148 on B200), <0 on error */
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Input description for the convolution kernels: a conv reads the channel concatenation of up to three
+ * sources (replaces torch.cat at models/module.py:80 and models/drmvsnet.py:157,161) and can apply the
+ * producer's GroupNorm+ReLU (models/module.py:101-102) or a 2x2/2 max-pool (models/drmvsnet.py:148,152) on load.
+ */
+enum { AARMVS_SRC_PLAIN = 0, AARMVS_SRC_GN_RELU = 1, AARMVS_SRC_MAXPOOL2 = 2, AARMVS_SRC_NCHW = 3 };
+
+typedef struct aarmvs_conv_src {
+    const float* ptr;          /* NHWC [H][W][channels]; MAXPOOL2: [2H][2W][channels]; NCHW: planar [planes][H][W] */
+    int channels;              /* channels contributed to the concat (multiple of 4; NCHW: planes padded up to 4) */
+    int mode;                  /* AARMVS_SRC_* */
+    int planes;                /* NCHW only: real plane count (3 for RGB) */
+    int gn_groups;             /* GN_RELU only */
+    const double* gn_sums;     /* GN_RELU only: [gn_groups][2] = (sum, sum of squares) written by the producer */
+    const float* gn_weight;    /* GN_RELU only: [channels] */
+    const float* gn_bias;      /* GN_RELU only: [channels] */
+    double gn_count;           /* GN_RELU only: elements per group */
+    size_t pp_stride;          /* 0, or floats between the two halves of a ping-pong pair */
+    int pp_phase;              /* with pp_stride: 0 = half written by the current plane (d & 1), 1 = previous plane */
+} aarmvs_conv_src;
+
+/* ---- FeatNet (models/drmvsnet.py:41-63, 7-24) ---------------------------------------------------------- */
+
+/* Conv2d(k, stride, pad=(k-1)/2) + bias -> pre-norm output [Hout][Wout][cout_stored], and the GroupNorm sums of
+ * the output (groups of 8 channels, models/module.py:101) accumulated into out_gn_sums (may be NULL).
+ * weight: [k*k][cin][cout] (tap-major repack of nn.Conv2d's [cout][cin][k][k]); cin = sum of src channels.
+ * Replaces nn.Conv2d inside convgnrelu (models/module.py:98-103) and p_conv / m_conv (module.py:118,124,134-136).
+ * Supported (cin, cout, k, stride): (4,8,3,1) (8,16,3,1) (16,32,3,1) (32,32,3,1) (32,32,3,2) (32,16,1,1) (32,8,1,1). */
+int aarmvs_conv2d(const aarmvs_conv_src* src, int nsrc, int Hin, int Win, int cin, int cout, int ksize, int stride,
+                  const float* weight, const float* bias, float* out, int cout_stored, double* out_gn_sums,
+                  void* stream);
+
+/* Modulated deformable 3x3 conv, 32 -> 32 channels (models/module.py:133-189, DeformConv2d.forward).
+ * x: the layer input (one conv source, usually GN_RELU of the trunk); offmask: [H][W][32] output of the fused
+ * p_conv/m_conv (channels 0-8 row offsets, 9-17 column offsets, 18-26 modulation logits, 27-31 unused);
+ * weight: [9][32][32] tap-major; out: pre-norm [H][W][32]; out_gn_sums: 4 groups. */
+int aarmvs_deform_conv(const aarmvs_conv_src* x, int H, int W, const float* offmask, const float* weight,
+                       const float* bias, float* out, double* out_gn_sums, void* stream);
+
+/* IntraViewAAModule tail (models/drmvsnet.py:19-24): GroupNorm+ReLU of the three 1x1 outputs, bilinear x2 / x4
+ * upsampling with align_corners=True and channel concat -> feature [H][W][32].  m0: [H][W][16], m1: [H/2][W/2][8],
+ * m2: [H/4][W/4][8]; sums/weight/bias as in aarmvs_conv_src (2, 1, 1 groups). */
+int aarmvs_feat_assemble(const float* m0, const float* m1, const float* m2, const double* sums0, const double* sums1,
+                         const double* sums2, const float* gnw0, const float* gnb0, const float* gnw1,
+                         const float* gnb1, const float* gnw2, const float* gnb2, int H, int W, float* feature,
+                         void* stream);
+
+/* ---- plane sweep: warp + inter-view adaptive aggregation ------------------------------------------------ */
+
+/* homo_warping_depthwise (models/module.py:6-38) for one source view and one depth: out [H][W][32].
+ * cam_host: 12 floats = rot (3x3 row-major) then trans of proj = src_proj @ inverse(ref_proj) (module.py:16-18). */
+int aarmvs_warp(const float* src, float* out, int H, int W, const float* cam_host, float depth, int align_corners,
+                void* stream);
+
+size_t aarmvs_omega_stats_bytes(int S);    /* S * 3 GroupNorms * (sum, sumsq) doubles; zero before each plane */
+int aarmvs_omega_tail_floats(void);        /* length of the packed omega tail parameter block (floats) */
+
+/* Pass A: for each of S source views gather at depth_values[d], c = (warp - ref)^2, t0 = conv3x3 32->4 (+bias)
+ * (omega.reweight_network.0.0, models/drmvsnet.py:31); writes t0 [S][H*W][4] and GroupNorm-1 sums.
+ * src: S feature maps, view v at src + v * view_stride floats; cams: [S][12] device floats;
+ * stem_w_host: [9][32][4] tap-major, stem_b_host: [4] (host: baked into the kernel parameter bank). */
+int aarmvs_cost_stem(const float* ref, const float* src, size_t view_stride, int H, int W, int S, const float* cams,
+                     const float* stem_w_host, const float* stem_b_host, const float* depth_values, int d_host,
+                     const int* d_dev, int align_corners, float* t0, double* stats, void* stream);
+
+/* Pass B (stage 2) / pass C (stage 3): GroupNorm-2 / GroupNorm-3 sums of the omega residual block
+ * (models/module.py:256-258) recomputed point-wise from t0.  tail_host: aarmvs_omega_tail_floats() floats. */
+int aarmvs_omega_stats(int stage, const float* t0, int H, int W, int S, const float* tail_host, double* stats,
+                       void* stream);
+
+/* Pass D: cost[p][c] = -(sum_v (omega_v(p) + 1) * (warp_v - ref)^2) / S  (models/drmvsnet.py:311-319), the input
+ * of the recurrent regulariser.  reweight_out: optional [S][H*W] omega maps (operator seam / tests), may be NULL. */
+int aarmvs_aggregate(const float* ref, const float* src, size_t view_stride, int H, int W, int S, const float* cams,
+                     const float* tail_host, const float* depth_values, int d_host, const int* d_dev,
+                     int align_corners, const float* t0, const double* stats, float* cost, float* reweight_out,
+                     void* stream);
+
+/* ---- recurrent regularisation (models/drmvsnet.py:119-167) --------------------------------------------- */
+
+/* ConvLSTMCell.forward (models/module.py:76-92).  Input = concat(src[0..nsrc-1], h_{d-1}); cin counts all of
+ * them.  weight_packed: [9][cin][4*hidden] with output channel order [hidden channel][i,f,o,g];
+ * bias_packed: [4*hidden] same order.  h_pair: two [H*W][hidden] halves; c_state: [H*W][hidden], in place.
+ * Plane 0 uses h = c = 0 without reading the buffers (module.py:94-96, drmvsnet.py:133-134).
+ * Supported (cin, hidden): (48,16) (32,16) (40,8). */
+int aarmvs_convlstm_cell(const aarmvs_conv_src* src, int nsrc, int H, int W, int cin, int hidden,
+                         const float* weight_packed, const float* bias_packed, float* h_pair, float* c_state,
+                         int d_host, const int* d_dev, void* stream);
+
+/* deConvGnReLU's ConvTranspose2d(16,16,k3,s2,p1,op1) (models/module.py:281): in [Hin][Win][16] (one conv source,
+ * typically a ping-pong h) -> pre-norm out [2Hin][2Win][16] + GroupNorm sums (2 groups).
+ * weight: [3][3][16 cin][16 cout] repack of ConvTranspose2d's [cin][cout][kh][kw]. */
+int aarmvs_deconv2x(const aarmvs_conv_src* in, int Hin, int Win, const float* weight, const float* bias, float* out,
+                    double* out_gn_sums, int d_host, const int* d_dev, void* stream);
+
+/* conv_0 (3x3, 8 -> 1; models/drmvsnet.py:165) fused with the winner-take-all update (drmvsnet.py:324-339):
+ * p = exp(cost); if (max_prob < p) {max_prob = p; depth = depth_values[d]; index = d}; exp_sum += p.
+ * At d == num_depth - 1 also writes conf = max_prob / exp_sum.  At d == 0 the state maps are treated as zero.
+ * weight_host: [9][8] tap-major, bias_host: [1] (host memory: baked into the kernel parameters).
+ * cost_volume: optional [num_depth][H*W] store of the regularised cost (training phase / tests), may be NULL. */
+int aarmvs_head_wta(const aarmvs_conv_src* h4, int H, int W, const float* weight_host, const float* bias_host,
+                    const float* depth_values, int num_depth, int d_host, const int* d_dev, float* max_prob,
+                    float* depth_map, float* exp_sum, int* index_map, float* conf, float* cost_volume, void* stream);
+
+/* End of a plane: ++*d_dev and zero `nzero` doubles of GroupNorm sums for the next plane. */
+int aarmvs_next_plane(int* d_dev, double* sums, int nzero, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
