@@ -190,21 +190,33 @@ class Engine:
                    "aarmvs_feat_assemble")
 
     # ------------------------------------------------------------------------------------------ one plane
-    def _plane(self, ws, w, stream):
-        """Enqueue the kernel chain of one depth plane; the plane index is read from ws['plane'] on the device."""
+    def _plane(self, ws, w, stream, marks=None):
+        """Enqueue the kernel chain of one depth plane; the plane index is read from ws['plane'] on the device.
+        marks: optional list collecting (stage name, CUDA event) after each stage (bench.py's per-kernel timing)."""
         lib, H, W, N = self.lib, ws["H"], ws["W"], ws["N"]
+
+        def mark(name):
+            if marks is not None:
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record(torch.cuda.current_stream())
+                marks.append((name, ev))
+
+        mark("begin")
         P, S = H * W, N - 1
         feat, dptr, ac = ws["feat"], _ptr(ws["plane"]), int(self.align_corners)
         ref, src = _ptr(feat), _ptr(feat, P * 32)
         ps = ws["psums"]
         capi.check(lib.aarmvs_cost_stem(ref, src, P * 32, H, W, S, _ptr(ws["cams"]), w["stem.w_host"], w["stem.b_host"],
                                         _ptr(ws["depths"]), 0, dptr, ac, _ptr(ws["t0"]), _ptr(ps), stream), "aarmvs_cost_stem")
+        mark("cost_stem")
         for stage in (2, 3):
             capi.check(lib.aarmvs_omega_stats(stage, _ptr(ws["t0"]), H, W, S, w["tail_host"], _ptr(ps), stream),
                        "aarmvs_omega_stats")
+        mark("omega_stats")
         capi.check(lib.aarmvs_aggregate(ref, src, P * 32, H, W, S, _ptr(ws["cams"]), w["tail_host"], _ptr(ws["depths"]), 0,
                                         dptr, ac, _ptr(ws["t0"]), _ptr(ps), _ptr(ws["cost"]), None, stream),
                    "aarmvs_aggregate")
+        mark("aggregate")
         h, c = ws["h"], ws["c"]
 
         def hsrc(i, mode=capi.SRC_PLAIN):          # h_i of the CURRENT plane (ping-pong half d & 1)
@@ -215,10 +227,12 @@ class Engine:
             capi.check(lib.aarmvs_convlstm_cell(arr, len(srcs), hh, ww, cin, _HID[i], _ptr(w[f"cell{i}.w"]),
                                                 _ptr(w[f"cell{i}.b"]), _ptr(h[i]), _ptr(c[i]), 0, dptr, stream),
                        f"aarmvs_convlstm_cell[{i}]")
+            mark(f"cell{i}")
 
         def deconv(i, src, hin, win, dst, sums):
             capi.check(lib.aarmvs_deconv2x(ctypes.byref(src), hin, win, _ptr(w[f"deconv{i}.w"]), _ptr(w[f"deconv{i}.b"]),
                                            _ptr(dst), _ptr(sums), 0, dptr, stream), f"aarmvs_deconv2x[{i}]")
+            mark(f"deconv{i}")
 
         H2, W2, H4, W4 = H // 2, W // 2, H // 4, W // 4
         s_up0, s_up1 = ps[S * 6:], ps[S * 6 + 4:]
@@ -238,6 +252,7 @@ class Engine:
                                        _ptr(ws["index"]), _ptr(ws["conf"]), _ptr(cv) if cv is not None else None, stream),
                    "aarmvs_head_wta")
         capi.check(lib.aarmvs_next_plane(dptr, _ptr(ps), ps.numel(), stream), "aarmvs_next_plane")
+        mark("head_wta")
 
     # ------------------------------------------------------------------------------------------ one depth map
     @staticmethod

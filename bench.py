@@ -1,0 +1,302 @@
+#!/usr/bin/env python
+"""bench.py -- depth maps/s and ms per depth plane of the AA-RMVSNet cost-volume pipeline on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg4|cfg1|tiny]
+
+One "step" = one whole depth map of the workload BASELINE.json quotes the metric on (cfg2: 1600x1184, N=7 views,
+D=512 planes, model_dtu_v2.ckpt, synthetic images/cameras): FeatNet on the 7 views + 512 depth planes.
+Rank r of N processes its own reference views (weak scaling; no collective on the data path, one final gather).
+
+Printed JSON (rank 0, one line): value = depth maps/s with the inputs already in HBM; e2e = the same through the
+public EMVSNet.forward with pinned HOST inputs (H2D + D2H inside the timed region); roofline = the dominant kernel
+(ConvLSTM cells, tensor bound) and, beside it, the warp/aggregate stage against the HBM roofline, both timed with
+CUDA events in this run; cpu_baseline = the oracle port (PyTorch CPU fp32) on the host cores, bounded sample.
+--impl reference times that CPU path as the line's value.
+"""
+import argparse
+import json
+import os
+import statistics as stats
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+WORKLOADS = {
+    # name: (H, W, N, D, ckpt, depth mode)
+    "cfg2": (1184, 1600, 7, 512, "model_dtu_v2.ckpt", "uniform"),
+    "cfg4": (1056, 1920, 7, 512, "model_blended_v2.ckpt", "inverse"),
+    "cfg1": (512, 640, 3, 48, "model_dtu_v2.ckpt", "inverse"),
+    "tiny": (64, 96, 3, 8, "model_dtu_v2.ckpt", "uniform"),
+}
+FLOP_PER_PX_PLANE = 105264            # ConvLSTM U-Net, SURVEY.md §8d
+CELL_FLOP_PER_PX = {"cell0": 55296, "cell1": 9216, "cell2": 2304, "cell3": 13824, "cell4": 23040}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        j = json.load(open(p))
+        return {"hbm_gbs": j["hbm_gbs"], "bf16_tflops": j["bf16_tflops"], "bf16_tflops_sustained": j["bf16_tflops_sustained"],
+                "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, smax, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        busy = [x for x in sm if x > 0.5 * max(sm)] if sm else []
+        return {"sm_mhz": stats.median(busy) if busy else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def load_sd(ckpt):
+    return torch.load(os.path.join(ROOT, "tests", "golden", ckpt), map_location="cpu", weights_only=False)["model"]
+
+
+# ------------------------------------------------------------------------------------------------- CPU arms
+def cpu_plane_sample(workload, threads=None, planes=1, warm_planes=1):
+    """Oracle port (oracle/aarmvs_oracle.py = the reference's algorithm, PyTorch CPU fp32) on the host cores:
+    FeatNet on ONE view at full resolution + `planes` depth planes with all N views, extrapolated to
+    N views x D planes.  Returns (seconds per depth map, featnet s/view, s/plane, cores)."""
+    from aarmvsnet_b200 import synth
+    from oracle import aarmvs_oracle as orc
+    H, W, N, D, ckpt, mode = WORKLOADS[workload]
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    sd = load_sd(ckpt)
+    s = synth.make_sample(H, W, N, D, seed=0, depth_mode=mode)
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        f = orc.feat_net(s["imgs"][:, 0], sd)
+        t_feat = time.perf_counter() - t0
+        feats = [f] + [f.roll(v, 3) for v in range(1, N)]          # timing does not depend on the feature values
+        state = orc.init_state(1, H, W)
+        pm, dv = s["proj_matrices"], s["depth_values"]
+        times = []
+        for d in range(warm_planes + planes):
+            t0 = time.perf_counter()
+            var = orc.aggregate_plane(feats[0], feats[1:], pm[:, 0], [pm[:, v] for v in range(1, N)], dv[:, d], sd)
+            cost, state = orc.unet_step(-1 * var, state, sd)
+            torch.exp(cost)
+            times.append(time.perf_counter() - t0)
+    t_plane = sum(times[warm_planes:]) / planes
+    return N * t_feat + D * t_plane, t_feat, t_plane, threads
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    H, W, N, D, ckpt, mode = WORKLOADS[args.workload]
+    total, t_feat, t_plane, cores = cpu_plane_sample(args.workload, planes=max(1, args.steps), warm_planes=1)
+    val = 1.0 / total
+    sample = (f"oracle port of the reference forward (PyTorch {torch.__version__} CPU fp32, {cores} threads): FeatNet on 1 of {N} "
+              f"views at {W}x{H} ({t_feat:.2f} s) + {max(1, args.steps)} timed depth planes with all {N} views after 1 warm-up "
+              f"plane ({t_plane:.2f} s/plane), extrapolated linearly to {N} views x {D} planes")
+    line = {"impl": "reference", "metric": "depth maps/sec", "value": val, "unit": "depth maps/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": total * 1e3, "ms_per_plane": total * 1e3 / D,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": config_dict(args.workload),
+            "cpu_baseline": {"value": val, "unit": "depth maps/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": "depth maps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def config_dict(workload):
+    H, W, N, D, ckpt, mode = WORKLOADS[workload]
+    return {"workload": f"{workload}: AA-RMVSNet test-phase forward, {W}x{H}, N={N} views, D={D} {mode} depth planes, {ckpt}, "
+                        "synthetic N(0,1) images + ring cameras", "height": H, "width": W, "views": N, "planes": D,
+            "checkpoint": ckpt, "l2": "per-step working set (features 1.7 GB + state 0.9 GB at cfg2) exceeds the 126 MB L2"}
+
+
+# ------------------------------------------------------------------------------------------------- GPU arm
+def stage_profile(engine, ws, w, planes=12):
+    """Per-stage CUDA-event timing of the plane chain, eager launches on the current stream (ms per plane)."""
+    import ctypes
+    stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    acc = {}
+    for it in range(planes + 2):
+        marks = []
+        ws["plane"].fill_(1)
+        engine._plane(ws, w, stream, marks)
+        torch.cuda.synchronize()
+        if it < 2:
+            continue
+        for (n0, e0), (n1, e1) in zip(marks[:-1], marks[1:]):
+            acc.setdefault(n1, []).append(e0.elapsed_time(e1))
+    return {k: sum(v) / len(v) for k, v in acc.items()}
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    import aarmvsnet_b200 as aa
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device (there is no CPU path); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    H, W, N, D, ckpt, mode = WORKLOADS[args.workload]
+    model = aa.EMVSNet(disparity_level=32, image_scale=1.0, max_h=H, max_w=W, return_depth=True)
+    model.load_state_dict(load_sd(ckpt), strict=True)
+    model = model.to(dev).eval()
+    eng = model._engine
+    total_steps = args.warmup + args.steps
+    # one distinct reference view (sample) per step and rank, host side pinned
+    samples = [aa.synth.make_sample(H, W, N, D, seed=1000 * rank + i, depth_mode=mode) for i in range(min(total_steps, 2))]
+    host = [{k: v[0].pin_memory() for k, v in s.items()} for s in samples]
+    resident = [{k: v.to(dev) for k, v in h.items()} for h in host]
+    h2d = sum(v.numel() * v.element_size() for v in host[0].values())
+    d2h = 2 * H * W * 4
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn):
+        for i in range(args.warmup):
+            fn(i)
+        barrier()
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(args.steps):
+            fn(args.warmup + i)
+        e1.record()
+        barrier()
+        clocks = sampler.stop() if rank == 0 else None
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item(), clocks
+
+    results = {}
+
+    def step_resident(i):
+        r = resident[i % len(resident)]
+        o = eng.depth_map(r["imgs"], r["proj_matrices"], r["depth_values"])
+        results["last"] = (o["depth"], o["photometric_confidence"])
+
+    out_host = torch.empty(2, H, W).pin_memory()
+
+    def step_e2e(i):
+        h = host[i % len(host)]
+        o = model(h["imgs"][None].to(dev, non_blocking=True), h["proj_matrices"][None].to(dev, non_blocking=True),
+                  h["depth_values"][None].to(dev, non_blocking=True))
+        out_host[0].copy_(o["depth"][0], non_blocking=True)
+        out_host[1].copy_(o["photometric_confidence"][0], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    ms_total, clocks = timed(step_resident)
+    if world > 1:    # the single end-of-scan gather of the [H,W] depth + confidence maps; outside the data path
+        maps = torch.stack(results["last"])
+        gathered = [torch.empty_like(maps) for _ in range(world)]
+        dist.all_gather(gathered, maps)
+    ms_e2e, _ = timed(step_e2e)
+
+    value = world * args.steps / (ms_total * 1e-3)
+    e2e_value = world * args.steps / (ms_e2e * 1e-3)
+    line = None
+    if rank == 0:
+        pk = peaks()
+        ws = eng._workspace(H, W, N, D, dev, False)
+        w = eng._weights(dev)
+        st = stage_profile(eng, ws, w)
+        P = H * W
+        wa_ms = st["cost_stem"] + st["omega_stats"] + st["aggregate"]
+        rec_ms = sum(st[k] for k in st if k.startswith(("cell", "deconv", "head")))
+        wa_bytes = 128 * P * (N + 1)
+        cell0_flops = CELL_FLOP_PER_PX["cell0"] * P
+        roofline = {"kernel": "conv_kernel<48,64,3,1,16,4,EPI_LSTM> (ConvLSTM cell 0, fp32 CUDA-core FMA in round 1)",
+                    "bound": "tensor", "achieved": cell0_flops / (st["cell0"] * 1e-3) / 1e12, "peak": pk["bf16_tflops_sustained"],
+                    "unit": "TFLOP/s", "traffic": None, "peak_source": pk["source"] + ", sustained bf16 (kernel timed inside a long step)"}
+        roofline["frac"] = roofline["achieved"] / roofline["peak"]
+        extra = {
+            "stage_ms_per_plane": {k: round(v, 4) for k, v in st.items()},
+            "recurrence": {"ms_per_plane": rec_ms, "achieved_tflops": FLOP_PER_PX_PLANE * P / (rec_ms * 1e-3) / 1e12,
+                           "frac_of_bf16_sustained": FLOP_PER_PX_PLANE * P / (rec_ms * 1e-3) / 1e12 / pk["bf16_tflops_sustained"]},
+            "warp_aggregate": {"bound": "hbm", "ms_per_plane": wa_ms, "algorithmic_bytes": wa_bytes,
+                               "achieved": wa_bytes / (wa_ms * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                               "frac": wa_bytes / (wa_ms * 1e-3) / 1e9 / pk["hbm_gbs"]},
+        }
+        cpu = None
+        if not args.no_cpu_baseline:
+            total, t_feat, t_plane, cores = cpu_plane_sample(args.workload, planes=1, warm_planes=1)
+            cpu = {"value": 1.0 / total, "unit": "depth maps/s", "cores": cores, "kind": "port",
+                   "sample": f"oracle port, FeatNet on 1 view ({t_feat:.2f} s) + 1 timed plane after 1 warm-up plane ({t_plane:.2f} s/plane) "
+                             f"at {W}x{H} N={N}, extrapolated to {N} views x {D} planes"}
+        line = {"metric": "depth maps/sec", "value": value, "unit": "depth maps/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "ms_per_plane": ms_total / args.steps / D,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": config_dict(args.workload), "clocks": clocks,
+                "e2e": {"value": e2e_value, "unit": "depth maps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "ms_per_step": ms_e2e / args.steps},
+                "gpu_launches": args.steps * (N * 16 + D * 13), "roofline": roofline, "cpu_baseline": cpu, **extra}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return line
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()
