@@ -131,6 +131,15 @@ int aarmvs_head_wta(const aarmvs_conv_src* h4, int H, int W, const float* weight
 /* End of a plane: ++*d_dev and zero `nzero` doubles of GroupNorm sums for the next plane. */
 int aarmvs_next_plane(int* d_dev, double* sums, int nzero, void* stream);
 
+/* ---- tensor-core building blocks ------------------------------------------------------------------------- */
+
+/* Known-answer test of the tcgen05 path shared by the ConvLSTM kernels (un-swizzled K-major shared-memory operands,
+ * 8-row groups `group_rows` rows apart, start row `shift`, TMEM accumulation, commit -> mbarrier, tcgen05.ld):
+ *   d[m][n] = sum_k a[shift + (m / 8) * group_rows + m % 8][k] * b[n][k],  m < 128, n < 64, fp16 inputs, fp32 out.
+ * a_f16: [a_rows][K] row-major fp16, b_f16: [64][K]; K multiple of 16, <= 256. */
+int aarmvs_tc_selftest(const void* a_f16, int a_rows, const void* b_f16, float* d, int K, int group_rows, int shift,
+                       void* stream);
+
 #ifdef __cplusplus
 }
 #endif
