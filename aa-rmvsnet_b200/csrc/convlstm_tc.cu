@@ -1,0 +1,341 @@
+// ConvLSTM cell as a tcgen05 / TMEM implicit GEMM (models/module.py:76-92).
+//
+//   gates[128 px][4*CH] = sum over 9 taps, K = Cin:  A_tap[128 px][Cin] * W_tap[Cin][4*CH]
+//
+// Precision: the parity bar (same winning plane on >= 99.9 % of the pixels) rules out single-pass TF32/BF16 operands
+// (hard part 1), so every fp32 operand x is split on the fly into two fp16 values x ~= hi + lo
+// (|x - hi - lo| <= 2^-22 |x|) and each K=16 step issues three kind::f16 MMAs with fp32 accumulation in TMEM:
+//   hi*hi + lo*hi + hi*lo      (the dropped lo*lo term is <= 2^-22 relative)
+// Useful FLOPs are counted once; the tensor pipe executes 3x as many.
+//
+// Tile: 16 rows x 8 columns of pixels = the 128 rows of the accumulator.  Row m = 8 g + i of the MMA is pixel
+// (row g, column i), so one 8-row core-matrix group is one tile row, and inside the staged halo tile
+// [18 rows][10 columns] the stride between groups is 10 pixels: a 3x3 tap (ky, kx) is just a different START ADDRESS
+// (ky * 10 + kx pixels further) into the same staged data -- no im2col copy, each input pixel is staged once per tile.
+// Shared-memory operand layout (un-swizzled, K-major): [16-byte K chunk = 8 channels][pixel][8 x fp16], i.e.
+// 8 pixels x 16 B contiguous per core matrix, SBO = 10 * 16 B, LBO = 180 * 16 B (validated by aarmvs_tc_selftest).
+//
+// Warp roles (persistent CTA, one per SM):  warps 0-7 epilogue (TMEM -> gates -> c, h),  warp 8 TMEM allocation + the
+// single MMA-issuing thread,  warps 9-16 loaders (global fp32 -> concat / GroupNorm+ReLU / max-pool on load -> fp16
+// hi/lo split -> shared memory).  Pipelines: 2 operand stages (loader <-> MMA) and 2 TMEM accumulators (MMA <->
+// epilogue), all hand-offs through mbarriers; tcgen05.commit releases operand stages and publishes accumulators.
+#include "common.cuh"
+#include "tc_common.cuh"
+#include "../../include/aarmvs.h"
+
+namespace {
+
+struct TcSrc {
+    const float* ptr;
+    const double* stats;
+    const float* gamma;
+    const float* beta;
+    int ch, mode, groups;
+    double count;
+    size_t pp_stride;
+    int pp_phase;
+};
+
+struct TcArgs {
+    TcSrc src[3];
+    int nsrc;
+    int H, W;
+    const __half* weight;      // [2 planes hi,lo][9 taps][KC8][NG][8] fp16
+    const float* bias;         // [NG], order [hidden channel][i,f,o,g]
+    float* h_pair;
+    float* c_state;
+    int d_host;
+    const int* d_dev;
+};
+
+constexpr int TR = 16, TCOL = 8, HR = TR + 2, HC = TCOL + 2, NPX = HR * HC;   // 180 staged pixels per tile
+constexpr int N_EPI_WARPS = 8, N_LOAD_WARPS = 8;
+constexpr int MMA_WARP = N_EPI_WARPS, FIRST_LOAD_WARP = MMA_WARP + 1;
+constexpr int N_THREADS = (N_EPI_WARPS + 1 + N_LOAD_WARPS) * 32;               // 544
+constexpr int N_STAGES = 2;
+
+template <int KSTEPS, int NG>
+struct TcCfg {
+    static constexpr int KC8 = 2 * KSTEPS;                       // 16-byte K chunks (8 channels each)
+    static constexpr int A_PLANE = KC8 * NPX * 16;               // bytes of one fp16 plane (hi or lo) of one stage
+    static constexpr int A_STAGE = 2 * A_PLANE;
+    static constexpr int B_PLANE = 9 * KC8 * NG * 16;
+    static constexpr int B_BYTES = 2 * B_PLANE;
+    static constexpr int SMEM = B_BYTES + N_STAGES * A_STAGE + 1024;
+    static constexpr int TMEM_COLS = 2 * NG;                     // two accumulators
+    static_assert(TMEM_COLS == 64 || TMEM_COLS == 128, "TMEM allocation must be a power of two >= 32");
+};
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ uint32_t pack_h2(__half a, __half b) {
+    return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16);
+}
+
+template <int KSTEPS, int NG>
+__global__ void __launch_bounds__(N_THREADS, 1) convlstm_tc_kernel(const __grid_constant__ TcArgs a) {
+    using C = TcCfg<KSTEPS, NG>;
+    constexpr int CH = NG / 4;
+    extern __shared__ __align__(1024) unsigned char smem[];
+    unsigned char* sB = smem;                                   // weights: [hi|lo][tap][kc8][n][16 B]
+    unsigned char* sA = smem + C::B_BYTES;                      // stages: [stage][hi|lo][kc8][px][16 B]
+    __shared__ uint64_t full_a[N_STAGES], empty_a[N_STAGES], tmem_full[2], tmem_empty[2];
+    __shared__ uint32_t tmem_base_s;
+    __shared__ float s_scale[48], s_shift[48], s_bias[NG];
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int d = plane_index(a.d_host, a.d_dev);
+
+    // ---- one-time setup: weights -> smem, GroupNorm scale/shift of normalised sources, barriers, TMEM
+    for (int i = tid; i < C::B_BYTES / 16; i += N_THREADS)
+        reinterpret_cast<uint4*>(sB)[i] = __ldg(reinterpret_cast<const uint4*>(a.weight) + i);
+    if (tid < 48) {
+        float sc = 1.f, sh = 0.f;
+        int base = 0;
+        for (int s = 0; s < a.nsrc; ++s) {
+            const TcSrc& S = a.src[s];
+            if (tid >= base && tid < base + S.ch && S.mode == AARMVS_SRC_GN_RELU) {
+                const int cl = tid - base;
+                float mean, rstd;
+                gn_mean_rstd(S.stats + (cl / (S.ch / S.groups)) * 2, S.count, mean, rstd);
+                sc = rstd * S.gamma[cl];
+                sh = S.beta[cl] - mean * sc;
+            }
+            base += S.ch;
+        }
+        s_scale[tid] = sc;
+        s_shift[tid] = sh;
+    }
+    if (tid < NG) s_bias[tid] = a.bias[tid];
+    if (tid == 0) {
+        for (int s = 0; s < N_STAGES; ++s) { tc::mbar_init(&full_a[s], N_LOAD_WARPS * 32); tc::mbar_init(&empty_a[s], 1); }
+        for (int b = 0; b < 2; ++b) { tc::mbar_init(&tmem_full[b], 1); tc::mbar_init(&tmem_empty[b], N_EPI_WARPS * 32); }
+        tc::mbar_fence_init();
+    }
+    if (warp == MMA_WARP) tc::tmem_alloc<C::TMEM_COLS>(&tmem_base_s);
+    tc::fence_async_smem();                  // weights were written through the generic proxy
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+
+    const int tiles_x = (a.W + TCOL - 1) / TCOL, tiles_y = (a.H + TR - 1) / TR;
+    const int ntiles = tiles_x * tiles_y;
+
+    if (warp >= FIRST_LOAD_WARP) {
+        // =========================================== loaders ===========================================
+        const int lt = tid - FIRST_LOAD_WARP * 32;               // 0..255
+        const float* sptr[3];
+        int sbase[4] = {0, 0, 0, 0};
+        for (int s = 0; s < 3; ++s) {
+            sptr[s] = nullptr;
+            if (s < a.nsrc) {
+                const TcSrc& S = a.src[s];
+                sptr[s] = S.pp_stride ? S.ptr + (size_t)((d + S.pp_phase) & 1) * S.pp_stride : S.ptr;
+                sbase[s + 1] = sbase[s] + S.ch;
+            } else {
+                sbase[s + 1] = sbase[s];
+            }
+        }
+        int it = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+            const int st = it % N_STAGES;
+            tc::mbar_wait(&empty_a[st], ((it / N_STAGES) & 1) ^ 1);
+            const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+            const int y0 = ty * TR - 1, x0 = tx * TCOL - 1;
+            unsigned char* stage = sA + st * C::A_STAGE;
+            for (int idx = lt; idx < C::KC8 * NPX; idx += N_LOAD_WARPS * 32) {
+                const int kc = idx / NPX, px = idx - kc * NPX;
+                const int r = px / HC, cc = px - r * HC;
+                const int y = y0 + r, x = x0 + cc;
+                const int c = kc * 8;
+                float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                if (y >= 0 && y < a.H && x >= 0 && x < a.W && c < sbase[a.nsrc]) {
+                    const int s = c < sbase[1] ? 0 : (c < sbase[2] ? 1 : 2);
+                    const TcSrc& S = a.src[s];
+                    const float* sp = s == 0 ? sptr[0] : s == 1 ? sptr[1] : sptr[2];
+                    const int cl = c - sbase[s];
+                    if (s == a.nsrc - 1 && d == 0) {
+                        // h_{-1} = 0 (module.py:94-96)
+                    } else if (S.mode == AARMVS_SRC_MAXPOOL2) {
+                        const size_t rowp = (size_t)2 * a.W * S.ch;
+                        const float* p = sp + (size_t)(2 * y) * rowp + (size_t)(2 * x) * S.ch + cl;
+#pragma unroll
+                        for (int hh = 0; hh < 2; ++hh) {
+                            const float4 q0 = ld4(p + hh * 4), q1 = ld4(p + S.ch + hh * 4), q2 = ld4(p + rowp + hh * 4),
+                                         q3 = ld4(p + rowp + S.ch + hh * 4);
+                            v[hh * 4 + 0] = fmaxf(fmaxf(q0.x, q1.x), fmaxf(q2.x, q3.x));
+                            v[hh * 4 + 1] = fmaxf(fmaxf(q0.y, q1.y), fmaxf(q2.y, q3.y));
+                            v[hh * 4 + 2] = fmaxf(fmaxf(q0.z, q1.z), fmaxf(q2.z, q3.z));
+                            v[hh * 4 + 3] = fmaxf(fmaxf(q0.w, q1.w), fmaxf(q2.w, q3.w));
+                        }
+                    } else {
+                        const float* p = sp + ((size_t)y * a.W + x) * S.ch + cl;
+                        const float4 q0 = ld4(p), q1 = ld4(p + 4);
+                        v[0] = q0.x; v[1] = q0.y; v[2] = q0.z; v[3] = q0.w;
+                        v[4] = q1.x; v[5] = q1.y; v[6] = q1.z; v[7] = q1.w;
+                        if (S.mode == AARMVS_SRC_GN_RELU) {
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) v[e] = fmaxf(fmaf(v[e], s_scale[c + e], s_shift[c + e]), 0.f);
+                        }
+                    }
+                }
+                __half hi[8], lo[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) tc::split_f16(v[e], hi[e], lo[e]);
+                const uint4 uh = make_uint4(pack_h2(hi[0], hi[1]), pack_h2(hi[2], hi[3]), pack_h2(hi[4], hi[5]), pack_h2(hi[6], hi[7]));
+                const uint4 ul = make_uint4(pack_h2(lo[0], lo[1]), pack_h2(lo[2], lo[3]), pack_h2(lo[4], lo[5]), pack_h2(lo[6], lo[7]));
+                *reinterpret_cast<uint4*>(stage + (size_t)idx * 16) = uh;
+                *reinterpret_cast<uint4*>(stage + C::A_PLANE + (size_t)idx * 16) = ul;
+            }
+            tc::fence_async_smem();
+            tc::mbar_arrive(&full_a[st]);
+        }
+    } else if (warp == MMA_WARP) {
+        // =========================================== MMA issuer ===========================================
+        if (lane == 0) {
+            const uint32_t idesc = tc::idesc_f16_f32(128, NG);
+            const uint32_t a_base = tc::smem_u32(sA), b_base = tc::smem_u32(sB);
+            int it = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+                const int st = it % N_STAGES, ab = it & 1;
+                tc::mbar_wait(&full_a[st], (it / N_STAGES) & 1);
+                tc::mbar_wait(&tmem_empty[ab], ((it >> 1) & 1) ^ 1);
+                tc::tc_fence_after();
+                const uint32_t dst = tmem_base + ab * NG;
+                const uint32_t a_hi = a_base + st * C::A_STAGE, a_lo = a_hi + C::A_PLANE;
+                uint32_t first = 0;
+#pragma unroll 1
+                for (int tap = 0; tap < 9; ++tap) {
+                    const uint32_t a_off = (uint32_t)((tap / 3) * HC + (tap % 3)) * 16;
+#pragma unroll
+                    for (int ks = 0; ks < KSTEPS; ++ks) {
+                        const uint32_t ak = (uint32_t)(2 * ks) * NPX * 16 + a_off;
+                        const uint32_t bk = (uint32_t)((tap * C::KC8 + 2 * ks) * NG) * 16;
+                        const uint64_t da_hi = tc::smem_desc(a_hi + ak, NPX * 16, HC * 16);
+                        const uint64_t da_lo = tc::smem_desc(a_lo + ak, NPX * 16, HC * 16);
+                        const uint64_t db_hi = tc::smem_desc(b_base + bk, NG * 16, 8 * 16);
+                        const uint64_t db_lo = tc::smem_desc(b_base + C::B_PLANE + bk, NG * 16, 8 * 16);
+                        tc::mma_f16(dst, da_lo, db_hi, idesc, first);   // small terms first
+                        first = 1;
+                        tc::mma_f16(dst, da_hi, db_lo, idesc, 1);
+                        tc::mma_f16(dst, da_hi, db_hi, idesc, 1);
+                    }
+                }
+                tc::mma_commit(&empty_a[st]);          // operand stage free once these MMAs have read it
+                tc::mma_commit(&tmem_full[ab]);        // accumulator complete
+            }
+        }
+    } else {
+        // =========================================== epilogue ===========================================
+        const int q = warp & 3, hf = warp >> 2;                  // TMEM lane quadrant, half of the gate columns
+        constexpr int NCOL = NG / 2, NHC = CH / 2;               // columns / hidden channels per thread
+        const int m = q * 32 + lane;
+        float* hdst = a.h_pair + (size_t)(d & 1) * a.H * a.W * CH;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+            const int ab = it & 1;
+            tc::mbar_wait(&tmem_full[ab], (it >> 1) & 1);
+            tc::tc_fence_after();
+            float g[NCOL];
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + ab * NG + hf * NCOL;
+            if constexpr (NCOL == 32) tc::tmem_ld32(taddr, g); else tmem_ld16(taddr, g);
+            tc::tc_fence_before();
+            tc::mbar_arrive(&tmem_empty[ab]);                    // accumulator is in registers: release it
+            const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+            const int y = ty * TR + (m >> 3), x = tx * TCOL + (m & 7);
+            if (y < a.H && x < a.W) {
+                const size_t pix = (size_t)y * a.W + x;
+                float* cp = a.c_state + pix * CH + hf * NHC;
+                float* hp = hdst + pix * CH + hf * NHC;
+                float cprev[NHC], cn[NHC], hn[NHC];
+#pragma unroll
+                for (int j = 0; j < NHC; j += 4) {
+                    const float4 t = d == 0 ? make_float4(0.f, 0.f, 0.f, 0.f) : ld4(cp + j);
+                    cprev[j] = t.x; cprev[j + 1] = t.y; cprev[j + 2] = t.z; cprev[j + 3] = t.w;
+                }
+#pragma unroll
+                for (int j = 0; j < NHC; ++j) {
+                    const float* bb = s_bias + hf * NCOL + j * 4;
+                    const float gi = sigmoidf_acc(g[j * 4 + 0] + bb[0]);
+                    const float gf = sigmoidf_acc(g[j * 4 + 1] + bb[1]);
+                    const float go = sigmoidf_acc(g[j * 4 + 2] + bb[2]);
+                    const float gg = tanhf(g[j * 4 + 3] + bb[3]);
+                    cn[j] = __fadd_rn(__fmul_rn(gf, cprev[j]), __fmul_rn(gi, gg));
+                    hn[j] = go * tanhf(cn[j]);
+                }
+#pragma unroll
+                for (int j = 0; j < NHC; j += 4) {
+                    st4(cp + j, make_float4(cn[j], cn[j + 1], cn[j + 2], cn[j + 3]));
+                    st4(hp + j, make_float4(hn[j], hn[j + 1], hn[j + 2], hn[j + 3]));
+                }
+            }
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == MMA_WARP) tc::tmem_dealloc<C::TMEM_COLS>(tmem_base);
+}
+
+template <int KSTEPS, int NG>
+int launch_tc(const TcArgs& a, cudaStream_t stream) {
+    using C = TcCfg<KSTEPS, NG>;
+    auto kern = convlstm_tc_kernel<KSTEPS, NG>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+        if (e != cudaSuccess) return (int)e;
+        attr_set = true;
+    }
+    const int ntiles = ((a.W + TCOL - 1) / TCOL) * ((a.H + TR - 1) / TR);
+    const int sms = aarmvs_sm_count();
+    if (sms <= 0) return AARMVS_ERR_ARG;
+    kern<<<ntiles < sms ? ntiles : sms, N_THREADS, C::SMEM, stream>>>(a);
+    AARMVS_LAUNCH_RESULT();
+}
+
+}  // namespace
+
+extern "C" int aarmvs_convlstm_cell_tc(const aarmvs_conv_src* src, int nsrc, int H, int W, int cin, int hidden,
+                                       const void* weight_f16, const float* bias_packed, float* h_pair, float* c_state,
+                                       int d_host, const int* d_dev, void* stream) {
+    AARMVS_CHECK_ARG(src && weight_f16 && bias_packed && h_pair && c_state && H > 0 && W > 0 && nsrc >= 1 && nsrc <= 2);
+    TcArgs a = {};
+    a.nsrc = nsrc + 1;
+    int csum = 0;
+    for (int s = 0; s <= nsrc; ++s) {
+        TcSrc& t = a.src[s];
+        if (s < nsrc) {
+            const aarmvs_conv_src& i = src[s];
+            AARMVS_CHECK_ARG(i.ptr && i.channels > 0 && i.channels % 8 == 0);
+            AARMVS_CHECK_ARG(i.mode == AARMVS_SRC_PLAIN || i.mode == AARMVS_SRC_GN_RELU || i.mode == AARMVS_SRC_MAXPOOL2);
+            if (i.mode == AARMVS_SRC_GN_RELU)
+                AARMVS_CHECK_ARG(i.gn_sums && i.gn_weight && i.gn_bias && i.gn_groups >= 1 && i.gn_count > 0);
+            t.ptr = i.ptr; t.stats = i.gn_sums; t.gamma = i.gn_weight; t.beta = i.gn_bias; t.ch = i.channels; t.mode = i.mode;
+            t.groups = i.gn_groups; t.count = i.gn_count; t.pp_stride = i.pp_stride; t.pp_phase = i.pp_phase;
+        } else {      // h_{d-1}: the half of the ping-pong pair that plane d does not write
+            t.ptr = h_pair; t.ch = hidden; t.mode = AARMVS_SRC_PLAIN; t.pp_stride = (size_t)H * W * hidden; t.pp_phase = 1;
+        }
+        csum += t.ch;
+    }
+    AARMVS_CHECK_ARG(csum == cin && cin <= 48);
+    a.H = H; a.W = W; a.weight = (const __half*)weight_f16; a.bias = bias_packed; a.h_pair = h_pair; a.c_state = c_state;
+    a.d_host = d_host; a.d_dev = d_dev;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (cin == 48 && hidden == 16) return launch_tc<3, 64>(a, st);     // cells 0, 3
+    if (cin == 32 && hidden == 16) return launch_tc<2, 64>(a, st);     // cells 1, 2
+    if (cin == 40 && hidden == 8) return launch_tc<3, 32>(a, st);      // cell 4 (K padded 40 -> 48 with zero channels)
+    return AARMVS_ERR_ARG;
+}

@@ -42,7 +42,10 @@ def _src_array(*srcs):
 class Engine:
     """Runs EMVSNet.forward's arithmetic for one model instance (weights are re-packed when they change)."""
 
-    def __init__(self, module, align_corners=False, use_graph=True):
+    def __init__(self, module, align_corners=False, use_graph=True, cell_math="tc"):
+        if cell_math not in ("tc", "fma"):
+            raise ValueError("cell_math must be 'tc' (tcgen05, split-fp16 operands) or 'fma' (fp32 CUDA cores)")
+        self.cell_math = cell_math
         self.module = module
         self.align_corners = bool(align_corners)     # grid_sample default under torch >= 1.3 is False (SURVEY.md §0.5)
         self.use_graph = use_graph
@@ -83,6 +86,8 @@ class Engine:
         for i in range(5):
             w[f"cell{i}.w"], w[f"cell{i}.b"] = pack.lstm_gates(sd[f"{cr}.cell_list.{i}.conv.weight"],
                                                                 sd[f"{cr}.cell_list.{i}.conv.bias"])
+            w[f"cell{i}.wtc"], _ = pack.lstm_gates_f16(sd[f"{cr}.cell_list.{i}.conv.weight"],
+                                                       sd[f"{cr}.cell_list.{i}.conv.bias"])
         for i in range(2):
             w[f"deconv{i}.w"] = pack.deconv_taps(sd[f"{cr}.deconv_{i}.conv.weight"])
             w[f"deconv{i}.b"] = sd[f"{cr}.deconv_{i}.conv.bias"].contiguous()
@@ -224,9 +229,14 @@ class Engine:
 
         def cell(i, srcs, hh, ww, cin):
             arr = _src_array(*srcs)
-            capi.check(lib.aarmvs_convlstm_cell(arr, len(srcs), hh, ww, cin, _HID[i], _ptr(w[f"cell{i}.w"]),
-                                                _ptr(w[f"cell{i}.b"]), _ptr(h[i]), _ptr(c[i]), 0, dptr, stream),
-                       f"aarmvs_convlstm_cell[{i}]")
+            if self.cell_math == "tc":
+                capi.check(lib.aarmvs_convlstm_cell_tc(arr, len(srcs), hh, ww, cin, _HID[i], _ptr(w[f"cell{i}.wtc"]),
+                                                       _ptr(w[f"cell{i}.b"]), _ptr(h[i]), _ptr(c[i]), 0, dptr, stream),
+                           f"aarmvs_convlstm_cell_tc[{i}]")
+            else:
+                capi.check(lib.aarmvs_convlstm_cell(arr, len(srcs), hh, ww, cin, _HID[i], _ptr(w[f"cell{i}.w"]),
+                                                    _ptr(w[f"cell{i}.b"]), _ptr(h[i]), _ptr(c[i]), 0, dptr, stream),
+                           f"aarmvs_convlstm_cell[{i}]")
             mark(f"cell{i}")
 
         def deconv(i, src, hin, win, dst, sums):

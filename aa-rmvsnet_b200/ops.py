@@ -89,7 +89,7 @@ def aggregate_plane(model, ref_fea, src_feas, ref_proj, src_projs, depth_value):
     return -_nchw(cost, H, W), rew.view(S, H, W)
 
 
-def convlstm_cell(model, cell_index, x, h, c):
+def convlstm_cell(model, cell_index, x, h, c, math=None):
     """ConvLSTMCell.forward (models/module.py:76-92) of cost_regularization.cell_list[cell_index].
     x [Cx,H,W], h, c [Ch,H,W] -> (h_next, c_next)."""
     _need_cuda(x)
@@ -102,9 +102,14 @@ def convlstm_cell(model, cell_index, x, h, c):
     h_pair = torch.empty(2, H * W, ch, device=dev)
     h_pair[0] = _nhwc(h.float())                       # plane d=1 reads half 0 and writes half 1
     cs = _nhwc(c.float())
-    capi.check(lib.aarmvs_convlstm_cell(_src_array(_src(xs, cx)), 1, H, W, cx + ch, ch, _ptr(w[f"cell{cell_index}.w"]),
-                                        _ptr(w[f"cell{cell_index}.b"]), _ptr(h_pair), _ptr(cs), 1, None, _stream(dev)),
-               "aarmvs_convlstm_cell")
+    if (math or eng.cell_math) == "tc":
+        capi.check(lib.aarmvs_convlstm_cell_tc(_src_array(_src(xs, cx)), 1, H, W, cx + ch, ch, _ptr(w[f"cell{cell_index}.wtc"]),
+                                               _ptr(w[f"cell{cell_index}.b"]), _ptr(h_pair), _ptr(cs), 1, None, _stream(dev)),
+                   "aarmvs_convlstm_cell_tc")
+    else:
+        capi.check(lib.aarmvs_convlstm_cell(_src_array(_src(xs, cx)), 1, H, W, cx + ch, ch, _ptr(w[f"cell{cell_index}.w"]),
+                                            _ptr(w[f"cell{cell_index}.b"]), _ptr(h_pair), _ptr(cs), 1, None, _stream(dev)),
+                   "aarmvs_convlstm_cell")
     return _nchw(h_pair[1], H, W), _nchw(cs, H, W)
 
 

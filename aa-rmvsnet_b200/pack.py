@@ -28,6 +28,20 @@ def lstm_gates(w, b):
     return conv_taps(w[perm]), b[perm].contiguous()
 
 
+def lstm_gates_f16(w, b):
+    """Tensor-core operand of a ConvLSTM cell: [2 planes hi,lo][9][cin_pad/8][4*hidden][8] fp16 (K-major 16-byte chunks of
+    8 input channels, cin padded with zero rows to a multiple of 16) + the fp32 bias, gate order as lstm_gates()."""
+    taps, bias = lstm_gates(w, b)                    # [9][cin][n] fp32
+    _, cin, n = taps.shape
+    cin_pad = (cin + 15) // 16 * 16
+    full = taps.new_zeros(9, cin_pad, n)
+    full[:, :cin] = taps
+    chunks = full.view(9, cin_pad // 8, 8, n).permute(0, 1, 3, 2).contiguous()      # [9][kc8][n][8]
+    hi = chunks.half()
+    lo = (chunks - hi.float()).half()
+    return torch.stack([hi, lo]).contiguous(), bias
+
+
 def deconv_taps(w):
     """nn.ConvTranspose2d weight [cin][cout][kh][kw] -> [kh][kw][cin][cout]."""
     return w.permute(2, 3, 0, 1).contiguous()

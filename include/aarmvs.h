@@ -113,6 +113,15 @@ int aarmvs_convlstm_cell(const aarmvs_conv_src* src, int nsrc, int H, int W, int
                          const float* weight_packed, const float* bias_packed, float* h_pair, float* c_state,
                          int d_host, const int* d_dev, void* stream);
 
+/* The same cell on the tensor cores (tcgen05.mma kind::f16, fp32 accumulation in TMEM).  fp32 operands are split
+ * on the fly into fp16 (hi, lo) pairs and each K step issues hi*hi + lo*hi + hi*lo, which keeps ~2^-21 relative
+ * accuracy per product (single-pass TF32 / BF16 fails the parity bar).  Same arguments as
+ * aarmvs_convlstm_cell except weight_f16: [2 planes hi,lo][9 taps][cin_pad/8][4*hidden][8] fp16 with cin_pad = cin
+ * rounded up to 16 (zero rows) and the output-channel order [hidden channel][i,f,o,g]; source channels multiples of 8. */
+int aarmvs_convlstm_cell_tc(const aarmvs_conv_src* src, int nsrc, int H, int W, int cin, int hidden,
+                            const void* weight_f16, const float* bias_packed, float* h_pair, float* c_state,
+                            int d_host, const int* d_dev, void* stream);
+
 /* deConvGnReLU's ConvTranspose2d(16,16,k3,s2,p1,op1) (models/module.py:281): in [Hin][Win][16] (one conv source,
  * typically a ping-pong h) -> pre-norm out [2Hin][2Win][16] + GroupNorm sums (2 groups).
  * weight: [3][3][16 cin][16 cout] repack of ConvTranspose2d's [cin][cout][kh][kw]. */

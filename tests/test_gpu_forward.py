@@ -22,10 +22,10 @@ def _model(g, return_depth=True, **kw):
 
 
 @pytest.mark.parametrize("name", CASES)
-@pytest.mark.parametrize("use_graph", [True, False])
-def test_forward_matches_reference(name, use_graph):
+@pytest.mark.parametrize("use_graph,cell_math", [(True, "tc"), (False, "tc"), (True, "fma")])
+def test_forward_matches_reference(name, use_graph, cell_math):
     g = load_golden(name)
-    m = _model(g, use_graph=use_graph)
+    m = _model(g, use_graph=use_graph, cell_math=cell_math)
     for _ in range(2):           # second call replays the captured plane graph
         out = m(g["imgs"].cuda(), g["proj_matrices"].cuda(), g["depth_values"].cuda())
     idx, want = out["index"].cpu().long(), g["index"].long()

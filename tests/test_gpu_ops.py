@@ -61,10 +61,12 @@ def test_deform_conv(ops_dtu, model):
     torch.testing.assert_close(big, ops_dtu["deform_big_out"][0], rtol=1e-4, atol=5e-4)
 
 
-def test_convlstm_cell(ops_dtu, model):
+@pytest.mark.parametrize("math", ["tc", "fma"])
+def test_convlstm_cell(ops_dtu, model, math):
+    """tc: tcgen05 implicit GEMM with split-fp16 operands; fma: fp32 CUDA-core kernel.  Same tolerance for both."""
     from aarmvsnet_b200 import ops
     g = ops_dtu
-    h, c = ops.convlstm_cell(model, 0, g["cell_x"][0].cuda(), g["cell_h"][0].cuda(), g["cell_c"][0].cuda())
+    h, c = ops.convlstm_cell(model, 0, g["cell_x"][0].cuda(), g["cell_h"][0].cuda(), g["cell_c"][0].cuda(), math=math)
     torch.testing.assert_close(h.cpu(), g["cell_h_out"][0], rtol=1e-5, atol=2e-5)
     torch.testing.assert_close(c.cpu(), g["cell_c_out"][0], rtol=1e-5, atol=2e-5)
 
