@@ -1,0 +1,235 @@
+// Pass A of the plane sweep on the tensor cores (models/module.py:6-38,
+// models/drmvsnet.py:31,311): for every source view, bilinear gather at depth d, c = (warp - ref)^2, and the omega
+// stem 3x3 conv 32 -> 4 as a tcgen05 implicit GEMM over the staged (warp - ref)^2 halo tile.
+//
+// Same tile / operand scheme as convlstm_tc.cu: 16 x 8 pixel tiles = the 128 accumulator rows, halo tile 18 x 10
+// staged once as un-swizzled K-major fp16 (hi, lo) planes [8-channel chunk][pixel][16 B]; a 3x3 tap is a start-address
+// shift.  N = 16 accumulator columns (4 real output channels; tcgen05 needs N % 16 == 0 at M = 128).
+// The gather is the expensive part (4 taps + ref = five 128-byte lines per pixel and view): 12 loader warps, 8 lanes per
+// pixel (one 128-byte line per tap and 8-lane group), sample positions computed once per pixel into shared memory.
+// Roles: warps 0-3 epilogue (TMEM -> +bias -> t0, GroupNorm-1 sums), warp 4 TMEM + MMA issue, warps 5-16 loaders.
+#include "common.cuh"
+#include "tc_common.cuh"
+#include "../../include/aarmvs.h"
+
+namespace {
+
+constexpr int TR = 16, TCOL = 8, HR = 18, HC = 10, NPX = HR * HC;        // 180 staged pixels
+constexpr int N_EPI = 4, MMA_WARP = 4, FIRST_LOAD = 5, N_LOAD = 12;
+constexpr int N_THREADS = (N_EPI + 1 + N_LOAD) * 32;                     // 544
+constexpr int LOAD_THREADS = N_LOAD * 32;                                // 384
+constexpr int N_STAGES = 4;
+constexpr int KC8 = 4, NCOLS = 16;
+constexpr int A_PLANE = KC8 * NPX * 16, A_STAGE = 2 * A_PLANE;           // 11520, 23040 bytes
+constexpr int B_PLANE = 9 * KC8 * NCOLS * 16, B_BYTES = 2 * B_PLANE;     // 9216, 18432 bytes
+constexpr int TAP_BYTES = NPX * 32;                                      // one Taps record (32 B) per staged pixel
+constexpr int SMEM = B_BYTES + N_STAGES * (A_STAGE + TAP_BYTES) + 1024;
+
+struct StemArgs {
+    const float* ref;
+    const float* src;
+    size_t view_stride;
+    int H, W, S;
+    const float* cams;
+    const __half* weight;       // [2][9][4][16][8] fp16
+    float bias[4];
+    const float* depth_values;
+    int d_host;
+    const int* d_dev;
+    int align_corners;
+    float* t0;
+    double* stats;
+};
+
+__device__ __forceinline__ uint32_t pack_h2(__half a, __half b) {
+    return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16);
+}
+
+__global__ void __launch_bounds__(N_THREADS, 1) cost_stem_tc_kernel(const __grid_constant__ StemArgs a) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    unsigned char* sB = smem;
+    unsigned char* sA = smem + B_BYTES;
+    unsigned char* sT = sA + N_STAGES * A_STAGE;
+    __shared__ uint64_t full_a[N_STAGES], empty_a[N_STAGES], tmem_full[2], tmem_empty[2];
+    __shared__ uint32_t tmem_base_s;
+    __shared__ float scam[AARMVS_MAX_SRC * 12];
+    __shared__ double sstat[AARMVS_MAX_SRC * 2];
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const float depth = a.depth_values[plane_index(a.d_host, a.d_dev)];
+
+    for (int i = tid; i < B_BYTES / 16; i += N_THREADS)
+        reinterpret_cast<uint4*>(sB)[i] = __ldg(reinterpret_cast<const uint4*>(a.weight) + i);
+    for (int i = tid; i < a.S * 12; i += N_THREADS) scam[i] = a.cams[i];
+    for (int i = tid; i < a.S * 2; i += N_THREADS) sstat[i] = 0.0;
+    if (tid == 0) {
+        for (int s = 0; s < N_STAGES; ++s) { tc::mbar_init(&full_a[s], LOAD_THREADS); tc::mbar_init(&empty_a[s], 1); }
+        for (int b = 0; b < 2; ++b) { tc::mbar_init(&tmem_full[b], 1); tc::mbar_init(&tmem_empty[b], N_EPI * 32); }
+        tc::mbar_fence_init();
+    }
+    if (warp == MMA_WARP) tc::tmem_alloc<32>(&tmem_base_s);
+    tc::fence_async_smem();
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+
+    const int tiles_x = (a.W + TCOL - 1) / TCOL, tiles_y = (a.H + TR - 1) / TR;
+    const int ntiles = tiles_x * tiles_y;
+    const size_t P = (size_t)a.H * a.W;
+
+    if (warp >= FIRST_LOAD) {
+        // =========================================== loaders: gather + (warp - ref)^2 + fp16 split ==================
+        const int lt = tid - FIRST_LOAD * 32;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+            const int y0 = ty * TR - 1, x0 = tx * TCOL - 1;
+            for (int v = 0; v < a.S; ++v, ++it) {
+                const int st = it % N_STAGES;
+                tc::mbar_wait(&empty_a[st], ((it / N_STAGES) & 1) ^ 1);
+                unsigned char* stage = sA + st * A_STAGE;
+                Taps* taps = reinterpret_cast<Taps*>(sT + st * TAP_BYTES);
+                // phase 1: one thread per staged pixel evaluates the homography and the bilinear tap set
+                if (lt < NPX) {
+                    const int r = lt / HC, cc = lt - r * HC;
+                    const int y = y0 + r, x = x0 + cc;
+                    Taps t;
+                    t.o_nw = t.o_ne = t.o_sw = t.o_se = -2;          // -2: pixel outside the image -> cost 0 (conv padding)
+                    t.w_nw = t.w_ne = t.w_sw = t.w_se = 0.f;
+                    if (y >= 0 && y < a.H && x >= 0 && x < a.W) {
+                        float ix, iy;
+                        sweep_position(scam + v * 12, (float)x, (float)y, depth, a.W, a.H, a.align_corners != 0, ix, iy);
+                        t = make_taps(ix, iy, a.W, a.H);
+                    }
+                    taps[lt] = t;
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(LOAD_THREADS) : "memory");
+                // phase 2: 8 lanes per pixel, 4 channels per lane
+                const float* sv = a.src + (size_t)v * a.view_stride;
+#pragma unroll 4
+                for (int i = lt; i < NPX * 8; i += LOAD_THREADS) {
+                    const int px = i >> 3, c4 = i & 7;
+                    const Taps t = taps[px];
+                    float4 cv = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (t.o_nw != -2) {
+                        const int r = px / HC, cc = px - r * HC;
+                        const float4 wv = gather_taps(sv, t, c4);
+                        const float4 rv = ldg4(a.ref + ((size_t)(y0 + r) * a.W + (x0 + cc)) * 32 + c4 * 4);
+                        const float dx = wv.x - rv.x, dy = wv.y - rv.y, dz = wv.z - rv.z, dw = wv.w - rv.w;
+                        cv = make_float4(dx * dx, dy * dy, dz * dz, dw * dw);
+                    }
+                    __half h0, h1, h2, h3, l0, l1, l2, l3;
+                    tc::split_f16(cv.x, h0, l0); tc::split_f16(cv.y, h1, l1);
+                    tc::split_f16(cv.z, h2, l2); tc::split_f16(cv.w, h3, l3);
+                    const size_t off = ((size_t)(c4 >> 1) * NPX + px) * 16 + (c4 & 1) * 8;
+                    *reinterpret_cast<uint2*>(stage + off) = make_uint2(pack_h2(h0, h1), pack_h2(h2, h3));
+                    *reinterpret_cast<uint2*>(stage + A_PLANE + off) = make_uint2(pack_h2(l0, l1), pack_h2(l2, l3));
+                }
+                tc::fence_async_smem();
+                tc::mbar_arrive(&full_a[st]);
+            }
+        }
+    } else if (warp == MMA_WARP) {
+        // =========================================== MMA issuer ===========================================
+        if (lane == 0) {
+            const uint32_t idesc = tc::idesc_f16_f32(128, NCOLS);
+            const uint32_t a_base = tc::smem_u32(sA), b_base = tc::smem_u32(sB);
+            const int total = ((ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x) * a.S;
+            for (int it = 0; it < total; ++it) {
+                const int st = it % N_STAGES, ab = it & 1;
+                tc::mbar_wait(&full_a[st], (it / N_STAGES) & 1);
+                tc::mbar_wait(&tmem_empty[ab], ((it >> 1) & 1) ^ 1);
+                tc::tc_fence_after();
+                const uint32_t dst = tmem_base + ab * NCOLS;
+                const uint32_t a_hi = a_base + st * A_STAGE, a_lo = a_hi + A_PLANE;
+                uint32_t first = 0;
+#pragma unroll 1
+                for (int tap = 0; tap < 9; ++tap) {
+                    const uint32_t a_off = (uint32_t)((tap / 3) * HC + (tap % 3)) * 16;
+#pragma unroll
+                    for (int ks = 0; ks < 2; ++ks) {
+                        const uint32_t ak = (uint32_t)(2 * ks) * NPX * 16 + a_off;
+                        const uint32_t bk = (uint32_t)((tap * KC8 + 2 * ks) * NCOLS) * 16;
+                        const uint64_t da_hi = tc::smem_desc(a_hi + ak, NPX * 16, HC * 16);
+                        const uint64_t da_lo = tc::smem_desc(a_lo + ak, NPX * 16, HC * 16);
+                        const uint64_t db_hi = tc::smem_desc(b_base + bk, NCOLS * 16, 8 * 16);
+                        const uint64_t db_lo = tc::smem_desc(b_base + B_PLANE + bk, NCOLS * 16, 8 * 16);
+                        tc::mma_f16(dst, da_lo, db_hi, idesc, first);
+                        first = 1;
+                        tc::mma_f16(dst, da_hi, db_lo, idesc, 1);
+                        tc::mma_f16(dst, da_hi, db_hi, idesc, 1);
+                    }
+                }
+                tc::mma_commit(&empty_a[st]);
+                tc::mma_commit(&tmem_full[ab]);
+            }
+        }
+    } else {
+        // =========================================== epilogue: t0 + GroupNorm-1 sums ==============================
+        const int m = warp * 32 + lane;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+            const int y = ty * TR + (m >> 3), x = tx * TCOL + (m & 7);
+            const bool valid = y < a.H && x < a.W;
+            for (int v = 0; v < a.S; ++v, ++it) {
+                const int ab = it & 1;
+                tc::mbar_wait(&tmem_full[ab], (it >> 1) & 1);
+                tc::tc_fence_after();
+                uint32_t r0, r1, r2, r3;
+                asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                             : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+                             : "r"(tmem_base + ((uint32_t)(warp * 32) << 16) + ab * NCOLS)
+                             : "memory");
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                tc::tc_fence_before();
+                tc::mbar_arrive(&tmem_empty[ab]);
+                float4 o = make_float4(__uint_as_float(r0) + a.bias[0], __uint_as_float(r1) + a.bias[1],
+                                       __uint_as_float(r2) + a.bias[2], __uint_as_float(r3) + a.bias[3]);
+                float s = 0.f, ss = 0.f;
+                if (valid) {
+                    st4(a.t0 + ((size_t)v * P + (size_t)y * a.W + x) * 4, o);
+                    s = (o.x + o.y) + (o.z + o.w);
+                    ss = (o.x * o.x + o.y * o.y) + (o.z * o.z + o.w * o.w);
+                }
+                double ds = warp_sum((double)s), dss = warp_sum((double)ss);
+                if (lane == 0) {
+                    atomicAdd(&sstat[v * 2 + 0], ds);
+                    atomicAdd(&sstat[v * 2 + 1], dss);
+                }
+            }
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == MMA_WARP) tc::tmem_dealloc<32>(tmem_base);
+    if (tid < a.S * 2) atomicAdd(a.stats + (tid >> 1) * 6 + (tid & 1), sstat[tid]);      // stats[v][GN1][sum, sumsq]
+}
+
+}  // namespace
+
+extern "C" int aarmvs_cost_stem_tc(const float* ref, const float* src, size_t view_stride, int H, int W, int S,
+                                   const float* cams, const void* stem_w_f16, const float* stem_b_host,
+                                   const float* depth_values, int d_host, const int* d_dev, int align_corners, float* t0,
+                                   double* stats, void* stream) {
+    AARMVS_CHECK_ARG(ref && src && t0 && stats && stem_w_f16 && stem_b_host && depth_values && cams && H > 0 && W > 0);
+    AARMVS_CHECK_ARG(S >= 1 && S <= AARMVS_MAX_SRC);
+    StemArgs a = {};
+    a.ref = ref; a.src = src; a.view_stride = view_stride; a.H = H; a.W = W; a.S = S; a.cams = cams;
+    a.weight = (const __half*)stem_w_f16;
+    for (int i = 0; i < 4; ++i) a.bias[i] = stem_b_host[i];
+    a.depth_values = depth_values; a.d_host = d_host; a.d_dev = d_dev; a.align_corners = align_corners; a.t0 = t0;
+    a.stats = stats;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(cost_stem_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+        if (e != cudaSuccess) return (int)e;
+        attr_set = true;
+    }
+    const int ntiles = ((W + TCOL - 1) / TCOL) * ((H + TR - 1) / TR);
+    const int sms = aarmvs_sm_count();
+    if (sms <= 0) return AARMVS_ERR_ARG;
+    cost_stem_tc_kernel<<<ntiles < sms ? ntiles : sms, N_THREADS, SMEM, (cudaStream_t)stream>>>(a);
+    AARMVS_LAUNCH_RESULT();
+}

@@ -96,6 +96,7 @@ class Engine:
         om = "omega.reweight_network"
         w["stem.w_host"] = capi.host_floats(pack.conv_taps(sd[om + ".0.0.weight"]).reshape(-1).cpu().tolist())
         w["stem.b_host"] = capi.host_floats(sd[om + ".0.0.bias"].cpu().tolist())
+        w["stem.wtc"] = pack.taps_f16(pack.conv_taps(sd[om + ".0.0.weight"]), n_pad=16)
         tail = pack.omega_tail(sd)
         assert tail.numel() == self.lib.aarmvs_omega_tail_floats()
         w["tail_host"] = capi.host_floats(tail.tolist())
@@ -194,6 +195,16 @@ class Engine:
                                             _ptr(g1[0]), _ptr(g1[1]), _ptr(g2[0]), _ptr(g2[1]), H, W, _ptr(out), stream),
                    "aarmvs_feat_assemble")
 
+    def cost_stem(self, ref, src, view_stride, H, W, S, cams, w, depths, d_host, dptr, t0, sums, stream):
+        """Pass A (gather, (warp - ref)^2, omega stem conv) on the tensor cores ('tc') or the fp32 FMA pipe ('fma')."""
+        ac = int(self.align_corners)
+        if self.cell_math == "tc":
+            capi.check(self.lib.aarmvs_cost_stem_tc(ref, src, view_stride, H, W, S, cams, _ptr(w["stem.wtc"]), w["stem.b_host"],
+                                                    depths, d_host, dptr, ac, t0, sums, stream), "aarmvs_cost_stem_tc")
+        else:
+            capi.check(self.lib.aarmvs_cost_stem(ref, src, view_stride, H, W, S, cams, w["stem.w_host"], w["stem.b_host"],
+                                                 depths, d_host, dptr, ac, t0, sums, stream), "aarmvs_cost_stem")
+
     # ------------------------------------------------------------------------------------------ one plane
     def _plane(self, ws, w, stream, marks=None):
         """Enqueue the kernel chain of one depth plane; the plane index is read from ws['plane'] on the device.
@@ -211,8 +222,7 @@ class Engine:
         feat, dptr, ac = ws["feat"], _ptr(ws["plane"]), int(self.align_corners)
         ref, src = _ptr(feat), _ptr(feat, P * 32)
         ps = ws["psums"]
-        capi.check(lib.aarmvs_cost_stem(ref, src, P * 32, H, W, S, _ptr(ws["cams"]), w["stem.w_host"], w["stem.b_host"],
-                                        _ptr(ws["depths"]), 0, dptr, ac, _ptr(ws["t0"]), _ptr(ps), stream), "aarmvs_cost_stem")
+        self.cost_stem(ref, src, P * 32, H, W, S, _ptr(ws["cams"]), w, _ptr(ws["depths"]), 0, dptr, _ptr(ws["t0"]), _ptr(ps), stream)
         mark("cost_stem")
         for stage in (2, 3):
             capi.check(lib.aarmvs_omega_stats(stage, _ptr(ws["t0"]), H, W, S, w["tail_host"], _ptr(ps), stream),

@@ -32,14 +32,21 @@ def lstm_gates_f16(w, b):
     """Tensor-core operand of a ConvLSTM cell: [2 planes hi,lo][9][cin_pad/8][4*hidden][8] fp16 (K-major 16-byte chunks of
     8 input channels, cin padded with zero rows to a multiple of 16) + the fp32 bias, gate order as lstm_gates()."""
     taps, bias = lstm_gates(w, b)                    # [9][cin][n] fp32
-    _, cin, n = taps.shape
+    return taps_f16(taps), bias
+
+
+def taps_f16(taps, n_pad=None):
+    """[9][cin][n] fp32 tap-major weights -> tcgen05 B operand [2 planes hi,lo][9][cin_pad/8][n_pad][8] fp16
+    (un-swizzled K-major: 16-byte chunks of 8 input channels; cin padded to a multiple of 16, n to n_pad, with zeros)."""
+    k, cin, n = taps.shape
     cin_pad = (cin + 15) // 16 * 16
-    full = taps.new_zeros(9, cin_pad, n)
-    full[:, :cin] = taps
-    chunks = full.view(9, cin_pad // 8, 8, n).permute(0, 1, 3, 2).contiguous()      # [9][kc8][n][8]
+    n_pad = n_pad or n
+    full = taps.new_zeros(k, cin_pad, n_pad)
+    full[:, :cin, :n] = taps
+    chunks = full.view(k, cin_pad // 8, 8, n_pad).permute(0, 1, 3, 2).contiguous()      # [9][kc8][n][8]
     hi = chunks.half()
     lo = (chunks - hi.float()).half()
-    return torch.stack([hi, lo]).contiguous(), bias
+    return torch.stack([hi, lo]).contiguous()
 
 
 def deconv_taps(w):

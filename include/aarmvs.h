@@ -90,6 +90,13 @@ int aarmvs_cost_stem(const float* ref, const float* src, size_t view_stride, int
                      const float* stem_w_host, const float* stem_b_host, const float* depth_values, int d_host,
                      const int* d_dev, int align_corners, float* t0, double* stats, void* stream);
 
+/* Pass A with the 3x3 stem conv on the tensor cores (tcgen05 implicit GEMM over the staged (warp - ref)^2 halo tile,
+ * split-fp16 operands, fp32 accumulation in TMEM).  Arguments as aarmvs_cost_stem except
+ * stem_w_f16: DEVICE [2 planes hi,lo][9 taps][4][16][8] fp16 (output channels padded 4 -> 16 with zeros). */
+int aarmvs_cost_stem_tc(const float* ref, const float* src, size_t view_stride, int H, int W, int S, const float* cams,
+                        const void* stem_w_f16, const float* stem_b_host, const float* depth_values, int d_host,
+                        const int* d_dev, int align_corners, float* t0, double* stats, void* stream);
+
 /* Pass B (stage 2) / pass C (stage 3): GroupNorm-2 / GroupNorm-3 sums of the omega residual block
  * (models/module.py:256-258) recomputed point-wise from t0.  tail_host: aarmvs_omega_tail_floats() floats. */
 int aarmvs_omega_stats(int stage, const float* t0, int H, int W, int S, const float* tail_host, double* stats,

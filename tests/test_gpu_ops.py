@@ -71,8 +71,18 @@ def test_convlstm_cell(ops_dtu, model, math):
     torch.testing.assert_close(c.cpu(), g["cell_c_out"][0], rtol=1e-5, atol=2e-5)
 
 
+@pytest.fixture(scope="module")
+def model_fma():
+    import aarmvsnet_b200 as aa
+    m = aa.EMVSNet(disparity_level=32, image_scale=1.0, max_h=32, max_w=40, return_depth=True, cell_math="fma")
+    m.load_state_dict(load_weights("model_dtu_v2.ckpt"), strict=True)
+    return m.cuda().eval()
+
+
+@pytest.mark.parametrize("math", ["tc", "fma"])
 @pytest.mark.parametrize("hw", [(32, 40), (36, 52), (20, 100)])
-def test_aggregate_plane_and_omega(ops_dtu, sd_dtu, model, hw):
+def test_aggregate_plane_and_omega(ops_dtu, sd_dtu, model, model_fma, hw, math):
+    model = model if math == "tc" else model_fma
     """warp + (warp-ref)^2 + omega + weighted sum, against the oracle, incl. sizes that do not fill the 16x32 tiles."""
     from aarmvsnet_b200 import ops, synth
     h, w = hw
