@@ -156,12 +156,19 @@ __global__ void __launch_bounds__(N_THREADS, 1) convlstm_tc_kernel(const __grid_
             const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
             const int y0 = ty * TR - 1, x0 = tx * TCOL - 1;
             unsigned char* stage = sA + st * C::A_STAGE;
-            for (int idx = lt; idx < C::KC8 * NPX; idx += N_LOAD_WARPS * 32) {
+            // two sweeps so that all global loads of this thread are in flight before the first conversion / store
+            constexpr int ITEMS = (C::KC8 * NPX + N_LOAD_WARPS * 32 - 1) / (N_LOAD_WARPS * 32);
+            float v[ITEMS][8];
+#pragma unroll
+            for (int k = 0; k < ITEMS; ++k) {
+                const int idx = lt + k * N_LOAD_WARPS * 32;
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[k][e] = 0.f;
+                if (idx >= C::KC8 * NPX) continue;
                 const int kc = idx / NPX, px = idx - kc * NPX;
                 const int r = px / HC, cc = px - r * HC;
                 const int y = y0 + r, x = x0 + cc;
                 const int c = kc * 8;
-                float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
                 if (y >= 0 && y < a.H && x >= 0 && x < a.W && c < sbase[a.nsrc]) {
                     const int s = c < sbase[1] ? 0 : (c < sbase[2] ? 1 : 2);
                     const TcSrc& S = a.src[s];
@@ -174,27 +181,32 @@ __global__ void __launch_bounds__(N_THREADS, 1) convlstm_tc_kernel(const __grid_
                         const float* p = sp + (size_t)(2 * y) * rowp + (size_t)(2 * x) * S.ch + cl;
 #pragma unroll
                         for (int hh = 0; hh < 2; ++hh) {
-                            const float4 q0 = ld4(p + hh * 4), q1 = ld4(p + S.ch + hh * 4), q2 = ld4(p + rowp + hh * 4),
-                                         q3 = ld4(p + rowp + S.ch + hh * 4);
-                            v[hh * 4 + 0] = fmaxf(fmaxf(q0.x, q1.x), fmaxf(q2.x, q3.x));
-                            v[hh * 4 + 1] = fmaxf(fmaxf(q0.y, q1.y), fmaxf(q2.y, q3.y));
-                            v[hh * 4 + 2] = fmaxf(fmaxf(q0.z, q1.z), fmaxf(q2.z, q3.z));
-                            v[hh * 4 + 3] = fmaxf(fmaxf(q0.w, q1.w), fmaxf(q2.w, q3.w));
+                            const float4 q0 = ldg4(p + hh * 4), q1 = ldg4(p + S.ch + hh * 4), q2 = ldg4(p + rowp + hh * 4),
+                                         q3 = ldg4(p + rowp + S.ch + hh * 4);
+                            v[k][hh * 4 + 0] = fmaxf(fmaxf(q0.x, q1.x), fmaxf(q2.x, q3.x));
+                            v[k][hh * 4 + 1] = fmaxf(fmaxf(q0.y, q1.y), fmaxf(q2.y, q3.y));
+                            v[k][hh * 4 + 2] = fmaxf(fmaxf(q0.z, q1.z), fmaxf(q2.z, q3.z));
+                            v[k][hh * 4 + 3] = fmaxf(fmaxf(q0.w, q1.w), fmaxf(q2.w, q3.w));
                         }
                     } else {
                         const float* p = sp + ((size_t)y * a.W + x) * S.ch + cl;
-                        const float4 q0 = ld4(p), q1 = ld4(p + 4);
-                        v[0] = q0.x; v[1] = q0.y; v[2] = q0.z; v[3] = q0.w;
-                        v[4] = q1.x; v[5] = q1.y; v[6] = q1.z; v[7] = q1.w;
+                        const float4 q0 = ldg4(p), q1 = ldg4(p + 4);
+                        v[k][0] = q0.x; v[k][1] = q0.y; v[k][2] = q0.z; v[k][3] = q0.w;
+                        v[k][4] = q1.x; v[k][5] = q1.y; v[k][6] = q1.z; v[k][7] = q1.w;
                         if (S.mode == AARMVS_SRC_GN_RELU) {
 #pragma unroll
-                            for (int e = 0; e < 8; ++e) v[e] = fmaxf(fmaf(v[e], s_scale[c + e], s_shift[c + e]), 0.f);
+                            for (int e = 0; e < 8; ++e) v[k][e] = fmaxf(fmaf(v[k][e], s_scale[c + e], s_shift[c + e]), 0.f);
                         }
                     }
                 }
+            }
+#pragma unroll
+            for (int k = 0; k < ITEMS; ++k) {
+                const int idx = lt + k * N_LOAD_WARPS * 32;
+                if (idx >= C::KC8 * NPX) continue;
                 __half hi[8], lo[8];
 #pragma unroll
-                for (int e = 0; e < 8; ++e) tc::split_f16(v[e], hi[e], lo[e]);
+                for (int e = 0; e < 8; ++e) tc::split_f16(v[k][e], hi[e], lo[e]);
                 const uint4 uh = make_uint4(pack_h2(hi[0], hi[1]), pack_h2(hi[2], hi[3]), pack_h2(hi[4], hi[5]), pack_h2(hi[6], hi[7]));
                 const uint4 ul = make_uint4(pack_h2(lo[0], lo[1]), pack_h2(lo[2], lo[3]), pack_h2(lo[4], lo[5]), pack_h2(lo[6], lo[7]));
                 *reinterpret_cast<uint4*>(stage + (size_t)idx * 16) = uh;

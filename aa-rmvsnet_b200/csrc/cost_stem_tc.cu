@@ -80,55 +80,89 @@ __global__ void __launch_bounds__(N_THREADS, 1) cost_stem_tc_kernel(const __grid
 
     if (warp >= FIRST_LOAD) {
         // =========================================== loaders: gather + (warp - ref)^2 + fp16 split ==================
+        // Software pipeline: the tap sets of fill it+1 are computed (one thread per staged pixel) while the loads of
+        // fill it are in flight; the gather itself is branch-free (out-of-image taps read a valid dummy line with
+        // weight 0) and issues the loads of two pixels x five lines before the first use.
         const int lt = tid - FIRST_LOAD * 32;
-        int it = 0;
-        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int my_tiles = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+        const int total = my_tiles * a.S;
+
+        auto compute_taps = [&](int it) {          // fill `it` -> tap slot it % N_STAGES
+            if (lt < NPX && it < total) {
+                const int tile = blockIdx.x + (it / a.S) * gridDim.x, v = it % a.S;
+                const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+                const int r = lt / HC, cc = lt - r * HC;
+                const int y = ty * TR - 1 + r, x = tx * TCOL - 1 + cc;
+                Taps t;
+                t.o_nw = t.o_ne = t.o_sw = t.o_se = -2;      // -2: pixel outside the image -> cost 0 (the conv's zero padding)
+                t.w_nw = t.w_ne = t.w_sw = t.w_se = 0.f;
+                if (y >= 0 && y < a.H && x >= 0 && x < a.W) {
+                    float ix, iy;
+                    sweep_position(scam + v * 12, (float)x, (float)y, depth, a.W, a.H, a.align_corners != 0, ix, iy);
+                    t = make_taps(ix, iy, a.W, a.H);
+                }
+                reinterpret_cast<Taps*>(sT + (it % N_STAGES) * TAP_BYTES)[lt] = t;
+            }
+        };
+
+        compute_taps(0);
+        asm volatile("bar.sync 1, %0;" ::"n"(LOAD_THREADS) : "memory");
+        for (int it = 0; it < total; ++it) {
+            const int tile = blockIdx.x + (it / a.S) * gridDim.x, v = it % a.S;
             const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
             const int y0 = ty * TR - 1, x0 = tx * TCOL - 1;
-            for (int v = 0; v < a.S; ++v, ++it) {
-                const int st = it % N_STAGES;
-                tc::mbar_wait(&empty_a[st], ((it / N_STAGES) & 1) ^ 1);
-                unsigned char* stage = sA + st * A_STAGE;
-                Taps* taps = reinterpret_cast<Taps*>(sT + st * TAP_BYTES);
-                // phase 1: one thread per staged pixel evaluates the homography and the bilinear tap set
-                if (lt < NPX) {
-                    const int r = lt / HC, cc = lt - r * HC;
-                    const int y = y0 + r, x = x0 + cc;
-                    Taps t;
-                    t.o_nw = t.o_ne = t.o_sw = t.o_se = -2;          // -2: pixel outside the image -> cost 0 (conv padding)
-                    t.w_nw = t.w_ne = t.w_sw = t.w_se = 0.f;
-                    if (y >= 0 && y < a.H && x >= 0 && x < a.W) {
-                        float ix, iy;
-                        sweep_position(scam + v * 12, (float)x, (float)y, depth, a.W, a.H, a.align_corners != 0, ix, iy);
-                        t = make_taps(ix, iy, a.W, a.H);
-                    }
-                    taps[lt] = t;
-                }
-                asm volatile("bar.sync 1, %0;" ::"n"(LOAD_THREADS) : "memory");
-                // phase 2: 8 lanes per pixel, 4 channels per lane
-                const float* sv = a.src + (size_t)v * a.view_stride;
-#pragma unroll 4
-                for (int i = lt; i < NPX * 8; i += LOAD_THREADS) {
+            const int st = it % N_STAGES;
+            tc::mbar_wait(&empty_a[st], ((it / N_STAGES) & 1) ^ 1);
+            unsigned char* stage = sA + st * A_STAGE;
+            const Taps* taps = reinterpret_cast<const Taps*>(sT + st * TAP_BYTES);
+            const float* sv = a.src + (size_t)v * a.view_stride;
+#pragma unroll
+            for (int batch = 0; batch < 2; ++batch) {
+                float4 ta[2], tb[2], tcn[2], td[2], rv[2];
+                float w0[2], w1[2], w2[2], w3[2];
+                bool inimg[2];
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const int i = min(lt + (batch * 2 + j) * LOAD_THREADS, NPX * 8 - 1);
                     const int px = i >> 3, c4 = i & 7;
                     const Taps t = taps[px];
-                    float4 cv = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (t.o_nw != -2) {
-                        const int r = px / HC, cc = px - r * HC;
-                        const float4 wv = gather_taps(sv, t, c4);
-                        const float4 rv = ldg4(a.ref + ((size_t)(y0 + r) * a.W + (x0 + cc)) * 32 + c4 * 4);
-                        const float dx = wv.x - rv.x, dy = wv.y - rv.y, dz = wv.z - rv.z, dw = wv.w - rv.w;
-                        cv = make_float4(dx * dx, dy * dy, dz * dz, dw * dw);
-                    }
-                    __half h0, h1, h2, h3, l0, l1, l2, l3;
-                    tc::split_f16(cv.x, h0, l0); tc::split_f16(cv.y, h1, l1);
-                    tc::split_f16(cv.z, h2, l2); tc::split_f16(cv.w, h3, l3);
-                    const size_t off = ((size_t)(c4 >> 1) * NPX + px) * 16 + (c4 & 1) * 8;
-                    *reinterpret_cast<uint2*>(stage + off) = make_uint2(pack_h2(h0, h1), pack_h2(h2, h3));
-                    *reinterpret_cast<uint2*>(stage + A_PLANE + off) = make_uint2(pack_h2(l0, l1), pack_h2(l2, l3));
+                    inimg[j] = t.o_nw != -2;
+                    w0[j] = t.o_nw >= 0 ? t.w_nw : 0.f; w1[j] = t.o_ne >= 0 ? t.w_ne : 0.f;
+                    w2[j] = t.o_sw >= 0 ? t.w_sw : 0.f; w3[j] = t.o_se >= 0 ? t.w_se : 0.f;
+                    ta[j] = ldg4(sv + (size_t)max(t.o_nw, 0) * 32 + c4 * 4);
+                    tb[j] = ldg4(sv + (size_t)max(t.o_ne, 0) * 32 + c4 * 4);
+                    tcn[j] = ldg4(sv + (size_t)max(t.o_sw, 0) * 32 + c4 * 4);
+                    td[j] = ldg4(sv + (size_t)max(t.o_se, 0) * 32 + c4 * 4);
+                    const int r = px / HC, cc = px - r * HC;
+                    const size_t rp = inimg[j] ? (size_t)(y0 + r) * a.W + (x0 + cc) : 0;
+                    rv[j] = ldg4(a.ref + rp * 32 + c4 * 4);
                 }
-                tc::fence_async_smem();
-                tc::mbar_arrive(&full_a[st]);
+                if (batch == 0) compute_taps(it + 1);        // ALU work under the loads' latency
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const int iraw = lt + (batch * 2 + j) * LOAD_THREADS;
+                    const int px = iraw >> 3, c4 = iraw & 7;
+                    // bilinear blend in ATen's order (see gather_taps); a zero weight reproduces the skipped tap exactly
+                    const float gx = __fmaf_rn(td[j].x, w3[j], __fmaf_rn(tcn[j].x, w2[j], __fmaf_rn(tb[j].x, w1[j], __fmul_rn(ta[j].x, w0[j]))));
+                    const float gy = __fmaf_rn(td[j].y, w3[j], __fmaf_rn(tcn[j].y, w2[j], __fmaf_rn(tb[j].y, w1[j], __fmul_rn(ta[j].y, w0[j]))));
+                    const float gz = __fmaf_rn(td[j].z, w3[j], __fmaf_rn(tcn[j].z, w2[j], __fmaf_rn(tb[j].z, w1[j], __fmul_rn(ta[j].z, w0[j]))));
+                    const float gw = __fmaf_rn(td[j].w, w3[j], __fmaf_rn(tcn[j].w, w2[j], __fmaf_rn(tb[j].w, w1[j], __fmul_rn(ta[j].w, w0[j]))));
+                    const float dx = gx - rv[j].x, dy = gy - rv[j].y, dz = gz - rv[j].z, dw = gw - rv[j].w;
+                    const float cx = inimg[j] ? dx * dx : 0.f, cy = inimg[j] ? dy * dy : 0.f;
+                    const float cz = inimg[j] ? dz * dz : 0.f, cw = inimg[j] ? dw * dw : 0.f;
+                    __half h0, h1, h2, h3, l0, l1, l2, l3;
+                    tc::split_f16(cx, h0, l0); tc::split_f16(cy, h1, l1);
+                    tc::split_f16(cz, h2, l2); tc::split_f16(cw, h3, l3);
+                    if (iraw < NPX * 8) {
+                        const size_t off = ((size_t)(c4 >> 1) * NPX + px) * 16 + (c4 & 1) * 8;
+                        *reinterpret_cast<uint2*>(stage + off) = make_uint2(pack_h2(h0, h1), pack_h2(h2, h3));
+                        *reinterpret_cast<uint2*>(stage + A_PLANE + off) = make_uint2(pack_h2(l0, l1), pack_h2(l2, l3));
+                    }
+                }
             }
+            tc::fence_async_smem();
+            tc::mbar_arrive(&full_a[st]);
+            asm volatile("bar.sync 1, %0;" ::"n"(LOAD_THREADS) : "memory");      // tap sets of fill it+1 are complete
         }
     } else if (warp == MMA_WARP) {
         // =========================================== MMA issuer ===========================================

@@ -216,7 +216,13 @@ __global__ void __launch_bounds__(256) omega_stats_kernel(const float* __restric
 
 // ------------------------------------------------------------------------------------------------ pass D
 // cost[p][c] = -( sum_v (omega_v(p) + 1) * (warp_v(p)[c] - ref(p)[c])^2 ) / S      (drmvsnet.py:311-319)
-// optional outputs for the operator seam: reweight [S][P].
+// optional output for the operator seam: reweight [S][P].
+// 8 lanes x float4 = one pixel; a CTA walks 8 x 16 pixel tiles so the two source rows a bilinear footprint touches are
+// shared through L1 between vertically adjacent pixels.  Lane j of a pixel's 8-lane group evaluates view j's homography,
+// tap set and omega weight once, the group reads them back with shuffles, and the taps of three views (12 lines) are
+// requested before the first is used.
+constexpr int AG_TH = 8, AG_TW = 16;
+
 __global__ void __launch_bounds__(256)
 aggregate_kernel(const float* __restrict__ ref, const float* __restrict__ src, size_t view_stride, int H, int W, int S,
                  const float* __restrict__ cams, const __grid_constant__ OmegaTail q,
@@ -236,45 +242,81 @@ aggregate_kernel(const float* __restrict__ ref, const float* __restrict__ src, s
         norms[threadIdx.x] = n;
     }
     __syncthreads();
-    const int chunk = threadIdx.x & 7;
+    const int sub = threadIdx.x & 7, grp = threadIdx.x >> 3;
     const float depth = depth_values[plane_index(d_host, d_dev)];
-    const float inv_s_den = (float)S;
-    for (size_t p = (size_t)blockIdx.x * 32 + (threadIdx.x >> 3); p < P; p += (size_t)gridDim.x * 32) {
-        const int y = (int)(p / W), x = (int)(p - (size_t)y * W);
-        const float4 rv = ldg4(ref + p * 32 + chunk * 4);
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int v0 = 0; v0 < S; v0 += 8) {
-            // lane `chunk` of the 8-lane group evaluates the reweight of view v0 + chunk, then it is broadcast
-            float wmine = 0.f;
-            if (v0 + chunk < S) {
-                const int v = v0 + chunk;
-                float a1[4], u[4], vv[4];
-                omega_u(q, norms[v], ldg4(t0 + ((size_t)v * P + p) * 4), a1, u);
-                omega_v(q, norms[v], u, vv);
-                wmine = omega_w(q, norms[v], a1, vv);
-                if (reweight_out) reweight_out[(size_t)v * P + p] = wmine;
-            }
-            const int nv = min(8, S - v0);
-            for (int k = 0; k < nv; ++k) {
-                const int v = v0 + k;
-                const float wv = __shfl_sync(0xffffffffu, wmine, k, 8) + 1.0f;
-                float ix, iy;
-                sweep_position(scam + v * 12, (float)x, (float)y, depth, W, H, align_corners != 0, ix, iy);
-                Taps t = make_taps(ix, iy, W, H);
-                float4 g = gather_taps(src + v * view_stride, t, chunk);
-                float dx = g.x - rv.x, dy = g.y - rv.y, dz = g.z - rv.z, dw = g.w - rv.w;
-                float cx = __fmul_rn(dx, dx), cy = __fmul_rn(dy, dy), cz = __fmul_rn(dz, dz), cw = __fmul_rn(dw, dw);
-                if (v == 0) {
-                    acc = make_float4(__fmul_rn(wv, cx), __fmul_rn(wv, cy), __fmul_rn(wv, cz), __fmul_rn(wv, cw));
-                } else {   // reference adds the rounded product (two ATen ops): keep mul and add separate
-                    acc.x = __fadd_rn(acc.x, __fmul_rn(wv, cx)); acc.y = __fadd_rn(acc.y, __fmul_rn(wv, cy));
-                    acc.z = __fadd_rn(acc.z, __fmul_rn(wv, cz)); acc.w = __fadd_rn(acc.w, __fmul_rn(wv, cw));
+    const float s_den = (float)S;
+    const int tiles_x = (W + AG_TW - 1) / AG_TW, tiles_y = (H + AG_TH - 1) / AG_TH;
+    for (int tile = blockIdx.x; tile < tiles_x * tiles_y; tile += gridDim.x) {
+        const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+#pragma unroll 1
+        for (int j = 0; j < 4; ++j) {
+            const int pl = j * 32 + grp;
+            const int y = ty * AG_TH + pl / AG_TW, x = tx * AG_TW + pl % AG_TW;
+            const bool valid = y < H && x < W;
+            const size_t p = valid ? (size_t)y * W + x : 0;
+            const float4 rv = ldg4(ref + p * 32 + sub * 4);
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int v0 = 0; v0 < S; v0 += 8) {
+                // this lane's view: sample position, taps and reweight
+                const int mv = v0 + sub;
+                Taps tm;
+                tm.o_nw = tm.o_ne = tm.o_sw = tm.o_se = -1;
+                tm.w_nw = tm.w_ne = tm.w_sw = tm.w_se = 0.f;
+                float wm = 0.f;
+                if (mv < S && valid) {
+                    float ix, iy;
+                    sweep_position(scam + mv * 12, (float)x, (float)y, depth, W, H, align_corners != 0, ix, iy);
+                    tm = make_taps(ix, iy, W, H);
+                    float a1[4], u[4], vv[4];
+                    omega_u(q, norms[mv], ldg4(t0 + ((size_t)mv * P + p) * 4), a1, u);
+                    omega_v(q, norms[mv], u, vv);
+                    wm = omega_w(q, norms[mv], a1, vv);
+                    if (reweight_out) reweight_out[(size_t)mv * P + p] = wm;
+                }
+                const int nv = min(8, S - v0);
+                for (int kb = 0; kb < nv; kb += 3) {
+                    float4 ta[3], tb[3], tcn[3], td[3];
+                    float w0[3], w1[3], w2[3], w3[3], wv[3];
+#pragma unroll
+                    for (int e = 0; e < 3; ++e) {
+                        const int k = min(kb + e, 7);
+                        const int o0 = __shfl_sync(0xffffffffu, tm.o_nw, k, 8), o1 = __shfl_sync(0xffffffffu, tm.o_ne, k, 8);
+                        const int o2 = __shfl_sync(0xffffffffu, tm.o_sw, k, 8), o3 = __shfl_sync(0xffffffffu, tm.o_se, k, 8);
+                        w0[e] = __shfl_sync(0xffffffffu, tm.w_nw, k, 8); w1[e] = __shfl_sync(0xffffffffu, tm.w_ne, k, 8);
+                        w2[e] = __shfl_sync(0xffffffffu, tm.w_sw, k, 8); w3[e] = __shfl_sync(0xffffffffu, tm.w_se, k, 8);
+                        wv[e] = __shfl_sync(0xffffffffu, wm, k, 8) + 1.0f;
+                        if (o0 < 0) w0[e] = 0.f;
+                        if (o1 < 0) w1[e] = 0.f;
+                        if (o2 < 0) w2[e] = 0.f;
+                        if (o3 < 0) w3[e] = 0.f;
+                        const float* sv = src + (size_t)min(v0 + kb + e, S - 1) * view_stride + sub * 4;
+                        ta[e] = ldg4(sv + (size_t)max(o0, 0) * 32);
+                        tb[e] = ldg4(sv + (size_t)max(o1, 0) * 32);
+                        tcn[e] = ldg4(sv + (size_t)max(o2, 0) * 32);
+                        td[e] = ldg4(sv + (size_t)max(o3, 0) * 32);
+                    }
+#pragma unroll
+                    for (int e = 0; e < 3; ++e) {
+                        if (kb + e >= nv) continue;
+                        const float gx = __fmaf_rn(td[e].x, w3[e], __fmaf_rn(tcn[e].x, w2[e], __fmaf_rn(tb[e].x, w1[e], __fmul_rn(ta[e].x, w0[e]))));
+                        const float gy = __fmaf_rn(td[e].y, w3[e], __fmaf_rn(tcn[e].y, w2[e], __fmaf_rn(tb[e].y, w1[e], __fmul_rn(ta[e].y, w0[e]))));
+                        const float gz = __fmaf_rn(td[e].z, w3[e], __fmaf_rn(tcn[e].z, w2[e], __fmaf_rn(tb[e].z, w1[e], __fmul_rn(ta[e].z, w0[e]))));
+                        const float gw = __fmaf_rn(td[e].w, w3[e], __fmaf_rn(tcn[e].w, w2[e], __fmaf_rn(tb[e].w, w1[e], __fmul_rn(ta[e].w, w0[e]))));
+                        const float dx = gx - rv.x, dy = gy - rv.y, dz = gz - rv.z, dw = gw - rv.w;
+                        const float cx = __fmul_rn(dx, dx), cy = __fmul_rn(dy, dy), cz = __fmul_rn(dz, dz), cw = __fmul_rn(dw, dw);
+                        if (v0 + kb + e == 0) {
+                            acc = make_float4(__fmul_rn(wv[e], cx), __fmul_rn(wv[e], cy), __fmul_rn(wv[e], cz), __fmul_rn(wv[e], cw));
+                        } else {   // the reference adds the rounded product (two ATen ops): keep mul and add separate
+                            acc.x = __fadd_rn(acc.x, __fmul_rn(wv[e], cx)); acc.y = __fadd_rn(acc.y, __fmul_rn(wv[e], cy));
+                            acc.z = __fadd_rn(acc.z, __fmul_rn(wv[e], cz)); acc.w = __fadd_rn(acc.w, __fmul_rn(wv[e], cw));
+                        }
+                    }
                 }
             }
+            if (valid)
+                st4(cost + p * 32 + sub * 4, make_float4(-__fdiv_rn(acc.x, s_den), -__fdiv_rn(acc.y, s_den),
+                                                         -__fdiv_rn(acc.z, s_den), -__fdiv_rn(acc.w, s_den)));
         }
-        float4 o = make_float4(-__fdiv_rn(acc.x, inv_s_den), -__fdiv_rn(acc.y, inv_s_den), -__fdiv_rn(acc.z, inv_s_den),
-                               -__fdiv_rn(acc.w, inv_s_den));
-        st4(cost + p * 32 + chunk * 4, o);
     }
 }
 
@@ -347,8 +389,8 @@ extern "C" int aarmvs_aggregate(const float* ref, const float* src, size_t view_
     AARMVS_CHECK_ARG(S >= 1 && S <= AARMVS_MAX_SRC);
     OmegaTail q;
     fill_tail(q, tail_host);
-    size_t P = (size_t)H * W;
-    int blocks = (int)min((P + 31) / 32, (size_t)148 * 16);
+    const int ntiles = ((W + AG_TW - 1) / AG_TW) * ((H + AG_TH - 1) / AG_TH);
+    const int blocks = ntiles < 148 * 8 ? ntiles : 148 * 8;
     aggregate_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(ref, src, view_stride, H, W, S, cams, q, depth_values, d_host,
                                                               d_dev, align_corners, t0, stats, cost, reweight_out);
     AARMVS_LAUNCH_RESULT();
