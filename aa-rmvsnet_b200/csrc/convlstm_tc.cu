@@ -204,11 +204,10 @@ __global__ void __launch_bounds__(N_THREADS, 1) convlstm_tc_kernel(const __grid_
             for (int k = 0; k < ITEMS; ++k) {
                 const int idx = lt + k * N_LOAD_WARPS * 32;
                 if (idx >= C::KC8 * NPX) continue;
-                __half hi[8], lo[8];
-#pragma unroll
-                for (int e = 0; e < 8; ++e) tc::split_f16(v[k][e], hi[e], lo[e]);
-                const uint4 uh = make_uint4(pack_h2(hi[0], hi[1]), pack_h2(hi[2], hi[3]), pack_h2(hi[4], hi[5]), pack_h2(hi[6], hi[7]));
-                const uint4 ul = make_uint4(pack_h2(lo[0], lo[1]), pack_h2(lo[2], lo[3]), pack_h2(lo[4], lo[5]), pack_h2(lo[6], lo[7]));
+                uint2 h0, l0, h1, l1;
+                tc::split4_f16(make_float4(v[k][0], v[k][1], v[k][2], v[k][3]), h0, l0);
+                tc::split4_f16(make_float4(v[k][4], v[k][5], v[k][6], v[k][7]), h1, l1);
+                const uint4 uh = make_uint4(h0.x, h0.y, h1.x, h1.y), ul = make_uint4(l0.x, l0.y, l1.x, l1.y);
                 *reinterpret_cast<uint4*>(stage + (size_t)idx * 16) = uh;
                 *reinterpret_cast<uint4*>(stage + C::A_PLANE + (size_t)idx * 16) = ul;
             }
@@ -281,12 +280,12 @@ __global__ void __launch_bounds__(N_THREADS, 1) convlstm_tc_kernel(const __grid_
 #pragma unroll
                 for (int j = 0; j < NHC; ++j) {
                     const float* bb = s_bias + hf * NCOL + j * 4;
-                    const float gi = sigmoidf_acc(g[j * 4 + 0] + bb[0]);
-                    const float gf = sigmoidf_acc(g[j * 4 + 1] + bb[1]);
-                    const float go = sigmoidf_acc(g[j * 4 + 2] + bb[2]);
-                    const float gg = tanhf(g[j * 4 + 3] + bb[3]);
+                    const float gi = tc::fast_sigmoid(g[j * 4 + 0] + bb[0]);
+                    const float gf = tc::fast_sigmoid(g[j * 4 + 1] + bb[1]);
+                    const float go = tc::fast_sigmoid(g[j * 4 + 2] + bb[2]);
+                    const float gg = tc::fast_tanh(g[j * 4 + 3] + bb[3]);
                     cn[j] = __fadd_rn(__fmul_rn(gf, cprev[j]), __fmul_rn(gi, gg));
-                    hn[j] = go * tanhf(cn[j]);
+                    hn[j] = go * tc::fast_tanh(cn[j]);
                 }
 #pragma unroll
                 for (int j = 0; j < NHC; j += 4) {

@@ -15,14 +15,14 @@
 namespace {
 
 constexpr int TR = 16, TCOL = 8, HR = 18, HC = 10, NPX = HR * HC;        // 180 staged pixels
-constexpr int N_EPI = 4, MMA_WARP = 4, FIRST_LOAD = 5, N_LOAD = 12;
-constexpr int N_THREADS = (N_EPI + 1 + N_LOAD) * 32;                     // 544
-constexpr int LOAD_THREADS = N_LOAD * 32;                                // 384
+constexpr int N_EPI = 4, MMA_WARP = 4, FIRST_LOAD = 5, N_LOAD = 16;
+constexpr int N_THREADS = (N_EPI + 1 + N_LOAD) * 32;                     // 672
+constexpr int LOAD_THREADS = N_LOAD * 32;                                // 512
 constexpr int N_STAGES = 4;
 constexpr int KC8 = 4, NCOLS = 16;
 constexpr int A_PLANE = KC8 * NPX * 16, A_STAGE = 2 * A_PLANE;           // 11520, 23040 bytes
 constexpr int B_PLANE = 9 * KC8 * NCOLS * 16, B_BYTES = 2 * B_PLANE;     // 9216, 18432 bytes
-constexpr int TAP_BYTES = NPX * 32;                                      // one Taps record (32 B) per staged pixel
+constexpr int TAP_BYTES = NPX * 48;                                      // one TapRec (48 B) per staged pixel
 constexpr int SMEM = B_BYTES + N_STAGES * (A_STAGE + TAP_BYTES) + 1024;
 
 struct StemArgs {
@@ -41,9 +41,14 @@ struct StemArgs {
     double* stats;
 };
 
-__device__ __forceinline__ uint32_t pack_h2(__half a, __half b) {
-    return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16);
-}
+// Gather recipe of one staged pixel, ready to use: float offsets of the four corner lines (out-of-image corners point
+// at line 0 with weight 0, which reproduces the skipped tap exactly), and the offset of the reference pixel
+// (-1: the pixel lies outside the image, its cost is the conv's zero padding).
+struct __align__(16) TapRec {
+    int o[4];
+    float w[4];
+    int ref_off, pad0, pad1, pad2;
+};
 
 __global__ void __launch_bounds__(N_THREADS, 1) cost_stem_tc_kernel(const __grid_constant__ StemArgs a) {
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -63,7 +68,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) cost_stem_tc_kernel(const __grid
     for (int i = tid; i < a.S * 12; i += N_THREADS) scam[i] = a.cams[i];
     for (int i = tid; i < a.S * 2; i += N_THREADS) sstat[i] = 0.0;
     if (tid == 0) {
-        for (int s = 0; s < N_STAGES; ++s) { tc::mbar_init(&full_a[s], LOAD_THREADS); tc::mbar_init(&empty_a[s], 1); }
+        for (int s = 0; s < N_STAGES; ++s) { tc::mbar_init(&full_a[s], LOAD_THREADS / N_STAGES); tc::mbar_init(&empty_a[s], 1); }
         for (int b = 0; b < 2; ++b) { tc::mbar_init(&tmem_full[b], 1); tc::mbar_init(&tmem_empty[b], N_EPI * 32); }
         tc::mbar_fence_init();
     }
@@ -80,89 +85,86 @@ __global__ void __launch_bounds__(N_THREADS, 1) cost_stem_tc_kernel(const __grid
 
     if (warp >= FIRST_LOAD) {
         // =========================================== loaders: gather + (warp - ref)^2 + fp16 split ==================
-        // Software pipeline: the tap sets of fill it+1 are computed (one thread per staged pixel) while the loads of
-        // fill it are in flight; the gather itself is branch-free (out-of-image taps read a valid dummy line with
-        // weight 0) and issues the loads of two pixels x five lines before the first use.
-        const int lt = tid - FIRST_LOAD * 32;
+        // Four independent loader groups of four warps; group g owns operand stage g and fills g, g+4, g+8, ... so four
+        // fills are in flight and one group's load latency is covered by the others' arithmetic.  Per fill: (1) one
+        // thread per staged pixel evaluates the homography and writes a ready-to-use gather recipe, (2) 8 lanes per
+        // pixel gather branch-free (out-of-image taps read line 0 with weight 0), two pixels' loads issued before use.
+        constexpr int GROUP_THREADS = LOAD_THREADS / N_STAGES;                   // 128
+        const int lt_all = tid - FIRST_LOAD * 32;
+        const int grp = lt_all / GROUP_THREADS, lt = lt_all - grp * GROUP_THREADS;
         const int my_tiles = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
         const int total = my_tiles * a.S;
-
-        auto compute_taps = [&](int it) {          // fill `it` -> tap slot it % N_STAGES
-            if (lt < NPX && it < total) {
-                const int tile = blockIdx.x + (it / a.S) * gridDim.x, v = it % a.S;
-                const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
-                const int r = lt / HC, cc = lt - r * HC;
+        unsigned char* stage = sA + grp * A_STAGE;
+        TapRec* taps = reinterpret_cast<TapRec*>(sT + grp * TAP_BYTES);
+        constexpr int ITEMS = (NPX * 8 + GROUP_THREADS - 1) / GROUP_THREADS;     // 12 (the last one partial)
+        for (int it = grp; it < total; it += N_STAGES) {
+            const int tile = blockIdx.x + (it / a.S) * gridDim.x, v = it % a.S;
+            const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+            // ---- (1) gather recipes (the previous fill's readers are past the barrier at the end of the loop body)
+            for (int px = lt; px < NPX; px += GROUP_THREADS) {
+                const int r = px / HC, cc = px - r * HC;
                 const int y = ty * TR - 1 + r, x = tx * TCOL - 1 + cc;
-                Taps t;
-                t.o_nw = t.o_ne = t.o_sw = t.o_se = -2;      // -2: pixel outside the image -> cost 0 (the conv's zero padding)
-                t.w_nw = t.w_ne = t.w_sw = t.w_se = 0.f;
+                TapRec rec;
+                rec.o[0] = rec.o[1] = rec.o[2] = rec.o[3] = 0;
+                rec.w[0] = rec.w[1] = rec.w[2] = rec.w[3] = 0.f;
+                rec.ref_off = -1; rec.pad0 = rec.pad1 = rec.pad2 = 0;
                 if (y >= 0 && y < a.H && x >= 0 && x < a.W) {
                     float ix, iy;
                     sweep_position(scam + v * 12, (float)x, (float)y, depth, a.W, a.H, a.align_corners != 0, ix, iy);
-                    t = make_taps(ix, iy, a.W, a.H);
+                    const Taps t = make_taps(ix, iy, a.W, a.H);
+                    rec.o[0] = max(t.o_nw, 0) * 32; rec.o[1] = max(t.o_ne, 0) * 32;
+                    rec.o[2] = max(t.o_sw, 0) * 32; rec.o[3] = max(t.o_se, 0) * 32;
+                    rec.w[0] = t.o_nw >= 0 ? t.w_nw : 0.f; rec.w[1] = t.o_ne >= 0 ? t.w_ne : 0.f;
+                    rec.w[2] = t.o_sw >= 0 ? t.w_sw : 0.f; rec.w[3] = t.o_se >= 0 ? t.w_se : 0.f;
+                    rec.ref_off = (y * a.W + x) * 32;
                 }
-                reinterpret_cast<Taps*>(sT + (it % N_STAGES) * TAP_BYTES)[lt] = t;
+                taps[px] = rec;
             }
-        };
-
-        compute_taps(0);
-        asm volatile("bar.sync 1, %0;" ::"n"(LOAD_THREADS) : "memory");
-        for (int it = 0; it < total; ++it) {
-            const int tile = blockIdx.x + (it / a.S) * gridDim.x, v = it % a.S;
-            const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
-            const int y0 = ty * TR - 1, x0 = tx * TCOL - 1;
-            const int st = it % N_STAGES;
-            tc::mbar_wait(&empty_a[st], ((it / N_STAGES) & 1) ^ 1);
-            unsigned char* stage = sA + st * A_STAGE;
-            const Taps* taps = reinterpret_cast<const Taps*>(sT + st * TAP_BYTES);
+            asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "n"(GROUP_THREADS) : "memory");
+            tc::mbar_wait(&empty_a[grp], ((it / N_STAGES) & 1) ^ 1);
+            // ---- (2) gather
             const float* sv = a.src + (size_t)v * a.view_stride;
-#pragma unroll
-            for (int batch = 0; batch < 2; ++batch) {
-                float4 ta[2], tb[2], tcn[2], td[2], rv[2];
-                float w0[2], w1[2], w2[2], w3[2];
-                bool inimg[2];
+#pragma unroll 1
+            for (int jb = 0; jb < ITEMS; jb += 2) {
+                float4 ta[2], tb[2], tcn[2], td[2], rv[2], wq[2];
+                int roff[2];
 #pragma unroll
                 for (int j = 0; j < 2; ++j) {
-                    const int i = min(lt + (batch * 2 + j) * LOAD_THREADS, NPX * 8 - 1);
-                    const int px = i >> 3, c4 = i & 7;
-                    const Taps t = taps[px];
-                    inimg[j] = t.o_nw != -2;
-                    w0[j] = t.o_nw >= 0 ? t.w_nw : 0.f; w1[j] = t.o_ne >= 0 ? t.w_ne : 0.f;
-                    w2[j] = t.o_sw >= 0 ? t.w_sw : 0.f; w3[j] = t.o_se >= 0 ? t.w_se : 0.f;
-                    ta[j] = ldg4(sv + (size_t)max(t.o_nw, 0) * 32 + c4 * 4);
-                    tb[j] = ldg4(sv + (size_t)max(t.o_ne, 0) * 32 + c4 * 4);
-                    tcn[j] = ldg4(sv + (size_t)max(t.o_sw, 0) * 32 + c4 * 4);
-                    td[j] = ldg4(sv + (size_t)max(t.o_se, 0) * 32 + c4 * 4);
-                    const int r = px / HC, cc = px - r * HC;
-                    const size_t rp = inimg[j] ? (size_t)(y0 + r) * a.W + (x0 + cc) : 0;
-                    rv[j] = ldg4(a.ref + rp * 32 + c4 * 4);
+                    const int i = min(lt + (jb + j) * GROUP_THREADS, NPX * 8 - 1);
+                    const int px = i >> 3, c4 = (i & 7) * 4;
+                    const int4 o = *reinterpret_cast<const int4*>(taps[px].o);
+                    wq[j] = *reinterpret_cast<const float4*>(taps[px].w);
+                    roff[j] = taps[px].ref_off;
+                    ta[j] = ldg4(sv + o.x + c4);
+                    tb[j] = ldg4(sv + o.y + c4);
+                    tcn[j] = ldg4(sv + o.z + c4);
+                    td[j] = ldg4(sv + o.w + c4);
+                    rv[j] = ldg4(a.ref + max(roff[j], 0) + c4);
                 }
-                if (batch == 0) compute_taps(it + 1);        // ALU work under the loads' latency
 #pragma unroll
                 for (int j = 0; j < 2; ++j) {
-                    const int iraw = lt + (batch * 2 + j) * LOAD_THREADS;
+                    const int iraw = lt + (jb + j) * GROUP_THREADS;
                     const int px = iraw >> 3, c4 = iraw & 7;
-                    // bilinear blend in ATen's order (see gather_taps); a zero weight reproduces the skipped tap exactly
-                    const float gx = __fmaf_rn(td[j].x, w3[j], __fmaf_rn(tcn[j].x, w2[j], __fmaf_rn(tb[j].x, w1[j], __fmul_rn(ta[j].x, w0[j]))));
-                    const float gy = __fmaf_rn(td[j].y, w3[j], __fmaf_rn(tcn[j].y, w2[j], __fmaf_rn(tb[j].y, w1[j], __fmul_rn(ta[j].y, w0[j]))));
-                    const float gz = __fmaf_rn(td[j].z, w3[j], __fmaf_rn(tcn[j].z, w2[j], __fmaf_rn(tb[j].z, w1[j], __fmul_rn(ta[j].z, w0[j]))));
-                    const float gw = __fmaf_rn(td[j].w, w3[j], __fmaf_rn(tcn[j].w, w2[j], __fmaf_rn(tb[j].w, w1[j], __fmul_rn(ta[j].w, w0[j]))));
+                    // bilinear blend in ATen's order (see gather_taps)
+                    const float gx = __fmaf_rn(td[j].x, wq[j].w, __fmaf_rn(tcn[j].x, wq[j].z, __fmaf_rn(tb[j].x, wq[j].y, __fmul_rn(ta[j].x, wq[j].x))));
+                    const float gy = __fmaf_rn(td[j].y, wq[j].w, __fmaf_rn(tcn[j].y, wq[j].z, __fmaf_rn(tb[j].y, wq[j].y, __fmul_rn(ta[j].y, wq[j].x))));
+                    const float gz = __fmaf_rn(td[j].z, wq[j].w, __fmaf_rn(tcn[j].z, wq[j].z, __fmaf_rn(tb[j].z, wq[j].y, __fmul_rn(ta[j].z, wq[j].x))));
+                    const float gw = __fmaf_rn(td[j].w, wq[j].w, __fmaf_rn(tcn[j].w, wq[j].z, __fmaf_rn(tb[j].w, wq[j].y, __fmul_rn(ta[j].w, wq[j].x))));
                     const float dx = gx - rv[j].x, dy = gy - rv[j].y, dz = gz - rv[j].z, dw = gw - rv[j].w;
-                    const float cx = inimg[j] ? dx * dx : 0.f, cy = inimg[j] ? dy * dy : 0.f;
-                    const float cz = inimg[j] ? dz * dz : 0.f, cw = inimg[j] ? dw * dw : 0.f;
-                    __half h0, h1, h2, h3, l0, l1, l2, l3;
-                    tc::split_f16(cx, h0, l0); tc::split_f16(cy, h1, l1);
-                    tc::split_f16(cz, h2, l2); tc::split_f16(cw, h3, l3);
+                    const bool in = roff[j] >= 0;
+                    const float4 cv = make_float4(in ? dx * dx : 0.f, in ? dy * dy : 0.f, in ? dz * dz : 0.f, in ? dw * dw : 0.f);
+                    uint2 hi, lo;
+                    tc::split4_f16(cv, hi, lo);
                     if (iraw < NPX * 8) {
                         const size_t off = ((size_t)(c4 >> 1) * NPX + px) * 16 + (c4 & 1) * 8;
-                        *reinterpret_cast<uint2*>(stage + off) = make_uint2(pack_h2(h0, h1), pack_h2(h2, h3));
-                        *reinterpret_cast<uint2*>(stage + A_PLANE + off) = make_uint2(pack_h2(l0, l1), pack_h2(l2, l3));
+                        *reinterpret_cast<uint2*>(stage + off) = hi;
+                        *reinterpret_cast<uint2*>(stage + A_PLANE + off) = lo;
                     }
                 }
             }
             tc::fence_async_smem();
-            tc::mbar_arrive(&full_a[st]);
-            asm volatile("bar.sync 1, %0;" ::"n"(LOAD_THREADS) : "memory");      // tap sets of fill it+1 are complete
+            tc::mbar_arrive(&full_a[grp]);
+            asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "n"(GROUP_THREADS) : "memory");   // recipes may be overwritten
         }
     } else if (warp == MMA_WARP) {
         // =========================================== MMA issuer ===========================================
