@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) convlstm_tc_kernel(const __grid_
         int it = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
             const int st = it % N_STAGES;
-            tc::mbar_wait(&empty_a[st], ((it / N_STAGES) & 1) ^ 1);
+            tc::mbar_wait_relaxed(&empty_a[st], ((it / N_STAGES) & 1) ^ 1);
             const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
             const int y0 = ty * TR - 1, x0 = tx * TCOL - 1;
             unsigned char* stage = sA + st * C::A_STAGE;
@@ -258,7 +258,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) convlstm_tc_kernel(const __grid_
         int it = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
             const int ab = it & 1;
-            tc::mbar_wait(&tmem_full[ab], (it >> 1) & 1);
+            tc::mbar_wait_relaxed(&tmem_full[ab], (it >> 1) & 1);
             tc::tc_fence_after();
             float g[NCOL];
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + ab * NG + hf * NCOL;

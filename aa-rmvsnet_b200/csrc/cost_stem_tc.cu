@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) cost_stem_tc_kernel(const __grid
                 taps[px] = rec;
             }
             asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "n"(GROUP_THREADS) : "memory");
-            tc::mbar_wait(&empty_a[grp], ((it / N_STAGES) & 1) ^ 1);
+            tc::mbar_wait_relaxed(&empty_a[grp], ((it / N_STAGES) & 1) ^ 1);
             // ---- (2) gather
             const float* sv = a.src + (size_t)v * a.view_stride;
 #pragma unroll 1
@@ -211,7 +211,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) cost_stem_tc_kernel(const __grid
             const bool valid = y < a.H && x < a.W;
             for (int v = 0; v < a.S; ++v, ++it) {
                 const int ab = it & 1;
-                tc::mbar_wait(&tmem_full[ab], (it >> 1) & 1);
+                tc::mbar_wait_relaxed(&tmem_full[ab], (it >> 1) & 1);
                 tc::tc_fence_after();
                 uint32_t r0, r1, r2, r3;
                 asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"

@@ -44,9 +44,20 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     return ok != 0;
 }
 // Bounded wait: a protocol bug must surface as a trapped launch, never as a hung GPU.
+// Latency-critical waiter (the MMA-issuing thread): tight polling.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     for (uint32_t spin = 0; spin < (1u << 28); ++spin)
         if (mbar_try_wait(bar, parity)) return;
+    __trap();
+}
+// Everyone else backs off between polls so that waiting warps do not take issue slots from working ones
+// (ncu: 55 % of the executed instructions of the first version were barrier polling).
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    for (uint32_t spin = 0; spin < (1u << 24); ++spin) {
+        __nanosleep(64);
+        if (mbar_try_wait(bar, parity)) return;
+    }
     __trap();
 }
 
