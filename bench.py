@@ -250,11 +250,30 @@ def run_ours(args):
         wa_ms = st["cost_stem"] + st["omega_stats"] + st["aggregate"]
         rec_ms = sum(st[k] for k in st if k.startswith(("cell", "deconv", "head")))
         wa_bytes = 128 * P * (N + 1)
-        cell0_flops = CELL_FLOP_PER_PX["cell0"] * P
-        roofline = {"kernel": "conv_kernel<48,64,3,1,16,4,EPI_LSTM> (ConvLSTM cell 0, fp32 CUDA-core FMA in round 1)",
-                    "bound": "tensor", "achieved": cell0_flops / (st["cell0"] * 1e-3) / 1e12, "peak": pk["bf16_tflops_sustained"],
-                    "unit": "TFLOP/s", "traffic": None, "peak_source": pk["source"] + ", sustained bf16 (kernel timed inside a long step)"}
+        S = N - 1
+        # the slowest kernel of the plane chain against ITS bound (algorithmic bytes / FLOPs as listed in DESIGN.md §3)
+        kernels = {
+            "cost_stem": ("cost_stem_tc_kernel (pass A: gather + (warp-ref)^2 + omega stem conv on tcgen05)", "hbm",
+                          128 * P * (S + 1) + 16 * P * S),
+            "aggregate": ("aggregate_kernel (pass D: re-gather + omega tail + weighted sum)", "hbm",
+                          128 * P * (S + 1) + 16 * P * S + 128 * P),
+            "omega_stats": ("omega_stats_kernel<2>+<3> (passes B, C)", "hbm", 2 * 16 * P * S),
+            "head_wta": ("head_wta_kernel", "hbm", 44 * P),
+        }
+        for i, name in enumerate(("cell0", "cell1", "cell2", "cell3", "cell4")):
+            kernels[name] = (f"convlstm_tc_kernel (ConvLSTM cell {i}: tcgen05 implicit GEMM, split-fp16 operands, "
+                             "useful FLOPs counted once)", "tensor", CELL_FLOP_PER_PX[name] * P)
+        top = max(kernels, key=lambda k: st[k])
+        kname, bound, work = kernels[top]
+        if bound == "hbm":
+            roofline = {"kernel": kname, "bound": "hbm", "achieved": work / (st[top] * 1e-3) / 1e9, "peak": pk["hbm_gbs"],
+                        "unit": "GB/s", "traffic": None, "peak_source": pk["source"] + ", STREAM-style copy"}
+        else:
+            roofline = {"kernel": kname, "bound": "tensor", "achieved": work / (st[top] * 1e-3) / 1e12,
+                        "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s", "traffic": None,
+                        "peak_source": pk["source"] + ", sustained bf16 (kernel timed inside a long step)"}
         roofline["frac"] = roofline["achieved"] / roofline["peak"]
+        roofline["ms_per_launch"] = st[top]
         extra = {
             "stage_ms_per_plane": {k: round(v, 4) for k, v in st.items()},
             "recurrence": {"ms_per_plane": rec_ms, "achieved_tflops": FLOP_PER_PX_PLANE * P / (rec_ms * 1e-3) / 1e12,
