@@ -43,10 +43,10 @@ PROTOTYPES = {
     "aarmvs_warp": (_I, [_P, _P, _I, _I, c_float_p, _F, _I, _P]),
     "aarmvs_omega_stats_bytes": (_SZ, [_I]),
     "aarmvs_omega_tail_floats": (_I, []),
-    "aarmvs_cost_stem": (_I, [_P, _P, _SZ, _I, _I, _I, _P, c_float_p, c_float_p, _P, _I, _P, _I, _P, _P, _P]),
-    "aarmvs_cost_stem_tc": (_I, [_P, _P, _SZ, _I, _I, _I, _P, _P, c_float_p, _P, _I, _P, _I, _P, _P, _P]),
-    "aarmvs_omega_stats": (_I, [_I, _P, _I, _I, _I, c_float_p, _P, _P]),
-    "aarmvs_aggregate": (_I, [_P, _P, _SZ, _I, _I, _I, _P, c_float_p, _P, _I, _P, _I, _P, _P, _P, _P, _P]),
+    "aarmvs_cost_stem": (_I, [_P, _P, _SZ, _I, _I, _I, _P, c_float_p, c_float_p, _P, _I, _P, _I, _I, _P, _P, _P]),
+    "aarmvs_cost_stem_tc": (_I, [_P, _P, _SZ, _I, _I, _I, _P, _P, c_float_p, _P, _I, _P, _I, _I, _P, _P, _P]),
+    "aarmvs_omega_stats": (_I, [_I, _P, _I, _I, _I, _I, c_float_p, _P, _P]),
+    "aarmvs_aggregate": (_I, [_P, _P, _SZ, _I, _I, _I, _P, c_float_p, _P, _I, _P, _I, _I, _P, _P, _P, _P, _P]),
     "aarmvs_convlstm_cell": (_I, [_SRCP, _I, _I, _I, _I, _I, _P, _P, _P, _P, _I, _P, _P]),
     "aarmvs_convlstm_cell_tc": (_I, [_SRCP, _I, _I, _I, _I, _I, _P, _P, _P, _P, _I, _P, _P]),
     "aarmvs_deconv2x": (_I, [_SRCP, _I, _I, _P, _P, _P, _P, _I, _P, _P]),
@@ -77,7 +77,7 @@ def load(build_if_missing=True):
         fn = getattr(lib, name)          # AttributeError here = ABI drift between the header and the library
         fn.restype = res
         fn.argtypes = args
-    if lib.aarmvs_version() != 1:
+    if lib.aarmvs_version() != 2:
         raise RuntimeError("libaarmvs_sm100.so: ABI version mismatch")
     _lib = lib
     return lib

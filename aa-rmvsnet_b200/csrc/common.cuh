@@ -10,6 +10,7 @@
 #define AARMVS_LAUNCH_RESULT() do { cudaError_t e__ = cudaGetLastError(); return e__ == cudaSuccess ? AARMVS_OK : (int)e__; } while (0)
 
 constexpr int AARMVS_MAX_SRC = 15;     // source views per sample (N - 1)
+constexpr int AARMVS_MAX_PLANES = 16;  // depth planes per launch of the plane-batched passes A-D
 constexpr float GN_EPS = 1e-5f;        // nn.GroupNorm default (models/module.py:101)
 
 struct Cams {                          // per source view: rot (row-major 3x3) then trans (3), models/module.py:16-18

@@ -216,38 +216,38 @@ __global__ void __launch_bounds__(N_THREADS, 1) convlstm_tc_kernel(const __grid_
         }
     } else if (warp == MMA_WARP) {
         // =========================================== MMA issuer ===========================================
-        if (lane == 0) {
-            const uint32_t idesc = tc::idesc_f16_f32(128, NG);
-            const uint32_t a_base = tc::smem_u32(sA), b_base = tc::smem_u32(sB);
-            int it = 0;
-            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-                const int st = it % N_STAGES, ab = it & 1;
-                tc::mbar_wait(&full_a[st], (it / N_STAGES) & 1);
-                tc::mbar_wait(&tmem_empty[ab], ((it >> 1) & 1) ^ 1);
-                tc::tc_fence_after();
-                const uint32_t dst = tmem_base + ab * NG;
-                const uint32_t a_hi = a_base + st * C::A_STAGE, a_lo = a_hi + C::A_PLANE;
-                uint32_t first = 0;
-#pragma unroll 1
+        // The whole warp runs the loop (uniform control flow keeps the descriptor arithmetic on the uniform datapath);
+        // one elected lane issues.  81 / 54 MMAs per tile, fully unrolled: descriptor low words are base + immediate.
+        const bool leader = tc::elect_one();
+        const uint32_t idesc = tc::idesc_f16_f32(128, NG);
+        const uint32_t a_base = tc::smem_u32(sA), b_base = tc::smem_u32(sB);
+        constexpr uint32_t A_HI = tc::desc_hi(HC * 16), B_HI = tc::desc_hi(8 * 16);
+        const uint32_t b_lo_hi = tc::desc_lo(b_base, NG * 16), b_lo_lo = tc::desc_lo(b_base + C::B_PLANE, NG * 16);
+        int it = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+            const int st = it % N_STAGES, ab = it & 1;
+            tc::mbar_wait(&full_a[st], (it / N_STAGES) & 1);
+            tc::mbar_wait(&tmem_empty[ab], ((it >> 1) & 1) ^ 1);
+            tc::tc_fence_after();
+            const uint32_t dst = tmem_base + ab * NG;
+            const uint32_t a_lo_hi = tc::desc_lo(a_base + st * C::A_STAGE, NPX * 16);
+            const uint32_t a_lo_lo = tc::desc_lo(a_base + st * C::A_STAGE + C::A_PLANE, NPX * 16);
+            if (leader) {
+#pragma unroll
                 for (int tap = 0; tap < 9; ++tap) {
-                    const uint32_t a_off = (uint32_t)((tap / 3) * HC + (tap % 3)) * 16;
 #pragma unroll
                     for (int ks = 0; ks < KSTEPS; ++ks) {
-                        const uint32_t ak = (uint32_t)(2 * ks) * NPX * 16 + a_off;
-                        const uint32_t bk = (uint32_t)((tap * C::KC8 + 2 * ks) * NG) * 16;
-                        const uint64_t da_hi = tc::smem_desc(a_hi + ak, NPX * 16, HC * 16);
-                        const uint64_t da_lo = tc::smem_desc(a_lo + ak, NPX * 16, HC * 16);
-                        const uint64_t db_hi = tc::smem_desc(b_base + bk, NG * 16, 8 * 16);
-                        const uint64_t db_lo = tc::smem_desc(b_base + C::B_PLANE + bk, NG * 16, 8 * 16);
-                        tc::mma_f16(dst, da_lo, db_hi, idesc, first);   // small terms first
-                        first = 1;
-                        tc::mma_f16(dst, da_hi, db_lo, idesc, 1);
-                        tc::mma_f16(dst, da_hi, db_hi, idesc, 1);
+                        const uint32_t ak = (uint32_t)(((2 * ks) * NPX + (tap / 3) * HC + (tap % 3)) * 16) >> 4;
+                        const uint32_t bk = (uint32_t)(((tap * C::KC8 + 2 * ks) * NG) * 16) >> 4;
+                        tc::mma_f16_parts(dst, a_lo_lo + ak, A_HI, b_lo_hi + bk, B_HI, idesc, (tap | ks) != 0);   // small terms first
+                        tc::mma_f16_parts(dst, a_lo_hi + ak, A_HI, b_lo_lo + bk, B_HI, idesc, 1);
+                        tc::mma_f16_parts(dst, a_lo_hi + ak, A_HI, b_lo_hi + bk, B_HI, idesc, 1);
                     }
                 }
                 tc::mma_commit(&empty_a[st]);          // operand stage free once these MMAs have read it
                 tc::mma_commit(&tmem_full[ab]);        // accumulator complete
             }
+            __syncwarp();
         }
     } else {
         // =========================================== epilogue ===========================================

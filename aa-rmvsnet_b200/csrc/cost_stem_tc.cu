@@ -29,8 +29,8 @@ struct StemArgs {
     const float* ref;
     const float* src;
     size_t view_stride;
-    int H, W, S;
-    const float* cams;
+    int H, W, S, K;             // K = planes per launch: fills run in (tile, view, plane) order so that a tile's source
+    const float* cams;          //     lines stay in L1 across consecutive planes
     const __half* weight;       // [2][9][4][16][8] fp16
     float bias[4];
     const float* depth_values;
@@ -58,15 +58,15 @@ __global__ void __launch_bounds__(N_THREADS, 1) cost_stem_tc_kernel(const __grid
     __shared__ uint64_t full_a[N_STAGES], empty_a[N_STAGES], tmem_full[2], tmem_empty[2];
     __shared__ uint32_t tmem_base_s;
     __shared__ float scam[AARMVS_MAX_SRC * 12];
-    __shared__ double sstat[AARMVS_MAX_SRC * 2];
+    __shared__ double sstat[AARMVS_MAX_PLANES * AARMVS_MAX_SRC * 2];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const float depth = a.depth_values[plane_index(a.d_host, a.d_dev)];
+    const float* depths = a.depth_values + plane_index(a.d_host, a.d_dev);
 
     for (int i = tid; i < B_BYTES / 16; i += N_THREADS)
         reinterpret_cast<uint4*>(sB)[i] = __ldg(reinterpret_cast<const uint4*>(a.weight) + i);
     for (int i = tid; i < a.S * 12; i += N_THREADS) scam[i] = a.cams[i];
-    for (int i = tid; i < a.S * 2; i += N_THREADS) sstat[i] = 0.0;
+    for (int i = tid; i < a.K * a.S * 2; i += N_THREADS) sstat[i] = 0.0;
     if (tid == 0) {
         for (int s = 0; s < N_STAGES; ++s) { tc::mbar_init(&full_a[s], LOAD_THREADS / N_STAGES); tc::mbar_init(&empty_a[s], 1); }
         for (int b = 0; b < 2; ++b) { tc::mbar_init(&tmem_full[b], 1); tc::mbar_init(&tmem_empty[b], N_EPI * 32); }
@@ -93,12 +93,14 @@ __global__ void __launch_bounds__(N_THREADS, 1) cost_stem_tc_kernel(const __grid
         const int lt_all = tid - FIRST_LOAD * 32;
         const int grp = lt_all / GROUP_THREADS, lt = lt_all - grp * GROUP_THREADS;
         const int my_tiles = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-        const int total = my_tiles * a.S;
+        const int SK = a.S * a.K;
+        const int total = my_tiles * SK;
         unsigned char* stage = sA + grp * A_STAGE;
         TapRec* taps = reinterpret_cast<TapRec*>(sT + grp * TAP_BYTES);
         constexpr int ITEMS = (NPX * 8 + GROUP_THREADS - 1) / GROUP_THREADS;     // 12 (the last one partial)
         for (int it = grp; it < total; it += N_STAGES) {
-            const int tile = blockIdx.x + (it / a.S) * gridDim.x, v = it % a.S;
+            const int tile = blockIdx.x + (it / SK) * gridDim.x, v = (it % SK) / a.K;
+            const float depth = depths[it % a.K];
             const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
             // ---- (1) gather recipes (the previous fill's readers are past the barrier at the end of the loop body)
             for (int px = lt; px < NPX; px += GROUP_THREADS) {
@@ -168,38 +170,36 @@ __global__ void __launch_bounds__(N_THREADS, 1) cost_stem_tc_kernel(const __grid
         }
     } else if (warp == MMA_WARP) {
         // =========================================== MMA issuer ===========================================
-        if (lane == 0) {
-            const uint32_t idesc = tc::idesc_f16_f32(128, NCOLS);
-            const uint32_t a_base = tc::smem_u32(sA), b_base = tc::smem_u32(sB);
-            const int total = ((ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x) * a.S;
-            for (int it = 0; it < total; ++it) {
-                const int st = it % N_STAGES, ab = it & 1;
-                tc::mbar_wait(&full_a[st], (it / N_STAGES) & 1);
-                tc::mbar_wait(&tmem_empty[ab], ((it >> 1) & 1) ^ 1);
-                tc::tc_fence_after();
-                const uint32_t dst = tmem_base + ab * NCOLS;
-                const uint32_t a_hi = a_base + st * A_STAGE, a_lo = a_hi + A_PLANE;
-                uint32_t first = 0;
-#pragma unroll 1
+        const bool leader = tc::elect_one();
+        const uint32_t idesc = tc::idesc_f16_f32(128, NCOLS);
+        const uint32_t a_base = tc::smem_u32(sA), b_base = tc::smem_u32(sB);
+        constexpr uint32_t A_HI = tc::desc_hi(HC * 16), B_HI = tc::desc_hi(8 * 16);
+        const uint32_t b_lo_hi = tc::desc_lo(b_base, NCOLS * 16), b_lo_lo = tc::desc_lo(b_base + B_PLANE, NCOLS * 16);
+        const int total = ((ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x) * a.S * a.K;
+        for (int it = 0; it < total; ++it) {
+            const int st = it % N_STAGES, ab = it & 1;
+            tc::mbar_wait(&full_a[st], (it / N_STAGES) & 1);
+            tc::mbar_wait(&tmem_empty[ab], ((it >> 1) & 1) ^ 1);
+            tc::tc_fence_after();
+            const uint32_t dst = tmem_base + ab * NCOLS;
+            const uint32_t a_lo_hi = tc::desc_lo(a_base + st * A_STAGE, NPX * 16);
+            const uint32_t a_lo_lo = tc::desc_lo(a_base + st * A_STAGE + A_PLANE, NPX * 16);
+            if (leader) {
+#pragma unroll
                 for (int tap = 0; tap < 9; ++tap) {
-                    const uint32_t a_off = (uint32_t)((tap / 3) * HC + (tap % 3)) * 16;
 #pragma unroll
                     for (int ks = 0; ks < 2; ++ks) {
-                        const uint32_t ak = (uint32_t)(2 * ks) * NPX * 16 + a_off;
-                        const uint32_t bk = (uint32_t)((tap * KC8 + 2 * ks) * NCOLS) * 16;
-                        const uint64_t da_hi = tc::smem_desc(a_hi + ak, NPX * 16, HC * 16);
-                        const uint64_t da_lo = tc::smem_desc(a_lo + ak, NPX * 16, HC * 16);
-                        const uint64_t db_hi = tc::smem_desc(b_base + bk, NCOLS * 16, 8 * 16);
-                        const uint64_t db_lo = tc::smem_desc(b_base + B_PLANE + bk, NCOLS * 16, 8 * 16);
-                        tc::mma_f16(dst, da_lo, db_hi, idesc, first);
-                        first = 1;
-                        tc::mma_f16(dst, da_hi, db_lo, idesc, 1);
-                        tc::mma_f16(dst, da_hi, db_hi, idesc, 1);
+                        const uint32_t ak = (uint32_t)(((2 * ks) * NPX + (tap / 3) * HC + (tap % 3)) * 16) >> 4;
+                        const uint32_t bk = (uint32_t)(((tap * KC8 + 2 * ks) * NCOLS) * 16) >> 4;
+                        tc::mma_f16_parts(dst, a_lo_lo + ak, A_HI, b_lo_hi + bk, B_HI, idesc, (tap | ks) != 0);
+                        tc::mma_f16_parts(dst, a_lo_hi + ak, A_HI, b_lo_lo + bk, B_HI, idesc, 1);
+                        tc::mma_f16_parts(dst, a_lo_hi + ak, A_HI, b_lo_hi + bk, B_HI, idesc, 1);
                     }
                 }
                 tc::mma_commit(&empty_a[st]);
                 tc::mma_commit(&tmem_full[ab]);
             }
+            __syncwarp();
         }
     } else {
         // =========================================== epilogue: t0 + GroupNorm-1 sums ==============================
@@ -209,7 +209,8 @@ __global__ void __launch_bounds__(N_THREADS, 1) cost_stem_tc_kernel(const __grid
             const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
             const int y = ty * TR + (m >> 3), x = tx * TCOL + (m & 7);
             const bool valid = y < a.H && x < a.W;
-            for (int v = 0; v < a.S; ++v, ++it) {
+            for (int vk = 0; vk < a.S * a.K; ++vk, ++it) {
+                const int v = (vk % a.K) * a.S + vk / a.K;          // slot (plane k, view v) of t0 / stats
                 const int ab = it & 1;
                 tc::mbar_wait_relaxed(&tmem_full[ab], (it >> 1) & 1);
                 tc::tc_fence_after();
@@ -240,18 +241,19 @@ __global__ void __launch_bounds__(N_THREADS, 1) cost_stem_tc_kernel(const __grid
     tc::tc_fence_before();
     __syncthreads();
     if (warp == MMA_WARP) tc::tmem_dealloc<32>(tmem_base);
-    if (tid < a.S * 2) atomicAdd(a.stats + (tid >> 1) * 6 + (tid & 1), sstat[tid]);      // stats[v][GN1][sum, sumsq]
+    if (tid < a.K * a.S * 2) atomicAdd(a.stats + (tid >> 1) * 6 + (tid & 1), sstat[tid]);      // stats[k][v][GN1][sum, sumsq]
 }
 
 }  // namespace
 
 extern "C" int aarmvs_cost_stem_tc(const float* ref, const float* src, size_t view_stride, int H, int W, int S,
                                    const float* cams, const void* stem_w_f16, const float* stem_b_host,
-                                   const float* depth_values, int d_host, const int* d_dev, int align_corners, float* t0,
-                                   double* stats, void* stream) {
+                                   const float* depth_values, int d_host, const int* d_dev, int planes, int align_corners,
+                                   float* t0, double* stats, void* stream) {
     AARMVS_CHECK_ARG(ref && src && t0 && stats && stem_w_f16 && stem_b_host && depth_values && cams && H > 0 && W > 0);
-    AARMVS_CHECK_ARG(S >= 1 && S <= AARMVS_MAX_SRC);
+    AARMVS_CHECK_ARG(S >= 1 && S <= AARMVS_MAX_SRC && planes >= 1 && planes <= AARMVS_MAX_PLANES);
     StemArgs a = {};
+    a.K = planes;
     a.ref = ref; a.src = src; a.view_stride = view_stride; a.H = H; a.W = W; a.S = S; a.cams = cams;
     a.weight = (const __half*)stem_w_f16;
     for (int i = 0; i < 4; ++i) a.bias[i] = stem_b_host[i];

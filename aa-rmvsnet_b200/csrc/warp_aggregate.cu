@@ -65,8 +65,10 @@ cost_stem_kernel(const float* __restrict__ ref, const float* __restrict__ src, s
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int chunk = tid & 7, grp = tid >> 3;           // 16 groups of 8 lanes
     const int tx0 = blockIdx.x * TA_W, ty0 = blockIdx.y * TA_H;
-    const float depth = depth_values[plane_index(d_host, d_dev)];
+    const float depth = depth_values[plane_index(d_host, d_dev) + blockIdx.z];
     const size_t P = (size_t)H * W;
+    t0 += (size_t)blockIdx.z * S * P * 4;
+    stats += (size_t)blockIdx.z * S * 6;
 
     for (int v = 0; v < S; ++v) {
         const float* sv = src + v * view_stride;
@@ -224,26 +226,26 @@ __global__ void __launch_bounds__(256) omega_stats_kernel(const float* __restric
 constexpr int AG_TH = 8, AG_TW = 16;
 
 __global__ void __launch_bounds__(256)
-aggregate_kernel(const float* __restrict__ ref, const float* __restrict__ src, size_t view_stride, int H, int W, int S,
+aggregate_kernel(const float* __restrict__ ref, const float* __restrict__ src, size_t view_stride, int H, int W, int S, int K,
                  const float* __restrict__ cams, const __grid_constant__ OmegaTail q,
                  const float* __restrict__ depth_values, int d_host, const int* __restrict__ d_dev, int align_corners,
                  const float* __restrict__ t0, const double* __restrict__ stats, float* __restrict__ cost,
                  float* __restrict__ reweight_out) {
-    __shared__ OmegaNorm norms[AARMVS_MAX_SRC];
+    __shared__ OmegaNorm norms_all[AARMVS_MAX_PLANES * AARMVS_MAX_SRC];
     __shared__ float scam[AARMVS_MAX_SRC * 12];
     for (int i = threadIdx.x; i < S * 12; i += blockDim.x) scam[i] = cams[i];
     const size_t P = (size_t)H * W;
-    if (threadIdx.x < S) {
+    if (threadIdx.x < S * K) {
         OmegaNorm n;
         const double cnt = 4.0 * (double)P;
         gn_mean_rstd(stats + threadIdx.x * 6 + 0, cnt, n.m1, n.r1);
         gn_mean_rstd(stats + threadIdx.x * 6 + 2, cnt, n.m2, n.r2);
         gn_mean_rstd(stats + threadIdx.x * 6 + 4, cnt, n.m3, n.r3);
-        norms[threadIdx.x] = n;
+        norms_all[threadIdx.x] = n;
     }
     __syncthreads();
     const int sub = threadIdx.x & 7, grp = threadIdx.x >> 3;
-    const float depth = depth_values[plane_index(d_host, d_dev)];
+    const float* depths = depth_values + plane_index(d_host, d_dev);
     const float s_den = (float)S;
     const int tiles_x = (W + AG_TW - 1) / AG_TW, tiles_y = (H + AG_TH - 1) / AG_TH;
     for (int tile = blockIdx.x; tile < tiles_x * tiles_y; tile += gridDim.x) {
@@ -255,6 +257,11 @@ aggregate_kernel(const float* __restrict__ ref, const float* __restrict__ src, s
             const bool valid = y < H && x < W;
             const size_t p = valid ? (size_t)y * W + x : 0;
             const float4 rv = ldg4(ref + p * 32 + sub * 4);
+            // planes innermost: the source lines this pixel touches at plane k+1 are the ones just fetched for plane k
+            for (int k = 0; k < K; ++k) {
+            const float depth = depths[k];
+            const OmegaNorm* norms = norms_all + k * S;
+            const float* t0k = t0 + (size_t)k * S * P * 4;
             float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
             for (int v0 = 0; v0 < S; v0 += 8) {
                 // this lane's view: sample position, taps and reweight
@@ -268,10 +275,10 @@ aggregate_kernel(const float* __restrict__ ref, const float* __restrict__ src, s
                     sweep_position(scam + mv * 12, (float)x, (float)y, depth, W, H, align_corners != 0, ix, iy);
                     tm = make_taps(ix, iy, W, H);
                     float a1[4], u[4], vv[4];
-                    omega_u(q, norms[mv], ldg4(t0 + ((size_t)mv * P + p) * 4), a1, u);
+                    omega_u(q, norms[mv], ldg4(t0k + ((size_t)mv * P + p) * 4), a1, u);
                     omega_v(q, norms[mv], u, vv);
                     wm = omega_w(q, norms[mv], a1, vv);
-                    if (reweight_out) reweight_out[(size_t)mv * P + p] = wm;
+                    if (reweight_out) reweight_out[((size_t)k * S + mv) * P + p] = wm;
                 }
                 const int nv = min(8, S - v0);
                 for (int kb = 0; kb < nv; kb += 3) {
@@ -314,8 +321,9 @@ aggregate_kernel(const float* __restrict__ ref, const float* __restrict__ src, s
                 }
             }
             if (valid)
-                st4(cost + p * 32 + sub * 4, make_float4(-__fdiv_rn(acc.x, s_den), -__fdiv_rn(acc.y, s_den),
-                                                         -__fdiv_rn(acc.z, s_den), -__fdiv_rn(acc.w, s_den)));
+                st4(cost + ((size_t)k * P + p) * 32 + sub * 4, make_float4(-__fdiv_rn(acc.x, s_den), -__fdiv_rn(acc.y, s_den),
+                                                                           -__fdiv_rn(acc.z, s_den), -__fdiv_rn(acc.w, s_den)));
+            }
         }
     }
 }
@@ -345,10 +353,10 @@ extern "C" size_t aarmvs_omega_stats_bytes(int S) { return (size_t)S * 6 * sizeo
 
 extern "C" int aarmvs_cost_stem(const float* ref, const float* src, size_t view_stride, int H, int W, int S,
                                 const float* cams, const float* stem_w, const float* stem_b,
-                                const float* depth_values, int d_host, const int* d_dev, int align_corners, float* t0,
-                                double* stats, void* stream) {
+                                const float* depth_values, int d_host, const int* d_dev, int planes, int align_corners,
+                                float* t0, double* stats, void* stream) {
     AARMVS_CHECK_ARG(ref && src && t0 && stats && stem_w && stem_b && depth_values && cams && H > 0 && W > 0);
-    AARMVS_CHECK_ARG(S >= 1 && S <= AARMVS_MAX_SRC);
+    AARMVS_CHECK_ARG(S >= 1 && S <= AARMVS_MAX_SRC && planes >= 1 && planes <= AARMVS_MAX_PLANES);
     StemParams sp;
     for (int i = 0; i < 9 * 32 * 4; ++i) sp.w[i] = stem_w[i];
     for (int i = 0; i < 4; ++i) sp.b[i] = stem_b[i];
@@ -359,7 +367,7 @@ extern "C" int aarmvs_cost_stem(const float* ref, const float* src, size_t view_
         if (e != cudaSuccess) return (int)e;
         attr_set = true;
     }
-    dim3 grid((W + TA_W - 1) / TA_W, (H + TA_H - 1) / TA_H);
+    dim3 grid((W + TA_W - 1) / TA_W, (H + TA_H - 1) / TA_H, planes);
     cost_stem_kernel<<<grid, TA_THREADS, smem, (cudaStream_t)stream>>>(ref, src, view_stride, H, W, S, cams, sp, depth_values,
                                                                       d_host, d_dev, align_corners, t0, stats);
     AARMVS_LAUNCH_RESULT();
@@ -369,9 +377,11 @@ static void fill_tail(OmegaTail& q, const float* t) { memcpy(&q, t, sizeof(Omega
 
 extern "C" int aarmvs_omega_tail_floats(void) { return (int)(sizeof(OmegaTail) / sizeof(float)); }
 
-extern "C" int aarmvs_omega_stats(int stage, const float* t0, int H, int W, int S, const float* tail_host, double* stats,
-                                  void* stream) {
+extern "C" int aarmvs_omega_stats(int stage, const float* t0, int H, int W, int S, int planes, const float* tail_host,
+                                  double* stats, void* stream) {
     AARMVS_CHECK_ARG(t0 && stats && tail_host && (stage == 2 || stage == 3) && S >= 1 && S <= AARMVS_MAX_SRC);
+    AARMVS_CHECK_ARG(planes >= 1 && planes <= AARMVS_MAX_PLANES);
+    S *= planes;          // t0 is [planes][S][P][4] and stats [planes][S][6]: every (plane, view) pair is one slot
     OmegaTail q;
     fill_tail(q, tail_host);
     size_t P = (size_t)H * W;
@@ -383,15 +393,15 @@ extern "C" int aarmvs_omega_stats(int stage, const float* t0, int H, int W, int 
 
 extern "C" int aarmvs_aggregate(const float* ref, const float* src, size_t view_stride, int H, int W, int S,
                                 const float* cams, const float* tail_host, const float* depth_values, int d_host,
-                                const int* d_dev, int align_corners, const float* t0, const double* stats, float* cost,
-                                float* reweight_out, void* stream) {
+                                const int* d_dev, int planes, int align_corners, const float* t0, const double* stats,
+                                float* cost, float* reweight_out, void* stream) {
     AARMVS_CHECK_ARG(ref && src && t0 && stats && cost && tail_host && depth_values && cams && H > 0 && W > 0);
-    AARMVS_CHECK_ARG(S >= 1 && S <= AARMVS_MAX_SRC);
+    AARMVS_CHECK_ARG(S >= 1 && S <= AARMVS_MAX_SRC && planes >= 1 && planes <= AARMVS_MAX_PLANES);
     OmegaTail q;
     fill_tail(q, tail_host);
     const int ntiles = ((W + AG_TW - 1) / AG_TW) * ((H + AG_TH - 1) / AG_TH);
     const int blocks = ntiles < 148 * 8 ? ntiles : 148 * 8;
-    aggregate_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(ref, src, view_stride, H, W, S, cams, q, depth_values, d_host,
+    aggregate_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(ref, src, view_stride, H, W, S, planes, cams, q, depth_values, d_host,
                                                               d_dev, align_corners, t0, stats, cost, reweight_out);
     AARMVS_LAUNCH_RESULT();
 }

@@ -3,9 +3,10 @@ weights, and the per-plane kernel chain, which is captured once into a CUDA grap
 plane (the plane index lives in device memory).  PyTorch is used for device memory and streams only.
 
 Per view (FeatNet, models/drmvsnet.py:41-63):   16 launches.
-Per depth plane (models/drmvsnet.py:306-334):   cost_stem, omega_stats x2, aggregate, cell0, cell1, cell2, deconv_0,
-                                                cell3, deconv_1, cell4, head_wta, next_plane = 13 launches, 0 host syncs
-                                                (the reference issues ~526 ATen ops and 12 host syncs).
+Per batch of K depth planes (models/drmvsnet.py:306-334): cost_stem, omega_stats x2, aggregate once for the K planes,
+                                                then per plane cell0, cell1, cell2, deconv_0, cell3, deconv_1, cell4,
+                                                head_wta, next_plane: 4 + 9 K launches, 0 host syncs
+                                                (the reference issues ~526 ATen ops and 12 host syncs PER PLANE).
 """
 import ctypes
 
@@ -42,10 +43,13 @@ def _src_array(*srcs):
 class Engine:
     """Runs EMVSNet.forward's arithmetic for one model instance (weights are re-packed when they change)."""
 
-    def __init__(self, module, align_corners=False, use_graph=True, cell_math="tc"):
+    def __init__(self, module, align_corners=False, use_graph=True, cell_math="tc", plane_batch=8):
         if cell_math not in ("tc", "fma"):
             raise ValueError("cell_math must be 'tc' (tcgen05, split-fp16 operands) or 'fma' (fp32 CUDA cores)")
         self.cell_math = cell_math
+        if not 1 <= plane_batch <= 16:
+            raise ValueError("plane_batch must be in 1..16")
+        self.plane_batch = plane_batch            # planes per launch of passes A-D (L1/L2 reuse of the source features)
         self.module = module
         self.align_corners = bool(align_corners)     # grid_sample default under torch >= 1.3 is False (SURVEY.md §0.5)
         self.use_graph = use_graph
@@ -118,7 +122,8 @@ class Engine:
             raise RuntimeError(f"2..16 views supported, got {N}")
         f32 = dict(device=device, dtype=torch.float32)
         P, S = H * W, N - 1
-        ws = {"H": H, "W": W, "N": N, "D": D, "graph": None, "warm": False}
+        K = min(self.plane_batch, D)
+        ws = {"H": H, "W": W, "N": N, "D": D, "K": K, "graph": None, "warm": False}
         ws["feat"] = torch.empty(N, P, 32, **f32)
         # FeatNet scratch (reused for every view)
         ws["a1"] = torch.empty(P, 8, **f32)
@@ -131,13 +136,13 @@ class Engine:
             ws[f"m{l}"] = torch.empty(pl, 16 if l == 0 else 8, **f32)
         ws["fsums"] = torch.zeros(64, device=device, dtype=torch.float64)
         # plane sweep
-        ws["t0"] = torch.empty(S, P, 4, **f32)
-        ws["cost"] = torch.empty(P, 32, **f32)
+        ws["t0"] = torch.empty(K, S, P, 4, **f32)
+        ws["cost"] = torch.empty(K, P, 32, **f32)
         ws["h"] = [torch.empty(2, P // (s * s), ch, **f32) for ch, s in zip(_HID, _SCALE)]
         ws["c"] = [torch.empty(P // (s * s), ch, **f32) for ch, s in zip(_HID, _SCALE)]
         ws["up0"] = torch.empty(P // 4, 16, **f32)
         ws["up1"] = torch.empty(P, 16, **f32)
-        ws["psums"] = torch.zeros(S * 6 + 8, device=device, dtype=torch.float64)
+        ws["psums"] = torch.zeros(K * S * 6 + 8, device=device, dtype=torch.float64)
         ws["plane"] = torch.zeros(1, device=device, dtype=torch.int32)
         ws["cams"] = torch.empty(S, 12, **f32)
         ws["depths"] = torch.empty(D, **f32)
@@ -195,19 +200,20 @@ class Engine:
                                             _ptr(g1[0]), _ptr(g1[1]), _ptr(g2[0]), _ptr(g2[1]), H, W, _ptr(out), stream),
                    "aarmvs_feat_assemble")
 
-    def cost_stem(self, ref, src, view_stride, H, W, S, cams, w, depths, d_host, dptr, t0, sums, stream):
+    def cost_stem(self, ref, src, view_stride, H, W, S, cams, w, depths, d_host, dptr, planes, t0, sums, stream):
         """Pass A (gather, (warp - ref)^2, omega stem conv) on the tensor cores ('tc') or the fp32 FMA pipe ('fma')."""
         ac = int(self.align_corners)
         if self.cell_math == "tc":
             capi.check(self.lib.aarmvs_cost_stem_tc(ref, src, view_stride, H, W, S, cams, _ptr(w["stem.wtc"]), w["stem.b_host"],
-                                                    depths, d_host, dptr, ac, t0, sums, stream), "aarmvs_cost_stem_tc")
+                                                    depths, d_host, dptr, planes, ac, t0, sums, stream), "aarmvs_cost_stem_tc")
         else:
             capi.check(self.lib.aarmvs_cost_stem(ref, src, view_stride, H, W, S, cams, w["stem.w_host"], w["stem.b_host"],
-                                                 depths, d_host, dptr, ac, t0, sums, stream), "aarmvs_cost_stem")
+                                                 depths, d_host, dptr, planes, ac, t0, sums, stream), "aarmvs_cost_stem")
 
     # ------------------------------------------------------------------------------------------ one plane
-    def _plane(self, ws, w, stream, marks=None):
-        """Enqueue the kernel chain of one depth plane; the plane index is read from ws['plane'] on the device.
+    def _batch(self, ws, w, stream, nplanes, marks=None):
+        """Enqueue the kernel chain of `nplanes` consecutive depth planes starting at the plane index held in
+        ws['plane'] (device memory): passes A-D once for the whole batch, then the recurrence plane by plane.
         marks: optional list collecting (stage name, CUDA event) after each stage (bench.py's per-kernel timing)."""
         lib, H, W, N = self.lib, ws["H"], ws["W"], ws["N"]
 
@@ -222,14 +228,16 @@ class Engine:
         feat, dptr, ac = ws["feat"], _ptr(ws["plane"]), int(self.align_corners)
         ref, src = _ptr(feat), _ptr(feat, P * 32)
         ps = ws["psums"]
-        self.cost_stem(ref, src, P * 32, H, W, S, _ptr(ws["cams"]), w, _ptr(ws["depths"]), 0, dptr, _ptr(ws["t0"]), _ptr(ps), stream)
+        n_omega = ws["K"] * S * 6
+        self.cost_stem(ref, src, P * 32, H, W, S, _ptr(ws["cams"]), w, _ptr(ws["depths"]), 0, dptr, nplanes, _ptr(ws["t0"]),
+                       _ptr(ps), stream)
         mark("cost_stem")
         for stage in (2, 3):
-            capi.check(lib.aarmvs_omega_stats(stage, _ptr(ws["t0"]), H, W, S, w["tail_host"], _ptr(ps), stream),
+            capi.check(lib.aarmvs_omega_stats(stage, _ptr(ws["t0"]), H, W, S, nplanes, w["tail_host"], _ptr(ps), stream),
                        "aarmvs_omega_stats")
         mark("omega_stats")
         capi.check(lib.aarmvs_aggregate(ref, src, P * 32, H, W, S, _ptr(ws["cams"]), w["tail_host"], _ptr(ws["depths"]), 0,
-                                        dptr, ac, _ptr(ws["t0"]), _ptr(ps), _ptr(ws["cost"]), None, stream),
+                                        dptr, nplanes, ac, _ptr(ws["t0"]), _ptr(ps), _ptr(ws["cost"]), None, stream),
                    "aarmvs_aggregate")
         mark("aggregate")
         h, c = ws["h"], ws["c"]
@@ -249,30 +257,35 @@ class Engine:
                            f"aarmvs_convlstm_cell[{i}]")
             mark(f"cell{i}")
 
-        def deconv(i, src, hin, win, dst, sums):
-            capi.check(lib.aarmvs_deconv2x(ctypes.byref(src), hin, win, _ptr(w[f"deconv{i}.w"]), _ptr(w[f"deconv{i}.b"]),
+        def deconv(i, src_, hin, win, dst, sums):
+            capi.check(lib.aarmvs_deconv2x(ctypes.byref(src_), hin, win, _ptr(w[f"deconv{i}.w"]), _ptr(w[f"deconv{i}.b"]),
                                            _ptr(dst), _ptr(sums), 0, dptr, stream), f"aarmvs_deconv2x[{i}]")
             mark(f"deconv{i}")
 
         H2, W2, H4, W4 = H // 2, W // 2, H // 4, W // 4
-        s_up0, s_up1 = ps[S * 6:], ps[S * 6 + 4:]
-        cell(0, [_src(ws["cost"], 32)], H, W, 48)
-        cell(1, [hsrc(0, capi.SRC_MAXPOOL2)], H2, W2, 32)
-        cell(2, [hsrc(1, capi.SRC_MAXPOOL2)], H4, W4, 32)
-        deconv(0, hsrc(2), H4, W4, ws["up0"], s_up0)
-        up0 = _src(ws["up0"], 16, capi.SRC_GN_RELU, sums=s_up0, gn=w["deconv0.gn"], groups=2, count=8 * (P // 4))
-        cell(3, [up0, hsrc(1)], H2, W2, 48)
-        deconv(1, hsrc(3), H2, W2, ws["up1"], s_up1)
-        up1 = _src(ws["up1"], 16, capi.SRC_GN_RELU, sums=s_up1, gn=w["deconv1.gn"], groups=2, count=8 * P)
-        cell(4, [up1, hsrc(0)], H, W, 40)
-        h4 = hsrc(4)
+        s_up0, s_up1 = ps[n_omega:], ps[n_omega + 4:]
         cv = ws["cost_volume"]
-        capi.check(lib.aarmvs_head_wta(ctypes.byref(h4), H, W, w["head.w_host"], w["head.b_host"], _ptr(ws["depths"]),
-                                       ws["D"], 0, dptr, _ptr(ws["max_prob"]), _ptr(ws["depth"]), _ptr(ws["exp_sum"]),
-                                       _ptr(ws["index"]), _ptr(ws["conf"]), _ptr(cv) if cv is not None else None, stream),
-                   "aarmvs_head_wta")
-        capi.check(lib.aarmvs_next_plane(dptr, _ptr(ps), ps.numel(), stream), "aarmvs_next_plane")
-        mark("head_wta")
+        for k in range(nplanes):
+            cell(0, [_src(ws["cost"][k], 32)], H, W, 48)
+            cell(1, [hsrc(0, capi.SRC_MAXPOOL2)], H2, W2, 32)
+            cell(2, [hsrc(1, capi.SRC_MAXPOOL2)], H4, W4, 32)
+            deconv(0, hsrc(2), H4, W4, ws["up0"], s_up0)
+            up0 = _src(ws["up0"], 16, capi.SRC_GN_RELU, sums=s_up0, gn=w["deconv0.gn"], groups=2, count=8 * (P // 4))
+            cell(3, [up0, hsrc(1)], H2, W2, 48)
+            deconv(1, hsrc(3), H2, W2, ws["up1"], s_up1)
+            up1 = _src(ws["up1"], 16, capi.SRC_GN_RELU, sums=s_up1, gn=w["deconv1.gn"], groups=2, count=8 * P)
+            cell(4, [up1, hsrc(0)], H, W, 40)
+            h4 = hsrc(4)
+            capi.check(lib.aarmvs_head_wta(ctypes.byref(h4), H, W, w["head.w_host"], w["head.b_host"], _ptr(ws["depths"]),
+                                           ws["D"], 0, dptr, _ptr(ws["max_prob"]), _ptr(ws["depth"]), _ptr(ws["exp_sum"]),
+                                           _ptr(ws["index"]), _ptr(ws["conf"]), _ptr(cv) if cv is not None else None, stream),
+                       "aarmvs_head_wta")
+            # ++plane; zero the deconv GroupNorm sums (and, after the last plane of the batch, the omega sums too)
+            if k == nplanes - 1:
+                capi.check(lib.aarmvs_next_plane(dptr, _ptr(ps), ps.numel(), stream), "aarmvs_next_plane")
+            else:
+                capi.check(lib.aarmvs_next_plane(dptr, _ptr(s_up0), 8, stream), "aarmvs_next_plane")
+            mark("head_wta")
 
     # ------------------------------------------------------------------------------------------ one depth map
     @staticmethod
@@ -301,21 +314,25 @@ class Engine:
         ws["depths"].copy_(depth_values.to(torch.float32), non_blocking=True)
         ws["plane"].zero_()
         ws["psums"].zero_()
+        K = ws["K"]
+        full, rem = divmod(D, K)
         start = 0
-        if self.use_graph and ws["graph"] is None:
-            self._plane(ws, w, stream)            # plane 0 eagerly: also sets the kernels' launch attributes
+        if self.use_graph and ws["graph"] is None and full > 0:
+            self._batch(ws, w, stream, K)         # first batch eagerly: also sets the kernels' launch attributes
             start = 1
             torch.cuda.synchronize(device)
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 cap = ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
-                self._plane(ws, w, cap)
+                self._batch(ws, w, cap, K)
             ws["graph"] = g
-        for _ in range(start, D):
+        for _ in range(start, full):
             if self.use_graph:
                 ws["graph"].replay()
             else:
-                self._plane(ws, w, stream)
+                self._batch(ws, w, stream, K)
+        if rem:
+            self._batch(ws, w, stream, rem)       # last partial batch
         out = {"depth": ws["depth"].view(H, W), "photometric_confidence": ws["conf"].view(H, W),
                "index": ws["index"].view(H, W)}
         if keep_cost:

@@ -79,11 +79,11 @@ def aggregate_plane(model, ref_fea, src_feas, ref_proj, src_projs, depth_value):
     cost = torch.empty(P, 32, device=dev)
     rew = torch.empty(S, P, device=dev)
     st, ac = _stream(dev), int(eng.align_corners)
-    eng.cost_stem(_ptr(feat), _ptr(feat, P * 32), P * 32, H, W, S, _ptr(cams), w, _ptr(depths), 0, None, _ptr(t0), _ptr(sums), st)
+    eng.cost_stem(_ptr(feat), _ptr(feat, P * 32), P * 32, H, W, S, _ptr(cams), w, _ptr(depths), 0, None, 1, _ptr(t0), _ptr(sums), st)
     for stage in (2, 3):
-        capi.check(lib.aarmvs_omega_stats(stage, _ptr(t0), H, W, S, w["tail_host"], _ptr(sums), st), "aarmvs_omega_stats")
+        capi.check(lib.aarmvs_omega_stats(stage, _ptr(t0), H, W, S, 1, w["tail_host"], _ptr(sums), st), "aarmvs_omega_stats")
     capi.check(lib.aarmvs_aggregate(_ptr(feat), _ptr(feat, P * 32), P * 32, H, W, S, _ptr(cams), w["tail_host"],
-                                    _ptr(depths), 0, None, ac, _ptr(t0), _ptr(sums), _ptr(cost), _ptr(rew), st),
+                                    _ptr(depths), 0, None, 1, ac, _ptr(t0), _ptr(sums), _ptr(cost), _ptr(rew), st),
                "aarmvs_aggregate")
     return -_nchw(cost, H, W), rew.view(S, H, W)
 

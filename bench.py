@@ -143,25 +143,28 @@ def config_dict(workload):
     H, W, N, D, ckpt, mode = WORKLOADS[workload]
     return {"workload": f"{workload}: AA-RMVSNet test-phase forward, {W}x{H}, N={N} views, D={D} {mode} depth planes, {ckpt}, "
                         "synthetic N(0,1) images + ring cameras", "height": H, "width": W, "views": N, "planes": D,
-            "checkpoint": ckpt, "l2": "per-step working set (features 1.7 GB + state 0.9 GB at cfg2) exceeds the 126 MB L2"}
+            "checkpoint": ckpt, "plane_batch": 8, "l2": "per-step working set (features 1.7 GB + state 0.9 GB at cfg2) exceeds the 126 MB L2"}
 
 
 # ------------------------------------------------------------------------------------------------- GPU arm
-def stage_profile(engine, ws, w, planes=12):
-    """Per-stage CUDA-event timing of the plane chain, eager launches on the current stream (ms per plane)."""
+def stage_profile(engine, ws, w, batches=3):
+    """Per-stage CUDA-event timing of the plane chain, eager launches on the current stream -> ms PER PLANE
+    (passes A-D run once per batch of K planes: their time is divided by K)."""
     import ctypes
     stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    K = ws["K"]
     acc = {}
-    for it in range(planes + 2):
+    for it in range(batches + 1):
         marks = []
         ws["plane"].fill_(1)
-        engine._plane(ws, w, stream, marks)
+        engine._batch(ws, w, stream, K, marks)
         torch.cuda.synchronize()
-        if it < 2:
+        if it < 1:
             continue
         for (n0, e0), (n1, e1) in zip(marks[:-1], marks[1:]):
             acc.setdefault(n1, []).append(e0.elapsed_time(e1))
-    return {k: sum(v) / len(v) for k, v in acc.items()}
+    per_batch = ("cost_stem", "omega_stats", "aggregate")
+    return {k: (sum(v) / batches / K if k in per_batch else sum(v) / len(v)) for k, v in acc.items()}
 
 
 def run_ours(args):
@@ -294,7 +297,7 @@ def run_ours(args):
                 "config": config_dict(args.workload), "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": "depth maps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_e2e / args.steps},
-                "gpu_launches": args.steps * (N * 16 + D * 13), "roofline": roofline, "cpu_baseline": cpu, **extra}
+                "gpu_launches": args.steps * (N * 16 + (D // eng.plane_batch) * 4 + D * 9), "roofline": roofline, "cpu_baseline": cpu, **extra}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

@@ -21,8 +21,9 @@ extern "C" {
 
 #define AARMVS_ERR_ARG 1000001
 #define AARMVS_MAX_SRC_VIEWS 15
+#define AARMVS_MAX_PLANES_PER_CALL 16
 
-int aarmvs_version(void);          /* ABI version, currently 1 */
+int aarmvs_version(void);          /* ABI version, currently 2 */
 int aarmvs_sm_count(void);         /* multiprocessors of the current device (148 on B200), <0 on error */
 
 /* ---------------------------------------------------------------------------------------------------------
@@ -79,8 +80,14 @@ int aarmvs_feat_assemble(const float* m0, const float* m1, const float* m2, cons
 int aarmvs_warp(const float* src, float* out, int H, int W, const float* cam_host, float depth, int align_corners,
                 void* stream);
 
-size_t aarmvs_omega_stats_bytes(int S);    /* S * 3 GroupNorms * (sum, sumsq) doubles; zero before each plane */
+size_t aarmvs_omega_stats_bytes(int S);    /* S * 3 GroupNorms * (sum, sumsq) doubles PER PLANE; zero before use */
 int aarmvs_omega_tail_floats(void);        /* length of the packed omega tail parameter block (floats) */
+
+/* PLANE BATCHING.  Passes A-D have no dependency across depth planes (only the recurrence has), so each call handles
+ * `planes` (1..16) consecutive planes d .. d+planes-1 in (tile, view, plane) order: the source-feature lines a tile
+ * touches at plane k+1 are almost the ones of plane k and are served from L1/L2 instead of HBM.
+ * Layouts: t0 [planes][S][H*W][4], stats [planes][S][3][2] doubles, cost [planes][H*W][32], reweight_out [planes][S][H*W].
+ */
 
 /* Pass A: for each of S source views gather at depth_values[d], c = (warp - ref)^2, t0 = conv3x3 32->4 (+bias)
  * (omega.reweight_network.0.0, models/drmvsnet.py:31); writes t0 [S][H*W][4] and GroupNorm-1 sums.
@@ -88,24 +95,24 @@ int aarmvs_omega_tail_floats(void);        /* length of the packed omega tail pa
  * stem_w_host: [9][32][4] tap-major, stem_b_host: [4] (host: baked into the kernel parameter bank). */
 int aarmvs_cost_stem(const float* ref, const float* src, size_t view_stride, int H, int W, int S, const float* cams,
                      const float* stem_w_host, const float* stem_b_host, const float* depth_values, int d_host,
-                     const int* d_dev, int align_corners, float* t0, double* stats, void* stream);
+                     const int* d_dev, int planes, int align_corners, float* t0, double* stats, void* stream);
 
 /* Pass A with the 3x3 stem conv on the tensor cores (tcgen05 implicit GEMM over the staged (warp - ref)^2 halo tile,
  * split-fp16 operands, fp32 accumulation in TMEM).  Arguments as aarmvs_cost_stem except
  * stem_w_f16: DEVICE [2 planes hi,lo][9 taps][4][16][8] fp16 (output channels padded 4 -> 16 with zeros). */
 int aarmvs_cost_stem_tc(const float* ref, const float* src, size_t view_stride, int H, int W, int S, const float* cams,
                         const void* stem_w_f16, const float* stem_b_host, const float* depth_values, int d_host,
-                        const int* d_dev, int align_corners, float* t0, double* stats, void* stream);
+                        const int* d_dev, int planes, int align_corners, float* t0, double* stats, void* stream);
 
 /* Pass B (stage 2) / pass C (stage 3): GroupNorm-2 / GroupNorm-3 sums of the omega residual block
  * (models/module.py:256-258) recomputed point-wise from t0.  tail_host: aarmvs_omega_tail_floats() floats. */
-int aarmvs_omega_stats(int stage, const float* t0, int H, int W, int S, const float* tail_host, double* stats,
-                       void* stream);
+int aarmvs_omega_stats(int stage, const float* t0, int H, int W, int S, int planes, const float* tail_host,
+                       double* stats, void* stream);
 
 /* Pass D: cost[p][c] = -(sum_v (omega_v(p) + 1) * (warp_v - ref)^2) / S  (models/drmvsnet.py:311-319), the input
  * of the recurrent regulariser.  reweight_out: optional [S][H*W] omega maps (operator seam / tests), may be NULL. */
 int aarmvs_aggregate(const float* ref, const float* src, size_t view_stride, int H, int W, int S, const float* cams,
-                     const float* tail_host, const float* depth_values, int d_host, const int* d_dev,
+                     const float* tail_host, const float* depth_values, int d_host, const int* d_dev, int planes,
                      int align_corners, const float* t0, const double* stats, float* cost, float* reweight_out,
                      void* stream);
 
