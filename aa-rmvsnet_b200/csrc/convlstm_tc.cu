@@ -46,6 +46,7 @@ struct TcArgs {
     float* c_state;
     int d_host;
     const int* d_dev;
+    unsigned long long* prof;   // debug: per-tile clock64 stamps of CTA 0 ([tile][12]), or null
 };
 
 constexpr int TR = 16, TCOL = 8, HR = TR + 2, HC = TCOL + 2, NPX = HR * HC;   // 180 staged pixels per tile
@@ -136,7 +137,12 @@ __global__ void __launch_bounds__(N_THREADS, 1) convlstm_tc_kernel(const __grid_
 
     if (warp >= FIRST_LOAD_WARP) {
         // =========================================== loaders ===========================================
-        const int lt = tid - FIRST_LOAD_WARP * 32;               // 0..255
+        // One item = 8 channels (32 B of fp32 -> one 16-byte fp16 chunk per plane) of one staged pixel.  The decoding of a
+        // thread's items (source, pixel, channel) does not depend on the tile and is done once; per tile an item costs
+        // an address, two (max-pool: eight) 16-byte loads, the split and two conflict-free 16-byte stores.
+        const int lt = tid - FIRST_LOAD_WARP * 32;
+        constexpr int LT = N_LOAD_WARPS * 32;
+        constexpr int ITEMS = (C::KC8 * NPX + LT - 1) / LT;
         const float* sptr[3];
         int sbase[4] = {0, 0, 0, 0};
         for (int s = 0; s < 3; ++s) {
@@ -149,70 +155,94 @@ __global__ void __launch_bounds__(N_THREADS, 1) convlstm_tc_kernel(const __grid_
                 sbase[s + 1] = sbase[s];
             }
         }
+        // per item: meta = source (2 bits; 3 = zero fill) | row << 2 | col << 7 | local channel << 11 | mode << 17, and
+        // the source's channel count
+        int meta[ITEMS], sch[ITEMS];
+        const float* base[ITEMS];
+#pragma unroll
+        for (int k = 0; k < ITEMS; ++k) {
+            const int idx = lt + k * LT;
+            int m = 3, ch = 0;
+            base[k] = nullptr;
+            if (idx < C::KC8 * NPX) {
+                const int kc = idx / NPX, px = idx - kc * NPX;
+                const int r = px / HC, cc = px - r * HC, c = kc * 8;
+                if (c < sbase[a.nsrc]) {
+                    const int s = c < sbase[1] ? 0 : (c < sbase[2] ? 1 : 2);
+                    const bool zero_h = (s == a.nsrc - 1 && d == 0);              // h_{-1} = 0 (module.py:94-96)
+                    if (!zero_h) {
+                        m = s | (r << 2) | (cc << 7) | ((c - sbase[s]) << 11) | (a.src[s].mode << 17);
+                        ch = a.src[s].ch;
+                        base[k] = (s == 0 ? sptr[0] : s == 1 ? sptr[1] : sptr[2]) + (c - sbase[s]);
+                    } else {
+                        m = 3 | (r << 2) | (cc << 7);
+                    }
+                } else {
+                    m = 3 | (r << 2) | (cc << 7);
+                }
+            } else {
+                m = -1;                                                             // no item
+            }
+            meta[k] = m; sch[k] = ch;
+        }
         int it = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
             const int st = it % N_STAGES;
-            tc::mbar_wait_relaxed(&empty_a[st], ((it / N_STAGES) & 1) ^ 1);
+            const bool pf = a.prof && blockIdx.x == 0 && lt == 0 && it < 64;
+            if (pf) a.prof[it * 12 + 0] = clock64();
             const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
             const int y0 = ty * TR - 1, x0 = tx * TCOL - 1;
-            unsigned char* stage = sA + st * C::A_STAGE;
-            // two sweeps so that all global loads of this thread are in flight before the first conversion / store
-            constexpr int ITEMS = (C::KC8 * NPX + N_LOAD_WARPS * 32 - 1) / (N_LOAD_WARPS * 32);
-            float v[ITEMS][8];
+            // loads first (registers), then wait for the stage, then convert + store
+            float4 va[ITEMS], vb[ITEMS];
 #pragma unroll
             for (int k = 0; k < ITEMS; ++k) {
-                const int idx = lt + k * N_LOAD_WARPS * 32;
-#pragma unroll
-                for (int e = 0; e < 8; ++e) v[k][e] = 0.f;
-                if (idx >= C::KC8 * NPX) continue;
-                const int kc = idx / NPX, px = idx - kc * NPX;
-                const int r = px / HC, cc = px - r * HC;
-                const int y = y0 + r, x = x0 + cc;
-                const int c = kc * 8;
-                if (y >= 0 && y < a.H && x >= 0 && x < a.W && c < sbase[a.nsrc]) {
-                    const int s = c < sbase[1] ? 0 : (c < sbase[2] ? 1 : 2);
-                    const TcSrc& S = a.src[s];
-                    const float* sp = s == 0 ? sptr[0] : s == 1 ? sptr[1] : sptr[2];
-                    const int cl = c - sbase[s];
-                    if (s == a.nsrc - 1 && d == 0) {
-                        // h_{-1} = 0 (module.py:94-96)
-                    } else if (S.mode == AARMVS_SRC_MAXPOOL2) {
-                        const size_t rowp = (size_t)2 * a.W * S.ch;
-                        const float* p = sp + (size_t)(2 * y) * rowp + (size_t)(2 * x) * S.ch + cl;
-#pragma unroll
-                        for (int hh = 0; hh < 2; ++hh) {
-                            const float4 q0 = ldg4(p + hh * 4), q1 = ldg4(p + S.ch + hh * 4), q2 = ldg4(p + rowp + hh * 4),
-                                         q3 = ldg4(p + rowp + S.ch + hh * 4);
-                            v[k][hh * 4 + 0] = fmaxf(fmaxf(q0.x, q1.x), fmaxf(q2.x, q3.x));
-                            v[k][hh * 4 + 1] = fmaxf(fmaxf(q0.y, q1.y), fmaxf(q2.y, q3.y));
-                            v[k][hh * 4 + 2] = fmaxf(fmaxf(q0.z, q1.z), fmaxf(q2.z, q3.z));
-                            v[k][hh * 4 + 3] = fmaxf(fmaxf(q0.w, q1.w), fmaxf(q2.w, q3.w));
-                        }
-                    } else {
-                        const float* p = sp + ((size_t)y * a.W + x) * S.ch + cl;
-                        const float4 q0 = ldg4(p), q1 = ldg4(p + 4);
-                        v[k][0] = q0.x; v[k][1] = q0.y; v[k][2] = q0.z; v[k][3] = q0.w;
-                        v[k][4] = q1.x; v[k][5] = q1.y; v[k][6] = q1.z; v[k][7] = q1.w;
-                        if (S.mode == AARMVS_SRC_GN_RELU) {
-#pragma unroll
-                            for (int e = 0; e < 8; ++e) v[k][e] = fmaxf(fmaf(v[k][e], s_scale[c + e], s_shift[c + e]), 0.f);
-                        }
+                va[k] = vb[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                const int m = meta[k];
+                if (m < 0 || (m & 3) == 3) continue;
+                const int y = y0 + ((m >> 2) & 31), x = x0 + ((m >> 7) & 15);
+                if (y < 0 || y >= a.H || x < 0 || x >= a.W) continue;
+                const int mode = m >> 17;
+                if (mode == AARMVS_SRC_MAXPOOL2) {
+                    const size_t rowp = (size_t)2 * a.W * sch[k];
+                    const float* p = base[k] + (size_t)(2 * y) * rowp + (size_t)(2 * x) * sch[k];
+                    const float4 q0 = ldg4(p), q1 = ldg4(p + sch[k]), q2 = ldg4(p + rowp), q3 = ldg4(p + rowp + sch[k]);
+                    const float4 r0 = ldg4(p + 4), r1 = ldg4(p + sch[k] + 4), r2 = ldg4(p + rowp + 4), r3 = ldg4(p + rowp + sch[k] + 4);
+                    va[k] = make_float4(fmaxf(fmaxf(q0.x, q1.x), fmaxf(q2.x, q3.x)), fmaxf(fmaxf(q0.y, q1.y), fmaxf(q2.y, q3.y)),
+                                        fmaxf(fmaxf(q0.z, q1.z), fmaxf(q2.z, q3.z)), fmaxf(fmaxf(q0.w, q1.w), fmaxf(q2.w, q3.w)));
+                    vb[k] = make_float4(fmaxf(fmaxf(r0.x, r1.x), fmaxf(r2.x, r3.x)), fmaxf(fmaxf(r0.y, r1.y), fmaxf(r2.y, r3.y)),
+                                        fmaxf(fmaxf(r0.z, r1.z), fmaxf(r2.z, r3.z)), fmaxf(fmaxf(r0.w, r1.w), fmaxf(r2.w, r3.w)));
+                } else {
+                    const float* p = base[k] + ((size_t)y * a.W + x) * sch[k];
+                    va[k] = ldg4(p);
+                    vb[k] = ldg4(p + 4);
+                    if (mode == AARMVS_SRC_GN_RELU) {          // the conv pads with zeros AFTER GroupNorm + ReLU
+                        const int c = sbase[m & 3] + ((m >> 11) & 63);
+                        const float* sc = s_scale + c;
+                        const float* sh = s_shift + c;
+                        va[k].x = fmaxf(fmaf(va[k].x, sc[0], sh[0]), 0.f); va[k].y = fmaxf(fmaf(va[k].y, sc[1], sh[1]), 0.f);
+                        va[k].z = fmaxf(fmaf(va[k].z, sc[2], sh[2]), 0.f); va[k].w = fmaxf(fmaf(va[k].w, sc[3], sh[3]), 0.f);
+                        vb[k].x = fmaxf(fmaf(vb[k].x, sc[4], sh[4]), 0.f); vb[k].y = fmaxf(fmaf(vb[k].y, sc[5], sh[5]), 0.f);
+                        vb[k].z = fmaxf(fmaf(vb[k].z, sc[6], sh[6]), 0.f); vb[k].w = fmaxf(fmaf(vb[k].w, sc[7], sh[7]), 0.f);
                     }
                 }
             }
+            tc::mbar_wait_relaxed(&empty_a[st], ((it / N_STAGES) & 1) ^ 1);
+            if (pf) a.prof[it * 12 + 1] = clock64();
+            unsigned char* stage = sA + st * C::A_STAGE;
 #pragma unroll
             for (int k = 0; k < ITEMS; ++k) {
-                const int idx = lt + k * N_LOAD_WARPS * 32;
-                if (idx >= C::KC8 * NPX) continue;
+                if (meta[k] < 0) continue;
+                const int idx = lt + k * LT;
                 uint2 h0, l0, h1, l1;
-                tc::split4_f16(make_float4(v[k][0], v[k][1], v[k][2], v[k][3]), h0, l0);
-                tc::split4_f16(make_float4(v[k][4], v[k][5], v[k][6], v[k][7]), h1, l1);
-                const uint4 uh = make_uint4(h0.x, h0.y, h1.x, h1.y), ul = make_uint4(l0.x, l0.y, l1.x, l1.y);
-                *reinterpret_cast<uint4*>(stage + (size_t)idx * 16) = uh;
-                *reinterpret_cast<uint4*>(stage + C::A_PLANE + (size_t)idx * 16) = ul;
+                tc::split4_f16(va[k], h0, l0);
+                tc::split4_f16(vb[k], h1, l1);
+                *reinterpret_cast<uint4*>(stage + (size_t)idx * 16) = make_uint4(h0.x, h0.y, h1.x, h1.y);
+                *reinterpret_cast<uint4*>(stage + C::A_PLANE + (size_t)idx * 16) = make_uint4(l0.x, l0.y, l1.x, l1.y);
             }
+            if (pf) a.prof[it * 12 + 2] = clock64();
             tc::fence_async_smem();
             tc::mbar_arrive(&full_a[st]);
+            if (pf) a.prof[it * 12 + 3] = clock64();
         }
     } else if (warp == MMA_WARP) {
         // =========================================== MMA issuer ===========================================
@@ -226,9 +256,13 @@ __global__ void __launch_bounds__(N_THREADS, 1) convlstm_tc_kernel(const __grid_
         int it = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
             const int st = it % N_STAGES, ab = it & 1;
+            const bool pf = a.prof && blockIdx.x == 0 && leader && it < 64;
+            if (pf) a.prof[it * 12 + 4] = clock64();
             tc::mbar_wait(&full_a[st], (it / N_STAGES) & 1);
+            if (pf) a.prof[it * 12 + 5] = clock64();
             tc::mbar_wait(&tmem_empty[ab], ((it >> 1) & 1) ^ 1);
             tc::tc_fence_after();
+            if (pf) a.prof[it * 12 + 6] = clock64();
             const uint32_t dst = tmem_base + ab * NG;
             const uint32_t a_lo_hi = tc::desc_lo(a_base + st * C::A_STAGE, NPX * 16);
             const uint32_t a_lo_lo = tc::desc_lo(a_base + st * C::A_STAGE + C::A_PLANE, NPX * 16);
@@ -247,6 +281,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) convlstm_tc_kernel(const __grid_
                 tc::mma_commit(&empty_a[st]);          // operand stage free once these MMAs have read it
                 tc::mma_commit(&tmem_full[ab]);        // accumulator complete
             }
+            if (pf) a.prof[it * 12 + 7] = clock64();
             __syncwarp();
         }
     } else {
@@ -258,13 +293,17 @@ __global__ void __launch_bounds__(N_THREADS, 1) convlstm_tc_kernel(const __grid_
         int it = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
             const int ab = it & 1;
+            const bool pf = a.prof && blockIdx.x == 0 && tid == 0 && it < 64;
+            if (pf) a.prof[it * 12 + 8] = clock64();
             tc::mbar_wait_relaxed(&tmem_full[ab], (it >> 1) & 1);
             tc::tc_fence_after();
+            if (pf) a.prof[it * 12 + 9] = clock64();
             float g[NCOL];
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + ab * NG + hf * NCOL;
             if constexpr (NCOL == 32) tc::tmem_ld32(taddr, g); else tmem_ld16(taddr, g);
             tc::tc_fence_before();
             tc::mbar_arrive(&tmem_empty[ab]);                    // accumulator is in registers: release it
+            if (pf) a.prof[it * 12 + 10] = clock64();
             const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
             const int y = ty * TR + (m >> 3), x = tx * TCOL + (m & 7);
             if (y < a.H && x < a.W) {
@@ -293,6 +332,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) convlstm_tc_kernel(const __grid_
                     st4(hp + j, make_float4(hn[j], hn[j + 1], hn[j + 2], hn[j + 3]));
                 }
             }
+            if (pf) a.prof[it * 12 + 11] = clock64();
         }
     }
     tc::tc_fence_before();
@@ -317,7 +357,12 @@ int launch_tc(const TcArgs& a, cudaStream_t stream) {
     AARMVS_LAUNCH_RESULT();
 }
 
+unsigned long long* g_prof = nullptr;
+
 }  // namespace
+
+// Debug only: CTA 0 of the next ConvLSTM launches writes clock64 stamps per tile ([64][12] uint64) into `buf` (device).
+extern "C" void aarmvs_debug_profile_buffer(void* buf) { g_prof = (unsigned long long*)buf; }
 
 extern "C" int aarmvs_convlstm_cell_tc(const aarmvs_conv_src* src, int nsrc, int H, int W, int cin, int hidden,
                                        const void* weight_f16, const float* bias_packed, float* h_pair, float* c_state,
@@ -343,7 +388,7 @@ extern "C" int aarmvs_convlstm_cell_tc(const aarmvs_conv_src* src, int nsrc, int
     }
     AARMVS_CHECK_ARG(csum == cin && cin <= 48);
     a.H = H; a.W = W; a.weight = (const __half*)weight_f16; a.bias = bias_packed; a.h_pair = h_pair; a.c_state = c_state;
-    a.d_host = d_host; a.d_dev = d_dev;
+    a.d_host = d_host; a.d_dev = d_dev; a.prof = g_prof;
     cudaStream_t st = (cudaStream_t)stream;
     if (cin == 48 && hidden == 16) return launch_tc<3, 64>(a, st);     // cells 0, 3
     if (cin == 32 && hidden == 16) return launch_tc<2, 64>(a, st);     // cells 1, 2

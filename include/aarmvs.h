@@ -163,6 +163,11 @@ int aarmvs_next_plane(int* d_dev, double* sums, int nzero, void* stream);
 int aarmvs_tc_selftest(const void* a_f16, int a_rows, const void* b_f16, float* d, int K, int group_rows, int shift,
                        void* stream);
 
+/* Debug aid (the only process-global state in the library, off by default): when set to a device buffer of
+ * 64 x 12 uint64, CTA 0 of subsequent aarmvs_convlstm_cell_tc launches records clock64 stamps of its loader / MMA /
+ * epilogue roles per tile.  Pass NULL to switch off. */
+void aarmvs_debug_profile_buffer(void* buf);
+
 #ifdef __cplusplus
 }
 #endif
