@@ -1,13 +1,17 @@
 // Pass A of the plane sweep on the tensor cores (models/module.py:6-38,
 // models/drmvsnet.py:31,311): for every source view, bilinear gather at depth d, c = (warp - ref)^2, and the omega
-// stem 3x3 conv 32 -> 4 as a tcgen05 implicit GEMM over the staged (warp - ref)^2 halo tile.
+// stem 3x3 conv 32 -> 4 (omega.reweight_network.0.0) on tcgen05.
 //
-// Same tile / operand scheme as convlstm_tc.cu: 16 x 8 pixel tiles = the 128 accumulator rows, halo tile 18 x 10
-// staged once as un-swizzled K-major fp16 (hi, lo) planes [8-channel chunk][pixel][16 B]; a 3x3 tap is a start-address
-// shift.  N = 16 accumulator columns (4 real output channels; tcgen05 needs N % 16 == 0 at M = 128).
-// The gather is the expensive part (4 taps + ref = five 128-byte lines per pixel and view): 12 loader warps, 8 lanes per
-// pixel (one 128-byte line per tap and 8-lane group), sample positions computed once per pixel into shared memory.
-// Roles: warps 0-3 epilogue (TMEM -> +bias -> t0, GroupNorm-1 sums), warp 4 TMEM + MMA issue, warps 5-16 loaders.
+// The conv is evaluated as  z[p][tap][o] = sum_c c[p][c] * w[o][c][tap]   (one GEMM per staged halo tile: M = the 180
+// halo pixels in two 128-row blocks, N = 9 taps x 4 outputs = 36 -> 48, K = 32 channels)  followed by the 9-tap shifted
+// sum  t0[q][o] = b[o] + sum_tap z[q + tap][tap][o]  in the epilogue.  Compared with a shifted-window implicit GEMM with
+// N = 16 (one MMA per tap, each re-reading the 128-row operand) this cuts the tensor core's shared-memory operand
+// traffic from 243 KB to 66 KB per tile and view; shared-memory/L1 bandwidth is what bounds this kernel.
+// Operands: un-swizzled K-major fp16 (hi, lo) planes [8-channel chunk][row][16 B] (see convlstm_tc.cu / tc_common.cuh).
+// The gather: four loader groups of four warps, 8 lanes per pixel (one 128-byte line per tap and 8-lane group), sample
+// positions computed once per pixel into shared memory, fills ordered (tile, view, plane) for L1 reuse across planes.
+// Roles: warps 0-3 epilogue (TMEM -> z exchange through smem -> 9-tap sum -> t0, GroupNorm-1 sums), warp 4 TMEM + MMA
+// issue, warps 5-20 loaders.
 #include "common.cuh"
 #include "tc_common.cuh"
 #include "../../include/aarmvs.h"
@@ -15,15 +19,19 @@
 namespace {
 
 constexpr int TR = 16, TCOL = 8, HR = 18, HC = 10, NPX = HR * HC;        // 180 staged pixels
+constexpr int AROWS = 192;                                               // operand rows per K chunk (>= NPX; the second
+                                                                         // 128-row block reads garbage rows that nobody uses)
 constexpr int N_EPI = 4, MMA_WARP = 4, FIRST_LOAD = 5, N_LOAD = 16;
 constexpr int N_THREADS = (N_EPI + 1 + N_LOAD) * 32;                     // 672
 constexpr int LOAD_THREADS = N_LOAD * 32;                                // 512
 constexpr int N_STAGES = 4;
-constexpr int KC8 = 4, NCOLS = 16;
-constexpr int A_PLANE = KC8 * NPX * 16, A_STAGE = 2 * A_PLANE;           // 11520, 23040 bytes
-constexpr int B_PLANE = 9 * KC8 * NCOLS * 16, B_BYTES = 2 * B_PLANE;     // 9216, 18432 bytes
+constexpr int KC8 = 4, NZ = 48;                                          // K chunks; accumulator columns (36 used)
+constexpr int A_PLANE = KC8 * AROWS * 16, A_STAGE = 2 * A_PLANE;         // 12288, 24576 bytes
+constexpr int B_PLANE = KC8 * NZ * 16, B_BYTES = 2 * B_PLANE;            // 3072, 6144 bytes
 constexpr int TAP_BYTES = NPX * 48;                                      // one TapRec (48 B) per staged pixel
-constexpr int SMEM = B_BYTES + N_STAGES * (A_STAGE + TAP_BYTES) + 1024;
+constexpr int Z_BYTES = 9 * NPX * 16;                                    // z exchange buffer [tap][pixel][4 floats]
+constexpr int SMEM = B_BYTES + N_STAGES * (A_STAGE + TAP_BYTES) + 2 * Z_BYTES + 1024;
+constexpr int TMEM_COLS = 256;                                           // 2 accumulators x 2 row blocks x 48 columns
 
 struct StemArgs {
     const float* ref;
@@ -31,7 +39,7 @@ struct StemArgs {
     size_t view_stride;
     int H, W, S, K;             // K = planes per launch: fills run in (tile, view, plane) order so that a tile's source
     const float* cams;          //     lines stay in L1 across consecutive planes
-    const __half* weight;       // [2][9][4][16][8] fp16
+    const __half* weight;       // [2 planes hi,lo][4 chunks][48 columns (tap*4 + out)][8] fp16
     float bias[4];
     const float* depth_values;
     int d_host;
@@ -55,6 +63,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) cost_stem_tc_kernel(const __grid
     unsigned char* sB = smem;
     unsigned char* sA = smem + B_BYTES;
     unsigned char* sT = sA + N_STAGES * A_STAGE;
+    unsigned char* sZ = sT + N_STAGES * TAP_BYTES;
     __shared__ uint64_t full_a[N_STAGES], empty_a[N_STAGES], tmem_full[2], tmem_empty[2];
     __shared__ uint32_t tmem_base_s;
     __shared__ float scam[AARMVS_MAX_SRC * 12];
@@ -72,7 +81,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) cost_stem_tc_kernel(const __grid
         for (int b = 0; b < 2; ++b) { tc::mbar_init(&tmem_full[b], 1); tc::mbar_init(&tmem_empty[b], N_EPI * 32); }
         tc::mbar_fence_init();
     }
-    if (warp == MMA_WARP) tc::tmem_alloc<32>(&tmem_base_s);
+    if (warp == MMA_WARP) tc::tmem_alloc<TMEM_COLS>(&tmem_base_s);
     tc::fence_async_smem();
     tc::tc_fence_before();
     __syncthreads();
@@ -158,7 +167,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) cost_stem_tc_kernel(const __grid
                     uint2 hi, lo;
                     tc::split4_f16(cv, hi, lo);
                     if (iraw < NPX * 8) {
-                        const size_t off = ((size_t)(c4 >> 1) * NPX + px) * 16 + (c4 & 1) * 8;
+                        const size_t off = ((size_t)(c4 >> 1) * AROWS + px) * 16 + (c4 & 1) * 8;
                         *reinterpret_cast<uint2*>(stage + off) = hi;
                         *reinterpret_cast<uint2*>(stage + A_PLANE + off) = lo;
                     }
@@ -171,27 +180,27 @@ __global__ void __launch_bounds__(N_THREADS, 1) cost_stem_tc_kernel(const __grid
     } else if (warp == MMA_WARP) {
         // =========================================== MMA issuer ===========================================
         const bool leader = tc::elect_one();
-        const uint32_t idesc = tc::idesc_f16_f32(128, NCOLS);
+        const uint32_t idesc = tc::idesc_f16_f32(128, NZ);
         const uint32_t a_base = tc::smem_u32(sA), b_base = tc::smem_u32(sB);
-        constexpr uint32_t A_HI = tc::desc_hi(HC * 16), B_HI = tc::desc_hi(8 * 16);
-        const uint32_t b_lo_hi = tc::desc_lo(b_base, NCOLS * 16), b_lo_lo = tc::desc_lo(b_base + B_PLANE, NCOLS * 16);
+        constexpr uint32_t A_HI = tc::desc_hi(8 * 16), B_HI = tc::desc_hi(8 * 16);
+        const uint32_t b_lo_hi = tc::desc_lo(b_base, NZ * 16), b_lo_lo = tc::desc_lo(b_base + B_PLANE, NZ * 16);
         const int total = ((ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x) * a.S * a.K;
         for (int it = 0; it < total; ++it) {
             const int st = it % N_STAGES, ab = it & 1;
             tc::mbar_wait(&full_a[st], (it / N_STAGES) & 1);
             tc::mbar_wait(&tmem_empty[ab], ((it >> 1) & 1) ^ 1);
             tc::tc_fence_after();
-            const uint32_t dst = tmem_base + ab * NCOLS;
-            const uint32_t a_lo_hi = tc::desc_lo(a_base + st * A_STAGE, NPX * 16);
-            const uint32_t a_lo_lo = tc::desc_lo(a_base + st * A_STAGE + A_PLANE, NPX * 16);
+            const uint32_t a_lo_hi = tc::desc_lo(a_base + st * A_STAGE, AROWS * 16);
+            const uint32_t a_lo_lo = tc::desc_lo(a_base + st * A_STAGE + A_PLANE, AROWS * 16);
             if (leader) {
 #pragma unroll
-                for (int tap = 0; tap < 9; ++tap) {
+                for (int mb = 0; mb < 2; ++mb) {
+                    const uint32_t dst = tmem_base + (ab * 2 + mb) * NZ;
 #pragma unroll
                     for (int ks = 0; ks < 2; ++ks) {
-                        const uint32_t ak = (uint32_t)(((2 * ks) * NPX + (tap / 3) * HC + (tap % 3)) * 16) >> 4;
-                        const uint32_t bk = (uint32_t)(((tap * KC8 + 2 * ks) * NCOLS) * 16) >> 4;
-                        tc::mma_f16_parts(dst, a_lo_lo + ak, A_HI, b_lo_hi + bk, B_HI, idesc, (tap | ks) != 0);
+                        const uint32_t ak = (uint32_t)((2 * ks) * AROWS + mb * 128);        // 16-byte units
+                        const uint32_t bk = (uint32_t)((2 * ks) * NZ);
+                        tc::mma_f16_parts(dst, a_lo_lo + ak, A_HI, b_lo_hi + bk, B_HI, idesc, ks != 0);
                         tc::mma_f16_parts(dst, a_lo_hi + ak, A_HI, b_lo_lo + bk, B_HI, idesc, 1);
                         tc::mma_f16_parts(dst, a_lo_hi + ak, A_HI, b_lo_hi + bk, B_HI, idesc, 1);
                     }
@@ -202,8 +211,9 @@ __global__ void __launch_bounds__(N_THREADS, 1) cost_stem_tc_kernel(const __grid
             __syncwarp();
         }
     } else {
-        // =========================================== epilogue: t0 + GroupNorm-1 sums ==============================
-        const int m = warp * 32 + lane;
+        // =========================================== epilogue: 9-tap sum, t0, GroupNorm-1 sums ===================
+        const int m = warp * 32 + lane;                           // TMEM lane = row of a 128-row block; output pixel of the tile
+        const int q0 = ((m >> 3) * HC + (m & 7)) * 16;            // byte offset of halo pixel (row, col) of output pixel m, tap (0,0)
         int it = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
@@ -212,18 +222,37 @@ __global__ void __launch_bounds__(N_THREADS, 1) cost_stem_tc_kernel(const __grid
             for (int vk = 0; vk < a.S * a.K; ++vk, ++it) {
                 const int v = (vk % a.K) * a.S + vk / a.K;          // slot (plane k, view v) of t0 / stats
                 const int ab = it & 1;
+                unsigned char* zb = sZ + (it & 1) * Z_BYTES;
                 tc::mbar_wait_relaxed(&tmem_full[ab], (it >> 1) & 1);
                 tc::tc_fence_after();
-                uint32_t r0, r1, r2, r3;
-                asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
-                             : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
-                             : "r"(tmem_base + ((uint32_t)(warp * 32) << 16) + ab * NCOLS)
-                             : "memory");
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                // z rows of this lane: halo pixels m (block 0) and 128 + m (block 1) -> zb[tap][pixel][4]
+#pragma unroll
+                for (int mb = 0; mb < 2; ++mb) {
+                    float z[32];
+                    uint32_t r0, r1, r2, r3;
+                    const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (ab * 2 + mb) * NZ;
+                    tc::tmem_ld32(taddr, z);
+                    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(taddr + 32) : "memory");
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    const int p = mb * 128 + m;
+                    if (p < NPX) {
+#pragma unroll
+                        for (int tap = 0; tap < 8; ++tap)
+                            st4(reinterpret_cast<float*>(zb + (tap * NPX + p) * 16), make_float4(z[tap * 4], z[tap * 4 + 1], z[tap * 4 + 2], z[tap * 4 + 3]));
+                        st4(reinterpret_cast<float*>(zb + (8 * NPX + p) * 16),
+                            make_float4(__uint_as_float(r0), __uint_as_float(r1), __uint_as_float(r2), __uint_as_float(r3)));
+                    }
+                }
                 tc::tc_fence_before();
                 tc::mbar_arrive(&tmem_empty[ab]);
-                float4 o = make_float4(__uint_as_float(r0) + a.bias[0], __uint_as_float(r1) + a.bias[1],
-                                       __uint_as_float(r2) + a.bias[2], __uint_as_float(r3) + a.bias[3]);
+                asm volatile("bar.sync 9, 128;" ::: "memory");      // all z rows of this fill are in zb (double-buffered)
+                float4 o = make_float4(a.bias[0], a.bias[1], a.bias[2], a.bias[3]);
+#pragma unroll
+                for (int tap = 0; tap < 9; ++tap) {
+                    const float4 t = ld4(reinterpret_cast<const float*>(zb + tap * NPX * 16 + q0 + ((tap / 3) * HC + (tap % 3)) * 16));
+                    o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w;
+                }
                 float s = 0.f, ss = 0.f;
                 if (valid) {
                     st4(a.t0 + ((size_t)v * P + (size_t)y * a.W + x) * 4, o);
@@ -240,7 +269,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) cost_stem_tc_kernel(const __grid
     }
     tc::tc_fence_before();
     __syncthreads();
-    if (warp == MMA_WARP) tc::tmem_dealloc<32>(tmem_base);
+    if (warp == MMA_WARP) tc::tmem_dealloc<TMEM_COLS>(tmem_base);
     if (tid < a.K * a.S * 2) atomicAdd(a.stats + (tid >> 1) * 6 + (tid & 1), sstat[tid]);      // stats[k][v][GN1][sum, sumsq]
 }
 

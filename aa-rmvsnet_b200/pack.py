@@ -49,6 +49,14 @@ def taps_f16(taps, n_pad=None):
     return torch.stack([hi, lo]).contiguous()
 
 
+def stem_z_f16(w):
+    """Omega stem conv [4][32][3][3] as the B operand of the z-GEMM (csrc/cost_stem_tc.cu):
+    column n = tap * 4 + out (36 -> 48), K = the 32 input channels -> [2 planes][1][4][48][8] fp16."""
+    cout, cin, k, _ = w.shape
+    cols = w.permute(1, 2, 3, 0).reshape(1, cin, k * k * cout)           # [1][cin][tap*4 + out]
+    return taps_f16(cols, n_pad=48)
+
+
 def deconv_taps(w):
     """nn.ConvTranspose2d weight [cin][cout][kh][kw] -> [kh][kw][cin][cout]."""
     return w.permute(2, 3, 0, 1).contiguous()

@@ -99,7 +99,8 @@ int aarmvs_cost_stem(const float* ref, const float* src, size_t view_stride, int
 
 /* Pass A with the 3x3 stem conv on the tensor cores (tcgen05 implicit GEMM over the staged (warp - ref)^2 halo tile,
  * split-fp16 operands, fp32 accumulation in TMEM).  Arguments as aarmvs_cost_stem except
- * stem_w_f16: DEVICE [2 planes hi,lo][9 taps][4][16][8] fp16 (output channels padded 4 -> 16 with zeros). */
+ * stem_w_f16: DEVICE [2 planes hi,lo][4 chunks of 8 input channels][48 columns][8] fp16, column = tap * 4 + output
+ * channel (36 used): the conv runs as one [pixels] x [9 taps * 4] GEMM + a shifted 9-tap sum in the epilogue. */
 int aarmvs_cost_stem_tc(const float* ref, const float* src, size_t view_stride, int H, int W, int S, const float* cams,
                         const void* stem_w_f16, const float* stem_b_host, const float* depth_values, int d_host,
                         const int* d_dev, int planes, int align_corners, float* t0, double* stats, void* stream);
