@@ -19,7 +19,7 @@
 namespace {
 
 constexpr int TR = 16, TCOL = 8, HR = 18, HC = 10, NPX = HR * HC;        // 180 staged pixels
-constexpr int AROWS = 192;                                               // operand rows per K chunk (>= NPX; the second
+constexpr int AROWS = 196;                                               // operand rows per K chunk (>= NPX; the second
                                                                          // 128-row block reads garbage rows that nobody uses)
 constexpr int N_EPI = 4, MMA_WARP = 4, FIRST_LOAD = 5, N_LOAD = 16;
 constexpr int N_THREADS = (N_EPI + 1 + N_LOAD) * 32;                     // 672
