@@ -60,11 +60,10 @@ struct TcCfg {
     static constexpr int KC8 = 2 * KSTEPS;                       // 16-byte K chunks (8 channels each)
     static constexpr int A_PLANE = KC8 * NPX * 16;               // bytes of one fp16 plane (hi or lo) of one stage
     static constexpr int A_STAGE = 2 * A_PLANE;
-    static constexpr int B_PLANE = 9 * KC8 * NG * 16;
-    static constexpr int B_BYTES = 2 * B_PLANE;
+    static constexpr int B_BYTES = 9 * KC8 * 2 * NG * 16;        // [tap][chunk][hi rows | lo rows][16 B]
     static constexpr int SMEM = B_BYTES + N_STAGES * A_STAGE + 1024;
-    static constexpr int TMEM_COLS = 2 * NG;                     // two accumulators
-    static_assert(TMEM_COLS == 64 || TMEM_COLS == 128, "TMEM allocation must be a power of two >= 32");
+    static constexpr int TMEM_COLS = 4 * NG;                     // two accumulators x (hi*hi + lo*hi | hi*lo) column blocks
+    static_assert(TMEM_COLS == 128 || TMEM_COLS == 256, "TMEM allocation must be a power of two >= 32");
 };
 
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
@@ -249,10 +248,10 @@ __global__ void __launch_bounds__(N_THREADS, 1) convlstm_tc_kernel(const __grid_
         // The whole warp runs the loop (uniform control flow keeps the descriptor arithmetic on the uniform datapath);
         // one elected lane issues.  81 / 54 MMAs per tile, fully unrolled: descriptor low words are base + immediate.
         const bool leader = tc::elect_one();
-        const uint32_t idesc = tc::idesc_f16_f32(128, NG);
+        const uint32_t idesc2 = tc::idesc_f16_f32(128, 2 * NG), idesc1 = tc::idesc_f16_f32(128, NG);
         const uint32_t a_base = tc::smem_u32(sA), b_base = tc::smem_u32(sB);
         constexpr uint32_t A_HI = tc::desc_hi(HC * 16), B_HI = tc::desc_hi(8 * 16);
-        const uint32_t b_lo_hi = tc::desc_lo(b_base, NG * 16), b_lo_lo = tc::desc_lo(b_base + C::B_PLANE, NG * 16);
+        const uint32_t b_lo = tc::desc_lo(b_base, 2 * NG * 16);       // [W_hi | W_lo] stacked along N: rows 0..NG-1 hi, NG..2NG-1 lo
         int it = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
             const int st = it % N_STAGES, ab = it & 1;
@@ -263,7 +262,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) convlstm_tc_kernel(const __grid_
             tc::mbar_wait(&tmem_empty[ab], ((it >> 1) & 1) ^ 1);
             tc::tc_fence_after();
             if (pf) a.prof[it * 12 + 6] = clock64();
-            const uint32_t dst = tmem_base + ab * NG;
+            const uint32_t dst = tmem_base + ab * 2 * NG;
             const uint32_t a_lo_hi = tc::desc_lo(a_base + st * C::A_STAGE, NPX * 16);
             const uint32_t a_lo_lo = tc::desc_lo(a_base + st * C::A_STAGE + C::A_PLANE, NPX * 16);
             if (leader) {
@@ -272,10 +271,11 @@ __global__ void __launch_bounds__(N_THREADS, 1) convlstm_tc_kernel(const __grid_
 #pragma unroll
                     for (int ks = 0; ks < KSTEPS; ++ks) {
                         const uint32_t ak = (uint32_t)(((2 * ks) * NPX + (tap / 3) * HC + (tap % 3)) * 16) >> 4;
-                        const uint32_t bk = (uint32_t)(((tap * C::KC8 + 2 * ks) * NG) * 16) >> 4;
-                        tc::mma_f16_parts(dst, a_lo_lo + ak, A_HI, b_lo_hi + bk, B_HI, idesc, (tap | ks) != 0);   // small terms first
-                        tc::mma_f16_parts(dst, a_lo_hi + ak, A_HI, b_lo_lo + bk, B_HI, idesc, 1);
-                        tc::mma_f16_parts(dst, a_lo_hi + ak, A_HI, b_lo_hi + bk, B_HI, idesc, 1);
+                        // A_hi x [W_hi | W_lo] fills columns [0, NG) (hi*hi) and [NG, 2NG) (hi*lo) in ONE instruction with
+                        // N = 2 NG, A_lo x W_hi adds into [0, NG): two A-operand reads per K step instead of three
+                        const uint32_t bk = (uint32_t)((tap * C::KC8 + 2 * ks) * 2 * NG);
+                        tc::mma_f16_parts(dst, a_lo_hi + ak, A_HI, b_lo + bk, B_HI, idesc2, (tap | ks) != 0);
+                        tc::mma_f16_parts(dst, a_lo_lo + ak, A_HI, b_lo + bk, B_HI, idesc1, 1);
                     }
                 }
                 tc::mma_commit(&empty_a[st]);          // operand stage free once these MMAs have read it
@@ -294,28 +294,34 @@ __global__ void __launch_bounds__(N_THREADS, 1) convlstm_tc_kernel(const __grid_
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
             const int ab = it & 1;
             const bool pf = a.prof && blockIdx.x == 0 && tid == 0 && it < 64;
+            // this thread's pixel and its previous cell state: requested BEFORE waiting for the accumulator so that the
+            // global-load latency overlaps the MMAs of this tile
+            const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+            const int y = ty * TR + (m >> 3), x = tx * TCOL + (m & 7);
+            const bool valid = y < a.H && x < a.W;
+            const size_t pix = valid ? (size_t)y * a.W + x : 0;
+            float* cp = a.c_state + pix * CH + hf * NHC;
+            float* hp = hdst + pix * CH + hf * NHC;
+            float cprev[NHC], cn[NHC], hn[NHC];
+#pragma unroll
+            for (int j = 0; j < NHC; j += 4) {
+                const float4 t = d == 0 ? make_float4(0.f, 0.f, 0.f, 0.f) : ld4(cp + j);
+                cprev[j] = t.x; cprev[j + 1] = t.y; cprev[j + 2] = t.z; cprev[j + 3] = t.w;
+            }
             if (pf) a.prof[it * 12 + 8] = clock64();
             tc::mbar_wait_relaxed(&tmem_full[ab], (it >> 1) & 1);
             tc::tc_fence_after();
             if (pf) a.prof[it * 12 + 9] = clock64();
-            float g[NCOL];
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + ab * NG + hf * NCOL;
-            if constexpr (NCOL == 32) tc::tmem_ld32(taddr, g); else tmem_ld16(taddr, g);
+            float g[NCOL], g2[NCOL];
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + ab * 2 * NG + hf * NCOL;
+            if constexpr (NCOL == 32) { tc::tmem_ld32(taddr, g); tc::tmem_ld32(taddr + NG, g2); }
+            else { tmem_ld16(taddr, g); tmem_ld16(taddr + NG, g2); }
+#pragma unroll
+            for (int j = 0; j < NCOL; ++j) g[j] += g2[j];            // (hi*hi + lo*hi) + hi*lo
             tc::tc_fence_before();
             tc::mbar_arrive(&tmem_empty[ab]);                    // accumulator is in registers: release it
             if (pf) a.prof[it * 12 + 10] = clock64();
-            const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
-            const int y = ty * TR + (m >> 3), x = tx * TCOL + (m & 7);
-            if (y < a.H && x < a.W) {
-                const size_t pix = (size_t)y * a.W + x;
-                float* cp = a.c_state + pix * CH + hf * NHC;
-                float* hp = hdst + pix * CH + hf * NHC;
-                float cprev[NHC], cn[NHC], hn[NHC];
-#pragma unroll
-                for (int j = 0; j < NHC; j += 4) {
-                    const float4 t = d == 0 ? make_float4(0.f, 0.f, 0.f, 0.f) : ld4(cp + j);
-                    cprev[j] = t.x; cprev[j + 1] = t.y; cprev[j + 2] = t.z; cprev[j + 3] = t.w;
-                }
+            if (valid) {
 #pragma unroll
                 for (int j = 0; j < NHC; ++j) {
                     const float* bb = s_bias + hf * NCOL + j * 4;

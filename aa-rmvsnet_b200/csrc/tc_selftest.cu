@@ -68,3 +68,48 @@ extern "C" int aarmvs_tc_selftest(const void* a_f16, int a_rows, const void* b_f
     tc_selftest_kernel<<<1, 128, smem, (cudaStream_t)stream>>>((const __half*)a_f16, a_rows, (const __half*)b_f16, d, K, group_rows, shift);
     AARMVS_LAUNCH_RESULT();
 }
+
+// ---- micro-benchmark: cycles per tcgen05.mma (M = 128, K = 16, fp16) as a function of N and of the operand layout ----
+__global__ void __launch_bounds__(128) tc_mma_bench_kernel(int N, int group_rows, int reps, int a_shift_rows, long long* out) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_base;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int i = tid; i < 48 * 1024 / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0u;
+    if (tid == 0) { tc::mbar_init(&bar, 1); tc::mbar_fence_init(); }
+    if (warp == 0) tc::tmem_alloc<256>(&tmem_base);
+    tc::fence_async_smem();
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    if (warp == 0) {
+        const bool leader = tc::elect_one();
+        const uint32_t idesc = tc::idesc_f16_f32(128, N);
+        const uint32_t a_lo = tc::desc_lo(tc::smem_u32(smem), 196 * 16), b_lo = tc::desc_lo(tc::smem_u32(smem) + 24 * 1024, N * 16);
+        const uint32_t a_hi = tc::desc_hi(group_rows * 16), b_hi = tc::desc_hi(8 * 16);
+        long long t0 = clock64();
+        if (leader) {
+            for (int r = 0; r < reps; ++r) {
+#pragma unroll
+                for (int j = 0; j < 9; ++j) tc::mma_f16_parts(tmem_base, a_lo + j * a_shift_rows, a_hi, b_lo, b_hi, idesc, 1);
+            }
+            tc::mma_commit(&bar);
+        }
+        __syncwarp();
+        tc::mbar_wait(&bar, 0);
+        long long t1 = clock64();
+        if (leader) out[blockIdx.x] = t1 - t0;
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc<256>(tmem_base);
+}
+
+// Debug: cycles for reps*9 MMAs (M=128, N, K=16) on every SM; out: [grid] int64.
+extern "C" int aarmvs_tc_mma_bench(int N, int group_rows, int reps, int a_shift_rows, int grid, long long* out, void* stream) {
+    AARMVS_CHECK_ARG(out && N >= 16 && N <= 256 && N % 16 == 0 && reps > 0 && grid > 0);
+    cudaError_t e = cudaFuncSetAttribute(tc_mma_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 48 * 1024);
+    if (e != cudaSuccess) return (int)e;
+    tc_mma_bench_kernel<<<grid, 128, 48 * 1024, (cudaStream_t)stream>>>(N, group_rows, reps, a_shift_rows, out);
+    AARMVS_LAUNCH_RESULT();
+}

@@ -29,10 +29,13 @@ def lstm_gates(w, b):
 
 
 def lstm_gates_f16(w, b):
-    """Tensor-core operand of a ConvLSTM cell: [2 planes hi,lo][9][cin_pad/8][4*hidden][8] fp16 (K-major 16-byte chunks of
-    8 input channels, cin padded with zero rows to a multiple of 16) + the fp32 bias, gate order as lstm_gates()."""
+    """Tensor-core operand of a ConvLSTM cell: [9][cin_pad/8][2 (hi, lo)][4*hidden][8] fp16 (K-major 16-byte chunks of
+    8 input channels, cin padded with zero rows to a multiple of 16; hi and lo rows stacked along N so that
+    A_hi x [W_hi | W_lo] is one MMA) + the fp32 bias, gate order as lstm_gates()."""
     taps, bias = lstm_gates(w, b)                    # [9][cin][n] fp32
-    return taps_f16(taps), bias
+    planes = taps_f16(taps)                          # [2][9][kc8][n][8]
+    # csrc/convlstm_tc.cu stacks hi and lo along N per (tap, chunk): [9][kc8][2][n][8]
+    return planes.permute(1, 2, 0, 3, 4).contiguous(), bias
 
 
 def taps_f16(taps, n_pad=None):

@@ -131,7 +131,7 @@ int aarmvs_convlstm_cell(const aarmvs_conv_src* src, int nsrc, int H, int W, int
 /* The same cell on the tensor cores (tcgen05.mma kind::f16, fp32 accumulation in TMEM).  fp32 operands are split
  * on the fly into fp16 (hi, lo) pairs and each K step issues hi*hi + lo*hi + hi*lo, which keeps ~2^-21 relative
  * accuracy per product (single-pass TF32 / BF16 fails the parity bar).  Same arguments as
- * aarmvs_convlstm_cell except weight_f16: [2 planes hi,lo][9 taps][cin_pad/8][4*hidden][8] fp16 with cin_pad = cin
+ * aarmvs_convlstm_cell except weight_f16: [9 taps][cin_pad/8][2 (hi, lo)][4*hidden][8] fp16 with cin_pad = cin
  * rounded up to 16 (zero rows) and the output-channel order [hidden channel][i,f,o,g]; source channels multiples of 8. */
 int aarmvs_convlstm_cell_tc(const aarmvs_conv_src* src, int nsrc, int H, int W, int cin, int hidden,
                             const void* weight_f16, const float* bias_packed, float* h_pair, float* c_state,
@@ -163,6 +163,10 @@ int aarmvs_next_plane(int* d_dev, double* sums, int nzero, void* stream);
  * a_f16: [a_rows][K] row-major fp16, b_f16: [64][K]; K multiple of 16, <= 256. */
 int aarmvs_tc_selftest(const void* a_f16, int a_rows, const void* b_f16, float* d, int K, int group_rows, int shift,
                        void* stream);
+
+/* Debug micro-benchmark: clock64 cycles for reps*9 back-to-back tcgen05.mma (M=128, N, K=16, fp16, un-swizzled operands
+ * with 8-row groups `group_rows` rows apart, start row advancing by a_shift_rows per instruction) on `grid` CTAs. */
+int aarmvs_tc_mma_bench(int N, int group_rows, int reps, int a_shift_rows, int grid, long long* out, void* stream);
 
 /* Debug aid (the only process-global state in the library, off by default): when set to a device buffer of
  * 64 x 12 uint64, CTA 0 of subsequent aarmvs_convlstm_cell_tc launches records clock64 stamps of its loader / MMA /
