@@ -27,7 +27,7 @@ def _digest(paths):
     for p in sorted(paths):
         with open(p, "rb") as f:
             h.update(f.read())
-    h.update(" ".join(NVCC_FLAGS).encode())
+    h.update((" ".join(NVCC_FLAGS) + os.environ.get("AARMVS_NVCC_EXTRA", "")).encode())
     return h.hexdigest()
 
 
@@ -45,7 +45,7 @@ def build_library(force=False, verbose=False):
         return LIB
     os.makedirs(LIBDIR, exist_ok=True)
     nvcc = _nvcc()
-    flags = [f for f in NVCC_FLAGS if f != "--use_fast_math=false"]
+    flags = [f for f in NVCC_FLAGS if f != "--use_fast_math=false"] + os.environ.get("AARMVS_NVCC_EXTRA", "").split()
     objs = [os.path.join(LIBDIR, os.path.basename(s)[:-3] + ".o") for s in srcs]
 
     def compile_one(pair):

@@ -21,7 +21,13 @@ namespace {
 constexpr int TR = 16, TCOL = 8, HR = 18, HC = 10, NPX = HR * HC;        // 180 staged pixels
 constexpr int AROWS = 196;                                               // operand rows per K chunk (>= NPX; the second
                                                                          // 128-row block reads garbage rows that nobody uses)
-constexpr int N_EPI = 4, MMA_WARP = 4, FIRST_LOAD = 5, N_LOAD = 16;
+#ifndef STEM_N_LOAD
+#define STEM_N_LOAD 16
+#endif
+#ifndef STEM_NB
+#define STEM_NB 2
+#endif
+constexpr int N_EPI = 4, MMA_WARP = 4, FIRST_LOAD = 5, N_LOAD = STEM_N_LOAD;
 constexpr int N_THREADS = (N_EPI + 1 + N_LOAD) * 32;                     // 672
 constexpr int LOAD_THREADS = N_LOAD * 32;                                // 512
 constexpr int N_STAGES = 4;
@@ -47,6 +53,7 @@ struct StemArgs {
     int align_corners;
     float* t0;
     double* stats;
+    int dbg;                    // debug ablation flags (aarmvs_debug_flags): 1 skip gather loads, 2 skip recipes, 4 skip MMA, 8 skip z exchange
 };
 
 // Gather recipe of one staged pixel, ready to use: float offsets of the four corner lines (out-of-image corners point
@@ -119,7 +126,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) cost_stem_tc_kernel(const __grid
                 rec.o[0] = rec.o[1] = rec.o[2] = rec.o[3] = 0;
                 rec.w[0] = rec.w[1] = rec.w[2] = rec.w[3] = 0.f;
                 rec.ref_off = -1; rec.pad0 = rec.pad1 = rec.pad2 = 0;
-                if (y >= 0 && y < a.H && x >= 0 && x < a.W) {
+                if (y >= 0 && y < a.H && x >= 0 && x < a.W && !(a.dbg & 2)) {
                     float ix, iy;
                     sweep_position(scam + v * 12, (float)x, (float)y, depth, a.W, a.H, a.align_corners != 0, ix, iy);
                     const Taps t = make_taps(ix, iy, a.W, a.H);
@@ -135,25 +142,30 @@ __global__ void __launch_bounds__(N_THREADS, 1) cost_stem_tc_kernel(const __grid
             tc::mbar_wait_relaxed(&empty_a[grp], ((it / N_STAGES) & 1) ^ 1);
             // ---- (2) gather
             const float* sv = a.src + (size_t)v * a.view_stride;
+            constexpr int NB = STEM_NB;
 #pragma unroll 1
-            for (int jb = 0; jb < ITEMS; jb += 2) {
-                float4 ta[2], tb[2], tcn[2], td[2], rv[2], wq[2];
-                int roff[2];
+            for (int jb = 0; jb < ((a.dbg & 16) ? 0 : ITEMS); jb += NB) {
+                float4 ta[NB], tb[NB], tcn[NB], td[NB], rv[NB], wq[NB];
+                int roff[NB];
 #pragma unroll
-                for (int j = 0; j < 2; ++j) {
+                for (int j = 0; j < NB; ++j) {
                     const int i = min(lt + (jb + j) * GROUP_THREADS, NPX * 8 - 1);
                     const int px = i >> 3, c4 = (i & 7) * 4;
                     const int4 o = *reinterpret_cast<const int4*>(taps[px].o);
                     wq[j] = *reinterpret_cast<const float4*>(taps[px].w);
                     roff[j] = taps[px].ref_off;
+                    if (a.dbg & 1) {
+                        ta[j] = tb[j] = tcn[j] = td[j] = rv[j] = make_float4(1.f, 2.f, 3.f, 4.f);
+                    } else {
                     ta[j] = ldg4(sv + o.x + c4);
                     tb[j] = ldg4(sv + o.y + c4);
                     tcn[j] = ldg4(sv + o.z + c4);
                     td[j] = ldg4(sv + o.w + c4);
                     rv[j] = ldg4(a.ref + max(roff[j], 0) + c4);
+                    }
                 }
 #pragma unroll
-                for (int j = 0; j < 2; ++j) {
+                for (int j = 0; j < NB; ++j) {
                     const int iraw = lt + (jb + j) * GROUP_THREADS;
                     const int px = iraw >> 3, c4 = iraw & 7;
                     // bilinear blend in ATen's order (see gather_taps)
@@ -193,6 +205,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) cost_stem_tc_kernel(const __grid
             const uint32_t a_lo_hi = tc::desc_lo(a_base + st * A_STAGE, AROWS * 16);
             const uint32_t a_lo_lo = tc::desc_lo(a_base + st * A_STAGE + A_PLANE, AROWS * 16);
             if (leader) {
+                if (!(a.dbg & 4))
 #pragma unroll
                 for (int mb = 0; mb < 2; ++mb) {
                     const uint32_t dst = tmem_base + (ab * 2 + mb) * NZ;
@@ -236,7 +249,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) cost_stem_tc_kernel(const __grid
                                  : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(taddr + 32) : "memory");
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                     const int p = mb * 128 + m;
-                    if (p < NPX) {
+                    if (p < NPX && !(a.dbg & 8)) {
 #pragma unroll
                         for (int tap = 0; tap < 8; ++tap)
                             st4(reinterpret_cast<float*>(zb + (tap * NPX + p) * 16), make_float4(z[tap * 4], z[tap * 4 + 1], z[tap * 4 + 2], z[tap * 4 + 3]));
@@ -246,6 +259,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) cost_stem_tc_kernel(const __grid
                 }
                 tc::tc_fence_before();
                 tc::mbar_arrive(&tmem_empty[ab]);
+                if (a.dbg & 32) continue;
                 asm volatile("bar.sync 9, 128;" ::: "memory");      // all z rows of this fill are in zb (double-buffered)
                 float4 o = make_float4(a.bias[0], a.bias[1], a.bias[2], a.bias[3]);
 #pragma unroll
@@ -273,7 +287,11 @@ __global__ void __launch_bounds__(N_THREADS, 1) cost_stem_tc_kernel(const __grid
     if (tid < a.K * a.S * 2) atomicAdd(a.stats + (tid >> 1) * 6 + (tid & 1), sstat[tid]);      // stats[k][v][GN1][sum, sumsq]
 }
 
+int g_dbg = 0;
+
 }  // namespace
+
+extern "C" void aarmvs_debug_flags(int flags) { g_dbg = flags; }
 
 extern "C" int aarmvs_cost_stem_tc(const float* ref, const float* src, size_t view_stride, int H, int W, int S,
                                    const float* cams, const void* stem_w_f16, const float* stem_b_host,
@@ -288,6 +306,7 @@ extern "C" int aarmvs_cost_stem_tc(const float* ref, const float* src, size_t vi
     for (int i = 0; i < 4; ++i) a.bias[i] = stem_b_host[i];
     a.depth_values = depth_values; a.d_host = d_host; a.d_dev = d_dev; a.align_corners = align_corners; a.t0 = t0;
     a.stats = stats;
+    a.dbg = g_dbg;
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(cost_stem_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);

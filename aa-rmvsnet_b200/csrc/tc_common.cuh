@@ -53,12 +53,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // Everyone else backs off between polls so that waiting warps do not take issue slots from working ones
 // (ncu: 55 % of the executed instructions of the first version were barrier polling).
 __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+#ifdef AARMVS_WAIT_NANOSLEEP
     if (mbar_try_wait(bar, parity)) return;
     for (uint32_t spin = 0; spin < (1u << 24); ++spin) {
-        __nanosleep(64);
+        __nanosleep(AARMVS_WAIT_NANOSLEEP);
         if (mbar_try_wait(bar, parity)) return;
     }
     __trap();
+#else
+    mbar_wait(bar, parity);          // try_wait already suspends the warp in hardware for a bounded time per poll
+#endif
 }
 
 // generic-proxy shared-memory writes -> visible to the async proxy (tcgen05.mma operand reads)

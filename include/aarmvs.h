@@ -168,6 +168,10 @@ int aarmvs_tc_selftest(const void* a_f16, int a_rows, const void* b_f16, float* 
  * with 8-row groups `group_rows` rows apart, start row advancing by a_shift_rows per instruction) on `grid` CTAs. */
 int aarmvs_tc_mma_bench(int N, int group_rows, int reps, int a_shift_rows, int grid, long long* out, void* stream);
 
+/* Debug ablation switches for aarmvs_cost_stem_tc (results become wrong; timing experiments only): 1 skip the gather
+ * loads, 2 skip the sample-position math, 4 skip the MMAs, 8 skip the z exchange.  0 = normal. */
+void aarmvs_debug_flags(int flags);
+
 /* Debug aid (the only process-global state in the library, off by default): when set to a device buffer of
  * 64 x 12 uint64, CTA 0 of subsequent aarmvs_convlstm_cell_tc launches records clock64 stamps of its loader / MMA /
  * epilogue roles per tile.  Pass NULL to switch off. */

@@ -1,0 +1,31 @@
+"""Debug: time aarmvs_cost_stem_tc at cfg2 (K = 8 planes) with parts of the kernel switched off."""
+import ctypes, sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import aarmvsnet_b200 as aa
+from aarmvsnet_b200 import capi
+from aarmvsnet_b200.engine import _ptr
+lib = capi.load()
+H, W, N, D, K = 1184, 1600, 7, 512, 8
+m = aa.EMVSNet(32, image_scale=1.0, max_h=H, max_w=W, return_depth=True).cuda().eval()
+eng = m._engine
+w = eng._weights(torch.device("cuda"))
+ws = eng._workspace(H, W, N, D, torch.device("cuda"), False)
+s = aa.synth.make_sample(H, W, N, D, seed=0)
+ws["feat"].normal_()
+ws["cams"].copy_(eng.relative_cameras(s["proj_matrices"][0]))
+ws["depths"].copy_(s["depth_values"][0])
+P, S = H * W, N - 1
+st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+def run():
+    eng.cost_stem(_ptr(ws["feat"]), _ptr(ws["feat"], P * 32), P * 32, H, W, S, _ptr(ws["cams"]), w, _ptr(ws["depths"]), 100, None, K,
+                  _ptr(ws["t0"]), _ptr(ws["psums"]), st)
+for flags, name in ((0, "full"), (1, "no gather loads"), (2, "no recipe math"), (3, "no loads, no recipes"), (4, "no MMA"), (8, "no z exchange"), (12, "no MMA, no z"), (15, "nothing but staging"), (31, "pipeline skeleton only"), (32, "no epilogue tail"), (47, "staging, no epilogue tail"), (63, "skeleton, no epilogue tail")):
+    lib.aarmvs_debug_flags(flags)
+    run(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(3): run()
+    e1.record(); torch.cuda.synchronize()
+    print(f"{name:24s} {e0.elapsed_time(e1) / 3 / K:.3f} ms/plane")
+lib.aarmvs_debug_flags(0)
