@@ -4,47 +4,53 @@
 //
 // The conv is evaluated as  z[p][tap][o] = sum_c c[p][c] * w[o][c][tap]   (one GEMM per staged halo tile: M = the 180
 // halo pixels in two 128-row blocks, N = 9 taps x 4 outputs = 36 -> 48, K = 32 channels)  followed by the 9-tap shifted
-// sum  t0[q][o] = b[o] + sum_tap z[q + tap][tap][o]  in the epilogue.  Compared with a shifted-window implicit GEMM with
-// N = 16 (one MMA per tap, each re-reading the 128-row operand) this cuts the tensor core's shared-memory operand
-// traffic from 243 KB to 66 KB per tile and view; shared-memory/L1 bandwidth is what bounds this kernel.
-// Operands: un-swizzled K-major fp16 (hi, lo) planes [8-channel chunk][row][16 B] (see convlstm_tc.cu / tc_common.cuh).
-// The gather: four loader groups of four warps, 8 lanes per pixel (one 128-byte line per tap and 8-lane group), sample
-// positions computed once per pixel into shared memory, fills ordered (tile, view, plane) for L1 reuse across planes.
-// Roles: warps 0-3 epilogue (TMEM -> z exchange through smem -> 9-tap sum -> t0, GroupNorm-1 sums), warp 4 TMEM + MMA
-// issue, warps 5-20 loaders.
+// sum  t0[q][o] = b[o] + sum_tap z[q + tap][tap][o].  Operands: un-swizzled K-major fp16 (hi, lo) planes
+// [8-channel chunk][row][16 B] (see convlstm_tc.cu / tc_common.cuh); fp32 accumulation in TMEM.
+//
+// Work unit = one "fill" = (tile of 16 x 8 pixels + halo, source view, plane); fills run in (tile, view, plane) order so
+// a tile's source lines stay in L1 across the planes of a batch.  The CTA (one per SM, persistent) is a ring of
+// independent WORKER GROUPS of four warps plus one MMA-issuing warp.  Group g owns operand stage g, recipe slot g and TMEM
+// accumulator g and walks fills g, g+G, g+2G, ...:
+//   1. one thread per staged pixel evaluates the homography and writes a ready-to-use gather recipe (shared memory);
+//   2. 8 lanes per pixel gather branch-free (out-of-image taps read line 0 with weight 0), (warp-ref)^2, fp16 split,
+//      stage -> arrive on full[g];                      [the MMA warp issues the 12 MMAs of that fill, commit -> done[g]]
+//   3. wait done[g]: TMEM -> z rows -> exchange through the (now free) operand stage -> 9-tap sum -> t0, GroupNorm-1 sums.
+// The groups are out of phase, so one group's load / MMA latency is covered by the others' arithmetic, and no role
+// waits on another group's progress (the first version had a single epilogue group that serialised the pipeline).
 #include "common.cuh"
 #include "tc_common.cuh"
 #include "../../include/aarmvs.h"
 
 namespace {
 
-constexpr int TR = 16, TCOL = 8, HR = 18, HC = 10, NPX = HR * HC;        // 180 staged pixels
-constexpr int AROWS = 196;                                               // operand rows per K chunk (>= NPX; the second
-                                                                         // 128-row block reads garbage rows that nobody uses)
-#ifndef STEM_N_LOAD
-#define STEM_N_LOAD 16
+#ifndef STEM_GROUPS
+#define STEM_GROUPS 4
 #endif
 #ifndef STEM_NB
-#define STEM_NB 2
+#define STEM_NB 3
 #endif
-constexpr int N_EPI = 4, MMA_WARP = 4, FIRST_LOAD = 5, N_LOAD = STEM_N_LOAD;
-constexpr int N_THREADS = (N_EPI + 1 + N_LOAD) * 32;                     // 672
-constexpr int LOAD_THREADS = N_LOAD * 32;                                // 512
-constexpr int N_STAGES = 4;
+constexpr int TR = 16, TCOL = 8, HR = 18, HC = 10, NPX = HR * HC;        // 180 staged pixels
+constexpr int AROWS = 204;                 // operand rows per K chunk: >= NPX, = 4 mod 8 (conflict-free chunk stride), and
+                                           // 2*4*AROWS*16 >= the z exchange buffer that reuses the stage
+constexpr int G = STEM_GROUPS;             // worker groups = operand stages = TMEM accumulators
+constexpr int GROUP_THREADS = 128;
+constexpr int N_THREADS = 32 + G * GROUP_THREADS;
 constexpr int KC8 = 4, NZ = 48;                                          // K chunks; accumulator columns (36 used)
-constexpr int A_PLANE = KC8 * AROWS * 16, A_STAGE = 2 * A_PLANE;         // 12288, 24576 bytes
+constexpr int A_PLANE = KC8 * AROWS * 16, A_STAGE = 2 * A_PLANE;         // 13056, 26112 bytes
 constexpr int B_PLANE = KC8 * NZ * 16, B_BYTES = 2 * B_PLANE;            // 3072, 6144 bytes
 constexpr int TAP_BYTES = NPX * 48;                                      // one TapRec (48 B) per staged pixel
-constexpr int Z_BYTES = 9 * NPX * 16;                                    // z exchange buffer [tap][pixel][4 floats]
-constexpr int SMEM = B_BYTES + N_STAGES * (A_STAGE + TAP_BYTES) + 2 * Z_BYTES + 1024;
-constexpr int TMEM_COLS = 256;                                           // 2 accumulators x 2 row blocks x 48 columns
+constexpr int Z_BYTES = 9 * NPX * 16;                                    // z exchange [tap][pixel][4 floats] = 25920
+static_assert(Z_BYTES <= A_STAGE, "the z exchange buffer reuses the operand stage");
+constexpr int SMEM = B_BYTES + G * (A_STAGE + TAP_BYTES) + 1024;
+constexpr int TMEM_COLS = 512;                                           // G accumulators x 2 row blocks x 48 columns
+static_assert(G * 2 * NZ <= TMEM_COLS, "accumulators exceed TMEM");
 
 struct StemArgs {
     const float* ref;
     const float* src;
     size_t view_stride;
-    int H, W, S, K;             // K = planes per launch: fills run in (tile, view, plane) order so that a tile's source
-    const float* cams;          //     lines stay in L1 across consecutive planes
+    int H, W, S, K;             // K = planes per launch
+    const float* cams;
     const __half* weight;       // [2 planes hi,lo][4 chunks][48 columns (tap*4 + out)][8] fp16
     float bias[4];
     const float* depth_values;
@@ -53,7 +59,8 @@ struct StemArgs {
     int align_corners;
     float* t0;
     double* stats;
-    int dbg;                    // debug ablation flags (aarmvs_debug_flags): 1 skip gather loads, 2 skip recipes, 4 skip MMA, 8 skip z exchange
+    unsigned long long* prof;   // debug: clock64 stamps of group 0 of CTA 0, [64 fills][8]
+    int dbg;                    // debug ablation flags (aarmvs_debug_flags): 1 skip gather loads, 2 skip recipes, 4 skip MMA
 };
 
 // Gather recipe of one staged pixel, ready to use: float offsets of the four corner lines (out-of-image corners point
@@ -69,12 +76,11 @@ __global__ void __launch_bounds__(N_THREADS, 1) cost_stem_tc_kernel(const __grid
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* sB = smem;
     unsigned char* sA = smem + B_BYTES;
-    unsigned char* sT = sA + N_STAGES * A_STAGE;
-    unsigned char* sZ = sT + N_STAGES * TAP_BYTES;
-    __shared__ uint64_t full_a[N_STAGES], empty_a[N_STAGES], tmem_full[2], tmem_empty[2];
+    unsigned char* sT = sA + G * A_STAGE;
+    __shared__ uint64_t full_a[G], done_a[G];
     __shared__ uint32_t tmem_base_s;
     __shared__ float scam[AARMVS_MAX_SRC * 12];
-    __shared__ double sstat[AARMVS_MAX_PLANES * AARMVS_MAX_SRC * 2];
+    __shared__ float2 sstat[G * 4][AARMVS_MAX_PLANES * AARMVS_MAX_SRC];      // per worker warp, per (plane, view): no atomics
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const float* depths = a.depth_values + plane_index(a.d_host, a.d_dev);
@@ -82,13 +88,12 @@ __global__ void __launch_bounds__(N_THREADS, 1) cost_stem_tc_kernel(const __grid
     for (int i = tid; i < B_BYTES / 16; i += N_THREADS)
         reinterpret_cast<uint4*>(sB)[i] = __ldg(reinterpret_cast<const uint4*>(a.weight) + i);
     for (int i = tid; i < a.S * 12; i += N_THREADS) scam[i] = a.cams[i];
-    for (int i = tid; i < a.K * a.S * 2; i += N_THREADS) sstat[i] = 0.0;
+    for (int i = tid; i < G * 4 * AARMVS_MAX_PLANES * AARMVS_MAX_SRC; i += N_THREADS) (&sstat[0][0])[i] = make_float2(0.f, 0.f);
     if (tid == 0) {
-        for (int s = 0; s < N_STAGES; ++s) { tc::mbar_init(&full_a[s], LOAD_THREADS / N_STAGES); tc::mbar_init(&empty_a[s], 1); }
-        for (int b = 0; b < 2; ++b) { tc::mbar_init(&tmem_full[b], 1); tc::mbar_init(&tmem_empty[b], N_EPI * 32); }
+        for (int s = 0; s < G; ++s) { tc::mbar_init(&full_a[s], GROUP_THREADS); tc::mbar_init(&done_a[s], 1); }
         tc::mbar_fence_init();
     }
-    if (warp == MMA_WARP) tc::tmem_alloc<TMEM_COLS>(&tmem_base_s);
+    if (warp == 0) tc::tmem_alloc<TMEM_COLS>(&tmem_base_s);
     tc::fence_async_smem();
     tc::tc_fence_before();
     __syncthreads();
@@ -98,27 +103,59 @@ __global__ void __launch_bounds__(N_THREADS, 1) cost_stem_tc_kernel(const __grid
     const int tiles_x = (a.W + TCOL - 1) / TCOL, tiles_y = (a.H + TR - 1) / TR;
     const int ntiles = tiles_x * tiles_y;
     const size_t P = (size_t)a.H * a.W;
+    const int my_tiles = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int SK = a.S * a.K;
+    const int total = my_tiles * SK;
 
-    if (warp >= FIRST_LOAD) {
-        // =========================================== loaders: gather + (warp - ref)^2 + fp16 split ==================
-        // Four independent loader groups of four warps; group g owns operand stage g and fills g, g+4, g+8, ... so four
-        // fills are in flight and one group's load latency is covered by the others' arithmetic.  Per fill: (1) one
-        // thread per staged pixel evaluates the homography and writes a ready-to-use gather recipe, (2) 8 lanes per
-        // pixel gather branch-free (out-of-image taps read line 0 with weight 0), two pixels' loads issued before use.
-        constexpr int GROUP_THREADS = LOAD_THREADS / N_STAGES;                   // 128
-        const int lt_all = tid - FIRST_LOAD * 32;
-        const int grp = lt_all / GROUP_THREADS, lt = lt_all - grp * GROUP_THREADS;
-        const int my_tiles = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-        const int SK = a.S * a.K;
-        const int total = my_tiles * SK;
-        unsigned char* stage = sA + grp * A_STAGE;
-        TapRec* taps = reinterpret_cast<TapRec*>(sT + grp * TAP_BYTES);
+    if (warp == 0) {
+        // =========================================== MMA issuer ===========================================
+        const bool leader = tc::elect_one();
+        const uint32_t idesc = tc::idesc_f16_f32(128, NZ);
+        const uint32_t a_base = tc::smem_u32(sA), b_base = tc::smem_u32(sB);
+        constexpr uint32_t A_HI = tc::desc_hi(8 * 16), B_HI = tc::desc_hi(8 * 16);
+        const uint32_t b_lo_hi = tc::desc_lo(b_base, NZ * 16), b_lo_lo = tc::desc_lo(b_base + B_PLANE, NZ * 16);
+        for (int it = 0; it < total; ++it) {
+            const int g = it % G;
+            tc::mbar_wait(&full_a[g], (it / G) & 1);
+            tc::tc_fence_after();
+            const uint32_t a_lo_hi = tc::desc_lo(a_base + g * A_STAGE, AROWS * 16);
+            const uint32_t a_lo_lo = tc::desc_lo(a_base + g * A_STAGE + A_PLANE, AROWS * 16);
+            if (leader) {
+                if (!(a.dbg & 4))
+#pragma unroll
+                for (int mb = 0; mb < 2; ++mb) {
+                    const uint32_t dst = tmem_base + (g * 2 + mb) * NZ;
+#pragma unroll
+                    for (int ks = 0; ks < 2; ++ks) {
+                        const uint32_t ak = (uint32_t)((2 * ks) * AROWS + mb * 128);        // 16-byte units
+                        const uint32_t bk = (uint32_t)((2 * ks) * NZ);
+                        tc::mma_f16_parts(dst, a_lo_lo + ak, A_HI, b_lo_hi + bk, B_HI, idesc, ks != 0);
+                        tc::mma_f16_parts(dst, a_lo_hi + ak, A_HI, b_lo_lo + bk, B_HI, idesc, 1);
+                        tc::mma_f16_parts(dst, a_lo_hi + ak, A_HI, b_lo_hi + bk, B_HI, idesc, 1);
+                    }
+                }
+                tc::mma_commit(&done_a[g]);        // operand stage free AND accumulator complete
+            }
+            __syncwarp();
+        }
+    } else {
+        // =========================================== worker groups ===========================================
+        const int g = (warp - 1) / 4, lt = tid - 32 - g * GROUP_THREADS;
+        const int quad = warp & 3;                                   // TMEM lane quadrant this warp may read
+        unsigned char* stage = sA + g * A_STAGE;
+        TapRec* taps = reinterpret_cast<TapRec*>(sT + g * TAP_BYTES);
+        const uint32_t bar_id = 1 + g;
         constexpr int ITEMS = (NPX * 8 + GROUP_THREADS - 1) / GROUP_THREADS;     // 12 (the last one partial)
-        for (int it = grp; it < total; it += N_STAGES) {
-            const int tile = blockIdx.x + (it / SK) * gridDim.x, v = (it % SK) / a.K;
-            const float depth = depths[it % a.K];
+        constexpr int NB = STEM_NB;
+        const int q0 = ((lt >> 3) * HC + (lt & 7)) * 16;              // output pixel lt of the tile -> halo pixel, tap (0,0)
+        for (int it = g; it < total; it += G) {
+            const int tile = blockIdx.x + (it / SK) * gridDim.x, v = (it % SK) / a.K, k = it % a.K;
+            const float depth = depths[k];
             const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
-            // ---- (1) gather recipes (the previous fill's readers are past the barrier at the end of the loop body)
+            const bool pf = a.prof && blockIdx.x == 0 && g == 0 && lt == 0 && it / G < 64;
+            unsigned long long* pp = a.prof + (it / G) * 8;
+            if (pf) pp[0] = clock64();
+            // ---- 1. gather recipes
             for (int px = lt; px < NPX; px += GROUP_THREADS) {
                 const int r = px / HC, cc = px - r * HC;
                 const int y = ty * TR - 1 + r, x = tx * TCOL - 1 + cc;
@@ -138,13 +175,13 @@ __global__ void __launch_bounds__(N_THREADS, 1) cost_stem_tc_kernel(const __grid
                 }
                 taps[px] = rec;
             }
-            asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "n"(GROUP_THREADS) : "memory");
-            tc::mbar_wait_relaxed(&empty_a[grp], ((it / N_STAGES) & 1) ^ 1);
-            // ---- (2) gather
+            // also orders the previous fill's z reads (step 3) before this fill's stage writes
+            asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(GROUP_THREADS) : "memory");
+            if (pf) pp[1] = clock64();
+            // ---- 2. gather, (warp - ref)^2, split, stage
             const float* sv = a.src + (size_t)v * a.view_stride;
-            constexpr int NB = STEM_NB;
 #pragma unroll 1
-            for (int jb = 0; jb < ((a.dbg & 16) ? 0 : ITEMS); jb += NB) {
+            for (int jb = 0; jb < ITEMS; jb += NB) {
                 float4 ta[NB], tb[NB], tcn[NB], td[NB], rv[NB], wq[NB];
                 int roff[NB];
 #pragma unroll
@@ -157,11 +194,11 @@ __global__ void __launch_bounds__(N_THREADS, 1) cost_stem_tc_kernel(const __grid
                     if (a.dbg & 1) {
                         ta[j] = tb[j] = tcn[j] = td[j] = rv[j] = make_float4(1.f, 2.f, 3.f, 4.f);
                     } else {
-                    ta[j] = ldg4(sv + o.x + c4);
-                    tb[j] = ldg4(sv + o.y + c4);
-                    tcn[j] = ldg4(sv + o.z + c4);
-                    td[j] = ldg4(sv + o.w + c4);
-                    rv[j] = ldg4(a.ref + max(roff[j], 0) + c4);
+                        ta[j] = ldg4(sv + o.x + c4);
+                        tb[j] = ldg4(sv + o.y + c4);
+                        tcn[j] = ldg4(sv + o.z + c4);
+                        td[j] = ldg4(sv + o.w + c4);
+                        rv[j] = ldg4(a.ref + max(roff[j], 0) + c4);
                     }
                 }
 #pragma unroll
@@ -185,113 +222,80 @@ __global__ void __launch_bounds__(N_THREADS, 1) cost_stem_tc_kernel(const __grid
                     }
                 }
             }
+            if (pf) pp[2] = clock64();
             tc::fence_async_smem();
-            tc::mbar_arrive(&full_a[grp]);
-            asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "n"(GROUP_THREADS) : "memory");   // recipes may be overwritten
-        }
-    } else if (warp == MMA_WARP) {
-        // =========================================== MMA issuer ===========================================
-        const bool leader = tc::elect_one();
-        const uint32_t idesc = tc::idesc_f16_f32(128, NZ);
-        const uint32_t a_base = tc::smem_u32(sA), b_base = tc::smem_u32(sB);
-        constexpr uint32_t A_HI = tc::desc_hi(8 * 16), B_HI = tc::desc_hi(8 * 16);
-        const uint32_t b_lo_hi = tc::desc_lo(b_base, NZ * 16), b_lo_lo = tc::desc_lo(b_base + B_PLANE, NZ * 16);
-        const int total = ((ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x) * a.S * a.K;
-        for (int it = 0; it < total; ++it) {
-            const int st = it % N_STAGES, ab = it & 1;
-            tc::mbar_wait(&full_a[st], (it / N_STAGES) & 1);
-            tc::mbar_wait(&tmem_empty[ab], ((it >> 1) & 1) ^ 1);
+            tc::mbar_arrive(&full_a[g]);
+            if (pf) pp[3] = clock64();
+            // ---- 3. accumulator -> z rows -> exchange through the operand stage (the MMAs have finished reading it)
+            tc::mbar_wait_relaxed(&done_a[g], (it / G) & 1);
             tc::tc_fence_after();
-            const uint32_t a_lo_hi = tc::desc_lo(a_base + st * A_STAGE, AROWS * 16);
-            const uint32_t a_lo_lo = tc::desc_lo(a_base + st * A_STAGE + A_PLANE, AROWS * 16);
-            if (leader) {
-                if (!(a.dbg & 4))
+            if (pf) pp[4] = clock64();
 #pragma unroll
-                for (int mb = 0; mb < 2; ++mb) {
-                    const uint32_t dst = tmem_base + (ab * 2 + mb) * NZ;
+            for (int mb = 0; mb < 2; ++mb) {
+                float z[32];
+                uint32_t r0, r1, r2, r3;
+                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (g * 2 + mb) * NZ;
+                tc::tmem_ld32(taddr, z);
+                asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                             : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(taddr + 32) : "memory");
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                const int p = mb * 128 + quad * 32 + lane;
+                if (p < NPX) {
 #pragma unroll
-                    for (int ks = 0; ks < 2; ++ks) {
-                        const uint32_t ak = (uint32_t)((2 * ks) * AROWS + mb * 128);        // 16-byte units
-                        const uint32_t bk = (uint32_t)((2 * ks) * NZ);
-                        tc::mma_f16_parts(dst, a_lo_lo + ak, A_HI, b_lo_hi + bk, B_HI, idesc, ks != 0);
-                        tc::mma_f16_parts(dst, a_lo_hi + ak, A_HI, b_lo_lo + bk, B_HI, idesc, 1);
-                        tc::mma_f16_parts(dst, a_lo_hi + ak, A_HI, b_lo_hi + bk, B_HI, idesc, 1);
-                    }
-                }
-                tc::mma_commit(&empty_a[st]);
-                tc::mma_commit(&tmem_full[ab]);
-            }
-            __syncwarp();
-        }
-    } else {
-        // =========================================== epilogue: 9-tap sum, t0, GroupNorm-1 sums ===================
-        const int m = warp * 32 + lane;                           // TMEM lane = row of a 128-row block; output pixel of the tile
-        const int q0 = ((m >> 3) * HC + (m & 7)) * 16;            // byte offset of halo pixel (row, col) of output pixel m, tap (0,0)
-        int it = 0;
-        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-            const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
-            const int y = ty * TR + (m >> 3), x = tx * TCOL + (m & 7);
-            const bool valid = y < a.H && x < a.W;
-            for (int vk = 0; vk < a.S * a.K; ++vk, ++it) {
-                const int v = (vk % a.K) * a.S + vk / a.K;          // slot (plane k, view v) of t0 / stats
-                const int ab = it & 1;
-                unsigned char* zb = sZ + (it & 1) * Z_BYTES;
-                tc::mbar_wait_relaxed(&tmem_full[ab], (it >> 1) & 1);
-                tc::tc_fence_after();
-                // z rows of this lane: halo pixels m (block 0) and 128 + m (block 1) -> zb[tap][pixel][4]
-#pragma unroll
-                for (int mb = 0; mb < 2; ++mb) {
-                    float z[32];
-                    uint32_t r0, r1, r2, r3;
-                    const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (ab * 2 + mb) * NZ;
-                    tc::tmem_ld32(taddr, z);
-                    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
-                                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(taddr + 32) : "memory");
-                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                    const int p = mb * 128 + m;
-                    if (p < NPX && !(a.dbg & 8)) {
-#pragma unroll
-                        for (int tap = 0; tap < 8; ++tap)
-                            st4(reinterpret_cast<float*>(zb + (tap * NPX + p) * 16), make_float4(z[tap * 4], z[tap * 4 + 1], z[tap * 4 + 2], z[tap * 4 + 3]));
-                        st4(reinterpret_cast<float*>(zb + (8 * NPX + p) * 16),
-                            make_float4(__uint_as_float(r0), __uint_as_float(r1), __uint_as_float(r2), __uint_as_float(r3)));
-                    }
-                }
-                tc::tc_fence_before();
-                tc::mbar_arrive(&tmem_empty[ab]);
-                if (a.dbg & 32) continue;
-                asm volatile("bar.sync 9, 128;" ::: "memory");      // all z rows of this fill are in zb (double-buffered)
-                float4 o = make_float4(a.bias[0], a.bias[1], a.bias[2], a.bias[3]);
-#pragma unroll
-                for (int tap = 0; tap < 9; ++tap) {
-                    const float4 t = ld4(reinterpret_cast<const float*>(zb + tap * NPX * 16 + q0 + ((tap / 3) * HC + (tap % 3)) * 16));
-                    o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w;
-                }
-                float s = 0.f, ss = 0.f;
-                if (valid) {
-                    st4(a.t0 + ((size_t)v * P + (size_t)y * a.W + x) * 4, o);
-                    s = (o.x + o.y) + (o.z + o.w);
-                    ss = (o.x * o.x + o.y * o.y) + (o.z * o.z + o.w * o.w);
-                }
-                double ds = warp_sum((double)s), dss = warp_sum((double)ss);
-                if (lane == 0) {
-                    atomicAdd(&sstat[v * 2 + 0], ds);
-                    atomicAdd(&sstat[v * 2 + 1], dss);
+                    for (int tap = 0; tap < 8; ++tap)
+                        st4(reinterpret_cast<float*>(stage + (tap * NPX + p) * 16), make_float4(z[tap * 4], z[tap * 4 + 1], z[tap * 4 + 2], z[tap * 4 + 3]));
+                    st4(reinterpret_cast<float*>(stage + (8 * NPX + p) * 16),
+                        make_float4(__uint_as_float(r0), __uint_as_float(r1), __uint_as_float(r2), __uint_as_float(r3)));
                 }
             }
+            tc::tc_fence_before();
+            asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(GROUP_THREADS) : "memory");
+            if (pf) pp[5] = clock64();
+            float4 o = make_float4(a.bias[0], a.bias[1], a.bias[2], a.bias[3]);
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) {
+                const float4 t = ld4(reinterpret_cast<const float*>(stage + tap * NPX * 16 + q0 + ((tap / 3) * HC + (tap % 3)) * 16));
+                o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w;
+            }
+            const int y = ty * TR + (lt >> 3), x = tx * TCOL + (lt & 7);
+            float s = 0.f, ss = 0.f;
+            const int slot = k * a.S + v;                               // (plane, view) slot of t0 / stats
+            if (y < a.H && x < a.W) {
+                st4(a.t0 + ((size_t)slot * P + (size_t)y * a.W + x) * 4, o);
+                s = (o.x + o.y) + (o.z + o.w);
+                ss = (o.x * o.x + o.y * o.y) + (o.z * o.z + o.w * o.w);
+            }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                s += __shfl_xor_sync(0xffffffffu, s, off);
+                ss += __shfl_xor_sync(0xffffffffu, ss, off);
+            }
+            if (lane == 0) {       // this warp's private accumulator: a tile contributes 32 pixels x 4 values, ~100 tiles per slot
+                float2 acc = sstat[warp - 1][slot];
+                acc.x += s; acc.y += ss;
+                sstat[warp - 1][slot] = acc;
+            }
+            if (pf) pp[6] = clock64();
         }
     }
     tc::tc_fence_before();
     __syncthreads();
-    if (warp == MMA_WARP) tc::tmem_dealloc<TMEM_COLS>(tmem_base);
-    if (tid < a.K * a.S * 2) atomicAdd(a.stats + (tid >> 1) * 6 + (tid & 1), sstat[tid]);      // stats[k][v][GN1][sum, sumsq]
+    if (warp == 0) tc::tmem_dealloc<TMEM_COLS>(tmem_base);
+    if (tid < a.K * a.S) {                                                   // stats[k][v][GN1][sum, sumsq]
+        double s = 0.0, ss = 0.0;
+        for (int w = 0; w < G * 4; ++w) { s += (double)sstat[w][tid].x; ss += (double)sstat[w][tid].y; }
+        atomicAdd(a.stats + tid * 6 + 0, s);
+        atomicAdd(a.stats + tid * 6 + 1, ss);
+    }
 }
 
 int g_dbg = 0;
+unsigned long long* g_stem_prof = nullptr;
 
 }  // namespace
 
 extern "C" void aarmvs_debug_flags(int flags) { g_dbg = flags; }
+extern "C" void aarmvs_debug_stem_profile_buffer(void* buf) { g_stem_prof = (unsigned long long*)buf; }
 
 extern "C" int aarmvs_cost_stem_tc(const float* ref, const float* src, size_t view_stride, int H, int W, int S,
                                    const float* cams, const void* stem_w_f16, const float* stem_b_host,
@@ -307,6 +311,7 @@ extern "C" int aarmvs_cost_stem_tc(const float* ref, const float* src, size_t vi
     a.depth_values = depth_values; a.d_host = d_host; a.d_dev = d_dev; a.align_corners = align_corners; a.t0 = t0;
     a.stats = stats;
     a.dbg = g_dbg;
+    a.prof = g_stem_prof;
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(cost_stem_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);

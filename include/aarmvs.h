@@ -171,6 +171,9 @@ int aarmvs_tc_mma_bench(int N, int group_rows, int reps, int a_shift_rows, int g
 /* Debug ablation switches for aarmvs_cost_stem_tc (results become wrong; timing experiments only): 1 skip the gather
  * loads, 2 skip the sample-position math, 4 skip the MMAs, 8 skip the z exchange.  0 = normal. */
 void aarmvs_debug_flags(int flags);
+/* Debug: worker group 0 of CTA 0 of subsequent aarmvs_cost_stem_tc launches records clock64 stamps per fill ([64][8]
+ * uint64 device buffer; NULL switches off). */
+void aarmvs_debug_stem_profile_buffer(void* buf);
 
 /* Debug aid (the only process-global state in the library, off by default): when set to a device buffer of
  * 64 x 12 uint64, CTA 0 of subsequent aarmvs_convlstm_cell_tc launches records clock64 stamps of its loader / MMA /

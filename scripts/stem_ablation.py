@@ -20,7 +20,7 @@ st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 def run():
     eng.cost_stem(_ptr(ws["feat"]), _ptr(ws["feat"], P * 32), P * 32, H, W, S, _ptr(ws["cams"]), w, _ptr(ws["depths"]), 100, None, K,
                   _ptr(ws["t0"]), _ptr(ws["psums"]), st)
-for flags, name in ((0, "full"), (1, "no gather loads"), (2, "no recipe math"), (3, "no loads, no recipes"), (4, "no MMA"), (8, "no z exchange"), (12, "no MMA, no z"), (15, "nothing but staging"), (31, "pipeline skeleton only"), (32, "no epilogue tail"), (47, "staging, no epilogue tail"), (63, "skeleton, no epilogue tail")):
+for flags, name in ((0, "full"), (1, "no gather loads"), (2, "no recipe math"), (3, "no loads, no recipes"), (4, "no MMA"), (7, "no loads/recipes/MMA")):
     lib.aarmvs_debug_flags(flags)
     run(); torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -29,3 +29,13 @@ for flags, name in ((0, "full"), (1, "no gather loads"), (2, "no recipe math"), 
     e1.record(); torch.cuda.synchronize()
     print(f"{name:24s} {e0.elapsed_time(e1) / 3 / K:.3f} ms/plane")
 lib.aarmvs_debug_flags(0)
+
+buf = torch.zeros(64 * 8, dtype=torch.int64, device="cuda")
+lib.aarmvs_debug_stem_profile_buffer(ctypes.c_void_p(buf.data_ptr()))
+run(); torch.cuda.synchronize()
+lib.aarmvs_debug_stem_profile_buffer(None)
+t = buf.view(64, 8).cpu()[8:56]
+t = (t - t[0, 0]).double()
+print("group-0 cycles per fill: recipes+bar %.0f | gather+stage %.0f | fence+arrive %.0f | wait MMA %.0f | z rows+bar %.0f | sum+store+stats %.0f | fill period %.0f" % (
+    (t[:, 1] - t[:, 0]).mean(), (t[:, 2] - t[:, 1]).mean(), (t[:, 3] - t[:, 2]).mean(), (t[:, 4] - t[:, 3]).mean(), (t[:, 5] - t[:, 4]).mean(),
+    (t[:, 6] - t[:, 5]).mean(), (t[1:, 0] - t[:-1, 0]).mean()))
