@@ -268,15 +268,22 @@ def run_ours(args):
                              "useful FLOPs counted once)", "tensor", CELL_FLOP_PER_PX[name] * P)
         top = max(kernels, key=lambda k: st[k])
         kname, bound, work = kernels[top]
+        batched = top in ("cost_stem", "omega_stats", "aggregate")       # one launch covers plane_batch planes
+        per_launch = eng.plane_batch if batched else 1
+        # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu captures (cfg2 only)
+        traffic_cfg2 = {"cost_stem": 2.819e9, "aggregate": 4.991e9, "cell0": 0.693e9, "cell1": 0.217e9, "cell2": 0.046e9,
+                        "cell3": 0.147e9, "cell4": 0.464e9, "head_wta": 0.083e9}      # profiles/r01d_*, r01e_*
+        roofline = {"kernel": kname, "bound": bound, "planes_per_launch": per_launch, "ms_per_launch": st[top] * per_launch,
+                    "algorithmic_work_per_launch": work * per_launch,
+                    "traffic": traffic_cfg2.get(top) if args.workload == "cfg2" else None,
+                    "traffic_source": "ncu --set full, profiles/r01d_stem_aggregate.txt / r01e_plane_kernels.txt"}
         if bound == "hbm":
-            roofline = {"kernel": kname, "bound": "hbm", "achieved": work / (st[top] * 1e-3) / 1e9, "peak": pk["hbm_gbs"],
-                        "unit": "GB/s", "traffic": None, "peak_source": pk["source"] + ", STREAM-style copy"}
+            roofline.update({"achieved": work / (st[top] * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                             "peak_source": pk["source"] + ", STREAM-style copy"})
         else:
-            roofline = {"kernel": kname, "bound": "tensor", "achieved": work / (st[top] * 1e-3) / 1e12,
-                        "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s", "traffic": None,
-                        "peak_source": pk["source"] + ", sustained bf16 (kernel timed inside a long step)"}
+            roofline.update({"achieved": work / (st[top] * 1e-3) / 1e12, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                             "peak_source": pk["source"] + ", sustained bf16 (kernel timed inside a long step)"})
         roofline["frac"] = roofline["achieved"] / roofline["peak"]
-        roofline["ms_per_launch"] = st[top]
         extra = {
             "stage_ms_per_plane": {k: round(v, 4) for k, v in st.items()},
             "recurrence": {"ms_per_plane": rec_ms, "achieved_tflops": FLOP_PER_PX_PLANE * P / (rec_ms * 1e-3) / 1e12,
