@@ -1,0 +1,77 @@
+"""Parity beyond the golden fixtures: a mid-size case against the CPU oracle run on the spot, and size-independent
+properties at BASELINE.json's full configuration (cfg2: 1600x1184, N=7, D=512) where the oracle would need hours."""
+import pytest
+import torch
+
+from conftest import load_weights
+
+pytestmark = pytest.mark.gpu
+
+
+def _model(h, w, ckpt="model_dtu_v2.ckpt", **kw):
+    import aarmvsnet_b200 as aa
+    m = aa.EMVSNet(disparity_level=32, image_scale=1.0, max_h=h, max_w=w, return_depth=True, **kw)
+    m.load_state_dict(load_weights(ckpt), strict=True)
+    return m.cuda().eval()
+
+
+def _run(m, s):
+    with torch.no_grad():
+        return m(s["imgs"].cuda(), s["proj_matrices"].cuda(), s["depth_values"].cuda())
+
+
+@pytest.mark.parametrize("smooth", [False, True])
+def test_mid_size_against_oracle(smooth):
+    """104x136 (ragged against the 16x8 / 8x16 / 8x32 kernel tiles), N=5, D=20, inverse depths."""
+    from aarmvsnet_b200 import synth
+    from oracle import aarmvs_oracle as orc
+    s = synth.make_sample(104, 136, 5, 20, seed=21, depth_mode="inverse", smooth=smooth)
+    out = _run(_model(104, 136), s)
+    ref = orc.forward_test(load_weights("model_dtu_v2.ckpt"), s["imgs"], s["proj_matrices"], s["depth_values"], return_index=True)
+    same = out["index"].cpu().long() == ref["index"]
+    frac = same.float().mean().item()
+    print(f"smooth={smooth}: same plane on {frac * 100:.4f}% of pixels")
+    assert frac >= 0.999
+    torch.testing.assert_close(out["depth"].cpu()[same], ref["depth"][same], rtol=0, atol=0)
+    torch.testing.assert_close(out["photometric_confidence"].cpu()[same], ref["photometric_confidence"][same], rtol=1e-3, atol=1e-3)
+
+
+def test_tensor_core_and_fma_cells_agree():
+    """The split-fp16 tcgen05 path against the fp32 CUDA-core path on the same inputs (no CPU needed): 320x256, D=24."""
+    from aarmvsnet_b200 import synth
+    s = synth.make_sample(256, 320, 4, 24, seed=5)
+    a = _run(_model(256, 320, cell_math="tc"), s)
+    b = _run(_model(256, 320, cell_math="fma"), s)
+    same = (a["index"] == b["index"]).float().mean().item()
+    print(f"tc vs fma: same plane on {same * 100:.4f}% of pixels")
+    assert same >= 0.999
+    assert (a["photometric_confidence"] - b["photometric_confidence"]).abs().max().item() < 5e-3
+
+
+def test_plane_batching_does_not_change_the_result():
+    from aarmvsnet_b200 import synth
+    s = synth.make_sample(128, 160, 4, 19, seed=9)          # 19 planes: batches of 8, 8, 3
+    a = _run(_model(128, 160, plane_batch=8), s)
+    b = _run(_model(128, 160, plane_batch=1), s)
+    assert (a["index"] == b["index"]).float().mean().item() >= 0.9999
+    torch.testing.assert_close(a["photometric_confidence"], b["photometric_confidence"], rtol=1e-4, atol=1e-5)
+
+
+def test_cfg2_full_size_properties():
+    """BASELINE cfg2.  Properties that hold for any correct forward: the depth is one of the hypotheses and matches the
+    winning index, 0 < confidence <= 1, everything finite, and a second call (graph replay) reproduces the first."""
+    from aarmvsnet_b200 import synth
+    H, W, N, D = 1184, 1600, 7, 512
+    s = synth.make_sample(H, W, N, D, seed=3)
+    m = _model(H, W)
+    a = _run(m, s)
+    dv = s["depth_values"][0].cuda()
+    idx = a["index"][0].long()
+    assert idx.min().item() >= 0 and idx.max().item() < D
+    assert torch.equal(a["depth"][0], dv[idx])
+    conf = a["photometric_confidence"][0]
+    assert torch.isfinite(conf).all() and conf.min().item() > 0 and conf.max().item() <= 1.0
+    assert idx.float().std().item() > 1.0                     # not a degenerate constant map
+    b = _run(m, s)
+    assert (a["index"] == b["index"]).float().mean().item() >= 0.99999
+    torch.testing.assert_close(a["photometric_confidence"], b["photometric_confidence"], rtol=1e-4, atol=1e-5)
