@@ -24,10 +24,10 @@
 namespace {
 
 #ifndef STEM_GROUPS
-#define STEM_GROUPS 4
+#define STEM_GROUPS 5
 #endif
 #ifndef STEM_NB
-#define STEM_NB 3
+#define STEM_NB 2
 #endif
 constexpr int TR = 16, TCOL = 8, HR = 18, HC = 10, NPX = HR * HC;        // 180 staged pixels
 constexpr int AROWS = 204;                 // operand rows per K chunk: >= NPX, = 4 mod 8 (conflict-free chunk stride), and

@@ -224,8 +224,14 @@ __global__ void __launch_bounds__(256) omega_stats_kernel(const float* __restric
 // tap set and omega weight once, the group reads them back with shuffles, and the taps of three views (12 lines) are
 // requested before the first is used.
 constexpr int AG_TH = 8, AG_TW = 16;
+#ifndef AGG_NBV
+#define AGG_NBV 1              // views whose taps are requested before the first is used
+#endif
+#ifndef AGG_MINB
+#define AGG_MINB 4             // resident CTAs per SM the register allocation aims for
+#endif
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, AGG_MINB)
 aggregate_kernel(const float* __restrict__ ref, const float* __restrict__ src, size_t view_stride, int H, int W, int S, int K,
                  const float* __restrict__ cams, const __grid_constant__ OmegaTail q,
                  const float* __restrict__ depth_values, int d_host, const int* __restrict__ d_dev, int align_corners,
@@ -281,11 +287,11 @@ aggregate_kernel(const float* __restrict__ ref, const float* __restrict__ src, s
                     if (reweight_out) reweight_out[((size_t)k * S + mv) * P + p] = wm;
                 }
                 const int nv = min(8, S - v0);
-                for (int kb = 0; kb < nv; kb += 3) {
-                    float4 ta[3], tb[3], tcn[3], td[3];
-                    float w0[3], w1[3], w2[3], w3[3], wv[3];
+                for (int kb = 0; kb < nv; kb += AGG_NBV) {
+                    float4 ta[AGG_NBV], tb[AGG_NBV], tcn[AGG_NBV], td[AGG_NBV];
+                    float w0[AGG_NBV], w1[AGG_NBV], w2[AGG_NBV], w3[AGG_NBV], wv[AGG_NBV];
 #pragma unroll
-                    for (int e = 0; e < 3; ++e) {
+                    for (int e = 0; e < AGG_NBV; ++e) {
                         const int k = min(kb + e, 7);
                         const int o0 = __shfl_sync(0xffffffffu, tm.o_nw, k, 8), o1 = __shfl_sync(0xffffffffu, tm.o_ne, k, 8);
                         const int o2 = __shfl_sync(0xffffffffu, tm.o_sw, k, 8), o3 = __shfl_sync(0xffffffffu, tm.o_se, k, 8);
@@ -303,7 +309,7 @@ aggregate_kernel(const float* __restrict__ ref, const float* __restrict__ src, s
                         td[e] = ldg4(sv + (size_t)max(o3, 0) * 32);
                     }
 #pragma unroll
-                    for (int e = 0; e < 3; ++e) {
+                    for (int e = 0; e < AGG_NBV; ++e) {
                         if (kb + e >= nv) continue;
                         const float gx = __fmaf_rn(td[e].x, w3[e], __fmaf_rn(tcn[e].x, w2[e], __fmaf_rn(tb[e].x, w1[e], __fmul_rn(ta[e].x, w0[e]))));
                         const float gy = __fmaf_rn(td[e].y, w3[e], __fmaf_rn(tcn[e].y, w2[e], __fmaf_rn(tb[e].y, w1[e], __fmul_rn(ta[e].y, w0[e]))));
@@ -400,7 +406,7 @@ extern "C" int aarmvs_aggregate(const float* ref, const float* src, size_t view_
     OmegaTail q;
     fill_tail(q, tail_host);
     const int ntiles = ((W + AG_TW - 1) / AG_TW) * ((H + AG_TH - 1) / AG_TH);
-    const int blocks = ntiles < 148 * 8 ? ntiles : 148 * 8;
+    const int blocks = ntiles < 148 * AGG_MINB ? ntiles : 148 * AGG_MINB;
     aggregate_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(ref, src, view_stride, H, W, S, planes, cams, q, depth_values, d_host,
                                                               d_dev, align_corners, t0, stats, cost, reweight_out);
     AARMVS_LAUNCH_RESULT();

@@ -39,3 +39,16 @@ t = (t - t[0, 0]).double()
 print("group-0 cycles per fill: recipes+bar %.0f | gather+stage %.0f | fence+arrive %.0f | wait MMA %.0f | z rows+bar %.0f | sum+store+stats %.0f | fill period %.0f" % (
     (t[:, 1] - t[:, 0]).mean(), (t[:, 2] - t[:, 1]).mean(), (t[:, 3] - t[:, 2]).mean(), (t[:, 4] - t[:, 3]).mean(), (t[:, 5] - t[:, 4]).mean(),
     (t[:, 6] - t[:, 5]).mean(), (t[1:, 0] - t[:-1, 0]).mean()))
+
+# ---- pass D (aggregate) timing, K planes
+cost = torch.empty(K, P, 32, device="cuda")
+def run_d():
+    capi.check(lib.aarmvs_aggregate(_ptr(ws["feat"]), _ptr(ws["feat"], P * 32), P * 32, H, W, S, _ptr(ws["cams"]), w["tail_host"],
+                                    _ptr(ws["depths"]), 100, None, K, 0, _ptr(ws["t0"]), _ptr(ws["psums"]), _ptr(cost), None, st), "agg")
+ws["psums"].fill_(1000.0)
+run_d(); torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(3): run_d()
+e1.record(); torch.cuda.synchronize()
+print(f"aggregate                {e0.elapsed_time(e1) / 3 / K:.3f} ms/plane")
