@@ -4,8 +4,8 @@ Public API mirrors the reference (models/drmvsnet.py): ``EMVSNet(...)(imgs, proj
 The arithmetic lives in lib/libaarmvs_sm100.so (C ABI: include/aarmvs.h); there is no CPU path.
 """
 from . import synth                                     # noqa: F401
-from .model import EMVSNet                              # noqa: F401
+from .model import EMVSNet, mvsnet_cls_loss             # noqa: F401
 from .ops import homo_warping_depthwise                 # noqa: F401
 
 __version__ = "0.1.0"
-__all__ = ["EMVSNet", "homo_warping_depthwise", "synth"]
+__all__ = ["EMVSNet", "mvsnet_cls_loss", "homo_warping_depthwise", "synth"]

@@ -142,3 +142,20 @@ class EMVSNet(nn.Module):
         # training phase (drmvsnet.py:289-295): softmax over the D regularised cost maps
         prob_volume = torch.softmax(torch.stack([o["cost_reg"] for o in outs]), dim=1)
         return prob_volume, None, None
+
+
+def mvsnet_cls_loss(prob_volume, depth_gt, mask, depth_value, return_prob_map=False):
+    """Training loss of the reference (models/drmvsnet.py:347-381), kept as plain tensor ops as SURVEY.md §8 row a16
+    prescribes: masked one-hot cross entropy of the probability volume against the hypothesis nearest to the ground
+    truth, plus the winner-take-all depth map.  prob_volume [B,D,H,W], depth_gt / mask [B,H,W], depth_value [B,D]."""
+    b, d, h, w = prob_volume.shape
+    planes = depth_value.view(b, d, 1, 1)
+    gt_index = (planes - depth_gt.unsqueeze(1)).abs().argmin(dim=1)
+    gt_index = torch.round(mask * gt_index.to(prob_volume.dtype)).long().unsqueeze(1)        # masked pixels -> plane 0
+    cross_entropy = -torch.log(prob_volume.gather(1, gt_index)).squeeze(1)
+    valid = mask.sum(dim=[1, 2]) + 1e-6
+    loss = ((mask * cross_entropy).sum(dim=[1, 2]) / valid).mean()
+    wta_depth = planes.expand(b, d, h, w).gather(1, prob_volume.argmax(dim=1, keepdim=True)).squeeze(1)
+    if return_prob_map:
+        return loss, wta_depth, prob_volume.max(dim=1)[0]
+    return loss, wta_depth

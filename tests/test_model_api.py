@@ -74,3 +74,15 @@ def test_synth_sample_is_deterministic_and_valid():
     assert ((u > 0) & (u < 40) & (v > 0) & (v < 32)).all()
     dv = synth.depth_hypotheses(8, "inverse")
     assert torch.all(dv[1:] > dv[:-1]) and abs(dv[0].item() - 425) < 1e-3
+
+
+def test_cls_loss_matches_reference_fixture():
+    """mvsnet_cls_loss (models/drmvsnet.py:347-381) against the value the unmodified reference produced."""
+    import aarmvsnet_b200 as aa
+    from conftest import load_golden
+    g = load_golden("train_32x40_n3_d6.pt")
+    loss, wta = aa.mvsnet_cls_loss(g["prob_volume"], g["depth_gt"], g["mask"], g["depth_values"])
+    torch.testing.assert_close(loss, g["loss"], rtol=1e-6, atol=1e-7)
+    torch.testing.assert_close(wta, g["wta_depth"], rtol=0, atol=0)
+    loss2, _, conf = aa.mvsnet_cls_loss(g["prob_volume"], g["depth_gt"], g["mask"], g["depth_values"], return_prob_map=True)
+    assert torch.equal(loss2, loss) and torch.equal(conf, g["prob_volume"].max(1)[0])
