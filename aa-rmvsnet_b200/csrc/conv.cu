@@ -368,31 +368,27 @@ extern "C" int aarmvs_convlstm_cell(const aarmvs_conv_src* src, int nsrc, int H,
 struct DeconvArgs {
     ConvSrc in;
     int Hin, Win;
-    const float* weight;   // [3][3][16][16]
-    const float* bias;
     float* out;
     double* out_stats;     // 2 groups
     int d_host;
     const int* d_dev;
 };
 
+struct DeconvW {           // by value in the kernel parameter (constant) bank: every FMA takes its weight operand from
+    float w[9 * 256];      // c[0][...] with no load instruction ([ky][kx][cin][cout])
+    float b[16];
+};
+
+// acc[co] += sum_ci x[ci] * w[ci][co]   (w: compile-time offset into the parameter bank)
 __device__ __forceinline__ void deconv_acc(float (&acc)[16], const float (&x)[16], const float* w) {
 #pragma unroll
     for (int ci = 0; ci < 16; ++ci)
 #pragma unroll
-        for (int k = 0; k < 16; k += 4) {
-            float4 w4 = ld4(w + ci * 16 + k);
-            acc[k] = fmaf(x[ci], w4.x, acc[k]);
-            acc[k + 1] = fmaf(x[ci], w4.y, acc[k + 1]);
-            acc[k + 2] = fmaf(x[ci], w4.z, acc[k + 2]);
-            acc[k + 3] = fmaf(x[ci], w4.w, acc[k + 3]);
-        }
+        for (int k = 0; k < 16; ++k) acc[k] = fmaf(x[ci], w[ci * 16 + k], acc[k]);
 }
 
-__global__ void __launch_bounds__(128) deconv2x_kernel(const __grid_constant__ DeconvArgs a) {
-    __shared__ __align__(16) float sw[9 * 256];
+__global__ void __launch_bounds__(128) deconv2x_kernel(const __grid_constant__ DeconvArgs a, const __grid_constant__ DeconvW W) {
     __shared__ float s_scale[16], s_shift[16];
-    for (int i = threadIdx.x; i < 9 * 256; i += blockDim.x) sw[i] = a.weight[i];
     if (threadIdx.x < 16) {
         float sc = 1.f, sh = 0.f;
         if (a.in.mode == AARMVS_SRC_GN_RELU) gn_scale_shift(a.in, threadIdx.x, sc, sh);
@@ -414,7 +410,7 @@ __global__ void __launch_bounds__(128) deconv2x_kernel(const __grid_constant__ D
                 const bool ok = yy < a.Hin && xx < a.Win;
 #pragma unroll
                 for (int k = 0; k < 16; k += 4) {
-                    float4 v = ok ? ld4(in + ((size_t)yy * a.Win + xx) * 16 + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    float4 v = ok ? ldg4(in + ((size_t)yy * a.Win + xx) * 16 + k) : make_float4(0.f, 0.f, 0.f, 0.f);
                     if (ok && a.in.mode == AARMVS_SRC_GN_RELU) {
                         v.x = fmaxf(fmaf(v.x, s_scale[k], s_shift[k]), 0.f);
                         v.y = fmaxf(fmaf(v.y, s_scale[k + 1], s_shift[k + 1]), 0.f);
@@ -426,31 +422,31 @@ __global__ void __launch_bounds__(128) deconv2x_kernel(const __grid_constant__ D
             };
             load(x00, i, j); load(x01, i, j + 1); load(x10, i + 1, j); load(x11, i + 1, j + 1);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                float acc[16];
+            for (int row = 0; row < 2; ++row) {        // output row 2i + row: the two columns 2j, 2j+1 are 128 contiguous bytes
+                float acc[2][16];
 #pragma unroll
-                for (int k = 0; k < 16; ++k) acc[k] = a.bias[k];
-                if (q == 0) {
-                    deconv_acc(acc, x00, sw + (1 * 3 + 1) * 256);
-                } else if (q == 1) {
-                    deconv_acc(acc, x00, sw + (1 * 3 + 2) * 256);
-                    deconv_acc(acc, x01, sw + (1 * 3 + 0) * 256);
-                } else if (q == 2) {
-                    deconv_acc(acc, x00, sw + (2 * 3 + 1) * 256);
-                    deconv_acc(acc, x10, sw + (0 * 3 + 1) * 256);
+                for (int k = 0; k < 16; ++k) acc[0][k] = acc[1][k] = W.b[k];
+                if (row == 0) {
+                    deconv_acc(acc[0], x00, W.w + (1 * 3 + 1) * 256);
+                    deconv_acc(acc[1], x00, W.w + (1 * 3 + 2) * 256);
+                    deconv_acc(acc[1], x01, W.w + (1 * 3 + 0) * 256);
                 } else {
-                    deconv_acc(acc, x00, sw + (2 * 3 + 2) * 256);
-                    deconv_acc(acc, x01, sw + (2 * 3 + 0) * 256);
-                    deconv_acc(acc, x10, sw + (0 * 3 + 2) * 256);
-                    deconv_acc(acc, x11, sw + (0 * 3 + 0) * 256);
+                    deconv_acc(acc[0], x00, W.w + (2 * 3 + 1) * 256);
+                    deconv_acc(acc[0], x10, W.w + (0 * 3 + 1) * 256);
+                    deconv_acc(acc[1], x00, W.w + (2 * 3 + 2) * 256);
+                    deconv_acc(acc[1], x01, W.w + (2 * 3 + 0) * 256);
+                    deconv_acc(acc[1], x10, W.w + (0 * 3 + 2) * 256);
+                    deconv_acc(acc[1], x11, W.w + (0 * 3 + 0) * 256);
                 }
-                float* o = a.out + ((size_t)(2 * i + (q >> 1)) * Wo + 2 * j + (q & 1)) * 16;
+                float* o = a.out + ((size_t)(2 * i + row) * Wo + 2 * j) * 16;
 #pragma unroll
-                for (int k = 0; k < 16; k += 4) {
-                    st4(o + k, make_float4(acc[k], acc[k + 1], acc[k + 2], acc[k + 3]));
-                    gs[k / 8] += (acc[k] + acc[k + 1]) + (acc[k + 2] + acc[k + 3]);
-                    gq[k / 8] += (acc[k] * acc[k] + acc[k + 1] * acc[k + 1]) + (acc[k + 2] * acc[k + 2] + acc[k + 3] * acc[k + 3]);
-                }
+                for (int c = 0; c < 2; ++c)
+#pragma unroll
+                    for (int k = 0; k < 16; k += 4) {
+                        st4(o + c * 16 + k, make_float4(acc[c][k], acc[c][k + 1], acc[c][k + 2], acc[c][k + 3]));
+                        gs[k / 8] += (acc[c][k] + acc[c][k + 1]) + (acc[c][k + 2] + acc[c][k + 3]);
+                        gq[k / 8] += (acc[c][k] * acc[c][k] + acc[c][k + 1] * acc[c][k + 1]) + (acc[c][k + 2] * acc[c][k + 2] + acc[c][k + 3] * acc[c][k + 3]);
+                    }
             }
         }
     }
@@ -466,19 +462,22 @@ __global__ void __launch_bounds__(128) deconv2x_kernel(const __grid_constant__ D
     }
 }
 
-extern "C" int aarmvs_deconv2x(const aarmvs_conv_src* in, int Hin, int Win, const float* weight, const float* bias,
+extern "C" int aarmvs_deconv2x(const aarmvs_conv_src* in, int Hin, int Win, const float* weight_host, const float* bias_host,
                                float* out, double* out_gn_sums, int d_host, const int* d_dev, void* stream) {
-    AARMVS_CHECK_ARG(in && weight && bias && out && Hin > 0 && Win > 0 && in->channels == 16);
+    AARMVS_CHECK_ARG(in && weight_host && bias_host && out && Hin > 0 && Win > 0 && in->channels == 16);
     AARMVS_CHECK_ARG(in->mode == AARMVS_SRC_PLAIN || in->mode == AARMVS_SRC_GN_RELU);
     DeconvArgs a = {};
     if (int e = convert_src(in, 1, &a.in)) return e;
-    a.Hin = Hin; a.Win = Win; a.weight = weight; a.bias = bias; a.out = out; a.out_stats = out_gn_sums;
+    a.Hin = Hin; a.Win = Win; a.out = out; a.out_stats = out_gn_sums;
     a.d_host = d_host; a.d_dev = d_dev;
+    DeconvW w;
+    for (int i = 0; i < 9 * 256; ++i) w.w[i] = weight_host[i];
+    for (int i = 0; i < 16; ++i) w.b[i] = bias_host[i];
     const int n = Hin * Win, sms = sm_count();
     if (sms <= 0) return AARMVS_ERR_ARG;
     int blocks = (n + 127) / 128;
     if (blocks > sms * 8) blocks = sms * 8;
-    deconv2x_kernel<<<blocks, 128, 0, (cudaStream_t)stream>>>(a);
+    deconv2x_kernel<<<blocks, 128, 0, (cudaStream_t)stream>>>(a, w);
     AARMVS_LAUNCH_RESULT();
 }
 

@@ -93,8 +93,8 @@ class Engine:
             w[f"cell{i}.wtc"], _ = pack.lstm_gates_f16(sd[f"{cr}.cell_list.{i}.conv.weight"],
                                                        sd[f"{cr}.cell_list.{i}.conv.bias"])
         for i in range(2):
-            w[f"deconv{i}.w"] = pack.deconv_taps(sd[f"{cr}.deconv_{i}.conv.weight"])
-            w[f"deconv{i}.b"] = sd[f"{cr}.deconv_{i}.conv.bias"].contiguous()
+            w[f"deconv{i}.w_host"] = capi.host_floats(pack.deconv_taps(sd[f"{cr}.deconv_{i}.conv.weight"]).reshape(-1).cpu().tolist())
+            w[f"deconv{i}.b_host"] = capi.host_floats(sd[f"{cr}.deconv_{i}.conv.bias"].cpu().tolist())
             w[f"deconv{i}.gn"] = (sd[f"{cr}.deconv_{i}.gn.weight"].contiguous(), sd[f"{cr}.deconv_{i}.gn.bias"].contiguous())
         # small layers whose parameters are baked into kernel parameter banks (host arrays)
         om = "omega.reweight_network"
@@ -258,7 +258,7 @@ class Engine:
             mark(f"cell{i}")
 
         def deconv(i, src_, hin, win, dst, sums):
-            capi.check(lib.aarmvs_deconv2x(ctypes.byref(src_), hin, win, _ptr(w[f"deconv{i}.w"]), _ptr(w[f"deconv{i}.b"]),
+            capi.check(lib.aarmvs_deconv2x(ctypes.byref(src_), hin, win, w[f"deconv{i}.w_host"], w[f"deconv{i}.b_host"],
                                            _ptr(dst), _ptr(sums), 0, dptr, stream), f"aarmvs_deconv2x[{i}]")
             mark(f"deconv{i}")
 

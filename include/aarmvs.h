@@ -139,9 +139,10 @@ int aarmvs_convlstm_cell_tc(const aarmvs_conv_src* src, int nsrc, int H, int W, 
 
 /* deConvGnReLU's ConvTranspose2d(16,16,k3,s2,p1,op1) (models/module.py:281): in [Hin][Win][16] (one conv source,
  * typically a ping-pong h) -> pre-norm out [2Hin][2Win][16] + GroupNorm sums (2 groups).
- * weight: [3][3][16 cin][16 cout] repack of ConvTranspose2d's [cin][cout][kh][kw]. */
-int aarmvs_deconv2x(const aarmvs_conv_src* in, int Hin, int Win, const float* weight, const float* bias, float* out,
-                    double* out_gn_sums, int d_host, const int* d_dev, void* stream);
+ * weight_host: [3][3][16 cin][16 cout] repack of ConvTranspose2d's [cin][cout][kh][kw], bias_host: [16] -- HOST
+ * memory: both are baked into the kernel parameter (constant) bank so the FMAs need no weight loads. */
+int aarmvs_deconv2x(const aarmvs_conv_src* in, int Hin, int Win, const float* weight_host, const float* bias_host,
+                    float* out, double* out_gn_sums, int d_host, const int* d_dev, void* stream);
 
 /* conv_0 (3x3, 8 -> 1; models/drmvsnet.py:165) fused with the winner-take-all update (drmvsnet.py:324-339):
  * p = exp(cost); if (max_prob < p) {max_prob = p; depth = depth_values[d]; index = d}; exp_sum += p.
