@@ -54,6 +54,7 @@ PROTOTYPES = {
     "aarmvs_next_plane": (_I, [_P, _P, _I, _P]),
     "aarmvs_debug_profile_buffer": (None, [_P]),
     "aarmvs_debug_flags": (None, [_I]),
+    "aarmvs_debug_cell_flags": (None, [_I]),
     "aarmvs_debug_stem_profile_buffer": (None, [_P]),
     "aarmvs_tc_mma_bench": (_I, [_I, _I, _I, _I, _I, _P, _P]),
     "aarmvs_tc_selftest": (_I, [_P, _I, _P, _P, _I, _I, _I, _P]),

@@ -47,6 +47,7 @@ struct TcArgs {
     int d_host;
     const int* d_dev;
     unsigned long long* prof;   // debug: per-tile clock64 stamps of CTA 0 ([tile][12]), or null
+    int dbg;                    // debug ablation: 1 loader skips global loads, 2 loader skips smem stores, 4 epilogue skips global I/O, 8 skip MMAs
 };
 
 constexpr int TR = 16, TCOL = 8, HR = TR + 2, HC = TCOL + 2, NPX = HR * HC;   // 180 staged pixels per tile
@@ -199,7 +200,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) convlstm_tc_kernel(const __grid_
                 const int m = meta[k];
                 if (m < 0 || (m & 3) == 3) continue;
                 const int y = y0 + ((m >> 2) & 31), x = x0 + ((m >> 7) & 15);
-                if (y < 0 || y >= a.H || x < 0 || x >= a.W) continue;
+                if (y < 0 || y >= a.H || x < 0 || x >= a.W || (a.dbg & 1)) continue;
                 const int mode = m >> 17;
                 if (mode == AARMVS_SRC_MAXPOOL2) {
                     const size_t rowp = (size_t)2 * a.W * sch[k];
@@ -230,7 +231,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) convlstm_tc_kernel(const __grid_
             unsigned char* stage = sA + st * C::A_STAGE;
 #pragma unroll
             for (int k = 0; k < ITEMS; ++k) {
-                if (meta[k] < 0) continue;
+                if (meta[k] < 0 || (a.dbg & 2)) continue;
                 const int idx = lt + k * LT;
                 uint2 h0, l0, h1, l1;
                 tc::split4_f16(va[k], h0, l0);
@@ -266,6 +267,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) convlstm_tc_kernel(const __grid_
             const uint32_t a_lo_hi = tc::desc_lo(a_base + st * C::A_STAGE, NPX * 16);
             const uint32_t a_lo_lo = tc::desc_lo(a_base + st * C::A_STAGE + C::A_PLANE, NPX * 16);
             if (leader) {
+                if (!(a.dbg & 8))
 #pragma unroll
                 for (int tap = 0; tap < 9; ++tap) {
 #pragma unroll
@@ -298,7 +300,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) convlstm_tc_kernel(const __grid_
             // global-load latency overlaps the MMAs of this tile
             const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
             const int y = ty * TR + (m >> 3), x = tx * TCOL + (m & 7);
-            const bool valid = y < a.H && x < a.W;
+            const bool valid = y < a.H && x < a.W && !(a.dbg & 4);
             const size_t pix = valid ? (size_t)y * a.W + x : 0;
             float* cp = a.c_state + pix * CH + hf * NHC;
             float* hp = hdst + pix * CH + hf * NHC;
@@ -364,11 +366,13 @@ int launch_tc(const TcArgs& a, cudaStream_t stream) {
 }
 
 unsigned long long* g_prof = nullptr;
+int g_cell_dbg = 0;
 
 }  // namespace
 
 // Debug only: CTA 0 of the next ConvLSTM launches writes clock64 stamps per tile ([64][12] uint64) into `buf` (device).
 extern "C" void aarmvs_debug_profile_buffer(void* buf) { g_prof = (unsigned long long*)buf; }
+extern "C" void aarmvs_debug_cell_flags(int flags) { g_cell_dbg = flags; }
 
 extern "C" int aarmvs_convlstm_cell_tc(const aarmvs_conv_src* src, int nsrc, int H, int W, int cin, int hidden,
                                        const void* weight_f16, const float* bias_packed, float* h_pair, float* c_state,
@@ -394,7 +398,7 @@ extern "C" int aarmvs_convlstm_cell_tc(const aarmvs_conv_src* src, int nsrc, int
     }
     AARMVS_CHECK_ARG(csum == cin && cin <= 48);
     a.H = H; a.W = W; a.weight = (const __half*)weight_f16; a.bias = bias_packed; a.h_pair = h_pair; a.c_state = c_state;
-    a.d_host = d_host; a.d_dev = d_dev; a.prof = g_prof;
+    a.d_host = d_host; a.d_dev = d_dev; a.prof = g_prof; a.dbg = g_cell_dbg;
     cudaStream_t st = (cudaStream_t)stream;
     if (cin == 48 && hidden == 16) return launch_tc<3, 64>(a, st);     // cells 0, 3
     if (cin == 32 && hidden == 16) return launch_tc<2, 64>(a, st);     // cells 1, 2

@@ -249,6 +249,18 @@ def run_ours(args):
         ws = eng._workspace(H, W, N, D, dev, False)
         w = eng._weights(dev)
         st = stage_profile(eng, ws, w)
+        # FeatNet alone (7 views of the last sample), CUDA events
+        import ctypes as _ct
+        _stream = _ct.c_void_p(torch.cuda.current_stream().cuda_stream)
+        _imgs = resident[0]["imgs"].contiguous()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for rep in range(2):
+            f0.record()
+            for v in range(N):
+                eng.feature_map(_imgs[v], ws["feat"][v], ws, w, _stream)
+            f1.record()
+            torch.cuda.synchronize()
+        featnet_ms = f0.elapsed_time(f1)
         P = H * W
         wa_ms = st["cost_stem"] + st["omega_stats"] + st["aggregate"]
         rec_ms = sum(st[k] for k in st if k.startswith(("cell", "deconv", "head")))
@@ -286,6 +298,7 @@ def run_ours(args):
         roofline["frac"] = roofline["achieved"] / roofline["peak"]
         extra = {
             "stage_ms_per_plane": {k: round(v, 4) for k, v in st.items()},
+            "featnet_ms_per_depth_map": featnet_ms, "featnet_ms_per_view": featnet_ms / N,
             "recurrence": {"ms_per_plane": rec_ms, "achieved_tflops": FLOP_PER_PX_PLANE * P / (rec_ms * 1e-3) / 1e12,
                            "frac_of_bf16_sustained": FLOP_PER_PX_PLANE * P / (rec_ms * 1e-3) / 1e12 / pk["bf16_tflops_sustained"]},
             "warp_aggregate": {"bound": "hbm", "ms_per_plane": wa_ms, "algorithmic_bytes": wa_bytes,

@@ -180,6 +180,9 @@ void aarmvs_debug_stem_profile_buffer(void* buf);
  * 64 x 12 uint64, CTA 0 of subsequent aarmvs_convlstm_cell_tc launches records clock64 stamps of its loader / MMA /
  * epilogue roles per tile.  Pass NULL to switch off. */
 void aarmvs_debug_profile_buffer(void* buf);
+/* Debug ablation switches for aarmvs_convlstm_cell_tc (results become wrong): 1 no global loads in the loader, 2 no
+ * operand stores, 4 no global I/O in the epilogue, 8 no MMAs. */
+void aarmvs_debug_cell_flags(int flags);
 
 #ifdef __cplusplus
 }

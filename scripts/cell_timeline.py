@@ -25,3 +25,13 @@ print("avg per tile: loader fill (wait1->stored) %.0f, loader wait %.0f | mma wa
     (d[:, 2] - d[:, 1]).float().mean(), (d[:, 1] - d[:, 0]).float().mean(), (d[:, 5] - d[:, 4]).float().mean(), (d[:, 6] - d[:, 5]).float().mean(),
     (d[:, 7] - d[:, 6]).float().mean(), (d[:, 9] - d[:, 8]).float().mean(), (d[:, 10] - d[:, 9]).float().mean(), (d[:, 11] - d[:, 10]).float().mean(),
     (d[1:, 7] - d[:-1, 7]).float().mean()))
+
+for flags, name in ((0, "full"), (1, "no loader LDG"), (2, "no loader STS"), (3, "no loader LDG/STS"), (4, "no epilogue global I/O"), (7, "MMA + handshakes only"), (8, "no MMA"), (15, "handshakes only")):
+    lib.aarmvs_debug_cell_flags(flags)
+    ops.convlstm_cell(m, 0, x, h, c); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5): ops.convlstm_cell(m, 0, x, h, c)
+    e1.record(); torch.cuda.synchronize()
+    print(f"{name:26s} {e0.elapsed_time(e1) / 5:.3f} ms  (incl. the NCHW<->NHWC conversions of the seam, constant)")
+lib.aarmvs_debug_cell_flags(0)
