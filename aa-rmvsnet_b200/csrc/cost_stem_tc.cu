@@ -59,6 +59,7 @@ struct StemArgs {
     int align_corners;
     float* t0;
     double* stats;
+    float* costv;               // optional [K][S][P][32]: (warp-ref)^2 of the tile's interior pixels for a gather-free pass D
     unsigned long long* prof;   // debug: clock64 stamps of group 0 of CTA 0, [64 fills][8]
     int dbg;                    // debug ablation flags (aarmvs_debug_flags): 1 skip gather loads, 2 skip recipes, 4 skip MMA
 };
@@ -162,7 +163,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) cost_stem_tc_kernel(const __grid
                 TapRec rec;
                 rec.o[0] = rec.o[1] = rec.o[2] = rec.o[3] = 0;
                 rec.w[0] = rec.w[1] = rec.w[2] = rec.w[3] = 0.f;
-                rec.ref_off = -1; rec.pad0 = rec.pad1 = rec.pad2 = 0;
+                rec.ref_off = -1; rec.pad0 = (r >= 1 && r <= TR && cc >= 1 && cc <= TCOL) ? 1 : 0; rec.pad1 = rec.pad2 = 0;   // pad0: interior pixel
                 if (y >= 0 && y < a.H && x >= 0 && x < a.W && !(a.dbg & 2)) {
                     float ix, iy;
                     sweep_position(scam + v * 12, (float)x, (float)y, depth, a.W, a.H, a.align_corners != 0, ix, iy);
@@ -180,10 +181,11 @@ __global__ void __launch_bounds__(N_THREADS, 1) cost_stem_tc_kernel(const __grid
             if (pf) pp[1] = clock64();
             // ---- 2. gather, (warp - ref)^2, split, stage
             const float* sv = a.src + (size_t)v * a.view_stride;
+            float* costv_slot = a.costv ? a.costv + ((size_t)(k * a.S + v) * P) * 32 : nullptr;
 #pragma unroll 1
             for (int jb = 0; jb < ITEMS; jb += NB) {
                 float4 ta[NB], tb[NB], tcn[NB], td[NB], rv[NB], wq[NB];
-                int roff[NB];
+                int roff[NB], interior[NB];
 #pragma unroll
                 for (int j = 0; j < NB; ++j) {
                     const int i = min(lt + (jb + j) * GROUP_THREADS, NPX * 8 - 1);
@@ -191,6 +193,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) cost_stem_tc_kernel(const __grid
                     const int4 o = *reinterpret_cast<const int4*>(taps[px].o);
                     wq[j] = *reinterpret_cast<const float4*>(taps[px].w);
                     roff[j] = taps[px].ref_off;
+                    interior[j] = taps[px].pad0;
                     if (a.dbg & 1) {
                         ta[j] = tb[j] = tcn[j] = td[j] = rv[j] = make_float4(1.f, 2.f, 3.f, 4.f);
                     } else {
@@ -213,6 +216,8 @@ __global__ void __launch_bounds__(N_THREADS, 1) cost_stem_tc_kernel(const __grid
                     const float dx = gx - rv[j].x, dy = gy - rv[j].y, dz = gz - rv[j].z, dw = gw - rv[j].w;
                     const bool in = roff[j] >= 0;
                     const float4 cv = make_float4(in ? dx * dx : 0.f, in ? dy * dy : 0.f, in ? dz * dz : 0.f, in ? dw * dw : 0.f);
+                    if (a.costv && in && interior[j] && iraw < NPX * 8)          // interior pixel of this tile, inside the image
+                        st4(costv_slot + roff[j] + c4 * 4, cv);
                     uint2 hi, lo;
                     tc::split4_f16(cv, hi, lo);
                     if (iraw < NPX * 8) {
@@ -300,7 +305,7 @@ extern "C" void aarmvs_debug_stem_profile_buffer(void* buf) { g_stem_prof = (uns
 extern "C" int aarmvs_cost_stem_tc(const float* ref, const float* src, size_t view_stride, int H, int W, int S,
                                    const float* cams, const void* stem_w_f16, const float* stem_b_host,
                                    const float* depth_values, int d_host, const int* d_dev, int planes, int align_corners,
-                                   float* t0, double* stats, void* stream) {
+                                   float* t0, double* stats, float* costv_out, void* stream) {
     AARMVS_CHECK_ARG(ref && src && t0 && stats && stem_w_f16 && stem_b_host && depth_values && cams && H > 0 && W > 0);
     AARMVS_CHECK_ARG(S >= 1 && S <= AARMVS_MAX_SRC && planes >= 1 && planes <= AARMVS_MAX_PLANES);
     StemArgs a = {};
@@ -310,6 +315,7 @@ extern "C" int aarmvs_cost_stem_tc(const float* ref, const float* src, size_t vi
     for (int i = 0; i < 4; ++i) a.bias[i] = stem_b_host[i];
     a.depth_values = depth_values; a.d_host = d_host; a.d_dev = d_dev; a.align_corners = align_corners; a.t0 = t0;
     a.stats = stats;
+    a.costv = costv_out;
     a.dbg = g_dbg;
     a.prof = g_stem_prof;
     static bool attr_set = false;

@@ -334,6 +334,65 @@ aggregate_kernel(const float* __restrict__ ref, const float* __restrict__ src, s
     }
 }
 
+// ------------------------------------------------------------------------------------------------ pass D, streamed
+// Same result as aggregate_kernel, but (warp - ref)^2 is read back from pass A's costv [K][S][P][32] instead of being
+// gathered a second time: a pure HBM stream (S * 128 + S * 16 B read, 128 B written per pixel and plane).
+__global__ void __launch_bounds__(256)
+aggregate_stream_kernel(const float* __restrict__ costv, int S, int K, size_t P, const __grid_constant__ OmegaTail q,
+                        const float* __restrict__ t0, const double* __restrict__ stats, float* __restrict__ cost,
+                        float* __restrict__ reweight_out) {
+    __shared__ OmegaNorm norms_all[AARMVS_MAX_PLANES * AARMVS_MAX_SRC];
+    if (threadIdx.x < S * K) {
+        OmegaNorm n;
+        const double cnt = 4.0 * (double)P;
+        gn_mean_rstd(stats + threadIdx.x * 6 + 0, cnt, n.m1, n.r1);
+        gn_mean_rstd(stats + threadIdx.x * 6 + 2, cnt, n.m2, n.r2);
+        gn_mean_rstd(stats + threadIdx.x * 6 + 4, cnt, n.m3, n.r3);
+        norms_all[threadIdx.x] = n;
+    }
+    __syncthreads();
+    const int sub = threadIdx.x & 7;
+    const float s_den = (float)S;
+    const size_t total = P * K;
+    for (size_t i = (size_t)blockIdx.x * 32 + (threadIdx.x >> 3); i < total; i += (size_t)gridDim.x * 32) {
+        const int k = (int)(i / P);
+        const size_t p = i - (size_t)k * P;
+        const OmegaNorm* norms = norms_all + k * S;
+        const float* t0k = t0 + (size_t)k * S * P * 4;
+        const float* cvk = costv + (size_t)k * S * P * 32;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int v0 = 0; v0 < S; v0 += 8) {
+            const int mv = v0 + sub;
+            float wm = 0.f;
+            if (mv < S) {            // lane j of the pixel's 8-lane group evaluates view v0 + j's reweight
+                float a1[4], u[4], vv[4];
+                omega_u(q, norms[mv], ldg4(t0k + ((size_t)mv * P + p) * 4), a1, u);
+                omega_v(q, norms[mv], u, vv);
+                wm = omega_w(q, norms[mv], a1, vv);
+                if (reweight_out) reweight_out[((size_t)k * S + mv) * P + p] = wm;
+            }
+            const int nv = min(8, S - v0);
+            float4 c[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+                if (e < nv) c[e] = ldg4(cvk + ((size_t)(v0 + e) * P + p) * 32 + sub * 4);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const float wv = __shfl_sync(0xffffffffu, wm, e, 8) + 1.0f;
+                if (e >= nv) continue;
+                if (v0 + e == 0) {
+                    acc = make_float4(__fmul_rn(wv, c[e].x), __fmul_rn(wv, c[e].y), __fmul_rn(wv, c[e].z), __fmul_rn(wv, c[e].w));
+                } else {
+                    acc.x = __fadd_rn(acc.x, __fmul_rn(wv, c[e].x)); acc.y = __fadd_rn(acc.y, __fmul_rn(wv, c[e].y));
+                    acc.z = __fadd_rn(acc.z, __fmul_rn(wv, c[e].z)); acc.w = __fadd_rn(acc.w, __fmul_rn(wv, c[e].w));
+                }
+            }
+        }
+        st4(cost + i * 32 + sub * 4, make_float4(-__fdiv_rn(acc.x, s_den), -__fdiv_rn(acc.y, s_den), -__fdiv_rn(acc.z, s_den),
+                                                 -__fdiv_rn(acc.w, s_den)));
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ C ABI
 #include "../../include/aarmvs.h"
 
@@ -400,11 +459,19 @@ extern "C" int aarmvs_omega_stats(int stage, const float* t0, int H, int W, int 
 extern "C" int aarmvs_aggregate(const float* ref, const float* src, size_t view_stride, int H, int W, int S,
                                 const float* cams, const float* tail_host, const float* depth_values, int d_host,
                                 const int* d_dev, int planes, int align_corners, const float* t0, const double* stats,
-                                float* cost, float* reweight_out, void* stream) {
-    AARMVS_CHECK_ARG(ref && src && t0 && stats && cost && tail_host && depth_values && cams && H > 0 && W > 0);
+                                const float* costv, float* cost, float* reweight_out, void* stream) {
+    AARMVS_CHECK_ARG(t0 && stats && cost && tail_host && H > 0 && W > 0);
     AARMVS_CHECK_ARG(S >= 1 && S <= AARMVS_MAX_SRC && planes >= 1 && planes <= AARMVS_MAX_PLANES);
     OmegaTail q;
     fill_tail(q, tail_host);
+    if (costv) {           // pass A kept (warp - ref)^2: stream it instead of gathering again
+        const size_t Pn = (size_t)H * W;
+        const size_t groups = (Pn * planes + 31) / 32;
+        const int nblk = (int)(groups < (size_t)148 * 32 ? groups : (size_t)148 * 32);
+        aggregate_stream_kernel<<<nblk, 256, 0, (cudaStream_t)stream>>>(costv, S, planes, Pn, q, t0, stats, cost, reweight_out);
+        AARMVS_LAUNCH_RESULT();
+    }
+    AARMVS_CHECK_ARG(ref && src && depth_values && cams);
     const int ntiles = ((W + AG_TW - 1) / AG_TW) * ((H + AG_TH - 1) / AG_TH);
     const int blocks = ntiles < 148 * AGG_MINB ? ntiles : 148 * AGG_MINB;
     aggregate_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(ref, src, view_stride, H, W, S, planes, cams, q, depth_values, d_host,

@@ -43,10 +43,11 @@ def _src_array(*srcs):
 class Engine:
     """Runs EMVSNet.forward's arithmetic for one model instance (weights are re-packed when they change)."""
 
-    def __init__(self, module, align_corners=False, use_graph=True, cell_math="tc", plane_batch=8):
+    def __init__(self, module, align_corners=False, use_graph=True, cell_math="tc", plane_batch=8, keep_costv=True):
         if cell_math not in ("tc", "fma"):
             raise ValueError("cell_math must be 'tc' (tcgen05, split-fp16 operands) or 'fma' (fp32 CUDA cores)")
         self.cell_math = cell_math
+        self.keep_costv = keep_costv
         if not 1 <= plane_batch <= 16:
             raise ValueError("plane_batch must be in 1..16")
         self.plane_batch = plane_batch            # planes per launch of passes A-D (L1/L2 reuse of the source features)
@@ -138,6 +139,8 @@ class Engine:
         # plane sweep
         ws["t0"] = torch.empty(K, S, P, 4, **f32)
         ws["cost"] = torch.empty(K, P, 32, **f32)
+        # (warp - ref)^2 kept by pass A so that pass D streams instead of gathering again (tensor-core path only)
+        ws["costv"] = torch.empty(K, S, P, 32, **f32) if self.cell_math == "tc" and self.keep_costv else None
         ws["h"] = [torch.empty(2, P // (s * s), ch, **f32) for ch, s in zip(_HID, _SCALE)]
         ws["c"] = [torch.empty(P // (s * s), ch, **f32) for ch, s in zip(_HID, _SCALE)]
         ws["up0"] = torch.empty(P // 4, 16, **f32)
@@ -200,12 +203,12 @@ class Engine:
                                             _ptr(g1[0]), _ptr(g1[1]), _ptr(g2[0]), _ptr(g2[1]), H, W, _ptr(out), stream),
                    "aarmvs_feat_assemble")
 
-    def cost_stem(self, ref, src, view_stride, H, W, S, cams, w, depths, d_host, dptr, planes, t0, sums, stream):
+    def cost_stem(self, ref, src, view_stride, H, W, S, cams, w, depths, d_host, dptr, planes, t0, sums, stream, costv=None):
         """Pass A (gather, (warp - ref)^2, omega stem conv) on the tensor cores ('tc') or the fp32 FMA pipe ('fma')."""
         ac = int(self.align_corners)
         if self.cell_math == "tc":
             capi.check(self.lib.aarmvs_cost_stem_tc(ref, src, view_stride, H, W, S, cams, _ptr(w["stem.wtc"]), w["stem.b_host"],
-                                                    depths, d_host, dptr, planes, ac, t0, sums, stream), "aarmvs_cost_stem_tc")
+                                                    depths, d_host, dptr, planes, ac, t0, sums, costv, stream), "aarmvs_cost_stem_tc")
         else:
             capi.check(self.lib.aarmvs_cost_stem(ref, src, view_stride, H, W, S, cams, w["stem.w_host"], w["stem.b_host"],
                                                  depths, d_host, dptr, planes, ac, t0, sums, stream), "aarmvs_cost_stem")
@@ -229,15 +232,16 @@ class Engine:
         ref, src = _ptr(feat), _ptr(feat, P * 32)
         ps = ws["psums"]
         n_omega = ws["K"] * S * 6
+        costv = _ptr(ws["costv"]) if ws["costv"] is not None else None
         self.cost_stem(ref, src, P * 32, H, W, S, _ptr(ws["cams"]), w, _ptr(ws["depths"]), 0, dptr, nplanes, _ptr(ws["t0"]),
-                       _ptr(ps), stream)
+                       _ptr(ps), stream, costv)
         mark("cost_stem")
         for stage in (2, 3):
             capi.check(lib.aarmvs_omega_stats(stage, _ptr(ws["t0"]), H, W, S, nplanes, w["tail_host"], _ptr(ps), stream),
                        "aarmvs_omega_stats")
         mark("omega_stats")
         capi.check(lib.aarmvs_aggregate(ref, src, P * 32, H, W, S, _ptr(ws["cams"]), w["tail_host"], _ptr(ws["depths"]), 0,
-                                        dptr, nplanes, ac, _ptr(ws["t0"]), _ptr(ps), _ptr(ws["cost"]), None, stream),
+                                        dptr, nplanes, ac, _ptr(ws["t0"]), _ptr(ps), costv, _ptr(ws["cost"]), None, stream),
                    "aarmvs_aggregate")
         mark("aggregate")
         h, c = ws["h"], ws["c"]

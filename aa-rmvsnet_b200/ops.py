@@ -62,7 +62,7 @@ def feat_net(model, img):
     return out
 
 
-def aggregate_plane(model, ref_fea, src_feas, ref_proj, src_projs, depth_value):
+def aggregate_plane(model, ref_fea, src_feas, ref_proj, src_projs, depth_value, stream_costv=True):
     """models/drmvsnet.py:307-318 for one sample: ref_fea [32,H,W], src_feas list of [32,H,W], projections [4,4].
     Returns (volume_variance [32,H,W], reweight maps [S,H,W])."""
     _need_cuda(ref_fea)
@@ -79,11 +79,13 @@ def aggregate_plane(model, ref_fea, src_feas, ref_proj, src_projs, depth_value):
     cost = torch.empty(P, 32, device=dev)
     rew = torch.empty(S, P, device=dev)
     st, ac = _stream(dev), int(eng.align_corners)
-    eng.cost_stem(_ptr(feat), _ptr(feat, P * 32), P * 32, H, W, S, _ptr(cams), w, _ptr(depths), 0, None, 1, _ptr(t0), _ptr(sums), st)
+    cv = torch.empty(S, P, 32, device=dev) if (eng.cell_math == "tc" and stream_costv) else None
+    costv = _ptr(cv) if cv is not None else None
+    eng.cost_stem(_ptr(feat), _ptr(feat, P * 32), P * 32, H, W, S, _ptr(cams), w, _ptr(depths), 0, None, 1, _ptr(t0), _ptr(sums), st, costv)
     for stage in (2, 3):
         capi.check(lib.aarmvs_omega_stats(stage, _ptr(t0), H, W, S, 1, w["tail_host"], _ptr(sums), st), "aarmvs_omega_stats")
     capi.check(lib.aarmvs_aggregate(_ptr(feat), _ptr(feat, P * 32), P * 32, H, W, S, _ptr(cams), w["tail_host"],
-                                    _ptr(depths), 0, None, 1, ac, _ptr(t0), _ptr(sums), _ptr(cost), _ptr(rew), st),
+                                    _ptr(depths), 0, None, 1, ac, _ptr(t0), _ptr(sums), costv, _ptr(cost), _ptr(rew), st),
                "aarmvs_aggregate")
     return -_nchw(cost, H, W), rew.view(S, H, W)
 

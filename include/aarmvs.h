@@ -100,10 +100,12 @@ int aarmvs_cost_stem(const float* ref, const float* src, size_t view_stride, int
 /* Pass A with the 3x3 stem conv on the tensor cores (tcgen05 implicit GEMM over the staged (warp - ref)^2 halo tile,
  * split-fp16 operands, fp32 accumulation in TMEM).  Arguments as aarmvs_cost_stem except
  * stem_w_f16: DEVICE [2 planes hi,lo][4 chunks of 8 input channels][48 columns][8] fp16, column = tap * 4 + output
- * channel (36 used): the conv runs as one [pixels] x [9 taps * 4] GEMM + a shifted 9-tap sum in the epilogue. */
+ * channel (36 used): the conv runs as one [pixels] x [9 taps * 4] GEMM + a shifted 9-tap sum in the epilogue.
+ * costv_out: optional [planes][S][H*W][32] store of (warp - ref)^2 (fp32) that lets aarmvs_aggregate skip its gather. */
 int aarmvs_cost_stem_tc(const float* ref, const float* src, size_t view_stride, int H, int W, int S, const float* cams,
                         const void* stem_w_f16, const float* stem_b_host, const float* depth_values, int d_host,
-                        const int* d_dev, int planes, int align_corners, float* t0, double* stats, void* stream);
+                        const int* d_dev, int planes, int align_corners, float* t0, double* stats, float* costv_out,
+                        void* stream);
 
 /* Pass B (stage 2) / pass C (stage 3): GroupNorm-2 / GroupNorm-3 sums of the omega residual block
  * (models/module.py:256-258) recomputed point-wise from t0.  tail_host: aarmvs_omega_tail_floats() floats. */
@@ -111,11 +113,12 @@ int aarmvs_omega_stats(int stage, const float* t0, int H, int W, int S, int plan
                        double* stats, void* stream);
 
 /* Pass D: cost[p][c] = -(sum_v (omega_v(p) + 1) * (warp_v - ref)^2) / S  (models/drmvsnet.py:311-319), the input
- * of the recurrent regulariser.  reweight_out: optional [S][H*W] omega maps (operator seam / tests), may be NULL. */
+ * of the recurrent regulariser.  costv: NULL = gather again; else pass A's costv_out, read back as a pure stream (ref, src,
+ * cams, depth_values are then unused).  reweight_out: optional omega maps (operator seam / tests), may be NULL. */
 int aarmvs_aggregate(const float* ref, const float* src, size_t view_stride, int H, int W, int S, const float* cams,
                      const float* tail_host, const float* depth_values, int d_host, const int* d_dev, int planes,
-                     int align_corners, const float* t0, const double* stats, float* cost, float* reweight_out,
-                     void* stream);
+                     int align_corners, const float* t0, const double* stats, const float* costv, float* cost,
+                     float* reweight_out, void* stream);
 
 /* ---- recurrent regularisation (models/drmvsnet.py:119-167) --------------------------------------------- */
 

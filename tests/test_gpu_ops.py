@@ -79,10 +79,12 @@ def model_fma():
     return m.cuda().eval()
 
 
-@pytest.mark.parametrize("math", ["tc", "fma"])
+@pytest.mark.parametrize("math", ["tc", "tc-gather", "fma"])
 @pytest.mark.parametrize("hw", [(32, 40), (36, 52), (20, 100)])
 def test_aggregate_plane_and_omega(ops_dtu, sd_dtu, model, model_fma, hw, math):
-    model = model if math == "tc" else model_fma
+    """tc: pass A keeps (warp-ref)^2 and pass D streams it; tc-gather / fma: pass D gathers a second time."""
+    stream_costv = math == "tc"
+    model = model_fma if math == "fma" else model
     """warp + (warp-ref)^2 + omega + weighted sum, against the oracle, incl. sizes that do not fill the 16x32 tiles."""
     from aarmvsnet_b200 import ops, synth
     h, w = hw
@@ -92,7 +94,7 @@ def test_aggregate_plane_and_omega(ops_dtu, sd_dtu, model, model_fma, hw, math):
     pm, dv = s["proj_matrices"], s["depth_values"][:, 1]
     want = orc.aggregate_plane(feats[0], feats[1:], pm[:, 0], [pm[:, v] for v in range(1, 4)], dv, sd_dtu)
     got, rew = ops.aggregate_plane(model, feats[0][0].cuda(), [f[0].cuda() for f in feats[1:]], pm[0, 0],
-                                   [pm[0, v] for v in range(1, 4)], dv[0])
+                                   [pm[0, v] for v in range(1, 4)], dv[0], stream_costv=stream_costv)
     for v in range(3):
         c = (orc.homo_warp(feats[v + 1], pm[:, v + 1], pm[:, 0], dv) - feats[0]).pow(2)
         torch.testing.assert_close(rew[v].cpu(), orc.omega(c, sd_dtu)[0, 0], rtol=1e-4, atol=2e-5)
