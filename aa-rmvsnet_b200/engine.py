@@ -301,8 +301,21 @@ class Engine:
         proj = torch.matmul(pm[1:], torch.inverse(ref))
         return torch.cat([proj[:, :3, :3].reshape(-1, 9), proj[:, :3, 3]], 1).contiguous()
 
-    def depth_map(self, imgs, proj_matrices, depth_values, keep_cost=False):
-        """imgs [N,3,H,W], proj_matrices [N,4,4], depth_values [D] -> dict of [H,W] maps (views of the workspace)."""
+    def features(self, img):
+        """FeatNet of one image [3,H,W] -> a new [H*W, 32] NHWC feature tensor (for per-scan feature caching)."""
+        device = img.device
+        if device.type != "cuda":
+            raise RuntimeError("aarmvsnet_b200 has no CPU path: inputs must live on a CUDA device")
+        _, H, W = img.shape
+        w = self._weights(device)
+        ws = self._workspace(H, W, 2, 1, device, False)
+        stream = ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+        self.feature_map(img.to(torch.float32).contiguous(), ws["feat"][0], ws, w, stream)
+        return ws["feat"][0].clone()
+
+    def depth_map(self, imgs, proj_matrices, depth_values, keep_cost=False, features=None):
+        """imgs [N,3,H,W], proj_matrices [N,4,4], depth_values [D] -> dict of [H,W] maps (views of the workspace).
+        features: optional list of N cached [H*W,32] feature tensors (from features()); FeatNet is then skipped."""
         device = imgs.device
         if device.type != "cuda":
             raise RuntimeError("aarmvsnet_b200 has no CPU path: inputs must live on a CUDA device")
@@ -311,9 +324,15 @@ class Engine:
         w = self._weights(device)
         ws = self._workspace(H, W, N, D, device, keep_cost)
         stream = ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
-        imgs = imgs.to(torch.float32).contiguous()
-        for v in range(N):
-            self.feature_map(imgs[v], ws["feat"][v], ws, w, stream)
+        if features is not None:
+            if len(features) != N:
+                raise RuntimeError(f"{N} views but {len(features)} cached feature maps")
+            for v in range(N):
+                ws["feat"][v].copy_(features[v], non_blocking=True)
+        else:
+            imgs = imgs.to(torch.float32).contiguous()
+            for v in range(N):
+                self.feature_map(imgs[v], ws["feat"][v], ws, w, stream)
         ws["cams"].copy_(self.relative_cameras(proj_matrices), non_blocking=True)
         ws["depths"].copy_(depth_values.to(torch.float32), non_blocking=True)
         ws["plane"].zero_()

@@ -118,6 +118,11 @@ class EMVSNet(nn.Module):
         self._engine = Engine(self, align_corners=align_corners, use_graph=use_graph, cell_math=cell_math,
                               plane_batch=plane_batch, keep_costv=keep_costv)
 
+    def features(self, img):
+        """FeatNet of one image [3,H,W] as the kernels' NHWC feature tensor [H*W,32] (cacheable across reference views)."""
+        with torch.no_grad():
+            return self._engine.features(img)
+
     def forward(self, imgs, proj_matrices, depth_values):
         if imgs.dim() != 5 or imgs.shape[2] != 3:
             raise RuntimeError(f"imgs must be [B,N,3,H,W], got {tuple(imgs.shape)}")

@@ -1,0 +1,97 @@
+"""Formats either side of the path: cam / pair parsers, crop + scale, PFM round trip (CPU)."""
+import os
+
+import numpy as np
+import pytest
+
+
+def _write_scan(tmp, n_views=4, h=72, w=88):
+    from PIL import Image
+    rng = np.random.default_rng(0)
+    os.makedirs(tmp / "images"); os.makedirs(tmp / "cams")
+    for v in range(n_views):
+        Image.fromarray(rng.integers(0, 255, (h, w, 3), dtype=np.uint8)).save(tmp / "images" / f"{v:08d}.png")
+        E = np.eye(4, dtype=np.float32); E[0, 3] = -30.0 * v
+        K = np.array([[150.0, 0, w / 2], [0, 150.0, h / 2], [0, 0, 1]], dtype=np.float32)
+        with open(tmp / "cams" / f"{v:08d}_cam.txt", "w") as f:
+            f.write("extrinsic\n" + "\n".join(" ".join(f"{x:.6f}" for x in row) for row in E) + "\n\n")
+            f.write("intrinsic\n" + "\n".join(" ".join(f"{x:.6f}" for x in row) for row in K) + "\n\n")
+            f.write("425.0 2.5\n")
+    with open(tmp / "pair.txt", "w") as f:
+        f.write(f"{n_views}\n")
+        for v in range(n_views):
+            others = [u for u in range(n_views) if u != v]
+            f.write(f"{v}\n{len(others)} " + " ".join(f"{u} {100.0 - u:.1f}" for u in others) + "\n")
+    return tmp
+
+
+def test_pair_and_cam_parsers(tmp_path):
+    from aarmvsnet_b200 import scanio
+    scan = _write_scan(tmp_path)
+    pairs = scanio.read_pair_file(scan / "pair.txt")
+    assert len(pairs) == 4 and pairs[0] == (0, [1, 2, 3]) and pairs[2] == (2, [0, 1, 3])
+    K, E, dmin, dint = scanio.read_cam_file(scan / "cams" / "00000002_cam.txt", interval_scale=0.4)
+    assert K.shape == (3, 3) and E.shape == (4, 4) and K.dtype == np.float32
+    assert E[0, 3] == -60.0 and K[0, 0] == 150.0 and dmin == 425.0 and abs(dint - 1.0) < 1e-6
+    P = scanio.projection(K, E)
+    np.testing.assert_allclose(P[:3, :4], K @ E[:3, :4])
+    assert (P[3] == [0, 0, 0, 1]).all()
+    img, *_ = scanio.load_view(str(scan), 1)
+    assert img.shape == (72, 88, 3) and abs(img.mean()) < 1e-4 and abs(img[..., 0].std() - 1) < 1e-3
+
+
+def test_depth_hypotheses_and_fit():
+    from aarmvsnet_b200 import scanio
+    d = scanio.depth_hypotheses(425.0, 1.0, 512, inverse_depth=False)
+    assert d.shape == (512,) and d[0] == 425.0 and d[-1] == 936.0 and d.dtype == np.float32
+    inv = scanio.depth_hypotheses(425.0, 1.0, 8, inverse_depth=True)
+    assert abs(inv[0] - 425.0) < 1e-3 and np.all(np.diff(inv) > 0)
+    np.testing.assert_allclose(np.diff(1.0 / inv), np.diff(1.0 / inv)[0], rtol=1e-4)      # uniform in 1/depth
+    assert scanio.fit_scale([(1200, 1600)], 600, 800) == 0.5
+    with pytest.raises(ValueError):
+        scanio.fit_scale([(500, 800)], 600, 800)
+    img = np.zeros((74, 91, 3), np.float32)
+    K = np.array([[100.0, 0, 45.5], [0, 100.0, 37.0], [0, 0, 1]], np.float32)
+    out, k2 = scanio.crop_view(img, K, 64, 88)
+    assert out.shape[:2] == (64, 88) and k2[0, 2] == K[0, 2] - 2 and k2[1, 2] == K[1, 2] - 5
+    out, k2 = scanio.crop_view(img, K, 600, 800)                 # fits: rounded down to multiples of 8
+    assert out.shape[:2] == (72, 88)
+
+
+def test_pfm_round_trip(tmp_path):
+    from aarmvsnet_b200 import scanio
+    a = np.random.default_rng(1).random((13, 17), dtype=np.float32)
+    scanio.save_pfm(tmp_path / "sub" / "a.pfm", a)
+    b, scale = scanio.read_pfm(tmp_path / "sub" / "a.pfm")
+    assert scale == 1.0 and np.array_equal(a, b)
+    raw = open(tmp_path / "sub" / "a.pfm", "rb").read()
+    assert raw.startswith(b"Pf\n17 13\n-1.000000\n")             # grey, width height, little endian
+    np.testing.assert_array_equal(np.frombuffer(raw[-17 * 4:], "<f4"), a[0])      # rows are stored bottom-up
+    c = np.random.default_rng(2).random((5, 4, 3), dtype=np.float32)
+    scanio.save_pfm(tmp_path / "c.pfm", c)
+    assert np.array_equal(scanio.read_pfm(tmp_path / "c.pfm")[0], c)
+    with pytest.raises(ValueError):
+        scanio.save_pfm(tmp_path / "d.pfm", a.astype(np.float64))
+
+
+@pytest.mark.gpu
+def test_eval_scan_driver(tmp_path):
+    """The driver end to end on a synthetic scan, with and without the per-scan feature cache."""
+    import subprocess
+    import sys
+    from conftest import ROOT
+    from aarmvsnet_b200 import scanio
+    scan = _write_scan(tmp_path / "scan0", n_views=4, h=72, w=88)
+    outs = []
+    for extra in ([], ["--cache_features"]):
+        out = tmp_path / ("out" + str(len(extra)))
+        cmd = [sys.executable, os.path.join(ROOT, "eval_scan.py"), "--scan", str(scan), "--out", str(out), "--numdepth", "16",
+               "--view_num", "3", "--max_h", "64", "--max_w", "80"] + extra
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        depth, _ = scanio.read_pfm(out / "depth_est" / "00000001.pfm")
+        conf, _ = scanio.read_pfm(out / "confidence" / "00000001.pfm")
+        assert depth.shape == (64, 80) and conf.shape == (64, 80) and (conf > 0).all() and (conf <= 1).all()
+        assert len(os.listdir(out / "depth_est")) == 4
+        outs.append((depth, conf))
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.allclose(outs[0][1], outs[1][1], atol=1e-6)
