@@ -337,7 +337,13 @@ aggregate_kernel(const float* __restrict__ ref, const float* __restrict__ src, s
 // ------------------------------------------------------------------------------------------------ pass D, streamed
 // Same result as aggregate_kernel, but (warp - ref)^2 is read back from pass A's costv [K][S][P][32] instead of being
 // gathered a second time: a pure HBM stream (S * 128 + S * 16 B read, 128 B written per pixel and plane).
-__global__ void __launch_bounds__(256)
+#ifndef AGS_PX
+#define AGS_PX 1               // pixels per 8-lane group and loop iteration (bytes in flight)
+#endif
+#ifndef AGS_MINB
+#define AGS_MINB 4
+#endif
+__global__ void __launch_bounds__(256, AGS_MINB)
 aggregate_stream_kernel(const float* __restrict__ costv, int S, int K, size_t P, const __grid_constant__ OmegaTail q,
                         const float* __restrict__ t0, const double* __restrict__ stats, float* __restrict__ cost,
                         float* __restrict__ reweight_out) {
@@ -353,43 +359,60 @@ aggregate_stream_kernel(const float* __restrict__ costv, int S, int K, size_t P,
     __syncthreads();
     const int sub = threadIdx.x & 7;
     const float s_den = (float)S;
-    const size_t total = P * K;
-    for (size_t i = (size_t)blockIdx.x * 32 + (threadIdx.x >> 3); i < total; i += (size_t)gridDim.x * 32) {
-        const int k = (int)(i / P);
-        const size_t p = i - (size_t)k * P;
-        const OmegaNorm* norms = norms_all + k * S;
-        const float* t0k = t0 + (size_t)k * S * P * 4;
-        const float* cvk = costv + (size_t)k * S * P * 32;
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const size_t total = P * K, stride = (size_t)gridDim.x * 32;
+    for (size_t i0 = (size_t)blockIdx.x * 32 + (threadIdx.x >> 3); i0 < total; i0 += stride * AGS_PX) {
+        float4 acc[AGS_PX];
+#pragma unroll
+        for (int u = 0; u < AGS_PX; ++u) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int v0 = 0; v0 < S; v0 += 8) {
-            const int mv = v0 + sub;
-            float wm = 0.f;
-            if (mv < S) {            // lane j of the pixel's 8-lane group evaluates view v0 + j's reweight
-                float a1[4], u[4], vv[4];
-                omega_u(q, norms[mv], ldg4(t0k + ((size_t)mv * P + p) * 4), a1, u);
-                omega_v(q, norms[mv], u, vv);
-                wm = omega_w(q, norms[mv], a1, vv);
-                if (reweight_out) reweight_out[((size_t)k * S + mv) * P + p] = wm;
+            const int nv = min(8, S - v0), mv = v0 + sub;
+            float4 c[AGS_PX][8], tq[AGS_PX];
+            // all loads of this step first
+#pragma unroll
+            for (int u = 0; u < AGS_PX; ++u) {
+                const size_t i = min(i0 + u * stride, total - 1);
+                const int k = (int)(i / P);
+                const size_t p = i - (size_t)k * P;
+                tq[u] = mv < S ? ldg4(t0 + ((size_t)(k * S + mv) * P + p) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int e = 0; e < 8; ++e)
+                    if (e < nv) c[u][e] = ldg4(costv + ((size_t)(k * S + v0 + e) * P + p) * 32 + sub * 4);
             }
-            const int nv = min(8, S - v0);
-            float4 c[8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e)
-                if (e < nv) c[e] = ldg4(cvk + ((size_t)(v0 + e) * P + p) * 32 + sub * 4);
+            for (int u = 0; u < AGS_PX; ++u) {
+                const size_t i = min(i0 + u * stride, total - 1);
+                const int k = (int)(i / P);
+                const size_t p = i - (size_t)k * P;
+                const OmegaNorm* norms = norms_all + k * S;
+                float wm = 0.f;
+                if (mv < S) {            // lane j of the pixel's 8-lane group evaluates view v0 + j's reweight
+                    float a1[4], uu[4], vv[4];
+                    omega_u(q, norms[mv], tq[u], a1, uu);
+                    omega_v(q, norms[mv], uu, vv);
+                    wm = omega_w(q, norms[mv], a1, vv);
+                    if (reweight_out && i0 + u * stride < total) reweight_out[((size_t)k * S + mv) * P + p] = wm;
+                }
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                const float wv = __shfl_sync(0xffffffffu, wm, e, 8) + 1.0f;
-                if (e >= nv) continue;
-                if (v0 + e == 0) {
-                    acc = make_float4(__fmul_rn(wv, c[e].x), __fmul_rn(wv, c[e].y), __fmul_rn(wv, c[e].z), __fmul_rn(wv, c[e].w));
-                } else {
-                    acc.x = __fadd_rn(acc.x, __fmul_rn(wv, c[e].x)); acc.y = __fadd_rn(acc.y, __fmul_rn(wv, c[e].y));
-                    acc.z = __fadd_rn(acc.z, __fmul_rn(wv, c[e].z)); acc.w = __fadd_rn(acc.w, __fmul_rn(wv, c[e].w));
+                for (int e = 0; e < 8; ++e) {
+                    const float wv = __shfl_sync(0xffffffffu, wm, e, 8) + 1.0f;
+                    if (e >= nv) continue;
+                    const float4 ce = c[u][e];
+                    if (v0 + e == 0) {
+                        acc[u] = make_float4(__fmul_rn(wv, ce.x), __fmul_rn(wv, ce.y), __fmul_rn(wv, ce.z), __fmul_rn(wv, ce.w));
+                    } else {
+                        acc[u].x = __fadd_rn(acc[u].x, __fmul_rn(wv, ce.x)); acc[u].y = __fadd_rn(acc[u].y, __fmul_rn(wv, ce.y));
+                        acc[u].z = __fadd_rn(acc[u].z, __fmul_rn(wv, ce.z)); acc[u].w = __fadd_rn(acc[u].w, __fmul_rn(wv, ce.w));
+                    }
                 }
             }
         }
-        st4(cost + i * 32 + sub * 4, make_float4(-__fdiv_rn(acc.x, s_den), -__fdiv_rn(acc.y, s_den), -__fdiv_rn(acc.z, s_den),
-                                                 -__fdiv_rn(acc.w, s_den)));
+#pragma unroll
+        for (int u = 0; u < AGS_PX; ++u) {
+            const size_t i = i0 + u * stride;
+            if (i < total)
+                st4(cost + i * 32 + sub * 4, make_float4(-__fdiv_rn(acc[u].x, s_den), -__fdiv_rn(acc[u].y, s_den),
+                                                         -__fdiv_rn(acc[u].z, s_den), -__fdiv_rn(acc[u].w, s_den)));
+        }
     }
 }
 
