@@ -59,7 +59,8 @@ struct StemArgs {
     int align_corners;
     float* t0;
     double* stats;
-    float* costv;               // optional [K][S][P][32]: (warp-ref)^2 of the tile's interior pixels for a gather-free pass D
+    float* costv;               // optional [K][S][P][32] (warp-ref)^2: written for the tile's interior pixels (mode 1) so pass D
+    int costv_mode;             //   need not gather again, or READ instead of gathering (mode 2: aarmvs_warp_cost wrote it)
     unsigned long long* prof;   // debug: clock64 stamps of group 0 of CTA 0, [64 fills][8]
     int dbg;                    // debug ablation flags (aarmvs_debug_flags): 1 skip gather loads, 2 skip recipes, 4 skip MMA
 };
@@ -156,8 +157,8 @@ __global__ void __launch_bounds__(N_THREADS, 1) cost_stem_tc_kernel(const __grid
             const bool pf = a.prof && blockIdx.x == 0 && g == 0 && lt == 0 && it / G < 64;
             unsigned long long* pp = a.prof + (it / G) * 8;
             if (pf) pp[0] = clock64();
-            // ---- 1. gather recipes
-            for (int px = lt; px < NPX; px += GROUP_THREADS) {
+            // ---- 1. gather recipes (not needed when (warp-ref)^2 is streamed from costv)
+            for (int px = lt; px < NPX && a.costv_mode != 2; px += GROUP_THREADS) {
                 const int r = px / HC, cc = px - r * HC;
                 const int y = ty * TR - 1 + r, x = tx * TCOL - 1 + cc;
                 TapRec rec;
@@ -182,6 +183,34 @@ __global__ void __launch_bounds__(N_THREADS, 1) cost_stem_tc_kernel(const __grid
             // ---- 2. gather, (warp - ref)^2, split, stage
             const float* sv = a.src + (size_t)v * a.view_stride;
             float* costv_slot = a.costv ? a.costv + ((size_t)(k * a.S + v) * P) * 32 : nullptr;
+            if (a.costv_mode == 2) {
+                // stream mode: stage the halo tile straight from costv (coalesced 128-byte lines, no gather, no recipes)
+#pragma unroll 1
+                for (int jb = 0; jb < ITEMS; jb += 4) {
+                    float4 cvv[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int i = lt + (jb + j) * GROUP_THREADS;
+                        const int px = min(i, NPX * 8 - 1) >> 3, c4 = i & 7;
+                        const int r = px / HC, cc = px - r * HC;
+                        const int y = ty * TR - 1 + r, x = tx * TCOL - 1 + cc;
+                        cvv[j] = (i < NPX * 8 && y >= 0 && y < a.H && x >= 0 && x < a.W)
+                                     ? ldg4(costv_slot + ((size_t)y * a.W + x) * 32 + c4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int i = lt + (jb + j) * GROUP_THREADS;
+                        const int px = i >> 3, c4 = i & 7;
+                        uint2 hi, lo;
+                        tc::split4_f16(cvv[j], hi, lo);
+                        if (i < NPX * 8) {
+                            const size_t off = ((size_t)(c4 >> 1) * AROWS + px) * 16 + (c4 & 1) * 8;
+                            *reinterpret_cast<uint2*>(stage + off) = hi;
+                            *reinterpret_cast<uint2*>(stage + A_PLANE + off) = lo;
+                        }
+                    }
+                }
+            } else
 #pragma unroll 1
             for (int jb = 0; jb < ITEMS; jb += NB) {
                 float4 ta[NB], tb[NB], tcn[NB], td[NB], rv[NB], wq[NB];
@@ -216,7 +245,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) cost_stem_tc_kernel(const __grid
                     const float dx = gx - rv[j].x, dy = gy - rv[j].y, dz = gz - rv[j].z, dw = gw - rv[j].w;
                     const bool in = roff[j] >= 0;
                     const float4 cv = make_float4(in ? dx * dx : 0.f, in ? dy * dy : 0.f, in ? dz * dz : 0.f, in ? dw * dw : 0.f);
-                    if (a.costv && in && interior[j] && iraw < NPX * 8)          // interior pixel of this tile, inside the image
+                    if (a.costv_mode == 1 && in && interior[j] && iraw < NPX * 8)          // interior pixel of this tile, inside the image
                         st4(costv_slot + roff[j] + c4 * 4, cv);
                     uint2 hi, lo;
                     tc::split4_f16(cv, hi, lo);
@@ -305,8 +334,10 @@ extern "C" void aarmvs_debug_stem_profile_buffer(void* buf) { g_stem_prof = (uns
 extern "C" int aarmvs_cost_stem_tc(const float* ref, const float* src, size_t view_stride, int H, int W, int S,
                                    const float* cams, const void* stem_w_f16, const float* stem_b_host,
                                    const float* depth_values, int d_host, const int* d_dev, int planes, int align_corners,
-                                   float* t0, double* stats, float* costv_out, void* stream) {
-    AARMVS_CHECK_ARG(ref && src && t0 && stats && stem_w_f16 && stem_b_host && depth_values && cams && H > 0 && W > 0);
+                                   float* t0, double* stats, float* costv, int costv_mode, void* stream) {
+    AARMVS_CHECK_ARG(t0 && stats && stem_w_f16 && stem_b_host && depth_values && H > 0 && W > 0);
+    AARMVS_CHECK_ARG(costv_mode >= 0 && costv_mode <= 2 && (costv_mode == 0 || costv));
+    AARMVS_CHECK_ARG(costv_mode == 2 || (ref && src && cams));
     AARMVS_CHECK_ARG(S >= 1 && S <= AARMVS_MAX_SRC && planes >= 1 && planes <= AARMVS_MAX_PLANES);
     StemArgs a = {};
     a.K = planes;
@@ -315,7 +346,7 @@ extern "C" int aarmvs_cost_stem_tc(const float* ref, const float* src, size_t vi
     for (int i = 0; i < 4; ++i) a.bias[i] = stem_b_host[i];
     a.depth_values = depth_values; a.d_host = d_host; a.d_dev = d_dev; a.align_corners = align_corners; a.t0 = t0;
     a.stats = stats;
-    a.costv = costv_out;
+    a.costv = costv; a.costv_mode = costv_mode;
     a.dbg = g_dbg;
     a.prof = g_stem_prof;
     static bool attr_set = false;

@@ -334,6 +334,70 @@ aggregate_kernel(const float* __restrict__ ref, const float* __restrict__ src, s
     }
 }
 
+// ------------------------------------------------------------------------------------------------ pass A1: warp cost
+// costv[k][v][p][c] = (warp_v(p; depth k)[c] - ref(p)[c])^2 for every pixel, view and plane of the batch, written once;
+// the omega stem conv (cost_stem_tc_kernel in stream mode) and pass D then read it back as plain streams, so the gather --
+// the expensive, L1-bound part of the plane sweep -- runs once per pixel instead of 2.4 times (halo + second pass).
+__global__ void __launch_bounds__(256, 4)
+warp_cost_kernel(const float* __restrict__ ref, const float* __restrict__ src, size_t view_stride, int H, int W, int S, int K,
+                 const float* __restrict__ cams, const float* __restrict__ depth_values, int d_host,
+                 const int* __restrict__ d_dev, int align_corners, float* __restrict__ costv) {
+    __shared__ float scam[AARMVS_MAX_SRC * 12];
+    for (int i = threadIdx.x; i < S * 12; i += blockDim.x) scam[i] = cams[i];
+    __syncthreads();
+    const size_t P = (size_t)H * W;
+    const int sub = threadIdx.x & 7, grp = threadIdx.x >> 3;
+    const float* depths = depth_values + plane_index(d_host, d_dev);
+    const int tiles_x = (W + AG_TW - 1) / AG_TW, tiles_y = (H + AG_TH - 1) / AG_TH;
+    for (int tile = blockIdx.x; tile < tiles_x * tiles_y; tile += gridDim.x) {
+        const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+#pragma unroll 1
+        for (int j = 0; j < 4; ++j) {
+            const int pl = j * 32 + grp;
+            const int y = ty * AG_TH + pl / AG_TW, x = tx * AG_TW + pl % AG_TW;
+            const bool valid = y < H && x < W;
+            const size_t p = valid ? (size_t)y * W + x : 0;
+            const float4 rv = ldg4(ref + p * 32 + sub * 4);
+            for (int k = 0; k < K; ++k) {          // planes innermost: plane k+1 touches the lines just fetched for plane k
+                const float depth = depths[k];
+                for (int v0 = 0; v0 < S; v0 += 8) {
+                    const int mv = v0 + sub;       // lane j of the pixel's 8-lane group evaluates view v0 + j's tap set
+                    Taps tm;
+                    tm.o_nw = tm.o_ne = tm.o_sw = tm.o_se = -1;
+                    tm.w_nw = tm.w_ne = tm.w_sw = tm.w_se = 0.f;
+                    if (mv < S && valid) {
+                        float ix, iy;
+                        sweep_position(scam + mv * 12, (float)x, (float)y, depth, W, H, align_corners != 0, ix, iy);
+                        tm = make_taps(ix, iy, W, H);
+                    }
+                    const int nv = min(8, S - v0);
+                    for (int e = 0; e < nv; ++e) {
+                        const int o0 = __shfl_sync(0xffffffffu, tm.o_nw, e, 8), o1 = __shfl_sync(0xffffffffu, tm.o_ne, e, 8);
+                        const int o2 = __shfl_sync(0xffffffffu, tm.o_sw, e, 8), o3 = __shfl_sync(0xffffffffu, tm.o_se, e, 8);
+                        float w0 = __shfl_sync(0xffffffffu, tm.w_nw, e, 8), w1 = __shfl_sync(0xffffffffu, tm.w_ne, e, 8);
+                        float w2 = __shfl_sync(0xffffffffu, tm.w_sw, e, 8), w3 = __shfl_sync(0xffffffffu, tm.w_se, e, 8);
+                        if (o0 < 0) w0 = 0.f;
+                        if (o1 < 0) w1 = 0.f;
+                        if (o2 < 0) w2 = 0.f;
+                        if (o3 < 0) w3 = 0.f;
+                        const float* sv = src + (size_t)(v0 + e) * view_stride + sub * 4;
+                        const float4 ta = ldg4(sv + (size_t)max(o0, 0) * 32), tb = ldg4(sv + (size_t)max(o1, 0) * 32);
+                        const float4 tcn = ldg4(sv + (size_t)max(o2, 0) * 32), td = ldg4(sv + (size_t)max(o3, 0) * 32);
+                        const float gx = __fmaf_rn(td.x, w3, __fmaf_rn(tcn.x, w2, __fmaf_rn(tb.x, w1, __fmul_rn(ta.x, w0))));
+                        const float gy = __fmaf_rn(td.y, w3, __fmaf_rn(tcn.y, w2, __fmaf_rn(tb.y, w1, __fmul_rn(ta.y, w0))));
+                        const float gz = __fmaf_rn(td.z, w3, __fmaf_rn(tcn.z, w2, __fmaf_rn(tb.z, w1, __fmul_rn(ta.z, w0))));
+                        const float gw = __fmaf_rn(td.w, w3, __fmaf_rn(tcn.w, w2, __fmaf_rn(tb.w, w1, __fmul_rn(ta.w, w0))));
+                        const float dx = gx - rv.x, dy = gy - rv.y, dz = gz - rv.z, dw = gw - rv.w;
+                        if (valid)
+                            st4(costv + (((size_t)k * S + v0 + e) * P + p) * 32 + sub * 4,
+                                make_float4(__fmul_rn(dx, dx), __fmul_rn(dy, dy), __fmul_rn(dz, dz), __fmul_rn(dw, dw)));
+                    }
+                }
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ pass D, streamed
 // Same result as aggregate_kernel, but (warp - ref)^2 is read back from pass A's costv [K][S][P][32] instead of being
 // gathered a second time: a pure HBM stream (S * 128 + S * 16 B read, 128 B written per pixel and plane).
@@ -458,6 +522,18 @@ extern "C" int aarmvs_cost_stem(const float* ref, const float* src, size_t view_
     dim3 grid((W + TA_W - 1) / TA_W, (H + TA_H - 1) / TA_H, planes);
     cost_stem_kernel<<<grid, TA_THREADS, smem, (cudaStream_t)stream>>>(ref, src, view_stride, H, W, S, cams, sp, depth_values,
                                                                       d_host, d_dev, align_corners, t0, stats);
+    AARMVS_LAUNCH_RESULT();
+}
+
+extern "C" int aarmvs_warp_cost(const float* ref, const float* src, size_t view_stride, int H, int W, int S, const float* cams,
+                                const float* depth_values, int d_host, const int* d_dev, int planes, int align_corners,
+                                float* costv, void* stream) {
+    AARMVS_CHECK_ARG(ref && src && cams && depth_values && costv && H > 0 && W > 0);
+    AARMVS_CHECK_ARG(S >= 1 && S <= AARMVS_MAX_SRC && planes >= 1 && planes <= AARMVS_MAX_PLANES);
+    const int ntiles = ((W + AG_TW - 1) / AG_TW) * ((H + AG_TH - 1) / AG_TH);
+    const int blocks = ntiles < 148 * 4 ? ntiles : 148 * 4;
+    warp_cost_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(ref, src, view_stride, H, W, S, planes, cams, depth_values, d_host,
+                                                               d_dev, align_corners, costv);
     AARMVS_LAUNCH_RESULT();
 }
 

@@ -43,11 +43,14 @@ def _src_array(*srcs):
 class Engine:
     """Runs EMVSNet.forward's arithmetic for one model instance (weights are re-packed when they change)."""
 
-    def __init__(self, module, align_corners=False, use_graph=True, cell_math="tc", plane_batch=8, keep_costv=True):
+    def __init__(self, module, align_corners=False, use_graph=True, cell_math="tc", plane_batch=8, keep_costv=True, split_gather=False):
         if cell_math not in ("tc", "fma"):
             raise ValueError("cell_math must be 'tc' (tcgen05, split-fp16 operands) or 'fma' (fp32 CUDA cores)")
         self.cell_math = cell_math
         self.keep_costv = keep_costv
+        # split_gather: gather once in aarmvs_warp_cost, then stream costv into the stem conv as well (measured slower than
+        # the fused pass A at cfg2: 1.25 vs 1.12 ms/plane, the stem kernel's staging/epilogue skeleton dominates either way)
+        self.split_gather = split_gather
         if not 1 <= plane_batch <= 16:
             raise ValueError("plane_batch must be in 1..16")
         self.plane_batch = plane_batch            # planes per launch of passes A-D (L1/L2 reuse of the source features)
@@ -204,11 +207,19 @@ class Engine:
                    "aarmvs_feat_assemble")
 
     def cost_stem(self, ref, src, view_stride, H, W, S, cams, w, depths, d_host, dptr, planes, t0, sums, stream, costv=None):
-        """Pass A (gather, (warp - ref)^2, omega stem conv) on the tensor cores ('tc') or the fp32 FMA pipe ('fma')."""
+        """Pass A (gather, (warp - ref)^2, omega stem conv) on the tensor cores ('tc') or the fp32 FMA pipe ('fma').
+        With costv (tc only): the gather runs once in aarmvs_warp_cost and the stem conv streams its result."""
         ac = int(self.align_corners)
         if self.cell_math == "tc":
+            if costv is not None and self.split_gather:
+                capi.check(self.lib.aarmvs_warp_cost(ref, src, view_stride, H, W, S, cams, depths, d_host, dptr, planes, ac, costv,
+                                                     stream), "aarmvs_warp_cost")
+                mode = 2
+            else:
+                mode = 1 if costv is not None else 0
             capi.check(self.lib.aarmvs_cost_stem_tc(ref, src, view_stride, H, W, S, cams, _ptr(w["stem.wtc"]), w["stem.b_host"],
-                                                    depths, d_host, dptr, planes, ac, t0, sums, costv, stream), "aarmvs_cost_stem_tc")
+                                                    depths, d_host, dptr, planes, ac, t0, sums, costv, mode, stream),
+                       "aarmvs_cost_stem_tc")
         else:
             capi.check(self.lib.aarmvs_cost_stem(ref, src, view_stride, H, W, S, cams, w["stem.w_host"], w["stem.b_host"],
                                                  depths, d_host, dptr, planes, ac, t0, sums, stream), "aarmvs_cost_stem")

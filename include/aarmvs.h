@@ -101,11 +101,19 @@ int aarmvs_cost_stem(const float* ref, const float* src, size_t view_stride, int
  * split-fp16 operands, fp32 accumulation in TMEM).  Arguments as aarmvs_cost_stem except
  * stem_w_f16: DEVICE [2 planes hi,lo][4 chunks of 8 input channels][48 columns][8] fp16, column = tap * 4 + output
  * channel (36 used): the conv runs as one [pixels] x [9 taps * 4] GEMM + a shifted 9-tap sum in the epilogue.
- * costv_out: optional [planes][S][H*W][32] store of (warp - ref)^2 (fp32) that lets aarmvs_aggregate skip its gather. */
+ * costv [planes][S][H*W][32] fp32 = (warp - ref)^2; costv_mode 0: unused; 1: WRITTEN here (interior pixels of each tile)
+ * so that aarmvs_aggregate can skip its gather; 2: READ here instead of gathering (aarmvs_warp_cost wrote it; ref, src and
+ * cams are then unused) -- the gather then runs exactly once per pixel, view and plane. */
 int aarmvs_cost_stem_tc(const float* ref, const float* src, size_t view_stride, int H, int W, int S, const float* cams,
                         const void* stem_w_f16, const float* stem_b_host, const float* depth_values, int d_host,
-                        const int* d_dev, int planes, int align_corners, float* t0, double* stats, float* costv_out,
-                        void* stream);
+                        const int* d_dev, int planes, int align_corners, float* t0, double* stats, float* costv,
+                        int costv_mode, void* stream);
+
+/* Pass A1 (used with costv_mode 2): costv[k][v][p][:] = (warp_v(p) - ref(p))^2 for the `planes` planes starting at d:
+ * homo_warping_depthwise (models/module.py:6-38) + the squared difference (models/drmvsnet.py:311), nothing else. */
+int aarmvs_warp_cost(const float* ref, const float* src, size_t view_stride, int H, int W, int S, const float* cams,
+                     const float* depth_values, int d_host, const int* d_dev, int planes, int align_corners, float* costv,
+                     void* stream);
 
 /* Pass B (stage 2) / pass C (stage 3): GroupNorm-2 / GroupNorm-3 sums of the omega residual block
  * (models/module.py:256-258) recomputed point-wise from t0.  tail_host: aarmvs_omega_tail_floats() floats. */
