@@ -89,7 +89,8 @@ __global__ void __launch_bounds__(N_THREADS, 1) cost_stem_tc_kernel(const __grid
 
     for (int i = tid; i < B_BYTES / 16; i += N_THREADS)
         reinterpret_cast<uint4*>(sB)[i] = __ldg(reinterpret_cast<const uint4*>(a.weight) + i);
-    for (int i = tid; i < a.S * 12; i += N_THREADS) scam[i] = a.cams[i];
+    if (a.costv_mode != 2)          // stream mode never evaluates a homography
+        for (int i = tid; i < a.S * 12; i += N_THREADS) scam[i] = a.cams[i];
     for (int i = tid; i < G * 4 * AARMVS_MAX_PLANES * AARMVS_MAX_SRC; i += N_THREADS) (&sstat[0][0])[i] = make_float2(0.f, 0.f);
     if (tid == 0) {
         for (int s = 0; s < G; ++s) { tc::mbar_init(&full_a[s], GROUP_THREADS); tc::mbar_init(&done_a[s], 1); }
@@ -186,10 +187,11 @@ __global__ void __launch_bounds__(N_THREADS, 1) cost_stem_tc_kernel(const __grid
             if (a.costv_mode == 2) {
                 // stream mode: stage the halo tile straight from costv (coalesced 128-byte lines, no gather, no recipes)
 #pragma unroll 1
-                for (int jb = 0; jb < ITEMS; jb += 4) {
-                    float4 cvv[4];
+                constexpr int SB = 6;                 // loads in flight per thread: HBM latency, not bandwidth, bounds this loop
+                for (int jb = 0; jb < ITEMS; jb += SB) {
+                    float4 cvv[SB];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
+                    for (int j = 0; j < SB; ++j) {
                         const int i = lt + (jb + j) * GROUP_THREADS;
                         const int px = min(i, NPX * 8 - 1) >> 3, c4 = i & 7;
                         const int r = px / HC, cc = px - r * HC;
@@ -198,7 +200,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) cost_stem_tc_kernel(const __grid
                                      ? ldg4(costv_slot + ((size_t)y * a.W + x) * 32 + c4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
                     }
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
+                    for (int j = 0; j < SB; ++j) {
                         const int i = lt + (jb + j) * GROUP_THREADS;
                         const int px = i >> 3, c4 = i & 7;
                         uint2 hi, lo;

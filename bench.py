@@ -268,10 +268,10 @@ def run_ours(args):
         S = N - 1
         # the slowest kernel of the plane chain against ITS bound (algorithmic bytes / FLOPs as listed in DESIGN.md §3)
         kernels = {
-            "cost_stem": ("cost_stem_tc_kernel (pass A: gather + (warp-ref)^2 + omega stem conv on tcgen05)", "hbm",
-                          128 * P * (S + 1) + 16 * P * S),
-            "aggregate": ("aggregate_kernel (pass D: re-gather + omega tail + weighted sum)", "hbm",
-                          128 * P * (S + 1) + 16 * P * S + 128 * P),
+            "cost_stem": ("cost_stem_tc_kernel (pass A: gather + (warp-ref)^2 + omega stem conv on tcgen05, stores costv)", "hbm",
+                          128 * P * (S + 1) + 16 * P * S + 128 * P * S),
+            "aggregate": ("aggregate_stream_kernel (pass D: omega tail + weighted sum over the stored (warp-ref)^2)", "hbm",
+                          (128 + 16) * P * S + 128 * P),
             "omega_stats": ("omega_stats_kernel<2>+<3> (passes B, C)", "hbm", 2 * 16 * P * S),
             "head_wta": ("head_wta_kernel", "hbm", 44 * P),
         }
@@ -283,12 +283,13 @@ def run_ours(args):
         batched = top in ("cost_stem", "omega_stats", "aggregate")       # one launch covers plane_batch planes
         per_launch = eng.plane_batch if batched else 1
         # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu captures (cfg2 only)
-        traffic_cfg2 = {"cost_stem": 2.819e9, "aggregate": 4.991e9, "cell0": 0.693e9, "cell1": 0.217e9, "cell2": 0.046e9,
-                        "cell3": 0.147e9, "cell4": 0.464e9, "head_wta": 0.083e9}      # profiles/r01d_*, r01e_*
+        traffic_cfg2 = {"cost_stem": 14.818e9, "aggregate": 15.026e9, "omega_stats": 2.92e9, "cell0": 0.693e9, "cell1": 0.217e9,
+                        "cell2": 0.046e9, "cell3": 0.147e9, "cell4": 0.464e9, "head_wta": 0.083e9}   # profiles/r01f_*
         roofline = {"kernel": kname, "bound": bound, "planes_per_launch": per_launch, "ms_per_launch": st[top] * per_launch,
                     "algorithmic_work_per_launch": work * per_launch,
                     "traffic": traffic_cfg2.get(top) if args.workload == "cfg2" else None,
-                    "traffic_source": "ncu --set full, profiles/r01d_stem_aggregate.txt / r01e_plane_kernels.txt"}
+                    "traffic_source": "ncu --set full, profiles/r01f_passes_AD.txt / r01f_recurrence.txt (pass A includes the 11.6 GB "
+                                      "costv store per 8-plane launch that replaces pass D's second gather)"}
         if bound == "hbm":
             roofline.update({"achieved": work / (st[top] * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
                              "peak_source": pk["source"] + ", STREAM-style copy"})

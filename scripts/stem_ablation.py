@@ -64,3 +64,28 @@ for _ in range(3): run_ds()
 e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / 3 / K
 print(f"aggregate (streamed)     {ms:.3f} ms/plane  = {(S * 144 + 128) * P / ms / 1e6:.0f} GB/s")
+
+# ---- split variant: A1 (warp_cost) and A2 (stem conv streaming costv) separately
+def timeit(fn, name, reps=3):
+    fn(); torch.cuda.synchronize()
+    e0.record()
+    for _ in range(reps): fn()
+    e1.record(); torch.cuda.synchronize()
+    print(f"{name:32s} {e0.elapsed_time(e1) / reps / K:.3f} ms/plane")
+ac = 0
+def run_a1():
+    capi.check(lib.aarmvs_warp_cost(_ptr(ws["feat"]), _ptr(ws["feat"], P * 32), P * 32, H, W, S, _ptr(ws["cams"]), _ptr(ws["depths"]), 100, None, K, ac,
+                                    _ptr(cv), st), "a1")
+def run_a2():
+    capi.check(lib.aarmvs_cost_stem_tc(None, None, 0, H, W, S, None, _ptr(w["stem.wtc"]), w["stem.b_host"], _ptr(ws["depths"]), 100, None, K, ac,
+                                       _ptr(ws["t0"]), _ptr(ws["psums"]), _ptr(cv), 2, st), "a2")
+timeit(run_a1, "A1 warp_cost (gather + store)")
+timeit(run_a2, "A2 stem conv streaming costv")
+lib.aarmvs_debug_stem_profile_buffer(ctypes.c_void_p(buf.data_ptr()))
+run_a2(); torch.cuda.synchronize()
+lib.aarmvs_debug_stem_profile_buffer(None)
+t = buf.view(64, 8).cpu()[8:56]
+t = (t - t[0, 0]).double()
+print("A2 group-0 cycles per fill: recipes+bar %.0f | load+stage %.0f | fence+arrive %.0f | wait MMA %.0f | z rows+bar %.0f | sum+store+stats %.0f | fill period %.0f" % (
+    (t[:, 1] - t[:, 0]).mean(), (t[:, 2] - t[:, 1]).mean(), (t[:, 3] - t[:, 2]).mean(), (t[:, 4] - t[:, 3]).mean(), (t[:, 5] - t[:, 4]).mean(),
+    (t[:, 6] - t[:, 5]).mean(), (t[1:, 0] - t[:-1, 0]).mean()))
