@@ -318,11 +318,12 @@ class Engine:
         if device.type != "cuda":
             raise RuntimeError("aarmvsnet_b200 has no CPU path: inputs must live on a CUDA device")
         _, H, W = img.shape
-        w = self._weights(device)
-        ws = self._workspace(H, W, 2, 1, device, False)
-        stream = ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
-        self.feature_map(img.to(torch.float32).contiguous(), ws["feat"][0], ws, w, stream)
-        return ws["feat"][0].clone()
+        with torch.cuda.device(device):
+            w = self._weights(device)
+            ws = self._workspace(H, W, 2, 1, device, False)
+            stream = ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+            self.feature_map(img.to(torch.float32).contiguous(), ws["feat"][0], ws, w, stream)
+            return ws["feat"][0].clone()
 
     def depth_map(self, imgs, proj_matrices, depth_values, keep_cost=False, features=None):
         """imgs [N,3,H,W], proj_matrices [N,4,4], depth_values [D] -> dict of [H,W] maps (views of the workspace).
@@ -330,8 +331,15 @@ class Engine:
         device = imgs.device
         if device.type != "cuda":
             raise RuntimeError("aarmvsnet_b200 has no CPU path: inputs must live on a CUDA device")
+        with torch.cuda.device(device):          # the C ABI launches on the calling thread's current device
+            return self._depth_map(imgs, proj_matrices, depth_values, keep_cost, features)
+
+    def _depth_map(self, imgs, proj_matrices, depth_values, keep_cost, features):
+        device = imgs.device
         N, _, H, W = imgs.shape
         D = depth_values.shape[0]
+        if D < 1:
+            raise RuntimeError("depth_values must hold at least one plane")
         w = self._weights(device)
         ws = self._workspace(H, W, N, D, device, keep_cost)
         stream = ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)

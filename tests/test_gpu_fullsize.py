@@ -36,6 +36,28 @@ def test_mid_size_against_oracle(smooth):
     torch.testing.assert_close(out["photometric_confidence"].cpu()[same], ref["photometric_confidence"][same], rtol=1e-3, atol=1e-3)
 
 
+def test_cfg1_crop_against_oracle():
+    """BASELINE cfg1 (640x512, N=3, D=48, inverse depths) on a 320x256 crop-sized sample: the oracle takes a few seconds on
+    the box's host cores.  Reports the plane-mismatch fraction next to the reference's own fp32-vs-fp64 floor (4.9e-5)."""
+    from aarmvsnet_b200 import synth
+    from oracle import aarmvs_oracle as orc
+    s = synth.make_sample(256, 320, 3, 48, seed=33, depth_mode="inverse")
+    out = _run(_model(256, 320), s)
+    ref = orc.forward_test(load_weights("model_dtu_v2.ckpt"), s["imgs"], s["proj_matrices"], s["depth_values"], return_index=True)
+    idx = out["index"].cpu().long()
+    same = idx == ref["index"]
+    mismatch = 1.0 - same.float().mean().item()
+    print(f"cfg1 crop: plane mismatch fraction {mismatch:.2e} (reference fp32 vs fp64: 4.9e-05), max index distance {(idx - ref['index']).abs().max().item()}")
+    assert mismatch <= 1e-3
+    interval = (s["depth_values"][0, 1:] - s["depth_values"][0, :-1]).abs()
+    rng = (s["depth_values"].max() - s["depth_values"].min()).item()
+    err = (out["depth"].cpu() - ref["depth"]).abs()
+    assert (err[same] == 0).all()
+    assert (err <= 0.5 * interval.min()).float().mean().item() >= 0.999
+    print(f"cfg1 crop: max |depth error| / depth range = {err.max().item() / rng:.2e} on {int((~same).sum())} differing pixels of {same.numel()}")
+    torch.testing.assert_close(out["photometric_confidence"].cpu()[same], ref["photometric_confidence"][same], rtol=1e-3, atol=1e-3)
+
+
 def test_tensor_core_and_fma_cells_agree():
     """The split-fp16 tcgen05 path against the fp32 CUDA-core path on the same inputs (no CPU needed): 320x256, D=24."""
     from aarmvsnet_b200 import synth
