@@ -268,8 +268,9 @@ def run_ours(args):
         S = N - 1
         # the slowest kernel of the plane chain against ITS bound (algorithmic bytes / FLOPs as listed in DESIGN.md §3)
         kernels = {
+            # pass A: the (warp-ref)^2 store for pass D (128*P*S, see `traffic`) is a design choice, not algorithmic work
             "cost_stem": ("cost_stem_tc_kernel (pass A: gather + (warp-ref)^2 + omega stem conv on tcgen05, stores costv)", "hbm",
-                          128 * P * (S + 1) + 16 * P * S + 128 * P * S),
+                          128 * P * (S + 1) + 16 * P * S),
             "aggregate": ("aggregate_stream_kernel (pass D: omega tail + weighted sum over the stored (warp-ref)^2)", "hbm",
                           (128 + 16) * P * S + 128 * P),
             "omega_stats": ("omega_stats_kernel<2>+<3> (passes B, C)", "hbm", 2 * 16 * P * S),
