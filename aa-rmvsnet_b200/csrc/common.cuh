@@ -17,6 +17,18 @@ struct Cams {                          // per source view: rot (row-major 3x3) t
     float m[AARMVS_MAX_SRC][12];
 };
 
+// Opt-in to > 48 KB of dynamic shared memory once per (kernel, device); `mask` is the call site's static bit set.
+template <class K>
+static inline cudaError_t ensure_dyn_smem(K kern, int bytes, unsigned long long& mask) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 64 && ((mask >> dev) & 1ull)) return cudaSuccess;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess && dev < 64) mask |= 1ull << dev;
+    return e;
+}
+
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }

@@ -352,12 +352,8 @@ template <int KSTEPS, int NG>
 int launch_tc(const TcArgs& a, cudaStream_t stream) {
     using C = TcCfg<KSTEPS, NG>;
     auto kern = convlstm_tc_kernel<KSTEPS, NG>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
-        if (e != cudaSuccess) return (int)e;
-        attr_set = true;
-    }
+    static unsigned long long smem_ok = 0;
+    if (cudaError_t e = ensure_dyn_smem(kern, C::SMEM, smem_ok)) return (int)e;
     const int ntiles = ((a.W + TCOL - 1) / TCOL) * ((a.H + TR - 1) / TR);
     const int sms = aarmvs_sm_count();
     if (sms <= 0) return AARMVS_ERR_ARG;

@@ -351,12 +351,8 @@ extern "C" int aarmvs_cost_stem_tc(const float* ref, const float* src, size_t vi
     a.costv = costv; a.costv_mode = costv_mode;
     a.dbg = g_dbg;
     a.prof = g_stem_prof;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(cost_stem_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
-        if (e != cudaSuccess) return (int)e;
-        attr_set = true;
-    }
+    static unsigned long long smem_ok = 0;
+    if (cudaError_t e = ensure_dyn_smem(cost_stem_tc_kernel, SMEM, smem_ok)) return (int)e;
     const int ntiles = ((W + TCOL - 1) / TCOL) * ((H + TR - 1) / TR);
     const int sms = aarmvs_sm_count();
     if (sms <= 0) return AARMVS_ERR_ARG;

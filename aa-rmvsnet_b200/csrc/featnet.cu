@@ -141,13 +141,9 @@ extern "C" int aarmvs_deform_conv(const aarmvs_conv_src* x, int H, int W, const 
     a.x = x->ptr; a.x_stats = x->gn_sums; a.x_gamma = x->gn_weight; a.x_beta = x->gn_bias; a.x_count = x->gn_count;
     a.x_groups = x->gn_groups; a.x_mode = x->mode; a.H = H; a.W = W; a.offmask = offmask; a.weight = weight; a.bias = bias;
     a.out = out; a.out_stats = out_gn_sums;
-    static bool attr_set = false;
     const int smem = 9 * 1024 * sizeof(float);
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(deform_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return (int)e;
-        attr_set = true;
-    }
+    static unsigned long long smem_ok = 0;
+    if (cudaError_t e = ensure_dyn_smem(deform_conv_kernel, smem, smem_ok)) return (int)e;
     const int sms = aarmvs_sm_count();
     if (sms <= 0) return AARMVS_ERR_ARG;
     int blocks = (H * W + 127) / 128;

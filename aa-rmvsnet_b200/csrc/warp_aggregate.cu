@@ -512,13 +512,9 @@ extern "C" int aarmvs_cost_stem(const float* ref, const float* src, size_t view_
     StemParams sp;
     for (int i = 0; i < 9 * 32 * 4; ++i) sp.w[i] = stem_w[i];
     for (int i = 0; i < 4; ++i) sp.b[i] = stem_b[i];
-    static bool attr_set = false;
     const int smem = TA_NPOS * 32 * sizeof(float);
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(cost_stem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return (int)e;
-        attr_set = true;
-    }
+    static unsigned long long smem_ok = 0;
+    if (cudaError_t e = ensure_dyn_smem(cost_stem_kernel, smem, smem_ok)) return (int)e;
     dim3 grid((W + TA_W - 1) / TA_W, (H + TA_H - 1) / TA_H, planes);
     cost_stem_kernel<<<grid, TA_THREADS, smem, (cudaStream_t)stream>>>(ref, src, view_stride, H, W, S, cams, sp, depth_values,
                                                                       d_host, d_dev, align_corners, t0, stats);
