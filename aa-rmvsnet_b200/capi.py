@@ -30,8 +30,19 @@ class ConvSrc(ctypes.Structure):
     ]
 
 
+class PlaneSrc(ctypes.Structure):
+    """struct aarmvs_plane_src (include/aarmvs.h): fp16 (hi, lo) operand planes [pp][2][channels/8][H][W][8]."""
+    _fields_ = [
+        ("planes", ctypes.c_void_p),
+        ("channels", ctypes.c_int),
+        ("pp", ctypes.c_int),
+        ("pp_phase", ctypes.c_int),
+    ]
+
+
 _P, _I, _SZ, _F = ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t, ctypes.c_float
 _SRCP = ctypes.POINTER(ConvSrc)
+_PLSP = ctypes.POINTER(PlaneSrc)
 
 # name -> (restype, argtypes); must list every symbol include/aarmvs.h declares (tests/test_capi_symbols.py)
 PROTOTYPES = {
@@ -47,9 +58,11 @@ PROTOTYPES = {
     "aarmvs_cost_stem_tc": (_I, [_P, _P, _SZ, _I, _I, _I, _P, _P, c_float_p, _P, _I, _P, _I, _I, _P, _P, _P, _I, _P]),
     "aarmvs_warp_cost": (_I, [_P, _P, _SZ, _I, _I, _I, _P, _P, _I, _P, _I, _I, _P, _P]),
     "aarmvs_omega_stats": (_I, [_I, _P, _I, _I, _I, _I, c_float_p, _P, _P]),
-    "aarmvs_aggregate": (_I, [_P, _P, _SZ, _I, _I, _I, _P, c_float_p, _P, _I, _P, _I, _I, _P, _P, _P, _P, _P, _P]),
+    "aarmvs_aggregate": (_I, [_P, _P, _SZ, _I, _I, _I, _P, c_float_p, _P, _I, _P, _I, _I, _P, _P, _P, _P, _P, _P, _P]),
+    "aarmvs_split_planes": (_I, [_SRCP, _I, _I, _P, _P]),
+    "aarmvs_cell_state_floats": (_SZ, [_I, _I, _I]),
     "aarmvs_convlstm_cell": (_I, [_SRCP, _I, _I, _I, _I, _I, _P, _P, _P, _P, _I, _P, _P]),
-    "aarmvs_convlstm_cell_tc": (_I, [_SRCP, _I, _I, _I, _I, _I, _P, _P, _P, _P, _I, _P, _P]),
+    "aarmvs_convlstm_cell_tc": (_I, [_PLSP, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _I, _P, _P]),
     "aarmvs_deconv2x": (_I, [_SRCP, _I, _I, c_float_p, c_float_p, _P, _P, _I, _P, _P]),
     "aarmvs_head_wta": (_I, [_SRCP, _I, _I, c_float_p, c_float_p, _P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
     "aarmvs_next_plane": (_I, [_P, _P, _I, _P]),
@@ -83,7 +96,7 @@ def load(build_if_missing=True):
         fn = getattr(lib, name)          # AttributeError here = ABI drift between the header and the library
         fn.restype = res
         fn.argtypes = args
-    if lib.aarmvs_version() != 2:
+    if lib.aarmvs_version() != 3:
         raise RuntimeError("libaarmvs_sm100.so: ABI version mismatch")
     _lib = lib
     return lib

@@ -277,7 +277,7 @@ static int sm_count() {
     return g_sm_count;
 }
 
-extern "C" int aarmvs_version(void) { return 2; }
+extern "C" int aarmvs_version(void) { return 3; }
 extern "C" int aarmvs_sm_count(void) { return sm_count(); }
 
 template <int CIN, int COUT, int KS, int STRIDE, int TCO, int TPX, int EPI>

@@ -1,0 +1,406 @@
+// ConvLSTM cell as a TMA-fed tcgen05 / TMEM implicit GEMM (models/module.py:76-92).
+//
+//   gates[128 px][4*CH] = sum over 9 taps, K = Cin:  A_tap[128 px][Cin] * W_tap[Cin][4*CH]
+//
+// Precision: the parity bar (same winning plane on >= 99.9 % of the pixels) rules out single-pass TF32/BF16 operands
+// (hard part 1), so every fp32 operand x travels as two fp16 values x ~= hi + lo
+// (|x - hi - lo| <= 2^-22 |x|) and each K=16 step issues kind::f16 MMAs with fp32 accumulation in TMEM:
+//   A_hi x [W_hi | W_lo]  (one instruction, N = 2*4CH)   +   A_lo x W_hi        (the dropped lo*lo term is <= 2^-22)
+// Useful FLOPs are counted once; the tensor pipe executes 3x as many.
+//
+// Operand planes.  Every tensor a cell reads lives in HBM ALREADY SPLIT, as "operand planes"
+//   [2 (hi, lo)][C/8 chunks][H][W][8 x fp16]
+// written by its producer (pass D for the cost, the cell epilogues for h and max-pool(h), aarmvs_split_planes for the
+// GroupNorm+ReLU'd deconvolution outputs).  One 16-byte element = 8 channels of one pixel = one row of a K-major
+// core matrix, so a TMA box of (10 pixels x 18 rows x chunks) lands in shared memory as exactly the un-swizzled
+// K-major operand [chunk][18 x 10 halo pixels][16 B] the MMA descriptors expect: no loader warps, no conversion, no
+// LSU traffic (the first version's per-pixel fp32 loads and on-the-fly split kept the L1 data pipe 81 % busy and
+// the tensor pipe 45 % busy).  TMA's out-of-bounds zero fill is the conv's zero padding.
+//
+// Tile: 16 rows x 8 columns of pixels = the 128 rows of the accumulator.  Row m = 8 g + i of the MMA is pixel
+// (row g, column i), so one 8-row core-matrix group is one tile row, and inside the staged halo tile
+// [18 rows][10 columns] the stride between groups is 10 pixels: a 3x3 tap (ky, kx) is just a different START ADDRESS
+// (ky * 10 + kx pixels further) into the same staged data -- no im2col copy, each input pixel is staged once per tile.
+// SBO = 10 * 16 B, LBO = 180 * 16 B (validated by aarmvs_tc_selftest).
+//
+// Warp roles (persistent CTA, one per SM): warps 0-7 epilogue (TMEM -> gates -> c, h), warp 8 TMEM allocation + the
+// single MMA-issuing thread, warp 9 the TMA producer.  NST operand stages (producer <-> MMA) and 2 TMEM accumulators
+// (MMA <-> epilogue), all hand-offs through mbarriers; tcgen05.commit releases operand stages and publishes
+// accumulators.  The cell state c is private to this kernel and kept in a tile-blocked layout
+// [tile][half][4-channel group][128 px][4] so that every access is a fully used 128-byte line.
+#include <cuda.h>
+#include "common.cuh"
+#include "tc_common.cuh"
+#include "../../include/aarmvs.h"
+
+namespace {
+
+constexpr int TR = 16, TCOL = 8, HR = TR + 2, HC = TCOL + 2, NPX = HR * HC;   // 180 staged pixels per tile
+constexpr int CHUNK_BYTES = NPX * 16;                                         // one 8-channel chunk of one fp16 plane
+constexpr int N_EPI_WARPS = 8, MMA_WARP = N_EPI_WARPS, TMA_WARP = MMA_WARP + 1;
+constexpr int N_THREADS = (N_EPI_WARPS + 2) * 32;                             // 320
+
+struct alignas(64) CellArgs {
+    CUtensorMap map[3];         // per source: (W*8 halfs, H, chunks, 2 = hi/lo, ping-pong halves), box (80, 18, chunks, 1, 1)
+    int nsrc;                   // sources incl. h_{d-1} (always the last one)
+    int chunks[3];              // 16-byte K chunks each source contributes
+    int pp_phase[3];            // < 0: single buffer; else the half to read is (d + pp_phase) & 1
+    int need_zero;              // K is padded beyond the sources' channels: the pad chunks of every stage must be zero
+    int H, W;
+    const __half* weight;       // [9 taps][KC8][2 (hi, lo)][NG][8] fp16
+    const float* bias;          // [NG], order [hidden channel][i,f,o,g]
+    __half* h_planes;           // [2 ping-pong][2][CH/8][H][W][8]: plane d writes half d & 1
+    float* c_blocked;           // [tiles][2 halves][CH/8][128][4]
+    float* h_f32;               // optional [2 ping-pong][H*W][CH] fp32 copy of h (deconvolution / head inputs, operator seam)
+    __half* pooled;             // optional [2][CH/8][H/2][W/2][8]: operand planes of max_pool2d(h, 2)
+    int d_host;
+    const int* d_dev;
+    unsigned long long* prof;   // debug: per-tile clock64 stamps of CTA 0 ([tile][12]), or null
+    int dbg;                    // debug ablation: 1 no TMA loads, 4 epilogue skips global I/O, 8 skip MMAs
+};
+
+template <int KSTEPS, int NG, int NST>
+struct Cfg {
+    static constexpr int KC8 = 2 * KSTEPS;                       // 16-byte K chunks (8 channels each)
+    static constexpr int A_PLANE = KC8 * CHUNK_BYTES;            // bytes of one fp16 plane (hi or lo) of one stage
+    static constexpr int A_STAGE = 2 * A_PLANE;
+    static constexpr int B_BYTES = 9 * KC8 * 2 * NG * 16;        // [tap][chunk][hi rows | lo rows][16 B]
+    static constexpr int SMEM = B_BYTES + NST * A_STAGE + 1024;
+    static constexpr int TMEM_COLS = 4 * NG;                     // two accumulators x (hi*hi + lo*hi | hi*lo) column blocks
+    static_assert(TMEM_COLS == 128 || TMEM_COLS == 256, "TMEM allocation must be a power of two >= 32");
+    static_assert(B_BYTES % 128 == 0 && A_PLANE % 128 == 0, "TMA destinations must be 128-byte aligned");
+    static_assert(SMEM <= 227 * 1024, "shared memory budget");
+};
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+template <int KSTEPS, int NG, int NST>
+__global__ void __launch_bounds__(N_THREADS, 1) convlstm_tma_kernel(const __grid_constant__ CellArgs a) {
+    using C = Cfg<KSTEPS, NG, NST>;
+    constexpr int CH = NG / 4, CHK = (CH + 7) / 8;
+    extern __shared__ __align__(1024) unsigned char smem[];
+    unsigned char* sB = smem;                                   // weights: [tap][kc8][hi rows | lo rows][16 B]
+    unsigned char* sA = smem + C::B_BYTES;                      // stages: [stage][hi|lo][kc8][px][16 B]
+    __shared__ uint64_t full_a[NST], empty_a[NST], tmem_full[2], tmem_empty[2], w_bar;
+    __shared__ uint32_t tmem_base_s;
+    __shared__ float s_bias[NG];
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int d = plane_index(a.d_host, a.d_dev);
+
+    // ---- one-time setup: barriers, TMEM, zeroed stages where no TMA will ever write (h_{-1} = 0 at plane 0,
+    //      module.py:94-96; K padding of cell 4)
+    if (d == 0 || a.need_zero)
+        for (int i = tid; i < NST * C::A_STAGE / 16; i += N_THREADS) reinterpret_cast<uint4*>(sA)[i] = make_uint4(0u, 0u, 0u, 0u);
+    if (tid < NG) s_bias[tid] = a.bias[tid];
+    if (tid == 0) {
+        for (int s = 0; s < NST; ++s) { tc::mbar_init(&full_a[s], 1); tc::mbar_init(&empty_a[s], 1); }
+        for (int b = 0; b < 2; ++b) { tc::mbar_init(&tmem_full[b], 1); tc::mbar_init(&tmem_empty[b], N_EPI_WARPS * 32); }
+        tc::mbar_init(&w_bar, 1);
+        tc::mbar_fence_init();
+    }
+    if (warp == MMA_WARP) tc::tmem_alloc<C::TMEM_COLS>(&tmem_base_s);
+    tc::fence_async_smem();                  // the zero fill went through the generic proxy
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+
+    const int tiles_x = (a.W + TCOL - 1) / TCOL, tiles_y = (a.H + TR - 1) / TR;
+    const int ntiles = tiles_x * tiles_y;
+
+    if (warp == TMA_WARP) {
+        // =========================================== TMA producer ===========================================
+        int cbase[3], sel[3];
+        const int nload = d == 0 ? a.nsrc - 1 : a.nsrc;            // plane 0: h_{-1} = 0, its chunks stay zero
+        uint32_t bytes = 0;
+        {
+            int cb = 0;
+            for (int s = 0; s < 3; ++s) {
+                cbase[s] = cb;
+                sel[s] = 0;
+                if (s < a.nsrc) {
+                    sel[s] = a.pp_phase[s] < 0 ? 0 : ((d + a.pp_phase[s]) & 1);
+                    if (s < nload) bytes += 2u * CHUNK_BYTES * a.chunks[s];
+                    cb += a.chunks[s];
+                }
+            }
+        }
+        if (lane == 0) {
+            for (int s = 0; s < a.nsrc; ++s) tc::tma_prefetch_desc(&a.map[s]);
+            tc::mbar_arrive_expect_tx(&w_bar, C::B_BYTES);
+            for (int off = 0; off < C::B_BYTES; off += 32768)
+                tc::bulk_load_1d(sB + off, reinterpret_cast<const unsigned char*>(a.weight) + off,
+                                 min(32768, C::B_BYTES - off), &w_bar);
+        }
+        int it = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+            const int st = it % NST;
+            const bool pf = a.prof && blockIdx.x == 0 && lane == 0 && it < 64;
+            if (lane == 0) {
+                if (pf) a.prof[it * 12 + 0] = clock64();
+                tc::mbar_wait(&empty_a[st], ((it / NST) & 1) ^ 1);
+                if (pf) a.prof[it * 12 + 1] = clock64();
+                const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+                const int y0 = ty * TR - 1, x0 = (tx * TCOL - 1) * 8;
+                unsigned char* stage = sA + st * C::A_STAGE;
+                if (a.dbg & 1) {
+                    tc::mbar_arrive(&full_a[st]);
+                } else {
+                    tc::mbar_arrive_expect_tx(&full_a[st], bytes);
+                    for (int s = 0; s < nload; ++s) {
+                        unsigned char* dst = stage + cbase[s] * CHUNK_BYTES;
+                        tc::tma_load_5d(dst, &a.map[s], &full_a[st], x0, y0, 0, 0, sel[s]);
+                        tc::tma_load_5d(dst + C::A_PLANE, &a.map[s], &full_a[st], x0, y0, 0, 1, sel[s]);
+                    }
+                }
+                if (pf) a.prof[it * 12 + 2] = a.prof[it * 12 + 3] = clock64();
+            }
+            __syncwarp();
+        }
+    } else if (warp == MMA_WARP) {
+        // =========================================== MMA issuer ===========================================
+        // The whole warp runs the loop (uniform control flow keeps the descriptor arithmetic on the uniform datapath);
+        // one elected lane issues.  81 / 54 MMAs per tile, fully unrolled: descriptor low words are base + immediate.
+        const bool leader = tc::elect_one();
+        const uint32_t idesc2 = tc::idesc_f16_f32(128, 2 * NG), idesc1 = tc::idesc_f16_f32(128, NG);
+        const uint32_t a_base = tc::smem_u32(sA), b_base = tc::smem_u32(sB);
+        constexpr uint32_t A_HI = tc::desc_hi(HC * 16), B_HI = tc::desc_hi(8 * 16);
+        const uint32_t b_lo = tc::desc_lo(b_base, 2 * NG * 16);       // [W_hi | W_lo] stacked along N: rows 0..NG-1 hi, NG..2NG-1 lo
+        tc::mbar_wait(&w_bar, 0);
+        int it = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+            const int st = it % NST, ab = it & 1;
+            const bool pf = a.prof && blockIdx.x == 0 && leader && it < 64;
+            if (pf) a.prof[it * 12 + 4] = clock64();
+            tc::mbar_wait(&full_a[st], (it / NST) & 1);
+            if (pf) a.prof[it * 12 + 5] = clock64();
+            tc::mbar_wait(&tmem_empty[ab], ((it >> 1) & 1) ^ 1);
+            tc::tc_fence_after();
+            if (pf) a.prof[it * 12 + 6] = clock64();
+            const uint32_t dst = tmem_base + ab * 2 * NG;
+            const uint32_t a_lo_hi = tc::desc_lo(a_base + st * C::A_STAGE, NPX * 16);
+            const uint32_t a_lo_lo = tc::desc_lo(a_base + st * C::A_STAGE + C::A_PLANE, NPX * 16);
+            if (leader) {
+                if (!(a.dbg & 8))
+#pragma unroll
+                for (int tap = 0; tap < 9; ++tap) {
+#pragma unroll
+                    for (int ks = 0; ks < KSTEPS; ++ks) {
+                        const uint32_t ak = (uint32_t)(((2 * ks) * NPX + (tap / 3) * HC + (tap % 3)) * 16) >> 4;
+                        // A_hi x [W_hi | W_lo] fills columns [0, NG) (hi*hi) and [NG, 2NG) (hi*lo) in ONE instruction with
+                        // N = 2 NG, A_lo x W_hi adds into [0, NG): two A-operand reads per K step instead of three
+                        const uint32_t bk = (uint32_t)((tap * C::KC8 + 2 * ks) * 2 * NG);
+                        tc::mma_f16_parts(dst, a_lo_hi + ak, A_HI, b_lo + bk, B_HI, idesc2, (tap | ks) != 0);
+                        tc::mma_f16_parts(dst, a_lo_lo + ak, A_HI, b_lo + bk, B_HI, idesc1, 1);
+                    }
+                }
+                tc::mma_commit(&empty_a[st]);          // operand stage free once these MMAs have read it
+                tc::mma_commit(&tmem_full[ab]);        // accumulator complete
+            }
+            if (pf) a.prof[it * 12 + 7] = clock64();
+            __syncwarp();
+        }
+    } else {
+        // =========================================== epilogue ===========================================
+        const int q = warp & 3, hf = warp >> 2;                  // TMEM lane quadrant, half of the gate columns
+        constexpr int NCOL = NG / 2, NHC = CH / 2, NJ4 = NHC / 4; // columns / hidden channels / float4 groups per thread
+        const int m = q * 32 + lane;
+        const size_t P = (size_t)a.H * a.W;
+        __half* hb = a.h_planes + (size_t)(d & 1) * 2 * CHK * P * 8;
+        float* hf32 = a.h_f32 ? a.h_f32 + (size_t)(d & 1) * P * CH : nullptr;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+            const int ab = it & 1;
+            const bool pf = a.prof && blockIdx.x == 0 && tid == 0 && it < 64;
+            // this thread's pixel and its previous cell state: requested BEFORE waiting for the accumulator so that the
+            // global-load latency overlaps the MMAs of this tile
+            const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+            const int y = ty * TR + (m >> 3), x = tx * TCOL + (m & 7);
+            const bool valid = y < a.H && x < a.W && !(a.dbg & 4);
+            const size_t pix = valid ? (size_t)y * a.W + x : 0;
+            float4* cp = reinterpret_cast<float4*>(a.c_blocked) + ((size_t)tile * 2 + hf) * NJ4 * 128 + m;
+            float cprev[NHC], cn[NHC], hn[NHC];
+#pragma unroll
+            for (int j = 0; j < NJ4; ++j) {
+                const float4 t = (d == 0 || !valid) ? make_float4(0.f, 0.f, 0.f, 0.f) : cp[j * 128];
+                cprev[4 * j] = t.x; cprev[4 * j + 1] = t.y; cprev[4 * j + 2] = t.z; cprev[4 * j + 3] = t.w;
+            }
+            if (pf) a.prof[it * 12 + 8] = clock64();
+            tc::mbar_wait_relaxed(&tmem_full[ab], (it >> 1) & 1);
+            tc::tc_fence_after();
+            if (pf) a.prof[it * 12 + 9] = clock64();
+            float g[NCOL], g2[NCOL];
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + ab * 2 * NG + hf * NCOL;
+            if constexpr (NCOL == 32) { tc::tmem_ld32(taddr, g); tc::tmem_ld32(taddr + NG, g2); }
+            else { tmem_ld16(taddr, g); tmem_ld16(taddr + NG, g2); }
+#pragma unroll
+            for (int j = 0; j < NCOL; ++j) g[j] += g2[j];            // (hi*hi + lo*hi) + hi*lo
+            tc::tc_fence_before();
+            tc::mbar_arrive(&tmem_empty[ab]);                    // accumulator is in registers: release it
+            if (pf) a.prof[it * 12 + 10] = clock64();
+            // pixels outside the image (ragged tiles) see zero operands: finite values that are never stored
+#pragma unroll
+            for (int j = 0; j < NHC; ++j) {
+                const float* bb = s_bias + hf * NCOL + j * 4;
+                const float gi = tc::fast_sigmoid(g[j * 4 + 0] + bb[0]);
+                const float gf = tc::fast_sigmoid(g[j * 4 + 1] + bb[1]);
+                const float go = tc::fast_sigmoid(g[j * 4 + 2] + bb[2]);
+                const float gg = tc::fast_tanh(g[j * 4 + 3] + bb[3]);
+                cn[j] = __fadd_rn(__fmul_rn(gf, cprev[j]), __fmul_rn(gi, gg));
+                hn[j] = go * tc::fast_tanh(cn[j]);
+            }
+            if (valid) {
+#pragma unroll
+                for (int j = 0; j < NJ4; ++j) cp[j * 128] = make_float4(cn[4 * j], cn[4 * j + 1], cn[4 * j + 2], cn[4 * j + 3]);
+                if constexpr (NHC == 8) {          // this thread owns chunk hf of the pixel: one 16-byte element per plane
+                    uint2 h0, l0, h1, l1;
+                    tc::split4_f16(make_float4(hn[0], hn[1], hn[2], hn[3]), h0, l0);
+                    tc::split4_f16(make_float4(hn[4], hn[5], hn[6], hn[7]), h1, l1);
+                    *reinterpret_cast<uint4*>(hb + ((size_t)hf * P + pix) * 8) = make_uint4(h0.x, h0.y, h1.x, h1.y);
+                    *reinterpret_cast<uint4*>(hb + ((size_t)(CHK + hf) * P + pix) * 8) = make_uint4(l0.x, l0.y, l1.x, l1.y);
+                } else {                           // CH = 8: half a chunk per thread
+                    uint2 h0, l0;
+                    tc::split4_f16(make_float4(hn[0], hn[1], hn[2], hn[3]), h0, l0);
+                    *reinterpret_cast<uint2*>(hb + pix * 8 + hf * 4) = h0;
+                    *reinterpret_cast<uint2*>(hb + (P + pix) * 8 + hf * 4) = l0;
+                }
+                if (hf32) {
+#pragma unroll
+                    for (int j = 0; j < NHC; j += 4)
+                        st4(hf32 + pix * CH + hf * NHC + j, make_float4(hn[j], hn[j + 1], hn[j + 2], hn[j + 3]));
+                }
+            }
+            if constexpr (NHC == 8) {
+                if (a.pooled) {                    // max_pool2d(h, 2) (drmvsnet.py:148,152): the 2x2 block is lanes ^1, ^8 of this warp
+                    float pm[NHC];
+#pragma unroll
+                    for (int j = 0; j < NHC; ++j) {
+                        float v = fmaxf(hn[j], __shfl_xor_sync(0xffffffffu, hn[j], 1));
+                        pm[j] = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 8));
+                    }
+                    if (valid && !(lane & 9)) {
+                        const size_t P4 = P >> 2, pp = (size_t)(y >> 1) * (a.W >> 1) + (x >> 1);
+                        uint2 h0, l0, h1, l1;
+                        tc::split4_f16(make_float4(pm[0], pm[1], pm[2], pm[3]), h0, l0);
+                        tc::split4_f16(make_float4(pm[4], pm[5], pm[6], pm[7]), h1, l1);
+                        *reinterpret_cast<uint4*>(a.pooled + ((size_t)hf * P4 + pp) * 8) = make_uint4(h0.x, h0.y, h1.x, h1.y);
+                        *reinterpret_cast<uint4*>(a.pooled + ((size_t)(CHK + hf) * P4 + pp) * 8) = make_uint4(l0.x, l0.y, l1.x, l1.y);
+                    }
+                }
+            }
+            if (pf) a.prof[it * 12 + 11] = clock64();
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == MMA_WARP) tc::tmem_dealloc<C::TMEM_COLS>(tmem_base);
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point query (the library links no libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// Operand planes [pp][2][chunks][H][W][8 halfs] -> 5-D map with the halo-tile box.
+int make_plane_map(CUtensorMap* map, const void* planes, int H, int W, int chunks, int pp) {
+    EncodeTiledFn enc = encode_tiled();
+    if (!enc) return AARMVS_ERR_ARG;
+    const cuuint64_t row = (cuuint64_t)W * 16, plane = (cuuint64_t)H * row;
+    cuuint64_t dims[5] = {(cuuint64_t)W * 8, (cuuint64_t)H, (cuuint64_t)chunks, 2, (cuuint64_t)pp};
+    cuuint64_t strides[4] = {row, plane, plane * chunks, plane * chunks * 2};
+    cuuint32_t box[5] = {(cuuint32_t)HC * 8, (cuuint32_t)HR, (cuuint32_t)chunks, 1, 1};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<void*>(planes), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? AARMVS_OK : AARMVS_ERR_ARG;
+}
+
+template <int KSTEPS, int NG, int NST>
+int launch_cell(const CellArgs& a, cudaStream_t stream) {
+    using C = Cfg<KSTEPS, NG, NST>;
+    auto kern = convlstm_tma_kernel<KSTEPS, NG, NST>;
+    static unsigned long long smem_ok = 0;
+    if (cudaError_t e = ensure_dyn_smem(kern, C::SMEM, smem_ok)) return (int)e;
+    const int ntiles = ((a.W + TCOL - 1) / TCOL) * ((a.H + TR - 1) / TR);
+    const int sms = aarmvs_sm_count();
+    if (sms <= 0) return AARMVS_ERR_ARG;
+    kern<<<ntiles < sms ? ntiles : sms, N_THREADS, C::SMEM, stream>>>(a);
+    AARMVS_LAUNCH_RESULT();
+}
+
+unsigned long long* g_prof = nullptr;
+int g_cell_dbg = 0;
+
+}  // namespace
+
+// Debug only: CTA 0 of the next ConvLSTM launches writes clock64 stamps per tile ([64][12] uint64) into `buf` (device).
+extern "C" void aarmvs_debug_profile_buffer(void* buf) { g_prof = (unsigned long long*)buf; }
+extern "C" void aarmvs_debug_cell_flags(int flags) { g_cell_dbg = flags; }
+
+extern "C" size_t aarmvs_cell_state_floats(int H, int W, int hidden) {
+    if (H <= 0 || W <= 0 || hidden <= 0) return 0;
+    return (size_t)((W + TCOL - 1) / TCOL) * ((H + TR - 1) / TR) * 128 * hidden;
+}
+
+extern "C" int aarmvs_convlstm_cell_tc(const aarmvs_plane_src* src, int nsrc, int H, int W, int cin, int hidden,
+                                       const void* weight_f16, const float* bias_packed, void* h_planes, float* c_blocked,
+                                       float* h_f32_pair, void* pooled_planes, int d_host, const int* d_dev, void* stream) {
+    AARMVS_CHECK_ARG(src && weight_f16 && bias_packed && h_planes && c_blocked && H > 0 && W > 0 && nsrc >= 1 && nsrc <= 2);
+    AARMVS_CHECK_ARG(hidden == 16 || hidden == 8);
+    AARMVS_CHECK_ARG(!pooled_planes || (hidden == 16 && H % 2 == 0 && W % 2 == 0));
+    CellArgs a = {};
+    a.nsrc = nsrc + 1;
+    int csum = 0;
+    for (int s = 0; s <= nsrc; ++s) {
+        const void* planes;
+        int ch, pp;
+        if (s < nsrc) {
+            AARMVS_CHECK_ARG(src[s].planes && src[s].channels > 0 && src[s].channels % 8 == 0 && (src[s].pp == 1 || src[s].pp == 2));
+            AARMVS_CHECK_ARG(((uintptr_t)src[s].planes & 15) == 0);
+            planes = src[s].planes; ch = src[s].channels; pp = src[s].pp;
+            a.pp_phase[s] = pp == 2 ? (src[s].pp_phase & 1) : -1;
+        } else {      // h_{d-1}: the half of the ping-pong pair that plane d does not write
+            planes = h_planes; ch = hidden; pp = 2;
+            a.pp_phase[s] = 1;
+        }
+        a.chunks[s] = ch / 8;
+        if (int e = make_plane_map(&a.map[s], planes, H, W, ch / 8, pp)) return e;
+        csum += ch;
+    }
+    AARMVS_CHECK_ARG(csum == cin && cin <= 48 && ((uintptr_t)h_planes & 15) == 0 && ((uintptr_t)weight_f16 & 15) == 0);
+    a.need_zero = cin % 16 != 0;
+    a.H = H; a.W = W; a.weight = (const __half*)weight_f16; a.bias = bias_packed; a.h_planes = (__half*)h_planes;
+    a.c_blocked = c_blocked; a.h_f32 = h_f32_pair; a.pooled = (__half*)pooled_planes;
+    a.d_host = d_host; a.d_dev = d_dev; a.prof = g_prof; a.dbg = g_cell_dbg;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (cin == 48 && hidden == 16) return launch_cell<3, 64, 3>(a, st);     // cells 0, 3
+    if (cin == 32 && hidden == 16) return launch_cell<2, 64, 4>(a, st);     // cells 1, 2
+    if (cin == 40 && hidden == 8) return launch_cell<3, 32, 4>(a, st);      // cell 4 (K padded 40 -> 48 with a zero chunk)
+    return AARMVS_ERR_ARG;
+}

@@ -30,7 +30,11 @@ namespace {
 #define STEM_NB 2
 #endif
 constexpr int TR = 16, TCOL = 8, HR = 18, HC = 10, NPX = HR * HC;        // 180 staged pixels
-constexpr int AROWS = 204;                 // operand rows per K chunk: >= NPX, = 4 mod 8 (conflict-free chunk stride), and
+#ifndef STEM_AROWS
+#define STEM_AROWS 210
+#endif
+constexpr int AROWS = STEM_AROWS;          // operand rows per K chunk: >= NPX; = 2 mod 8 puts the four chunks a half-warp's
+                                           // 8-byte stores touch (2 pixels x 8 lanes) in four disjoint groups of 8 banks; and
                                            // 2*4*AROWS*16 >= the z exchange buffer that reuses the stage
 constexpr int G = STEM_GROUPS;             // worker groups = operand stages = TMEM accumulators
 constexpr int GROUP_THREADS = 128;

@@ -11,6 +11,7 @@
 // so the 5-D cost volume and the per-view 32-channel cost never reach HBM.  Layout: features NHWC fp32 (one pixel
 // = 128 B = one cache line per bilinear tap); 8 lanes x float4 cover one pixel, a warp covers 4 pixels per load.
 #include "common.cuh"
+#include "tc_common.cuh"
 #include <string.h>
 
 struct StemParams {            // omega.reweight_network.0.0 repacked [tap][cin][cout] + bias; lives in the
@@ -410,7 +411,7 @@ warp_cost_kernel(const float* __restrict__ ref, const float* __restrict__ src, s
 __global__ void __launch_bounds__(256, AGS_MINB)
 aggregate_stream_kernel(const float* __restrict__ costv, int S, int K, size_t P, const __grid_constant__ OmegaTail q,
                         const float* __restrict__ t0, const double* __restrict__ stats, float* __restrict__ cost,
-                        float* __restrict__ reweight_out) {
+                        __half* __restrict__ cost_planes, float* __restrict__ reweight_out) {
     __shared__ OmegaNorm norms_all[AARMVS_MAX_PLANES * AARMVS_MAX_SRC];
     if (threadIdx.x < S * K) {
         OmegaNorm n;
@@ -473,9 +474,19 @@ aggregate_stream_kernel(const float* __restrict__ costv, int S, int K, size_t P,
 #pragma unroll
         for (int u = 0; u < AGS_PX; ++u) {
             const size_t i = i0 + u * stride;
-            if (i < total)
-                st4(cost + i * 32 + sub * 4, make_float4(-__fdiv_rn(acc[u].x, s_den), -__fdiv_rn(acc[u].y, s_den),
-                                                         -__fdiv_rn(acc[u].z, s_den), -__fdiv_rn(acc[u].w, s_den)));
+            if (i >= total) continue;
+            const float4 r = make_float4(-__fdiv_rn(acc[u].x, s_den), -__fdiv_rn(acc[u].y, s_den),
+                                         -__fdiv_rn(acc[u].z, s_den), -__fdiv_rn(acc[u].w, s_den));
+            if (cost_planes) {       // fp16 (hi, lo) operand planes [K][2][4 chunks][P][8] for the TMA-fed ConvLSTM cell 0
+                const size_t k = i / P, p = i - k * P;
+                uint2 hi, lo;
+                tc::split4_f16(r, hi, lo);
+                const size_t off = ((k * 8 + (sub >> 1)) * P + p) * 8 + (sub & 1) * 4;
+                *reinterpret_cast<uint2*>(cost_planes + off) = hi;
+                *reinterpret_cast<uint2*>(cost_planes + off + 4 * P * 8) = lo;
+            } else {
+                st4(cost + i * 32 + sub * 4, r);
+            }
         }
     }
 }
@@ -554,8 +565,9 @@ extern "C" int aarmvs_omega_stats(int stage, const float* t0, int H, int W, int 
 extern "C" int aarmvs_aggregate(const float* ref, const float* src, size_t view_stride, int H, int W, int S,
                                 const float* cams, const float* tail_host, const float* depth_values, int d_host,
                                 const int* d_dev, int planes, int align_corners, const float* t0, const double* stats,
-                                const float* costv, float* cost, float* reweight_out, void* stream) {
-    AARMVS_CHECK_ARG(t0 && stats && cost && tail_host && H > 0 && W > 0);
+                                const float* costv, float* cost, void* cost_planes, float* reweight_out, void* stream) {
+    AARMVS_CHECK_ARG(t0 && stats && tail_host && H > 0 && W > 0);
+    AARMVS_CHECK_ARG(cost_planes ? (costv && ((uintptr_t)cost_planes & 15) == 0) : cost != nullptr);
     AARMVS_CHECK_ARG(S >= 1 && S <= AARMVS_MAX_SRC && planes >= 1 && planes <= AARMVS_MAX_PLANES);
     OmegaTail q;
     fill_tail(q, tail_host);
@@ -563,7 +575,7 @@ extern "C" int aarmvs_aggregate(const float* ref, const float* src, size_t view_
         const size_t Pn = (size_t)H * W;
         const size_t groups = (Pn * planes + 31) / 32;
         const int nblk = (int)(groups < (size_t)148 * 32 ? groups : (size_t)148 * 32);
-        aggregate_stream_kernel<<<nblk, 256, 0, (cudaStream_t)stream>>>(costv, S, planes, Pn, q, t0, stats, cost, reweight_out);
+        aggregate_stream_kernel<<<nblk, 256, 0, (cudaStream_t)stream>>>(costv, S, planes, Pn, q, t0, stats, cost, (__half*)cost_planes, reweight_out);
         AARMVS_LAUNCH_RESULT();
     }
     AARMVS_CHECK_ARG(ref && src && depth_values && cams);

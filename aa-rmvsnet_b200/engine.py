@@ -40,6 +40,18 @@ def _src_array(*srcs):
     return arr
 
 
+def _psrc(t, channels, pp=1, phase=0):
+    """Operand planes [pp][2][channels/8][H][W][8] fp16 as a source of the tensor-core cell (struct aarmvs_plane_src)."""
+    s = capi.PlaneSrc()
+    s.planes = t.data_ptr()
+    s.channels, s.pp, s.pp_phase = channels, pp, phase
+    return s
+
+
+def _psrc_array(*srcs):
+    return (capi.PlaneSrc * len(srcs))(*srcs)
+
+
 class Engine:
     """Runs EMVSNet.forward's arithmetic for one model instance (weights are re-packed when they change)."""
 
@@ -141,11 +153,26 @@ class Engine:
         ws["fsums"] = torch.zeros(64, device=device, dtype=torch.float64)
         # plane sweep
         ws["t0"] = torch.empty(K, S, P, 4, **f32)
-        ws["cost"] = torch.empty(K, P, 32, **f32)
+        tc = self.cell_math == "tc"
         # (warp - ref)^2 kept by pass A so that pass D streams instead of gathering again (tensor-core path only)
-        ws["costv"] = torch.empty(K, S, P, 32, **f32) if self.cell_math == "tc" and self.keep_costv else None
-        ws["h"] = [torch.empty(2, P // (s * s), ch, **f32) for ch, s in zip(_HID, _SCALE)]
-        ws["c"] = [torch.empty(P // (s * s), ch, **f32) for ch, s in zip(_HID, _SCALE)]
+        ws["costv"] = torch.empty(K, S, P, 32, **f32) if tc and self.keep_costv else None
+        ws["cost"] = torch.empty(K, P, 32, **f32) if ws["costv"] is None else None
+        if tc:
+            # everything the cells read is kept as fp16 (hi, lo) operand planes [2][C/8][H][W][8] (include/aarmvs.h):
+            # cost (pass D), h ping-pong pairs and max-pooled h (cell epilogues), GroupNorm+ReLU'd deconv outputs
+            f16 = dict(device=device, dtype=torch.float16)
+            ws["costp"] = torch.empty(K, 2, 4, P, 8, **f16)
+            ws["hp"] = [torch.zeros(2, 2, (ch + 7) // 8, P // (s * s), 8, **f16) for ch, s in zip(_HID, _SCALE)]
+            ws["pool"] = [torch.empty(2, 2, P // 4, 8, **f16), torch.empty(2, 2, P // 16, 8, **f16)]
+            ws["up0p"] = torch.empty(2, 2, P // 4, 8, **f16)
+            ws["up1p"] = torch.empty(2, 2, P, 8, **f16)
+            ws["c"] = [torch.empty(self.lib.aarmvs_cell_state_floats(H // s, W // s, ch), **f32) for ch, s in zip(_HID, _SCALE)]
+            # fp32 copies of h only where a CUDA-core kernel reads it (deconv_0, deconv_1, conv_0)
+            ws["h"] = [torch.empty(2, P // (s * s), ch, **f32) if i >= 2 else None
+                       for i, (ch, s) in enumerate(zip(_HID, _SCALE))]
+        else:
+            ws["h"] = [torch.empty(2, P // (s * s), ch, **f32) for ch, s in zip(_HID, _SCALE)]
+            ws["c"] = [torch.empty(P // (s * s), ch, **f32) for ch, s in zip(_HID, _SCALE)]
         ws["up0"] = torch.empty(P // 4, 16, **f32)
         ws["up1"] = torch.empty(P, 16, **f32)
         ws["psums"] = torch.zeros(K * S * 6 + 8, device=device, dtype=torch.float64)
@@ -224,6 +251,10 @@ class Engine:
             capi.check(self.lib.aarmvs_cost_stem(ref, src, view_stride, H, W, S, cams, w["stem.w_host"], w["stem.b_host"],
                                                  depths, d_host, dptr, planes, ac, t0, sums, stream), "aarmvs_cost_stem")
 
+    def split_planes(self, src, H, W, planes, stream):
+        """fp32 NHWC source (optionally GroupNorm+ReLU'd on the fly) -> fp16 (hi, lo) operand planes of the tc cells."""
+        capi.check(self.lib.aarmvs_split_planes(ctypes.byref(src), H, W, _ptr(planes), stream), "aarmvs_split_planes")
+
     # ------------------------------------------------------------------------------------------ one plane
     def _batch(self, ws, w, stream, nplanes, marks=None):
         """Enqueue the kernel chain of `nplanes` consecutive depth planes starting at the plane index held in
@@ -251,9 +282,16 @@ class Engine:
             capi.check(lib.aarmvs_omega_stats(stage, _ptr(ws["t0"]), H, W, S, nplanes, w["tail_host"], _ptr(ps), stream),
                        "aarmvs_omega_stats")
         mark("omega_stats")
+        tc = self.cell_math == "tc"
+        # tensor-core cells: pass D writes the cost straight into cell 0's operand planes
+        direct = tc and costv is not None
         capi.check(lib.aarmvs_aggregate(ref, src, P * 32, H, W, S, _ptr(ws["cams"]), w["tail_host"], _ptr(ws["depths"]), 0,
-                                        dptr, nplanes, ac, _ptr(ws["t0"]), _ptr(ps), costv, _ptr(ws["cost"]), None, stream),
-                   "aarmvs_aggregate")
+                                        dptr, nplanes, ac, _ptr(ws["t0"]), _ptr(ps), costv,
+                                        None if direct else _ptr(ws["cost"]), _ptr(ws["costp"]) if direct else None, None,
+                                        stream), "aarmvs_aggregate")
+        if tc and not direct:
+            for k in range(nplanes):
+                self.split_planes(_src(ws["cost"][k], 32), H, W, ws["costp"][k], stream)
         mark("aggregate")
         h, c = ws["h"], ws["c"]
 
@@ -262,15 +300,22 @@ class Engine:
 
         def cell(i, srcs, hh, ww, cin):
             arr = _src_array(*srcs)
-            if self.cell_math == "tc":
-                capi.check(lib.aarmvs_convlstm_cell_tc(arr, len(srcs), hh, ww, cin, _HID[i], _ptr(w[f"cell{i}.wtc"]),
-                                                       _ptr(w[f"cell{i}.b"]), _ptr(h[i]), _ptr(c[i]), 0, dptr, stream),
-                           f"aarmvs_convlstm_cell_tc[{i}]")
-            else:
-                capi.check(lib.aarmvs_convlstm_cell(arr, len(srcs), hh, ww, cin, _HID[i], _ptr(w[f"cell{i}.w"]),
-                                                    _ptr(w[f"cell{i}.b"]), _ptr(h[i]), _ptr(c[i]), 0, dptr, stream),
-                           f"aarmvs_convlstm_cell[{i}]")
+            capi.check(lib.aarmvs_convlstm_cell(arr, len(srcs), hh, ww, cin, _HID[i], _ptr(w[f"cell{i}.w"]),
+                                                _ptr(w[f"cell{i}.b"]), _ptr(h[i]), _ptr(c[i]), 0, dptr, stream),
+                       f"aarmvs_convlstm_cell[{i}]")
             mark(f"cell{i}")
+
+        def cell_tc(i, srcs, hh, ww, cin, pooled=None):
+            arr = _psrc_array(*srcs)
+            capi.check(lib.aarmvs_convlstm_cell_tc(arr, len(srcs), hh, ww, cin, _HID[i], _ptr(w[f"cell{i}.wtc"]),
+                                                   _ptr(w[f"cell{i}.b"]), _ptr(ws["hp"][i]), _ptr(c[i]),
+                                                   _ptr(h[i]) if h[i] is not None else None,
+                                                   _ptr(pooled) if pooled is not None else None, 0, dptr, stream),
+                       f"aarmvs_convlstm_cell_tc[{i}]")
+            mark(f"cell{i}")
+
+        def hplanes(i):          # h_i of the CURRENT plane as operand planes (ping-pong half d & 1)
+            return _psrc(ws["hp"][i], _HID[i], pp=2, phase=0)
 
         def deconv(i, src_, hin, win, dst, sums):
             capi.check(lib.aarmvs_deconv2x(ctypes.byref(src_), hin, win, w[f"deconv{i}.w_host"], w[f"deconv{i}.b_host"],
@@ -281,15 +326,28 @@ class Engine:
         s_up0, s_up1 = ps[n_omega:], ps[n_omega + 4:]
         cv = ws["cost_volume"]
         for k in range(nplanes):
-            cell(0, [_src(ws["cost"][k], 32)], H, W, 48)
-            cell(1, [hsrc(0, capi.SRC_MAXPOOL2)], H2, W2, 32)
-            cell(2, [hsrc(1, capi.SRC_MAXPOOL2)], H4, W4, 32)
-            deconv(0, hsrc(2), H4, W4, ws["up0"], s_up0)
             up0 = _src(ws["up0"], 16, capi.SRC_GN_RELU, sums=s_up0, gn=w["deconv0.gn"], groups=2, count=8 * (P // 4))
-            cell(3, [up0, hsrc(1)], H2, W2, 48)
-            deconv(1, hsrc(3), H2, W2, ws["up1"], s_up1)
             up1 = _src(ws["up1"], 16, capi.SRC_GN_RELU, sums=s_up1, gn=w["deconv1.gn"], groups=2, count=8 * P)
-            cell(4, [up1, hsrc(0)], H, W, 40)
+            if tc:
+                cell_tc(0, [_psrc(ws["costp"][k], 32)], H, W, 48, pooled=ws["pool"][0])
+                cell_tc(1, [_psrc(ws["pool"][0], 16)], H2, W2, 32, pooled=ws["pool"][1])
+                cell_tc(2, [_psrc(ws["pool"][1], 16)], H4, W4, 32)
+                deconv(0, hsrc(2), H4, W4, ws["up0"], s_up0)
+                self.split_planes(up0, H2, W2, ws["up0p"], stream)          # GroupNorm + ReLU need the whole map's sums
+                mark("deconv0_split")
+                cell_tc(3, [_psrc(ws["up0p"], 16), hplanes(1)], H2, W2, 48)
+                deconv(1, hsrc(3), H2, W2, ws["up1"], s_up1)
+                self.split_planes(up1, H, W, ws["up1p"], stream)
+                mark("deconv1_split")
+                cell_tc(4, [_psrc(ws["up1p"], 16), hplanes(0)], H, W, 40)
+            else:
+                cell(0, [_src(ws["cost"][k], 32)], H, W, 48)
+                cell(1, [hsrc(0, capi.SRC_MAXPOOL2)], H2, W2, 32)
+                cell(2, [hsrc(1, capi.SRC_MAXPOOL2)], H4, W4, 32)
+                deconv(0, hsrc(2), H4, W4, ws["up0"], s_up0)
+                cell(3, [up0, hsrc(1)], H2, W2, 48)
+                deconv(1, hsrc(3), H2, W2, ws["up1"], s_up1)
+                cell(4, [up1, hsrc(0)], H, W, 40)
             h4 = hsrc(4)
             capi.check(lib.aarmvs_head_wta(ctypes.byref(h4), H, W, w["head.w_host"], w["head.b_host"], _ptr(ws["depths"]),
                                            ws["D"], 0, dptr, _ptr(ws["max_prob"]), _ptr(ws["depth"]), _ptr(ws["exp_sum"]),

@@ -10,7 +10,7 @@ import ctypes
 import torch
 
 from . import capi
-from .engine import Engine, _ptr, _src, _src_array
+from .engine import Engine, _psrc, _psrc_array, _ptr, _src, _src_array
 
 
 def _nhwc(x):          # [C,H,W] -> [H*W, C] contiguous
@@ -85,9 +85,24 @@ def aggregate_plane(model, ref_fea, src_feas, ref_proj, src_projs, depth_value, 
     for stage in (2, 3):
         capi.check(lib.aarmvs_omega_stats(stage, _ptr(t0), H, W, S, 1, w["tail_host"], _ptr(sums), st), "aarmvs_omega_stats")
     capi.check(lib.aarmvs_aggregate(_ptr(feat), _ptr(feat, P * 32), P * 32, H, W, S, _ptr(cams), w["tail_host"],
-                                    _ptr(depths), 0, None, 1, ac, _ptr(t0), _ptr(sums), costv, _ptr(cost), _ptr(rew), st),
+                                    _ptr(depths), 0, None, 1, ac, _ptr(t0), _ptr(sums), costv, _ptr(cost), None, _ptr(rew), st),
                "aarmvs_aggregate")
     return -_nchw(cost, H, W), rew.view(S, H, W)
+
+
+def _block_state(c, H, W):
+    """[H*W, CH] NHWC cell state -> the tile-blocked layout of aarmvs_convlstm_cell_tc (include/aarmvs.h)."""
+    ch = c.shape[1]
+    ty, tx = (H + 15) // 16, (W + 7) // 8
+    full = c.new_zeros(ty * 16, tx * 8, ch)
+    full[:H, :W] = c.view(H, W, ch)
+    return full.view(ty, 16, tx, 8, 2, ch // 8, 4).permute(0, 2, 4, 5, 1, 3, 6).contiguous().view(-1)
+
+
+def _unblock_state(cb, H, W, ch):
+    ty, tx = (H + 15) // 16, (W + 7) // 8
+    full = cb.view(ty, tx, 2, ch // 8, 16, 8, 4).permute(0, 4, 1, 5, 2, 3, 6).reshape(ty * 16, tx * 8, ch)
+    return full[:H, :W].reshape(H * W, ch).contiguous()
 
 
 def convlstm_cell(model, cell_index, x, h, c, math=None):
@@ -103,13 +118,23 @@ def convlstm_cell(model, cell_index, x, h, c, math=None):
     h_pair = torch.empty(2, H * W, ch, device=dev)
     h_pair[0] = _nhwc(h.float())                       # plane d=1 reads half 0 and writes half 1
     cs = _nhwc(c.float())
+    st = _stream(dev)
     if (math or eng.cell_math) == "tc":
-        capi.check(lib.aarmvs_convlstm_cell_tc(_src_array(_src(xs, cx)), 1, H, W, cx + ch, ch, _ptr(w[f"cell{cell_index}.wtc"]),
-                                               _ptr(w[f"cell{cell_index}.b"]), _ptr(h_pair), _ptr(cs), 1, None, _stream(dev)),
+        # the tensor-core kernel reads fp16 (hi, lo) operand planes and keeps c tile-blocked: convert at the seam
+        xp = torch.empty(2, cx // 8, H * W, 8, device=dev, dtype=torch.float16)
+        hp = torch.zeros(2, 2, (ch + 7) // 8, H * W, 8, device=dev, dtype=torch.float16)
+        eng.split_planes(_src(xs, cx), H, W, xp, st)
+        if ch % 8 == 0:
+            eng.split_planes(_src(h_pair[0], ch), H, W, hp[0], st)
+        cb = _block_state(cs, H, W)
+        assert cb.numel() == lib.aarmvs_cell_state_floats(H, W, ch)
+        capi.check(lib.aarmvs_convlstm_cell_tc(_psrc_array(_psrc(xp, cx)), 1, H, W, cx + ch, ch, _ptr(w[f"cell{cell_index}.wtc"]),
+                                               _ptr(w[f"cell{cell_index}.b"]), _ptr(hp), _ptr(cb), _ptr(h_pair), None, 1, None, st),
                    "aarmvs_convlstm_cell_tc")
+        cs = _unblock_state(cb, H, W, ch)
     else:
         capi.check(lib.aarmvs_convlstm_cell(_src_array(_src(xs, cx)), 1, H, W, cx + ch, ch, _ptr(w[f"cell{cell_index}.w"]),
-                                            _ptr(w[f"cell{cell_index}.b"]), _ptr(h_pair), _ptr(cs), 1, None, _stream(dev)),
+                                            _ptr(w[f"cell{cell_index}.b"]), _ptr(h_pair), _ptr(cs), 1, None, st),
                    "aarmvs_convlstm_cell")
     return _nchw(h_pair[1], H, W), _nchw(cs, H, W)
 

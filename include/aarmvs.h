@@ -23,7 +23,7 @@ extern "C" {
 #define AARMVS_MAX_SRC_VIEWS 15
 #define AARMVS_MAX_PLANES_PER_CALL 16
 
-int aarmvs_version(void);          /* ABI version, currently 2 */
+int aarmvs_version(void);          /* ABI version, currently 3 */
 int aarmvs_sm_count(void);         /* multiprocessors of the current device (148 on B200), <0 on error */
 
 /* ---------------------------------------------------------------------------------------------------------
@@ -122,11 +122,13 @@ int aarmvs_omega_stats(int stage, const float* t0, int H, int W, int S, int plan
 
 /* Pass D: cost[p][c] = -(sum_v (omega_v(p) + 1) * (warp_v - ref)^2) / S  (models/drmvsnet.py:311-319), the input
  * of the recurrent regulariser.  costv: NULL = gather again; else pass A's costv_out, read back as a pure stream (ref, src,
- * cams, depth_values are then unused).  reweight_out: optional omega maps (operator seam / tests), may be NULL. */
+ * cams, depth_values are then unused).  reweight_out: optional omega maps (operator seam / tests), may be NULL.
+ * cost_planes (needs costv): write the result as fp16 (hi, lo) operand planes [planes][2][4][H][W][8] (see
+ * aarmvs_plane_src) instead of fp32 `cost`, which may then be NULL. */
 int aarmvs_aggregate(const float* ref, const float* src, size_t view_stride, int H, int W, int S, const float* cams,
                      const float* tail_host, const float* depth_values, int d_host, const int* d_dev, int planes,
                      int align_corners, const float* t0, const double* stats, const float* costv, float* cost,
-                     float* reweight_out, void* stream);
+                     void* cost_planes, float* reweight_out, void* stream);
 
 /* ---- recurrent regularisation (models/drmvsnet.py:119-167) --------------------------------------------- */
 
@@ -139,14 +141,41 @@ int aarmvs_convlstm_cell(const aarmvs_conv_src* src, int nsrc, int H, int W, int
                          const float* weight_packed, const float* bias_packed, float* h_pair, float* c_state,
                          int d_host, const int* d_dev, void* stream);
 
-/* The same cell on the tensor cores (tcgen05.mma kind::f16, fp32 accumulation in TMEM).  fp32 operands are split
- * on the fly into fp16 (hi, lo) pairs and each K step issues hi*hi + lo*hi + hi*lo, which keeps ~2^-21 relative
- * accuracy per product (single-pass TF32 / BF16 fails the parity bar).  Same arguments as
- * aarmvs_convlstm_cell except weight_f16: [9 taps][cin_pad/8][2 (hi, lo)][4*hidden][8] fp16 with cin_pad = cin
- * rounded up to 16 (zero rows) and the output-channel order [hidden channel][i,f,o,g]; source channels multiples of 8. */
-int aarmvs_convlstm_cell_tc(const aarmvs_conv_src* src, int nsrc, int H, int W, int cin, int hidden,
-                            const void* weight_f16, const float* bias_packed, float* h_pair, float* c_state,
-                            int d_host, const int* d_dev, void* stream);
+/* Operand planes: how the tensor-core cell kernel receives every input.  A C-channel fp32 map x [H][W][C] is stored
+ * as two fp16 planes with x ~= hi + lo (hi = x with the low 13 mantissa bits cleared, lo = fp16(x - hi), 2^-22 relative):
+ *   [pp ping-pong halves][2 (hi, lo)][C/8 chunks][H][W][8 channels] fp16
+ * so that one 16-byte element is 8 channels of one pixel = one row of a K-major tcgen05 core matrix and a TMA box of
+ * (10 x 18 pixels x chunks) IS the staged halo tile of the implicit GEMM.  Producers write this layout directly
+ * (aarmvs_aggregate's cost_planes, the cell's own h / pooled outputs, aarmvs_split_planes). */
+typedef struct aarmvs_plane_src {
+    const void* planes;        /* device pointer, 16-byte aligned */
+    int channels;              /* multiple of 8 */
+    int pp;                    /* 1 = single buffer, 2 = ping-pong pair */
+    int pp_phase;              /* pp == 2: 0 = half written by the current plane (d & 1), 1 = previous plane's half */
+} aarmvs_plane_src;
+
+/* fp32 [H][W][channels] (mode PLAIN or GN_RELU: the producer's GroupNorm + ReLU is applied first, models/module.py:284-286)
+ * -> operand planes [2][channels/8][H][W][8]. */
+int aarmvs_split_planes(const aarmvs_conv_src* src, int H, int W, void* planes, void* stream);
+
+/* Floats of the cell-state buffer of aarmvs_convlstm_cell_tc: c lives in a tile-blocked layout private to the kernel,
+ * [tiles of 16 rows x 8 columns, row-major over ceil(H/16) x ceil(W/8)][2 halves of the hidden channels][hidden/8]
+ * [128 pixels of the tile, row-major][4 channels]  (every access of the epilogue is a fully used 128-byte line). */
+size_t aarmvs_cell_state_floats(int H, int W, int hidden);
+
+/* The same cell on the tensor cores (tcgen05.mma kind::f16, fp32 accumulation in TMEM), fed by TMA from operand planes.
+ * Each K step issues hi*hi + lo*hi + hi*lo, which keeps ~2^-21 relative accuracy per product (single-pass TF32 / BF16
+ * fails the parity bar).  Input = concat(src[0..nsrc-1], h_{d-1}); cin counts all of them.
+ * weight_f16: [9 taps][cin_pad/8][2 (hi, lo)][4*hidden][8] fp16 with cin_pad = cin rounded up to 16 (zero rows) and the
+ * output-channel order [hidden channel][i,f,o,g]; bias_packed as aarmvs_convlstm_cell.
+ * h_planes: ping-pong operand planes [2][2][hidden/8][H][W][8]; plane d reads half (d+1)&1 as h_{d-1} (not at d = 0,
+ * where h = c = 0) and writes half d&1.  c_blocked: aarmvs_cell_state_floats() floats, in place.
+ * h_f32_pair: optional fp32 copy of h, two [H*W][hidden] halves (half d&1 written) for the deconvolution / head kernels.
+ * pooled_planes: optional operand planes [2][hidden/8][H/2][W/2][8] of max_pool2d(h, 2) (models/drmvsnet.py:148,152;
+ * hidden == 16 only).  Supported (cin, hidden): (48,16) (32,16) (40,8). */
+int aarmvs_convlstm_cell_tc(const aarmvs_plane_src* src, int nsrc, int H, int W, int cin, int hidden,
+                            const void* weight_f16, const float* bias_packed, void* h_planes, float* c_blocked,
+                            float* h_f32_pair, void* pooled_planes, int d_host, const int* d_dev, void* stream);
 
 /* deConvGnReLU's ConvTranspose2d(16,16,k3,s2,p1,op1) (models/module.py:281): in [Hin][Win][16] (one conv source,
  * typically a ping-pong h) -> pre-norm out [2Hin][2Win][16] + GroupNorm sums (2 groups).
@@ -191,8 +220,8 @@ void aarmvs_debug_stem_profile_buffer(void* buf);
  * 64 x 12 uint64, CTA 0 of subsequent aarmvs_convlstm_cell_tc launches records clock64 stamps of its loader / MMA /
  * epilogue roles per tile.  Pass NULL to switch off. */
 void aarmvs_debug_profile_buffer(void* buf);
-/* Debug ablation switches for aarmvs_convlstm_cell_tc (results become wrong): 1 no global loads in the loader, 2 no
- * operand stores, 4 no global I/O in the epilogue, 8 no MMAs. */
+/* Debug ablation switches for aarmvs_convlstm_cell_tc (results become wrong): 1 no TMA loads,
+ * 4 no global I/O in the epilogue, 8 no MMAs. */
 void aarmvs_debug_cell_flags(int flags);
 
 #ifdef __cplusplus

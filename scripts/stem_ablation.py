@@ -44,7 +44,7 @@ print("group-0 cycles per fill: recipes+bar %.0f | gather+stage %.0f | fence+arr
 cost = torch.empty(K, P, 32, device="cuda")
 def run_d():
     capi.check(lib.aarmvs_aggregate(_ptr(ws["feat"]), _ptr(ws["feat"], P * 32), P * 32, H, W, S, _ptr(ws["cams"]), w["tail_host"],
-                                    _ptr(ws["depths"]), 100, None, K, 0, _ptr(ws["t0"]), _ptr(ws["psums"]), None, _ptr(cost), None, st), "agg")
+                                    _ptr(ws["depths"]), 100, None, K, 0, _ptr(ws["t0"]), _ptr(ws["psums"]), None, _ptr(cost), None, None, st), "agg")
 ws["psums"].fill_(1000.0)
 run_d(); torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -57,7 +57,7 @@ print(f"aggregate                {e0.elapsed_time(e1) / 3 / K:.3f} ms/plane")
 cv = torch.randn(K, S, P, 32, device="cuda")
 def run_ds():
     capi.check(lib.aarmvs_aggregate(None, None, 0, H, W, S, None, w["tail_host"], None, 100, None, K, 0, _ptr(ws["t0"]), _ptr(ws["psums"]),
-                                    _ptr(cv), _ptr(cost), None, st), "agg stream")
+                                    _ptr(cv), _ptr(cost), None, None, st), "agg stream")
 run_ds(); torch.cuda.synchronize()
 e0.record()
 for _ in range(3): run_ds()

@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), n
     assert sorted(capi.PROTOTYPES) == names        # the ctypes table and the header agree
-    assert lib.aarmvs_version() == 2
+    assert lib.aarmvs_version() == 3
 
 
 def test_library_is_sm100a_and_has_no_torch_dependency():
