@@ -2,10 +2,13 @@
 // models/drmvsnet.py:31,311): for every source view, bilinear gather at depth d, c = (warp - ref)^2, and the omega
 // stem 3x3 conv 32 -> 4 (omega.reweight_network.0.0) on tcgen05.
 //
-// The conv is evaluated as  z[p][tap][o] = sum_c c[p][c] * w[o][c][tap]   (one GEMM per staged halo tile: M = the 180
-// halo pixels in two 128-row blocks, N = 9 taps x 4 outputs = 36 -> 48, K = 32 channels)  followed by the 9-tap shifted
-// sum  t0[q][o] = b[o] + sum_tap z[q + tap][tap][o].  Operands: un-swizzled K-major fp16 (hi, lo) planes
-// [8-channel chunk][row][16 B] (see convlstm_tc.cu / tc_common.cuh); fp32 accumulation in TMEM.
+// The conv is an implicit GEMM exactly like the ConvLSTM cells (convlstm_tma.cu): M = the 128 pixels of a 16 x 8 tile,
+// K = 32 channels, and a 3x3 tap is only a different descriptor start address into the staged [18][10] halo tile:
+//   t0[p][o] = b[o] + sum_tap sum_c c[p + tap][c] * w[o][c][tap]            (9 taps x 2 K-steps x 2 MMAs per fill, N = 16)
+// B rows 0-3 hold fp16 hi(w), rows 8-11 lo(w); A_hi x B and A_lo x B accumulate hi*hi + lo*hi in columns 0-3 and
+// hi*lo + lo*lo in columns 8-11 (fp32 in TMEM), and the epilogue adds the two blocks.  Operands: un-swizzled K-major
+// fp16 planes [8-channel chunk][row][16 B] (tc_common.cuh).  (The first version computed z[p][tap][o] for all 180 halo
+// pixels and summed the shifted taps through shared memory: 430 of its 2 700 L1 wavefronts per fill.)
 //
 // Work unit = one "fill" = (tile of 16 x 8 pixels + halo, source view, plane); fills run in (tile, view, plane) order so
 // a tile's source lines stay in L1 across the planes of a batch.  The CTA (one per SM, persistent) is a ring of
@@ -13,8 +16,8 @@
 // accumulator g and walks fills g, g+G, g+2G, ...:
 //   1. one thread per staged pixel evaluates the homography and writes a ready-to-use gather recipe (shared memory);
 //   2. 8 lanes per pixel gather branch-free (out-of-image taps read line 0 with weight 0), (warp-ref)^2, fp16 split,
-//      stage -> arrive on full[g];                      [the MMA warp issues the 12 MMAs of that fill, commit -> done[g]]
-//   3. wait done[g]: TMEM -> z rows -> exchange through the (now free) operand stage -> 9-tap sum -> t0, GroupNorm-1 sums.
+//      stage -> arrive on full[g];                      [the MMA warp issues the 36 MMAs of that fill, commit -> done[g]]
+//   3. wait done[g]: TMEM -> t0 (+ bias), GroupNorm-1 sums.
 // The groups are out of phase, so one group's load / MMA latency is covered by the others' arithmetic, and no role
 // waits on another group's progress (the first version had a single epilogue group that serialised the pipeline).
 #include "common.cuh"
@@ -31,23 +34,25 @@ namespace {
 #endif
 constexpr int TR = 16, TCOL = 8, HR = 18, HC = 10, NPX = HR * HC;        // 180 staged pixels
 #ifndef STEM_AROWS
-#define STEM_AROWS 210
+#define STEM_AROWS 186
 #endif
 constexpr int AROWS = STEM_AROWS;          // operand rows per K chunk: >= NPX; = 2 mod 8 puts the four chunks a half-warp's
-                                           // 8-byte stores touch (2 pixels x 8 lanes) in four disjoint groups of 8 banks; and
-                                           // 2*4*AROWS*16 >= the z exchange buffer that reuses the stage
+                                           // 8-byte stores touch (2 pixels x 8 lanes) in four disjoint groups of 8 banks
+static_assert(AROWS >= 180, "a chunk holds the 18 x 10 halo tile");
 constexpr int G = STEM_GROUPS;             // worker groups = operand stages = TMEM accumulators
 constexpr int GROUP_THREADS = 128;
 constexpr int N_THREADS = 32 + G * GROUP_THREADS;
-constexpr int KC8 = 4, NZ = 48;                                          // K chunks; accumulator columns (36 used)
-constexpr int A_PLANE = KC8 * AROWS * 16, A_STAGE = 2 * A_PLANE;         // 13056, 26112 bytes
-constexpr int B_PLANE = KC8 * NZ * 16, B_BYTES = 2 * B_PLANE;            // 3072, 6144 bytes
+constexpr int KC8 = 4, NB = 16;                                          // K chunks; accumulator columns (0-3 and 8-11 used)
+constexpr int A_PLANE = KC8 * AROWS * 16, A_STAGE = 2 * A_PLANE;
+constexpr int B_BYTES = 9 * KC8 * NB * 16;                               // [tap][chunk][16 rows][16 B] = 9216 bytes
 constexpr int TAP_BYTES = NPX * 48;                                      // one TapRec (48 B) per staged pixel
-constexpr int Z_BYTES = 9 * NPX * 16;                                    // z exchange [tap][pixel][4 floats] = 25920
-static_assert(Z_BYTES <= A_STAGE, "the z exchange buffer reuses the operand stage");
-constexpr int SMEM = B_BYTES + G * (A_STAGE + TAP_BYTES) + 1024;
-constexpr int TMEM_COLS = 512;                                           // G accumulators x 2 row blocks x 48 columns
-static_assert(G * 2 * NZ <= TMEM_COLS, "accumulators exceed TMEM");
+constexpr int SMEM_FIXED = B_BYTES + G * (A_STAGE + TAP_BYTES) + 1024;    // + G * 4 warps * planes * S * 8 bytes of GroupNorm partial sums
+#ifndef STEM_ACC_STRIDE
+#define STEM_ACC_STRIDE 32
+#endif
+constexpr int ACC = STEM_ACC_STRIDE;       // TMEM columns between the groups' accumulators
+constexpr int TMEM_COLS = G * ACC <= 32 ? 32 : G * ACC <= 64 ? 64 : G * ACC <= 128 ? 128 : G * ACC <= 256 ? 256 : 512;
+static_assert(G * ACC <= 512 && ACC >= NB, "accumulators exceed the TMEM allocation");
 
 struct StemArgs {
     const float* ref;
@@ -55,7 +60,7 @@ struct StemArgs {
     size_t view_stride;
     int H, W, S, K;             // K = planes per launch
     const float* cams;
-    const __half* weight;       // [2 planes hi,lo][4 chunks][48 columns (tap*4 + out)][8] fp16
+    const __half* weight;       // [9 taps][4 chunks][16 rows: 0-3 hi(w[o]), 8-11 lo(w[o])][8] fp16
     float bias[4];
     const float* depth_values;
     int d_host;
@@ -83,10 +88,11 @@ __global__ void __launch_bounds__(N_THREADS, 1) cost_stem_tc_kernel(const __grid
     unsigned char* sB = smem;
     unsigned char* sA = smem + B_BYTES;
     unsigned char* sT = sA + G * A_STAGE;
+    const int SK = a.S * a.K;
+    float2* sstat = reinterpret_cast<float2*>(sT + G * TAP_BYTES);      // [worker warp][(plane, view)] GroupNorm partial sums: no atomics
     __shared__ uint64_t full_a[G], done_a[G];
     __shared__ uint32_t tmem_base_s;
     __shared__ float scam[AARMVS_MAX_SRC * 12];
-    __shared__ float2 sstat[G * 4][AARMVS_MAX_PLANES * AARMVS_MAX_SRC];      // per worker warp, per (plane, view): no atomics
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const float* depths = a.depth_values + plane_index(a.d_host, a.d_dev);
@@ -95,7 +101,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) cost_stem_tc_kernel(const __grid
         reinterpret_cast<uint4*>(sB)[i] = __ldg(reinterpret_cast<const uint4*>(a.weight) + i);
     if (a.costv_mode != 2)          // stream mode never evaluates a homography
         for (int i = tid; i < a.S * 12; i += N_THREADS) scam[i] = a.cams[i];
-    for (int i = tid; i < G * 4 * AARMVS_MAX_PLANES * AARMVS_MAX_SRC; i += N_THREADS) (&sstat[0][0])[i] = make_float2(0.f, 0.f);
+    for (int i = tid; i < G * 4 * SK; i += N_THREADS) sstat[i] = make_float2(0.f, 0.f);
     if (tid == 0) {
         for (int s = 0; s < G; ++s) { tc::mbar_init(&full_a[s], GROUP_THREADS); tc::mbar_init(&done_a[s], 1); }
         tc::mbar_fence_init();
@@ -111,16 +117,15 @@ __global__ void __launch_bounds__(N_THREADS, 1) cost_stem_tc_kernel(const __grid
     const int ntiles = tiles_x * tiles_y;
     const size_t P = (size_t)a.H * a.W;
     const int my_tiles = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-    const int SK = a.S * a.K;
     const int total = my_tiles * SK;
 
     if (warp == 0) {
         // =========================================== MMA issuer ===========================================
         const bool leader = tc::elect_one();
-        const uint32_t idesc = tc::idesc_f16_f32(128, NZ);
+        const uint32_t idesc = tc::idesc_f16_f32(128, NB);
         const uint32_t a_base = tc::smem_u32(sA), b_base = tc::smem_u32(sB);
-        constexpr uint32_t A_HI = tc::desc_hi(8 * 16), B_HI = tc::desc_hi(8 * 16);
-        const uint32_t b_lo_hi = tc::desc_lo(b_base, NZ * 16), b_lo_lo = tc::desc_lo(b_base + B_PLANE, NZ * 16);
+        constexpr uint32_t A_HI = tc::desc_hi(HC * 16), B_HI = tc::desc_hi(8 * 16);    // 8-row groups: one tile row / 8 B rows apart
+        const uint32_t b_lo = tc::desc_lo(b_base, NB * 16);
         for (int it = 0; it < total; ++it) {
             const int g = it % G;
             tc::mbar_wait(&full_a[g], (it / G) & 1);
@@ -128,17 +133,16 @@ __global__ void __launch_bounds__(N_THREADS, 1) cost_stem_tc_kernel(const __grid
             const uint32_t a_lo_hi = tc::desc_lo(a_base + g * A_STAGE, AROWS * 16);
             const uint32_t a_lo_lo = tc::desc_lo(a_base + g * A_STAGE + A_PLANE, AROWS * 16);
             if (leader) {
+                const uint32_t dst = tmem_base + g * ACC;
                 if (!(a.dbg & 4))
 #pragma unroll
-                for (int mb = 0; mb < 2; ++mb) {
-                    const uint32_t dst = tmem_base + (g * 2 + mb) * NZ;
+                for (int tap = 0; tap < 9; ++tap) {
 #pragma unroll
                     for (int ks = 0; ks < 2; ++ks) {
-                        const uint32_t ak = (uint32_t)((2 * ks) * AROWS + mb * 128);        // 16-byte units
-                        const uint32_t bk = (uint32_t)((2 * ks) * NZ);
-                        tc::mma_f16_parts(dst, a_lo_lo + ak, A_HI, b_lo_hi + bk, B_HI, idesc, ks != 0);
-                        tc::mma_f16_parts(dst, a_lo_hi + ak, A_HI, b_lo_lo + bk, B_HI, idesc, 1);
-                        tc::mma_f16_parts(dst, a_lo_hi + ak, A_HI, b_lo_hi + bk, B_HI, idesc, 1);
+                        const uint32_t ak = (uint32_t)((2 * ks) * AROWS + (tap / 3) * HC + (tap % 3));      // 16-byte units
+                        const uint32_t bk = (uint32_t)((tap * KC8 + 2 * ks) * NB);
+                        tc::mma_f16_parts(dst, a_lo_hi + ak, A_HI, b_lo + bk, B_HI, idesc, (tap | ks) != 0);
+                        tc::mma_f16_parts(dst, a_lo_lo + ak, A_HI, b_lo + bk, B_HI, idesc, 1);
                     }
                 }
                 tc::mma_commit(&done_a[g]);        // operand stage free AND accumulator complete
@@ -154,7 +158,6 @@ __global__ void __launch_bounds__(N_THREADS, 1) cost_stem_tc_kernel(const __grid
         const uint32_t bar_id = 1 + g;
         constexpr int ITEMS = (NPX * 8 + GROUP_THREADS - 1) / GROUP_THREADS;     // 12 (the last one partial)
         constexpr int NB = STEM_NB;
-        const int q0 = ((lt >> 3) * HC + (lt & 7)) * 16;              // output pixel lt of the tile -> halo pixel, tap (0,0)
         for (int it = g; it < total; it += G) {
             const int tile = blockIdx.x + (it / SK) * gridDim.x, v = (it % SK) / a.K, k = it % a.K;
             const float depth = depths[k];
@@ -182,7 +185,8 @@ __global__ void __launch_bounds__(N_THREADS, 1) cost_stem_tc_kernel(const __grid
                 }
                 taps[px] = rec;
             }
-            // also orders the previous fill's z reads (step 3) before this fill's stage writes
+            // (the stage and the recipes of the previous fill are free: every thread of the group arrived on full[g] after its
+            //  last read, and done[g] was observed after the MMAs' last read)
             asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(GROUP_THREADS) : "memory");
             if (pf) pp[1] = clock64();
             // ---- 2. gather, (warp - ref)^2, split, stage
@@ -266,38 +270,29 @@ __global__ void __launch_bounds__(N_THREADS, 1) cost_stem_tc_kernel(const __grid
             tc::fence_async_smem();
             tc::mbar_arrive(&full_a[g]);
             if (pf) pp[3] = clock64();
-            // ---- 3. accumulator -> z rows -> exchange through the operand stage (the MMAs have finished reading it)
+            // ---- 3. accumulator row of this thread's pixel -> t0
             tc::mbar_wait_relaxed(&done_a[g], (it / G) & 1);
             tc::tc_fence_after();
             if (pf) pp[4] = clock64();
-#pragma unroll
-            for (int mb = 0; mb < 2; ++mb) {
-                float z[32];
-                uint32_t r0, r1, r2, r3;
-                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (g * 2 + mb) * NZ;
-                tc::tmem_ld32(taddr, z);
-                asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
-                             : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(taddr + 32) : "memory");
+            float4 o;
+            {
+                uint32_t r[16];
+                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + g * ACC;
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                      "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                    : "r"(taddr)
+                    : "memory");
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                const int p = mb * 128 + quad * 32 + lane;
-                if (p < NPX) {
-#pragma unroll
-                    for (int tap = 0; tap < 8; ++tap)
-                        st4(reinterpret_cast<float*>(stage + (tap * NPX + p) * 16), make_float4(z[tap * 4], z[tap * 4 + 1], z[tap * 4 + 2], z[tap * 4 + 3]));
-                    st4(reinterpret_cast<float*>(stage + (8 * NPX + p) * 16),
-                        make_float4(__uint_as_float(r0), __uint_as_float(r1), __uint_as_float(r2), __uint_as_float(r3)));
-                }
+                o = make_float4(a.bias[0] + (__uint_as_float(r[0]) + __uint_as_float(r[8])), a.bias[1] + (__uint_as_float(r[1]) + __uint_as_float(r[9])),
+                                a.bias[2] + (__uint_as_float(r[2]) + __uint_as_float(r[10])), a.bias[3] + (__uint_as_float(r[3]) + __uint_as_float(r[11])));
             }
             tc::tc_fence_before();
-            asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(GROUP_THREADS) : "memory");
             if (pf) pp[5] = clock64();
-            float4 o = make_float4(a.bias[0], a.bias[1], a.bias[2], a.bias[3]);
-#pragma unroll
-            for (int tap = 0; tap < 9; ++tap) {
-                const float4 t = ld4(reinterpret_cast<const float*>(stage + tap * NPX * 16 + q0 + ((tap / 3) * HC + (tap % 3)) * 16));
-                o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w;
-            }
-            const int y = ty * TR + (lt >> 3), x = tx * TCOL + (lt & 7);
+            const int m = quad * 32 + lane;                             // accumulator row = pixel (m >> 3, m & 7) of the tile
+            const int y = ty * TR + (m >> 3), x = tx * TCOL + (m & 7);
             float s = 0.f, ss = 0.f;
             const int slot = k * a.S + v;                               // (plane, view) slot of t0 / stats
             if (y < a.H && x < a.W) {
@@ -311,9 +306,9 @@ __global__ void __launch_bounds__(N_THREADS, 1) cost_stem_tc_kernel(const __grid
                 ss += __shfl_xor_sync(0xffffffffu, ss, off);
             }
             if (lane == 0) {       // this warp's private accumulator: a tile contributes 32 pixels x 4 values, ~100 tiles per slot
-                float2 acc = sstat[warp - 1][slot];
+                float2 acc = sstat[(warp - 1) * SK + slot];
                 acc.x += s; acc.y += ss;
-                sstat[warp - 1][slot] = acc;
+                sstat[(warp - 1) * SK + slot] = acc;
             }
             if (pf) pp[6] = clock64();
         }
@@ -323,7 +318,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) cost_stem_tc_kernel(const __grid
     if (warp == 0) tc::tmem_dealloc<TMEM_COLS>(tmem_base);
     if (tid < a.K * a.S) {                                                   // stats[k][v][GN1][sum, sumsq]
         double s = 0.0, ss = 0.0;
-        for (int w = 0; w < G * 4; ++w) { s += (double)sstat[w][tid].x; ss += (double)sstat[w][tid].y; }
+        for (int w = 0; w < G * 4; ++w) { s += (double)sstat[w * SK + tid].x; ss += (double)sstat[w * SK + tid].y; }
         atomicAdd(a.stats + tid * 6 + 0, s);
         atomicAdd(a.stats + tid * 6 + 1, ss);
     }
@@ -336,6 +331,8 @@ unsigned long long* g_stem_prof = nullptr;
 
 extern "C" void aarmvs_debug_flags(int flags) { g_dbg = flags; }
 extern "C" void aarmvs_debug_stem_profile_buffer(void* buf) { g_stem_prof = (unsigned long long*)buf; }
+
+extern "C" int aarmvs_cost_stem_tc_max_slots(void) { return (227 * 1024 - 2048 - SMEM_FIXED) / (G * 4 * 8); }
 
 extern "C" int aarmvs_cost_stem_tc(const float* ref, const float* src, size_t view_stride, int H, int W, int S,
                                    const float* cams, const void* stem_w_f16, const float* stem_b_host,
@@ -356,7 +353,11 @@ extern "C" int aarmvs_cost_stem_tc(const float* ref, const float* src, size_t vi
     a.dbg = g_dbg;
     a.prof = g_stem_prof;
     static unsigned long long smem_ok = 0;
-    if (cudaError_t e = ensure_dyn_smem(cost_stem_tc_kernel, SMEM, smem_ok)) return (int)e;
+    constexpr int SMEM_CAP = 227 * 1024 - 2048;      // the kernel also has ~1 KB of static shared memory
+    static_assert(SMEM_FIXED + G * 4 * 8 * 8 <= SMEM_CAP, "shared memory budget");
+    if (cudaError_t e = ensure_dyn_smem(cost_stem_tc_kernel, SMEM_CAP, smem_ok)) return (int)e;
+    const int SMEM = SMEM_FIXED + G * 4 * planes * S * 8;
+    AARMVS_CHECK_ARG(SMEM <= SMEM_CAP);          // planes * S <= aarmvs_cost_stem_tc_max_slots()
     const int ntiles = ((W + TCOL - 1) / TCOL) * ((H + TR - 1) / TR);
     const int sms = aarmvs_sm_count();
     if (sms <= 0) return AARMVS_ERR_ARG;

@@ -116,7 +116,7 @@ class Engine:
         om = "omega.reweight_network"
         w["stem.w_host"] = capi.host_floats(pack.conv_taps(sd[om + ".0.0.weight"]).reshape(-1).cpu().tolist())
         w["stem.b_host"] = capi.host_floats(sd[om + ".0.0.bias"].cpu().tolist())
-        w["stem.wtc"] = pack.stem_z_f16(sd[om + ".0.0.weight"])
+        w["stem.wtc"] = pack.stem_taps_f16(sd[om + ".0.0.weight"])
         tail = pack.omega_tail(sd)
         assert tail.numel() == self.lib.aarmvs_omega_tail_floats()
         w["tail_host"] = capi.host_floats(tail.tolist())

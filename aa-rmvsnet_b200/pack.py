@@ -52,12 +52,17 @@ def taps_f16(taps, n_pad=None):
     return torch.stack([hi, lo]).contiguous()
 
 
-def stem_z_f16(w):
-    """Omega stem conv [4][32][3][3] as the B operand of the z-GEMM (csrc/cost_stem_tc.cu):
-    column n = tap * 4 + out (36 -> 48), K = the 32 input channels -> [2 planes][1][4][48][8] fp16."""
+def stem_taps_f16(w):
+    """Omega stem conv [4][32][3][3] as the B operand of pass A's implicit GEMM (csrc/cost_stem_tc.cu):
+    [9 taps][4 chunks of 8 input channels][16 rows][8] fp16, rows 0-3 = hi(w[o]), rows 8-11 = lo(w[o]), others zero."""
     cout, cin, k, _ = w.shape
-    cols = w.permute(1, 2, 3, 0).reshape(1, cin, k * k * cout)           # [1][cin][tap*4 + out]
-    return taps_f16(cols, n_pad=48)
+    taps = w.permute(2, 3, 1, 0).reshape(k * k, cin, cout)                # [tap][c][o]
+    hi = taps.half()
+    lo = (taps - hi.float()).half()
+    out = torch.zeros(k * k, cin // 8, 16, 8, dtype=torch.float16, device=w.device)
+    out[:, :, 0:cout] = hi.view(k * k, cin // 8, 8, cout).permute(0, 1, 3, 2)
+    out[:, :, 8:8 + cout] = lo.view(k * k, cin // 8, 8, cout).permute(0, 1, 3, 2)
+    return out.contiguous()
 
 
 def deconv_taps(w):

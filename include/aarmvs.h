@@ -99,11 +99,12 @@ int aarmvs_cost_stem(const float* ref, const float* src, size_t view_stride, int
 
 /* Pass A with the 3x3 stem conv on the tensor cores (tcgen05 implicit GEMM over the staged (warp - ref)^2 halo tile,
  * split-fp16 operands, fp32 accumulation in TMEM).  Arguments as aarmvs_cost_stem except
- * stem_w_f16: DEVICE [2 planes hi,lo][4 chunks of 8 input channels][48 columns][8] fp16, column = tap * 4 + output
- * channel (36 used): the conv runs as one [pixels] x [9 taps * 4] GEMM + a shifted 9-tap sum in the epilogue.
+ * stem_w_f16: DEVICE [9 taps][4 chunks of 8 input channels][16 rows][8] fp16, rows 0-3 = hi(w[o]), rows 8-11 = lo(w[o])
+ * (others zero): per tile the conv is 9 taps x 2 K-steps x (A_hi, A_lo) MMAs with N = 16, taps addressed by descriptor.
  * costv [planes][S][H*W][32] fp32 = (warp - ref)^2; costv_mode 0: unused; 1: WRITTEN here (interior pixels of each tile)
  * so that aarmvs_aggregate can skip its gather; 2: READ here instead of gathering (aarmvs_warp_cost wrote it; ref, src and
  * cams are then unused) -- the gather then runs exactly once per pixel, view and plane. */
+int aarmvs_cost_stem_tc_max_slots(void);   /* upper bound of planes * S per launch (shared-memory GroupNorm partial sums) */
 int aarmvs_cost_stem_tc(const float* ref, const float* src, size_t view_stride, int H, int W, int S, const float* cams,
                         const void* stem_w_f16, const float* stem_b_host, const float* depth_values, int d_host,
                         const int* d_dev, int planes, int align_corners, float* t0, double* stats, float* costv,
@@ -210,7 +211,7 @@ int aarmvs_tc_selftest(const void* a_f16, int a_rows, const void* b_f16, float* 
 int aarmvs_tc_mma_bench(int N, int group_rows, int reps, int a_shift_rows, int grid, long long* out, void* stream);
 
 /* Debug ablation switches for aarmvs_cost_stem_tc (results become wrong; timing experiments only): 1 skip the gather
- * loads, 2 skip the sample-position math, 4 skip the MMAs, 8 skip the z exchange.  0 = normal. */
+ * loads, 2 skip the sample-position math, 4 skip the MMAs.  0 = normal. */
 void aarmvs_debug_flags(int flags);
 /* Debug: worker group 0 of CTA 0 of subsequent aarmvs_cost_stem_tc launches records clock64 stamps per fill ([64][8]
  * uint64 device buffer; NULL switches off). */
