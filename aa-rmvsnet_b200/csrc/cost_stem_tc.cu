@@ -74,14 +74,44 @@ struct StemArgs {
     int dbg;                    // debug ablation flags (aarmvs_debug_flags): 1 skip gather loads, 2 skip recipes, 4 skip MMA
 };
 
-// Gather recipe of one staged pixel, ready to use: float offsets of the four corner lines (out-of-image corners point
-// at line 0 with weight 0, which reproduces the skipped tap exactly), and the offset of the reference pixel
-// (-1: the pixel lies outside the image, its cost is the conv's zero padding).
+// Gather recipe of one staged pixel, ready to use: BYTE offsets of the four corner lines (out-of-image corners point
+// at line 0 with weight 0, which reproduces the skipped tap exactly), the byte offset of the reference pixel
+// (-1: the pixel lies outside the image, its cost is the conv's zero padding) and whether this fill owns the pixel's
+// costv line (interior pixel of the tile, inside the image).
 struct __align__(16) TapRec {
-    int o[4];
+    unsigned o[4];
     float w[4];
-    int ref_off, pad0, pad1, pad2;
+    int ref_off, keep, pad1, pad2;
 };
+
+// Packed fp32 pairs (Blackwell FFMA2 / FMUL2 / FADD2): IEEE round-to-nearest per lane, i.e. bit-identical to the scalar
+// __fmaf_rn / __fmul_rn / __fsub_rn chains they replace, at half the issue slots.
+__device__ __forceinline__ uint64_t pk2(float lo, float hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void upk2(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ uint64_t sub2(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+
+__device__ __forceinline__ float4 ldg4b(const unsigned char* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ void sts64(uint32_t addr, uint2 v) {
+    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(v.x), "r"(v.y) : "memory");
+}
 
 __global__ void __launch_bounds__(N_THREADS, 1) cost_stem_tc_kernel(const __grid_constant__ StemArgs a) {
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -158,30 +188,37 @@ __global__ void __launch_bounds__(N_THREADS, 1) cost_stem_tc_kernel(const __grid
         const uint32_t bar_id = 1 + g;
         constexpr int ITEMS = (NPX * 8 + GROUP_THREADS - 1) / GROUP_THREADS;     // 12 (the last one partial)
         constexpr int NB = STEM_NB;
-        for (int it = g; it < total; it += G) {
-            const int tile = blockIdx.x + (it / SK) * gridDim.x, v = (it % SK) / a.K, k = it % a.K;
+        // a thread always handles the same 16-byte slice (4 channels) of its pixels: item j is pixel px0 + 16 j
+        const int c4i = lt & 7, px0 = lt >> 3;
+        const uint32_t st_thread = tc::smem_u32(stage) + (uint32_t)((c4i >> 1) * AROWS * 16 + (c4i & 1) * 8);
+        const bool keep_cv = a.costv_mode == 1;
+        // fill it = g, g + G, ... decoded incrementally as (tile slot tl, view v, plane k): it = (tl * S + v) * K + k
+        int tl = g / SK, v = (g % SK) / a.K, k = g % a.K, n = 0;
+        for (int it = g; it < total; it += G, ++n) {
+            const int tile = blockIdx.x + tl * gridDim.x;
             const float depth = depths[k];
             const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
-            const bool pf = a.prof && blockIdx.x == 0 && g == 0 && lt == 0 && it / G < 64;
-            unsigned long long* pp = a.prof + (it / G) * 8;
+            const bool pf = a.prof && blockIdx.x == 0 && g == 0 && lt == 0 && n < 64;
+            unsigned long long* pp = a.prof + n * 8;
             if (pf) pp[0] = clock64();
             // ---- 1. gather recipes (not needed when (warp-ref)^2 is streamed from costv)
             for (int px = lt; px < NPX && a.costv_mode != 2; px += GROUP_THREADS) {
                 const int r = px / HC, cc = px - r * HC;
                 const int y = ty * TR - 1 + r, x = tx * TCOL - 1 + cc;
                 TapRec rec;
-                rec.o[0] = rec.o[1] = rec.o[2] = rec.o[3] = 0;
+                rec.o[0] = rec.o[1] = rec.o[2] = rec.o[3] = 0u;
                 rec.w[0] = rec.w[1] = rec.w[2] = rec.w[3] = 0.f;
-                rec.ref_off = -1; rec.pad0 = (r >= 1 && r <= TR && cc >= 1 && cc <= TCOL) ? 1 : 0; rec.pad1 = rec.pad2 = 0;   // pad0: interior pixel
+                rec.ref_off = -1; rec.keep = 0; rec.pad1 = rec.pad2 = 0;
                 if (y >= 0 && y < a.H && x >= 0 && x < a.W && !(a.dbg & 2)) {
                     float ix, iy;
                     sweep_position(scam + v * 12, (float)x, (float)y, depth, a.W, a.H, a.align_corners != 0, ix, iy);
                     const Taps t = make_taps(ix, iy, a.W, a.H);
-                    rec.o[0] = max(t.o_nw, 0) * 32; rec.o[1] = max(t.o_ne, 0) * 32;
-                    rec.o[2] = max(t.o_sw, 0) * 32; rec.o[3] = max(t.o_se, 0) * 32;
+                    rec.o[0] = (unsigned)max(t.o_nw, 0) * 128u; rec.o[1] = (unsigned)max(t.o_ne, 0) * 128u;
+                    rec.o[2] = (unsigned)max(t.o_sw, 0) * 128u; rec.o[3] = (unsigned)max(t.o_se, 0) * 128u;
                     rec.w[0] = t.o_nw >= 0 ? t.w_nw : 0.f; rec.w[1] = t.o_ne >= 0 ? t.w_ne : 0.f;
                     rec.w[2] = t.o_sw >= 0 ? t.w_sw : 0.f; rec.w[3] = t.o_se >= 0 ? t.w_se : 0.f;
-                    rec.ref_off = (y * a.W + x) * 32;
+                    rec.ref_off = (y * a.W + x) * 128;
+                    rec.keep = (r >= 1 && r <= TR && cc >= 1 && cc <= TCOL) ? 1 : 0;
                 }
                 taps[px] = rec;
             }
@@ -220,49 +257,60 @@ __global__ void __launch_bounds__(N_THREADS, 1) cost_stem_tc_kernel(const __grid
                         }
                     }
                 }
-            } else
+            } else {
+                const unsigned char* svb = reinterpret_cast<const unsigned char*>(sv) + c4i * 16;
+                const unsigned char* refb = reinterpret_cast<const unsigned char*>(a.ref) + c4i * 16;
+                unsigned char* cvb = reinterpret_cast<unsigned char*>(costv_slot) + c4i * 16;
 #pragma unroll 1
-            for (int jb = 0; jb < ITEMS; jb += NB) {
-                float4 ta[NB], tb[NB], tcn[NB], td[NB], rv[NB], wq[NB];
-                int roff[NB], interior[NB];
+                for (int jb = 0; jb < ITEMS; jb += NB) {
+                    float4 ta[NB], tb[NB], tcn[NB], td[NB], rv[NB], wq[NB];
+                    int2 rk[NB];
 #pragma unroll
-                for (int j = 0; j < NB; ++j) {
-                    const int i = min(lt + (jb + j) * GROUP_THREADS, NPX * 8 - 1);
-                    const int px = i >> 3, c4 = (i & 7) * 4;
-                    const int4 o = *reinterpret_cast<const int4*>(taps[px].o);
-                    wq[j] = *reinterpret_cast<const float4*>(taps[px].w);
-                    roff[j] = taps[px].ref_off;
-                    interior[j] = taps[px].pad0;
-                    if (a.dbg & 1) {
-                        ta[j] = tb[j] = tcn[j] = td[j] = rv[j] = make_float4(1.f, 2.f, 3.f, 4.f);
-                    } else {
-                        ta[j] = ldg4(sv + o.x + c4);
-                        tb[j] = ldg4(sv + o.y + c4);
-                        tcn[j] = ldg4(sv + o.z + c4);
-                        td[j] = ldg4(sv + o.w + c4);
-                        rv[j] = ldg4(a.ref + max(roff[j], 0) + c4);
+                    for (int j = 0; j < NB; ++j) {
+                        const TapRec* rec = taps + min(px0 + (jb + j) * 16, NPX - 1);
+                        const uint4 o = *reinterpret_cast<const uint4*>(rec->o);
+                        wq[j] = *reinterpret_cast<const float4*>(rec->w);
+                        rk[j] = *reinterpret_cast<const int2*>(&rec->ref_off);
+                        ta[j] = ldg4b(svb + o.x);
+                        tb[j] = ldg4b(svb + o.y);
+                        tcn[j] = ldg4b(svb + o.z);
+                        td[j] = ldg4b(svb + o.w);
+                        rv[j] = ldg4b(refb + (unsigned)max(rk[j].x, 0));
                     }
-                }
 #pragma unroll
-                for (int j = 0; j < NB; ++j) {
-                    const int iraw = lt + (jb + j) * GROUP_THREADS;
-                    const int px = iraw >> 3, c4 = iraw & 7;
-                    // bilinear blend in ATen's order (see gather_taps)
-                    const float gx = __fmaf_rn(td[j].x, wq[j].w, __fmaf_rn(tcn[j].x, wq[j].z, __fmaf_rn(tb[j].x, wq[j].y, __fmul_rn(ta[j].x, wq[j].x))));
-                    const float gy = __fmaf_rn(td[j].y, wq[j].w, __fmaf_rn(tcn[j].y, wq[j].z, __fmaf_rn(tb[j].y, wq[j].y, __fmul_rn(ta[j].y, wq[j].x))));
-                    const float gz = __fmaf_rn(td[j].z, wq[j].w, __fmaf_rn(tcn[j].z, wq[j].z, __fmaf_rn(tb[j].z, wq[j].y, __fmul_rn(ta[j].z, wq[j].x))));
-                    const float gw = __fmaf_rn(td[j].w, wq[j].w, __fmaf_rn(tcn[j].w, wq[j].z, __fmaf_rn(tb[j].w, wq[j].y, __fmul_rn(ta[j].w, wq[j].x))));
-                    const float dx = gx - rv[j].x, dy = gy - rv[j].y, dz = gz - rv[j].z, dw = gw - rv[j].w;
-                    const bool in = roff[j] >= 0;
-                    const float4 cv = make_float4(in ? dx * dx : 0.f, in ? dy * dy : 0.f, in ? dz * dz : 0.f, in ? dw * dw : 0.f);
-                    if (a.costv_mode == 1 && in && interior[j] && iraw < NPX * 8)          // interior pixel of this tile, inside the image
-                        st4(costv_slot + roff[j] + c4 * 4, cv);
-                    uint2 hi, lo;
-                    tc::split4_f16(cv, hi, lo);
-                    if (iraw < NPX * 8) {
-                        const size_t off = ((size_t)(c4 >> 1) * AROWS + px) * 16 + (c4 & 1) * 8;
-                        *reinterpret_cast<uint2*>(stage + off) = hi;
-                        *reinterpret_cast<uint2*>(stage + A_PLANE + off) = lo;
+                    for (int j = 0; j < NB; ++j) {
+                        const int pxr = px0 + (jb + j) * 16;
+                        // bilinear blend in ATen's order (see gather_taps): fma(se, w, fma(sw, w, fma(ne, w, nw * w))), two channels
+                        // per instruction
+                        const uint64_t w0 = pk2(wq[j].x, wq[j].x), w1 = pk2(wq[j].y, wq[j].y), w2 = pk2(wq[j].z, wq[j].z), w3 = pk2(wq[j].w, wq[j].w);
+                        const uint64_t g01 = fma2(pk2(td[j].x, td[j].y), w3, fma2(pk2(tcn[j].x, tcn[j].y), w2,
+                                                  fma2(pk2(tb[j].x, tb[j].y), w1, mul2(pk2(ta[j].x, ta[j].y), w0))));
+                        const uint64_t g23 = fma2(pk2(td[j].z, td[j].w), w3, fma2(pk2(tcn[j].z, tcn[j].w), w2,
+                                                  fma2(pk2(tb[j].z, tb[j].w), w1, mul2(pk2(ta[j].z, ta[j].w), w0))));
+                        // outside the image the cost is the conv's zero padding: d * 0 = +-0 exactly (finite features), d * 1 = d
+                        const float inf_ = rk[j].x >= 0 ? 1.0f : 0.0f;
+                        const uint64_t in2 = pk2(inf_, inf_);
+                        const uint64_t d01 = mul2(sub2(g01, pk2(rv[j].x, rv[j].y)), in2), d23 = mul2(sub2(g23, pk2(rv[j].z, rv[j].w)), in2);
+                        const uint64_t c01 = mul2(d01, d01), c23 = mul2(d23, d23);
+                        float4 cv;
+                        upk2(c01, cv.x, cv.y);
+                        upk2(c23, cv.z, cv.w);
+                        if (keep_cv && rk[j].y && pxr < NPX)             // this fill owns the pixel's costv line
+                            *reinterpret_cast<float4*>(cvb + (unsigned)rk[j].x) = cv;
+                        // fp16 split as tc::split4_f16: hi = top 11 mantissa bits, lo = fp16(x - hi)
+                        const float h0 = __uint_as_float(__float_as_uint(cv.x) & 0xFFFFE000u), h1 = __uint_as_float(__float_as_uint(cv.y) & 0xFFFFE000u);
+                        const float h2 = __uint_as_float(__float_as_uint(cv.z) & 0xFFFFE000u), h3 = __uint_as_float(__float_as_uint(cv.w) & 0xFFFFE000u);
+                        float l0, l1, l2, l3;
+                        upk2(sub2(c01, pk2(h0, h1)), l0, l1);
+                        upk2(sub2(c23, pk2(h2, h3)), l2, l3);
+                        const __half2 ha = __floats2half2_rn(h0, h1), hb = __floats2half2_rn(h2, h3);
+                        const __half2 la = __floats2half2_rn(l0, l1), lb = __floats2half2_rn(l2, l3);
+                        const uint2 hi = make_uint2(*reinterpret_cast<const uint32_t*>(&ha), *reinterpret_cast<const uint32_t*>(&hb));
+                        const uint2 lo = make_uint2(*reinterpret_cast<const uint32_t*>(&la), *reinterpret_cast<const uint32_t*>(&lb));
+                        if (pxr < NPX) {
+                            sts64(st_thread + pxr * 16, hi);
+                            sts64(st_thread + A_PLANE + pxr * 16, lo);
+                        }
                     }
                 }
             }
@@ -271,7 +319,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) cost_stem_tc_kernel(const __grid
             tc::mbar_arrive(&full_a[g]);
             if (pf) pp[3] = clock64();
             // ---- 3. accumulator row of this thread's pixel -> t0
-            tc::mbar_wait_relaxed(&done_a[g], (it / G) & 1);
+            tc::mbar_wait_relaxed(&done_a[g], n & 1);
             tc::tc_fence_after();
             if (pf) pp[4] = clock64();
             float4 o;
@@ -311,6 +359,8 @@ __global__ void __launch_bounds__(N_THREADS, 1) cost_stem_tc_kernel(const __grid
                 sstat[(warp - 1) * SK + slot] = acc;
             }
             if (pf) pp[6] = clock64();
+            k += G;
+            while (k >= a.K) { k -= a.K; if (++v == a.S) { v = 0; ++tl; } }
         }
     }
     tc::tc_fence_before();

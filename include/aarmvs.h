@@ -210,8 +210,7 @@ int aarmvs_tc_selftest(const void* a_f16, int a_rows, const void* b_f16, float* 
  * with 8-row groups `group_rows` rows apart, start row advancing by a_shift_rows per instruction) on `grid` CTAs. */
 int aarmvs_tc_mma_bench(int N, int group_rows, int reps, int a_shift_rows, int grid, long long* out, void* stream);
 
-/* Debug ablation switches for aarmvs_cost_stem_tc (results become wrong; timing experiments only): 1 skip the gather
- * loads, 2 skip the sample-position math, 4 skip the MMAs.  0 = normal. */
+/* Debug ablation switches for aarmvs_cost_stem_tc (results become wrong; timing experiments only): 2 skip the sample-position math, 4 skip the MMAs.  0 = normal. */
 void aarmvs_debug_flags(int flags);
 /* Debug: worker group 0 of CTA 0 of subsequent aarmvs_cost_stem_tc launches records clock64 stamps per fill ([64][8]
  * uint64 device buffer; NULL switches off). */

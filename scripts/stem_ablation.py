@@ -20,7 +20,7 @@ st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 def run():
     eng.cost_stem(_ptr(ws["feat"]), _ptr(ws["feat"], P * 32), P * 32, H, W, S, _ptr(ws["cams"]), w, _ptr(ws["depths"]), 100, None, K,
                   _ptr(ws["t0"]), _ptr(ws["psums"]), st)
-for flags, name in ((0, "full"), (1, "no gather loads"), (2, "no recipe math"), (3, "no loads, no recipes"), (4, "no MMA"), (7, "no loads/recipes/MMA")):
+for flags, name in ((0, "full"), (2, "no recipe math"), (4, "no MMA"), (6, "no recipes, no MMA")):
     lib.aarmvs_debug_flags(flags)
     run(); torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
