@@ -79,7 +79,8 @@ _lib = None
 
 
 def library_path():
-    return _build.LIB
+    """In-tree library; AARMVS_LIB overrides it (kernel tuning experiments with differently compiled variants)."""
+    return os.environ.get("AARMVS_LIB") or _build.LIB
 
 
 def load(build_if_missing=True):

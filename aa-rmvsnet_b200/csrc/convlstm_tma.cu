@@ -23,11 +23,11 @@
 // (ky * 10 + kx pixels further) into the same staged data -- no im2col copy, each input pixel is staged once per tile.
 // SBO = 10 * 16 B, LBO = 180 * 16 B (validated by aarmvs_tc_selftest).
 //
-// Warp roles (persistent CTA, one per SM): warps 0-7 epilogue (TMEM -> gates -> c, h), warp 8 TMEM allocation + the
-// single MMA-issuing thread, warp 9 the TMA producer.  NST operand stages (producer <-> MMA) and 2 TMEM accumulators
+// Warp roles (persistent CTA, one per SM): warps 0-15 epilogue (TMEM -> gates -> c, h; four warps per TMEM lane quadrant,
+// each a quarter of the gate columns), warp 16 TMEM allocation + the single MMA-issuing thread, warp 17 the TMA producer.  NST operand stages (producer <-> MMA) and 2 TMEM accumulators
 // (MMA <-> epilogue), all hand-offs through mbarriers; tcgen05.commit releases operand stages and publishes
 // accumulators.  The cell state c is private to this kernel and kept in a tile-blocked layout
-// [tile][half][4-channel group][128 px][4] so that every access is a fully used 128-byte line.
+// [tile][quarter of the hidden channels][128 px][CH/4] so that every access is a fully used 128-byte line.
 #include <cuda.h>
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -37,8 +37,8 @@ namespace {
 
 constexpr int TR = 16, TCOL = 8, HR = TR + 2, HC = TCOL + 2, NPX = HR * HC;   // 180 staged pixels per tile
 constexpr int CHUNK_BYTES = NPX * 16;                                         // one 8-channel chunk of one fp16 plane
-constexpr int N_EPI_WARPS = 8, MMA_WARP = N_EPI_WARPS, TMA_WARP = MMA_WARP + 1;
-constexpr int N_THREADS = (N_EPI_WARPS + 2) * 32;                             // 320
+constexpr int N_EPI_WARPS = 16, MMA_WARP = N_EPI_WARPS, TMA_WARP = MMA_WARP + 1;
+constexpr int N_THREADS = (N_EPI_WARPS + 2) * 32;                             // 576
 
 struct alignas(64) CellArgs {
     CUtensorMap map[3];         // per source: (W*8 halfs, H, chunks, 2 = hi/lo, ping-pong halves), box (80, 18, chunks, 1, 1)
@@ -50,7 +50,7 @@ struct alignas(64) CellArgs {
     const __half* weight;       // [9 taps][KC8][2 (hi, lo)][NG][8] fp16
     const float* bias;          // [NG], order [hidden channel][i,f,o,g]
     __half* h_planes;           // [2 ping-pong][2][CH/8][H][W][8]: plane d writes half d & 1
-    float* c_blocked;           // [tiles][2 halves][CH/8][128][4]
+    float* c_blocked;           // [tiles][4 quarters][128][CH/4]
     float* h_f32;               // optional [2 ping-pong][H*W][CH] fp32 copy of h (deconvolution / head inputs, operator seam)
     __half* pooled;             // optional [2][CH/8][H/2][W/2][8]: operand planes of max_pool2d(h, 2)
     int d_host;
@@ -85,6 +85,22 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
+
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// e^{-x} and e^{-2x} in the exp2 domain, clamped so that the product of four (1 + e) terms stays finite (2^120):
+// sigmoid(x) >= 2^-30 instead of underflowing further, an absolute error below 1e-9.
+__device__ __forceinline__ float exp_neg(float x) { return tc::ex2_approx(fminf(-1.4426950408889634f * x, 30.0f)); }
+__device__ __forceinline__ float exp_neg2(float x) { return tc::ex2_approx(fminf(-2.8853900817779268f * x, 30.0f)); }
 
 template <int KSTEPS, int NG, int NST>
 __global__ void __launch_bounds__(N_THREADS, 1) convlstm_tma_kernel(const __grid_constant__ CellArgs a) {
@@ -180,23 +196,26 @@ __global__ void __launch_bounds__(N_THREADS, 1) convlstm_tma_kernel(const __grid
         constexpr uint32_t A_HI = tc::desc_hi(HC * 16), B_HI = tc::desc_hi(8 * 16);
         const uint32_t b_lo = tc::desc_lo(b_base, 2 * NG * 16);       // [W_hi | W_lo] stacked along N: rows 0..NG-1 hi, NG..2NG-1 lo
         tc::mbar_wait(&w_bar, 0);
+        // The barriers of tile i+1 are resolved while the MMAs of tile i are still being issued (the issuing thread is
+        // throttled by the tensor pipe anyway), so the pipe does not drain between tiles: neither barrier of tile i+1
+        // depends on tile i (its stage was released NST tiles earlier, its accumulator two tiles earlier).
         int it = 0;
+        if ((int)blockIdx.x < ntiles) {
+            tc::mbar_wait(&full_a[0], 0);
+            tc::mbar_wait(&tmem_empty[0], 1);
+            tc::tc_fence_after();
+        }
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
             const int st = it % NST, ab = it & 1;
             const bool pf = a.prof && blockIdx.x == 0 && leader && it < 64;
-            if (pf) a.prof[it * 12 + 4] = clock64();
-            tc::mbar_wait(&full_a[st], (it / NST) & 1);
-            if (pf) a.prof[it * 12 + 5] = clock64();
-            tc::mbar_wait(&tmem_empty[ab], ((it >> 1) & 1) ^ 1);
-            tc::tc_fence_after();
-            if (pf) a.prof[it * 12 + 6] = clock64();
+            if (pf) a.prof[it * 12 + 4] = a.prof[it * 12 + 5] = a.prof[it * 12 + 6] = clock64();
             const uint32_t dst = tmem_base + ab * 2 * NG;
             const uint32_t a_lo_hi = tc::desc_lo(a_base + st * C::A_STAGE, NPX * 16);
             const uint32_t a_lo_lo = tc::desc_lo(a_base + st * C::A_STAGE + C::A_PLANE, NPX * 16);
-            if (leader) {
-                if (!(a.dbg & 8))
+            const bool more = tile + (int)gridDim.x < ntiles;
 #pragma unroll
-                for (int tap = 0; tap < 9; ++tap) {
+            for (int tap = 0; tap < 9; ++tap) {
+                if (leader && !(a.dbg & 8)) {
 #pragma unroll
                     for (int ks = 0; ks < KSTEPS; ++ks) {
                         const uint32_t ak = (uint32_t)(((2 * ks) * NPX + (tap / 3) * HC + (tap % 3)) * 16) >> 4;
@@ -207,6 +226,13 @@ __global__ void __launch_bounds__(N_THREADS, 1) convlstm_tma_kernel(const __grid
                         tc::mma_f16_parts(dst, a_lo_lo + ak, A_HI, b_lo + bk, B_HI, idesc1, 1);
                     }
                 }
+                if (tap == 5 && more) {          // next tile's operands and accumulator
+                    tc::mbar_wait(&full_a[(it + 1) % NST], ((it + 1) / NST) & 1);
+                    tc::mbar_wait(&tmem_empty[(it + 1) & 1], (((it + 1) >> 1) & 1) ^ 1);
+                    tc::tc_fence_after();
+                }
+            }
+            if (leader) {
                 tc::mma_commit(&empty_a[st]);          // operand stage free once these MMAs have read it
                 tc::mma_commit(&tmem_full[ab]);        // accumulator complete
             }
@@ -215,75 +241,104 @@ __global__ void __launch_bounds__(N_THREADS, 1) convlstm_tma_kernel(const __grid
         }
     } else {
         // =========================================== epilogue ===========================================
-        const int q = warp & 3, hf = warp >> 2;                  // TMEM lane quadrant, half of the gate columns
-        constexpr int NCOL = NG / 2, NHC = CH / 2, NJ4 = NHC / 4; // columns / hidden channels / float4 groups per thread
+        const int q = warp & 3, part = warp >> 2;                // TMEM lane quadrant, quarter of the gate columns
+        constexpr int NCOL = NG / 4, NHC = CH / 4;               // gate columns / hidden channels per thread: 16 / 4 or 8 / 2
         const int m = q * 32 + lane;
         const size_t P = (size_t)a.H * a.W;
         __half* hb = a.h_planes + (size_t)(d & 1) * 2 * CHK * P * 8;
         float* hf32 = a.h_f32 ? a.h_f32 + (size_t)(d & 1) * P * CH : nullptr;
+        // this thread's NHC channels inside the operand planes: chunk (8 channels) and offset inside its 16-byte element
+        const int chunk = (part * NHC) >> 3, sub = (part * NHC) & 7;
+        float bias_r[NCOL];
+#pragma unroll
+        for (int j = 0; j < NCOL; ++j) bias_r[j] = s_bias[part * NCOL + j];
+        // previous cell state of this thread's pixel of tile `t` (zero at plane 0 and outside the image)
+        auto load_c = [&](int t, float (&cv)[NHC]) {
+            const int ty = t / tiles_x, tx = t - ty * tiles_x;
+            const bool ok = t < ntiles && ty * TR + (m >> 3) < a.H && tx * TCOL + (m & 7) < a.W && d != 0 && !(a.dbg & 4);
+            const float* p = a.c_blocked + (((size_t)t * 4 + part) * 128 + m) * NHC;
+            if constexpr (NHC == 4) {
+                const float4 v = ok ? ld4(p) : make_float4(0.f, 0.f, 0.f, 0.f);
+                cv[0] = v.x; cv[1] = v.y; cv[2] = v.z; cv[3] = v.w;
+            } else {
+                const float2 v = ok ? *reinterpret_cast<const float2*>(p) : make_float2(0.f, 0.f);
+                cv[0] = v.x; cv[1] = v.y;
+            }
+        };
+        float cnext[NHC];
+        load_c(blockIdx.x, cnext);
         int it = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
             const int ab = it & 1;
             const bool pf = a.prof && blockIdx.x == 0 && tid == 0 && it < 64;
-            // this thread's pixel and its previous cell state: requested BEFORE waiting for the accumulator so that the
-            // global-load latency overlaps the MMAs of this tile
             const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
             const int y = ty * TR + (m >> 3), x = tx * TCOL + (m & 7);
             const bool valid = y < a.H && x < a.W && !(a.dbg & 4);
             const size_t pix = valid ? (size_t)y * a.W + x : 0;
-            float4* cp = reinterpret_cast<float4*>(a.c_blocked) + ((size_t)tile * 2 + hf) * NJ4 * 128 + m;
+            float* cp = a.c_blocked + (((size_t)tile * 4 + part) * 128 + m) * NHC;
             float cprev[NHC], cn[NHC], hn[NHC];
 #pragma unroll
-            for (int j = 0; j < NJ4; ++j) {
-                const float4 t = (d == 0 || !valid) ? make_float4(0.f, 0.f, 0.f, 0.f) : cp[j * 128];
-                cprev[4 * j] = t.x; cprev[4 * j + 1] = t.y; cprev[4 * j + 2] = t.z; cprev[4 * j + 3] = t.w;
-            }
+            for (int j = 0; j < NHC; ++j) cprev[j] = cnext[j];
+            // the NEXT tile's state is requested now: its global-load latency hides behind this tile's gate math (with the
+            // small-K cells the accumulator of the next tile is ready before this one's epilogue ends)
+            load_c(tile + gridDim.x, cnext);
             if (pf) a.prof[it * 12 + 8] = clock64();
             tc::mbar_wait_relaxed(&tmem_full[ab], (it >> 1) & 1);
             tc::tc_fence_after();
             if (pf) a.prof[it * 12 + 9] = clock64();
             float g[NCOL], g2[NCOL];
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + ab * 2 * NG + hf * NCOL;
-            if constexpr (NCOL == 32) { tc::tmem_ld32(taddr, g); tc::tmem_ld32(taddr + NG, g2); }
-            else { tmem_ld16(taddr, g); tmem_ld16(taddr + NG, g2); }
-#pragma unroll
-            for (int j = 0; j < NCOL; ++j) g[j] += g2[j];            // (hi*hi + lo*hi) + hi*lo
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + ab * 2 * NG + part * NCOL;
+            if constexpr (NCOL == 16) { tmem_ld16(taddr, g); tmem_ld16(taddr + NG, g2); }
+            else { tmem_ld8(taddr, g); tmem_ld8(taddr + NG, g2); }
             tc::tc_fence_before();
             tc::mbar_arrive(&tmem_empty[ab]);                    // accumulator is in registers: release it
             if (pf) a.prof[it * 12 + 10] = clock64();
-            // pixels outside the image (ragged tiles) see zero operands: finite values that are never stored
+            // pixels outside the image (ragged tiles) see zero operands: finite values that are never stored.
+            // Gates with ONE reciprocal per hidden channel: with a = 1 + e^-i, b = 1 + e^-f, c = 1 + e^-o, d = 1 + e^-2g and
+            // r = 1 / (abcd):  sigmoid(i) = r*cd*b, sigmoid(f) = r*cd*a, sigmoid(o) = r*ab*d, tanh(g) = 2*r*ab*c - 1
+            // (MUFU.EX2 / MUFU.RCP are quarter-rate: 6.5 instead of 10 per channel; relative error a few ulp).
+            float ec[NHC], go[NHC];
 #pragma unroll
             for (int j = 0; j < NHC; ++j) {
-                const float* bb = s_bias + hf * NCOL + j * 4;
-                const float gi = tc::fast_sigmoid(g[j * 4 + 0] + bb[0]);
-                const float gf = tc::fast_sigmoid(g[j * 4 + 1] + bb[1]);
-                const float go = tc::fast_sigmoid(g[j * 4 + 2] + bb[2]);
-                const float gg = tc::fast_tanh(g[j * 4 + 3] + bb[3]);
+                const float* bb = bias_r + j * 4;
+                const float pa = 1.0f + exp_neg((g[j * 4 + 0] + g2[j * 4 + 0]) + bb[0]);      // (hi*hi + lo*hi) + hi*lo, + bias
+                const float pb = 1.0f + exp_neg((g[j * 4 + 1] + g2[j * 4 + 1]) + bb[1]);
+                const float pc = 1.0f + exp_neg((g[j * 4 + 2] + g2[j * 4 + 2]) + bb[2]);
+                const float pd = 1.0f + exp_neg2((g[j * 4 + 3] + g2[j * 4 + 3]) + bb[3]);
+                const float pab = pa * pb, pcd = pc * pd;
+                const float r = tc::rcp_approx(pab * pcd);
+                const float rab = r * pcd, rcd = r * pab;                                    // 1/(ab), 1/(cd)
+                const float gi = rab * pb, gf = rab * pa;
+                go[j] = rcd * pd;
+                const float gg = fmaf(2.0f, rcd * pc, -1.0f);
                 cn[j] = __fadd_rn(__fmul_rn(gf, cprev[j]), __fmul_rn(gi, gg));
-                hn[j] = go * tc::fast_tanh(cn[j]);
+                ec[j] = 1.0f + exp_neg2(cn[j]);
+            }
+#pragma unroll
+            for (int j = 0; j < NHC; j += 2) {           // tanh(c') of two channels with one reciprocal
+                const float r = tc::rcp_approx(ec[j] * ec[j + 1]);
+                hn[j] = go[j] * fmaf(2.0f, r * ec[j + 1], -1.0f);
+                hn[j + 1] = go[j + 1] * fmaf(2.0f, r * ec[j], -1.0f);
             }
             if (valid) {
-#pragma unroll
-                for (int j = 0; j < NJ4; ++j) cp[j * 128] = make_float4(cn[4 * j], cn[4 * j + 1], cn[4 * j + 2], cn[4 * j + 3]);
-                if constexpr (NHC == 8) {          // this thread owns chunk hf of the pixel: one 16-byte element per plane
-                    uint2 h0, l0, h1, l1;
-                    tc::split4_f16(make_float4(hn[0], hn[1], hn[2], hn[3]), h0, l0);
-                    tc::split4_f16(make_float4(hn[4], hn[5], hn[6], hn[7]), h1, l1);
-                    *reinterpret_cast<uint4*>(hb + ((size_t)hf * P + pix) * 8) = make_uint4(h0.x, h0.y, h1.x, h1.y);
-                    *reinterpret_cast<uint4*>(hb + ((size_t)(CHK + hf) * P + pix) * 8) = make_uint4(l0.x, l0.y, l1.x, l1.y);
-                } else {                           // CH = 8: half a chunk per thread
+                if constexpr (NHC == 4) {
+                    st4(cp, make_float4(cn[0], cn[1], cn[2], cn[3]));
                     uint2 h0, l0;
                     tc::split4_f16(make_float4(hn[0], hn[1], hn[2], hn[3]), h0, l0);
-                    *reinterpret_cast<uint2*>(hb + pix * 8 + hf * 4) = h0;
-                    *reinterpret_cast<uint2*>(hb + (P + pix) * 8 + hf * 4) = l0;
-                }
-                if (hf32) {
-#pragma unroll
-                    for (int j = 0; j < NHC; j += 4)
-                        st4(hf32 + pix * CH + hf * NHC + j, make_float4(hn[j], hn[j + 1], hn[j + 2], hn[j + 3]));
+                    *reinterpret_cast<uint2*>(hb + ((size_t)chunk * P + pix) * 8 + sub) = h0;
+                    *reinterpret_cast<uint2*>(hb + ((size_t)(CHK + chunk) * P + pix) * 8 + sub) = l0;
+                    if (hf32) st4(hf32 + pix * CH + part * NHC, make_float4(hn[0], hn[1], hn[2], hn[3]));
+                } else {
+                    *reinterpret_cast<float2*>(cp) = make_float2(cn[0], cn[1]);
+                    __half hh0, hl0, hh1, hl1;
+                    tc::split_f16_trunc(hn[0], hh0, hl0);
+                    tc::split_f16_trunc(hn[1], hh1, hl1);
+                    *reinterpret_cast<__half2*>(hb + ((size_t)chunk * P + pix) * 8 + sub) = __halves2half2(hh0, hh1);
+                    *reinterpret_cast<__half2*>(hb + ((size_t)(CHK + chunk) * P + pix) * 8 + sub) = __halves2half2(hl0, hl1);
+                    if (hf32) *reinterpret_cast<float2*>(hf32 + pix * CH + part * NHC) = make_float2(hn[0], hn[1]);
                 }
             }
-            if constexpr (NHC == 8) {
+            if constexpr (NHC == 4) {
                 if (a.pooled) {                    // max_pool2d(h, 2) (drmvsnet.py:148,152): the 2x2 block is lanes ^1, ^8 of this warp
                     float pm[NHC];
 #pragma unroll
@@ -293,11 +348,10 @@ __global__ void __launch_bounds__(N_THREADS, 1) convlstm_tma_kernel(const __grid
                     }
                     if (valid && !(lane & 9)) {
                         const size_t P4 = P >> 2, pp = (size_t)(y >> 1) * (a.W >> 1) + (x >> 1);
-                        uint2 h0, l0, h1, l1;
+                        uint2 h0, l0;
                         tc::split4_f16(make_float4(pm[0], pm[1], pm[2], pm[3]), h0, l0);
-                        tc::split4_f16(make_float4(pm[4], pm[5], pm[6], pm[7]), h1, l1);
-                        *reinterpret_cast<uint4*>(a.pooled + ((size_t)hf * P4 + pp) * 8) = make_uint4(h0.x, h0.y, h1.x, h1.y);
-                        *reinterpret_cast<uint4*>(a.pooled + ((size_t)(CHK + hf) * P4 + pp) * 8) = make_uint4(l0.x, l0.y, l1.x, l1.y);
+                        *reinterpret_cast<uint2*>(a.pooled + ((size_t)chunk * P4 + pp) * 8 + sub) = h0;
+                        *reinterpret_cast<uint2*>(a.pooled + ((size_t)(CHK + chunk) * P4 + pp) * 8 + sub) = l0;
                     }
                 }
             }

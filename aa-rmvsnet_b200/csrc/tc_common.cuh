@@ -185,6 +185,13 @@ __device__ __forceinline__ void split_f16(float x, __half& hi, __half& lo) {
     lo = __float2half_rn(x - __half2float(hi));
 }
 
+// One value, the same truncating split as split4_f16.
+__device__ __forceinline__ void split_f16_trunc(float x, __half& hi, __half& lo) {
+    const float h = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+    hi = __float2half_rn(h);
+    lo = __float2half_rn(x - h);
+}
+
 // Four fp32 values -> packed fp16 (hi) and (lo) pairs.  hi = x with the low 13 mantissa bits cleared (exactly an fp16
 // value in the normal range), lo = x - hi (exact in fp32, <= 2^-11 |x|, rounded to fp16): x ~= hi + lo to 2^-22 |x|.
 // 3.5 instructions per element (LOP, FADD, 2 x half of a packed F2F) instead of 5+ for round-to-nearest splitting.

@@ -474,17 +474,24 @@ aggregate_stream_kernel(const float* __restrict__ costv, int S, int K, size_t P,
 #pragma unroll
         for (int u = 0; u < AGS_PX; ++u) {
             const size_t i = i0 + u * stride;
-            if (i >= total) continue;
             const float4 r = make_float4(-__fdiv_rn(acc[u].x, s_den), -__fdiv_rn(acc[u].y, s_den),
                                          -__fdiv_rn(acc[u].z, s_den), -__fdiv_rn(acc[u].w, s_den));
             if (cost_planes) {       // fp16 (hi, lo) operand planes [K][2][4 chunks][P][8] for the TMA-fed ConvLSTM cell 0
-                const size_t k = i / P, p = i - k * P;
+                // lanes (sub, sub ^ 1) hold the two halves of one 8-channel chunk: the even lane stores the chunk's 16-byte hi
+                // element, the odd lane its lo element (the whole 8-lane group is in or out of range together)
                 uint2 hi, lo;
                 tc::split4_f16(r, hi, lo);
-                const size_t off = ((k * 8 + (sub >> 1)) * P + p) * 8 + (sub & 1) * 4;
-                *reinterpret_cast<uint2*>(cost_planes + off) = hi;
-                *reinterpret_cast<uint2*>(cost_planes + off + 4 * P * 8) = lo;
-            } else {
+                const bool odd = sub & 1;
+                const uint2 give = odd ? hi : lo;
+                uint2 got;
+                got.x = __shfl_xor_sync(0xffffffffu, give.x, 1);
+                got.y = __shfl_xor_sync(0xffffffffu, give.y, 1);
+                if (i < total) {
+                    const size_t k = i / P, p = i - k * P;
+                    const size_t off = ((k * 8 + (odd ? 4 : 0) + (sub >> 1)) * P + p) * 8;
+                    *reinterpret_cast<uint4*>(cost_planes + off) = odd ? make_uint4(got.x, got.y, lo.x, lo.y) : make_uint4(hi.x, hi.y, got.x, got.y);
+                }
+            } else if (i < total) {
                 st4(cost + i * 32 + sub * 4, r);
             }
         }

@@ -96,12 +96,12 @@ def _block_state(c, H, W):
     ty, tx = (H + 15) // 16, (W + 7) // 8
     full = c.new_zeros(ty * 16, tx * 8, ch)
     full[:H, :W] = c.view(H, W, ch)
-    return full.view(ty, 16, tx, 8, 2, ch // 8, 4).permute(0, 2, 4, 5, 1, 3, 6).contiguous().view(-1)
+    return full.view(ty, 16, tx, 8, 4, ch // 4).permute(0, 2, 4, 1, 3, 5).contiguous().view(-1)
 
 
 def _unblock_state(cb, H, W, ch):
     ty, tx = (H + 15) // 16, (W + 7) // 8
-    full = cb.view(ty, tx, 2, ch // 8, 16, 8, 4).permute(0, 4, 1, 5, 2, 3, 6).reshape(ty * 16, tx * 8, ch)
+    full = cb.view(ty, tx, 4, 16, 8, ch // 4).permute(0, 3, 1, 4, 2, 5).reshape(ty * 16, tx * 8, ch)
     return full[:H, :W].reshape(H * W, ch).contiguous()
 
 

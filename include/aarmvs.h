@@ -160,8 +160,8 @@ typedef struct aarmvs_plane_src {
 int aarmvs_split_planes(const aarmvs_conv_src* src, int H, int W, void* planes, void* stream);
 
 /* Floats of the cell-state buffer of aarmvs_convlstm_cell_tc: c lives in a tile-blocked layout private to the kernel,
- * [tiles of 16 rows x 8 columns, row-major over ceil(H/16) x ceil(W/8)][2 halves of the hidden channels][hidden/8]
- * [128 pixels of the tile, row-major][4 channels]  (every access of the epilogue is a fully used 128-byte line). */
+ * [tiles of 16 rows x 8 columns, row-major over ceil(H/16) x ceil(W/8)][4 quarters of the hidden channels]
+ * [128 pixels of the tile, row-major][hidden/4 channels]  (every access of the epilogue is a fully used 128-byte line). */
 size_t aarmvs_cell_state_floats(int H, int W, int hidden);
 
 /* The same cell on the tensor cores (tcgen05.mma kind::f16, fp32 accumulation in TMEM), fed by TMA from operand planes.
