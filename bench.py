@@ -277,19 +277,19 @@ def run_ours(args):
             "head_wta": ("head_wta_kernel", "hbm", 44 * P),
         }
         for i, name in enumerate(("cell0", "cell1", "cell2", "cell3", "cell4")):
-            kernels[name] = (f"convlstm_tc_kernel (ConvLSTM cell {i}: tcgen05 implicit GEMM, split-fp16 operands, "
+            kernels[name] = (f"convlstm_tma_kernel (ConvLSTM cell {i}: TMA-fed tcgen05 implicit GEMM, split-fp16 operands, "
                              "useful FLOPs counted once)", "tensor", CELL_FLOP_PER_PX[name] * P)
         top = max(kernels, key=lambda k: st[k])
         kname, bound, work = kernels[top]
         batched = top in ("cost_stem", "omega_stats", "aggregate")       # one launch covers plane_batch planes
         per_launch = eng.plane_batch if batched else 1
         # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu captures (cfg2 only)
-        traffic_cfg2 = {"cost_stem": 14.818e9, "aggregate": 15.026e9, "omega_stats": 2.92e9, "cell0": 0.693e9, "cell1": 0.217e9,
-                        "cell2": 0.046e9, "cell3": 0.147e9, "cell4": 0.464e9, "head_wta": 0.083e9}   # profiles/r01f_*
+        traffic_cfg2 = {"cost_stem": 14.810e9, "aggregate": 15.028e9, "omega_stats": 2.92e9, "cell0": 0.721e9, "cell1": 0.112e9,
+                        "cell2": 0.023e9, "cell3": 0.165e9, "cell4": 0.511e9, "head_wta": 0.085e9}   # profiles/r01k_*
         roofline = {"kernel": kname, "bound": bound, "planes_per_launch": per_launch, "ms_per_launch": st[top] * per_launch,
                     "algorithmic_work_per_launch": work * per_launch,
                     "traffic": traffic_cfg2.get(top) if args.workload == "cfg2" else None,
-                    "traffic_source": "ncu --set full, profiles/r01f_passes_AD.txt / r01f_recurrence.txt (pass A includes the 11.6 GB "
+                    "traffic_source": "ncu --set full, profiles/r01k_passes_AD.txt / r01k_recurrence.txt (pass A includes the 11.6 GB "
                                       "costv store per 8-plane launch that replaces pass D's second gather)"}
         if bound == "hbm":
             roofline.update({"achieved": work / (st[top] * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
@@ -302,7 +302,12 @@ def run_ours(args):
             "stage_ms_per_plane": {k: round(v, 4) for k, v in st.items()},
             "featnet_ms_per_depth_map": featnet_ms, "featnet_ms_per_view": featnet_ms / N,
             "recurrence": {"ms_per_plane": rec_ms, "achieved_tflops": FLOP_PER_PX_PLANE * P / (rec_ms * 1e-3) / 1e12,
-                           "frac_of_bf16_sustained": FLOP_PER_PX_PLANE * P / (rec_ms * 1e-3) / 1e12 / pk["bf16_tflops_sustained"]},
+                           "frac_of_bf16_sustained": FLOP_PER_PX_PLANE * P / (rec_ms * 1e-3) / 1e12 / pk["bf16_tflops_sustained"],
+                           "note": "useful FLOPs counted once; the split-fp16 operands execute 3x as many",
+                           # hardware counter of the committed ncu capture (cfg2), not measured in this run
+                           "tensor_pipe_active_pct_ncu": {"cell0": 71.8, "cell1": 56.8, "cell2": 41.8, "cell3": 62.5, "cell4": 42.3,
+                                                          "source": "profiles/r01k_recurrence.txt, sm__pipe_tensor_cycles_active"}
+                           if args.workload == "cfg2" else None},
             "warp_aggregate": {"bound": "hbm", "ms_per_plane": wa_ms, "algorithmic_bytes": wa_bytes,
                                "achieved": wa_bytes / (wa_ms * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
                                "frac": wa_bytes / (wa_ms * 1e-3) / 1e9 / pk["hbm_gbs"]},
