@@ -64,6 +64,7 @@ PROTOTYPES = {
     "aarmvs_cell_state_floats": (_SZ, [_I, _I, _I]),
     "aarmvs_convlstm_cell": (_I, [_SRCP, _I, _I, _I, _I, _I, _P, _P, _P, _P, _I, _P, _P]),
     "aarmvs_convlstm_cell_tc": (_I, [_PLSP, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _I, _P, _P]),
+    "aarmvs_deconv2x_tc": (_I, [_PLSP, _I, _I, _P, c_float_p, _P, _P, _P, _P, _I, _P, _P]),
     "aarmvs_deconv2x": (_I, [_SRCP, _I, _I, c_float_p, c_float_p, _P, _P, _I, _P, _P]),
     "aarmvs_head_wta": (_I, [_SRCP, _I, _I, c_float_p, c_float_p, _P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
     "aarmvs_next_plane": (_I, [_P, _P, _I, _P]),

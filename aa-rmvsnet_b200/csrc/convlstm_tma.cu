@@ -28,15 +28,16 @@
 // (MMA <-> epilogue), all hand-offs through mbarriers; tcgen05.commit releases operand stages and publishes
 // accumulators.  The cell state c is private to this kernel and kept in a tile-blocked layout
 // [tile][quarter of the hidden channels][128 px][CH/4] so that every access is a fully used 128-byte line.
-#include <cuda.h>
 #include "common.cuh"
 #include "tc_common.cuh"
+#include "plane_map.cuh"
 #include "../../include/aarmvs.h"
 
 namespace {
 
 constexpr int TR = 16, TCOL = 8, HR = TR + 2, HC = TCOL + 2, NPX = HR * HC;   // 180 staged pixels per tile
 constexpr int CHUNK_BYTES = NPX * 16;                                         // one 8-channel chunk of one fp16 plane
+static_assert(HR == planemap::BOX_ROWS && HC == planemap::BOX_COLS, "the tensor-map box is the staged halo tile");
 constexpr int N_EPI_WARPS = 16, MMA_WARP = N_EPI_WARPS, TMA_WARP = MMA_WARP + 1;
 constexpr int N_THREADS = (N_EPI_WARPS + 2) * 32;                             // 576
 
@@ -363,38 +364,6 @@ __global__ void __launch_bounds__(N_THREADS, 1) convlstm_tma_kernel(const __grid
     if (warp == MMA_WARP) tc::tmem_dealloc<C::TMEM_COLS>(tmem_base);
 }
 
-// cuTensorMapEncodeTiled through the runtime's driver entry point query (the library links no libcuda)
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn encode_tiled() {
-    static EncodeTiledFn fn = nullptr;
-    if (!fn) {
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-            q == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<EncodeTiledFn>(p);
-    }
-    return fn;
-}
-
-// Operand planes [pp][2][chunks][H][W][8 halfs] -> 5-D map with the halo-tile box.
-int make_plane_map(CUtensorMap* map, const void* planes, int H, int W, int chunks, int pp) {
-    EncodeTiledFn enc = encode_tiled();
-    if (!enc) return AARMVS_ERR_ARG;
-    const cuuint64_t row = (cuuint64_t)W * 16, plane = (cuuint64_t)H * row;
-    cuuint64_t dims[5] = {(cuuint64_t)W * 8, (cuuint64_t)H, (cuuint64_t)chunks, 2, (cuuint64_t)pp};
-    cuuint64_t strides[4] = {row, plane, plane * chunks, plane * chunks * 2};
-    cuuint32_t box[5] = {(cuuint32_t)HC * 8, (cuuint32_t)HR, (cuuint32_t)chunks, 1, 1};
-    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<void*>(planes), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    return r == CUDA_SUCCESS ? AARMVS_OK : AARMVS_ERR_ARG;
-}
-
 template <int KSTEPS, int NG, int NST>
 int launch_cell(const CellArgs& a, cudaStream_t stream) {
     using C = Cfg<KSTEPS, NG, NST>;
@@ -444,7 +413,7 @@ extern "C" int aarmvs_convlstm_cell_tc(const aarmvs_plane_src* src, int nsrc, in
             a.pp_phase[s] = 1;
         }
         a.chunks[s] = ch / 8;
-        if (int e = make_plane_map(&a.map[s], planes, H, W, ch / 8, pp)) return e;
+        if (int e = planemap::make_plane_map(&a.map[s], planes, H, W, ch / 8, pp)) return e;
         csum += ch;
     }
     AARMVS_CHECK_ARG(csum == cin && cin <= 48 && ((uintptr_t)h_planes & 15) == 0 && ((uintptr_t)weight_f16 & 15) == 0);

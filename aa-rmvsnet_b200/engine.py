@@ -111,6 +111,7 @@ class Engine:
         for i in range(2):
             w[f"deconv{i}.w_host"] = capi.host_floats(pack.deconv_taps(sd[f"{cr}.deconv_{i}.conv.weight"]).reshape(-1).cpu().tolist())
             w[f"deconv{i}.b_host"] = capi.host_floats(sd[f"{cr}.deconv_{i}.conv.bias"].cpu().tolist())
+            w[f"deconv{i}.wtc"] = pack.deconv_pairs_f16(sd[f"{cr}.deconv_{i}.conv.weight"])
             w[f"deconv{i}.gn"] = (sd[f"{cr}.deconv_{i}.gn.weight"].contiguous(), sd[f"{cr}.deconv_{i}.gn.bias"].contiguous())
         # small layers whose parameters are baked into kernel parameter banks (host arrays)
         om = "omega.reweight_network"
@@ -167,14 +168,15 @@ class Engine:
             ws["up0p"] = torch.empty(2, 2, P // 4, 8, **f16)
             ws["up1p"] = torch.empty(2, 2, P, 8, **f16)
             ws["c"] = [torch.empty(self.lib.aarmvs_cell_state_floats(H // s, W // s, ch), **f32) for ch, s in zip(_HID, _SCALE)]
-            # fp32 copies of h only where a CUDA-core kernel reads it (deconv_0, deconv_1, conv_0)
-            ws["h"] = [torch.empty(2, P // (s * s), ch, **f32) if i >= 2 else None
+            # fp32 copy of h only where a CUDA-core kernel reads it (conv_0 in head_wta)
+            ws["h"] = [torch.empty(2, P // (s * s), ch, **f32) if i == 4 else None
                        for i, (ch, s) in enumerate(zip(_HID, _SCALE))]
         else:
             ws["h"] = [torch.empty(2, P // (s * s), ch, **f32) for ch, s in zip(_HID, _SCALE)]
             ws["c"] = [torch.empty(P // (s * s), ch, **f32) for ch, s in zip(_HID, _SCALE)]
-        ws["up0"] = torch.empty(P // 4, 16, **f32)
-        ws["up1"] = torch.empty(P, 16, **f32)
+        if not tc:               # fp32 deconvolution outputs (the tensor-core path writes operand planes directly)
+            ws["up0"] = torch.empty(P // 4, 16, **f32)
+            ws["up1"] = torch.empty(P, 16, **f32)
         ws["psums"] = torch.zeros(K * S * 6 + 8, device=device, dtype=torch.float64)
         ws["plane"] = torch.zeros(1, device=device, dtype=torch.int32)
         ws["cams"] = torch.empty(S, 12, **f32)
@@ -322,25 +324,30 @@ class Engine:
                                            _ptr(dst), _ptr(sums), 0, dptr, stream), f"aarmvs_deconv2x[{i}]")
             mark(f"deconv{i}")
 
+        def deconv_tc(i, src_, hin, win, sums, out_planes):
+            """deConvGnReLU on the tensor cores: statistics pass, then the same GEMM again with GroupNorm + ReLU + split."""
+            g = w[f"deconv{i}.gn"]
+            for out in (None, out_planes):
+                capi.check(lib.aarmvs_deconv2x_tc(ctypes.byref(src_), hin, win, _ptr(w[f"deconv{i}.wtc"]), w[f"deconv{i}.b_host"],
+                                                  _ptr(sums), _ptr(g[0]), _ptr(g[1]), _ptr(out) if out is not None else None,
+                                                  0, dptr, stream), f"aarmvs_deconv2x_tc[{i}]")
+            mark(f"deconv{i}")
+
         H2, W2, H4, W4 = H // 2, W // 2, H // 4, W // 4
         s_up0, s_up1 = ps[n_omega:], ps[n_omega + 4:]
         cv = ws["cost_volume"]
         for k in range(nplanes):
-            up0 = _src(ws["up0"], 16, capi.SRC_GN_RELU, sums=s_up0, gn=w["deconv0.gn"], groups=2, count=8 * (P // 4))
-            up1 = _src(ws["up1"], 16, capi.SRC_GN_RELU, sums=s_up1, gn=w["deconv1.gn"], groups=2, count=8 * P)
             if tc:
                 cell_tc(0, [_psrc(ws["costp"][k], 32)], H, W, 48, pooled=ws["pool"][0])
                 cell_tc(1, [_psrc(ws["pool"][0], 16)], H2, W2, 32, pooled=ws["pool"][1])
                 cell_tc(2, [_psrc(ws["pool"][1], 16)], H4, W4, 32)
-                deconv(0, hsrc(2), H4, W4, ws["up0"], s_up0)
-                self.split_planes(up0, H2, W2, ws["up0p"], stream)          # GroupNorm + ReLU need the whole map's sums
-                mark("deconv0_split")
+                deconv_tc(0, hplanes(2), H4, W4, s_up0, ws["up0p"])
                 cell_tc(3, [_psrc(ws["up0p"], 16), hplanes(1)], H2, W2, 48)
-                deconv(1, hsrc(3), H2, W2, ws["up1"], s_up1)
-                self.split_planes(up1, H, W, ws["up1p"], stream)
-                mark("deconv1_split")
+                deconv_tc(1, hplanes(3), H2, W2, s_up1, ws["up1p"])
                 cell_tc(4, [_psrc(ws["up1p"], 16), hplanes(0)], H, W, 40)
             else:
+                up0 = _src(ws["up0"], 16, capi.SRC_GN_RELU, sums=s_up0, gn=w["deconv0.gn"], groups=2, count=8 * (P // 4))
+                up1 = _src(ws["up1"], 16, capi.SRC_GN_RELU, sums=s_up1, gn=w["deconv1.gn"], groups=2, count=8 * P)
                 cell(0, [_src(ws["cost"][k], 32)], H, W, 48)
                 cell(1, [hsrc(0, capi.SRC_MAXPOOL2)], H2, W2, 32)
                 cell(2, [hsrc(1, capi.SRC_MAXPOOL2)], H4, W4, 32)

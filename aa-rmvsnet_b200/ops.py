@@ -139,6 +139,29 @@ def convlstm_cell(model, cell_index, x, h, c, math=None):
     return _nchw(h_pair[1], H, W), _nchw(cs, H, W)
 
 
+def deconv_gn_relu(model, index, x):
+    """deConvGnReLU.forward (models/module.py:269-287) of cost_regularization.deconv_{index} on the tensor cores.
+    x [16,H,W] -> [16,2H,2W] (the kernel's fp16 (hi, lo) operand planes summed back to fp32)."""
+    _need_cuda(x)
+    eng = model._engine
+    lib, dev = eng.lib, x.device
+    w = eng._weights(dev)
+    _, H, W = x.shape
+    st = _stream(dev)
+    xp = torch.empty(2, 2, H * W, 8, device=dev, dtype=torch.float16)
+    eng.split_planes(_src(_nhwc(x.float()), 16), H, W, xp, st)
+    out = torch.empty(2, 2, 4 * H * W, 8, device=dev, dtype=torch.float16)
+    sums = torch.zeros(4, device=dev, dtype=torch.float64)
+    g = w[f"deconv{index}.gn"]
+    src = _psrc(xp, 16)
+    for o in (None, out):
+        capi.check(lib.aarmvs_deconv2x_tc(ctypes.byref(src), H, W, _ptr(w[f"deconv{index}.wtc"]), w[f"deconv{index}.b_host"],
+                                          _ptr(sums), _ptr(g[0]), _ptr(g[1]), _ptr(o) if o is not None else None, 1, None, st),
+                   "aarmvs_deconv2x_tc")
+    y = out.float().sum(0)                                   # hi + lo: [2 chunks][4HW][8]
+    return y.permute(1, 0, 2).reshape(2 * H, 2 * W, 16).permute(2, 0, 1).contiguous()
+
+
 def deform_conv(model, level, x):
     """DeformConv2d.forward (models/module.py:133-189) of feature.intraAA.deformconv{level}[0].  x [32,H,W] -> [32,H,W]."""
     _need_cuda(x)

@@ -70,6 +70,24 @@ def deconv_taps(w):
     return w.permute(2, 3, 0, 1).contiguous()
 
 
+# (ky, kx) of the nine (output parity class, tap) pairs of csrc/deconv_tc.cu, in its issue order
+DECONV_PAIRS = ((1, 1), (1, 2), (1, 0), (2, 1), (0, 1), (2, 2), (2, 0), (0, 2), (0, 0))
+
+
+def deconv_pairs_f16(w):
+    """nn.ConvTranspose2d weight [cin=16][cout=16][3][3] -> B operands of the tensor-core deconvolution:
+    [9 pairs][2 chunks of 8 input channels][32 rows: 0-15 hi(W[.][co]), 16-31 lo][8] fp16."""
+    cin, cout = w.shape[:2]
+    out = torch.zeros(len(DECONV_PAIRS), cin // 8, 2 * cout, 8, dtype=torch.float16, device=w.device)
+    for p, (ky, kx) in enumerate(DECONV_PAIRS):
+        m = w[:, :, ky, kx].float()                          # [ci][co]
+        hi = m.half()
+        lo = (m - hi.float()).half()
+        out[p, :, :cout] = hi.view(cin // 8, 8, cout).permute(0, 2, 1)
+        out[p, :, cout:] = lo.view(cin // 8, 8, cout).permute(0, 2, 1)
+    return out.contiguous()
+
+
 def omega_tail(sd, prefix="omega.reweight_network"):
     """Flat parameter block in the order of struct OmegaTail (csrc/warp_aggregate.cu)."""
     s = prefix + ".1.stem"

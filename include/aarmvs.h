@@ -185,6 +185,18 @@ int aarmvs_convlstm_cell_tc(const aarmvs_plane_src* src, int nsrc, int H, int W,
 int aarmvs_deconv2x(const aarmvs_conv_src* in, int Hin, int Win, const float* weight_host, const float* bias_host,
                     float* out, double* out_gn_sums, int d_host, const int* d_dev, void* stream);
 
+/* The same layer on the tensor cores, fed by TMA from the operand planes of h (16 channels) and run twice per plane
+ * because GroupNorm (models/module.py:284) needs the sums of the whole output map:
+ *   out_planes == NULL: transposed conv -> gn_sums [2 groups][sum, sumsq] += (nothing is stored; zero gn_sums before);
+ *   out_planes != NULL: transposed conv again -> GroupNorm(gn_sums, gn_weight, gn_bias) + ReLU -> fp16 split ->
+ *                       operand planes [2][2][2Hin][2Win][8] of the next cell.
+ * weight_f16: DEVICE [9 (class, tap) pairs][2 chunks][32 rows: 0-15 hi(W[.][co]), 16-31 lo][8] fp16 in the pair order
+ * W[1][1], W[1][2], W[1][0], W[2][1], W[0][1], W[2][2], W[2][0], W[0][2], W[0][0] of ConvTranspose2d's [cin][cout][ky][kx];
+ * bias_host: [16] host memory. */
+int aarmvs_deconv2x_tc(const aarmvs_plane_src* in, int Hin, int Win, const void* weight_f16, const float* bias_host,
+                       double* gn_sums, const float* gn_weight, const float* gn_bias, void* out_planes, int d_host,
+                       const int* d_dev, void* stream);
+
 /* conv_0 (3x3, 8 -> 1; models/drmvsnet.py:165) fused with the winner-take-all update (drmvsnet.py:324-339):
  * p = exp(cost); if (max_prob < p) {max_prob = p; depth = depth_values[d]; index = d}; exp_sum += p.
  * At d == num_depth - 1 also writes conf = max_prob / exp_sum.  At d == 0 the state maps are treated as zero.

@@ -71,6 +71,22 @@ def test_convlstm_cell(ops_dtu, model, math):
     torch.testing.assert_close(c.cpu(), g["cell_c_out"][0], rtol=1e-5, atol=2e-5)
 
 
+@pytest.mark.parametrize("hw", [(16, 8), (20, 28), (37, 50)])
+def test_deconv_gn_relu_tensor_core(sd_dtu, model, hw):
+    """deConvGnReLU as a two-pass tcgen05 GEMM (statistics, then normalise + split) against torch's ConvTranspose2d +
+    GroupNorm + ReLU, incl. sizes that do not fill the 16x8 tiles."""
+    import torch.nn.functional as F
+    from aarmvsnet_b200 import ops
+    h, w = hw
+    x = torch.randn(16, h, w, generator=torch.Generator().manual_seed(h * 100 + w))
+    for i in range(2):
+        p = f"cost_regularization.deconv_{i}"
+        y = F.conv_transpose2d(x[None], sd_dtu[p + ".conv.weight"], sd_dtu[p + ".conv.bias"], stride=2, padding=1, output_padding=1)
+        want = F.relu(F.group_norm(y, 2, sd_dtu[p + ".gn.weight"], sd_dtu[p + ".gn.bias"], eps=1e-5))[0]
+        got = ops.deconv_gn_relu(model, i, x.cuda()).cpu()
+        torch.testing.assert_close(got, want, rtol=1e-5, atol=2e-5)
+
+
 @pytest.fixture(scope="module")
 def model_fma():
     import aarmvsnet_b200 as aa
