@@ -209,6 +209,20 @@ int aarmvs_head_wta(const aarmvs_conv_src* h4, int H, int W, const float* weight
 /* End of a plane: ++*d_dev and zero `nzero` doubles of GroupNorm sums for the next plane. */
 int aarmvs_next_plane(int* d_dev, double* sums, int nzero, void* stream);
 
+/* ---- depth-map fusion filter (the step after the path; fusion.py:71-133, 179-225) ------------------------ */
+
+/* Geometric-consistency filter of one reference view against S <= 10 source views (reproject with the reference depth,
+ * sample the source depth like cv2.remap INTER_LINEAR, project back, nine nested thresholds dist < i/4 px and
+ * |d_rep - d| / d < i/1300, i = 2..10; geo_mask = OR_i (views passing i >= i) for i < S + 1; averaged depth
+ * (sum of the consistent reprojected depths + d) / (count + 1)).
+ * mats: DEVICE [S][aarmvs_fuse_view_mats() = 60] float64 per source view: inv(K_ref)[9], (E_src inv(E_ref))[3x4],
+ * K_src[9], inv(K_src)[9], (E_ref inv(E_src))[3x4], K_ref[9], each prepared in float32 as numpy does (fusion.py:80-105).
+ * depth_src: [S][H*W].  final_mask = geo_mask && conf_ref > photo_threshold (may be NULL with conf_ref), geo_sum may be NULL. */
+int aarmvs_fuse_view_mats(void);
+int aarmvs_fuse_view(const float* depth_ref, const float* conf_ref, const float* depth_src, int S, int H, int W,
+                     const double* mats, float photo_threshold, unsigned char* geo_mask, unsigned char* final_mask,
+                     float* depth_avg, int* geo_sum, void* stream);
+
 /* ---- tensor-core building blocks ------------------------------------------------------------------------- */
 
 /* Known-answer test of the tcgen05 path shared by the ConvLSTM kernels (un-swizzled K-major shared-memory operands,
