@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(256) fuse_view_kernel(const float* __restrict_
             double xr, yr, zr;
             mat34(m + 39, X, Y, Z, xr, yr, zr);                                      // back in the reference camera space
             const float depth_rep = (float)zr;
-            mat3(m + 48, xr, yr, zr, kx, ky, kz);
+            mat3(m + 51, xr, yr, zr, kx, ky, kz);
             const float x_rep = (float)(kx / kz), y_rep = (float)(ky / kz);
             const double ex = (double)x_rep - (double)x, ey = (double)y_rep - (double)y;
             const double dist = sqrt(ex * ex + ey * ey);

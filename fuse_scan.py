@@ -73,7 +73,7 @@ def main():
         dist.init_process_group("nccl")
 
     pairs = scanio.read_pair_file(os.path.join(args.scan, "pair.txt"))
-    mine = scan_mod.shard_views(len(pairs), rank, world)
+    mine = scan_mod.shard_views(len(pairs), world, rank)
     depth = lambda v: scanio.read_pfm(os.path.join(args.out, args.depth_dir, f"{v:08d}.pfm"))[0]      # noqa: E731
     pts, cols = [], []
     t0 = time.time()
