@@ -122,6 +122,7 @@ class Engine:
         assert tail.numel() == self.lib.aarmvs_omega_tail_floats()
         w["tail_host"] = capi.host_floats(tail.tolist())
         w["head.w_host"] = capi.host_floats(pack.conv_taps(sd[cr + ".conv_0.weight"]).reshape(-1).cpu().tolist())
+        w["head.wtc"] = pack.head_pairs_f16(sd[cr + ".conv_0.weight"])
         w["head.b_host"] = capi.host_floats(sd[cr + ".conv_0.bias"].cpu().tolist())
         self.w, self._wkey = w, key
         self._ws.clear()                 # graphs bake host-side parameters: drop them with the old weights
@@ -168,9 +169,7 @@ class Engine:
             ws["up0p"] = torch.empty(2, 2, P // 4, 8, **f16)
             ws["up1p"] = torch.empty(2, 2, P, 8, **f16)
             ws["c"] = [torch.empty(self.lib.aarmvs_cell_state_floats(H // s, W // s, ch), **f32) for ch, s in zip(_HID, _SCALE)]
-            # fp32 copy of h only where a CUDA-core kernel reads it (conv_0 in head_wta)
-            ws["h"] = [torch.empty(2, P // (s * s), ch, **f32) if i == 4 else None
-                       for i, (ch, s) in enumerate(zip(_HID, _SCALE))]
+            ws["h"] = [None] * 5              # no fp32 copies of h: deconvolutions and the head read the planes too
         else:
             ws["h"] = [torch.empty(2, P // (s * s), ch, **f32) for ch, s in zip(_HID, _SCALE)]
             ws["c"] = [torch.empty(P // (s * s), ch, **f32) for ch, s in zip(_HID, _SCALE)]
@@ -355,11 +354,17 @@ class Engine:
                 cell(3, [up0, hsrc(1)], H2, W2, 48)
                 deconv(1, hsrc(3), H2, W2, ws["up1"], s_up1)
                 cell(4, [up1, hsrc(0)], H, W, 40)
-            h4 = hsrc(4)
-            capi.check(lib.aarmvs_head_wta(ctypes.byref(h4), H, W, w["head.w_host"], w["head.b_host"], _ptr(ws["depths"]),
-                                           ws["D"], 0, dptr, _ptr(ws["max_prob"]), _ptr(ws["depth"]), _ptr(ws["exp_sum"]),
-                                           _ptr(ws["index"]), _ptr(ws["conf"]), _ptr(cv) if cv is not None else None, stream),
-                       "aarmvs_head_wta")
+            if tc:
+                capi.check(lib.aarmvs_head_wta_tc(_ptr(ws["hp"][4]), H, W, _ptr(w["head.wtc"]), w["head.b_host"], _ptr(ws["depths"]),
+                                                  ws["D"], 0, dptr, _ptr(ws["max_prob"]), _ptr(ws["depth"]), _ptr(ws["exp_sum"]),
+                                                  _ptr(ws["index"]), _ptr(ws["conf"]), _ptr(cv) if cv is not None else None,
+                                                  stream), "aarmvs_head_wta_tc")
+            else:
+                h4 = hsrc(4)
+                capi.check(lib.aarmvs_head_wta(ctypes.byref(h4), H, W, w["head.w_host"], w["head.b_host"], _ptr(ws["depths"]),
+                                               ws["D"], 0, dptr, _ptr(ws["max_prob"]), _ptr(ws["depth"]), _ptr(ws["exp_sum"]),
+                                               _ptr(ws["index"]), _ptr(ws["conf"]), _ptr(cv) if cv is not None else None, stream),
+                           "aarmvs_head_wta")
             # ++plane; zero the deconv GroupNorm sums (and, after the last plane of the batch, the omega sums too)
             if k == nplanes - 1:
                 capi.check(lib.aarmvs_next_plane(dptr, _ptr(ps), ps.numel(), stream), "aarmvs_next_plane")

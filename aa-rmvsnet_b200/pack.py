@@ -88,6 +88,24 @@ def deconv_pairs_f16(w):
     return out.contiguous()
 
 
+# taps (ky * 3 + kx) of the five two-tap MMAs of csrc/head_tc.cu; -1 = zero weights
+HEAD_PAIRS = ((0, 1), (2, 3), (4, 5), (6, 7), (8, -1))
+
+
+def head_pairs_f16(w):
+    """conv_0 weight [1][8][3][3] -> [5 pairs][2 taps][16 rows][8] fp16, row 0 = hi(w[tap][c]), row 8 = lo, others zero."""
+    taps = w[0].permute(1, 2, 0).reshape(9, 8).float()          # [tap][c]
+    hi = taps.half()
+    lo = (taps - hi.float()).half()
+    out = torch.zeros(len(HEAD_PAIRS), 2, 16, 8, dtype=torch.float16, device=w.device)
+    for p, pair in enumerate(HEAD_PAIRS):
+        for j, t in enumerate(pair):
+            if t >= 0:
+                out[p, j, 0] = hi[t]
+                out[p, j, 8] = lo[t]
+    return out.contiguous()
+
+
 def omega_tail(sd, prefix="omega.reweight_network"):
     """Flat parameter block in the order of struct OmegaTail (csrc/warp_aggregate.cu)."""
     s = prefix + ".1.stem"

@@ -206,6 +206,13 @@ int aarmvs_head_wta(const aarmvs_conv_src* h4, int H, int W, const float* weight
                     const float* depth_values, int num_depth, int d_host, const int* d_dev, float* max_prob,
                     float* depth_map, float* exp_sum, int* index_map, float* conf, float* cost_volume, void* stream);
 
+/* The same head on the tensor cores, fed by TMA from h4's ping-pong operand planes [2][2][1][H][W][8] (half d & 1 is
+ * read): two taps per K = 16 MMA.  weight_f16: DEVICE [5 pairs][2 taps][16 rows][8] fp16 with row 0 = hi(w), row 8 = lo(w)
+ * for the tap pairs (0,1) (2,3) (4,5) (6,7) (8,-) of tap = ky * 3 + kx; other arguments as aarmvs_head_wta. */
+int aarmvs_head_wta_tc(const void* h4_planes, int H, int W, const void* weight_f16, const float* bias_host,
+                       const float* depth_values, int num_depth, int d_host, const int* d_dev, float* max_prob,
+                       float* depth_map, float* exp_sum, int* index_map, float* conf, float* cost_volume, void* stream);
+
 /* End of a plane: ++*d_dev and zero `nzero` doubles of GroupNorm sums for the next plane. */
 int aarmvs_next_plane(int* d_dev, double* sums, int nzero, void* stream);
 
