@@ -107,6 +107,7 @@ __device__ __forceinline__ void sweep_position(const float* cam, float x, float 
 struct Taps {
     int o_nw, o_ne, o_sw, o_se;
     float w_nw, w_ne, w_sw, w_se;
+    int xi, yi;                      // integer coordinates of the north-west corner (0 when no corner can be inside)
 };
 
 __device__ __forceinline__ Taps make_taps(float ix, float iy, int W, int H) {
@@ -123,6 +124,7 @@ __device__ __forceinline__ Taps make_taps(float ix, float iy, int W, int H) {
     bool x0 = fx >= 0.0f && fx <= (float)(W - 1), x1 = ex >= 0.0f && ex <= (float)(W - 1);
     bool y0 = fy >= 0.0f && fy <= (float)(H - 1), y1 = sy >= 0.0f && sy <= (float)(H - 1);
     int xi = x0 || x1 ? (int)fx : 0, yi = y0 || y1 ? (int)fy : 0;
+    t.xi = xi; t.yi = yi;
     t.o_nw = (x0 && y0) ? yi * W + xi : -1;
     t.o_ne = (x1 && y0) ? yi * W + xi + 1 : -1;
     t.o_sw = (x0 && y1) ? (yi + 1) * W + xi : -1;

@@ -45,7 +45,7 @@ constexpr int N_THREADS = 32 + G * GROUP_THREADS;
 constexpr int KC8 = 4, NB = 16;                                          // K chunks; accumulator columns (0-3 and 8-11 used)
 constexpr int A_PLANE = KC8 * AROWS * 16, A_STAGE = 2 * A_PLANE;
 constexpr int B_BYTES = 9 * KC8 * NB * 16;                               // [tap][chunk][16 rows][16 B] = 9216 bytes
-constexpr int TAP_BYTES = NPX * 48;                                      // one TapRec (48 B) per staged pixel
+constexpr int TAP_BYTES = NPX * 32;                                      // one TapRec (32 B) per staged pixel
 constexpr int SMEM_FIXED = B_BYTES + G * (A_STAGE + TAP_BYTES) + 1024;    // + G * 4 warps * planes * S * 8 bytes of GroupNorm partial sums
 #ifndef STEM_ACC_STRIDE
 #define STEM_ACC_STRIDE 32
@@ -74,14 +74,16 @@ struct StemArgs {
     int dbg;                    // debug ablation flags (aarmvs_debug_flags): 1 skip gather loads, 2 skip recipes, 4 skip MMA
 };
 
-// Gather recipe of one staged pixel, ready to use: BYTE offsets of the four corner lines (out-of-image corners point
-// at line 0 with weight 0, which reproduces the skipped tap exactly), the byte offset of the reference pixel
-// (-1: the pixel lies outside the image, its cost is the conv's zero padding) and whether this fill owns the pixel's
-// costv line (interior pixel of the tile, inside the image).
+// Gather recipe of one staged pixel (32 bytes; the L1 data pipe bounds this kernel, so the record is kept to two loads):
+// the four bilinear weights (0 for corners outside the image, which reproduces the skipped tap exactly), the BYTE offset
+// of the clamped north-west line with the clamped column / row steps in bits 0 / 1 (a zero-weight corner may read any
+// valid line), and the byte offset of the reference pixel with the "this fill owns the pixel's costv line" flag in
+// bit 0 (-1: the pixel lies outside the image, its cost is the conv's zero padding).
 struct __align__(16) TapRec {
-    unsigned o[4];
     float w[4];
-    int ref_off, keep, pad1, pad2;
+    unsigned base;
+    int ref;
+    unsigned pad0, pad1;
 };
 
 // Packed fp32 pairs (Blackwell FFMA2 / FMUL2 / FADD2): IEEE round-to-nearest per lane, i.e. bit-identical to the scalar
@@ -192,6 +194,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) cost_stem_tc_kernel(const __grid
         const int c4i = lt & 7, px0 = lt >> 3;
         const uint32_t st_thread = tc::smem_u32(stage) + (uint32_t)((c4i >> 1) * AROWS * 16 + (c4i & 1) * 8);
         const bool keep_cv = a.costv_mode == 1;
+        const unsigned row_bytes = (unsigned)a.W * 128u;
         // fill it = g, g + G, ... decoded incrementally as (tile slot tl, view v, plane k): it = (tl * S + v) * K + k
         int tl = g / SK, v = (g % SK) / a.K, k = g % a.K, n = 0;
         for (int it = g; it < total; it += G, ++n) {
@@ -206,19 +209,18 @@ __global__ void __launch_bounds__(N_THREADS, 1) cost_stem_tc_kernel(const __grid
                 const int r = px / HC, cc = px - r * HC;
                 const int y = ty * TR - 1 + r, x = tx * TCOL - 1 + cc;
                 TapRec rec;
-                rec.o[0] = rec.o[1] = rec.o[2] = rec.o[3] = 0u;
                 rec.w[0] = rec.w[1] = rec.w[2] = rec.w[3] = 0.f;
-                rec.ref_off = -1; rec.keep = 0; rec.pad1 = rec.pad2 = 0;
+                rec.base = 0u; rec.ref = -1; rec.pad0 = rec.pad1 = 0u;
                 if (y >= 0 && y < a.H && x >= 0 && x < a.W && !(a.dbg & 2)) {
                     float ix, iy;
                     sweep_position(scam + v * 12, (float)x, (float)y, depth, a.W, a.H, a.align_corners != 0, ix, iy);
                     const Taps t = make_taps(ix, iy, a.W, a.H);
-                    rec.o[0] = (unsigned)max(t.o_nw, 0) * 128u; rec.o[1] = (unsigned)max(t.o_ne, 0) * 128u;
-                    rec.o[2] = (unsigned)max(t.o_sw, 0) * 128u; rec.o[3] = (unsigned)max(t.o_se, 0) * 128u;
                     rec.w[0] = t.o_nw >= 0 ? t.w_nw : 0.f; rec.w[1] = t.o_ne >= 0 ? t.w_ne : 0.f;
                     rec.w[2] = t.o_sw >= 0 ? t.w_sw : 0.f; rec.w[3] = t.o_se >= 0 ? t.w_se : 0.f;
-                    rec.ref_off = (y * a.W + x) * 128;
-                    rec.keep = (r >= 1 && r <= TR && cc >= 1 && cc <= TCOL) ? 1 : 0;
+                    const int xw = min(max(t.xi, 0), a.W - 1), xe = min(max(t.xi + 1, 0), a.W - 1);
+                    const int yn = min(max(t.yi, 0), a.H - 1), ys = min(max(t.yi + 1, 0), a.H - 1);
+                    rec.base = (unsigned)(yn * a.W + xw) * 128u | (unsigned)(xe - xw) | ((unsigned)(ys - yn) << 1);
+                    rec.ref = (y * a.W + x) * 128 + ((r >= 1 && r <= TR && cc >= 1 && cc <= TCOL) ? 1 : 0);
                 }
                 taps[px] = rec;
             }
@@ -264,18 +266,19 @@ __global__ void __launch_bounds__(N_THREADS, 1) cost_stem_tc_kernel(const __grid
 #pragma unroll 1
                 for (int jb = 0; jb < ITEMS; jb += NB) {
                     float4 ta[NB], tb[NB], tcn[NB], td[NB], rv[NB], wq[NB];
-                    int2 rk[NB];
+                    int rk[NB];
 #pragma unroll
                     for (int j = 0; j < NB; ++j) {
                         const TapRec* rec = taps + min(px0 + (jb + j) * 16, NPX - 1);
-                        const uint4 o = *reinterpret_cast<const uint4*>(rec->o);
                         wq[j] = *reinterpret_cast<const float4*>(rec->w);
-                        rk[j] = *reinterpret_cast<const int2*>(&rec->ref_off);
-                        ta[j] = ldg4b(svb + o.x);
-                        tb[j] = ldg4b(svb + o.y);
-                        tcn[j] = ldg4b(svb + o.z);
-                        td[j] = ldg4b(svb + o.w);
-                        rv[j] = ldg4b(refb + (unsigned)max(rk[j].x, 0));
+                        const uint2 br = *reinterpret_cast<const uint2*>(&rec->base);
+                        rk[j] = (int)br.y;
+                        const unsigned o0 = br.x & ~127u, o1 = o0 + ((br.x & 1u) << 7), od = (br.x & 2u) ? row_bytes : 0u;
+                        ta[j] = ldg4b(svb + o0);
+                        tb[j] = ldg4b(svb + o1);
+                        tcn[j] = ldg4b(svb + (o0 + od));
+                        td[j] = ldg4b(svb + (o1 + od));
+                        rv[j] = ldg4b(refb + ((unsigned)max(rk[j], 0) & ~127u));
                     }
 #pragma unroll
                     for (int j = 0; j < NB; ++j) {
@@ -288,15 +291,15 @@ __global__ void __launch_bounds__(N_THREADS, 1) cost_stem_tc_kernel(const __grid
                         const uint64_t g23 = fma2(pk2(td[j].z, td[j].w), w3, fma2(pk2(tcn[j].z, tcn[j].w), w2,
                                                   fma2(pk2(tb[j].z, tb[j].w), w1, mul2(pk2(ta[j].z, ta[j].w), w0))));
                         // outside the image the cost is the conv's zero padding: d * 0 = +-0 exactly (finite features), d * 1 = d
-                        const float inf_ = rk[j].x >= 0 ? 1.0f : 0.0f;
+                        const float inf_ = rk[j] >= 0 ? 1.0f : 0.0f;
                         const uint64_t in2 = pk2(inf_, inf_);
                         const uint64_t d01 = mul2(sub2(g01, pk2(rv[j].x, rv[j].y)), in2), d23 = mul2(sub2(g23, pk2(rv[j].z, rv[j].w)), in2);
                         const uint64_t c01 = mul2(d01, d01), c23 = mul2(d23, d23);
                         float4 cv;
                         upk2(c01, cv.x, cv.y);
                         upk2(c23, cv.z, cv.w);
-                        if (keep_cv && rk[j].y && pxr < NPX)             // this fill owns the pixel's costv line
-                            *reinterpret_cast<float4*>(cvb + (unsigned)rk[j].x) = cv;
+                        if (keep_cv && rk[j] >= 0 && (rk[j] & 1) && pxr < NPX)        // this fill owns the pixel's costv line
+                            *reinterpret_cast<float4*>(cvb + ((unsigned)rk[j] & ~127u)) = cv;
                         // fp16 split as tc::split4_f16: hi = top 11 mantissa bits, lo = fp16(x - hi)
                         const float h0 = __uint_as_float(__float_as_uint(cv.x) & 0xFFFFE000u), h1 = __uint_as_float(__float_as_uint(cv.y) & 0xFFFFE000u);
                         const float h2 = __uint_as_float(__float_as_uint(cv.z) & 0xFFFFE000u), h3 = __uint_as_float(__float_as_uint(cv.w) & 0xFFFFE000u);

@@ -580,6 +580,8 @@ extern "C" int aarmvs_aggregate(const float* ref, const float* src, size_t view_
     fill_tail(q, tail_host);
     if (costv) {           // pass A kept (warp - ref)^2: stream it instead of gathering again
         const size_t Pn = (size_t)H * W;
+        // the four 8-lane pixel groups of a warp enter and leave the kernel's loop together (its shuffles name the full warp)
+        AARMVS_CHECK_ARG(Pn % 4 == 0);
         const size_t groups = (Pn * planes + 31) / 32;
         const int nblk = (int)(groups < (size_t)148 * 32 ? groups : (size_t)148 * 32);
         aggregate_stream_kernel<<<nblk, 256, 0, (cudaStream_t)stream>>>(costv, S, planes, Pn, q, t0, stats, cost, (__half*)cost_planes, reweight_out);
