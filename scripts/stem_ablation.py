@@ -65,6 +65,17 @@ e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / 3 / K
 print(f"aggregate (streamed)     {ms:.3f} ms/plane  = {(S * 144 + 128) * P / ms / 1e6:.0f} GB/s")
 
+costp = torch.empty(K, 2, 4, P, 8, device="cuda", dtype=torch.float16)
+def run_dp():
+    capi.check(lib.aarmvs_aggregate(None, None, 0, H, W, S, None, w["tail_host"], None, 100, None, K, 0, _ptr(ws["t0"]), _ptr(ws["psums"]),
+                                    _ptr(cv), None, _ptr(costp), None, st), "agg stream planes")
+run_dp(); torch.cuda.synchronize()
+e0.record()
+for _ in range(3): run_dp()
+e1.record(); torch.cuda.synchronize()
+ms = e0.elapsed_time(e1) / 3 / K
+print(f"aggregate (streamed, operand planes out)  {ms:.3f} ms/plane  = {(S * 144 + 128) * P / ms / 1e6:.0f} GB/s")
+
 # ---- split variant: A1 (warp_cost) and A2 (stem conv streaming costv) separately
 def timeit(fn, name, reps=3):
     fn(); torch.cuda.synchronize()
