@@ -26,21 +26,28 @@
 
 namespace {
 
+#ifndef STEM_NBLK
+#define STEM_NBLK 1             // 8-column MMA blocks per tile: the tile is 16 x (8 NBLK) pixels
+#endif
 #ifndef STEM_GROUPS
-#define STEM_GROUPS 5
+#define STEM_GROUPS (STEM_NBLK == 1 ? 5 : 3)
 #endif
 #ifndef STEM_NB
 #define STEM_NB 2
 #endif
-constexpr int TR = 16, TCOL = 8, HR = 18, HC = 10, NPX = HR * HC;        // 180 staged pixels
+constexpr int NBLK = STEM_NBLK;
+// NBLK = 2 (16 x 16 tiles: 324 staged pixels for 256 outputs = 27 % halo instead of 41 %) was measured SLOWER at cfg2
+// (0.91 vs 0.86 ms/plane): only three 256-thread groups fit in shared memory and each waits 4 800 cycles per fill for
+// its 72 MMAs with too few other groups to cover it.
+constexpr int TR = 16, TCOL = 8 * NBLK, HR = TR + 2, HC = TCOL + 2, NPX = HR * HC;
 #ifndef STEM_AROWS
-#define STEM_AROWS 186
+#define STEM_AROWS (STEM_NBLK == 1 ? 186 : 330)
 #endif
 constexpr int AROWS = STEM_AROWS;          // operand rows per K chunk: >= NPX; = 2 mod 8 puts the four chunks a half-warp's
                                            // 8-byte stores touch (2 pixels x 8 lanes) in four disjoint groups of 8 banks
-static_assert(AROWS >= 180, "a chunk holds the 18 x 10 halo tile");
+static_assert(AROWS >= NPX && AROWS % 8 == 2, "a chunk holds the halo tile; conflict-free chunk stride");
 constexpr int G = STEM_GROUPS;             // worker groups = operand stages = TMEM accumulators
-constexpr int GROUP_THREADS = 128;
+constexpr int GROUP_THREADS = 128 * NBLK;      // one thread per output pixel = per accumulator row
 constexpr int N_THREADS = 32 + G * GROUP_THREADS;
 constexpr int KC8 = 4, NB = 16;                                          // K chunks; accumulator columns (0-3 and 8-11 used)
 constexpr int A_PLANE = KC8 * AROWS * 16, A_STAGE = 2 * A_PLANE;
@@ -51,8 +58,9 @@ constexpr int SMEM_FIXED = B_BYTES + G * (A_STAGE + TAP_BYTES) + 1024;    // + G
 #define STEM_ACC_STRIDE 32
 #endif
 constexpr int ACC = STEM_ACC_STRIDE;       // TMEM columns between the groups' accumulators
-constexpr int TMEM_COLS = G * ACC <= 32 ? 32 : G * ACC <= 64 ? 64 : G * ACC <= 128 ? 128 : G * ACC <= 256 ? 256 : 512;
-static_assert(G * ACC <= 512 && ACC >= NB, "accumulators exceed the TMEM allocation");
+constexpr int NACC = G * NBLK;             // accumulators: one per group and 8-column block
+constexpr int TMEM_COLS = NACC * ACC <= 32 ? 32 : NACC * ACC <= 64 ? 64 : NACC * ACC <= 128 ? 128 : NACC * ACC <= 256 ? 256 : 512;
+static_assert(NACC * ACC <= 512 && ACC >= NB, "accumulators exceed the TMEM allocation");
 
 struct StemArgs {
     const float* ref;
@@ -133,7 +141,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) cost_stem_tc_kernel(const __grid
         reinterpret_cast<uint4*>(sB)[i] = __ldg(reinterpret_cast<const uint4*>(a.weight) + i);
     if (a.costv_mode != 2)          // stream mode never evaluates a homography
         for (int i = tid; i < a.S * 12; i += N_THREADS) scam[i] = a.cams[i];
-    for (int i = tid; i < G * 4 * SK; i += N_THREADS) sstat[i] = make_float2(0.f, 0.f);
+    for (int i = tid; i < G * 4 * NBLK * SK; i += N_THREADS) sstat[i] = make_float2(0.f, 0.f);
     if (tid == 0) {
         for (int s = 0; s < G; ++s) { tc::mbar_init(&full_a[s], GROUP_THREADS); tc::mbar_init(&done_a[s], 1); }
         tc::mbar_fence_init();
@@ -165,16 +173,19 @@ __global__ void __launch_bounds__(N_THREADS, 1) cost_stem_tc_kernel(const __grid
             const uint32_t a_lo_hi = tc::desc_lo(a_base + g * A_STAGE, AROWS * 16);
             const uint32_t a_lo_lo = tc::desc_lo(a_base + g * A_STAGE + A_PLANE, AROWS * 16);
             if (leader) {
-                const uint32_t dst = tmem_base + g * ACC;
                 if (!(a.dbg & 4))
 #pragma unroll
-                for (int tap = 0; tap < 9; ++tap) {
+                for (int mb = 0; mb < NBLK; ++mb) {          // 8-column block of the tile: 8 staged pixels further
+                    const uint32_t dst = tmem_base + (g * NBLK + mb) * ACC;
 #pragma unroll
-                    for (int ks = 0; ks < 2; ++ks) {
-                        const uint32_t ak = (uint32_t)((2 * ks) * AROWS + (tap / 3) * HC + (tap % 3));      // 16-byte units
-                        const uint32_t bk = (uint32_t)((tap * KC8 + 2 * ks) * NB);
-                        tc::mma_f16_parts(dst, a_lo_hi + ak, A_HI, b_lo + bk, B_HI, idesc, (tap | ks) != 0);
-                        tc::mma_f16_parts(dst, a_lo_lo + ak, A_HI, b_lo + bk, B_HI, idesc, 1);
+                    for (int tap = 0; tap < 9; ++tap) {
+#pragma unroll
+                        for (int ks = 0; ks < 2; ++ks) {
+                            const uint32_t ak = (uint32_t)((2 * ks) * AROWS + (tap / 3) * HC + (tap % 3) + mb * 8);      // 16-byte units
+                            const uint32_t bk = (uint32_t)((tap * KC8 + 2 * ks) * NB);
+                            tc::mma_f16_parts(dst, a_lo_hi + ak, A_HI, b_lo + bk, B_HI, idesc, (tap | ks) != 0);
+                            tc::mma_f16_parts(dst, a_lo_lo + ak, A_HI, b_lo + bk, B_HI, idesc, 1);
+                        }
                     }
                 }
                 tc::mma_commit(&done_a[g]);        // operand stage free AND accumulator complete
@@ -183,14 +194,15 @@ __global__ void __launch_bounds__(N_THREADS, 1) cost_stem_tc_kernel(const __grid
         }
     } else {
         // =========================================== worker groups ===========================================
-        const int g = (warp - 1) / 4, lt = tid - 32 - g * GROUP_THREADS;
+        const int g = (warp - 1) / (4 * NBLK), lt = tid - 32 - g * GROUP_THREADS;
+        const int mb = ((warp - 1) >> 2) % NBLK;                      // 8-column block whose accumulator this warp reads
         const int quad = warp & 3;                                   // TMEM lane quadrant this warp may read
         unsigned char* stage = sA + g * A_STAGE;
         TapRec* taps = reinterpret_cast<TapRec*>(sT + g * TAP_BYTES);
         const uint32_t bar_id = 1 + g;
         constexpr int ITEMS = (NPX * 8 + GROUP_THREADS - 1) / GROUP_THREADS;     // 12 (the last one partial)
         constexpr int NB = STEM_NB;
-        // a thread always handles the same 16-byte slice (4 channels) of its pixels: item j is pixel px0 + 16 j
+        // a thread always handles the same 16-byte slice (4 channels) of its pixels: item j is pixel px0 + (GROUP_THREADS / 8) j
         const int c4i = lt & 7, px0 = lt >> 3;
         const uint32_t st_thread = tc::smem_u32(stage) + (uint32_t)((c4i >> 1) * AROWS * 16 + (c4i & 1) * 8);
         const bool keep_cv = a.costv_mode == 1;
@@ -269,7 +281,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) cost_stem_tc_kernel(const __grid
                     int rk[NB];
 #pragma unroll
                     for (int j = 0; j < NB; ++j) {
-                        const TapRec* rec = taps + min(px0 + (jb + j) * 16, NPX - 1);
+                        const TapRec* rec = taps + min(px0 + (jb + j) * (GROUP_THREADS / 8), NPX - 1);
                         wq[j] = *reinterpret_cast<const float4*>(rec->w);
                         const uint2 br = *reinterpret_cast<const uint2*>(&rec->base);
                         rk[j] = (int)br.y;
@@ -282,7 +294,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) cost_stem_tc_kernel(const __grid
                     }
 #pragma unroll
                     for (int j = 0; j < NB; ++j) {
-                        const int pxr = px0 + (jb + j) * 16;
+                        const int pxr = px0 + (jb + j) * (GROUP_THREADS / 8);
                         // bilinear blend in ATen's order (see gather_taps): fma(se, w, fma(sw, w, fma(ne, w, nw * w))), two channels
                         // per instruction
                         const uint64_t w0 = pk2(wq[j].x, wq[j].x), w1 = pk2(wq[j].y, wq[j].y), w2 = pk2(wq[j].z, wq[j].z), w3 = pk2(wq[j].w, wq[j].w);
@@ -328,7 +340,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) cost_stem_tc_kernel(const __grid
             float4 o;
             {
                 uint32_t r[16];
-                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + g * ACC;
+                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (g * NBLK + mb) * ACC;
                 asm volatile(
                     "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
                     "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
@@ -343,7 +355,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) cost_stem_tc_kernel(const __grid
             tc::tc_fence_before();
             if (pf) pp[5] = clock64();
             const int m = quad * 32 + lane;                             // accumulator row = pixel (m >> 3, m & 7) of the tile
-            const int y = ty * TR + (m >> 3), x = tx * TCOL + (m & 7);
+            const int y = ty * TR + (m >> 3), x = tx * TCOL + mb * 8 + (m & 7);
             float s = 0.f, ss = 0.f;
             const int slot = k * a.S + v;                               // (plane, view) slot of t0 / stats
             if (y < a.H && x < a.W) {
@@ -371,7 +383,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) cost_stem_tc_kernel(const __grid
     if (warp == 0) tc::tmem_dealloc<TMEM_COLS>(tmem_base);
     if (tid < a.K * a.S) {                                                   // stats[k][v][GN1][sum, sumsq]
         double s = 0.0, ss = 0.0;
-        for (int w = 0; w < G * 4; ++w) { s += (double)sstat[w * SK + tid].x; ss += (double)sstat[w * SK + tid].y; }
+        for (int w = 0; w < G * 4 * NBLK; ++w) { s += (double)sstat[w * SK + tid].x; ss += (double)sstat[w * SK + tid].y; }
         atomicAdd(a.stats + tid * 6 + 0, s);
         atomicAdd(a.stats + tid * 6 + 1, ss);
     }
@@ -385,7 +397,7 @@ unsigned long long* g_stem_prof = nullptr;
 extern "C" void aarmvs_debug_flags(int flags) { g_dbg = flags; }
 extern "C" void aarmvs_debug_stem_profile_buffer(void* buf) { g_stem_prof = (unsigned long long*)buf; }
 
-extern "C" int aarmvs_cost_stem_tc_max_slots(void) { return (227 * 1024 - 2048 - SMEM_FIXED) / (G * 4 * 8); }
+extern "C" int aarmvs_cost_stem_tc_max_slots(void) { return (227 * 1024 - 2048 - SMEM_FIXED) / (G * 4 * NBLK * 8); }
 
 extern "C" int aarmvs_cost_stem_tc(const float* ref, const float* src, size_t view_stride, int H, int W, int S,
                                    const float* cams, const void* stem_w_f16, const float* stem_b_host,
@@ -407,9 +419,9 @@ extern "C" int aarmvs_cost_stem_tc(const float* ref, const float* src, size_t vi
     a.prof = g_stem_prof;
     static unsigned long long smem_ok = 0;
     constexpr int SMEM_CAP = 227 * 1024 - 2048;      // the kernel also has ~1 KB of static shared memory
-    static_assert(SMEM_FIXED + G * 4 * 8 * 8 <= SMEM_CAP, "shared memory budget");
+    static_assert(SMEM_FIXED + G * 4 * NBLK * 8 * 8 <= SMEM_CAP, "shared memory budget");
     if (cudaError_t e = ensure_dyn_smem(cost_stem_tc_kernel, SMEM_CAP, smem_ok)) return (int)e;
-    const int SMEM = SMEM_FIXED + G * 4 * planes * S * 8;
+    const int SMEM = SMEM_FIXED + G * 4 * NBLK * planes * S * 8;
     AARMVS_CHECK_ARG(SMEM <= SMEM_CAP);          // planes * S <= aarmvs_cost_stem_tc_max_slots()
     const int ntiles = ((W + TCOL - 1) / TCOL) * ((H + TR - 1) / TR);
     const int sms = aarmvs_sm_count();
