@@ -48,7 +48,7 @@ struct alignas(64) CellArgs {
     int pp_phase[3];            // < 0: single buffer; else the half to read is (d + pp_phase) & 1
     int need_zero;              // K is padded beyond the sources' channels: the pad chunks of every stage must be zero
     int H, W;
-    const __half* weight;       // [9 taps][KC8][2 (hi, lo)][NG][8] fp16
+    const __half* weight;       // [K steps][2 chunks][2 (hi, lo)][NG][8] fp16 (Cfg::NSTEPS steps)
     const float* bias;          // [NG], order [hidden channel][i,f,o,g]
     __half* h_planes;           // [2 ping-pong][2][CH/8][H][W][8]: plane d writes half d & 1
     float* c_blocked;           // [tiles][4 quarters][128][CH/4]
@@ -63,9 +63,14 @@ struct alignas(64) CellArgs {
 template <int KSTEPS, int NG, int NST>
 struct Cfg {
     static constexpr int KC8 = 2 * KSTEPS;                       // 16-byte K chunks (8 channels each)
+    // Cell 4 (40 input channels = 5 chunks): instead of padding every tap to 3 K steps with a zero chunk, the fifth chunk
+    // of TWO taps shares one K = 16 step (the second chunk of an MMA is just a leading-byte-offset away: the next tap's
+    // pixel): 9 x 2 + 5 = 23 K steps instead of 27.
+    static constexpr bool PACK = (KSTEPS == 3 && NG == 32);
+    static constexpr int NSTEPS = PACK ? 23 : 9 * KSTEPS;
     static constexpr int A_PLANE = KC8 * CHUNK_BYTES;            // bytes of one fp16 plane (hi or lo) of one stage
     static constexpr int A_STAGE = 2 * A_PLANE;
-    static constexpr int B_BYTES = 9 * KC8 * 2 * NG * 16;        // [tap][chunk][hi rows | lo rows][16 B]
+    static constexpr int B_BYTES = NSTEPS * 2 * 2 * NG * 16;     // [K step][2 chunks][hi rows | lo rows][16 B]
     static constexpr int SMEM = B_BYTES + NST * A_STAGE + 1024;
     static constexpr int TMEM_COLS = 4 * NG;                     // two accumulators x (hi*hi + lo*hi | hi*lo) column blocks
     static_assert(TMEM_COLS == 128 || TMEM_COLS == 256, "TMEM allocation must be a power of two >= 32");
@@ -170,21 +175,20 @@ __global__ void __launch_bounds__(N_THREADS, 1) convlstm_tma_kernel(const __grid
                 if (pf) a.prof[it * 12 + 0] = clock64();
                 tc::mbar_wait(&empty_a[st], ((it / NST) & 1) ^ 1);
                 if (pf) a.prof[it * 12 + 1] = clock64();
-                const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
-                const int y0 = ty * TR - 1, x0 = (tx * TCOL - 1) * 8;
-                unsigned char* stage = sA + st * C::A_STAGE;
-                if (a.dbg & 1) {
-                    tc::mbar_arrive(&full_a[st]);
-                } else {
-                    tc::mbar_arrive_expect_tx(&full_a[st], bytes);
-                    for (int s = 0; s < nload; ++s) {
-                        unsigned char* dst = stage + cbase[s] * CHUNK_BYTES;
-                        tc::tma_load_5d(dst, &a.map[s], &full_a[st], x0, y0, 0, 0, sel[s]);
-                        tc::tma_load_5d(dst + C::A_PLANE, &a.map[s], &full_a[st], x0, y0, 0, 1, sel[s]);
-                    }
-                }
-                if (pf) a.prof[it * 12 + 2] = a.prof[it * 12 + 3] = clock64();
+                if (a.dbg & 1) tc::mbar_arrive(&full_a[st]);
+                else tc::mbar_arrive_expect_tx(&full_a[st], bytes);
             }
+            __syncwarp();
+            // one lane per (source, hi / lo plane): the up to six tensor copies of a tile are issued by ONE warp instruction
+            // (a single thread issuing them back to back spent ~400 cycles per copy: 2 400 cycles per tile for cell 4,
+            // as long as its MMAs)
+            if (lane < 2 * nload && !(a.dbg & 1)) {
+                const int s = lane >> 1, hl = lane & 1;
+                const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+                unsigned char* dst = sA + st * C::A_STAGE + hl * C::A_PLANE + cbase[s] * CHUNK_BYTES;
+                tc::tma_load_5d(dst, &a.map[s], &full_a[st], (tx * TCOL - 1) * 8, ty * TR - 1, 0, hl, sel[s]);
+            }
+            if (pf) a.prof[it * 12 + 2] = a.prof[it * 12 + 3] = clock64();
             __syncwarp();
         }
     } else if (warp == MMA_WARP) {
@@ -217,14 +221,26 @@ __global__ void __launch_bounds__(N_THREADS, 1) convlstm_tma_kernel(const __grid
 #pragma unroll
             for (int tap = 0; tap < 9; ++tap) {
                 if (leader && !(a.dbg & 8)) {
+                    constexpr int KS_TAP = C::PACK ? 2 : KSTEPS;            // full two-chunk K steps of one tap
 #pragma unroll
-                    for (int ks = 0; ks < KSTEPS; ++ks) {
+                    for (int ks = 0; ks < KS_TAP; ++ks) {
                         const uint32_t ak = (uint32_t)(((2 * ks) * NPX + (tap / 3) * HC + (tap % 3)) * 16) >> 4;
                         // A_hi x [W_hi | W_lo] fills columns [0, NG) (hi*hi) and [NG, 2NG) (hi*lo) in ONE instruction with
                         // N = 2 NG, A_lo x W_hi adds into [0, NG): two A-operand reads per K step instead of three
-                        const uint32_t bk = (uint32_t)((tap * C::KC8 + 2 * ks) * 2 * NG);
+                        const uint32_t bk = (uint32_t)((tap * KS_TAP + ks) * 2 * 2 * NG);
                         tc::mma_f16_parts(dst, a_lo_hi + ak, A_HI, b_lo + bk, B_HI, idesc2, (tap | ks) != 0);
                         tc::mma_f16_parts(dst, a_lo_lo + ak, A_HI, b_lo + bk, B_HI, idesc1, 1);
+                    }
+                    if constexpr (C::PACK) {
+                        if (tap % 2 == 0) {        // chunk 4 of taps (tap, tap + 1) in one K step; tap 8 pairs with itself x zero weights
+                            constexpr int CH4 = 4 * NPX;
+                            const int o0 = (tap / 3) * HC + (tap % 3);
+                            const int o1 = tap == 8 ? o0 : ((tap + 1) / 3) * HC + ((tap + 1) % 3);
+                            const uint32_t sa = a_base + st * C::A_STAGE + (CH4 + o0) * 16;
+                            const uint32_t bk = (uint32_t)((18 + tap / 2) * 2 * 2 * NG);
+                            tc::mma_f16_parts(dst, tc::desc_lo(sa, (o1 - o0) * 16), A_HI, b_lo + bk, B_HI, idesc2, 1);
+                            tc::mma_f16_parts(dst, tc::desc_lo(sa + C::A_PLANE, (o1 - o0) * 16), A_HI, b_lo + bk, B_HI, idesc1, 1);
+                        }
                     }
                 }
                 if (tap == 5 && more) {          // next tile's operands and accumulator
@@ -417,7 +433,7 @@ extern "C" int aarmvs_convlstm_cell_tc(const aarmvs_plane_src* src, int nsrc, in
         csum += ch;
     }
     AARMVS_CHECK_ARG(csum == cin && cin <= 48 && ((uintptr_t)h_planes & 15) == 0 && ((uintptr_t)weight_f16 & 15) == 0);
-    a.need_zero = cin % 16 != 0;
+    a.need_zero = 0;          // K padding is never read: cell 4 packs its fifth chunk (see Cfg::PACK)
     a.H = H; a.W = W; a.weight = (const __half*)weight_f16; a.bias = bias_packed; a.h_planes = (__half*)h_planes;
     a.c_blocked = c_blocked; a.h_f32 = h_f32_pair; a.pooled = (__half*)pooled_planes;
     a.d_host = d_host; a.d_dev = d_dev; a.prof = g_prof; a.dbg = g_cell_dbg;

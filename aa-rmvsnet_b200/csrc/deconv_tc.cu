@@ -104,11 +104,12 @@ __global__ void __launch_bounds__(N_THREADS, 1) deconv_tc_kernel(const __grid_co
             const int st = it % NST;
             if (lane == 0) {
                 tc::mbar_wait(&empty_a[st], ((it / NST) & 1) ^ 1);
-                const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
-                unsigned char* stage = sA + st * A_STAGE;
                 tc::mbar_arrive_expect_tx(&full_a[st], A_STAGE);
-                tc::tma_load_5d(stage, &a.map, &full_a[st], tx * TCOL * 8, ty * TR, 0, 0, sel);
-                tc::tma_load_5d(stage + A_PLANE, &a.map, &full_a[st], tx * TCOL * 8, ty * TR, 0, 1, sel);
+            }
+            __syncwarp();
+            if (lane < 2) {          // hi and lo planes: both copies in one warp instruction
+                const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+                tc::tma_load_5d(sA + st * A_STAGE + lane * A_PLANE, &a.map, &full_a[st], tx * TCOL * 8, ty * TR, 0, lane, sel);
             }
             __syncwarp();
         }

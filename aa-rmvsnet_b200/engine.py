@@ -106,8 +106,8 @@ class Engine:
         for i in range(5):
             w[f"cell{i}.w"], w[f"cell{i}.b"] = pack.lstm_gates(sd[f"{cr}.cell_list.{i}.conv.weight"],
                                                                 sd[f"{cr}.cell_list.{i}.conv.bias"])
-            w[f"cell{i}.wtc"], _ = pack.lstm_gates_f16(sd[f"{cr}.cell_list.{i}.conv.weight"],
-                                                       sd[f"{cr}.cell_list.{i}.conv.bias"])
+            w[f"cell{i}.wtc"], _ = pack.lstm_gates_f16_steps(sd[f"{cr}.cell_list.{i}.conv.weight"],
+                                                             sd[f"{cr}.cell_list.{i}.conv.bias"])
         for i in range(2):
             w[f"deconv{i}.w_host"] = capi.host_floats(pack.deconv_taps(sd[f"{cr}.deconv_{i}.conv.weight"]).reshape(-1).cpu().tolist())
             w[f"deconv{i}.b_host"] = capi.host_floats(sd[f"{cr}.deconv_{i}.conv.bias"].cpu().tolist())

@@ -28,14 +28,24 @@ def lstm_gates(w, b):
     return conv_taps(w[perm]), b[perm].contiguous()
 
 
-def lstm_gates_f16(w, b):
-    """Tensor-core operand of a ConvLSTM cell: [9][cin_pad/8][2 (hi, lo)][4*hidden][8] fp16 (K-major 16-byte chunks of
-    8 input channels, cin padded with zero rows to a multiple of 16; hi and lo rows stacked along N so that
-    A_hi x [W_hi | W_lo] is one MMA) + the fp32 bias, gate order as lstm_gates()."""
+def lstm_gates_f16_steps(w, b):
+    """The same operand arranged by K STEP, [steps][2 chunks][2 (hi, lo)][4*hidden][8] fp16, as csrc/convlstm_tma.cu issues
+    them: per tap one step per 16 input channels; when cin % 16 == 8 (cell 4: 40 channels) the last chunk of taps
+    (0,1) (2,3) (4,5) (6,7) (8,-) shares one step each (9 * 2 + 5 = 23 steps instead of 27 zero-padded ones)."""
     taps, bias = lstm_gates(w, b)                    # [9][cin][n] fp32
-    planes = taps_f16(taps)                          # [2][9][kc8][n][8]
-    # csrc/convlstm_tc.cu stacks hi and lo along N per (tap, chunk): [9][kc8][2][n][8]
-    return planes.permute(1, 2, 0, 3, 4).contiguous(), bias
+    k, cin, n = taps.shape
+    full = cin // 16
+
+    def chunk(t, c0):                                # [2 (hi, lo)][n][8] of channels c0 .. c0+8 of tap t (zeros for t < 0)
+        blk = taps.new_zeros(8, n) if t < 0 else taps[t, c0:c0 + 8]
+        hi = blk.half()
+        lo = (blk - hi.float()).half()
+        return torch.stack([hi.t(), lo.t()])
+
+    steps = [torch.stack([chunk(t, 16 * s), chunk(t, 16 * s + 8)]) for t in range(k) for s in range(full)]
+    if cin % 16:
+        steps += [torch.stack([chunk(t, 16 * full), chunk(t + 1 if t + 1 < k else -1, 16 * full)]) for t in range(0, k, 2)]
+    return torch.stack(steps).contiguous(), bias
 
 
 def taps_f16(taps, n_pad=None):

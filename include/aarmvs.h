@@ -167,8 +167,10 @@ size_t aarmvs_cell_state_floats(int H, int W, int hidden);
 /* The same cell on the tensor cores (tcgen05.mma kind::f16, fp32 accumulation in TMEM), fed by TMA from operand planes.
  * Each K step issues hi*hi + lo*hi + hi*lo, which keeps ~2^-21 relative accuracy per product (single-pass TF32 / BF16
  * fails the parity bar).  Input = concat(src[0..nsrc-1], h_{d-1}); cin counts all of them.
- * weight_f16: [9 taps][cin_pad/8][2 (hi, lo)][4*hidden][8] fp16 with cin_pad = cin rounded up to 16 (zero rows) and the
- * output-channel order [hidden channel][i,f,o,g]; bias_packed as aarmvs_convlstm_cell.
+ * weight_f16: [K steps][2 chunks of 8 input channels][2 (hi, lo)][4*hidden][8] fp16, output-channel order
+ * [hidden channel][i,f,o,g]: per tap one step per 16 input channels; with cin = 40 the fifth chunk of the tap pairs
+ * (0,1) (2,3) (4,5) (6,7) (8,-) shares one step each, after the 18 regular ones (23 steps; pack.lstm_gates_f16_steps);
+ * bias_packed as aarmvs_convlstm_cell.
  * h_planes: ping-pong operand planes [2][2][hidden/8][H][W][8]; plane d reads half (d+1)&1 as h_{d-1} (not at d = 0,
  * where h = c = 0) and writes half d&1.  c_blocked: aarmvs_cell_state_floats() floats, in place.
  * h_f32_pair: optional fp32 copy of h, two [H*W][hidden] halves (half d&1 written) for the deconvolution / head kernels.
