@@ -57,7 +57,7 @@ struct alignas(64) CellArgs {
     int d_host;
     const int* d_dev;
     unsigned long long* prof;   // debug: per-tile clock64 stamps of CTA 0 ([tile][12]), or null
-    int dbg;                    // debug ablation: 1 no TMA loads, 4 epilogue skips global I/O, 8 skip MMAs
+    int dbg;                    // debug ablation: 1 no TMA loads, 4 epilogue skips global I/O, 8 skip MMAs, 16 no transcendentals, 32 no pooling
 };
 
 template <int KSTEPS, int NG, int NST>
@@ -318,6 +318,12 @@ __global__ void __launch_bounds__(N_THREADS, 1) convlstm_tma_kernel(const __grid
 #pragma unroll
             for (int j = 0; j < NHC; ++j) {
                 const float* bb = bias_r + j * 4;
+                if (a.dbg & 16) {          // debug ablation: no transcendental math
+                    cn[j] = (g[j * 4 + 0] + g2[j * 4 + 0]) + bb[0] + cprev[j];
+                    go[j] = (g[j * 4 + 1] + g2[j * 4 + 1]) + (g[j * 4 + 2] + g2[j * 4 + 2]) + (g[j * 4 + 3] + g2[j * 4 + 3]);
+                    ec[j] = 1.0f;
+                    continue;
+                }
                 const float pa = 1.0f + exp_neg((g[j * 4 + 0] + g2[j * 4 + 0]) + bb[0]);      // (hi*hi + lo*hi) + hi*lo, + bias
                 const float pb = 1.0f + exp_neg((g[j * 4 + 1] + g2[j * 4 + 1]) + bb[1]);
                 const float pc = 1.0f + exp_neg((g[j * 4 + 2] + g2[j * 4 + 2]) + bb[2]);
@@ -356,7 +362,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) convlstm_tma_kernel(const __grid
                 }
             }
             if constexpr (NHC == 4) {
-                if (a.pooled) {                    // max_pool2d(h, 2) (drmvsnet.py:148,152): the 2x2 block is lanes ^1, ^8 of this warp
+                if (a.pooled && !(a.dbg & 32)) {    // max_pool2d(h, 2) (drmvsnet.py:148,152): the 2x2 block is lanes ^1, ^8 of this warp
                     float pm[NHC];
 #pragma unroll
                     for (int j = 0; j < NHC; ++j) {

@@ -256,7 +256,7 @@ void aarmvs_debug_stem_profile_buffer(void* buf);
  * epilogue roles per tile.  Pass NULL to switch off. */
 void aarmvs_debug_profile_buffer(void* buf);
 /* Debug ablation switches for aarmvs_convlstm_cell_tc (results become wrong): 1 no TMA loads,
- * 4 no global I/O in the epilogue, 8 no MMAs. */
+ * 4 no global I/O in the epilogue, 8 no MMAs, 16 no gate transcendentals, 32 no max-pool output. */
 void aarmvs_debug_cell_flags(int flags);
 
 #ifdef __cplusplus

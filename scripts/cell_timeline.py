@@ -52,7 +52,7 @@ print("avg per tile: TMA issue %.0f, producer wait %.0f | mma wait full %.0f, wa
     (d[:, 7] - d[:, 6]).float().mean(), (d[:, 9] - d[:, 8]).float().mean(), (d[:, 10] - d[:, 9]).float().mean(), (d[:, 11] - d[:, 10]).float().mean(),
     (d[1:, 7] - d[:-1, 7]).float().mean()))
 
-for flags, name in ((0, "full"), (1, "no TMA loads"), (4, "no epilogue global I/O"), (5, "MMA + handshakes only"), (8, "no MMA"), (13, "handshakes only")):
+for flags, name in ((0, "full"), (1, "no TMA loads"), (4, "no epilogue global I/O"), (5, "MMA + handshakes only"), (8, "no MMA"), (13, "handshakes only"), (16, "no gate transcendentals"), (32, "no max-pool output"), (48, "neither"), (61, "handshakes, no transcendentals, no pool")):
     lib.aarmvs_debug_cell_flags(flags)
     run(); torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
