@@ -39,6 +39,11 @@ struct alignas(64) HeadTcArgs {
     const int* d_dev;
     float *max_prob, *depth_map, *exp_sum, *conf, *cost_volume;
     int* index_map;
+    // optional fused training loss (mvsnet_cls_loss, models/drmvsnet.py:347-381, without the [D][H][W] probability volume)
+    const int* gt_index;        // [H*W] hypothesis nearest to the ground truth (0 where the mask is 0)
+    const float* mask;          // [H*W]
+    float* gt_cost;             // [H*W] state: regularised cost at the ground-truth plane
+    double* loss_sum;           // += sum over pixels of mask * (log(sum_d exp(cost_d)) - cost_gt) at the last plane
 };
 
 __global__ void __launch_bounds__(N_THREADS, CTAS_PER_SM) head_tc_kernel(const __grid_constant__ HeadTcArgs a) {
@@ -116,6 +121,7 @@ __global__ void __launch_bounds__(N_THREADS, CTAS_PER_SM) head_tc_kernel(const _
         const int m = warp * 32 + lane;
         const float depth = a.depth_values[d];
         const size_t n = (size_t)a.H * a.W;
+        float ce_sum = 0.f;
         int it = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
             const int ab = it & 1;
@@ -142,6 +148,12 @@ __global__ void __launch_bounds__(N_THREADS, CTAS_PER_SM) head_tc_kernel(const _
             tc::mbar_arrive(&tmem_empty[ab]);
             if (!valid) continue;
             const float acc = (__uint_as_float(r[0]) + __uint_as_float(r[8])) + a.bias;
+            float gc = 0.f;
+            if (a.gt_index) {
+                const int gi = a.gt_index[p];
+                if (d == gi) { gc = acc; a.gt_cost[p] = acc; }
+                else if (d == a.num_depth - 1) gc = a.gt_cost[p];
+            }
             if (a.cost_volume) a.cost_volume[(size_t)d * n + p] = acc;
             const float prob = expf(acc);
             float mp = mp0;
@@ -154,7 +166,15 @@ __global__ void __launch_bounds__(N_THREADS, CTAS_PER_SM) head_tc_kernel(const _
             const float es = __fadd_rn(es0, prob);
             a.max_prob[p] = mp;
             a.exp_sum[p] = es;
-            if (d == a.num_depth - 1) a.conf[p] = __fdiv_rn(mp, es);
+            if (d == a.num_depth - 1) {
+                a.conf[p] = __fdiv_rn(mp, es);
+                // -log softmax(cost)[gt] = log(sum_d exp(cost_d)) - cost_gt, times the mask (drmvsnet.py:366-369)
+                if (a.gt_index) ce_sum += a.mask[p] * (logf(es) - gc);
+            }
+        }
+        if (a.gt_index && d == a.num_depth - 1) {
+            const double s = warp_sum((double)ce_sum);
+            if (lane == 0) atomicAdd(a.loss_sum, s);
         }
     }
     tc::tc_fence_before();
@@ -166,7 +186,8 @@ __global__ void __launch_bounds__(N_THREADS, CTAS_PER_SM) head_tc_kernel(const _
 
 extern "C" int aarmvs_head_wta_tc(const void* h4_planes, int H, int W, const void* weight_f16, const float* bias_host,
                                   const float* depth_values, int num_depth, int d_host, const int* d_dev, float* max_prob,
-                                  float* depth_map, float* exp_sum, int* index_map, float* conf, float* cost_volume, void* stream) {
+                                  float* depth_map, float* exp_sum, int* index_map, float* conf, float* cost_volume,
+                                  const int* gt_index, const float* gt_mask, float* gt_cost, double* loss_sum, void* stream) {
     AARMVS_CHECK_ARG(h4_planes && weight_f16 && bias_host && depth_values && max_prob && depth_map && exp_sum && index_map && conf);
     AARMVS_CHECK_ARG(H > 0 && W > 0 && num_depth > 0 && ((uintptr_t)h4_planes & 15) == 0 && ((uintptr_t)weight_f16 & 15) == 0);
     HeadTcArgs a = {};
@@ -175,6 +196,8 @@ extern "C" int aarmvs_head_wta_tc(const void* h4_planes, int H, int W, const voi
     a.depth_values = depth_values; a.num_depth = num_depth; a.d_host = d_host; a.d_dev = d_dev;
     a.max_prob = max_prob; a.depth_map = depth_map; a.exp_sum = exp_sum; a.index_map = index_map; a.conf = conf;
     a.cost_volume = cost_volume;
+    AARMVS_CHECK_ARG(!gt_index || (gt_mask && gt_cost && loss_sum));
+    a.gt_index = gt_index; a.mask = gt_mask; a.gt_cost = gt_cost; a.loss_sum = loss_sum;
     static unsigned long long smem_ok = 0;
     if (cudaError_t e = ensure_dyn_smem(head_tc_kernel, SMEM, smem_ok)) return (int)e;
     const int ntiles = ((W + TCOL - 1) / TCOL) * ((H + TR - 1) / TR);

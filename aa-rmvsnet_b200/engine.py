@@ -129,8 +129,8 @@ class Engine:
         return w
 
     # ------------------------------------------------------------------------------------------ workspace
-    def _workspace(self, H, W, N, D, device, keep_cost):
-        key = (H, W, N, D, str(device), keep_cost)
+    def _workspace(self, H, W, N, D, device, keep_cost, with_loss=False):
+        key = (H, W, N, D, str(device), keep_cost, with_loss)
         ws = self._ws.get(key)
         if ws is not None:
             return ws
@@ -186,6 +186,9 @@ class Engine:
         ws["conf"] = torch.empty(P, **f32)
         ws["index"] = torch.empty(P, device=device, dtype=torch.int32)
         ws["cost_volume"] = torch.empty(D, P, **f32) if keep_cost else None
+        # fused training loss (tensor-core path): nearest-hypothesis index, mask, cost at that plane, loss accumulator
+        ws["gt"] = ((torch.zeros(P, device=device, dtype=torch.int32), torch.zeros(P, **f32), torch.zeros(P, **f32),
+                     torch.zeros(1, device=device, dtype=torch.float64)) if with_loss else None)
         self._ws[key] = ws
         return ws
 
@@ -358,6 +361,7 @@ class Engine:
                 capi.check(lib.aarmvs_head_wta_tc(_ptr(ws["hp"][4]), H, W, _ptr(w["head.wtc"]), w["head.b_host"], _ptr(ws["depths"]),
                                                   ws["D"], 0, dptr, _ptr(ws["max_prob"]), _ptr(ws["depth"]), _ptr(ws["exp_sum"]),
                                                   _ptr(ws["index"]), _ptr(ws["conf"]), _ptr(cv) if cv is not None else None,
+                                                  *([_ptr(t) for t in ws["gt"]] if ws["gt"] is not None else [None] * 4),
                                                   stream), "aarmvs_head_wta_tc")
             else:
                 h4 = hsrc(4)
@@ -395,23 +399,50 @@ class Engine:
             self.feature_map(img.to(torch.float32).contiguous(), ws["feat"][0], ws, w, stream)
             return ws["feat"][0].clone()
 
-    def depth_map(self, imgs, proj_matrices, depth_values, keep_cost=False, features=None):
+    @staticmethod
+    def nearest_hypothesis(depth_values, depth_gt, mask):
+        """gt_index of mvsnet_cls_loss (models/drmvsnet.py:357-362): argmin_d |depth_values[d] - depth_gt| (first minimum),
+        zeroed where the mask is 0 -- from the two neighbouring hypotheses of a monotone sampling instead of a [D,H,W]
+        volume.  depth_values [D], depth_gt / mask [H,W] -> int32 [H*W]."""
+        dv = depth_values.to(torch.float32)
+        D = dv.numel()
+        inc = bool(dv[-1] >= dv[0])
+        srt = dv if inc else dv.flip(0)
+        gt = depth_gt.to(torch.float32).reshape(-1)
+        hi = torch.bucketize(gt, srt).clamp(0, D - 1)                  # first sorted hypothesis >= gt
+        lo = (hi - 1).clamp(0, D - 1)
+        if not inc:
+            hi, lo = D - 1 - hi, D - 1 - lo
+        first, second = torch.minimum(lo, hi), torch.maximum(lo, hi)  # argmin keeps the lower index on ties
+        idx = torch.where((dv[second] - gt).abs() < (dv[first] - gt).abs(), second, first)
+        return torch.round(mask.to(torch.float32).reshape(-1) * idx.to(torch.float32)).to(torch.int32)
+
+    def depth_map(self, imgs, proj_matrices, depth_values, keep_cost=False, features=None, loss_gt=None):
         """imgs [N,3,H,W], proj_matrices [N,4,4], depth_values [D] -> dict of [H,W] maps (views of the workspace).
-        features: optional list of N cached [H*W,32] feature tensors (from features()); FeatNet is then skipped."""
+        features: optional list of N cached [H*W,32] feature tensors (from features()); FeatNet is then skipped.
+        loss_gt: optional (depth_gt [H,W], mask [H,W]): the head also accumulates the masked cross entropy of
+        mvsnet_cls_loss -> out["ce_sum"] (float64 scalar tensor), without any [D,H,W] volume (tensor-core path)."""
         device = imgs.device
         if device.type != "cuda":
             raise RuntimeError("aarmvsnet_b200 has no CPU path: inputs must live on a CUDA device")
         with torch.cuda.device(device):          # the C ABI launches on the calling thread's current device
-            return self._depth_map(imgs, proj_matrices, depth_values, keep_cost, features)
+            return self._depth_map(imgs, proj_matrices, depth_values, keep_cost, features, loss_gt)
 
-    def _depth_map(self, imgs, proj_matrices, depth_values, keep_cost, features):
+    def _depth_map(self, imgs, proj_matrices, depth_values, keep_cost, features, loss_gt=None):
         device = imgs.device
         N, _, H, W = imgs.shape
         D = depth_values.shape[0]
         if D < 1:
             raise RuntimeError("depth_values must hold at least one plane")
         w = self._weights(device)
-        ws = self._workspace(H, W, N, D, device, keep_cost)
+        if loss_gt is not None and self.cell_math != "tc":
+            raise RuntimeError("the fused loss lives in the tensor-core head kernel (cell_math='tc')")
+        ws = self._workspace(H, W, N, D, device, keep_cost, loss_gt is not None)
+        if loss_gt is not None:
+            gt_index, gt_mask, _, loss_acc = ws["gt"]
+            gt_index.copy_(self.nearest_hypothesis(depth_values.to(device), loss_gt[0].to(device), loss_gt[1].to(device)))
+            gt_mask.copy_(loss_gt[1].to(device=device, dtype=torch.float32).reshape(-1))
+            loss_acc.zero_()
         stream = ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
         if features is not None:
             if len(features) != N:
@@ -449,4 +480,6 @@ class Engine:
                "index": ws["index"].view(H, W)}
         if keep_cost:
             out["cost_reg"] = ws["cost_volume"].view(D, H, W)
+        if loss_gt is not None:
+            out["ce_sum"] = ws["gt"][3][0]
         return out

@@ -149,6 +149,22 @@ class EMVSNet(nn.Module):
         return prob_volume, None, None
 
 
+    def forward_loss(self, imgs, proj_matrices, depth_values, depth_gt, mask):
+        """Training-phase forward fused with mvsnet_cls_loss (models/drmvsnet.py:272-295 + 347-381): returns
+        (loss, wta_depth_map) = mvsnet_cls_loss(self_train(imgs, ...)[0], depth_gt, mask, depth_values), but the masked
+        cross entropy -log softmax(cost)[gt] = log(sum_d exp(cost_d)) - cost_gt is accumulated by the head kernel plane by
+        plane, so the [B,D,H,W] probability volume is never stored.  No autograd."""
+        B = imgs.shape[0]
+        losses, depths = [], []
+        with torch.no_grad():
+            for b in range(B):
+                o = self._engine.depth_map(imgs[b], proj_matrices[b], depth_values[b], loss_gt=(depth_gt[b], mask[b]))
+                valid = mask[b].to(torch.float32).sum() + 1e-6                      # drmvsnet.py:351
+                losses.append(o["ce_sum"].to(torch.float32) / valid.to(o["ce_sum"].device))
+                depths.append(o["depth"].clone())
+        return torch.stack(losses).mean(), torch.stack(depths)
+
+
 def mvsnet_cls_loss(prob_volume, depth_gt, mask, depth_value, return_prob_map=False):
     """Training loss of the reference (models/drmvsnet.py:347-381), kept as plain tensor ops as SURVEY.md §8 row a16
     prescribes: masked one-hot cross entropy of the probability volume against the hypothesis nearest to the ground

@@ -210,10 +210,14 @@ int aarmvs_head_wta(const aarmvs_conv_src* h4, int H, int W, const float* weight
 
 /* The same head on the tensor cores, fed by TMA from h4's ping-pong operand planes [2][2][1][H][W][8] (half d & 1 is
  * read): two taps per K = 16 MMA.  weight_f16: DEVICE [5 pairs][2 taps][16 rows][8] fp16 with row 0 = hi(w), row 8 = lo(w)
- * for the tap pairs (0,1) (2,3) (4,5) (6,7) (8,-) of tap = ky * 3 + kx; other arguments as aarmvs_head_wta. */
+ * for the tap pairs (0,1) (2,3) (4,5) (6,7) (8,-) of tap = ky * 3 + kx; other arguments as aarmvs_head_wta.
+ * Optional fused training loss (mvsnet_cls_loss, models/drmvsnet.py:347-381, without the [D][H][W] probability volume):
+ * gt_index [H*W] = hypothesis nearest to the ground truth (0 where gt_mask is 0), gt_mask [H*W], gt_cost [H*W] state;
+ * at the last plane *loss_sum += sum_p gt_mask[p] * (log(sum_d exp(cost_d[p])) - cost_gt[p]).  All four NULL: no loss. */
 int aarmvs_head_wta_tc(const void* h4_planes, int H, int W, const void* weight_f16, const float* bias_host,
                        const float* depth_values, int num_depth, int d_host, const int* d_dev, float* max_prob,
-                       float* depth_map, float* exp_sum, int* index_map, float* conf, float* cost_volume, void* stream);
+                       float* depth_map, float* exp_sum, int* index_map, float* conf, float* cost_volume,
+                       const int* gt_index, const float* gt_mask, float* gt_cost, double* loss_sum, void* stream);
 
 /* End of a plane: ++*d_dev and zero `nzero` doubles of GroupNorm sums for the next plane. */
 int aarmvs_next_plane(int* d_dev, double* sums, int nzero, void* stream);

@@ -73,3 +73,26 @@ def test_input_validation():
         m(g["imgs"][..., :46, :].cuda(), g["proj_matrices"].cuda(), g["depth_values"].cuda())   # H % 4 != 0
     with pytest.raises(AssertionError):
         m(g["imgs"].cuda(), g["proj_matrices"][:, :2].cuda(), g["depth_values"].cuda())
+
+
+def test_fused_training_loss_matches_reference():
+    """EMVSNet.forward_loss (cross entropy accumulated in the head kernel, no [D,H,W] volume) against the loss the
+    unmodified reference computed for the same sample, and against mvsnet_cls_loss on our own probability volume."""
+    import aarmvsnet_b200 as aa
+    from conftest import load_golden, load_weights
+    g = load_golden("train_32x40_n3_d6.pt")
+    m = aa.EMVSNet(disparity_level=32, image_scale=1.0, max_h=32, max_w=40, return_depth=False)
+    m.load_state_dict(load_weights(g["ckpt"]), strict=True)
+    m = m.cuda().eval()
+    args = [g[k].cuda() for k in ("imgs", "proj_matrices", "depth_values")]
+    loss, wta = m.forward_loss(*args, g["depth_gt"].cuda(), g["mask"].cuda())
+    torch.testing.assert_close(loss.cpu(), g["loss"], rtol=2e-4, atol=1e-5)
+    prob = m(*args)[0]
+    loss2, wta2 = aa.mvsnet_cls_loss(prob, g["depth_gt"].cuda(), g["mask"].cuda(), g["depth_values"].cuda())
+    torch.testing.assert_close(loss, loss2, rtol=1e-4, atol=1e-5)
+    assert (wta == wta2).float().mean() >= 0.999
+    # nearest-hypothesis index without the [D,H,W] volume == the reference's argmin
+    dv, gt, mk = g["depth_values"][0], g["depth_gt"][0], g["mask"][0]
+    want = torch.round(mk * (dv.view(-1, 1, 1) - gt).abs().argmin(0).float()).int().reshape(-1)
+    got = m._engine.nearest_hypothesis(dv, gt, mk)
+    assert torch.equal(got, want)
