@@ -1,0 +1,61 @@
+"""Host-side weight repacking (aarmvsnet_b200/pack.py): the fp16 (hi, lo) tensor-core operands must reproduce the
+checkpoint tensors (hi + lo = w to fp16-pair accuracy) in the layouts documented in include/aarmvs.h."""
+import torch
+
+from aarmvsnet_b200 import pack
+
+
+def _close(a, b):
+    torch.testing.assert_close(a, b, rtol=0, atol=2e-7 * max(1.0, float(b.abs().max())))
+
+
+def test_lstm_gate_steps_layout():
+    gen = torch.Generator().manual_seed(0)
+    for cin, hid in ((48, 16), (32, 16), (40, 8)):
+        w = torch.randn(4 * hid, cin, 3, 3, generator=gen)
+        b = torch.randn(4 * hid, generator=gen)
+        steps, bias = pack.lstm_gates_f16_steps(w, b)
+        n = 4 * hid
+        assert steps.shape == ((9 * (cin // 16) + (5 if cin % 16 else 0)), 2, 2, n, 8)
+        taps, bias_ref = pack.lstm_gates(w, b)                     # [9][cin][n], gate order [hidden][i,f,o,g]
+        assert torch.equal(bias, bias_ref)
+        full = cin // 16
+        rec = (steps[:, :, 0].float() + steps[:, :, 1].float())    # [steps][2 chunks][n][8]
+        for t in range(9):
+            for s in range(full):
+                for c in range(2):
+                    _close(rec[t * full + s, c].t(), taps[t, 16 * s + 8 * c:16 * s + 8 * c + 8])
+        if cin % 16:                                               # fifth chunk of the tap pairs (0,1) (2,3) (4,5) (6,7) (8,-)
+            for p in range(5):
+                _close(rec[9 * full + p, 0].t(), taps[2 * p, 16 * full:])
+                if 2 * p + 1 < 9:
+                    _close(rec[9 * full + p, 1].t(), taps[2 * p + 1, 16 * full:])
+                else:
+                    assert not rec[9 * full + p, 1].any()
+        # gate order: output channel hc * 4 + g of the packed operand is row g * hidden + hc of the checkpoint
+        _close(taps[4, :, 1 * 4 + 2], w[2 * hid + 1, :, 1, 1])
+
+
+def test_stem_deconv_head_operands():
+    gen = torch.Generator().manual_seed(1)
+    w = torch.randn(4, 32, 3, 3, generator=gen)
+    op = pack.stem_taps_f16(w)                                     # [9][4][16][8]: rows 0-3 hi, 8-11 lo
+    assert op.shape == (9, 4, 16, 8) and not op[:, :, 4:8].any() and not op[:, :, 12:].any()
+    rec = op[:, :, 0:4].float() + op[:, :, 8:12].float()          # [tap][chunk][o][8]
+    _close(rec.permute(2, 1, 3, 0).reshape(4, 32, 3, 3), w)
+    wd = torch.randn(16, 16, 3, 3, generator=gen)                  # ConvTranspose2d [cin][cout][ky][kx]
+    od = pack.deconv_pairs_f16(wd)
+    assert od.shape == (9, 2, 32, 8)
+    for p, (ky, kx) in enumerate(pack.DECONV_PAIRS):
+        rec = od[p, :, :16].float() + od[p, :, 16:].float()       # [chunk][co][8 ci]
+        _close(rec.permute(0, 2, 1).reshape(16, 16), wd[:, :, ky, kx])
+    wh = torch.randn(1, 8, 3, 3, generator=gen)
+    oh = pack.head_pairs_f16(wh)
+    assert oh.shape == (5, 2, 16, 8)
+    for p, pair in enumerate(pack.HEAD_PAIRS):
+        for j, t in enumerate(pair):
+            rec = oh[p, j, 0].float() + oh[p, j, 8].float()
+            if t < 0:
+                assert not oh[p, j].any()
+            else:
+                _close(rec, wh[0, :, t // 3, t % 3])
