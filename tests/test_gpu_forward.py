@@ -96,3 +96,22 @@ def test_fused_training_loss_matches_reference():
     want = torch.round(mk * (dv.view(-1, 1, 1) - gt).abs().argmin(0).float()).int().reshape(-1)
     got = m._engine.nearest_hypothesis(dv, gt, mk)
     assert torch.equal(got, want)
+
+
+@pytest.mark.parametrize("shape", [(16, 16, 2, 1, 8), (16, 24, 3, 3, 8), (20, 12, 2, 9, 4), (8, 8, 3, 5, 2), (28, 36, 9, 17, 16),
+                                   (64, 40, 16, 4, 3)])
+def test_edge_shapes_against_oracle(sd_dtu, shape):
+    """Images smaller than one tile (TMA boxes larger than the tensor), 2 and 16 views, one plane, partial plane batches:
+    the first (eager + capture) and the second (graph replay) call against the CPU oracle."""
+    import aarmvsnet_b200 as aa
+    from oracle import aarmvs_oracle as orc
+    H, W, N, D, pb = shape
+    m = aa.EMVSNet(32, image_scale=1.0, max_h=H, max_w=W, return_depth=True, plane_batch=pb)
+    m.load_state_dict(sd_dtu, strict=True)
+    m = m.cuda().eval()
+    s = aa.synth.make_sample(H, W, N, D, seed=H * W + N)
+    ref = orc.forward_test(sd_dtu, s["imgs"], s["proj_matrices"], s["depth_values"], return_index=True)
+    for _ in range(2):
+        out = m(s["imgs"].cuda(), s["proj_matrices"].cuda(), s["depth_values"].cuda())
+        assert (out["index"].cpu().long() == ref["index"]).float().mean() >= 0.995
+        torch.testing.assert_close(out["photometric_confidence"].cpu(), ref["photometric_confidence"], rtol=0, atol=1e-3)
