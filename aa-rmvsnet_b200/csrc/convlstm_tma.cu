@@ -23,9 +23,8 @@
 // (ky * 10 + kx pixels further) into the same staged data -- no im2col copy, each input pixel is staged once per tile.
 // SBO = 10 * 16 B, LBO = 180 * 16 B (validated by aarmvs_tc_selftest).
 //
-// Warp roles (persistent CTA, one per SM): warps 0-15 epilogue (TMEM -> gates -> c, h; two groups of eight warps on
-// alternate tiles, inside a group two warps per TMEM lane quadrant, each half of the hidden channels), warp 16 TMEM
-// allocation + the single MMA-issuing thread, warp 17 the TMA producer.  NST operand stages (producer <-> MMA) and 2 TMEM accumulators
+// Warp roles (persistent CTA, one per SM): warps 0-15 epilogue (TMEM -> gates -> c, h; four warps per TMEM lane quadrant,
+// each a quarter of the gate columns), warp 16 TMEM allocation + the single MMA-issuing thread, warp 17 the TMA producer.  NST operand stages (producer <-> MMA) and 2 TMEM accumulators
 // (MMA <-> epilogue), all hand-offs through mbarriers; tcgen05.commit releases operand stages and publishes
 // accumulators.  The cell state c is private to this kernel and kept in a tile-blocked layout
 // [tile][quarter of the hidden channels][128 px][CH/4] so that every access is a fully used 128-byte line.
@@ -130,7 +129,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) convlstm_tma_kernel(const __grid
     if (tid < NG) s_bias[tid] = a.bias[tid];
     if (tid == 0) {
         for (int s = 0; s < NST; ++s) { tc::mbar_init(&full_a[s], 1); tc::mbar_init(&empty_a[s], 1); }
-        for (int b = 0; b < 2; ++b) { tc::mbar_init(&tmem_full[b], 1); tc::mbar_init(&tmem_empty[b], N_EPI_WARPS / 2 * 32); }
+        for (int b = 0; b < 2; ++b) { tc::mbar_init(&tmem_full[b], 1); tc::mbar_init(&tmem_empty[b], N_EPI_WARPS * 32); }
         tc::mbar_init(&w_bar, 1);
         tc::mbar_fence_init();
     }
@@ -259,25 +258,23 @@ __global__ void __launch_bounds__(N_THREADS, 1) convlstm_tma_kernel(const __grid
         }
     } else {
         // =========================================== epilogue ===========================================
-        // Two groups of eight warps work on ALTERNATE tiles (group = accumulator buffer), so two epilogues are in flight:
-        // one epilogue is a latency chain (accumulator -> exponentials -> reciprocals -> stores) that a single group could
-        // not hide for the cells whose tile needs few MMAs.  Inside a group a warp owns a TMEM lane quadrant and HALF of
-        // the hidden channels (a whole 8-channel chunk when CH = 16: 16-byte plane stores), processed in two passes of
-        // NCOL gate columns to bound the registers.
-        const int q = warp & 3, grp = warp >> 3, part = (warp >> 2) & 1;
-        constexpr int NCOL = NG / 4, NHQ = CH / 4, NHC = CH / 2;  // per pass: gate columns, hidden channels; per thread: channels
+        const int q = warp & 3, part = warp >> 2;                // TMEM lane quadrant, quarter of the gate columns
+        constexpr int NCOL = NG / 4, NHC = CH / 4;               // gate columns / hidden channels per thread: 16 / 4 or 8 / 2
         const int m = q * 32 + lane;
         const size_t P = (size_t)a.H * a.W;
         __half* hb = a.h_planes + (size_t)(d & 1) * 2 * CHK * P * 8;
         float* hf32 = a.h_f32 ? a.h_f32 + (size_t)(d & 1) * P * CH : nullptr;
         // this thread's NHC channels inside the operand planes: chunk (8 channels) and offset inside its 16-byte element
         const int chunk = (part * NHC) >> 3, sub = (part * NHC) & 7;
-        // previous cell state of this thread's pixel of tile `t`, quarter `qt` of the channels (zero at plane 0 / outside)
-        auto load_c = [&](int t, int qt, float (&cv)[NHQ]) {
+        float bias_r[NCOL];
+#pragma unroll
+        for (int j = 0; j < NCOL; ++j) bias_r[j] = s_bias[part * NCOL + j];
+        // previous cell state of this thread's pixel of tile `t` (zero at plane 0 and outside the image)
+        auto load_c = [&](int t, float (&cv)[NHC]) {
             const int ty = t / tiles_x, tx = t - ty * tiles_x;
             const bool ok = t < ntiles && ty * TR + (m >> 3) < a.H && tx * TCOL + (m & 7) < a.W && d != 0 && !(a.dbg & 4);
-            const float* p = a.c_blocked + (((size_t)t * 4 + qt) * 128 + m) * NHQ;
-            if constexpr (NHQ == 4) {
+            const float* p = a.c_blocked + (((size_t)t * 4 + part) * 128 + m) * NHC;
+            if constexpr (NHC == 4) {
                 const float4 v = ok ? ld4(p) : make_float4(0.f, 0.f, 0.f, 0.f);
                 cv[0] = v.x; cv[1] = v.y; cv[2] = v.z; cv[3] = v.w;
             } else {
@@ -285,100 +282,86 @@ __global__ void __launch_bounds__(N_THREADS, 1) convlstm_tma_kernel(const __grid
                 cv[0] = v.x; cv[1] = v.y;
             }
         };
-        float cnext[2][NHQ];
-        const int step = 2 * (int)gridDim.x;
-        load_c(blockIdx.x + grp * gridDim.x, part * 2, cnext[0]);
-        load_c(blockIdx.x + grp * gridDim.x, part * 2 + 1, cnext[1]);
-        for (int it = grp, tile = blockIdx.x + grp * gridDim.x; tile < ntiles; tile += step, it += 2) {
-            const int ab = grp;
+        float cnext[NHC];
+        load_c(blockIdx.x, cnext);
+        int it = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+            const int ab = it & 1;
             const bool pf = a.prof && blockIdx.x == 0 && tid == 0 && it < 64;
             const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
             const int y = ty * TR + (m >> 3), x = tx * TCOL + (m & 7);
             const bool valid = y < a.H && x < a.W && !(a.dbg & 4);
             const size_t pix = valid ? (size_t)y * a.W + x : 0;
-            float cprev[2][NHQ], hn[NHC];
+            float* cp = a.c_blocked + (((size_t)tile * 4 + part) * 128 + m) * NHC;
+            float cprev[NHC], cn[NHC], hn[NHC];
 #pragma unroll
-            for (int hh = 0; hh < 2; ++hh)
-#pragma unroll
-                for (int j = 0; j < NHQ; ++j) cprev[hh][j] = cnext[hh][j];
-            // this group's NEXT tile: its state is requested now, the latency hides behind this tile's gate math
-            load_c(tile + step, part * 2, cnext[0]);
-            load_c(tile + step, part * 2 + 1, cnext[1]);
+            for (int j = 0; j < NHC; ++j) cprev[j] = cnext[j];
+            // the NEXT tile's state is requested now: its global-load latency hides behind this tile's gate math (with the
+            // small-K cells the accumulator of the next tile is ready before this one's epilogue ends)
+            load_c(tile + gridDim.x, cnext);
             if (pf) a.prof[it * 12 + 8] = clock64();
             tc::mbar_wait_relaxed(&tmem_full[ab], (it >> 1) & 1);
             tc::tc_fence_after();
             if (pf) a.prof[it * 12 + 9] = clock64();
+            float g[NCOL], g2[NCOL];
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + ab * 2 * NG + part * NCOL;
+            if constexpr (NCOL == 16) { tmem_ld16(taddr, g); tmem_ld16(taddr + NG, g2); }
+            else { tmem_ld8(taddr, g); tmem_ld8(taddr + NG, g2); }
+            tc::tc_fence_before();
+            tc::mbar_arrive(&tmem_empty[ab]);                    // accumulator is in registers: release it
+            if (pf) a.prof[it * 12 + 10] = clock64();
+            // pixels outside the image (ragged tiles) see zero operands: finite values that are never stored.
+            // Gates with ONE reciprocal per hidden channel: with a = 1 + e^-i, b = 1 + e^-f, c = 1 + e^-o, d = 1 + e^-2g and
+            // r = 1 / (abcd):  sigmoid(i) = r*cd*b, sigmoid(f) = r*cd*a, sigmoid(o) = r*ab*d, tanh(g) = 2*r*ab*c - 1
+            // (MUFU.EX2 / MUFU.RCP are quarter-rate: 6.5 instead of 10 per channel; relative error a few ulp).
+            float ec[NHC], go[NHC];
 #pragma unroll
-            for (int hh = 0; hh < 2; ++hh) {
-                const int qt = part * 2 + hh;                     // quarter of the hidden channels / gate columns
-                float g[NCOL], g2[NCOL];
-                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + ab * 2 * NG + qt * NCOL;
-                if constexpr (NCOL == 16) { tmem_ld16(taddr, g); tmem_ld16(taddr + NG, g2); }
-                else { tmem_ld8(taddr, g); tmem_ld8(taddr + NG, g2); }
-                if (hh == 1) {
-                    tc::tc_fence_before();
-                    tc::mbar_arrive(&tmem_empty[ab]);            // accumulator is in registers: release it
-                    if (pf) a.prof[it * 12 + 10] = clock64();
+            for (int j = 0; j < NHC; ++j) {
+                const float* bb = bias_r + j * 4;
+                if (a.dbg & 16) {          // debug ablation: no transcendental math
+                    cn[j] = (g[j * 4 + 0] + g2[j * 4 + 0]) + bb[0] + cprev[j];
+                    go[j] = (g[j * 4 + 1] + g2[j * 4 + 1]) + (g[j * 4 + 2] + g2[j * 4 + 2]) + (g[j * 4 + 3] + g2[j * 4 + 3]);
+                    ec[j] = 1.0f;
+                    continue;
                 }
-                // pixels outside the image (ragged tiles) see zero operands: finite values that are never stored.
-                // Gates with ONE reciprocal per hidden channel: with a = 1 + e^-i, b = 1 + e^-f, c = 1 + e^-o, d = 1 + e^-2g and
-                // r = 1 / (abcd):  sigmoid(i) = r*cd*b, sigmoid(f) = r*cd*a, sigmoid(o) = r*ab*d, tanh(g) = 2*r*ab*c - 1
-                // (MUFU.EX2 / MUFU.RCP are quarter-rate: 6.5 instead of 10 per channel; relative error a few ulp).
-                float ec[NHQ], go[NHQ], cn[NHQ];
+                const float pa = 1.0f + exp_neg((g[j * 4 + 0] + g2[j * 4 + 0]) + bb[0]);      // (hi*hi + lo*hi) + hi*lo, + bias
+                const float pb = 1.0f + exp_neg((g[j * 4 + 1] + g2[j * 4 + 1]) + bb[1]);
+                const float pc = 1.0f + exp_neg((g[j * 4 + 2] + g2[j * 4 + 2]) + bb[2]);
+                const float pd = 1.0f + exp_neg2((g[j * 4 + 3] + g2[j * 4 + 3]) + bb[3]);
+                const float pab = pa * pb, pcd = pc * pd;
+                const float r = tc::rcp_approx(pab * pcd);
+                const float rab = r * pcd, rcd = r * pab;                                    // 1/(ab), 1/(cd)
+                const float gi = rab * pb, gf = rab * pa;
+                go[j] = rcd * pd;
+                const float gg = fmaf(2.0f, rcd * pc, -1.0f);
+                cn[j] = __fadd_rn(__fmul_rn(gf, cprev[j]), __fmul_rn(gi, gg));
+                ec[j] = 1.0f + exp_neg2(cn[j]);
+            }
 #pragma unroll
-                for (int j = 0; j < NHQ; ++j) {
-                    const float* bb = s_bias + qt * NCOL + j * 4;
-                    if (a.dbg & 16) {          // debug ablation: no transcendental math
-                        cn[j] = (g[j * 4 + 0] + g2[j * 4 + 0]) + bb[0] + cprev[hh][j];
-                        go[j] = (g[j * 4 + 1] + g2[j * 4 + 1]) + (g[j * 4 + 2] + g2[j * 4 + 2]) + (g[j * 4 + 3] + g2[j * 4 + 3]);
-                        ec[j] = 1.0f;
-                        continue;
-                    }
-                    const float pa = 1.0f + exp_neg((g[j * 4 + 0] + g2[j * 4 + 0]) + bb[0]);      // (hi*hi + lo*hi) + hi*lo, + bias
-                    const float pb = 1.0f + exp_neg((g[j * 4 + 1] + g2[j * 4 + 1]) + bb[1]);
-                    const float pc = 1.0f + exp_neg((g[j * 4 + 2] + g2[j * 4 + 2]) + bb[2]);
-                    const float pd = 1.0f + exp_neg2((g[j * 4 + 3] + g2[j * 4 + 3]) + bb[3]);
-                    const float pab = pa * pb, pcd = pc * pd;
-                    const float r = tc::rcp_approx(pab * pcd);
-                    const float rab = r * pcd, rcd = r * pab;                                    // 1/(ab), 1/(cd)
-                    const float gi = rab * pb, gf = rab * pa;
-                    go[j] = rcd * pd;
-                    const float gg = fmaf(2.0f, rcd * pc, -1.0f);
-                    cn[j] = __fadd_rn(__fmul_rn(gf, cprev[hh][j]), __fmul_rn(gi, gg));
-                    ec[j] = 1.0f + exp_neg2(cn[j]);
-                }
-#pragma unroll
-                for (int j = 0; j < NHQ; j += 2) {           // tanh(c') of two channels with one reciprocal
-                    const float r = tc::rcp_approx(ec[j] * ec[j + 1]);
-                    hn[hh * NHQ + j] = go[j] * fmaf(2.0f, r * ec[j + 1], -1.0f);
-                    hn[hh * NHQ + j + 1] = go[j + 1] * fmaf(2.0f, r * ec[j], -1.0f);
-                }
-                if (valid) {
-                    float* cp = a.c_blocked + (((size_t)tile * 4 + qt) * 128 + m) * NHQ;
-                    if constexpr (NHQ == 4) st4(cp, make_float4(cn[0], cn[1], cn[2], cn[3]));
-                    else *reinterpret_cast<float2*>(cp) = make_float2(cn[0], cn[1]);
-                }
+            for (int j = 0; j < NHC; j += 2) {           // tanh(c') of two channels with one reciprocal
+                const float r = tc::rcp_approx(ec[j] * ec[j + 1]);
+                hn[j] = go[j] * fmaf(2.0f, r * ec[j + 1], -1.0f);
+                hn[j + 1] = go[j + 1] * fmaf(2.0f, r * ec[j], -1.0f);
             }
             if (valid) {
-                if constexpr (NHC == 8) {          // this thread owns chunk `part` of the pixel: one 16-byte element per plane
-                    uint2 h0, l0, h1, l1;
-                    tc::split4_f16(make_float4(hn[0], hn[1], hn[2], hn[3]), h0, l0);
-                    tc::split4_f16(make_float4(hn[4], hn[5], hn[6], hn[7]), h1, l1);
-                    *reinterpret_cast<uint4*>(hb + ((size_t)chunk * P + pix) * 8) = make_uint4(h0.x, h0.y, h1.x, h1.y);
-                    *reinterpret_cast<uint4*>(hb + ((size_t)(CHK + chunk) * P + pix) * 8) = make_uint4(l0.x, l0.y, l1.x, l1.y);
-                    if (hf32) {
-                        st4(hf32 + pix * CH + part * NHC, make_float4(hn[0], hn[1], hn[2], hn[3]));
-                        st4(hf32 + pix * CH + part * NHC + 4, make_float4(hn[4], hn[5], hn[6], hn[7]));
-                    }
-                } else {                           // CH = 8: half a chunk per thread
+                if constexpr (NHC == 4) {
+                    st4(cp, make_float4(cn[0], cn[1], cn[2], cn[3]));
                     uint2 h0, l0;
                     tc::split4_f16(make_float4(hn[0], hn[1], hn[2], hn[3]), h0, l0);
                     *reinterpret_cast<uint2*>(hb + ((size_t)chunk * P + pix) * 8 + sub) = h0;
                     *reinterpret_cast<uint2*>(hb + ((size_t)(CHK + chunk) * P + pix) * 8 + sub) = l0;
                     if (hf32) st4(hf32 + pix * CH + part * NHC, make_float4(hn[0], hn[1], hn[2], hn[3]));
+                } else {
+                    *reinterpret_cast<float2*>(cp) = make_float2(cn[0], cn[1]);
+                    __half hh0, hl0, hh1, hl1;
+                    tc::split_f16_trunc(hn[0], hh0, hl0);
+                    tc::split_f16_trunc(hn[1], hh1, hl1);
+                    *reinterpret_cast<__half2*>(hb + ((size_t)chunk * P + pix) * 8 + sub) = __halves2half2(hh0, hh1);
+                    *reinterpret_cast<__half2*>(hb + ((size_t)(CHK + chunk) * P + pix) * 8 + sub) = __halves2half2(hl0, hl1);
+                    if (hf32) *reinterpret_cast<float2*>(hf32 + pix * CH + part * NHC) = make_float2(hn[0], hn[1]);
                 }
             }
-            if constexpr (NHC == 8) {
+            if constexpr (NHC == 4) {
                 if (a.pooled && !(a.dbg & 32)) {    // max_pool2d(h, 2) (drmvsnet.py:148,152): the 2x2 block is lanes ^1, ^8 of this warp
                     float pm[NHC];
 #pragma unroll
@@ -388,11 +371,10 @@ __global__ void __launch_bounds__(N_THREADS, 1) convlstm_tma_kernel(const __grid
                     }
                     if (valid && !(lane & 9)) {
                         const size_t P4 = P >> 2, pp = (size_t)(y >> 1) * (a.W >> 1) + (x >> 1);
-                        uint2 h0, l0, h1, l1;
+                        uint2 h0, l0;
                         tc::split4_f16(make_float4(pm[0], pm[1], pm[2], pm[3]), h0, l0);
-                        tc::split4_f16(make_float4(pm[4], pm[5], pm[6], pm[7]), h1, l1);
-                        *reinterpret_cast<uint4*>(a.pooled + ((size_t)chunk * P4 + pp) * 8) = make_uint4(h0.x, h0.y, h1.x, h1.y);
-                        *reinterpret_cast<uint4*>(a.pooled + ((size_t)(CHK + chunk) * P4 + pp) * 8) = make_uint4(l0.x, l0.y, l1.x, l1.y);
+                        *reinterpret_cast<uint2*>(a.pooled + ((size_t)chunk * P4 + pp) * 8 + sub) = h0;
+                        *reinterpret_cast<uint2*>(a.pooled + ((size_t)(CHK + chunk) * P4 + pp) * 8 + sub) = l0;
                     }
                 }
             }
