@@ -285,11 +285,11 @@ def run_ours(args):
         per_launch = eng.plane_batch if batched else 1
         # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu captures (cfg2 only)
         traffic_cfg2 = {"cost_stem": 14.810e9, "aggregate": 15.028e9, "omega_stats": 2.92e9, "cell0": 0.721e9, "cell1": 0.114e9,
-                        "cell2": 0.023e9, "cell3": 0.148e9, "cell4": 0.463e9, "head_wta": 0.082e9}   # profiles/r01k_passes_AD, r01p_recurrence
+                        "cell2": 0.023e9, "cell3": 0.145e9, "cell4": 0.462e9, "head_wta": 0.082e9}   # profiles/r01k_passes_AD, r01t_recurrence
         roofline = {"kernel": kname, "bound": bound, "planes_per_launch": per_launch, "ms_per_launch": st[top] * per_launch,
                     "algorithmic_work_per_launch": work * per_launch,
                     "traffic": traffic_cfg2.get(top) if args.workload == "cfg2" else None,
-                    "traffic_source": "ncu --set full, profiles/r01k_passes_AD.txt / r01p_recurrence.txt (pass A includes the 11.6 GB "
+                    "traffic_source": "ncu --set full, profiles/r01k_passes_AD.txt / r01t_recurrence.txt (pass A includes the 11.6 GB "
                                       "costv store per 8-plane launch that replaces pass D's second gather)"}
         if bound == "hbm":
             roofline.update({"achieved": work / (st[top] * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
@@ -305,8 +305,8 @@ def run_ours(args):
                            "frac_of_bf16_sustained": FLOP_PER_PX_PLANE * P / (rec_ms * 1e-3) / 1e12 / pk["bf16_tflops_sustained"],
                            "note": "useful FLOPs counted once; the split-fp16 operands execute 3x as many",
                            # hardware counter of the committed ncu capture (cfg2), not measured in this run
-                           "tensor_pipe_active_pct_ncu": {"cell0": 71.7, "cell1": 56.9, "cell2": 43.4, "cell3": 65.8, "cell4": 43.0,
-                                                          "source": "profiles/r01p_recurrence.txt, sm__pipe_tensor_cycles_active"}
+                           "tensor_pipe_active_pct_ncu": {"cell0": 71.0, "cell1": 50.3, "cell2": 41.2, "cell3": 66.3, "cell4": 40.3,
+                                                          "source": "profiles/r01t_recurrence.txt, sm__pipe_tensor_cycles_active"}
                            if args.workload == "cfg2" else None},
             "warp_aggregate": {"bound": "hbm", "ms_per_plane": wa_ms, "algorithmic_bytes": wa_bytes,
                                "achieved": wa_bytes / (wa_ms * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
