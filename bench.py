@@ -324,7 +324,8 @@ def run_ours(args):
                 "config": dict(config_dict(args.workload), plane_batch=eng.plane_batch), "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": "depth maps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_e2e / args.steps},
-                "gpu_launches": args.steps * (N * 16 + (D // eng.plane_batch) * 4 + D * 9), "roofline": roofline, "cpu_baseline": cpu, **extra}
+                # FeatNet 16 per view; passes A-D 4 per batch; per plane 5 cells + 2 x 2 deconvolution passes + head + next_plane
+                "gpu_launches": args.steps * (N * 16 + -(-D // eng.plane_batch) * 4 + D * 11), "roofline": roofline, "cpu_baseline": cpu, **extra}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
