@@ -50,6 +50,7 @@ PROTOTYPES = {
     "aarmvs_sm_count": (_I, []),
     "aarmvs_conv2d": (_I, [_SRCP, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _I, _P, _P]),
     "aarmvs_deform_conv": (_I, [_SRCP, _I, _I, _P, _P, _P, _P, _P, _P]),
+    "aarmvs_deform_conv_tc": (_I, [_SRCP, _I, _I, _P, _P, _P, _P, _P, _P]),
     "aarmvs_feat_assemble": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P]),
     "aarmvs_warp": (_I, [_P, _P, _I, _I, c_float_p, _F, _I, _P]),
     "aarmvs_omega_stats_bytes": (_SZ, [_I]),

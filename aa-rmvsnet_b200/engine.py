@@ -99,6 +99,7 @@ class Engine:
             w[f"pm{l}.w"] = pack.conv_taps(pm_w, cout_pad=32)
             w[f"pm{l}.b"] = pack.pad_vec(pm_b, 32)
             w[f"dc{l}.w"] = pack.conv_taps(sd[dc + ".0.conv.weight"])
+            w[f"dc{l}.wtc"] = pack.deform_taps_f16(sd[dc + ".0.conv.weight"])
             w[f"dc{l}.b"] = sd[dc + ".0.conv.bias"].contiguous()
             w[f"dc{l}.gn"] = (sd[dc + ".1.weight"].contiguous(), sd[dc + ".1.bias"].contiguous())
             convgn(f"head{l}", f"feature.intraAA.conv{l}")
@@ -225,9 +226,14 @@ class Engine:
             hl, wl, pl = H // s, W // s, P // (s * s)
             x = gn(ws[f"x{l}"], 32, f"conv{l}", f"conv{l}", pl)
             conv(f"pm{l}", [x], hl, wl, 32, 32, 3, 1, ws[f"om{l}"], 32, None)
-            capi.check(lib.aarmvs_deform_conv(ctypes.byref(x), hl, wl, _ptr(ws[f"om{l}"]), _ptr(w[f"dc{l}.w"]),
-                                              _ptr(w[f"dc{l}.b"]), _ptr(ws[f"dc{l}"]), _ptr(sl(f"dc{l}")), stream),
-                       "aarmvs_deform_conv")
+            if self.cell_math == "tc":
+                capi.check(lib.aarmvs_deform_conv_tc(ctypes.byref(x), hl, wl, _ptr(ws[f"om{l}"]), _ptr(w[f"dc{l}.wtc"]),
+                                                     _ptr(w[f"dc{l}.b"]), _ptr(ws[f"dc{l}"]), _ptr(sl(f"dc{l}")), stream),
+                           "aarmvs_deform_conv_tc")
+            else:
+                capi.check(lib.aarmvs_deform_conv(ctypes.byref(x), hl, wl, _ptr(ws[f"om{l}"]), _ptr(w[f"dc{l}.w"]),
+                                                  _ptr(w[f"dc{l}.b"]), _ptr(ws[f"dc{l}"]), _ptr(sl(f"dc{l}")), stream),
+                           "aarmvs_deform_conv")
             ch = 16 if l == 0 else 8
             conv(f"head{l}", [gn(ws[f"dc{l}"], 32, f"dc{l}", f"dc{l}", pl)], hl, wl, 32, ch, 1, 1, ws[f"m{l}"], ch,
                  f"head{l}")

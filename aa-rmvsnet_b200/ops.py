@@ -162,8 +162,9 @@ def deconv_gn_relu(model, index, x):
     return y.permute(1, 0, 2).reshape(2 * H, 2 * W, 16).permute(2, 0, 1).contiguous()
 
 
-def deform_conv(model, level, x):
-    """DeformConv2d.forward (models/module.py:133-189) of feature.intraAA.deformconv{level}[0].  x [32,H,W] -> [32,H,W]."""
+def deform_conv(model, level, x, math=None):
+    """DeformConv2d.forward (models/module.py:133-189) of feature.intraAA.deformconv{level}[0].  x [32,H,W] -> [32,H,W].
+    math: "tc" (tcgen05, gathered split-fp16 operand) or "fma" (fp32 CUDA cores); default = the engine's cell_math."""
     _need_cuda(x)
     eng = model._engine
     lib, dev = eng.lib, x.device
@@ -176,6 +177,10 @@ def deform_conv(model, level, x):
     st = _stream(dev)
     capi.check(lib.aarmvs_conv2d(_src_array(src), 1, H, W, 32, 32, 3, 1, _ptr(w[f"pm{level}.w"]), _ptr(w[f"pm{level}.b"]),
                                  _ptr(om), 32, None, st), "aarmvs_conv2d:pm")
-    capi.check(lib.aarmvs_deform_conv(ctypes.byref(src), H, W, _ptr(om), _ptr(w[f"dc{level}.w"]), _ptr(w[f"dc{level}.b"]),
-                                      _ptr(out), None, st), "aarmvs_deform_conv")
+    if (math or eng.cell_math) == "tc":
+        capi.check(lib.aarmvs_deform_conv_tc(ctypes.byref(src), H, W, _ptr(om), _ptr(w[f"dc{level}.wtc"]), _ptr(w[f"dc{level}.b"]),
+                                             _ptr(out), None, st), "aarmvs_deform_conv_tc")
+    else:
+        capi.check(lib.aarmvs_deform_conv(ctypes.byref(src), H, W, _ptr(om), _ptr(w[f"dc{level}.w"]), _ptr(w[f"dc{level}.b"]),
+                                          _ptr(out), None, st), "aarmvs_deform_conv")
     return _nchw(out, H, W)

@@ -80,6 +80,19 @@ def deconv_taps(w):
     return w.permute(2, 3, 0, 1).contiguous()
 
 
+def deform_taps_f16(w):
+    """DeformConv2d.conv weight [32 out][32 in][3][3] -> B operand of csrc/deform_tc.cu:
+    [9 taps][2 K steps of 16 input channels][2 chunks][64 rows: 0-31 hi(w[o]), 32-63 lo][8] fp16."""
+    cout, cin, k, _ = w.shape
+    taps = w.permute(2, 3, 1, 0).reshape(k * k, cin, cout).float()      # [tap][c][o]
+    hi = taps.half()
+    lo = (taps - hi.float()).half()
+    out = torch.zeros(k * k, cin // 16, 2, 2 * cout, 8, dtype=torch.float16, device=w.device)
+    out[:, :, :, :cout] = hi.view(k * k, cin // 16, 2, 8, cout).permute(0, 1, 2, 4, 3)
+    out[:, :, :, cout:] = lo.view(k * k, cin // 16, 2, 8, cout).permute(0, 1, 2, 4, 3)
+    return out.contiguous()
+
+
 # (ky, kx) of the nine (output parity class, tap) pairs of csrc/deconv_tc.cu, in its issue order
 DECONV_PAIRS = ((1, 1), (1, 2), (1, 0), (2, 1), (0, 1), (2, 2), (2, 0), (0, 2), (0, 0))
 

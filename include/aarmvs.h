@@ -65,6 +65,12 @@ int aarmvs_conv2d(const aarmvs_conv_src* src, int nsrc, int Hin, int Win, int ci
 int aarmvs_deform_conv(const aarmvs_conv_src* x, int H, int W, const float* offmask, const float* weight,
                        const float* bias, float* out, double* out_gn_sums, void* stream);
 
+/* The same layer on the tensor cores (gathered A operand staged as fp16 (hi, lo), 8 lanes per pixel and corner line,
+ * nine taps accumulated in TMEM).  weight_f16: DEVICE [9 taps][2 K steps][2 chunks][64 rows: 0-31 hi(w[o]), 32-63 lo][8]
+ * fp16 (pack.deform_taps_f16); other arguments as aarmvs_deform_conv.  H * W * 128 must stay below 2^32. */
+int aarmvs_deform_conv_tc(const aarmvs_conv_src* x, int H, int W, const float* offmask, const void* weight_f16,
+                          const float* bias, float* out, double* out_gn_sums, void* stream);
+
 /* IntraViewAAModule tail (models/drmvsnet.py:19-24): GroupNorm+ReLU of the three 1x1 outputs, bilinear x2 / x4
  * upsampling with align_corners=True and channel concat -> feature [H][W][32].  m0: [H][W][16], m1: [H/2][W/2][8],
  * m2: [H/4][W/4][8]; sums/weight/bias as in aarmvs_conv_src (2, 1, 1 groups). */

@@ -52,12 +52,14 @@ def test_featnet(ops_dtu, model):
     torch.testing.assert_close(got, ops_dtu["feat_out"], rtol=1e-4, atol=1e-4)
 
 
-def test_deform_conv(ops_dtu, model):
+@pytest.mark.parametrize("math", ["tc", "fma"])
+def test_deform_conv(ops_dtu, model, math):
+    """tc: gathered operand staged as split fp16 for tcgen05; fma: fp32 CUDA-core kernel.  Same tolerance for both."""
     from aarmvsnet_b200 import ops
-    got = ops.deform_conv(model, 1, ops_dtu["deform_in"][0].cuda()).cpu()
+    got = ops.deform_conv(model, 1, ops_dtu["deform_in"][0].cuda(), math=math).cpu()
     torch.testing.assert_close(got, ops_dtu["deform_out"][0], rtol=1e-4, atol=1e-4)
     # large offsets: sampling positions clamp at the padded border (module.py:153-159)
-    big = ops.deform_conv(model, 0, ops_dtu["deform_big_in"][0].cuda()).cpu()
+    big = ops.deform_conv(model, 0, ops_dtu["deform_big_in"][0].cuda(), math=math).cpu()
     torch.testing.assert_close(big, ops_dtu["deform_big_out"][0], rtol=1e-4, atol=5e-4)
 
 

@@ -59,3 +59,20 @@ def test_stem_deconv_head_operands():
                 assert not oh[p, j].any()
             else:
                 _close(rec, wh[0, :, t // 3, t % 3])
+
+
+def test_deform_taps_layout():
+    """B operand of csrc/deform_tc.cu: [9 taps][2 K steps][2 chunks][64 rows: hi(w[o]) | lo(w[o])][8 channels]."""
+    gen = torch.Generator().manual_seed(1)
+    w = torch.randn(32, 32, 3, 3, generator=gen)
+    b = pack.deform_taps_f16(w)
+    assert b.shape == (9, 2, 2, 64, 8) and b.dtype == torch.float16
+    rec = b[:, :, :, :32].float() + b[:, :, :, 32:].float()          # [tap][step][chunk][o][8]
+    for t in range(9):
+        ky, kx = divmod(t, 3)
+        for s in range(2):
+            for c in range(2):
+                c0 = 16 * s + 8 * c
+                _close(rec[t, s, c], w[:, c0:c0 + 8, ky, kx])
+    # hi carries the value to fp16 precision, lo only the remainder
+    assert (b[:, :, :, 32:].float().abs() <= b[:, :, :, :32].float().abs() * 2 ** -10 + 1e-7).all()
