@@ -35,6 +35,11 @@ namespace {
 #ifndef STEM_NB
 #define STEM_NB 2
 #endif
+#ifndef STEM_VREUSE
+#define STEM_VREUSE 0           // 1: gather threads walk columns and keep the lines shared by vertically adjacent pixels in registers
+                                // (40 % fewer line reads; measured SLOWER, 0.911 vs 0.873 ms/plane: the gather phase is bound by
+                                // load latency at two pixels in flight per thread, not by L1 wavefronts)
+#endif
 constexpr int NBLK = STEM_NBLK;
 // NBLK = 2 (16 x 16 tiles: 324 staged pixels for 256 outputs = 27 % halo instead of 41 %) was measured SLOWER at cfg2
 // (0.91 vs 0.86 ms/plane): only three 256-thread groups fit in shared memory and each waits 4 800 cycles per fill for
@@ -53,7 +58,11 @@ constexpr int KC8 = 4, NB = 16;                                          // K ch
 constexpr int A_PLANE = KC8 * AROWS * 16, A_STAGE = 2 * A_PLANE;
 constexpr int B_BYTES = 9 * KC8 * NB * 16;                               // [tap][chunk][16 rows][16 B] = 9216 bytes
 constexpr int TAP_BYTES = NPX * 32;                                      // one TapRec (32 B) per staged pixel
-constexpr int SMEM_FIXED = B_BYTES + G * (A_STAGE + TAP_BYTES) + 1024;    // + G * 4 warps * planes * S * 8 bytes of GroupNorm partial sums
+#ifndef STEM_AHEAD
+#define STEM_AHEAD 1            // recipes of a group's NEXT fill are evaluated while the MMAs of the current one run (two recipe slots)
+#endif
+constexpr int TAP_SLOTS = STEM_AHEAD ? 2 : 1;
+constexpr int SMEM_FIXED = B_BYTES + G * (A_STAGE + TAP_SLOTS * TAP_BYTES) + 1024;    // + G * 4 warps * planes * S * 8 bytes of GroupNorm partial sums
 #ifndef STEM_ACC_STRIDE
 #define STEM_ACC_STRIDE 32
 #endif
@@ -129,7 +138,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) cost_stem_tc_kernel(const __grid
     unsigned char* sA = smem + B_BYTES;
     unsigned char* sT = sA + G * A_STAGE;
     const int SK = a.S * a.K;
-    float2* sstat = reinterpret_cast<float2*>(sT + G * TAP_BYTES);      // [worker warp][(plane, view)] GroupNorm partial sums: no atomics
+    float2* sstat = reinterpret_cast<float2*>(sT + G * TAP_SLOTS * TAP_BYTES);      // [worker warp][(plane, view)] GroupNorm partial sums: no atomics
     __shared__ uint64_t full_a[G], done_a[G];
     __shared__ uint32_t tmem_base_s;
     __shared__ float scam[AARMVS_MAX_SRC * 12];
@@ -198,7 +207,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) cost_stem_tc_kernel(const __grid
         const int mb = ((warp - 1) >> 2) % NBLK;                      // 8-column block whose accumulator this warp reads
         const int quad = warp & 3;                                   // TMEM lane quadrant this warp may read
         unsigned char* stage = sA + g * A_STAGE;
-        TapRec* taps = reinterpret_cast<TapRec*>(sT + g * TAP_BYTES);
+        TapRec* const taps_g = reinterpret_cast<TapRec*>(sT + g * TAP_SLOTS * TAP_BYTES);
         const uint32_t bar_id = 1 + g;
         constexpr int ITEMS = (NPX * 8 + GROUP_THREADS - 1) / GROUP_THREADS;     // 12 (the last one partial)
         constexpr int NB = STEM_NB;
@@ -209,23 +218,22 @@ __global__ void __launch_bounds__(N_THREADS, 1) cost_stem_tc_kernel(const __grid
         const unsigned row_bytes = (unsigned)a.W * 128u;
         // fill it = g, g + G, ... decoded incrementally as (tile slot tl, view v, plane k): it = (tl * S + v) * K + k
         int tl = g / SK, v = (g % SK) / a.K, k = g % a.K, n = 0;
-        for (int it = g; it < total; it += G, ++n) {
-            const int tile = blockIdx.x + tl * gridDim.x;
-            const float depth = depths[k];
-            const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
-            const bool pf = a.prof && blockIdx.x == 0 && g == 0 && lt == 0 && n < 64;
-            unsigned long long* pp = a.prof + n * 8;
-            if (pf) pp[0] = clock64();
-            // ---- 1. gather recipes (not needed when (warp-ref)^2 is streamed from costv)
-            for (int px = lt; px < NPX && a.costv_mode != 2; px += GROUP_THREADS) {
+        // gather recipes of fill (tile slot tl_, view v_, plane k_): one thread per staged pixel (not needed when (warp-ref)^2 is
+        // streamed from costv)
+        auto write_recipes = [&](int tl_, int v_, int k_, TapRec* dst) {
+            if (a.costv_mode == 2) return;
+            const int tile_ = blockIdx.x + tl_ * gridDim.x;
+            const int ty_ = tile_ / tiles_x, tx_ = tile_ - ty_ * tiles_x;
+            const float depth_ = depths[k_];
+            for (int px = lt; px < NPX; px += GROUP_THREADS) {
                 const int r = px / HC, cc = px - r * HC;
-                const int y = ty * TR - 1 + r, x = tx * TCOL - 1 + cc;
+                const int y = ty_ * TR - 1 + r, x = tx_ * TCOL - 1 + cc;
                 TapRec rec;
                 rec.w[0] = rec.w[1] = rec.w[2] = rec.w[3] = 0.f;
                 rec.base = 0u; rec.ref = -1; rec.pad0 = rec.pad1 = 0u;
                 if (y >= 0 && y < a.H && x >= 0 && x < a.W && !(a.dbg & 2)) {
                     float ix, iy;
-                    sweep_position(scam + v * 12, (float)x, (float)y, depth, a.W, a.H, a.align_corners != 0, ix, iy);
+                    sweep_position(scam + v_ * 12, (float)x, (float)y, depth_, a.W, a.H, a.align_corners != 0, ix, iy);
                     const Taps t = make_taps(ix, iy, a.W, a.H);
                     rec.w[0] = t.o_nw >= 0 ? t.w_nw : 0.f; rec.w[1] = t.o_ne >= 0 ? t.w_ne : 0.f;
                     rec.w[2] = t.o_sw >= 0 ? t.w_sw : 0.f; rec.w[3] = t.o_se >= 0 ? t.w_se : 0.f;
@@ -234,8 +242,20 @@ __global__ void __launch_bounds__(N_THREADS, 1) cost_stem_tc_kernel(const __grid
                     rec.base = (unsigned)(yn * a.W + xw) * 128u | (unsigned)(xe - xw) | ((unsigned)(ys - yn) << 1);
                     rec.ref = (y * a.W + x) * 128 + ((r >= 1 && r <= TR && cc >= 1 && cc <= TCOL) ? 1 : 0);
                 }
-                taps[px] = rec;
+                dst[px] = rec;
             }
+        };
+        if (STEM_AHEAD && g < total) write_recipes(tl, v, k, taps_g);
+        for (int it = g; it < total; it += G, ++n) {
+            const int tile = blockIdx.x + tl * gridDim.x;
+            const float depth = depths[k];
+            const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+            const bool pf = a.prof && blockIdx.x == 0 && g == 0 && lt == 0 && n < 64;
+            unsigned long long* pp = a.prof + n * 8;
+            if (pf) pp[0] = clock64();
+            // ---- 1. gather recipes
+            TapRec* const taps = taps_g + (STEM_AHEAD ? (n & 1) * NPX : 0);
+            if (!STEM_AHEAD) write_recipes(tl, v, k, taps);
             // (the stage and the recipes of the previous fill are free: every thread of the group arrived on full[g] after its
             //  last read, and done[g] was observed after the MMAs' last read)
             asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(GROUP_THREADS) : "memory");
@@ -275,6 +295,76 @@ __global__ void __launch_bounds__(N_THREADS, 1) cost_stem_tc_kernel(const __grid
                 const unsigned char* svb = reinterpret_cast<const unsigned char*>(sv) + c4i * 16;
                 const unsigned char* refb = reinterpret_cast<const unsigned char*>(a.ref) + c4i * 16;
                 unsigned char* cvb = reinterpret_cast<unsigned char*>(costv_slot) + c4i * 16;
+                // one staged pixel: blend in ATen's order (see gather_taps): fma(se, w, fma(sw, w, fma(ne, w, nw * w))), two channels
+                // per instruction; (warp - ref)^2; costv line; fp16 split; stage
+                auto finish = [&](const float4& ta, const float4& tb, const float4& tcn, const float4& td, const float4& rv,
+                                  const float4& wq, int rk, int pxr) {
+                    const uint64_t w0 = pk2(wq.x, wq.x), w1 = pk2(wq.y, wq.y), w2 = pk2(wq.z, wq.z), w3 = pk2(wq.w, wq.w);
+                    const uint64_t g01 = fma2(pk2(td.x, td.y), w3, fma2(pk2(tcn.x, tcn.y), w2, fma2(pk2(tb.x, tb.y), w1, mul2(pk2(ta.x, ta.y), w0))));
+                    const uint64_t g23 = fma2(pk2(td.z, td.w), w3, fma2(pk2(tcn.z, tcn.w), w2, fma2(pk2(tb.z, tb.w), w1, mul2(pk2(ta.z, ta.w), w0))));
+                    // outside the image the cost is the conv's zero padding: d * 0 = +-0 exactly (finite features), d * 1 = d
+                    const float inf_ = rk >= 0 ? 1.0f : 0.0f;
+                    const uint64_t in2 = pk2(inf_, inf_);
+                    const uint64_t d01 = mul2(sub2(g01, pk2(rv.x, rv.y)), in2), d23 = mul2(sub2(g23, pk2(rv.z, rv.w)), in2);
+                    const uint64_t c01 = mul2(d01, d01), c23 = mul2(d23, d23);
+                    float4 cv;
+                    upk2(c01, cv.x, cv.y);
+                    upk2(c23, cv.z, cv.w);
+                    if (keep_cv && rk >= 0 && (rk & 1) && pxr < NPX)        // this fill owns the pixel's costv line
+                        *reinterpret_cast<float4*>(cvb + ((unsigned)rk & ~127u)) = cv;
+                    // fp16 split as tc::split4_f16: hi = top 11 mantissa bits, lo = fp16(x - hi)
+                    const float h0 = __uint_as_float(__float_as_uint(cv.x) & 0xFFFFE000u), h1 = __uint_as_float(__float_as_uint(cv.y) & 0xFFFFE000u);
+                    const float h2 = __uint_as_float(__float_as_uint(cv.z) & 0xFFFFE000u), h3 = __uint_as_float(__float_as_uint(cv.w) & 0xFFFFE000u);
+                    float l0, l1, l2, l3;
+                    upk2(sub2(c01, pk2(h0, h1)), l0, l1);
+                    upk2(sub2(c23, pk2(h2, h3)), l2, l3);
+                    const __half2 ha = __floats2half2_rn(h0, h1), hb = __floats2half2_rn(h2, h3);
+                    const __half2 la = __floats2half2_rn(l0, l1), lb = __floats2half2_rn(l2, l3);
+                    const uint2 hi = make_uint2(*reinterpret_cast<const uint32_t*>(&ha), *reinterpret_cast<const uint32_t*>(&hb));
+                    const uint2 lo = make_uint2(*reinterpret_cast<const uint32_t*>(&la), *reinterpret_cast<const uint32_t*>(&lb));
+                    if (pxr < NPX) {
+                        sts64(st_thread + pxr * 16, hi);
+                        sts64(st_thread + A_PLANE + pxr * 16, lo);
+                    }
+                };
+#if STEM_VREUSE
+                // A thread walks UROWS vertically adjacent staged pixels: where the warp is locally a translation, the south
+                // lines of one pixel ARE the north lines of the pixel below (same addresses), so they are taken from registers
+                // instead of being gathered again -- 14 instead of 24 line reads per unit.  The L1 data pipe (one wavefront per
+                // 128-byte line) is what bounds this kernel.
+                constexpr int UROWS = 6, UNITS = (HR / UROWS) * HC;
+                static_assert(HR % UROWS == 0 && UROWS % 2 == 0, "units tile the staged rows");
+#pragma unroll 1
+                for (int u = px0; u < UNITS; u += GROUP_THREADS / 8) {
+                    const int ut = u / HC;
+                    int pxr = ut * (UROWS - 1) * HC + u;                  // (row ut * UROWS, column u - ut * HC)
+                    float4 pc = make_float4(0.f, 0.f, 0.f, 0.f), pd = pc;
+                    unsigned want = 2u;                                   // (north-west line | column step) the registers hold; bit 1 = none
+#pragma unroll 1
+                    for (int jb = 0; jb < UROWS; jb += 2, pxr += 2 * HC) {
+                        const TapRec* rec0 = taps + pxr;
+                        const TapRec* rec1 = rec0 + HC;
+                        const float4 wq0 = *reinterpret_cast<const float4*>(rec0->w), wq1 = *reinterpret_cast<const float4*>(rec1->w);
+                        const uint2 br0 = *reinterpret_cast<const uint2*>(&rec0->base), br1 = *reinterpret_cast<const uint2*>(&rec1->base);
+                        const unsigned a0 = br0.x & ~127u, a1 = a0 + ((br0.x & 1u) << 7), ad = (br0.x & 2u) ? row_bytes : 0u;
+                        const unsigned b0 = br1.x & ~127u, b1 = b0 + ((br1.x & 1u) << 7), bd = (br1.x & 2u) ? row_bytes : 0u;
+                        const bool ra = (br0.x & ~2u) == want;
+                        const bool rb = (br1.x & ~2u) == ((a0 + ad) | (br0.x & 1u));
+                        float4 ta0 = pc, tb0 = pd, ta1, tb1;
+                        if (!ra) { ta0 = ldg4b(svb + a0); tb0 = ldg4b(svb + a1); }
+                        const float4 tc0 = ldg4b(svb + (a0 + ad)), td0 = ldg4b(svb + (a1 + ad));
+                        if (!rb) { ta1 = ldg4b(svb + b0); tb1 = ldg4b(svb + b1); }
+                        const float4 tc1 = ldg4b(svb + (b0 + bd)), td1 = ldg4b(svb + (b1 + bd));
+                        const float4 rv0 = ldg4b(refb + ((unsigned)max((int)br0.y, 0) & ~127u));
+                        const float4 rv1 = ldg4b(refb + ((unsigned)max((int)br1.y, 0) & ~127u));
+                        if (rb) { ta1 = tc0; tb1 = td0; }
+                        finish(ta0, tb0, tc0, td0, rv0, wq0, (int)br0.y, pxr);
+                        finish(ta1, tb1, tc1, td1, rv1, wq1, (int)br1.y, pxr + HC);
+                        pc = tc1; pd = td1;
+                        want = (b0 + bd) | (br1.x & 1u);
+                    }
+                }
+#else
 #pragma unroll 1
                 for (int jb = 0; jb < ITEMS; jb += NB) {
                     float4 ta[NB], tb[NB], tcn[NB], td[NB], rv[NB], wq[NB];
@@ -293,45 +383,19 @@ __global__ void __launch_bounds__(N_THREADS, 1) cost_stem_tc_kernel(const __grid
                         rv[j] = ldg4b(refb + ((unsigned)max(rk[j], 0) & ~127u));
                     }
 #pragma unroll
-                    for (int j = 0; j < NB; ++j) {
-                        const int pxr = px0 + (jb + j) * (GROUP_THREADS / 8);
-                        // bilinear blend in ATen's order (see gather_taps): fma(se, w, fma(sw, w, fma(ne, w, nw * w))), two channels
-                        // per instruction
-                        const uint64_t w0 = pk2(wq[j].x, wq[j].x), w1 = pk2(wq[j].y, wq[j].y), w2 = pk2(wq[j].z, wq[j].z), w3 = pk2(wq[j].w, wq[j].w);
-                        const uint64_t g01 = fma2(pk2(td[j].x, td[j].y), w3, fma2(pk2(tcn[j].x, tcn[j].y), w2,
-                                                  fma2(pk2(tb[j].x, tb[j].y), w1, mul2(pk2(ta[j].x, ta[j].y), w0))));
-                        const uint64_t g23 = fma2(pk2(td[j].z, td[j].w), w3, fma2(pk2(tcn[j].z, tcn[j].w), w2,
-                                                  fma2(pk2(tb[j].z, tb[j].w), w1, mul2(pk2(ta[j].z, ta[j].w), w0))));
-                        // outside the image the cost is the conv's zero padding: d * 0 = +-0 exactly (finite features), d * 1 = d
-                        const float inf_ = rk[j] >= 0 ? 1.0f : 0.0f;
-                        const uint64_t in2 = pk2(inf_, inf_);
-                        const uint64_t d01 = mul2(sub2(g01, pk2(rv[j].x, rv[j].y)), in2), d23 = mul2(sub2(g23, pk2(rv[j].z, rv[j].w)), in2);
-                        const uint64_t c01 = mul2(d01, d01), c23 = mul2(d23, d23);
-                        float4 cv;
-                        upk2(c01, cv.x, cv.y);
-                        upk2(c23, cv.z, cv.w);
-                        if (keep_cv && rk[j] >= 0 && (rk[j] & 1) && pxr < NPX)        // this fill owns the pixel's costv line
-                            *reinterpret_cast<float4*>(cvb + ((unsigned)rk[j] & ~127u)) = cv;
-                        // fp16 split as tc::split4_f16: hi = top 11 mantissa bits, lo = fp16(x - hi)
-                        const float h0 = __uint_as_float(__float_as_uint(cv.x) & 0xFFFFE000u), h1 = __uint_as_float(__float_as_uint(cv.y) & 0xFFFFE000u);
-                        const float h2 = __uint_as_float(__float_as_uint(cv.z) & 0xFFFFE000u), h3 = __uint_as_float(__float_as_uint(cv.w) & 0xFFFFE000u);
-                        float l0, l1, l2, l3;
-                        upk2(sub2(c01, pk2(h0, h1)), l0, l1);
-                        upk2(sub2(c23, pk2(h2, h3)), l2, l3);
-                        const __half2 ha = __floats2half2_rn(h0, h1), hb = __floats2half2_rn(h2, h3);
-                        const __half2 la = __floats2half2_rn(l0, l1), lb = __floats2half2_rn(l2, l3);
-                        const uint2 hi = make_uint2(*reinterpret_cast<const uint32_t*>(&ha), *reinterpret_cast<const uint32_t*>(&hb));
-                        const uint2 lo = make_uint2(*reinterpret_cast<const uint32_t*>(&la), *reinterpret_cast<const uint32_t*>(&lb));
-                        if (pxr < NPX) {
-                            sts64(st_thread + pxr * 16, hi);
-                            sts64(st_thread + A_PLANE + pxr * 16, lo);
-                        }
-                    }
+                    for (int j = 0; j < NB; ++j)
+                        finish(ta[j], tb[j], tcn[j], td[j], rv[j], wq[j], rk[j], px0 + (jb + j) * (GROUP_THREADS / 8));
                 }
+#endif
             }
             if (pf) pp[2] = clock64();
             tc::fence_async_smem();
             tc::mbar_arrive(&full_a[g]);
+            // next fill of this group: (tl2, v2, k2).  Its recipes go to the other slot while this fill's MMAs run: every thread of
+            // the group has passed this fill's bar.sync, i.e. finished reading that slot in the previous fill.
+            int tl2 = tl, v2 = v, k2 = k + G;
+            while (k2 >= a.K) { k2 -= a.K; if (++v2 == a.S) { v2 = 0; ++tl2; } }
+            if (STEM_AHEAD && it + G < total) write_recipes(tl2, v2, k2, taps_g + ((n + 1) & 1) * NPX);
             if (pf) pp[3] = clock64();
             // ---- 3. accumulator row of this thread's pixel -> t0
             tc::mbar_wait_relaxed(&done_a[g], n & 1);
@@ -374,8 +438,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) cost_stem_tc_kernel(const __grid
                 sstat[(warp - 1) * SK + slot] = acc;
             }
             if (pf) pp[6] = clock64();
-            k += G;
-            while (k >= a.K) { k -= a.K; if (++v == a.S) { v = 0; ++tl; } }
+            tl = tl2; v = v2; k = k2;
         }
     }
     tc::tc_fence_before();
