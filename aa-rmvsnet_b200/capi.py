@@ -58,6 +58,8 @@ PROTOTYPES = {
     "aarmvs_cost_stem": (_I, [_P, _P, _SZ, _I, _I, _I, _P, c_float_p, c_float_p, _P, _I, _P, _I, _I, _P, _P, _P]),
     "aarmvs_cost_stem_tc": (_I, [_P, _P, _SZ, _I, _I, _I, _P, _P, c_float_p, _P, _I, _P, _I, _I, _P, _P, _P, _I, _P]),
     "aarmvs_cost_stem_tc_max_slots": (_I, []),
+    "aarmvs_sweep_recipes": (_I, [_I, _I, _I, _P, _P, _I, _P, _I, _I, _P, _P, _P]),
+    "aarmvs_cost_stem_tc_recipes": (_I, [_P, _P, _SZ, _I, _I, _I, _P, _P, c_float_p, _P, _I, _P, _I, _I, _P, _P, _P, _I, _P, _P, _P]),
     "aarmvs_warp_cost": (_I, [_P, _P, _SZ, _I, _I, _I, _P, _P, _I, _P, _I, _I, _P, _P]),
     "aarmvs_omega_stats": (_I, [_I, _P, _I, _I, _I, _I, c_float_p, _P, _P]),
     "aarmvs_aggregate": (_I, [_P, _P, _SZ, _I, _I, _I, _P, c_float_p, _P, _I, _P, _I, _I, _P, _P, _P, _P, _P, _P, _P]),

@@ -85,6 +85,8 @@ struct StemArgs {
     int align_corners;
     float* t0;
     double* stats;
+    const float* rec_w;         // optional precomputed gather recipes (aarmvs_sweep_recipes): weights [K][S][P][4] and
+    const unsigned* rec_base;   //   north-west line | step flags [K][S][P]; null: evaluated here
     float* costv;               // optional [K][S][P][32] (warp-ref)^2: written for the tile's interior pixels (mode 1) so pass D
     int costv_mode;             //   need not gather again, or READ instead of gathering (mode 2: aarmvs_warp_cost wrote it)
     unsigned long long* prof;   // debug: clock64 stamps of group 0 of CTA 0, [64 fills][8]
@@ -130,6 +132,51 @@ __device__ __forceinline__ uint64_t sub2(uint64_t a, uint64_t b) {
 __device__ __forceinline__ float4 ldg4b(const unsigned char* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ void sts64(uint32_t addr, uint2 v) {
     asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(v.x), "r"(v.y) : "memory");
+}
+
+// Sample position of pixel (x, y) in one source view at one depth -> the four bilinear weights (0 for corners outside the
+// image) and the byte offset of the clamped north-west line | column step | row step << 1 (TapRec.w / TapRec.base).
+__device__ __forceinline__ void make_recipe(const float* cam, int x, int y, float depth, int W, int H, bool align_corners,
+                                            float4& wts, unsigned& base) {
+    float ix, iy;
+    sweep_position(cam, (float)x, (float)y, depth, W, H, align_corners, ix, iy);
+    const Taps t = make_taps(ix, iy, W, H);
+    wts = make_float4(t.o_nw >= 0 ? t.w_nw : 0.f, t.o_ne >= 0 ? t.w_ne : 0.f, t.o_sw >= 0 ? t.w_sw : 0.f, t.o_se >= 0 ? t.w_se : 0.f);
+    const int xw = min(max(t.xi, 0), W - 1), xe = min(max(t.xi + 1, 0), W - 1);
+    const int yn = min(max(t.yi, 0), H - 1), ys = min(max(t.yi + 1, 0), H - 1);
+    base = (unsigned)(yn * W + xw) * 128u | (unsigned)(xe - xw) | ((unsigned)(ys - yn) << 1);
+}
+
+// Pass R: the recipes of every (plane, view, pixel) of a plane batch, once and without the halo pixels pass A would
+// re-evaluate per tile (41 % more) -- pass A then only copies them (the recipe arithmetic, four IEEE divisions per sample for
+// bit-exact positions, was 28 % of its issue slots).
+struct RecipeArgs {
+    int H, W, S, K;
+    const float* cams;
+    const float* depth_values;
+    int d_host;
+    const int* d_dev;
+    int align_corners;
+    float* rec_w;
+    unsigned* rec_base;
+};
+
+__global__ void __launch_bounds__(256) sweep_recipes_kernel(const __grid_constant__ RecipeArgs a) {
+    __shared__ float cam[12];
+    const int slot = blockIdx.y, k = slot / a.S, v = slot - k * a.S;
+    if (threadIdx.x < 12) cam[threadIdx.x] = a.cams[v * 12 + threadIdx.x];
+    __syncthreads();
+    const float depth = a.depth_values[plane_index(a.d_host, a.d_dev) + k];
+    const int P = a.H * a.W;
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < P; p += gridDim.x * blockDim.x) {
+        const int y = p / a.W, x = p - y * a.W;
+        float4 wts;
+        unsigned base;
+        make_recipe(cam, x, y, depth, a.W, a.H, a.align_corners != 0, wts, base);
+        const size_t idx = (size_t)slot * P + p;
+        st4(a.rec_w + idx * 4, wts);
+        a.rec_base[idx] = base;
+    }
 }
 
 __global__ void __launch_bounds__(N_THREADS, 1) cost_stem_tc_kernel(const __grid_constant__ StemArgs a) {
@@ -232,14 +279,15 @@ __global__ void __launch_bounds__(N_THREADS, 1) cost_stem_tc_kernel(const __grid
                 rec.w[0] = rec.w[1] = rec.w[2] = rec.w[3] = 0.f;
                 rec.base = 0u; rec.ref = -1; rec.pad0 = rec.pad1 = 0u;
                 if (y >= 0 && y < a.H && x >= 0 && x < a.W && !(a.dbg & 2)) {
-                    float ix, iy;
-                    sweep_position(scam + v_ * 12, (float)x, (float)y, depth_, a.W, a.H, a.align_corners != 0, ix, iy);
-                    const Taps t = make_taps(ix, iy, a.W, a.H);
-                    rec.w[0] = t.o_nw >= 0 ? t.w_nw : 0.f; rec.w[1] = t.o_ne >= 0 ? t.w_ne : 0.f;
-                    rec.w[2] = t.o_sw >= 0 ? t.w_sw : 0.f; rec.w[3] = t.o_se >= 0 ? t.w_se : 0.f;
-                    const int xw = min(max(t.xi, 0), a.W - 1), xe = min(max(t.xi + 1, 0), a.W - 1);
-                    const int yn = min(max(t.yi, 0), a.H - 1), ys = min(max(t.yi + 1, 0), a.H - 1);
-                    rec.base = (unsigned)(yn * a.W + xw) * 128u | (unsigned)(xe - xw) | ((unsigned)(ys - yn) << 1);
+                    float4 wts;
+                    if (a.rec_w) {                               // precomputed by pass R
+                        const size_t idx = (size_t)(k_ * a.S + v_) * P + (size_t)(y * a.W + x);
+                        wts = ldg4(a.rec_w + idx * 4);
+                        rec.base = __ldg(a.rec_base + idx);
+                    } else {
+                        make_recipe(scam + v_ * 12, x, y, depth_, a.W, a.H, a.align_corners != 0, wts, rec.base);
+                    }
+                    rec.w[0] = wts.x; rec.w[1] = wts.y; rec.w[2] = wts.z; rec.w[3] = wts.w;
                     rec.ref = (y * a.W + x) * 128 + ((r >= 1 && r <= TR && cc >= 1 && cc <= TCOL) ? 1 : 0);
                 }
                 dst[px] = rec;
@@ -462,10 +510,11 @@ extern "C" void aarmvs_debug_stem_profile_buffer(void* buf) { g_stem_prof = (uns
 
 extern "C" int aarmvs_cost_stem_tc_max_slots(void) { return (227 * 1024 - 2048 - SMEM_FIXED) / (G * 4 * NBLK * 8); }
 
-extern "C" int aarmvs_cost_stem_tc(const float* ref, const float* src, size_t view_stride, int H, int W, int S,
-                                   const float* cams, const void* stem_w_f16, const float* stem_b_host,
-                                   const float* depth_values, int d_host, const int* d_dev, int planes, int align_corners,
-                                   float* t0, double* stats, float* costv, int costv_mode, void* stream) {
+namespace {
+int launch_cost_stem_tc(const float* ref, const float* src, size_t view_stride, int H, int W, int S, const float* cams,
+                        const void* stem_w_f16, const float* stem_b_host, const float* depth_values, int d_host, const int* d_dev,
+                        int planes, int align_corners, float* t0, double* stats, float* costv, int costv_mode, const float* rec_w,
+                        const unsigned* rec_base, void* stream) {
     AARMVS_CHECK_ARG(t0 && stats && stem_w_f16 && stem_b_host && depth_values && H > 0 && W > 0);
     AARMVS_CHECK_ARG(costv_mode >= 0 && costv_mode <= 2 && (costv_mode == 0 || costv));
     AARMVS_CHECK_ARG(costv_mode == 2 || (ref && src && cams));
@@ -478,6 +527,7 @@ extern "C" int aarmvs_cost_stem_tc(const float* ref, const float* src, size_t vi
     a.depth_values = depth_values; a.d_host = d_host; a.d_dev = d_dev; a.align_corners = align_corners; a.t0 = t0;
     a.stats = stats;
     a.costv = costv; a.costv_mode = costv_mode;
+    a.rec_w = rec_w; a.rec_base = rec_base;
     a.dbg = g_dbg;
     a.prof = g_stem_prof;
     static unsigned long long smem_ok = 0;
@@ -490,5 +540,39 @@ extern "C" int aarmvs_cost_stem_tc(const float* ref, const float* src, size_t vi
     const int sms = aarmvs_sm_count();
     if (sms <= 0) return AARMVS_ERR_ARG;
     cost_stem_tc_kernel<<<ntiles < sms ? ntiles : sms, N_THREADS, SMEM, (cudaStream_t)stream>>>(a);
+    AARMVS_LAUNCH_RESULT();
+}
+}  // namespace
+
+extern "C" int aarmvs_cost_stem_tc(const float* ref, const float* src, size_t view_stride, int H, int W, int S,
+                                   const float* cams, const void* stem_w_f16, const float* stem_b_host,
+                                   const float* depth_values, int d_host, const int* d_dev, int planes, int align_corners,
+                                   float* t0, double* stats, float* costv, int costv_mode, void* stream) {
+    return launch_cost_stem_tc(ref, src, view_stride, H, W, S, cams, stem_w_f16, stem_b_host, depth_values, d_host, d_dev, planes,
+                               align_corners, t0, stats, costv, costv_mode, nullptr, nullptr, stream);
+}
+
+extern "C" int aarmvs_cost_stem_tc_recipes(const float* ref, const float* src, size_t view_stride, int H, int W, int S,
+                                           const float* cams, const void* stem_w_f16, const float* stem_b_host,
+                                           const float* depth_values, int d_host, const int* d_dev, int planes,
+                                           int align_corners, float* t0, double* stats, float* costv, int costv_mode,
+                                           const float* rec_w, const unsigned* rec_base, void* stream) {
+    AARMVS_CHECK_ARG(rec_w && rec_base && costv_mode != 2 && ((uintptr_t)rec_w & 15) == 0);
+    return launch_cost_stem_tc(ref, src, view_stride, H, W, S, cams, stem_w_f16, stem_b_host, depth_values, d_host, d_dev, planes,
+                               align_corners, t0, stats, costv, costv_mode, rec_w, rec_base, stream);
+}
+
+extern "C" int aarmvs_sweep_recipes(int H, int W, int S, const float* cams, const float* depth_values, int d_host,
+                                    const int* d_dev, int planes, int align_corners, float* rec_w, unsigned* rec_base,
+                                    void* stream) {
+    AARMVS_CHECK_ARG(cams && depth_values && rec_w && rec_base && H > 0 && W > 0 && ((uintptr_t)rec_w & 15) == 0);
+    AARMVS_CHECK_ARG(S >= 1 && S <= AARMVS_MAX_SRC && planes >= 1 && planes <= AARMVS_MAX_PLANES);
+    AARMVS_CHECK_ARG((size_t)H * W * 128 < 0xFFFFFFFFull);
+    RecipeArgs a = {};
+    a.H = H; a.W = W; a.S = S; a.K = planes; a.cams = cams; a.depth_values = depth_values; a.d_host = d_host; a.d_dev = d_dev;
+    a.align_corners = align_corners; a.rec_w = rec_w; a.rec_base = rec_base;
+    const int P = H * W;
+    const int bx = (P + 256 * 4 - 1) / (256 * 4);                 // four pixels per thread
+    sweep_recipes_kernel<<<dim3(bx, planes * S), 256, 0, (cudaStream_t)stream>>>(a);
     AARMVS_LAUNCH_RESULT();
 }

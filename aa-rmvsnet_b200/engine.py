@@ -55,7 +55,8 @@ def _psrc_array(*srcs):
 class Engine:
     """Runs EMVSNet.forward's arithmetic for one model instance (weights are re-packed when they change)."""
 
-    def __init__(self, module, align_corners=False, use_graph=True, cell_math="tc", plane_batch=8, keep_costv=True, split_gather=False):
+    def __init__(self, module, align_corners=False, use_graph=True, cell_math="tc", plane_batch=8, keep_costv=True, split_gather=False,
+                 recipes=False):
         if cell_math not in ("tc", "fma"):
             raise ValueError("cell_math must be 'tc' (tcgen05, split-fp16 operands) or 'fma' (fp32 CUDA cores)")
         self.cell_math = cell_math
@@ -63,6 +64,9 @@ class Engine:
         # split_gather: gather once in aarmvs_warp_cost, then stream costv into the stem conv as well (measured slower than
         # the fused pass A at cfg2: 1.25 vs 1.12 ms/plane, the stem kernel's staging/epilogue skeleton dominates either way)
         self.split_gather = split_gather
+        # recipes: pass R (aarmvs_sweep_recipes) evaluates the sample positions of a plane batch once and pass A copies them.
+        # Measured at cfg2: pass R 0.067 + pass A 0.932 ms/plane against 0.948 with the recipes evaluated inside pass A -> off.
+        self.recipes = recipes
         if not 1 <= plane_batch <= 16:
             raise ValueError("plane_batch must be in 1..16")
         self.plane_batch = plane_batch            # planes per launch of passes A-D (L1/L2 reuse of the source features)
@@ -160,6 +164,9 @@ class Engine:
         # (warp - ref)^2 kept by pass A so that pass D streams instead of gathering again (tensor-core path only)
         ws["costv"] = torch.empty(K, S, P, 32, **f32) if tc and self.keep_costv else None
         ws["cost"] = torch.empty(K, P, 32, **f32) if ws["costv"] is None else None
+        if tc and self.recipes and not self.split_gather:
+            ws["rec_w"] = torch.empty(K, S, P, 4, **f32)
+            ws["rec_base"] = torch.empty(K, S, P, device=device, dtype=torch.int32)
         if tc:
             # everything the cells read is kept as fp16 (hi, lo) operand planes [2][C/8][H][W][8] (include/aarmvs.h):
             # cost (pass D), h ping-pong pairs and max-pooled h (cell epilogues), GroupNorm+ReLU'd deconv outputs
@@ -243,7 +250,13 @@ class Engine:
                                             _ptr(g1[0]), _ptr(g1[1]), _ptr(g2[0]), _ptr(g2[1]), H, W, _ptr(out), stream),
                    "aarmvs_feat_assemble")
 
-    def cost_stem(self, ref, src, view_stride, H, W, S, cams, w, depths, d_host, dptr, planes, t0, sums, stream, costv=None):
+    def sweep_recipes(self, H, W, S, cams, depths, d_host, dptr, planes, rec_w, rec_base, stream):
+        """Pass R: sample positions of `planes` planes x S views x H*W pixels -> gather recipes for pass A."""
+        capi.check(self.lib.aarmvs_sweep_recipes(H, W, S, cams, depths, d_host, dptr, planes, int(self.align_corners), rec_w, rec_base,
+                                                 stream), "aarmvs_sweep_recipes")
+
+    def cost_stem(self, ref, src, view_stride, H, W, S, cams, w, depths, d_host, dptr, planes, t0, sums, stream, costv=None,
+                  recipes=None, sweep=True):
         """Pass A (gather, (warp - ref)^2, omega stem conv) on the tensor cores ('tc') or the fp32 FMA pipe ('fma').
         With costv (tc only): the gather runs once in aarmvs_warp_cost and the stem conv streams its result."""
         ac = int(self.align_corners)
@@ -254,6 +267,14 @@ class Engine:
                 mode = 2
             else:
                 mode = 1 if costv is not None else 0
+            if recipes is not None and mode != 2:
+                rec_w, rec_base = recipes
+                if sweep:
+                    self.sweep_recipes(H, W, S, cams, depths, d_host, dptr, planes, rec_w, rec_base, stream)
+                capi.check(self.lib.aarmvs_cost_stem_tc_recipes(ref, src, view_stride, H, W, S, cams, _ptr(w["stem.wtc"]),
+                                                                w["stem.b_host"], depths, d_host, dptr, planes, ac, t0, sums, costv,
+                                                                mode, rec_w, rec_base, stream), "aarmvs_cost_stem_tc_recipes")
+                return
             capi.check(self.lib.aarmvs_cost_stem_tc(ref, src, view_stride, H, W, S, cams, _ptr(w["stem.wtc"]), w["stem.b_host"],
                                                     depths, d_host, dptr, planes, ac, t0, sums, costv, mode, stream),
                        "aarmvs_cost_stem_tc")
@@ -285,8 +306,12 @@ class Engine:
         ps = ws["psums"]
         n_omega = ws["K"] * S * 6
         costv = _ptr(ws["costv"]) if ws["costv"] is not None else None
+        recipes = (_ptr(ws["rec_w"]), _ptr(ws["rec_base"])) if "rec_w" in ws else None
+        if recipes is not None:
+            self.sweep_recipes(H, W, S, _ptr(ws["cams"]), _ptr(ws["depths"]), 0, dptr, nplanes, *recipes, stream)
+            mark("recipes")
         self.cost_stem(ref, src, P * 32, H, W, S, _ptr(ws["cams"]), w, _ptr(ws["depths"]), 0, dptr, nplanes, _ptr(ws["t0"]),
-                       _ptr(ps), stream, costv)
+                       _ptr(ps), stream, costv, recipes, sweep=False)
         mark("cost_stem")
         for stage in (2, 3):
             capi.check(lib.aarmvs_omega_stats(stage, _ptr(ws["t0"]), H, W, S, nplanes, w["tail_host"], _ptr(ps), stream),

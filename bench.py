@@ -163,7 +163,7 @@ def stage_profile(engine, ws, w, batches=3):
             continue
         for (n0, e0), (n1, e1) in zip(marks[:-1], marks[1:]):
             acc.setdefault(n1, []).append(e0.elapsed_time(e1))
-    per_batch = ("cost_stem", "omega_stats", "aggregate")
+    per_batch = ("recipes", "cost_stem", "omega_stats", "aggregate")
     return {k: (sum(v) / batches / K if k in per_batch else sum(v) / len(v)) for k, v in acc.items()}
 
 
@@ -261,8 +261,28 @@ def run_ours(args):
             f1.record()
             torch.cuda.synchronize()
         featnet_ms = f0.elapsed_time(f1)
+        # the deformable layers of the last view alone (SURVEY.md §8d "FeatNet / deformable gather": read x + write y, 128 B/px each,
+        # at the layer's scale; the offset/modulation map adds another 128 B/px read)
+        from aarmvsnet_b200 import capi as _capi
+        from aarmvsnet_b200.engine import _ptr as _p, _src as _mk_src
+        deform = {}
+        for l, sc in enumerate((1, 2, 4)):
+            hl, wl, pl = H // sc, W // sc, (H // sc) * (W // sc)
+            xsrc = _mk_src(ws[f"x{l}"], 32, _capi.SRC_GN_RELU, sums=ws["fsums"][(6, 14, 22)[l]:], gn=w[f"conv{l}.gn"], groups=4, count=8 * pl)
+            d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            for rep in range(2):
+                d0.record()
+                _capi.check(eng.lib.aarmvs_deform_conv_tc(_ct.byref(xsrc), hl, wl, _p(ws[f"om{l}"]), _p(w[f"dc{l}.wtc"]), _p(w[f"dc{l}.b"]),
+                                                          _p(ws[f"dc{l}"]), None, _stream), "aarmvs_deform_conv_tc")
+                d1.record()
+                torch.cuda.synchronize()
+            ms = d0.elapsed_time(d1)
+            deform[f"level{l}"] = {"ms": round(ms, 4), "algorithmic_bytes": 256 * pl, "achieved_gbs": 256 * pl / (ms * 1e-3) / 1e9}
+        deform["kernel"] = "deform_tc_kernel (modulated deformable 3x3 conv: 36 gathered 128-byte lines per pixel, tcgen05 contraction)"
+        deform["bound"] = "hbm by definition (read x + write y); in practice the 36 line gathers per pixel through L1"
+        deform["frac"] = deform["level0"]["achieved_gbs"] / peaks()["hbm_gbs"]
         P = H * W
-        wa_ms = st["cost_stem"] + st["omega_stats"] + st["aggregate"]
+        wa_ms = st.get("recipes", 0.0) + st["cost_stem"] + st["omega_stats"] + st["aggregate"]
         rec_ms = sum(st[k] for k in st if k.startswith(("cell", "deconv", "head")))
         wa_bytes = 128 * P * (N + 1)
         S = N - 1
@@ -300,7 +320,7 @@ def run_ours(args):
         roofline["frac"] = roofline["achieved"] / roofline["peak"]
         extra = {
             "stage_ms_per_plane": {k: round(v, 4) for k, v in st.items()},
-            "featnet_ms_per_depth_map": featnet_ms, "featnet_ms_per_view": featnet_ms / N,
+            "featnet_ms_per_depth_map": featnet_ms, "featnet_ms_per_view": featnet_ms / N, "deform_gather": deform,
             "recurrence": {"ms_per_plane": rec_ms, "achieved_tflops": FLOP_PER_PX_PLANE * P / (rec_ms * 1e-3) / 1e12,
                            "frac_of_bf16_sustained": FLOP_PER_PX_PLANE * P / (rec_ms * 1e-3) / 1e12 / pk["bf16_tflops_sustained"],
                            "note": "useful FLOPs counted once; the split-fp16 operands execute 3x as many",
@@ -324,8 +344,8 @@ def run_ours(args):
                 "config": dict(config_dict(args.workload), plane_batch=eng.plane_batch), "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": "depth maps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_e2e / args.steps},
-                # FeatNet 16 per view; passes A-D 4 per batch; per plane 5 cells + 2 x 2 deconvolution passes + head + next_plane
-                "gpu_launches": args.steps * (N * 16 + -(-D // eng.plane_batch) * 4 + D * 11), "roofline": roofline, "cpu_baseline": cpu, **extra}
+                # FeatNet 16 per view; passes (R,) A-D (5) 4 per batch; per plane 5 cells + 2 x 2 deconvolution passes + head + next_plane
+                "gpu_launches": args.steps * (N * 16 + -(-D // eng.plane_batch) * (5 if "rec_w" in ws else 4) + D * 11), "roofline": roofline, "cpu_baseline": cpu, **extra}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

@@ -116,6 +116,18 @@ int aarmvs_cost_stem_tc(const float* ref, const float* src, size_t view_stride, 
                         const int* d_dev, int planes, int align_corners, float* t0, double* stats, float* costv,
                         int costv_mode, void* stream);
 
+/* Pass R: the gather recipes of pass A for every (plane, source view, pixel) of a plane batch, evaluated once (pass A itself
+ * would re-evaluate them for the halo pixels of every tile): rec_w [planes][S][H*W][4] = the four bilinear weights (0 for a
+ * corner outside the source image), rec_base [planes][S][H*W] = byte offset of the clamped north-west source line | column
+ * step | row step << 1.  Same arithmetic as aarmvs_warp (bit-exact sample positions).  H * W * 128 < 2^32. */
+int aarmvs_sweep_recipes(int H, int W, int S, const float* cams, const float* depth_values, int d_host, const int* d_dev,
+                         int planes, int align_corners, float* rec_w, unsigned* rec_base, void* stream);
+/* aarmvs_cost_stem_tc reading the recipes of aarmvs_sweep_recipes instead of evaluating them (costv_mode 0 or 1). */
+int aarmvs_cost_stem_tc_recipes(const float* ref, const float* src, size_t view_stride, int H, int W, int S, const float* cams,
+                                const void* stem_w_f16, const float* stem_b_host, const float* depth_values, int d_host,
+                                const int* d_dev, int planes, int align_corners, float* t0, double* stats, float* costv,
+                                int costv_mode, const float* rec_w, const unsigned* rec_base, void* stream);
+
 /* Pass A1 (used with costv_mode 2): costv[k][v][p][:] = (warp_v(p) - ref(p))^2 for the `planes` planes starting at d:
  * homo_warping_depthwise (models/module.py:6-38) + the squared difference (models/drmvsnet.py:311), nothing else. */
 int aarmvs_warp_cost(const float* ref, const float* src, size_t view_stride, int H, int W, int S, const float* cams,

@@ -30,6 +30,27 @@ for flags, name in ((0, "full"), (2, "no recipe math"), (4, "no MMA"), (6, "no r
     print(f"{name:24s} {e0.elapsed_time(e1) / 3 / K:.3f} ms/plane")
 lib.aarmvs_debug_flags(0)
 
+# ---- production configuration: costv stored (mode 1); recipes inline vs precomputed by pass R
+def timeit0(fn, reps=3):
+    fn(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps): fn()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps / K
+rec_w, rec_base = torch.empty(K, S, P, 4, device="cuda"), torch.empty(K, S, P, device="cuda", dtype=torch.int32)
+rec = (_ptr(rec_w), _ptr(rec_base))
+def run_a1(recipes=None):
+    eng.cost_stem(_ptr(ws["feat"]), _ptr(ws["feat"], P * 32), P * 32, H, W, S, _ptr(ws["cams"]), w, _ptr(ws["depths"]), 100, None, K,
+                  _ptr(ws["t0"]), _ptr(ws["psums"]), st, _ptr(ws["costv"]), recipes, sweep=False)
+def run_r():
+    eng.sweep_recipes(H, W, S, _ptr(ws["cams"]), _ptr(ws["depths"]), 100, None, K, *rec, st)
+print(f"pass A, costv stored, recipes inline      {timeit0(run_a1):.3f} ms/plane")
+t0_inline = ws["t0"].clone(); cv_inline = ws["costv"][:, :, ::97].clone()
+print(f"pass R (sweep_recipes)                    {timeit0(run_r):.3f} ms/plane")
+print(f"pass A, costv stored, recipes from pass R {timeit0(lambda: run_a1(rec)):.3f} ms/plane")
+print("recipes vs inline: t0 identical", torch.equal(t0_inline, ws["t0"]), " costv identical", torch.equal(cv_inline, ws["costv"][:, :, ::97]))
+
 buf = torch.zeros(64 * 8, dtype=torch.int64, device="cuda")
 lib.aarmvs_debug_stem_profile_buffer(ctypes.c_void_p(buf.data_ptr()))
 run(); torch.cuda.synchronize()
