@@ -36,9 +36,9 @@ namespace {
 #define STEM_NB 2
 #endif
 #ifndef STEM_VREUSE
-#define STEM_VREUSE 0           // 1: gather threads walk columns and keep the lines shared by vertically adjacent pixels in registers
-                                // (40 % fewer line reads; measured SLOWER, 0.911 vs 0.873 ms/plane: the gather phase is bound by
-                                // load latency at two pixels in flight per thread, not by L1 wavefronts)
+#define STEM_VREUSE 1           // gather threads walk columns of six staged pixels and keep the source lines shared by vertically
+                                // adjacent pixels in registers: 14 instead of 24 line reads per column.  (Measured slower before the
+                                // recipes moved off the critical path, 0.911 vs 0.873 ms/plane; with them 0.881 vs 0.932.)
 #endif
 constexpr int NBLK = STEM_NBLK;
 // NBLK = 2 (16 x 16 tiles: 324 staged pixels for 256 outputs = 27 % halo instead of 41 %) was measured SLOWER at cfg2
@@ -58,6 +58,9 @@ constexpr int KC8 = 4, NB = 16;                                          // K ch
 constexpr int A_PLANE = KC8 * AROWS * 16, A_STAGE = 2 * A_PLANE;
 constexpr int B_BYTES = 9 * KC8 * NB * 16;                               // [tap][chunk][16 rows][16 B] = 9216 bytes
 constexpr int TAP_BYTES = NPX * 32;                                      // one TapRec (32 B) per staged pixel
+#ifndef STEM_PREFETCH
+#define STEM_PREFETCH 1         // recipe threads prefetch the source lines of their pixel (west lines only; 2: all four)
+#endif
 #ifndef STEM_AHEAD
 #define STEM_AHEAD 1            // recipes of a group's NEXT fill are evaluated while the MMAs of the current one run (two recipe slots)
 #endif
@@ -288,6 +291,19 @@ __global__ void __launch_bounds__(N_THREADS, 1) cost_stem_tc_kernel(const __grid
                         make_recipe(scam + v_ * 12, x, y, depth_, a.W, a.H, a.align_corners != 0, wts, rec.base);
                     }
                     rec.w[0] = wts.x; rec.w[1] = wts.y; rec.w[2] = wts.z; rec.w[3] = wts.w;
+#if STEM_PREFETCH
+                    {   // the gather of this fill starts thousands of cycles from now (after the current fill's MMAs): pull its
+                        // source lines towards L1 meanwhile (ncu: 40 % of the warp stalls are the gather's first use of a load)
+                        const unsigned char* sb = reinterpret_cast<const unsigned char*>(a.src + (size_t)v_ * a.view_stride);
+                        const unsigned o0 = rec.base & ~127u, ox = (rec.base & 1u) << 7, od = (rec.base & 2u) ? (unsigned)a.W * 128u : 0u;
+                        asm volatile("prefetch.global.L1 [%0];" ::"l"(sb + o0));
+                        if (od) asm volatile("prefetch.global.L1 [%0];" ::"l"(sb + (o0 + od)));
+                        if (ox && (cc == HC - 1 || STEM_PREFETCH > 1)) {      // the east lines are the next pixel's west lines, except in the last column
+                            asm volatile("prefetch.global.L1 [%0];" ::"l"(sb + (o0 + ox)));
+                            if (od) asm volatile("prefetch.global.L1 [%0];" ::"l"(sb + (o0 + ox + od)));
+                        }
+                    }
+#endif
                     rec.ref = (y * a.W + x) * 128 + ((r >= 1 && r <= TR && cc >= 1 && cc <= TCOL) ? 1 : 0);
                 }
                 dst[px] = rec;
@@ -390,12 +406,16 @@ __global__ void __launch_bounds__(N_THREADS, 1) cost_stem_tc_kernel(const __grid
                     unsigned want = 2u;                                   // (north-west line | column step) the registers hold; bit 1 = none
 #pragma unroll 1
                     for (int jb = 0; jb < UROWS; jb += 2, pxr += 2 * HC) {
+                        // (written out for two rows: all loads of both rows are issued before the first use; a generic
+                        //  array-and-loop form of this body was scheduled with row 0's arithmetic ahead of row 1's loads and
+                        //  measured 0.957 instead of 0.881 ms/plane)
                         const TapRec* rec0 = taps + pxr;
                         const TapRec* rec1 = rec0 + HC;
                         const float4 wq0 = *reinterpret_cast<const float4*>(rec0->w), wq1 = *reinterpret_cast<const float4*>(rec1->w);
                         const uint2 br0 = *reinterpret_cast<const uint2*>(&rec0->base), br1 = *reinterpret_cast<const uint2*>(&rec1->base);
                         const unsigned a0 = br0.x & ~127u, a1 = a0 + ((br0.x & 1u) << 7), ad = (br0.x & 2u) ? row_bytes : 0u;
                         const unsigned b0 = br1.x & ~127u, b1 = b0 + ((br1.x & 1u) << 7), bd = (br1.x & 2u) ? row_bytes : 0u;
+                        // a pixel's north lines (and column step) = the south lines of the pixel above: taken from registers
                         const bool ra = (br0.x & ~2u) == want;
                         const bool rb = (br1.x & ~2u) == ((a0 + ad) | (br0.x & 1u));
                         float4 ta0 = pc, tb0 = pd, ta1, tb1;

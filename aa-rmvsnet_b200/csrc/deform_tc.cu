@@ -4,8 +4,9 @@
 //
 // i.e. a GEMM with M = pixels, K = 9 taps x 32 channels, N = 32, whose A operand is GATHERED: per pixel and tap four
 // clamped corner lines (module.py:150-165).  The structure is pass A's (cost_stem_tc.cu): a ring of independent worker
-// groups, each owning an operand stage and a TMEM accumulator.  A group takes a tile of 128 consecutive pixels (one
-// thread per pixel holds its 27 offsets / modulation logits) and walks the nine taps: write the gather recipes of the
+// groups, each owning an operand stage and a TMEM accumulator.  A group takes a tile of 16 x 8 pixels (one thread per
+// pixel holds its 27 offsets / modulation logits; a 2-D tile keeps the 180 source lines its nine taps share in L1 -- with
+// 128 consecutive pixels of one row the footprint was 390 lines and the L1 hit rate 36 %) and walks the nine taps: write the gather recipes of the
 // tap, gather with 8 lanes per pixel (one fully used 128-byte line per corner -- the CUDA-core kernel this replaces had
 // one THREAD per pixel: 32 L1 wavefronts per load instruction, 3.5 ms per full-resolution layer), apply the input's
 // GroupNorm + ReLU, blend in the reference's operation order, split to fp16 (hi, lo), stage a K-major operand; the MMA
@@ -18,7 +19,7 @@
 namespace {
 
 constexpr int G = 5, GROUP_THREADS = 128, N_THREADS = 32 + G * GROUP_THREADS;
-constexpr int TILE = 128;                                              // pixels per tile = accumulator rows
+constexpr int TILE = 128, TILE_R = 16, TILE_C = 8;                     // pixels per tile = accumulator rows; row m = pixel (m / 8, m % 8)
 constexpr int AROWS = 130;                                             // operand rows per K chunk (= 2 mod 8: conflict-free stores)
 constexpr int KC8 = 4;                                                 // 32 channels of one tap
 constexpr int A_PLANE = KC8 * AROWS * 16, A_STAGE = 2 * A_PLANE;       // 8320, 16640
@@ -87,8 +88,8 @@ __global__ void __launch_bounds__(N_THREADS, 1) deform_tc_kernel(const __grid_co
     tc::tc_fence_after();
     const uint32_t tmem_base = tmem_base_s;
 
-    const int n = a.H * a.W;
-    const int ntiles = (n + TILE - 1) / TILE;
+    const int tiles_x = (a.W + TILE_C - 1) / TILE_C;
+    const int ntiles = tiles_x * ((a.H + TILE_R - 1) / TILE_R);
     const int my_tiles = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
     if (warp == 0) {
@@ -145,10 +146,12 @@ __global__ void __launch_bounds__(N_THREADS, 1) deform_tc_kernel(const __grid_co
         int n_it = 0;
         for (int tl = g; tl < my_tiles; tl += G) {
           const int tile = blockIdx.x + tl * gridDim.x;
-          const int p = tile * TILE + lt;                               // this thread's pixel for the recipes
+          const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+          const int pi = ty * TILE_R + (lt >> 3), pj = tx * TILE_C + (lt & 7);    // this thread's pixel for the recipes
+          const bool valid = pi < a.H && pj < a.W;
           float om[27];
           {
-              const float* q = a.offmask + (size_t)min(p, n - 1) * 32;
+              const float* q = a.offmask + (valid ? (size_t)(pi * a.W + pj) * 32 : 0);
 #pragma unroll
               for (int c = 0; c < 24; c += 4) {
                   const float4 t = ldg4(q + c);
@@ -157,7 +160,6 @@ __global__ void __launch_bounds__(N_THREADS, 1) deform_tc_kernel(const __grid_co
               const float4 t = ldg4(q + 24);
               om[24] = t.x; om[25] = t.y; om[26] = t.z;
           }
-          const int pi = p / a.W, pj = p - pi * a.W;
 #pragma unroll 1
           for (int k = 0; k < 9; ++k, ++n_it) {
             // ---- 1. recipe of pixel lt for tap k (module.py:150-165, 201-219: positions in the zero-padded image)
@@ -166,7 +168,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) deform_tc_kernel(const __grid_co
                 rec.o[0] = rec.o[1] = rec.o[2] = rec.o[3] = 0u;
                 rec.g[0] = rec.g[1] = rec.g[2] = rec.g[3] = 0.f;
                 rec.m = 0.f; rec.pad0 = rec.pad1 = rec.pad2 = 0.f;
-                if (p < n) {
+                if (valid) {
                     float o_r = 0.f, o_c = 0.f, o_m = 0.f;
 #pragma unroll
                     for (int t = 0; t < 9; ++t)
@@ -247,9 +249,9 @@ __global__ void __launch_bounds__(N_THREADS, 1) deform_tc_kernel(const __grid_co
             tc::tmem_ld32(taddr, acc);
             tc::tmem_ld32(taddr + 32, acc2);
             tc::tc_fence_before();                                       // ordered before this thread's next arrive on full[g]
-            const int po = tile * TILE + quad * 32 + lane;
-            if (po < n) {
-                float* o = a.out + (size_t)po * 32;
+            const int m = quad * 32 + lane, oy = ty * TILE_R + (m >> 3), ox = tx * TILE_C + (m & 7);
+            if (oy < a.H && ox < a.W) {
+                float* o = a.out + (size_t)(oy * a.W + ox) * 32;
 #pragma unroll
                 for (int c = 0; c < 32; c += 4) {
                     const float4 r = make_float4((acc[c] + acc2[c]) + s_bias[c], (acc[c + 1] + acc2[c + 1]) + s_bias[c + 1],
@@ -292,7 +294,7 @@ extern "C" int aarmvs_deform_conv_tc(const aarmvs_conv_src* x, int H, int W, con
     a.bias = bias; a.out = out; a.out_stats = out_gn_sums;
     static unsigned long long smem_ok = 0;
     if (cudaError_t e = ensure_dyn_smem(deform_tc_kernel, SMEM, smem_ok)) return (int)e;
-    const int ntiles = (H * W + TILE - 1) / TILE;
+    const int ntiles = ((W + TILE_C - 1) / TILE_C) * ((H + TILE_R - 1) / TILE_R);
     const int sms = aarmvs_sm_count();
     if (sms <= 0) return AARMVS_ERR_ARG;
     deform_tc_kernel<<<ntiles < sms ? ntiles : sms, N_THREADS, SMEM, (cudaStream_t)stream>>>(a);
