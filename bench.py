@@ -304,12 +304,12 @@ def run_ours(args):
         batched = top in ("cost_stem", "omega_stats", "aggregate")       # one launch covers plane_batch planes
         per_launch = eng.plane_batch if batched else 1
         # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu captures (cfg2 only)
-        traffic_cfg2 = {"cost_stem": 14.810e9, "aggregate": 15.028e9, "omega_stats": 2.92e9, "cell0": 0.721e9, "cell1": 0.114e9,
-                        "cell2": 0.023e9, "cell3": 0.145e9, "cell4": 0.462e9, "head_wta": 0.082e9}   # profiles/r01k_passes_AD, r01t_recurrence
+        traffic_cfg2 = {"cost_stem": 14.961e9, "aggregate": 15.028e9, "omega_stats": 2.92e9, "cell0": 0.721e9, "cell1": 0.114e9,
+                        "cell2": 0.023e9, "cell3": 0.145e9, "cell4": 0.462e9, "head_wta": 0.082e9}   # profiles/r01x_pass_a, r01k_passes_AD, r01t_recurrence
         roofline = {"kernel": kname, "bound": bound, "planes_per_launch": per_launch, "ms_per_launch": st[top] * per_launch,
                     "algorithmic_work_per_launch": work * per_launch,
                     "traffic": traffic_cfg2.get(top) if args.workload == "cfg2" else None,
-                    "traffic_source": "ncu --set full, profiles/r01k_passes_AD.txt / r01t_recurrence.txt (pass A includes the 11.6 GB "
+                    "traffic_source": "ncu --set full, profiles/r01x_pass_a.txt / r01k_passes_AD.txt / r01t_recurrence.txt (pass A includes the 11.6 GB "
                                       "costv store per 8-plane launch that replaces pass D's second gather)"}
         if bound == "hbm":
             roofline.update({"achieved": work / (st[top] * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
