@@ -97,3 +97,24 @@ def test_cfg2_full_size_properties():
     b = _run(m, s)
     assert (a["index"] == b["index"]).float().mean().item() >= 0.99999
     torch.testing.assert_close(a["photometric_confidence"], b["photometric_confidence"], rtol=1e-4, atol=1e-5)
+
+
+def test_cfg4_full_size_properties_and_recipe_path():
+    """BASELINE cfg4 (Tanks&Temples shape 1920x1056, N=7, D=512, model_blended_v2.ckpt, inverse depths): the same
+    size-independent properties as cfg2, plus a cross-check of two kernel paths at full size -- pass A copying the gather
+    recipes of pass R (aarmvs_sweep_recipes) must reproduce pass A evaluating them itself bit for bit."""
+    from aarmvsnet_b200 import synth
+    H, W, N, D = 1056, 1920, 7, 512
+    s = synth.make_sample(H, W, N, D, seed=4, depth_mode="inverse")
+    a = _run(_model(H, W, ckpt="model_blended_v2.ckpt"), s)
+    dv = s["depth_values"][0].cuda()
+    idx = a["index"][0].long()
+    assert idx.min().item() >= 0 and idx.max().item() < D
+    assert torch.equal(a["depth"][0], dv[idx])
+    conf = a["photometric_confidence"][0]
+    assert torch.isfinite(conf).all() and conf.min().item() > 0 and conf.max().item() <= 1.0
+    assert idx.float().std().item() > 1.0
+    torch.cuda.empty_cache()
+    b = _run(_model(H, W, ckpt="model_blended_v2.ckpt", recipes=True), s)
+    assert torch.equal(a["index"], b["index"])
+    assert torch.equal(a["photometric_confidence"], b["photometric_confidence"])
