@@ -118,3 +118,22 @@ def test_cfg4_full_size_properties_and_recipe_path():
     b = _run(_model(H, W, ckpt="model_blended_v2.ckpt", recipes=True), s)
     assert torch.equal(a["index"], b["index"])
     assert torch.equal(a["photometric_confidence"], b["photometric_confidence"])
+
+
+def test_cfg2_full_resolution_few_planes_against_oracle():
+    """BASELINE cfg2's image size and view count (1600x1184, N=7) with D=6 planes, against the CPU oracle run on the box's host
+    cores (~40 s): the tiling, the 32-bit byte offsets and the ragged last tiles of every kernel at the real resolution, where
+    the full D=512 run is only property-checked."""
+    from aarmvsnet_b200 import synth
+    from oracle import aarmvs_oracle as orc
+    H, W, N, D = 1184, 1600, 7, 6
+    s = synth.make_sample(H, W, N, D, seed=5, smooth=True)
+    out = _run(_model(H, W), s)
+    ref = orc.forward_test(load_weights("model_dtu_v2.ckpt"), s["imgs"], s["proj_matrices"], s["depth_values"], return_index=True)
+    idx = out["index"].cpu().long()
+    same = idx == ref["index"]
+    mismatch = 1.0 - same.float().mean().item()
+    print(f"cfg2 resolution, D=6: plane mismatch fraction {mismatch:.2e} on {same.numel()} pixels")
+    assert mismatch <= 1e-3
+    assert (out["depth"].cpu()[same] == ref["depth"][same]).all()
+    torch.testing.assert_close(out["photometric_confidence"].cpu()[same], ref["photometric_confidence"][same], rtol=1e-3, atol=1e-3)
