@@ -537,6 +537,7 @@ int launch_cost_stem_tc(const float* ref, const float* src, size_t view_stride, 
                         const unsigned* rec_base, void* stream) {
     AARMVS_CHECK_ARG(t0 && stats && stem_w_f16 && stem_b_host && depth_values && H > 0 && W > 0);
     AARMVS_CHECK_ARG(costv_mode >= 0 && costv_mode <= 2 && (costv_mode == 0 || costv));
+    AARMVS_CHECK_ARG((size_t)H * W * 128 < 0x7FFFFFFFull);          // gather recipes hold 32-bit byte offsets (TapRec.ref is signed)
     AARMVS_CHECK_ARG(costv_mode == 2 || (ref && src && cams));
     AARMVS_CHECK_ARG(S >= 1 && S <= AARMVS_MAX_SRC && planes >= 1 && planes <= AARMVS_MAX_PLANES);
     StemArgs a = {};

@@ -109,7 +109,8 @@ int aarmvs_cost_stem(const float* ref, const float* src, size_t view_stride, int
  * (others zero): per tile the conv is 9 taps x 2 K-steps x (A_hi, A_lo) MMAs with N = 16, taps addressed by descriptor.
  * costv [planes][S][H*W][32] fp32 = (warp - ref)^2; costv_mode 0: unused; 1: WRITTEN here (interior pixels of each tile)
  * so that aarmvs_aggregate can skip its gather; 2: READ here instead of gathering (aarmvs_warp_cost wrote it; ref, src and
- * cams are then unused) -- the gather then runs exactly once per pixel, view and plane. */
+ * cams are then unused) -- the gather then runs exactly once per pixel, view and plane.  H * W * 128 < 2^31 (the gather
+ * recipes hold 32-bit byte offsets): larger images return AARMVS_ERR_ARG. */
 int aarmvs_cost_stem_tc_max_slots(void);   /* upper bound of planes * S per launch (shared-memory GroupNorm partial sums) */
 int aarmvs_cost_stem_tc(const float* ref, const float* src, size_t view_stride, int H, int W, int S, const float* cams,
                         const void* stem_w_f16, const float* stem_b_host, const float* depth_values, int d_host,
