@@ -270,10 +270,8 @@ __global__ void __launch_bounds__(N_THREADS, 1) cost_stem_tc_kernel(const __grid
         int tl = g / SK, v = (g % SK) / a.K, k = g % a.K, n = 0;
         // gather recipes of fill (tile slot tl_, view v_, plane k_): one thread per staged pixel (not needed when (warp-ref)^2 is
         // streamed from costv)
-        auto write_recipes = [&](int tl_, int v_, int k_, TapRec* dst) {
+        auto write_recipes = [&](int ty_, int tx_, int v_, int k_, TapRec* dst) {
             if (a.costv_mode == 2) return;
-            const int tile_ = blockIdx.x + tl_ * gridDim.x;
-            const int ty_ = tile_ / tiles_x, tx_ = tile_ - ty_ * tiles_x;
             const float depth_ = depths[k_];
             for (int px = lt; px < NPX; px += GROUP_THREADS) {
                 const int r = px / HC, cc = px - r * HC;
@@ -309,17 +307,16 @@ __global__ void __launch_bounds__(N_THREADS, 1) cost_stem_tc_kernel(const __grid
                 dst[px] = rec;
             }
         };
-        if (STEM_AHEAD && g < total) write_recipes(tl, v, k, taps_g);
+        // tile coordinates of the current fill: the division is redone only when a group moves on to another tile
+        int ty = (int)(blockIdx.x + tl * gridDim.x) / tiles_x, tx = (int)(blockIdx.x + tl * gridDim.x) - ty * tiles_x;
+        if (STEM_AHEAD && g < total) write_recipes(ty, tx, v, k, taps_g);
         for (int it = g; it < total; it += G, ++n) {
-            const int tile = blockIdx.x + tl * gridDim.x;
-            const float depth = depths[k];
-            const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
             const bool pf = a.prof && blockIdx.x == 0 && g == 0 && lt == 0 && n < 64;
             unsigned long long* pp = a.prof + n * 8;
             if (pf) pp[0] = clock64();
             // ---- 1. gather recipes
             TapRec* const taps = taps_g + (STEM_AHEAD ? (n & 1) * NPX : 0);
-            if (!STEM_AHEAD) write_recipes(tl, v, k, taps);
+            if (!STEM_AHEAD) write_recipes(ty, tx, v, k, taps);
             // (the stage and the recipes of the previous fill are free: every thread of the group arrived on full[g] after its
             //  last read, and done[g] was observed after the MMAs' last read)
             asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(GROUP_THREADS) : "memory");
@@ -362,7 +359,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) cost_stem_tc_kernel(const __grid
                 // one staged pixel: blend in ATen's order (see gather_taps): fma(se, w, fma(sw, w, fma(ne, w, nw * w))), two channels
                 // per instruction; (warp - ref)^2; costv line; fp16 split; stage
                 auto finish = [&](const float4& ta, const float4& tb, const float4& tcn, const float4& td, const float4& rv,
-                                  const float4& wq, int rk, int pxr) {
+                                  const float4& wq, int rk, int pxr, const bool in_tile) {
                     const uint64_t w0 = pk2(wq.x, wq.x), w1 = pk2(wq.y, wq.y), w2 = pk2(wq.z, wq.z), w3 = pk2(wq.w, wq.w);
                     const uint64_t g01 = fma2(pk2(td.x, td.y), w3, fma2(pk2(tcn.x, tcn.y), w2, fma2(pk2(tb.x, tb.y), w1, mul2(pk2(ta.x, ta.y), w0))));
                     const uint64_t g23 = fma2(pk2(td.z, td.w), w3, fma2(pk2(tcn.z, tcn.w), w2, fma2(pk2(tb.z, tb.w), w1, mul2(pk2(ta.z, ta.w), w0))));
@@ -374,7 +371,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) cost_stem_tc_kernel(const __grid
                     float4 cv;
                     upk2(c01, cv.x, cv.y);
                     upk2(c23, cv.z, cv.w);
-                    if (keep_cv && rk >= 0 && (rk & 1) && pxr < NPX)        // this fill owns the pixel's costv line
+                    if (keep_cv && rk >= 0 && (rk & 1) && in_tile)          // this fill owns the pixel's costv line
                         *reinterpret_cast<float4*>(cvb + ((unsigned)rk & ~127u)) = cv;
                     // fp16 split as tc::split4_f16: hi = top 11 mantissa bits, lo = fp16(x - hi)
                     const float h0 = __uint_as_float(__float_as_uint(cv.x) & 0xFFFFE000u), h1 = __uint_as_float(__float_as_uint(cv.y) & 0xFFFFE000u);
@@ -386,7 +383,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) cost_stem_tc_kernel(const __grid
                     const __half2 la = __floats2half2_rn(l0, l1), lb = __floats2half2_rn(l2, l3);
                     const uint2 hi = make_uint2(*reinterpret_cast<const uint32_t*>(&ha), *reinterpret_cast<const uint32_t*>(&hb));
                     const uint2 lo = make_uint2(*reinterpret_cast<const uint32_t*>(&la), *reinterpret_cast<const uint32_t*>(&lb));
-                    if (pxr < NPX) {
+                    if (in_tile) {
                         sts64(st_thread + pxr * 16, hi);
                         sts64(st_thread + A_PLANE + pxr * 16, lo);
                     }
@@ -426,8 +423,8 @@ __global__ void __launch_bounds__(N_THREADS, 1) cost_stem_tc_kernel(const __grid
                         const float4 rv0 = ldg4b(refb + ((unsigned)max((int)br0.y, 0) & ~127u));
                         const float4 rv1 = ldg4b(refb + ((unsigned)max((int)br1.y, 0) & ~127u));
                         if (rb) { ta1 = tc0; tb1 = td0; }
-                        finish(ta0, tb0, tc0, td0, rv0, wq0, (int)br0.y, pxr);
-                        finish(ta1, tb1, tc1, td1, rv1, wq1, (int)br1.y, pxr + HC);
+                        finish(ta0, tb0, tc0, td0, rv0, wq0, (int)br0.y, pxr, true);          // units never leave the staged tile
+                        finish(ta1, tb1, tc1, td1, rv1, wq1, (int)br1.y, pxr + HC, true);
                         pc = tc1; pd = td1;
                         want = (b0 + bd) | (br1.x & 1u);
                     }
@@ -452,7 +449,8 @@ __global__ void __launch_bounds__(N_THREADS, 1) cost_stem_tc_kernel(const __grid
                     }
 #pragma unroll
                     for (int j = 0; j < NB; ++j)
-                        finish(ta[j], tb[j], tcn[j], td[j], rv[j], wq[j], rk[j], px0 + (jb + j) * (GROUP_THREADS / 8));
+                        finish(ta[j], tb[j], tcn[j], td[j], rv[j], wq[j], rk[j], px0 + (jb + j) * (GROUP_THREADS / 8),
+                               px0 + (jb + j) * (GROUP_THREADS / 8) < NPX);
                 }
 #endif
             }
@@ -463,7 +461,13 @@ __global__ void __launch_bounds__(N_THREADS, 1) cost_stem_tc_kernel(const __grid
             // the group has passed this fill's bar.sync, i.e. finished reading that slot in the previous fill.
             int tl2 = tl, v2 = v, k2 = k + G;
             while (k2 >= a.K) { k2 -= a.K; if (++v2 == a.S) { v2 = 0; ++tl2; } }
-            if (STEM_AHEAD && it + G < total) write_recipes(tl2, v2, k2, taps_g + ((n + 1) & 1) * NPX);
+            int ty2 = ty, tx2 = tx;
+            if (tl2 != tl) {
+                const int tile2 = blockIdx.x + tl2 * gridDim.x;
+                ty2 = tile2 / tiles_x;
+                tx2 = tile2 - ty2 * tiles_x;
+            }
+            if (STEM_AHEAD && it + G < total) write_recipes(ty2, tx2, v2, k2, taps_g + ((n + 1) & 1) * NPX);
             if (pf) pp[3] = clock64();
             // ---- 3. accumulator row of this thread's pixel -> t0
             tc::mbar_wait_relaxed(&done_a[g], n & 1);
@@ -506,7 +510,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) cost_stem_tc_kernel(const __grid
                 sstat[(warp - 1) * SK + slot] = acc;
             }
             if (pf) pp[6] = clock64();
-            tl = tl2; v = v2; k = k2;
+            tl = tl2; v = v2; k = k2; ty = ty2; tx = tx2;
         }
     }
     tc::tc_fence_before();
