@@ -17,6 +17,16 @@ def shard_views(num_views, world_size, rank):
     return range(start, start + base + (1 if rank < extra else 0))
 
 
+def shard_units(views_per_scan, world_size, rank):
+    """Several scans in one job (the reference's eval.py walks a test list of scans, eval.py:56-62): the work units are the
+    (scan, reference view) pairs of ALL scans in order, cut into contiguous balanced slices, so the ceiling of one scan
+    (49 views on 8 GPUs: the slowest rank has 7, a 7.0x speed-up) does not repeat per scan -- two scans give ceil(98 / 8) = 13
+    units on the slowest rank instead of 14.  Contiguous slices keep a rank inside one scan as long as possible (per-scan
+    feature cache).  Returns this rank's list of (scan index, view index)."""
+    units = [(s, v) for s, n in enumerate(views_per_scan) for v in range(n)]
+    return [units[i] for i in shard_views(len(units), world_size, rank)]
+
+
 def max_share(num_views, world_size):
     return -(-num_views // world_size)
 

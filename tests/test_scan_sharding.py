@@ -22,6 +22,19 @@ def test_shard_views_is_a_partition():
         scan.shard_views(4, 2, 2)
 
 
+def test_shard_units_over_several_scans():
+    from aarmvsnet_b200 import scan
+    counts = [49, 49, 5]
+    for world in (1, 2, 8):
+        seen = []
+        for r in range(world):
+            seen += scan.shard_units(counts, world, r)
+        assert seen == [(s, v) for s, n in enumerate(counts) for v in range(n)]          # a partition, in order
+    sizes = [len(scan.shard_units([49, 49], 8, r)) for r in range(8)]
+    assert max(sizes) == 13 and min(sizes) == 12                    # per-scan sharding would leave 14 on the slowest rank
+    assert scan.shard_units([3], 2, 1) == [(0, 2)]
+
+
 def _worker(rank, world, port, n_views, out):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)

@@ -95,3 +95,13 @@ def test_eval_scan_driver(tmp_path):
         assert len(os.listdir(out / "depth_est")) == 4
         outs.append((depth, conf))
     assert np.array_equal(outs[0][0], outs[1][0]) and np.allclose(outs[0][1], outs[1][1], atol=1e-6)
+    # several scans in one job: units = (scan, view) pairs, outputs under OUT/<scan folder>/; the feature cache is per scan
+    scan1 = _write_scan(tmp_path / "scan1", n_views=3, h=72, w=88)
+    out = tmp_path / "out_multi"
+    cmd = [sys.executable, os.path.join(ROOT, "eval_scan.py"), "--scan", str(scan), str(scan1), "--out", str(out), "--numdepth", "16",
+           "--view_num", "3", "--max_h", "64", "--max_w", "80", "--cache_features"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert len(os.listdir(out / "scan0" / "depth_est")) == 4 and len(os.listdir(out / "scan1" / "depth_est")) == 3
+    depth, _ = scanio.read_pfm(out / "scan0" / "depth_est" / "00000001.pfm")
+    assert np.array_equal(depth, outs[0][0])
