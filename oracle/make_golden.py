@@ -133,8 +133,30 @@ def train_fixture(ckpt, h, w, n, d, seed):
             "depth_gt": depth_gt, "mask": mask, "loss": loss, "wta_depth": wta}
 
 
+def grads_fixture(train_path):
+    """Backward of the training step (train.py:288-300: loss = mvsnet_cls_loss(model(...)); loss.backward()) of the UNMODIFIED
+    reference on the sample of the train fixture: d loss / d parameter for all 90 parameters.  Pins the autograd of the oracle
+    (tests/test_oracle_golden.py::test_training_gradients), the reference the round-2 backward kernels are checked against."""
+    from models.drmvsnet import mvsnet_cls_loss
+    t = torch.load(train_path, map_location="cpu", weights_only=False)
+    m = load_reference(t["ckpt"], t["h"], t["w"], return_depth=False)
+    for p in m.parameters():
+        p.requires_grad_(True)
+    prob, _, _ = m(t["imgs"], t["proj_matrices"], t["depth_values"])
+    loss, _ = mvsnet_cls_loss(prob, t["depth_gt"], t["mask"], t["depth_values"])
+    loss.backward()
+    grads = {k: p.grad.detach().clone() for k, p in m.named_parameters() if p.grad is not None}
+    assert abs(loss.item() - float(t["loss"])) <= 1e-5 * abs(float(t["loss"]))
+    return {"train_fixture": os.path.basename(train_path), "loss": loss.detach(), "grads": grads}
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == "grads":          # only the gradient fixture (the others stay untouched)
+        g = grads_fixture(os.path.join(GOLD, "train_32x40_n3_d6.pt"))
+        torch.save(g, os.path.join(GOLD, "train_grads_32x40_n3_d6.pt"))
+        print("train_grads_32x40_n3_d6.pt", len(g["grads"]), "parameter gradients, loss", float(g["loss"]))
+        return
     for ck in ("model_dtu_v2.ckpt", "model_blended_v2.ckpt"):
         dst = os.path.join(GOLD, ck)
         if not os.path.exists(dst):
@@ -146,6 +168,7 @@ def main():
     torch.save(e2e_fixture("model_blended_v2.ckpt", 40, 56, 4, 12, seed=3, depth_mode="inverse", batch=2),
                os.path.join(GOLD, "e2e_blended_40x56_n4_d12_b2.pt"))
     torch.save(train_fixture("model_dtu_v2.ckpt", 32, 40, 3, 6, seed=4), os.path.join(GOLD, "train_32x40_n3_d6.pt"))
+    torch.save(grads_fixture(os.path.join(GOLD, "train_32x40_n3_d6.pt")), os.path.join(GOLD, "train_grads_32x40_n3_d6.pt"))
     for f in sorted(os.listdir(GOLD)):
         print(f, os.path.getsize(os.path.join(GOLD, f)))
 

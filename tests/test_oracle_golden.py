@@ -75,3 +75,28 @@ def test_forward_train_phase_and_loss():
     loss, wta = orc.cls_loss(g["prob_volume"], g["depth_gt"], g["mask"], g["depth_values"])
     torch.testing.assert_close(loss, g["loss"], rtol=1e-6, atol=1e-7)
     torch.testing.assert_close(wta, g["wta_depth"], rtol=0, atol=0)
+
+
+def test_training_gradients():
+    """Backward of the training step (train.py:288-300): autograd through the oracle's train-phase forward and loss must
+    reproduce d loss / d parameter of the UNMODIFIED reference for all 90 parameters (tests/golden/train_grads_*.pt,
+    oracle/make_golden.py grads).  This pins the reference the backward kernels of config 5 are to be checked against."""
+    g = load_golden("train_32x40_n3_d6.pt")
+    gg = load_golden("train_grads_32x40_n3_d6.pt")
+    sd = {k: v.clone().requires_grad_(True) for k, v in load_weights(g["ckpt"]).items()}
+    prob = orc.forward_train(sd, g["imgs"], g["proj_matrices"], g["depth_values"])
+    loss, _ = orc.cls_loss(prob, g["depth_gt"], g["mask"], g["depth_values"])
+    torch.testing.assert_close(loss.detach(), gg["loss"], rtol=1e-5, atol=1e-6)
+    loss.backward()
+    assert set(gg["grads"]) == set(sd) and len(sd) == 90
+    worst = 0.0
+    top = max(v.abs().max().item() for v in gg["grads"].values())
+    for k, want in gg["grads"].items():
+        got = sd[k].grad
+        assert got is not None, k
+        # conv_0.bias shifts every plane's cost alike, so its true gradient through the softmax is 0 (1.5e-8 of rounding noise
+        # in the reference): tensors are compared on the scale of their own largest gradient, with a floor from the global one
+        scale = max(want.abs().max().item(), 1e-4 * top)
+        worst = max(worst, (got - want).abs().max().item() / scale)
+        torch.testing.assert_close(got, want, rtol=1e-3, atol=2e-4 * scale, msg=lambda m, k=k: f"{k}: {m}")
+    print(f"worst max-abs gradient error relative to the tensor's largest gradient: {worst:.2e}")
