@@ -74,6 +74,7 @@ PROTOTYPES = {
     "aarmvs_fuse_view": (_I, [_P, _P, _P, _I, _I, _I, _P, _F, _P, _P, _P, _P, _P]),
     "aarmvs_head_wta_tc": (_I, [_P, _I, _I, _P, c_float_p, _P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "aarmvs_next_plane": (_I, [_P, _P, _I, _P]),
+    "aarmvs_loss_grad": (_I, [_P, _P, _P, _F, _I, _SZ, _P, _P]),
     "aarmvs_debug_profile_buffer": (None, [_P]),
     "aarmvs_debug_flags": (None, [_I]),
     "aarmvs_debug_cell_flags": (None, [_I]),

@@ -184,3 +184,21 @@ def deform_conv(model, level, x, math=None):
         capi.check(lib.aarmvs_deform_conv(ctypes.byref(src), H, W, _ptr(om), _ptr(w[f"dc{level}.w"]), _ptr(w[f"dc{level}.b"]),
                                           _ptr(out), None, st), "aarmvs_deform_conv")
     return _nchw(out, H, W)
+
+
+def loss_grad(model, cost_volume, depth_gt, mask, depth_values, batch=1):
+    """d mvsnet_cls_loss / d regularised cost (models/drmvsnet.py:289-291, 347-381) for one sample: the first step of the
+    backward pass.  cost_volume [D,H,W] (the train-phase forward's regularised costs, before the softmax), depth_gt / mask
+    [H,W], depth_values [D]; batch = B of the loss's mean over samples.  Returns [D,H,W]."""
+    _need_cuda(cost_volume)
+    eng = model._engine
+    D, H, W = cost_volume.shape
+    P = H * W
+    cost = cost_volume.to(torch.float32).contiguous().view(D, P)
+    mk = mask.to(device=cost.device, dtype=torch.float32).reshape(-1).contiguous()
+    gt = eng.nearest_hypothesis(depth_values.to(cost.device), depth_gt.to(cost.device), mk.view(H, W)).contiguous()
+    scale = 1.0 / ((float(mk.sum().item()) + 1e-6) * batch)
+    out = torch.empty_like(cost)
+    capi.check(eng.lib.aarmvs_loss_grad(_ptr(cost), _ptr(gt), _ptr(mk), scale, D, P, _ptr(out), _stream(cost.device)), "aarmvs_loss_grad")
+    return out.view(D, H, W)
+

@@ -257,6 +257,14 @@ int aarmvs_fuse_view(const float* depth_ref, const float* conf_ref, const float*
 
 /* ---- tensor-core building blocks ------------------------------------------------------------------------- */
 
+/* Training tail, first step of the backward pass (models/drmvsnet.py:289-291 softmax over the D regularised costs, :347-381
+ * mvsnet_cls_loss): d loss / d cost for every plane from the stored regularised costs,
+ *   dcost[d][p] = scale * mask[p] * (softmax_d(cost[:, p]) - [d == gt_index[p]]),  scale = 1 / ((sum_p mask[p] + 1e-6) * B).
+ * cost, dcost: [D][P] fp32 (plane major, one sample); gt_index: [P] int32 = round(mask * argmin_d |depth_values[d] - depth_gt|);
+ * mask: [P] fp32. */
+int aarmvs_loss_grad(const float* cost, const int* gt_index, const float* mask, float scale, int D, size_t P, float* dcost,
+                     void* stream);
+
 /* Known-answer test of the tcgen05 path shared by the ConvLSTM kernels (un-swizzled K-major shared-memory operands,
  * 8-row groups `group_rows` rows apart, start row `shift`, TMEM accumulation, commit -> mbarrier, tcgen05.ld):
  *   d[m][n] = sum_k a[shift + (m / 8) * group_rows + m % 8][k] * b[n][k],  m < 128, n < 64, fp16 inputs, fp32 out.

@@ -117,3 +117,25 @@ def test_edge_shapes_against_oracle(sd_dtu, shape):
         out = m(s["imgs"].cuda(), s["proj_matrices"].cuda(), s["depth_values"].cuda())
         assert (out["index"].cpu().long() == ref["index"]).float().mean() >= 0.995
         torch.testing.assert_close(out["photometric_confidence"].cpu(), ref["photometric_confidence"], rtol=0, atol=1e-3)
+
+
+def test_loss_gradient_wrt_cost_matches_autograd():
+    """aarmvs_loss_grad (first step of the backward pass): d mvsnet_cls_loss / d regularised cost against autograd through the
+    oracle's loss (pinned to the reference's, tests/test_oracle_golden.py) on the reference's own probability volume
+    (log prob is a cost volume with exactly that softmax)."""
+    import aarmvsnet_b200 as aa
+    from aarmvsnet_b200 import ops
+    from conftest import load_golden, load_weights
+    from oracle import aarmvs_oracle as orc
+    g = load_golden("train_32x40_n3_d6.pt")
+    cost = torch.log(g["prob_volume"][0]).clone().requires_grad_(True)                      # [D,H,W]
+    loss, _ = orc.cls_loss(torch.softmax(cost, 0).unsqueeze(0), g["depth_gt"], g["mask"], g["depth_values"])
+    torch.testing.assert_close(loss.detach(), g["loss"], rtol=1e-5, atol=1e-6)
+    loss.backward()
+    m = aa.EMVSNet(disparity_level=32, image_scale=1.0, max_h=32, max_w=40, return_depth=False)
+    m.load_state_dict(load_weights(g["ckpt"]), strict=True)
+    m = m.cuda().eval()
+    got = ops.loss_grad(m, cost.detach().cuda(), g["depth_gt"][0].cuda(), g["mask"][0].cuda(), g["depth_values"][0].cuda()).cpu()
+    scale = cost.grad.abs().max().item()
+    torch.testing.assert_close(got, cost.grad, rtol=1e-4, atol=1e-5 * scale)
+    assert (got[:, g["mask"][0] == 0] == 0).all()                                           # masked pixels carry no gradient
