@@ -3,7 +3,7 @@
 TEST INFRASTRUCTURE ONLY.  This file is a plain PyTorch fp32 (CPU) restatement of the reference's
 algorithm for the hot path, written as stateless functions over a checkpoint ``state_dict``.  It is
 the checker for the CUDA path: only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU
-baseline legs may import it.  The product (``aa-rmvsnet_b200/``) never does.
+baseline legs may import it.  The product (``aarmvsnet_b200/``) never does.
 
 Parity pin: the reference has no tests or golden vectors of its own, so this
 restatement is pinned against outputs of the reference itself run in the build container
