@@ -1,5 +1,6 @@
 """Builds lib/libaarmvs_sm100.so from csrc/*.cu with nvcc for sm_100a (in-tree; the .so travels with the repo)."""
 import concurrent.futures
+import fcntl
 import glob
 import hashlib
 import os
@@ -41,9 +42,22 @@ def build_library(force=False, verbose=False):
     deps = srcs + glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(INCLUDE, "*.h"))
     stamp = os.path.join(LIBDIR, "build.sha256")
     digest = _digest(deps)
-    if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read().strip() == digest:
+    def fresh():
+        return os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read().strip() == digest
+
+    if not force and fresh():
         return LIB
     os.makedirs(LIBDIR, exist_ok=True)
+    # several ranks of one job may get here at once (torch.distributed.run): one builds, the others wait on the lock and
+    # then find the library fresh; the .so is linked under a temporary name and renamed into place, never seen half-written
+    with open(os.path.join(LIBDIR, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        if not force and fresh():
+            return LIB
+        return _build_locked(srcs, stamp, digest, verbose)
+
+
+def _build_locked(srcs, stamp, digest, verbose):
     nvcc = _nvcc()
     flags = [f for f in NVCC_FLAGS if f != "--use_fast_math=false"] + os.environ.get("AARMVS_NVCC_EXTRA", "").split()
     objs = [os.path.join(LIBDIR, os.path.basename(s)[:-3] + ".o") for s in srcs]
@@ -62,10 +76,12 @@ def build_library(force=False, verbose=False):
                 raise RuntimeError(f"nvcc failed on {src}:\n{r.stdout}\n{r.stderr}")
     with open(os.path.join(LIBDIR, "ptxas.log"), "w") as f:
         f.write("\n".join(logs))
-    r = subprocess.run([nvcc, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a"],
+    tmp = f"{LIB}.tmp.{os.getpid()}"
+    r = subprocess.run([nvcc, "-shared", "-o", tmp, *objs, "-gencode", "arch=compute_100a,code=sm_100a"],
                        capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    os.replace(tmp, LIB)
     with open(stamp, "w") as f:
         f.write(digest)
     if verbose:

@@ -8,6 +8,7 @@ import os
 from . import build as _build
 
 ERR_ARG = 1000001
+ABI_VERSION = 4
 SRC_PLAIN, SRC_GN_RELU, SRC_MAXPOOL2, SRC_NCHW = 0, 1, 2, 3
 
 c_float_p = ctypes.POINTER(ctypes.c_float)
@@ -58,8 +59,6 @@ PROTOTYPES = {
     "aarmvs_cost_stem": (_I, [_P, _P, _SZ, _I, _I, _I, _P, c_float_p, c_float_p, _P, _I, _P, _I, _I, _P, _P, _P]),
     "aarmvs_cost_stem_tc": (_I, [_P, _P, _SZ, _I, _I, _I, _P, _P, c_float_p, _P, _I, _P, _I, _I, _P, _P, _P, _I, _P]),
     "aarmvs_cost_stem_tc_max_slots": (_I, []),
-    "aarmvs_sweep_recipes": (_I, [_I, _I, _I, _P, _P, _I, _P, _I, _I, _P, _P, _P]),
-    "aarmvs_cost_stem_tc_recipes": (_I, [_P, _P, _SZ, _I, _I, _I, _P, _P, c_float_p, _P, _I, _P, _I, _I, _P, _P, _P, _I, _P, _P, _P]),
     "aarmvs_warp_cost": (_I, [_P, _P, _SZ, _I, _I, _I, _P, _P, _I, _P, _I, _I, _P, _P]),
     "aarmvs_omega_stats": (_I, [_I, _P, _I, _I, _I, _I, c_float_p, _P, _P]),
     "aarmvs_aggregate": (_I, [_P, _P, _SZ, _I, _I, _I, _P, c_float_p, _P, _I, _P, _I, _I, _P, _P, _P, _P, _P, _P, _P]),
@@ -75,12 +74,16 @@ PROTOTYPES = {
     "aarmvs_head_wta_tc": (_I, [_P, _I, _I, _P, c_float_p, _P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "aarmvs_next_plane": (_I, [_P, _P, _I, _P]),
     "aarmvs_loss_grad": (_I, [_P, _P, _P, _F, _I, _SZ, _P, _P]),
+    "aarmvs_tc_mma_bench": (_I, [_I, _I, _I, _I, _I, _P, _P]),
+    "aarmvs_tc_selftest": (_I, [_P, _I, _P, _P, _I, _I, _I, _P]),
+}
+
+# exported only by -DAARMVS_DEBUG builds (scripts/cell_timeline.py, scripts/stem_ablation.py); bound when present
+DEBUG_PROTOTYPES = {
     "aarmvs_debug_profile_buffer": (None, [_P]),
     "aarmvs_debug_flags": (None, [_I]),
     "aarmvs_debug_cell_flags": (None, [_I]),
     "aarmvs_debug_stem_profile_buffer": (None, [_P]),
-    "aarmvs_tc_mma_bench": (_I, [_I, _I, _I, _I, _I, _P, _P]),
-    "aarmvs_tc_selftest": (_I, [_P, _I, _P, _P, _I, _I, _I, _P]),
 }
 
 _lib = None
@@ -91,22 +94,28 @@ def library_path():
     return os.environ.get("AARMVS_LIB") or _build.LIB
 
 
-def load(build_if_missing=True):
-    """Load (building first if the .so is absent and nvcc is present) and type every entry point."""
+def load():
+    """Make sure the in-tree library matches csrc/ (digest stamp; rebuilds with nvcc when it does not, raises when that is
+    impossible -- a stale library never runs silently), load it and type every entry point."""
     global _lib
     if _lib is not None:
         return _lib
     path = library_path()
-    if not os.path.exists(path):
-        if not build_if_missing:
-            raise RuntimeError(f"{path} is missing: run `python __graft_entry__.py build` (nvcc, sm_100a)")
+    if path == _build.LIB:
         _build.build_library()
+    elif not os.path.exists(path):
+        raise RuntimeError(f"AARMVS_LIB={path} does not exist")
     lib = ctypes.CDLL(path)
     for name, (res, args) in PROTOTYPES.items():
         fn = getattr(lib, name)          # AttributeError here = ABI drift between the header and the library
         fn.restype = res
         fn.argtypes = args
-    if lib.aarmvs_version() != 3:
+    for name, (res, args) in DEBUG_PROTOTYPES.items():
+        if hasattr(lib, name):
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+    if lib.aarmvs_version() != ABI_VERSION:
         raise RuntimeError("libaarmvs_sm100.so: ABI version mismatch")
     _lib = lib
     return lib

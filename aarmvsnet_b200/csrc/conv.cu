@@ -266,30 +266,24 @@ __global__ void __launch_bounds__(256, 1) conv_kernel(const __grid_constant__ Co
     }
 }
 
-static int g_sm_count = 0;
+// multiprocessor count of the CURRENT device (a cached device attribute of the runtime: no global state here, and a process
+// that drives several GPUs gets each one's own count)
 static int sm_count() {
-    if (g_sm_count == 0) {
-        int dev = 0, n = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
-            return -1;
-        g_sm_count = n;
-    }
-    return g_sm_count;
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+        return -1;
+    return n;
 }
 
-extern "C" int aarmvs_version(void) { return 3; }
+extern "C" int aarmvs_version(void) { return 4; }
 extern "C" int aarmvs_sm_count(void) { return sm_count(); }
 
 template <int CIN, int COUT, int KS, int STRIDE, int TCO, int TPX, int EPI>
 static int launch_conv(const ConvArgs& a, cudaStream_t stream) {
     using C = ConvCfg<CIN, COUT, KS, STRIDE, TCO, TPX, EPI>;
     auto kern = conv_kernel<CIN, COUT, KS, STRIDE, TCO, TPX, EPI>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
-        if (e != cudaSuccess) return (int)e;
-        attr_set = true;
-    }
+    static unsigned long long smem_ok = 0;          // per (kernel, device): the attribute is a per-device property
+    if (cudaError_t e = ensure_dyn_smem(kern, (int)C::SMEM, smem_ok)) return (int)e;
     const int tiles = ((a.Wout + C::TW - 1) / C::TW) * ((a.Hout + C::TH - 1) / C::TH);
     const int sms = sm_count();
     if (sms <= 0) return AARMVS_ERR_ARG;

@@ -56,9 +56,21 @@ struct alignas(64) CellArgs {
     __half* pooled;             // optional [2][CH/8][H/2][W/2][8]: operand planes of max_pool2d(h, 2)
     int d_host;
     const int* d_dev;
+#ifdef AARMVS_DEBUG
     unsigned long long* prof;   // debug: per-tile clock64 stamps of CTA 0 ([tile][12]), or null
     int dbg;                    // debug ablation: 1 no TMA loads, 4 epilogue skips global I/O, 8 skip MMAs, 16 no transcendentals, 32 no pooling
+#endif
 };
+
+// Debug hooks (scripts/cell_timeline.py) exist only in -DAARMVS_DEBUG builds: the product library carries neither the
+// process-global switches nor their branches in the hot loops.
+#ifdef AARMVS_DEBUG
+#define CELL_DBG(a, flag) (((a).dbg & (flag)) != 0)
+#define CELL_PROF(a) ((a).prof)
+#else
+#define CELL_DBG(a, flag) (0)
+#define CELL_PROF(a) ((unsigned long long*)nullptr)
+#endif
 
 template <int KSTEPS, int NG, int NST>
 struct Cfg {
@@ -170,25 +182,25 @@ __global__ void __launch_bounds__(N_THREADS, 1) convlstm_tma_kernel(const __grid
         int it = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
             const int st = it % NST;
-            const bool pf = a.prof && blockIdx.x == 0 && lane == 0 && it < 64;
+            const bool pf = CELL_PROF(a) && blockIdx.x == 0 && lane == 0 && it < 64;
             if (lane == 0) {
-                if (pf) a.prof[it * 12 + 0] = clock64();
+                if (pf) CELL_PROF(a)[it * 12 + 0] = clock64();
                 tc::mbar_wait(&empty_a[st], ((it / NST) & 1) ^ 1);
-                if (pf) a.prof[it * 12 + 1] = clock64();
-                if (a.dbg & 1) tc::mbar_arrive(&full_a[st]);
+                if (pf) CELL_PROF(a)[it * 12 + 1] = clock64();
+                if CELL_DBG(a, 1) tc::mbar_arrive(&full_a[st]);
                 else tc::mbar_arrive_expect_tx(&full_a[st], bytes);
             }
             __syncwarp();
             // one lane per (source, hi / lo plane): the up to six tensor copies of a tile are issued by ONE warp instruction
             // (a single thread issuing them back to back spent ~400 cycles per copy: 2 400 cycles per tile for cell 4,
             // as long as its MMAs)
-            if (lane < 2 * nload && !(a.dbg & 1)) {
+            if (lane < 2 * nload && !CELL_DBG(a, 1)) {
                 const int s = lane >> 1, hl = lane & 1;
                 const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
                 unsigned char* dst = sA + st * C::A_STAGE + hl * C::A_PLANE + cbase[s] * CHUNK_BYTES;
                 tc::tma_load_5d(dst, &a.map[s], &full_a[st], (tx * TCOL - 1) * 8, ty * TR - 1, 0, hl, sel[s]);
             }
-            if (pf) a.prof[it * 12 + 2] = a.prof[it * 12 + 3] = clock64();
+            if (pf) CELL_PROF(a)[it * 12 + 2] = CELL_PROF(a)[it * 12 + 3] = clock64();
             __syncwarp();
         }
     } else if (warp == MMA_WARP) {
@@ -212,15 +224,15 @@ __global__ void __launch_bounds__(N_THREADS, 1) convlstm_tma_kernel(const __grid
         }
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
             const int st = it % NST, ab = it & 1;
-            const bool pf = a.prof && blockIdx.x == 0 && leader && it < 64;
-            if (pf) a.prof[it * 12 + 4] = a.prof[it * 12 + 5] = a.prof[it * 12 + 6] = clock64();
+            const bool pf = CELL_PROF(a) && blockIdx.x == 0 && leader && it < 64;
+            if (pf) CELL_PROF(a)[it * 12 + 4] = CELL_PROF(a)[it * 12 + 5] = CELL_PROF(a)[it * 12 + 6] = clock64();
             const uint32_t dst = tmem_base + ab * 2 * NG;
             const uint32_t a_lo_hi = tc::desc_lo(a_base + st * C::A_STAGE, NPX * 16);
             const uint32_t a_lo_lo = tc::desc_lo(a_base + st * C::A_STAGE + C::A_PLANE, NPX * 16);
             const bool more = tile + (int)gridDim.x < ntiles;
 #pragma unroll
             for (int tap = 0; tap < 9; ++tap) {
-                if (leader && !(a.dbg & 8)) {
+                if (leader && !CELL_DBG(a, 8)) {
                     constexpr int KS_TAP = C::PACK ? 2 : KSTEPS;            // full two-chunk K steps of one tap
 #pragma unroll
                     for (int ks = 0; ks < KS_TAP; ++ks) {
@@ -253,7 +265,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) convlstm_tma_kernel(const __grid
                 tc::mma_commit(&empty_a[st]);          // operand stage free once these MMAs have read it
                 tc::mma_commit(&tmem_full[ab]);        // accumulator complete
             }
-            if (pf) a.prof[it * 12 + 7] = clock64();
+            if (pf) CELL_PROF(a)[it * 12 + 7] = clock64();
             __syncwarp();
         }
     } else {
@@ -272,7 +284,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) convlstm_tma_kernel(const __grid
         // previous cell state of this thread's pixel of tile `t` (zero at plane 0 and outside the image)
         auto load_c = [&](int t, float (&cv)[NHC]) {
             const int ty = t / tiles_x, tx = t - ty * tiles_x;
-            const bool ok = t < ntiles && ty * TR + (m >> 3) < a.H && tx * TCOL + (m & 7) < a.W && d != 0 && !(a.dbg & 4);
+            const bool ok = t < ntiles && ty * TR + (m >> 3) < a.H && tx * TCOL + (m & 7) < a.W && d != 0 && !CELL_DBG(a, 4);
             const float* p = a.c_blocked + (((size_t)t * 4 + part) * 128 + m) * NHC;
             if constexpr (NHC == 4) {
                 const float4 v = ok ? ld4(p) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -287,10 +299,10 @@ __global__ void __launch_bounds__(N_THREADS, 1) convlstm_tma_kernel(const __grid
         int it = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
             const int ab = it & 1;
-            const bool pf = a.prof && blockIdx.x == 0 && tid == 0 && it < 64;
+            const bool pf = CELL_PROF(a) && blockIdx.x == 0 && tid == 0 && it < 64;
             const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
             const int y = ty * TR + (m >> 3), x = tx * TCOL + (m & 7);
-            const bool valid = y < a.H && x < a.W && !(a.dbg & 4);
+            const bool valid = y < a.H && x < a.W && !CELL_DBG(a, 4);
             const size_t pix = valid ? (size_t)y * a.W + x : 0;
             float* cp = a.c_blocked + (((size_t)tile * 4 + part) * 128 + m) * NHC;
             float cprev[NHC], cn[NHC], hn[NHC];
@@ -299,17 +311,17 @@ __global__ void __launch_bounds__(N_THREADS, 1) convlstm_tma_kernel(const __grid
             // the NEXT tile's state is requested now: its global-load latency hides behind this tile's gate math (with the
             // small-K cells the accumulator of the next tile is ready before this one's epilogue ends)
             load_c(tile + gridDim.x, cnext);
-            if (pf) a.prof[it * 12 + 8] = clock64();
+            if (pf) CELL_PROF(a)[it * 12 + 8] = clock64();
             tc::mbar_wait_relaxed(&tmem_full[ab], (it >> 1) & 1);
             tc::tc_fence_after();
-            if (pf) a.prof[it * 12 + 9] = clock64();
+            if (pf) CELL_PROF(a)[it * 12 + 9] = clock64();
             float g[NCOL], g2[NCOL];
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + ab * 2 * NG + part * NCOL;
             if constexpr (NCOL == 16) { tmem_ld16(taddr, g); tmem_ld16(taddr + NG, g2); }
             else { tmem_ld8(taddr, g); tmem_ld8(taddr + NG, g2); }
             tc::tc_fence_before();
             tc::mbar_arrive(&tmem_empty[ab]);                    // accumulator is in registers: release it
-            if (pf) a.prof[it * 12 + 10] = clock64();
+            if (pf) CELL_PROF(a)[it * 12 + 10] = clock64();
             // pixels outside the image (ragged tiles) see zero operands: finite values that are never stored.
             // Gates with ONE reciprocal per hidden channel: with a = 1 + e^-i, b = 1 + e^-f, c = 1 + e^-o, d = 1 + e^-2g and
             // r = 1 / (abcd):  sigmoid(i) = r*cd*b, sigmoid(f) = r*cd*a, sigmoid(o) = r*ab*d, tanh(g) = 2*r*ab*c - 1
@@ -318,7 +330,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) convlstm_tma_kernel(const __grid
 #pragma unroll
             for (int j = 0; j < NHC; ++j) {
                 const float* bb = bias_r + j * 4;
-                if (a.dbg & 16) {          // debug ablation: no transcendental math
+                if CELL_DBG(a, 16) {          // debug ablation: no transcendental math
                     cn[j] = (g[j * 4 + 0] + g2[j * 4 + 0]) + bb[0] + cprev[j];
                     go[j] = (g[j * 4 + 1] + g2[j * 4 + 1]) + (g[j * 4 + 2] + g2[j * 4 + 2]) + (g[j * 4 + 3] + g2[j * 4 + 3]);
                     ec[j] = 1.0f;
@@ -362,7 +374,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) convlstm_tma_kernel(const __grid
                 }
             }
             if constexpr (NHC == 4) {
-                if (a.pooled && !(a.dbg & 32)) {    // max_pool2d(h, 2) (drmvsnet.py:148,152): the 2x2 block is lanes ^1, ^8 of this warp
+                if (a.pooled && !CELL_DBG(a, 32)) {    // max_pool2d(h, 2) (drmvsnet.py:148,152): the 2x2 block is lanes ^1, ^8 of this warp
                     float pm[NHC];
 #pragma unroll
                     for (int j = 0; j < NHC; ++j) {
@@ -378,7 +390,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) convlstm_tma_kernel(const __grid
                     }
                 }
             }
-            if (pf) a.prof[it * 12 + 11] = clock64();
+            if (pf) CELL_PROF(a)[it * 12 + 11] = clock64();
         }
     }
     tc::tc_fence_before();
@@ -399,14 +411,18 @@ int launch_cell(const CellArgs& a, cudaStream_t stream) {
     AARMVS_LAUNCH_RESULT();
 }
 
+#ifdef AARMVS_DEBUG
 unsigned long long* g_prof = nullptr;
 int g_cell_dbg = 0;
+#endif
 
 }  // namespace
 
+#ifdef AARMVS_DEBUG
 // Debug only: CTA 0 of the next ConvLSTM launches writes clock64 stamps per tile ([64][12] uint64) into `buf` (device).
 extern "C" void aarmvs_debug_profile_buffer(void* buf) { g_prof = (unsigned long long*)buf; }
 extern "C" void aarmvs_debug_cell_flags(int flags) { g_cell_dbg = flags; }
+#endif
 
 extern "C" size_t aarmvs_cell_state_floats(int H, int W, int hidden) {
     if (H <= 0 || W <= 0 || hidden <= 0) return 0;
@@ -442,7 +458,10 @@ extern "C" int aarmvs_convlstm_cell_tc(const aarmvs_plane_src* src, int nsrc, in
     a.need_zero = 0;          // K padding is never read: cell 4 packs its fifth chunk (see Cfg::PACK)
     a.H = H; a.W = W; a.weight = (const __half*)weight_f16; a.bias = bias_packed; a.h_planes = (__half*)h_planes;
     a.c_blocked = c_blocked; a.h_f32 = h_f32_pair; a.pooled = (__half*)pooled_planes;
-    a.d_host = d_host; a.d_dev = d_dev; a.prof = g_prof; a.dbg = g_cell_dbg;
+    a.d_host = d_host; a.d_dev = d_dev;
+#ifdef AARMVS_DEBUG
+    a.prof = g_prof; a.dbg = g_cell_dbg;
+#endif
     cudaStream_t st = (cudaStream_t)stream;
     if (cin == 48 && hidden == 16) return launch_cell<3, 64, 3>(a, st);     // cells 0, 3
     if (cin == 32 && hidden == 16) return launch_cell<2, 64, 4>(a, st);     // cells 1, 2

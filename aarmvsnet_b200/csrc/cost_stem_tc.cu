@@ -88,13 +88,23 @@ struct StemArgs {
     int align_corners;
     float* t0;
     double* stats;
-    const float* rec_w;         // optional precomputed gather recipes (aarmvs_sweep_recipes): weights [K][S][P][4] and
-    const unsigned* rec_base;   //   north-west line | step flags [K][S][P]; null: evaluated here
-    float* costv;               // optional [K][S][P][32] (warp-ref)^2: written for the tile's interior pixels (mode 1) so pass D
-    int costv_mode;             //   need not gather again, or READ instead of gathering (mode 2: aarmvs_warp_cost wrote it)
+    float* costv;               // optional [K][S][P][32] (warp-ref)^2: written for the tile's interior pixels (mode 1) so that pass D
+    int costv_mode;             //   need not gather again
+#ifdef AARMVS_DEBUG
     unsigned long long* prof;   // debug: clock64 stamps of group 0 of CTA 0, [64 fills][8]
-    int dbg;                    // debug ablation flags (aarmvs_debug_flags): 1 skip gather loads, 2 skip recipes, 4 skip MMA
+    int dbg;                    // debug ablation flags (aarmvs_debug_flags): 2 skip recipes, 4 skip MMA
+#endif
 };
+
+// Debug hooks (timing experiments of scripts/stem_ablation.py) exist only in -DAARMVS_DEBUG builds: the product library has
+// neither the process-global switches nor their branches in the hot loops.
+#ifdef AARMVS_DEBUG
+#define STEM_DBG(a, flag) ((a).dbg & (flag))
+#define STEM_PROF(a) ((a).prof)
+#else
+#define STEM_DBG(a, flag) (0)
+#define STEM_PROF(a) ((unsigned long long*)nullptr)
+#endif
 
 // Gather recipe of one staged pixel (32 bytes; the L1 data pipe bounds this kernel, so the record is kept to two loads):
 // the four bilinear weights (0 for corners outside the image, which reproduces the skipped tap exactly), the BYTE offset
@@ -150,38 +160,6 @@ __device__ __forceinline__ void make_recipe(const float* cam, int x, int y, floa
     base = (unsigned)(yn * W + xw) * 128u | (unsigned)(xe - xw) | ((unsigned)(ys - yn) << 1);
 }
 
-// Pass R: the recipes of every (plane, view, pixel) of a plane batch, once and without the halo pixels pass A would
-// re-evaluate per tile (41 % more) -- pass A then only copies them (the recipe arithmetic, four IEEE divisions per sample for
-// bit-exact positions, was 28 % of its issue slots).
-struct RecipeArgs {
-    int H, W, S, K;
-    const float* cams;
-    const float* depth_values;
-    int d_host;
-    const int* d_dev;
-    int align_corners;
-    float* rec_w;
-    unsigned* rec_base;
-};
-
-__global__ void __launch_bounds__(256) sweep_recipes_kernel(const __grid_constant__ RecipeArgs a) {
-    __shared__ float cam[12];
-    const int slot = blockIdx.y, k = slot / a.S, v = slot - k * a.S;
-    if (threadIdx.x < 12) cam[threadIdx.x] = a.cams[v * 12 + threadIdx.x];
-    __syncthreads();
-    const float depth = a.depth_values[plane_index(a.d_host, a.d_dev) + k];
-    const int P = a.H * a.W;
-    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < P; p += gridDim.x * blockDim.x) {
-        const int y = p / a.W, x = p - y * a.W;
-        float4 wts;
-        unsigned base;
-        make_recipe(cam, x, y, depth, a.W, a.H, a.align_corners != 0, wts, base);
-        const size_t idx = (size_t)slot * P + p;
-        st4(a.rec_w + idx * 4, wts);
-        a.rec_base[idx] = base;
-    }
-}
-
 __global__ void __launch_bounds__(N_THREADS, 1) cost_stem_tc_kernel(const __grid_constant__ StemArgs a) {
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* sB = smem;
@@ -198,8 +176,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) cost_stem_tc_kernel(const __grid
 
     for (int i = tid; i < B_BYTES / 16; i += N_THREADS)
         reinterpret_cast<uint4*>(sB)[i] = __ldg(reinterpret_cast<const uint4*>(a.weight) + i);
-    if (a.costv_mode != 2)          // stream mode never evaluates a homography
-        for (int i = tid; i < a.S * 12; i += N_THREADS) scam[i] = a.cams[i];
+    for (int i = tid; i < a.S * 12; i += N_THREADS) scam[i] = a.cams[i];
     for (int i = tid; i < G * 4 * NBLK * SK; i += N_THREADS) sstat[i] = make_float2(0.f, 0.f);
     if (tid == 0) {
         for (int s = 0; s < G; ++s) { tc::mbar_init(&full_a[s], GROUP_THREADS); tc::mbar_init(&done_a[s], 1); }
@@ -232,7 +209,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) cost_stem_tc_kernel(const __grid
             const uint32_t a_lo_hi = tc::desc_lo(a_base + g * A_STAGE, AROWS * 16);
             const uint32_t a_lo_lo = tc::desc_lo(a_base + g * A_STAGE + A_PLANE, AROWS * 16);
             if (leader) {
-                if (!(a.dbg & 4))
+                if (!STEM_DBG(a, 4))
 #pragma unroll
                 for (int mb = 0; mb < NBLK; ++mb) {          // 8-column block of the tile: 8 staged pixels further
                     const uint32_t dst = tmem_base + (g * NBLK + mb) * ACC;
@@ -268,10 +245,8 @@ __global__ void __launch_bounds__(N_THREADS, 1) cost_stem_tc_kernel(const __grid
         const unsigned row_bytes = (unsigned)a.W * 128u;
         // fill it = g, g + G, ... decoded incrementally as (tile slot tl, view v, plane k): it = (tl * S + v) * K + k
         int tl = g / SK, v = (g % SK) / a.K, k = g % a.K, n = 0;
-        // gather recipes of fill (tile slot tl_, view v_, plane k_): one thread per staged pixel (not needed when (warp-ref)^2 is
-        // streamed from costv)
+        // gather recipes of fill (tile slot tl_, view v_, plane k_): one thread per staged pixel
         auto write_recipes = [&](int ty_, int tx_, int v_, int k_, TapRec* dst) {
-            if (a.costv_mode == 2) return;
             const float depth_ = depths[k_];
             for (int px = lt; px < NPX; px += GROUP_THREADS) {
                 const int r = px / HC, cc = px - r * HC;
@@ -279,15 +254,9 @@ __global__ void __launch_bounds__(N_THREADS, 1) cost_stem_tc_kernel(const __grid
                 TapRec rec;
                 rec.w[0] = rec.w[1] = rec.w[2] = rec.w[3] = 0.f;
                 rec.base = 0u; rec.ref = -1; rec.pad0 = rec.pad1 = 0u;
-                if (y >= 0 && y < a.H && x >= 0 && x < a.W && !(a.dbg & 2)) {
+                if (y >= 0 && y < a.H && x >= 0 && x < a.W && !STEM_DBG(a, 2)) {
                     float4 wts;
-                    if (a.rec_w) {                               // precomputed by pass R
-                        const size_t idx = (size_t)(k_ * a.S + v_) * P + (size_t)(y * a.W + x);
-                        wts = ldg4(a.rec_w + idx * 4);
-                        rec.base = __ldg(a.rec_base + idx);
-                    } else {
-                        make_recipe(scam + v_ * 12, x, y, depth_, a.W, a.H, a.align_corners != 0, wts, rec.base);
-                    }
+                    make_recipe(scam + v_ * 12, x, y, depth_, a.W, a.H, a.align_corners != 0, wts, rec.base);
                     rec.w[0] = wts.x; rec.w[1] = wts.y; rec.w[2] = wts.z; rec.w[3] = wts.w;
 #if STEM_PREFETCH
                     {   // the gather of this fill starts thousands of cycles from now (after the current fill's MMAs): pull its
@@ -311,8 +280,8 @@ __global__ void __launch_bounds__(N_THREADS, 1) cost_stem_tc_kernel(const __grid
         int ty = (int)(blockIdx.x + tl * gridDim.x) / tiles_x, tx = (int)(blockIdx.x + tl * gridDim.x) - ty * tiles_x;
         if (STEM_AHEAD && g < total) write_recipes(ty, tx, v, k, taps_g);
         for (int it = g; it < total; it += G, ++n) {
-            const bool pf = a.prof && blockIdx.x == 0 && g == 0 && lt == 0 && n < 64;
-            unsigned long long* pp = a.prof + n * 8;
+            const bool pf = STEM_PROF(a) && blockIdx.x == 0 && g == 0 && lt == 0 && n < 64;
+            unsigned long long* pp = STEM_PROF(a) + n * 8;
             if (pf) pp[0] = clock64();
             // ---- 1. gather recipes
             TapRec* const taps = taps_g + (STEM_AHEAD ? (n & 1) * NPX : 0);
@@ -324,35 +293,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) cost_stem_tc_kernel(const __grid
             // ---- 2. gather, (warp - ref)^2, split, stage
             const float* sv = a.src + (size_t)v * a.view_stride;
             float* costv_slot = a.costv ? a.costv + ((size_t)(k * a.S + v) * P) * 32 : nullptr;
-            if (a.costv_mode == 2) {
-                // stream mode: stage the halo tile straight from costv (coalesced 128-byte lines, no gather, no recipes)
-#pragma unroll 1
-                constexpr int SB = 6;                 // loads in flight per thread: HBM latency, not bandwidth, bounds this loop
-                for (int jb = 0; jb < ITEMS; jb += SB) {
-                    float4 cvv[SB];
-#pragma unroll
-                    for (int j = 0; j < SB; ++j) {
-                        const int i = lt + (jb + j) * GROUP_THREADS;
-                        const int px = min(i, NPX * 8 - 1) >> 3, c4 = i & 7;
-                        const int r = px / HC, cc = px - r * HC;
-                        const int y = ty * TR - 1 + r, x = tx * TCOL - 1 + cc;
-                        cvv[j] = (i < NPX * 8 && y >= 0 && y < a.H && x >= 0 && x < a.W)
-                                     ? ldg4(costv_slot + ((size_t)y * a.W + x) * 32 + c4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    }
-#pragma unroll
-                    for (int j = 0; j < SB; ++j) {
-                        const int i = lt + (jb + j) * GROUP_THREADS;
-                        const int px = i >> 3, c4 = i & 7;
-                        uint2 hi, lo;
-                        tc::split4_f16(cvv[j], hi, lo);
-                        if (i < NPX * 8) {
-                            const size_t off = ((size_t)(c4 >> 1) * AROWS + px) * 16 + (c4 & 1) * 8;
-                            *reinterpret_cast<uint2*>(stage + off) = hi;
-                            *reinterpret_cast<uint2*>(stage + A_PLANE + off) = lo;
-                        }
-                    }
-                }
-            } else {
+            {
                 const unsigned char* svb = reinterpret_cast<const unsigned char*>(sv) + c4i * 16;
                 const unsigned char* refb = reinterpret_cast<const unsigned char*>(a.ref) + c4i * 16;
                 unsigned char* cvb = reinterpret_cast<unsigned char*>(costv_slot) + c4i * 16;
@@ -524,25 +465,28 @@ __global__ void __launch_bounds__(N_THREADS, 1) cost_stem_tc_kernel(const __grid
     }
 }
 
+#ifdef AARMVS_DEBUG
 int g_dbg = 0;
 unsigned long long* g_stem_prof = nullptr;
+#endif
 
 }  // namespace
 
+#ifdef AARMVS_DEBUG
 extern "C" void aarmvs_debug_flags(int flags) { g_dbg = flags; }
 extern "C" void aarmvs_debug_stem_profile_buffer(void* buf) { g_stem_prof = (unsigned long long*)buf; }
+#endif
 
 extern "C" int aarmvs_cost_stem_tc_max_slots(void) { return (227 * 1024 - 2048 - SMEM_FIXED) / (G * 4 * NBLK * 8); }
 
 namespace {
 int launch_cost_stem_tc(const float* ref, const float* src, size_t view_stride, int H, int W, int S, const float* cams,
                         const void* stem_w_f16, const float* stem_b_host, const float* depth_values, int d_host, const int* d_dev,
-                        int planes, int align_corners, float* t0, double* stats, float* costv, int costv_mode, const float* rec_w,
-                        const unsigned* rec_base, void* stream) {
+                        int planes, int align_corners, float* t0, double* stats, float* costv, int costv_mode, void* stream) {
     AARMVS_CHECK_ARG(t0 && stats && stem_w_f16 && stem_b_host && depth_values && H > 0 && W > 0);
-    AARMVS_CHECK_ARG(costv_mode >= 0 && costv_mode <= 2 && (costv_mode == 0 || costv));
+    AARMVS_CHECK_ARG(costv_mode >= 0 && costv_mode <= 1 && (costv_mode == 0 || costv));
     AARMVS_CHECK_ARG((size_t)H * W * 128 < 0x7FFFFFFFull);          // gather recipes hold 32-bit byte offsets (TapRec.ref is signed)
-    AARMVS_CHECK_ARG(costv_mode == 2 || (ref && src && cams));
+    AARMVS_CHECK_ARG(ref && src && cams);
     AARMVS_CHECK_ARG(S >= 1 && S <= AARMVS_MAX_SRC && planes >= 1 && planes <= AARMVS_MAX_PLANES);
     StemArgs a = {};
     a.K = planes;
@@ -552,9 +496,10 @@ int launch_cost_stem_tc(const float* ref, const float* src, size_t view_stride, 
     a.depth_values = depth_values; a.d_host = d_host; a.d_dev = d_dev; a.align_corners = align_corners; a.t0 = t0;
     a.stats = stats;
     a.costv = costv; a.costv_mode = costv_mode;
-    a.rec_w = rec_w; a.rec_base = rec_base;
+#ifdef AARMVS_DEBUG
     a.dbg = g_dbg;
     a.prof = g_stem_prof;
+#endif
     static unsigned long long smem_ok = 0;
     constexpr int SMEM_CAP = 227 * 1024 - 2048;      // the kernel also has ~1 KB of static shared memory
     static_assert(SMEM_FIXED + G * 4 * NBLK * 8 * 8 <= SMEM_CAP, "shared memory budget");
@@ -574,30 +519,5 @@ extern "C" int aarmvs_cost_stem_tc(const float* ref, const float* src, size_t vi
                                    const float* depth_values, int d_host, const int* d_dev, int planes, int align_corners,
                                    float* t0, double* stats, float* costv, int costv_mode, void* stream) {
     return launch_cost_stem_tc(ref, src, view_stride, H, W, S, cams, stem_w_f16, stem_b_host, depth_values, d_host, d_dev, planes,
-                               align_corners, t0, stats, costv, costv_mode, nullptr, nullptr, stream);
-}
-
-extern "C" int aarmvs_cost_stem_tc_recipes(const float* ref, const float* src, size_t view_stride, int H, int W, int S,
-                                           const float* cams, const void* stem_w_f16, const float* stem_b_host,
-                                           const float* depth_values, int d_host, const int* d_dev, int planes,
-                                           int align_corners, float* t0, double* stats, float* costv, int costv_mode,
-                                           const float* rec_w, const unsigned* rec_base, void* stream) {
-    AARMVS_CHECK_ARG(rec_w && rec_base && costv_mode != 2 && ((uintptr_t)rec_w & 15) == 0);
-    return launch_cost_stem_tc(ref, src, view_stride, H, W, S, cams, stem_w_f16, stem_b_host, depth_values, d_host, d_dev, planes,
-                               align_corners, t0, stats, costv, costv_mode, rec_w, rec_base, stream);
-}
-
-extern "C" int aarmvs_sweep_recipes(int H, int W, int S, const float* cams, const float* depth_values, int d_host,
-                                    const int* d_dev, int planes, int align_corners, float* rec_w, unsigned* rec_base,
-                                    void* stream) {
-    AARMVS_CHECK_ARG(cams && depth_values && rec_w && rec_base && H > 0 && W > 0 && ((uintptr_t)rec_w & 15) == 0);
-    AARMVS_CHECK_ARG(S >= 1 && S <= AARMVS_MAX_SRC && planes >= 1 && planes <= AARMVS_MAX_PLANES);
-    AARMVS_CHECK_ARG((size_t)H * W * 128 < 0xFFFFFFFFull);
-    RecipeArgs a = {};
-    a.H = H; a.W = W; a.S = S; a.K = planes; a.cams = cams; a.depth_values = depth_values; a.d_host = d_host; a.d_dev = d_dev;
-    a.align_corners = align_corners; a.rec_w = rec_w; a.rec_base = rec_base;
-    const int P = H * W;
-    const int bx = (P + 256 * 4 - 1) / (256 * 4);                 // four pixels per thread
-    sweep_recipes_kernel<<<dim3(bx, planes * S), 256, 0, (cudaStream_t)stream>>>(a);
-    AARMVS_LAUNCH_RESULT();
+                               align_corners, t0, stats, costv, costv_mode, stream);
 }

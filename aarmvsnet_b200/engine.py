@@ -8,6 +8,7 @@ Per batch of K depth planes (models/drmvsnet.py:306-334): cost_stem, omega_stats
                                                 head_wta, next_plane: 4 + 9 K launches, 0 host syncs
                                                 (the reference issues ~526 ATen ops and 12 host syncs PER PLANE).
 """
+import collections
 import ctypes
 
 import torch
@@ -55,18 +56,14 @@ def _psrc_array(*srcs):
 class Engine:
     """Runs EMVSNet.forward's arithmetic for one model instance (weights are re-packed when they change)."""
 
-    def __init__(self, module, align_corners=False, use_graph=True, cell_math="tc", plane_batch=8, keep_costv=True, split_gather=False,
-                 recipes=False):
+    MAX_WORKSPACES = 2        # per-shape workspaces (and their captured graphs) kept alive; least recently used is dropped
+
+    def __init__(self, module, align_corners=False, use_graph=True, cell_math="tc", plane_batch=8, keep_costv=True):
+        # cell_math "fma" (fp32 CUDA-core kernels) is a precision reference for the tests, not a product path
         if cell_math not in ("tc", "fma"):
             raise ValueError("cell_math must be 'tc' (tcgen05, split-fp16 operands) or 'fma' (fp32 CUDA cores)")
         self.cell_math = cell_math
         self.keep_costv = keep_costv
-        # split_gather: gather once in aarmvs_warp_cost, then stream costv into the stem conv as well (measured slower than
-        # the fused pass A at cfg2: 1.25 vs 1.12 ms/plane, the stem kernel's staging/epilogue skeleton dominates either way)
-        self.split_gather = split_gather
-        # recipes: pass R (aarmvs_sweep_recipes) evaluates the sample positions of a plane batch once and pass A copies them.
-        # Measured at cfg2: pass R 0.067 + pass A 0.932 ms/plane against 0.948 with the recipes evaluated inside pass A -> off.
-        self.recipes = recipes
         if not 1 <= plane_batch <= 16:
             raise ValueError("plane_batch must be in 1..16")
         self.plane_batch = plane_batch            # planes per launch of passes A-D (L1/L2 reuse of the source features)
@@ -75,7 +72,8 @@ class Engine:
         self.use_graph = use_graph
         self.lib = capi.load()
         self._wkey = None
-        self._ws = {}
+        self._ws = collections.OrderedDict()          # LRU of sweep workspaces, see _workspace
+        self._fs = collections.OrderedDict()          # LRU of FeatNet scratch buffers, see _feat_scratch
 
     # ------------------------------------------------------------------------------------------ weights
     def _weights(self, device):
@@ -83,7 +81,8 @@ class Engine:
         key = (str(device),) + tuple((p.data_ptr(), p._version) for p in params)
         if key == self._wkey:
             return self.w
-        sd = {k: v.detach().to(device=device, dtype=torch.float32) for k, v in self.module.state_dict().items()}
+        # re-pack on the HOST and upload each packed tensor once (a few dozen copies instead of ~1 000 tiny device kernels)
+        sd = {k: v.detach().to(device="cpu", dtype=torch.float32) for k, v in self.module.state_dict().items()}
         w = {}
 
         def convgn(name, prefix, cin_pad=None):
@@ -129,6 +128,8 @@ class Engine:
         w["head.w_host"] = capi.host_floats(pack.conv_taps(sd[cr + ".conv_0.weight"]).reshape(-1).cpu().tolist())
         w["head.wtc"] = pack.head_pairs_f16(sd[cr + ".conv_0.weight"])
         w["head.b_host"] = capi.host_floats(sd[cr + ".conv_0.bias"].cpu().tolist())
+        w = {k: (v.to(device) if torch.is_tensor(v) else tuple(t.to(device) for t in v) if isinstance(v, tuple) else v)
+             for k, v in w.items()}
         self.w, self._wkey = w, key
         self._ws.clear()                 # graphs bake host-side parameters: drop them with the old weights
         return w
@@ -138,7 +139,10 @@ class Engine:
         key = (H, W, N, D, str(device), keep_cost, with_loss)
         ws = self._ws.get(key)
         if ws is not None:
+            self._ws.move_to_end(key)
             return ws
+        while len(self._ws) >= self.MAX_WORKSPACES:          # a scan mixes view counts / shapes: do not let slabs pile up
+            self._ws.popitem(last=False)
         if H % 4 or W % 4:
             raise RuntimeError(f"feature height and width must be multiples of 4, got {H}x{W} (models/drmvsnet.py:51-52, 148-160)")
         if not 2 <= N <= 16:
@@ -148,25 +152,13 @@ class Engine:
         K = min(self.plane_batch, D)
         ws = {"H": H, "W": W, "N": N, "D": D, "K": K, "graph": None, "warm": False}
         ws["feat"] = torch.empty(N, P, 32, **f32)
-        # FeatNet scratch (reused for every view)
-        ws["a1"] = torch.empty(P, 8, **f32)
-        ws["a2"] = torch.empty(P, 16, **f32)
-        for l, s in enumerate((1, 2, 4)):
-            pl = P // (s * s)
-            ws[f"x{l}"] = torch.empty(pl, 32, **f32)
-            ws[f"om{l}"] = torch.empty(pl, 32, **f32)
-            ws[f"dc{l}"] = torch.empty(pl, 32, **f32)
-            ws[f"m{l}"] = torch.empty(pl, 16 if l == 0 else 8, **f32)
-        ws["fsums"] = torch.zeros(64, device=device, dtype=torch.float64)
+        ws.update(self._feat_scratch(H, W, device))
         # plane sweep
         ws["t0"] = torch.empty(K, S, P, 4, **f32)
         tc = self.cell_math == "tc"
         # (warp - ref)^2 kept by pass A so that pass D streams instead of gathering again (tensor-core path only)
         ws["costv"] = torch.empty(K, S, P, 32, **f32) if tc and self.keep_costv else None
         ws["cost"] = torch.empty(K, P, 32, **f32) if ws["costv"] is None else None
-        if tc and self.recipes and not self.split_gather:
-            ws["rec_w"] = torch.empty(K, S, P, 4, **f32)
-            ws["rec_base"] = torch.empty(K, S, P, device=device, dtype=torch.int32)
         if tc:
             # everything the cells read is kept as fp16 (hi, lo) operand planes [2][C/8][H][W][8] (include/aarmvs.h):
             # cost (pass D), h ping-pong pairs and max-pooled h (cell epilogues), GroupNorm+ReLU'd deconv outputs
@@ -199,6 +191,30 @@ class Engine:
                      torch.zeros(1, device=device, dtype=torch.float64)) if with_loss else None)
         self._ws[key] = ws
         return ws
+
+    def _feat_scratch(self, H, W, device):
+        """FeatNet scratch (reused for every view), separate from the sweep workspace so features() allocates only this."""
+        key = (H, W, str(device))
+        fs = self._fs.get(key)
+        if fs is not None:
+            self._fs.move_to_end(key)
+            return fs
+        if H % 4 or W % 4:
+            raise RuntimeError(f"feature height and width must be multiples of 4, got {H}x{W} (models/drmvsnet.py:51-52, 148-160)")
+        while len(self._fs) >= self.MAX_WORKSPACES:
+            self._fs.popitem(last=False)
+        f32 = dict(device=device, dtype=torch.float32)
+        P = H * W
+        fs = {"H": H, "W": W, "a1": torch.empty(P, 8, **f32), "a2": torch.empty(P, 16, **f32)}
+        for l, s in enumerate((1, 2, 4)):
+            pl = P // (s * s)
+            fs[f"x{l}"] = torch.empty(pl, 32, **f32)
+            fs[f"om{l}"] = torch.empty(pl, 32, **f32)
+            fs[f"dc{l}"] = torch.empty(pl, 32, **f32)
+            fs[f"m{l}"] = torch.empty(pl, 16 if l == 0 else 8, **f32)
+        fs["fsums"] = torch.zeros(64, device=device, dtype=torch.float64)
+        self._fs[key] = fs
+        return fs
 
     # ------------------------------------------------------------------------------------------ FeatNet
     def feature_map(self, img, out, ws, w, stream):
@@ -250,34 +266,14 @@ class Engine:
                                             _ptr(g1[0]), _ptr(g1[1]), _ptr(g2[0]), _ptr(g2[1]), H, W, _ptr(out), stream),
                    "aarmvs_feat_assemble")
 
-    def sweep_recipes(self, H, W, S, cams, depths, d_host, dptr, planes, rec_w, rec_base, stream):
-        """Pass R: sample positions of `planes` planes x S views x H*W pixels -> gather recipes for pass A."""
-        capi.check(self.lib.aarmvs_sweep_recipes(H, W, S, cams, depths, d_host, dptr, planes, int(self.align_corners), rec_w, rec_base,
-                                                 stream), "aarmvs_sweep_recipes")
-
-    def cost_stem(self, ref, src, view_stride, H, W, S, cams, w, depths, d_host, dptr, planes, t0, sums, stream, costv=None,
-                  recipes=None, sweep=True):
-        """Pass A (gather, (warp - ref)^2, omega stem conv) on the tensor cores ('tc') or the fp32 FMA pipe ('fma').
-        With costv (tc only): the gather runs once in aarmvs_warp_cost and the stem conv streams its result."""
+    def cost_stem(self, ref, src, view_stride, H, W, S, cams, w, depths, d_host, dptr, planes, t0, sums, stream, costv=None):
+        """Pass A (gather, (warp - ref)^2, omega stem conv) on the tensor cores ('tc'; with costv the per-view cost is also
+        stored so that pass D streams it instead of gathering again) or the fp32 FMA pipe ('fma', test reference)."""
         ac = int(self.align_corners)
         if self.cell_math == "tc":
-            if costv is not None and self.split_gather:
-                capi.check(self.lib.aarmvs_warp_cost(ref, src, view_stride, H, W, S, cams, depths, d_host, dptr, planes, ac, costv,
-                                                     stream), "aarmvs_warp_cost")
-                mode = 2
-            else:
-                mode = 1 if costv is not None else 0
-            if recipes is not None and mode != 2:
-                rec_w, rec_base = recipes
-                if sweep:
-                    self.sweep_recipes(H, W, S, cams, depths, d_host, dptr, planes, rec_w, rec_base, stream)
-                capi.check(self.lib.aarmvs_cost_stem_tc_recipes(ref, src, view_stride, H, W, S, cams, _ptr(w["stem.wtc"]),
-                                                                w["stem.b_host"], depths, d_host, dptr, planes, ac, t0, sums, costv,
-                                                                mode, rec_w, rec_base, stream), "aarmvs_cost_stem_tc_recipes")
-                return
             capi.check(self.lib.aarmvs_cost_stem_tc(ref, src, view_stride, H, W, S, cams, _ptr(w["stem.wtc"]), w["stem.b_host"],
-                                                    depths, d_host, dptr, planes, ac, t0, sums, costv, mode, stream),
-                       "aarmvs_cost_stem_tc")
+                                                    depths, d_host, dptr, planes, ac, t0, sums, costv, 1 if costv is not None else 0,
+                                                    stream), "aarmvs_cost_stem_tc")
         else:
             capi.check(self.lib.aarmvs_cost_stem(ref, src, view_stride, H, W, S, cams, w["stem.w_host"], w["stem.b_host"],
                                                  depths, d_host, dptr, planes, ac, t0, sums, stream), "aarmvs_cost_stem")
@@ -306,12 +302,8 @@ class Engine:
         ps = ws["psums"]
         n_omega = ws["K"] * S * 6
         costv = _ptr(ws["costv"]) if ws["costv"] is not None else None
-        recipes = (_ptr(ws["rec_w"]), _ptr(ws["rec_base"])) if "rec_w" in ws else None
-        if recipes is not None:
-            self.sweep_recipes(H, W, S, _ptr(ws["cams"]), _ptr(ws["depths"]), 0, dptr, nplanes, *recipes, stream)
-            mark("recipes")
         self.cost_stem(ref, src, P * 32, H, W, S, _ptr(ws["cams"]), w, _ptr(ws["depths"]), 0, dptr, nplanes, _ptr(ws["t0"]),
-                       _ptr(ps), stream, costv, recipes, sweep=False)
+                       _ptr(ps), stream, costv)
         mark("cost_stem")
         for stage in (2, 3):
             capi.check(lib.aarmvs_omega_stats(stage, _ptr(ws["t0"]), H, W, S, nplanes, w["tail_host"], _ptr(ps), stream),
@@ -412,7 +404,7 @@ class Engine:
     def relative_cameras(proj_matrices):
         """rot | trans of src_proj @ inverse(ref_proj) per source view (models/module.py:16-18), evaluated on the host
         with the same torch ops as the reference so the fp32 values are the reference's.  [N,4,4] -> [N-1,12]."""
-        pm = proj_matrices.detach().to("cpu", torch.float32)
+        pm = proj_matrices.detach().to("cpu", torch.float32)        # no copy / sync when the caller already holds host matrices
         ref = pm[0:1]
         proj = torch.matmul(pm[1:], torch.inverse(ref))
         return torch.cat([proj[:, :3, :3].reshape(-1, 9), proj[:, :3, 3]], 1).contiguous()
@@ -425,10 +417,11 @@ class Engine:
         _, H, W = img.shape
         with torch.cuda.device(device):
             w = self._weights(device)
-            ws = self._workspace(H, W, 2, 1, device, False)
+            fs = self._feat_scratch(H, W, device)
+            out = torch.empty(H * W, 32, device=device, dtype=torch.float32)
             stream = ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
-            self.feature_map(img.to(torch.float32).contiguous(), ws["feat"][0], ws, w, stream)
-            return ws["feat"][0].clone()
+            self.feature_map(img.to(torch.float32).contiguous(), out, fs, w, stream)
+            return out
 
     @staticmethod
     def nearest_hypothesis(depth_values, depth_gt, mask):

@@ -107,7 +107,7 @@ class EMVSNet(nn.Module):
     a non-default max_h/max_w raises the same way the reference's torch.cat would."""
 
     def __init__(self, disparity_level=32, image_scale=0.25, max_h=960, max_w=480, return_depth=False,
-                 align_corners=False, use_graph=True, strict_size=False, cell_math="tc", plane_batch=8, keep_costv=True, split_gather=False, recipes=False):
+                 align_corners=False, use_graph=True, strict_size=False, cell_math="tc", plane_batch=8, keep_costv=True):
         super().__init__()
         self.feature = FeatNet()
         self.cost_regularization = UNetConvLSTM()
@@ -116,7 +116,7 @@ class EMVSNet(nn.Module):
         self.input_size = (int(max_h * image_scale), int(max_w * image_scale))
         self.strict_size = strict_size
         self._engine = Engine(self, align_corners=align_corners, use_graph=use_graph, cell_math=cell_math,
-                              plane_batch=plane_batch, keep_costv=keep_costv, split_gather=split_gather, recipes=recipes)
+                              plane_batch=plane_batch, keep_costv=keep_costv)
 
     def features(self, img):
         """FeatNet of one image [3,H,W] as the kernels' NHWC feature tensor [H*W,32] (cacheable across reference views)."""

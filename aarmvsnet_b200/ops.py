@@ -54,11 +54,12 @@ def feat_net(model, img):
     eng = model._engine
     B, _, H, W = img.shape
     w = eng._weights(img.device)
-    ws = eng._workspace(H, W, 2, 1, img.device, False)
+    fs = eng._feat_scratch(H, W, img.device)
+    feat = torch.empty(H * W, 32, device=img.device)
     out = torch.empty(B, 32, H, W, device=img.device)
     for b in range(B):
-        eng.feature_map(img[b].float().contiguous(), ws["feat"][0], ws, w, _stream(img.device))
-        out[b] = _nchw(ws["feat"][0], H, W)
+        eng.feature_map(img[b].float().contiguous(), feat, fs, w, _stream(img.device))
+        out[b] = _nchw(feat, H, W)
     return out
 
 

@@ -23,7 +23,7 @@ extern "C" {
 #define AARMVS_MAX_SRC_VIEWS 15
 #define AARMVS_MAX_PLANES_PER_CALL 16
 
-int aarmvs_version(void);          /* ABI version, currently 3 */
+int aarmvs_version(void);          /* ABI version, currently 4 */
 int aarmvs_sm_count(void);         /* multiprocessors of the current device (148 on B200), <0 on error */
 
 /* ---------------------------------------------------------------------------------------------------------
@@ -108,29 +108,17 @@ int aarmvs_cost_stem(const float* ref, const float* src, size_t view_stride, int
  * stem_w_f16: DEVICE [9 taps][4 chunks of 8 input channels][16 rows][8] fp16, rows 0-3 = hi(w[o]), rows 8-11 = lo(w[o])
  * (others zero): per tile the conv is 9 taps x 2 K-steps x (A_hi, A_lo) MMAs with N = 16, taps addressed by descriptor.
  * costv [planes][S][H*W][32] fp32 = (warp - ref)^2; costv_mode 0: unused; 1: WRITTEN here (interior pixels of each tile)
- * so that aarmvs_aggregate can skip its gather; 2: READ here instead of gathering (aarmvs_warp_cost wrote it; ref, src and
- * cams are then unused) -- the gather then runs exactly once per pixel, view and plane.  H * W * 128 < 2^31 (the gather
- * recipes hold 32-bit byte offsets): larger images return AARMVS_ERR_ARG. */
+ * so that aarmvs_aggregate can skip its gather -- the gather then runs exactly once per pixel, view and plane.
+ * H * W * 128 < 2^31 (the gather recipes hold 32-bit byte offsets): larger images return AARMVS_ERR_ARG. */
 int aarmvs_cost_stem_tc_max_slots(void);   /* upper bound of planes * S per launch (shared-memory GroupNorm partial sums) */
 int aarmvs_cost_stem_tc(const float* ref, const float* src, size_t view_stride, int H, int W, int S, const float* cams,
                         const void* stem_w_f16, const float* stem_b_host, const float* depth_values, int d_host,
                         const int* d_dev, int planes, int align_corners, float* t0, double* stats, float* costv,
                         int costv_mode, void* stream);
 
-/* Pass R: the gather recipes of pass A for every (plane, source view, pixel) of a plane batch, evaluated once (pass A itself
- * would re-evaluate them for the halo pixels of every tile): rec_w [planes][S][H*W][4] = the four bilinear weights (0 for a
- * corner outside the source image), rec_base [planes][S][H*W] = byte offset of the clamped north-west source line | column
- * step | row step << 1.  Same arithmetic as aarmvs_warp (bit-exact sample positions).  H * W * 128 < 2^32. */
-int aarmvs_sweep_recipes(int H, int W, int S, const float* cams, const float* depth_values, int d_host, const int* d_dev,
-                         int planes, int align_corners, float* rec_w, unsigned* rec_base, void* stream);
-/* aarmvs_cost_stem_tc reading the recipes of aarmvs_sweep_recipes instead of evaluating them (costv_mode 0 or 1). */
-int aarmvs_cost_stem_tc_recipes(const float* ref, const float* src, size_t view_stride, int H, int W, int S, const float* cams,
-                                const void* stem_w_f16, const float* stem_b_host, const float* depth_values, int d_host,
-                                const int* d_dev, int planes, int align_corners, float* t0, double* stats, float* costv,
-                                int costv_mode, const float* rec_w, const unsigned* rec_base, void* stream);
-
-/* Pass A1 (used with costv_mode 2): costv[k][v][p][:] = (warp_v(p) - ref(p))^2 for the `planes` planes starting at d:
- * homo_warping_depthwise (models/module.py:6-38) + the squared difference (models/drmvsnet.py:311), nothing else. */
+/* costv[k][v][p][:] = (warp_v(p) - ref(p))^2 for the `planes` planes starting at d: homo_warping_depthwise
+ * (models/module.py:6-38) + the squared difference (models/drmvsnet.py:311), nothing else.  Used by the backward pass, which
+ * re-materialises the per-view cost of one plane (the operand of the omega stem's weight gradient). */
 int aarmvs_warp_cost(const float* ref, const float* src, size_t view_stride, int H, int W, int S, const float* cams,
                      const float* depth_values, int d_host, const int* d_dev, int planes, int align_corners, float* costv,
                      void* stream);
@@ -276,19 +264,24 @@ int aarmvs_tc_selftest(const void* a_f16, int a_rows, const void* b_f16, float* 
  * with 8-row groups `group_rows` rows apart, start row advancing by a_shift_rows per instruction) on `grid` CTAs. */
 int aarmvs_tc_mma_bench(int N, int group_rows, int reps, int a_shift_rows, int grid, long long* out, void* stream);
 
+/* ---- debug hooks: only in libraries built with -DAARMVS_DEBUG (AARMVS_NVCC_EXTRA=-DAARMVS_DEBUG python -m
+ * aarmvsnet_b200.build --force); the product library has no process-global state and does not export them. */
+#ifdef AARMVS_DEBUG
 /* Debug ablation switches for aarmvs_cost_stem_tc (results become wrong; timing experiments only): 2 skip the sample-position math, 4 skip the MMAs.  0 = normal. */
 void aarmvs_debug_flags(int flags);
 /* Debug: worker group 0 of CTA 0 of subsequent aarmvs_cost_stem_tc launches records clock64 stamps per fill ([64][8]
  * uint64 device buffer; NULL switches off). */
 void aarmvs_debug_stem_profile_buffer(void* buf);
 
-/* Debug aid (the only process-global state in the library, off by default): when set to a device buffer of
+/* Debug aid: when set to a device buffer of
  * 64 x 12 uint64, CTA 0 of subsequent aarmvs_convlstm_cell_tc launches records clock64 stamps of its loader / MMA /
  * epilogue roles per tile.  Pass NULL to switch off. */
 void aarmvs_debug_profile_buffer(void* buf);
 /* Debug ablation switches for aarmvs_convlstm_cell_tc (results become wrong): 1 no TMA loads,
  * 4 no global I/O in the epilogue, 8 no MMAs, 16 no gate transcendentals, 32 no max-pool output. */
 void aarmvs_debug_cell_flags(int flags);
+
+#endif
 
 #ifdef __cplusplus
 }

@@ -11,6 +11,7 @@ from conftest import ROOT
 def _declared():
     text = open(os.path.join(ROOT, "include", "aarmvs.h")).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    text = re.sub(r"#ifdef AARMVS_DEBUG.*?#endif", "", text, flags=re.S)      # debug hooks: -DAARMVS_DEBUG builds only
     return sorted(set(re.findall(r"\b(aarmvs_[a-z0-9_]+)\s*\(", text)))
 
 
@@ -23,7 +24,9 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), n
     assert sorted(capi.PROTOTYPES) == names        # the ctypes table and the header agree
-    assert lib.aarmvs_version() == 3
+    assert lib.aarmvs_version() == capi.ABI_VERSION
+    for n in capi.DEBUG_PROTOTYPES:                 # the product library carries no process-global debug switches
+        assert not hasattr(lib, n), n
 
 
 def test_library_is_sm100a_and_has_no_torch_dependency():

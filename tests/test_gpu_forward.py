@@ -22,29 +22,26 @@ def _model(g, return_depth=True, **kw):
 
 
 @pytest.mark.parametrize("name", CASES)
-@pytest.mark.parametrize("use_graph,cell_math,plane_batch", [(True, "tc", 8), (False, "tc", 5), (True, "fma", 1), (True, "tc", 3), (True, "tc-gather", 4), (True, "tc-split", 8), (True, "tc-recipes", 8)])
+@pytest.mark.parametrize("use_graph,cell_math,plane_batch", [(True, "tc", 8), (False, "tc", 5), (True, "fma", 1), (True, "tc", 3), (True, "tc-gather", 4)])
 def test_forward_matches_reference(name, use_graph, cell_math, plane_batch):
     """plane_batch 8 / 5 / 3 / 1 against D = 8 / 24 / 12: full batches, a partial last batch, and no batching."""
     g = load_golden(name)
-    # tc: pass A gathers and stores costv, pass D streams it; tc-split: gather once (aarmvs_warp_cost), stem conv and pass D
-    # both stream costv; tc-gather: both passes gather (no costv buffer); tc-recipes: pass A copies the gather recipes of pass R
-    # (aarmvs_sweep_recipes) instead of evaluating them itself
-    keep, split = cell_math != "tc-gather", cell_math == "tc-split"
-    m = _model(g, use_graph=use_graph, cell_math=cell_math.split("-")[0], plane_batch=plane_batch, keep_costv=keep, split_gather=split,
-               recipes=cell_math == "tc-recipes")
+    # tc: pass A gathers and stores costv, pass D streams it; tc-gather: both passes gather (no costv buffer);
+    # fma: the fp32 CUDA-core kernels kept as a precision reference
+    m = _model(g, use_graph=use_graph, cell_math=cell_math.split("-")[0], plane_batch=plane_batch, keep_costv=cell_math != "tc-gather")
     for _ in range(2):           # second call replays the captured plane graph
         out = m(g["imgs"].cuda(), g["proj_matrices"].cuda(), g["depth_values"].cuda())
     idx, want = out["index"].cpu().long(), g["index"].long()
     same = idx == want
     frac = same.float().mean().item()
     print(f"{name}: same plane {frac * 100:.4f}%")
-    assert frac >= 0.999
+    assert frac >= 0.9998                      # measured: 100 % on all three fixtures
     depth = out["depth"].cpu()
     torch.testing.assert_close(depth[same], g["depth"][same], rtol=0, atol=0)
     interval = (g["depth_values"][:, 1:] - g["depth_values"][:, :-1]).abs().min().item()
     rng = (g["depth_values"].max() - g["depth_values"].min()).item()
     assert ((depth - g["depth"]).abs() <= 0.5 * interval).float().mean().item() >= 0.999
-    assert (idx - want).abs().max().item() <= 1 or frac >= 0.9995      # disagreements are neighbouring-plane near ties
+    assert (idx - want).abs().max().item() <= 1                        # disagreements are neighbouring-plane near ties
     torch.testing.assert_close(out["photometric_confidence"].cpu()[same], g["photometric_confidence"][same],
                                rtol=1e-3, atol=1e-3)
     assert out["evidential_prediction"] is None

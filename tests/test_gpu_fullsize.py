@@ -7,6 +7,10 @@ from conftest import load_weights
 
 pytestmark = pytest.mark.gpu
 
+# plane-mismatch bar against the oracle: 4x the reference's own fp32-vs-fp64 disagreement (4.9e-5); measured
+# values in round 1 were 2.4e-5 (cfg1 crop) and 5.3e-6 (cfg2 resolution)
+MISMATCH_BAR = 2e-4
+
 
 def _model(h, w, ckpt="model_dtu_v2.ckpt", **kw):
     import aarmvsnet_b200 as aa
@@ -31,31 +35,73 @@ def test_mid_size_against_oracle(smooth):
     same = out["index"].cpu().long() == ref["index"]
     frac = same.float().mean().item()
     print(f"smooth={smooth}: same plane on {frac * 100:.4f}% of pixels")
-    assert frac >= 0.999
+    assert frac >= 1.0 - MISMATCH_BAR
+    assert (out["index"].cpu().long() - ref["index"]).abs().max().item() <= 1
     torch.testing.assert_close(out["depth"].cpu()[same], ref["depth"][same], rtol=0, atol=0)
     torch.testing.assert_close(out["photometric_confidence"].cpu()[same], ref["photometric_confidence"][same], rtol=1e-3, atol=1e-3)
 
 
-def test_cfg1_crop_against_oracle():
-    """BASELINE cfg1 (640x512, N=3, D=48, inverse depths) on a 320x256 crop-sized sample: the oracle takes a few seconds on
-    the box's host cores.  Reports the plane-mismatch fraction next to the reference's own fp32-vs-fp64 floor (4.9e-5)."""
-    from aarmvsnet_b200 import synth
-    from oracle import aarmvs_oracle as orc
-    s = synth.make_sample(256, 320, 3, 48, seed=33, depth_mode="inverse")
-    out = _run(_model(256, 320), s)
-    ref = orc.forward_test(load_weights("model_dtu_v2.ckpt"), s["imgs"], s["proj_matrices"], s["depth_values"], return_index=True)
+def _compare(tag, out, ref, s, conf_tol=1e-3):
+    """north_star parity statistics of one forward against the oracle: plane-mismatch fraction (bar: MISMATCH_BAR, next to the
+    reference's own fp32-vs-fp64 floor of 4.9e-5), neighbouring planes only, depth identical where the plane is, depth error
+    against the range, confidence."""
     idx = out["index"].cpu().long()
     same = idx == ref["index"]
     mismatch = 1.0 - same.float().mean().item()
-    print(f"cfg1 crop: plane mismatch fraction {mismatch:.2e} (reference fp32 vs fp64: 4.9e-05), max index distance {(idx - ref['index']).abs().max().item()}")
-    assert mismatch <= 1e-3
-    interval = (s["depth_values"][0, 1:] - s["depth_values"][0, :-1]).abs()
+    dist = (idx - ref["index"]).abs().max().item()
     rng = (s["depth_values"].max() - s["depth_values"].min()).item()
     err = (out["depth"].cpu() - ref["depth"]).abs()
+    dconf = (out["photometric_confidence"].cpu() - ref["photometric_confidence"]).abs()
+    print(f"{tag}: plane mismatch fraction {mismatch:.2e} (reference fp32 vs fp64: 4.9e-05) on {same.numel()} pixels, max index "
+          f"distance {dist}, max |depth error| / range {err.max().item() / rng:.2e}, max |dconf| {dconf[same].max().item():.2e}")
+    assert mismatch <= MISMATCH_BAR
+    assert dist <= 1
     assert (err[same] == 0).all()
-    assert (err <= 0.5 * interval.min()).float().mean().item() >= 0.999
-    print(f"cfg1 crop: max |depth error| / depth range = {err.max().item() / rng:.2e} on {int((~same).sum())} differing pixels of {same.numel()}")
-    torch.testing.assert_close(out["photometric_confidence"].cpu()[same], ref["photometric_confidence"][same], rtol=1e-3, atol=1e-3)
+    interval = (s["depth_values"][0, 1:] - s["depth_values"][0, :-1]).abs()
+    assert (err <= 0.5 * interval.min()).float().mean().item() >= 1.0 - MISMATCH_BAR
+    torch.testing.assert_close(out["photometric_confidence"].cpu()[same], ref["photometric_confidence"][same], rtol=conf_tol, atol=conf_tol)
+    return mismatch
+
+
+def test_cfg1_full_against_oracle():
+    """BASELINE cfg1 in full: 640x512, N=3, D=48 inverse-depth planes, model_dtu_v2.ckpt, against the oracle run on the box's
+    host cores (~25 s)."""
+    from aarmvsnet_b200 import synth
+    from oracle import aarmvs_oracle as orc
+    s = synth.make_sample(512, 640, 3, 48, seed=33, depth_mode="inverse")
+    out = _run(_model(512, 640), s)
+    ref = orc.forward_test(load_weights("model_dtu_v2.ckpt"), s["imgs"], s["proj_matrices"], s["depth_values"], return_index=True)
+    _compare("cfg1 640x512 N=3 D=48", out, ref, s)
+
+
+def test_long_recurrence_d512_against_oracle():
+    """The headline depth count: D = 512 dependent ConvLSTM steps (split-fp16 products, approximate gate transcendentals and
+    fp64-vs-ATen GroupNorm sums accumulate through the recurrence) at 128x160, N=5, uniform depths, against the oracle; also
+    prints the drift of the regularised cost at planes 1 / 64 / 256 / 511."""
+    from aarmvsnet_b200 import synth
+    from oracle import aarmvs_oracle as orc
+    H, W, N, D = 128, 160, 5, 512
+    s = synth.make_sample(H, W, N, D, seed=41)
+    m = _model(H, W)
+    out = _run(m, s)
+    ref = orc.forward_test(load_weights("model_dtu_v2.ckpt"), s["imgs"], s["proj_matrices"], s["depth_values"], return_index=True,
+                           return_cost=True)
+    o = m._engine.depth_map(s["imgs"][0].cuda(), s["proj_matrices"][0], s["depth_values"][0].cuda(), keep_cost=True)
+    cost = o["cost_reg"].cpu()
+    drift = {d: (cost[d] - ref["cost_reg"][0, d]).abs().max().item() for d in (1, 64, 256, 511)}
+    print("D=512 recurrence: max |cost_reg - oracle| at planes 1/64/256/511:", ", ".join(f"{v:.2e}" for v in drift.values()))
+    assert max(drift.values()) < 2e-3
+    _compare("128x160 N=5 D=512", out, ref, s)
+
+
+def test_blended_mid_size_against_oracle():
+    """model_blended_v2.ckpt beyond the 40x56 golden fixture: 128x160, N=7, D=64 inverse depths."""
+    from aarmvsnet_b200 import synth
+    from oracle import aarmvs_oracle as orc
+    s = synth.make_sample(128, 160, 7, 64, seed=43, depth_mode="inverse")
+    out = _run(_model(128, 160, ckpt="model_blended_v2.ckpt"), s)
+    ref = orc.forward_test(load_weights("model_blended_v2.ckpt"), s["imgs"], s["proj_matrices"], s["depth_values"], return_index=True)
+    _compare("blended 128x160 N=7 D=64", out, ref, s)
 
 
 def test_tensor_core_and_fma_cells_agree():
@@ -66,7 +112,7 @@ def test_tensor_core_and_fma_cells_agree():
     b = _run(_model(256, 320, cell_math="fma"), s)
     same = (a["index"] == b["index"]).float().mean().item()
     print(f"tc vs fma: same plane on {same * 100:.4f}% of pixels")
-    assert same >= 0.999
+    assert same >= 1.0 - MISMATCH_BAR
     assert (a["photometric_confidence"] - b["photometric_confidence"]).abs().max().item() < 5e-3
 
 
@@ -99,10 +145,9 @@ def test_cfg2_full_size_properties():
     torch.testing.assert_close(a["photometric_confidence"], b["photometric_confidence"], rtol=1e-4, atol=1e-5)
 
 
-def test_cfg4_full_size_properties_and_recipe_path():
+def test_cfg4_full_size_properties():
     """BASELINE cfg4 (Tanks&Temples shape 1920x1056, N=7, D=512, model_blended_v2.ckpt, inverse depths): the same
-    size-independent properties as cfg2, plus a cross-check of two kernel paths at full size -- pass A copying the gather
-    recipes of pass R (aarmvs_sweep_recipes) must reproduce pass A evaluating them itself bit for bit."""
+    size-independent properties as cfg2."""
     from aarmvsnet_b200 import synth
     H, W, N, D = 1056, 1920, 7, 512
     s = synth.make_sample(H, W, N, D, seed=4, depth_mode="inverse")
@@ -114,10 +159,6 @@ def test_cfg4_full_size_properties_and_recipe_path():
     conf = a["photometric_confidence"][0]
     assert torch.isfinite(conf).all() and conf.min().item() > 0 and conf.max().item() <= 1.0
     assert idx.float().std().item() > 1.0
-    torch.cuda.empty_cache()
-    b = _run(_model(H, W, ckpt="model_blended_v2.ckpt", recipes=True), s)
-    assert torch.equal(a["index"], b["index"])
-    assert torch.equal(a["photometric_confidence"], b["photometric_confidence"])
 
 
 def test_cfg2_full_resolution_few_planes_against_oracle():
@@ -134,6 +175,6 @@ def test_cfg2_full_resolution_few_planes_against_oracle():
     same = idx == ref["index"]
     mismatch = 1.0 - same.float().mean().item()
     print(f"cfg2 resolution, D=6: plane mismatch fraction {mismatch:.2e} on {same.numel()} pixels")
-    assert mismatch <= 1e-3
+    assert mismatch <= MISMATCH_BAR and (idx - ref["index"]).abs().max().item() <= 1
     assert (out["depth"].cpu()[same] == ref["depth"][same]).all()
     torch.testing.assert_close(out["photometric_confidence"].cpu()[same], ref["photometric_confidence"][same], rtol=1e-3, atol=1e-3)
