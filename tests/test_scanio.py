@@ -25,6 +25,56 @@ def _write_scan(tmp, n_views=4, h=72, w=88):
     return tmp
 
 
+def _golden_scan(tmp, case):
+    """Rebuilds the scan folder of one case of tests/golden/scanio_ref.npz (bytes stored by oracle/make_golden_scanio.py)."""
+    from conftest import GOLD
+    g = np.load(os.path.join(GOLD, "scanio_ref.npz"))
+    prefix = f"{case}/file/"
+    for key in g.files:
+        if key.startswith(prefix):
+            p = tmp / key[len(prefix):]
+            os.makedirs(p.parent, exist_ok=True)
+            p.write_bytes(g[key].tobytes())
+    return g
+
+
+@pytest.mark.parametrize("case,kw", [("a", dict(view_num=3, numdepth=16, interval_scale=0.8, inverse_depth=False, max_h=96, max_w=128)),
+                                     ("b", dict(view_num=3, numdepth=16, interval_scale=1.06, inverse_depth=False, max_h=64, max_w=80)),
+                                     ("c", dict(view_num=5, numdepth=12, interval_scale=1.0, inverse_depth=True, max_h=72, max_w=88))])
+def test_loader_matches_reference_dataset(tmp_path, case, kw):
+    """eval_scan.build_sample (scanio parsers, standardisation, adaptive scale, centre crop, projection matrices, depth
+    hypotheses) against what the UNMODIFIED reference loader MVSDataset.__getitem__ returned for the same scan folder
+    (datasets/data_eval_transform.py:89-174, datasets/preprocess.py:26-63): bit for bit."""
+    import argparse
+    import eval_scan
+    from aarmvsnet_b200 import scanio
+    g = _golden_scan(tmp_path, case)
+    pairs = scanio.read_pair_file(tmp_path / "pair.txt")
+    assert len(pairs) == int(g[f"{case}/len"])
+    args = argparse.Namespace(**kw)
+    for idx in (0, len(pairs) - 1):
+        ref, srcs = pairs[idx]
+        ids, imgs, projs, depth_values = eval_scan.build_sample(str(tmp_path), ref, srcs, args)
+        assert ids[0] == ref and len(ids) == g[f"{case}/{idx}/proj_matrices"].shape[0]
+        np.testing.assert_array_equal(projs, g[f"{case}/{idx}/proj_matrices"])
+        np.testing.assert_array_equal(depth_values, g[f"{case}/{idx}/depth_values"])
+        if f"{case}/{idx}/imgs" in g.files:
+            np.testing.assert_array_equal(imgs, g[f"{case}/{idx}/imgs"])
+
+
+def test_pfm_writer_matches_reference_bytes(tmp_path):
+    """scanio.save_pfm against the bytes the reference's save_pfm wrote (datasets/data_io.py:48-74)."""
+    from conftest import GOLD
+    from aarmvsnet_b200 import scanio
+    g = np.load(os.path.join(GOLD, "scanio_ref.npz"))
+    for key in ("grey", "color"):
+        p = tmp_path / (key + ".pfm")
+        scanio.save_pfm(p, g[f"pfm/{key}/array"])
+        assert p.read_bytes() == g[f"pfm/{key}/bytes"].tobytes()
+        back, scale = scanio.read_pfm(p)
+        assert scale == 1.0 and np.array_equal(back, g[f"pfm/{key}/array"])
+
+
 def test_pair_and_cam_parsers(tmp_path):
     from aarmvsnet_b200 import scanio
     scan = _write_scan(tmp_path)
@@ -105,3 +155,34 @@ def test_eval_scan_driver(tmp_path):
     assert len(os.listdir(out / "scan0" / "depth_est")) == 4 and len(os.listdir(out / "scan1" / "depth_est")) == 3
     depth, _ = scanio.read_pfm(out / "scan0" / "depth_est" / "00000001.pfm")
     assert np.array_equal(depth, outs[0][0])
+
+
+@pytest.mark.gpu
+def test_eval_scan_driver_against_reference_loader_and_oracle(tmp_path):
+    """The whole caller chain against the reference's: eval_scan.py on the scan folder of golden case "b" must write the depth /
+    confidence maps that the oracle forward (pinned to the reference model) produces from the sample the UNMODIFIED reference
+    loader returned for that folder (tests/golden/scanio_ref.npz)."""
+    import subprocess
+    import sys
+    import torch
+    from conftest import ROOT, load_weights
+    from aarmvsnet_b200 import scanio
+    from oracle import aarmvs_oracle as orc
+    g = _golden_scan(tmp_path / "scan_b", "b")
+    out = tmp_path / "out"
+    cmd = [sys.executable, os.path.join(ROOT, "eval_scan.py"), "--scan", str(tmp_path / "scan_b"), "--out", str(out), "--numdepth", "16",
+           "--view_num", "3", "--max_h", "64", "--max_w", "80", "--interval_scale", "1.06", "--cache_features"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    sd = load_weights("model_dtu_v2.ckpt")
+    for idx, ref_view in ((0, 0), (3, 3)):
+        imgs = torch.from_numpy(g["b/0/imgs"])[None] if idx == 0 else None
+        if imgs is None:
+            continue                                      # images are stored for the first sample only
+        ref = orc.forward_test(sd, imgs, torch.from_numpy(g[f"b/{idx}/proj_matrices"])[None],
+                               torch.from_numpy(g[f"b/{idx}/depth_values"])[None])
+        depth, _ = scanio.read_pfm(out / "depth_est" / f"{ref_view:08d}.pfm")
+        conf, _ = scanio.read_pfm(out / "confidence" / f"{ref_view:08d}.pfm")
+        same = torch.from_numpy(depth.copy()) == ref["depth"][0]
+        assert same.float().mean().item() >= 0.999
+        np.testing.assert_allclose(conf[same.numpy()], ref["photometric_confidence"][0].numpy()[same.numpy()], atol=1e-3, rtol=1e-3)
