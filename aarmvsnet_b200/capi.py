@@ -41,9 +41,19 @@ class PlaneSrc(ctypes.Structure):
     ]
 
 
+class Seg(ctypes.Structure):
+    """struct aarmvs_seg (include/aarmvs.h): one channel segment of a concatenated / split NHWC operand."""
+    _fields_ = [
+        ("ptr", ctypes.c_void_p),
+        ("channels", ctypes.c_int),
+        ("accumulate", ctypes.c_int),
+    ]
+
+
 _P, _I, _SZ, _F = ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t, ctypes.c_float
 _SRCP = ctypes.POINTER(ConvSrc)
 _PLSP = ctypes.POINTER(PlaneSrc)
+_SEGP = ctypes.POINTER(Seg)
 
 # name -> (restype, argtypes); must list every symbol include/aarmvs.h declares (tests/test_capi_symbols.py)
 PROTOTYPES = {
@@ -74,6 +84,21 @@ PROTOTYPES = {
     "aarmvs_head_wta_tc": (_I, [_P, _I, _I, _P, c_float_p, _P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "aarmvs_next_plane": (_I, [_P, _P, _I, _P]),
     "aarmvs_loss_grad": (_I, [_P, _P, _P, _F, _I, _SZ, _P, _P]),
+    # backward pass (fp32 NHWC primitives, csrc/backward*.cu)
+    "aarmvs_conv_nhwc": (_I, [_SEGP, _I, _I, _I, _SEGP, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P]),
+    "aarmvs_conv_bwd_weight": (_I, [_SEGP, _I, _I, _I, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P]),
+    "aarmvs_gn_sums": (_I, [_P, _SZ, _I, _I, _P, _P]),
+    "aarmvs_gn_relu_apply": (_I, [_P, _SZ, _I, _I, _P, _P, _P, _I, _P, _P]),
+    "aarmvs_gn_relu_bwd": (_I, [_I, _P, _P, _SZ, _I, _I, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P]),
+    "aarmvs_lstm_gates_bwd": (_I, [_P, _P, _P, _P, _P, _P, _SZ, _I, _P]),
+    "aarmvs_maxpool2": (_I, [_P, _I, _I, _I, _P, _P]),
+    "aarmvs_maxpool2_bwd": (_I, [_P, _P, _I, _I, _I, _P, _P]),
+    "aarmvs_aggregate_bwd": (_I, [_P, _P, _P, _I, _SZ, _P, _P, _P]),
+    "aarmvs_omega_bwd": (_I, [_I, _P, _P, _I, _I, _I, c_float_p, _P, _P, _P, _P, _P]),
+    "aarmvs_warp_bwd": (_I, [_P, _P, _SZ, _I, _I, _I, _P, _F, _I, _P, _P, _P, _P]),
+    "aarmvs_feat_assemble_bwd": (_I, [_P, _I, _I, _P, _P, _P, _P]),
+    "aarmvs_deform_sample": (_I, [_P, _I, _I, _P, _P, _P, _P]),
+    "aarmvs_deform_bwd": (_I, [_P, _I, _I, _P, _P, _P, _P, _P, _P]),
     "aarmvs_tc_mma_bench": (_I, [_I, _I, _I, _I, _I, _P, _P]),
     "aarmvs_tc_selftest": (_I, [_P, _I, _P, _P, _I, _I, _I, _P]),
 }

@@ -1,0 +1,502 @@
+// Backward pass of the path, part 1: the dense primitives (BASELINE config 5; train.py:288-307 `loss.backward()` through
+// models/drmvsnet.py:272-295).  Everything here is fp32 on NHWC tensors, CUDA-core FMA:
+//
+//   conv_nhwc_kernel      direct convolution / transposed convolution over a channel CONCAT of inputs, writing (or adding
+//                         to) a channel SPLIT of outputs.  One kernel covers the gate pre-activations recomputed per plane
+//                         (module.py:80-82), every data gradient dX = dY (*) W^T (stride 1 and 2; the deconvolution's is a
+//                         strided conv, module.py:281), the ConvTranspose forward itself, and the 1x1 layers of FeatNet.
+//   conv_wgrad_kernel     dW[tap][ci][co] += sum_p X[p + tap][ci] * dY[p][co] (+ bias gradient), fp32 atomics at the end.
+//   gn_*                  GroupNorm (+ReLU) materialisation, statistics, and the two-pass backward (global sums, then dX).
+//   lstm_gates_bwd        module.py:83-90 backwards: d gates, d c_{d-1} from d h_d, d c_d.
+//   maxpool2 / _bwd       drmvsnet.py:148,152; the gradient goes to the first maximum of the window in scan order (ATen).
+//
+// The training shape is small (128 x 160 feature maps, B = 4, D = 192: SURVEY.md §8d cfg5), so the backward keeps whole
+// fp32 activations in HBM and is bound by launch count and FMA issue, not by the tensor pipe; the inference path's tcgen05
+// kernels are untouched.
+#include "common.cuh"
+#include "../../include/aarmvs.h"
+
+namespace {
+
+struct Seg {
+    float* ptr;
+    int ch;
+    int acc;
+};
+
+static int convert_segs(const aarmvs_seg* in, int n, Seg* out, int& total) {
+    total = 0;
+    for (int s = 0; s < n; ++s) {
+        if (!in[s].ptr || in[s].channels <= 0) return AARMVS_ERR_ARG;
+        out[s].ptr = in[s].ptr;
+        out[s].ch = in[s].channels;
+        out[s].acc = in[s].accumulate;
+        total += in[s].channels;
+    }
+    return AARMVS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ generic conv
+constexpr int GC_CO = 16, GC_THREADS = 128;
+
+struct GConvArgs {
+    Seg in[3], out[3];
+    int nin, nout;
+    int Hin, Win, Hout, Wout, cin, cout, ks, stride, transposed;
+    const float* w;        // [ks*ks][cin][cout]
+    const float* bias;     // [cout] or null
+};
+
+__global__ void __launch_bounds__(GC_THREADS) conv_nhwc_kernel(const __grid_constant__ GConvArgs a) {
+    extern __shared__ __align__(16) float sw[];          // [ks*ks][cin][GC_CO] of this output-channel tile, zero padded
+    const int tid = threadIdx.x;
+    const int co0 = blockIdx.y * GC_CO;
+    const int rows = a.ks * a.ks * a.cin;
+    for (int i = tid; i < rows * GC_CO; i += GC_THREADS) {
+        const int r = i / GC_CO, k = i - r * GC_CO;
+        sw[i] = co0 + k < a.cout ? __ldg(a.w + (size_t)r * a.cout + co0 + k) : 0.f;
+    }
+    __syncthreads();
+    const int P = a.Hout * a.Wout, pad = (a.ks - 1) / 2;
+    for (int p = blockIdx.x * GC_THREADS + tid; p < P; p += gridDim.x * GC_THREADS) {
+        const int Y = p / a.Wout, X = p - Y * a.Wout;
+        float acc[GC_CO];
+#pragma unroll
+        for (int k = 0; k < GC_CO; ++k) acc[k] = (a.bias && co0 + k < a.cout) ? __ldg(a.bias + co0 + k) : 0.f;
+        for (int ky = 0; ky < a.ks; ++ky) {
+            int y;
+            if (a.transposed) {
+                const int t = Y + pad - ky;
+                if (t < 0 || t % a.stride) continue;
+                y = t / a.stride;
+            } else {
+                y = a.stride * Y - pad + ky;
+            }
+            if (y < 0 || y >= a.Hin) continue;
+            for (int kx = 0; kx < a.ks; ++kx) {
+                int x;
+                if (a.transposed) {
+                    const int t = X + pad - kx;
+                    if (t < 0 || t % a.stride) continue;
+                    x = t / a.stride;
+                } else {
+                    x = a.stride * X - pad + kx;
+                }
+                if (x < 0 || x >= a.Win) continue;
+                const float* wt = sw + (size_t)(ky * a.ks + kx) * a.cin * GC_CO;
+                const size_t pix = (size_t)y * a.Win + x;
+                for (int s = 0; s < a.nin; ++s) {
+                    const int ch = a.in[s].ch;
+                    const float* ip = a.in[s].ptr + pix * ch;
+                    if ((ch & 3) == 0) {
+                        for (int c = 0; c < ch; c += 4) {
+                            const float4 v = ld4(ip + c);
+                            const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const float* wr = wt + (c + e) * GC_CO;
+#pragma unroll
+                                for (int k = 0; k < GC_CO; k += 4) {
+                                    const float4 w4 = ld4(wr + k);
+                                    acc[k] = fmaf(vv[e], w4.x, acc[k]);
+                                    acc[k + 1] = fmaf(vv[e], w4.y, acc[k + 1]);
+                                    acc[k + 2] = fmaf(vv[e], w4.z, acc[k + 2]);
+                                    acc[k + 3] = fmaf(vv[e], w4.w, acc[k + 3]);
+                                }
+                            }
+                        }
+                    } else {
+                        for (int c = 0; c < ch; ++c) {
+                            const float v = ip[c];
+                            const float* wr = wt + c * GC_CO;
+#pragma unroll
+                            for (int k = 0; k < GC_CO; ++k) acc[k] = fmaf(v, wr[k], acc[k]);
+                        }
+                    }
+                    wt += ch * GC_CO;
+                }
+            }
+        }
+        // store: output channel co0 + k lives in the segment that covers it
+        int base = 0;
+        for (int s = 0; s < a.nout; ++s) {
+            const int ch = a.out[s].ch;
+            float* op = a.out[s].ptr + (size_t)p * ch;
+#pragma unroll
+            for (int k = 0; k < GC_CO; ++k) {
+                const int co = co0 + k;
+                if (co >= base && co < base + ch && co < a.cout) {
+                    float* q = op + (co - base);
+                    *q = a.out[s].acc ? *q + acc[k] : acc[k];
+                }
+            }
+            base += ch;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ weight gradient
+constexpr int WG_PX = 32, WG_CI = 16, WG_CO = 64, WG_THREADS = 64;
+
+struct WGArgs {
+    Seg x[3];
+    int nx;
+    const float* dy;       // [Hy][Wy][cy]
+    int Hx, Wx, Hy, Wy, cx, cy, ks, stride, chunk;
+    float* dw;             // [ks*ks][cx][cy], +=
+    float* db;             // [cy], += (or null)
+};
+
+__global__ void __launch_bounds__(WG_THREADS) conv_wgrad_kernel(const __grid_constant__ WGArgs a) {
+    __shared__ __align__(16) float xs[WG_PX][WG_CI];
+    __shared__ __align__(16) float ds[WG_PX][WG_CO];
+    const int tid = threadIdx.x;
+    const int tap = blockIdx.y, ky = tap / a.ks, kx = tap - ky * a.ks, pad = (a.ks - 1) / 2;
+    const int ci0 = blockIdx.z * WG_CI;
+    const int ci4 = tid >> 4, co4 = tid & 15;
+    const int P = a.Hy * a.Wy;
+    const int p_begin = blockIdx.x * a.chunk, p_end = min(P, p_begin + a.chunk);
+    float acc[4][4] = {};
+    float bsum[4] = {0.f, 0.f, 0.f, 0.f};
+    const bool want_bias = a.db && tap == 0 && blockIdx.z == 0 && ci4 == 0;
+    for (int p0 = p_begin; p0 < p_end; p0 += WG_PX) {
+        // stage X[p + tap][ci0 .. ci0 + 16): one item = (pixel, channel)
+        for (int it = tid; it < WG_PX * WG_CI; it += WG_THREADS) {
+            const int px = it / WG_CI, c = ci0 + (it - px * WG_CI);
+            const int p = p0 + px;
+            float v = 0.f;
+            if (p < p_end && c < a.cx) {
+                const int Y = p / a.Wy, X = p - Y * a.Wy;
+                const int y = a.stride * Y - pad + ky, x = a.stride * X - pad + kx;
+                if (y >= 0 && y < a.Hx && x >= 0 && x < a.Wx) {
+                    int base = 0, s = 0;
+                    while (s < a.nx - 1 && c >= base + a.x[s].ch) { base += a.x[s].ch; ++s; }
+                    v = a.x[s].ptr[((size_t)y * a.Wx + x) * a.x[s].ch + (c - base)];
+                }
+            }
+            xs[px][it - px * WG_CI] = v;
+        }
+        for (int it = tid; it < WG_PX * WG_CO; it += WG_THREADS) {
+            const int px = it / WG_CO, c = it - px * WG_CO;
+            const int p = p0 + px;
+            ds[px][c] = (p < p_end && c < a.cy) ? a.dy[(size_t)p * a.cy + c] : 0.f;
+        }
+        __syncthreads();
+        if (co4 * 4 < a.cy) {
+#pragma unroll 4
+            for (int px = 0; px < WG_PX; ++px) {
+                const float4 xv = *reinterpret_cast<const float4*>(&xs[px][ci4 * 4]);
+                const float4 dv = *reinterpret_cast<const float4*>(&ds[px][co4 * 4]);
+                const float xa[4] = {xv.x, xv.y, xv.z, xv.w}, da[4] = {dv.x, dv.y, dv.z, dv.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(xa[i], da[j], acc[i][j]);
+                if (want_bias) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) bsum[j] += da[j];
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (co4 * 4 < a.cy) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int ci = ci0 + ci4 * 4 + i;
+            if (ci >= a.cx) continue;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int co = co4 * 4 + j;
+                if (co < a.cy) atomicAdd(a.dw + ((size_t)tap * a.cx + ci) * a.cy + co, acc[i][j]);
+            }
+        }
+        if (want_bias) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (co4 * 4 + j < a.cy) atomicAdd(a.db + co4 * 4 + j, bsum[j]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ GroupNorm
+// x [P][C]; group g = channels [g * C / groups, (g + 1) * C / groups) over all P pixels; sums = fp64 (sum, sum of squares).
+__global__ void __launch_bounds__(256) gn_sums_kernel(const float* __restrict__ x, size_t n /* P * C */, int C, int groups,
+                                                      double* __restrict__ sums) {
+    __shared__ double sh[8 * 2];       // up to 8 groups
+    if (threadIdx.x < 16) sh[threadIdx.x] = 0.0;
+    __syncthreads();
+    const int gch = C / groups;
+    double s[8] = {}, q[8] = {};
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int g = (int)(i % C) / gch;
+        const double v = (double)x[i];
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            if (k == g) { s[k] += v; q[k] += v * v; }
+    }
+    for (int k = 0; k < groups; ++k) {
+        const double a = warp_sum(s[k]), b = warp_sum(q[k]);
+        if ((threadIdx.x & 31) == 0) { atomicAdd(&sh[k * 2], a); atomicAdd(&sh[k * 2 + 1], b); }
+    }
+    __syncthreads();
+    if (threadIdx.x < groups * 2) atomicAdd(sums + threadIdx.x, sh[threadIdx.x]);
+}
+
+__global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__ x, size_t n, int C, int groups, size_t P,
+                                                       const double* __restrict__ sums, const float* __restrict__ gamma,
+                                                       const float* __restrict__ beta, int relu, float* __restrict__ y) {
+    __shared__ float sc[64], sf[64];
+    if (threadIdx.x < C) {
+        const int gch = C / groups;
+        float mean, rstd;
+        gn_mean_rstd(sums + (threadIdx.x / gch) * 2, (double)gch * (double)P, mean, rstd);
+        sc[threadIdx.x] = rstd * gamma[threadIdx.x];
+        sf[threadIdx.x] = beta[threadIdx.x] - mean * rstd * gamma[threadIdx.x];
+    }
+    __syncthreads();
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C);
+        const float v = fmaf(x[i], sc[c], sf[c]);
+        y[i] = relu ? fmaxf(v, 0.f) : v;
+    }
+}
+
+// Backward of y = [ReLU](gamma * xhat + beta), xhat = (x - mean) * rstd over a group of M = (C / groups) * P elements:
+//   dz = dy * [y > 0];  S1[c] = sum_p dz * xhat,  S2[c] = sum_p dz            (stage 1: chan_sums [C][2], fp64)
+//   A_g = sum_{c in g} gamma_c S1[c],  B_g = sum_{c in g} gamma_c S2[c]
+//   dx = rstd * (gamma_c * dz - (xhat * A_g + B_g) / M);  dgamma += S1, dbeta += S2   (stage 2)
+struct GnBwdArgs {
+    const float* x;
+    const float* dy;
+    size_t P;
+    int C, groups, relu;
+    const double* sums;
+    const float* gamma;
+    const float* beta;
+    double* chan_sums;     // [C][2]
+    float* dx;             // stage 2 (may alias dy)
+    float* dgamma;         // stage 2, +=
+    float* dbeta;
+    float* dx_chan_sum;    // stage 2, optional [C] += sum_p dx (the bias gradient of the producing conv)
+};
+
+template <int STAGE>
+__global__ void __launch_bounds__(256) gn_bwd_kernel(const __grid_constant__ GnBwdArgs a) {
+    __shared__ float s_mean[8], s_rstd[8], s_A[8], s_B[8];
+    __shared__ double s_acc[64 * 2];
+    const int C = a.C, gch = C / a.groups;
+    const double M = (double)gch * (double)a.P;
+    if (threadIdx.x < a.groups) {
+        float mean, rstd;
+        gn_mean_rstd(a.sums + threadIdx.x * 2, M, mean, rstd);
+        s_mean[threadIdx.x] = mean;
+        s_rstd[threadIdx.x] = rstd;
+        if (STAGE == 2) {
+            double A = 0.0, B = 0.0;
+            for (int c = threadIdx.x * gch; c < (threadIdx.x + 1) * gch; ++c) {
+                A += (double)a.gamma[c] * a.chan_sums[c * 2];
+                B += (double)a.gamma[c] * a.chan_sums[c * 2 + 1];
+            }
+            s_A[threadIdx.x] = (float)(A / M);
+            s_B[threadIdx.x] = (float)(B / M);
+        }
+    }
+    if (threadIdx.x < 2 * C) s_acc[threadIdx.x] = 0.0;
+    __syncthreads();
+    const size_t n = a.P * (size_t)C;
+    // grid stride is a multiple of C (launcher), so a thread always meets the same channel
+    const size_t first = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = (int)(first % C), g = c / gch;
+    const float mean = s_mean[g], rstd = s_rstd[g], gam = a.gamma[c], bet = a.beta[c];
+    double t1 = 0.0, t2 = 0.0;
+    float f1 = 0.f, f2 = 0.f;
+    int it = 0;
+    for (size_t i = first; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float xh = (a.x[i] - mean) * rstd;
+        float dz = a.dy[i];
+        if (a.relu && fmaf(gam, xh, bet) <= 0.f) dz = 0.f;
+        if (STAGE == 1) {
+            f1 += dz * xh;
+            f2 += dz;
+        } else {
+            const float dx = rstd * (gam * dz - (xh * s_A[g] + s_B[g]));
+            a.dx[i] = dx;
+            f1 += dx;
+        }
+        if (++it == 16) { t1 += f1; t2 += f2; f1 = f2 = 0.f; it = 0; }
+    }
+    t1 += f1; t2 += f2;
+    if (STAGE == 1) {
+        atomicAdd(&s_acc[c * 2], t1);
+        atomicAdd(&s_acc[c * 2 + 1], t2);
+        __syncthreads();
+        if (threadIdx.x < 2 * C) atomicAdd(a.chan_sums + threadIdx.x, s_acc[threadIdx.x]);
+    } else {
+        if (a.dx_chan_sum) {
+            atomicAdd(&s_acc[c * 2], t1);
+            __syncthreads();
+            if (threadIdx.x < C) atomicAdd(a.dx_chan_sum + threadIdx.x, (float)s_acc[threadIdx.x * 2]);
+        }
+        if (blockIdx.x == 0 && threadIdx.x < C) {
+            a.dgamma[threadIdx.x] += (float)a.chan_sums[threadIdx.x * 2];
+            a.dbeta[threadIdx.x] += (float)a.chan_sums[threadIdx.x * 2 + 1];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ LSTM gates
+// gates [P][4*Ch] = conv output incl. bias, channel blocks i | f | o | g (module.py:83).
+__global__ void __launch_bounds__(256) lstm_gates_bwd_kernel(const float* __restrict__ gates, const float* __restrict__ c_prev,
+                                                             const float* __restrict__ c_new, const float* __restrict__ dh,
+                                                             float* __restrict__ dc, float* __restrict__ dgates, size_t P, int Ch) {
+    const size_t n = P * (size_t)Ch;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t p = i / Ch;
+        const int c = (int)(i - p * Ch);
+        const float* gp = gates + p * 4 * Ch;
+        const float gi = sigmoidf_acc(gp[c]), gf = sigmoidf_acc(gp[Ch + c]), go = sigmoidf_acc(gp[2 * Ch + c]);
+        const float gg = tanhf(gp[3 * Ch + c]);
+        const float cp = c_prev ? c_prev[i] : 0.f;
+        const float th = tanhf(c_new[i]);
+        const float dhv = dh[i];
+        const float dct = dc[i] + dhv * go * (1.f - th * th);
+        float* dg = dgates + p * 4 * Ch;
+        dg[c] = dct * gg * gi * (1.f - gi);
+        dg[Ch + c] = dct * cp * gf * (1.f - gf);
+        dg[2 * Ch + c] = dhv * th * go * (1.f - go);
+        dg[3 * Ch + c] = dct * gi * (1.f - gg * gg);
+        dc[i] = dct * gf;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ max pool 2x2 / 2
+__global__ void __launch_bounds__(256) maxpool2_kernel(const float* __restrict__ x, int H, int W, int C, float* __restrict__ out) {
+    const int Ho = H / 2, Wo = W / 2;
+    const size_t n = (size_t)Ho * Wo * C;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C);
+        const size_t pp = i / C;
+        const int yo = (int)(pp / Wo), xo = (int)(pp - (size_t)yo * Wo);
+        const float* q = x + ((size_t)(2 * yo) * W + 2 * xo) * C + c;
+        out[i] = fmaxf(fmaxf(q[0], q[C]), fmaxf(q[(size_t)W * C], q[(size_t)W * C + C]));
+    }
+}
+
+__global__ void __launch_bounds__(256) maxpool2_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dout, int H, int W,
+                                                           int C, float* __restrict__ dx) {
+    const int Ho = H / 2, Wo = W / 2;
+    const size_t n = (size_t)Ho * Wo * C;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C);
+        const size_t pp = i / C;
+        const int yo = (int)(pp / Wo), xo = (int)(pp - (size_t)yo * Wo);
+        const size_t o00 = ((size_t)(2 * yo) * W + 2 * xo) * C + c;
+        const size_t off[4] = {o00, o00 + C, o00 + (size_t)W * C, o00 + (size_t)W * C + C};
+        int best = 0;
+        float bv = x[off[0]];
+#pragma unroll
+        for (int k = 1; k < 4; ++k) {
+            const float v = x[off[k]];
+            if (v > bv) { bv = v; best = k; }       // strict: the first maximum in scan order keeps the gradient (ATen)
+        }
+        dx[off[best]] += dout[i];
+    }
+}
+
+static int grid_for(size_t n, int threads) {
+    size_t b = (n + threads - 1) / threads;
+    const size_t cap = 148 * 16;
+    return (int)(b < cap ? (b ? b : 1) : cap);
+}
+
+}  // namespace
+
+// ================================================================================================ C ABI
+extern "C" int aarmvs_conv_nhwc(const aarmvs_seg* in, int nin, int Hin, int Win, const aarmvs_seg* out, int nout, int Hout, int Wout,
+                                int cin, int cout, int ksize, int stride, int transposed, const float* weight, const float* bias,
+                                void* stream) {
+    AARMVS_CHECK_ARG(in && out && weight && nin >= 1 && nin <= 3 && nout >= 1 && nout <= 3);
+    AARMVS_CHECK_ARG(Hin > 0 && Win > 0 && Hout > 0 && Wout > 0 && (ksize == 1 || ksize == 3) && (stride == 1 || stride == 2));
+    GConvArgs a = {};
+    int ci = 0, co = 0;
+    if (int e = convert_segs(in, nin, a.in, ci)) return e;
+    if (int e = convert_segs(out, nout, a.out, co)) return e;
+    AARMVS_CHECK_ARG(ci == cin && co == cout);
+    a.nin = nin; a.nout = nout; a.Hin = Hin; a.Win = Win; a.Hout = Hout; a.Wout = Wout; a.cin = cin; a.cout = cout;
+    a.ks = ksize; a.stride = stride; a.transposed = transposed ? 1 : 0; a.w = weight; a.bias = bias;
+    const int smem = ksize * ksize * cin * GC_CO * (int)sizeof(float);
+    AARMVS_CHECK_ARG(smem <= 200 * 1024);
+    static unsigned long long smem_ok = 0;
+    if (smem > 48 * 1024)
+        if (cudaError_t e = ensure_dyn_smem(conv_nhwc_kernel, 200 * 1024, smem_ok)) return (int)e;
+    dim3 grid(grid_for((size_t)Hout * Wout, GC_THREADS), (cout + GC_CO - 1) / GC_CO);
+    conv_nhwc_kernel<<<grid, GC_THREADS, smem, (cudaStream_t)stream>>>(a);
+    AARMVS_LAUNCH_RESULT();
+}
+
+extern "C" int aarmvs_conv_bwd_weight(const aarmvs_seg* x, int nx, int Hx, int Wx, const float* dy, int Hy, int Wy, int cx, int cy,
+                                      int ksize, int stride, float* dweight, float* dbias, void* stream) {
+    AARMVS_CHECK_ARG(x && dy && dweight && nx >= 1 && nx <= 3 && Hx > 0 && Wx > 0 && Hy > 0 && Wy > 0);
+    AARMVS_CHECK_ARG((ksize == 1 || ksize == 3) && (stride == 1 || stride == 2) && cy >= 1 && cy <= WG_CO);
+    WGArgs a = {};
+    int c = 0;
+    if (int e = convert_segs(x, nx, a.x, c)) return e;
+    AARMVS_CHECK_ARG(c == cx);
+    a.nx = nx; a.dy = dy; a.Hx = Hx; a.Wx = Wx; a.Hy = Hy; a.Wy = Wy; a.cx = cx; a.cy = cy; a.ks = ksize; a.stride = stride;
+    a.dw = dweight; a.db = dbias;
+    const int P = Hy * Wy;
+    int chunks = (P + 511) / 512;                                  // >= 512 pixels per block: few atomics per weight
+    const int per_chunk = ksize * ksize * ((cx + WG_CI - 1) / WG_CI);
+    while (chunks > 1 && chunks * per_chunk > 148 * 32) chunks = (chunks + 1) / 2;
+    a.chunk = ((P + chunks - 1) / chunks + WG_PX - 1) / WG_PX * WG_PX;
+    chunks = (P + a.chunk - 1) / a.chunk;
+    dim3 grid(chunks, ksize * ksize, (cx + WG_CI - 1) / WG_CI);
+    conv_wgrad_kernel<<<grid, WG_THREADS, 0, (cudaStream_t)stream>>>(a);
+    AARMVS_LAUNCH_RESULT();
+}
+
+extern "C" int aarmvs_gn_sums(const float* x, size_t P, int C, int groups, double* sums, void* stream) {
+    AARMVS_CHECK_ARG(x && sums && P > 0 && C >= 1 && C <= 64 && groups >= 1 && groups <= 8 && C % groups == 0);
+    gn_sums_kernel<<<grid_for(P * C, 256), 256, 0, (cudaStream_t)stream>>>(x, P * C, C, groups, sums);
+    AARMVS_LAUNCH_RESULT();
+}
+
+extern "C" int aarmvs_gn_relu_apply(const float* x, size_t P, int C, int groups, const double* sums, const float* gamma,
+                                    const float* beta, int relu, float* y, void* stream) {
+    AARMVS_CHECK_ARG(x && y && sums && gamma && beta && P > 0 && C >= 1 && C <= 64 && groups >= 1 && groups <= 8 && C % groups == 0);
+    gn_apply_kernel<<<grid_for(P * C, 256), 256, 0, (cudaStream_t)stream>>>(x, P * C, C, groups, P, sums, gamma, beta, relu, y);
+    AARMVS_LAUNCH_RESULT();
+}
+
+extern "C" int aarmvs_gn_relu_bwd(int stage, const float* x, const float* dy, size_t P, int C, int groups, const double* sums,
+                                  const float* gamma, const float* beta, int relu, double* chan_sums, float* dx, float* dgamma,
+                                  float* dbeta, float* dx_chan_sum, void* stream) {
+    AARMVS_CHECK_ARG(x && dy && sums && gamma && beta && chan_sums && P > 0 && (stage == 1 || stage == 2));
+    AARMVS_CHECK_ARG(C >= 1 && C <= 64 && 256 % C == 0 && groups >= 1 && groups <= 8 && C % groups == 0);
+    AARMVS_CHECK_ARG(stage == 1 || (dx && dgamma && dbeta));
+    GnBwdArgs a = {x, dy, P, C, groups, relu, sums, gamma, beta, chan_sums, dx, dgamma, dbeta, dx_chan_sum};
+    const int grid = grid_for(P * C, 256);          // blockDim (256) is a multiple of C: every thread keeps its channel
+    if (stage == 1) gn_bwd_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(a);
+    else gn_bwd_kernel<2><<<grid, 256, 0, (cudaStream_t)stream>>>(a);
+    AARMVS_LAUNCH_RESULT();
+}
+
+extern "C" int aarmvs_lstm_gates_bwd(const float* gates, const float* c_prev, const float* c_new, const float* dh, float* dc,
+                                     float* dgates, size_t P, int hidden, void* stream) {
+    AARMVS_CHECK_ARG(gates && c_new && dh && dc && dgates && P > 0 && hidden > 0);
+    lstm_gates_bwd_kernel<<<grid_for(P * hidden, 256), 256, 0, (cudaStream_t)stream>>>(gates, c_prev, c_new, dh, dc, dgates, P, hidden);
+    AARMVS_LAUNCH_RESULT();
+}
+
+extern "C" int aarmvs_maxpool2(const float* x, int H, int W, int C, float* out, void* stream) {
+    AARMVS_CHECK_ARG(x && out && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0 && C > 0);
+    maxpool2_kernel<<<grid_for((size_t)(H / 2) * (W / 2) * C, 256), 256, 0, (cudaStream_t)stream>>>(x, H, W, C, out);
+    AARMVS_LAUNCH_RESULT();
+}
+
+extern "C" int aarmvs_maxpool2_bwd(const float* x, const float* dout, int H, int W, int C, float* dx, void* stream) {
+    AARMVS_CHECK_ARG(x && dout && dx && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0 && C > 0);
+    maxpool2_bwd_kernel<<<grid_for((size_t)(H / 2) * (W / 2) * C, 256), 256, 0, (cudaStream_t)stream>>>(x, dout, H, W, C, dx);
+    AARMVS_LAUNCH_RESULT();
+}

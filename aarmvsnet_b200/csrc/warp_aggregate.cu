@@ -8,24 +8,19 @@
 //   pass B  omega_stats_kernel<2>   t0 -> GN1/ReLU -> 1x1 -> GroupNorm-2 sums          (reads t0 only)
 //   pass C  omega_stats_kernel<3>   ... -> GN2/ReLU -> 1x1 -> GroupNorm-3 sums         (reads t0 only)
 //   pass D  aggregate_kernel   re-gather, omega tail from t0 + the three statistics, sum_v (1 + w_v) c_v, * -1/S
-// so the 5-D cost volume and the per-view 32-channel cost never reach HBM.  Layout: features NHWC fp32 (one pixel
-// = 128 B = one cache line per bilinear tap); 8 lanes x float4 cover one pixel, a warp covers 4 pixels per load.
+// The 5-D cost volume [B,32,D,H,W] never exists.  On the tensor-core path (cost_stem_tc.cu + aggregate_stream_kernel below)
+// the per-view 32-channel cost of the K planes of ONE batch does travel through HBM once -- pass A stores it (costv
+// [K][S][P][32], 11.6 GB at cfg2) and pass D streams it back -- because gathering a second time was measured slower
+// (0.56 vs 0.37 ms/plane); the gathering kernels of this file keep it on chip.  Layout: features NHWC fp32
+// (one pixel = 128 B = one cache line per bilinear tap); 8 lanes x float4 cover one pixel, a warp covers 4 pixels per load.
 #include "common.cuh"
 #include "tc_common.cuh"
+#include "omega.cuh"
 #include <string.h>
 
 struct StemParams {            // omega.reweight_network.0.0 repacked [tap][cin][cout] + bias; lives in the
     float w[9 * 32 * 4];       // kernel parameter (constant) bank, so the 1152 FMAs per pixel take their
     float b[4];                // weight operand straight from c[0][...] with no load instruction
-};
-
-struct OmegaTail {             // the 1x1 layers and GroupNorm affines of omega (models/drmvsnet.py:31-34)
-    float g1[4], b1[4];        // reweight_network.0.1   GroupNorm(1, 4)
-    float w1[16], c1[4];       // reweight_network.1.stem.0.0  conv1x1 4->4  (w[o*4+i])
-    float g2[4], b2[4];        // reweight_network.1.stem.0.1
-    float w2[16], c2[4];       // reweight_network.1.stem.1
-    float g3[4], b3[4];        // reweight_network.1.stem.2
-    float w3[4], c3;           // reweight_network.2  conv1x1 4->1
 };
 
 // ------------------------------------------------------------------------------------------------ plain warp
@@ -141,46 +136,7 @@ cost_stem_kernel(const float* __restrict__ ref, const float* __restrict__ src, s
     }
 }
 
-// ------------------------------------------------------------------------------------------------ omega tail
-struct OmegaNorm { float m1, r1, m2, r2, m3, r3; };
-
-// a1 = ReLU(GN1(t0));  u = conv1x1(a1)
-__device__ __forceinline__ void omega_u(const OmegaTail& q, const OmegaNorm& n, float4 t, float (&a1)[4], float (&u)[4]) {
-    const float tv[4] = {t.x, t.y, t.z, t.w};
-#pragma unroll
-    for (int k = 0; k < 4; ++k) a1[k] = fmaxf((tv[k] - n.m1) * n.r1 * q.g1[k] + q.b1[k], 0.f);
-#pragma unroll
-    for (int o = 0; o < 4; ++o) {
-        float s = q.c1[o];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) s = fmaf(q.w1[o * 4 + i], a1[i], s);
-        u[o] = s;
-    }
-}
-// a2 = ReLU(GN2(u));  v = conv1x1(a2)
-__device__ __forceinline__ void omega_v(const OmegaTail& q, const OmegaNorm& n, const float (&u)[4], float (&vv)[4]) {
-    float a2[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) a2[k] = fmaxf((u[k] - n.m2) * n.r2 * q.g2[k] + q.b2[k], 0.f);
-#pragma unroll
-    for (int o = 0; o < 4; ++o) {
-        float s = q.c2[o];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) s = fmaf(q.w2[o * 4 + i], a2[i], s);
-        vv[o] = s;
-    }
-}
-// w = sigmoid(conv1x1(ReLU(GN3(v) + a1)))
-__device__ __forceinline__ float omega_w(const OmegaTail& q, const OmegaNorm& n, const float (&a1)[4], const float (&vv)[4]) {
-    float s = q.c3;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        float r = fmaxf(((vv[k] - n.m3) * n.r3 * q.g3[k] + q.b3[k]) + a1[k], 0.f);
-        s = fmaf(q.w3[k], r, s);
-    }
-    return sigmoidf_acc(s);
-}
-
+// ------------------------------------------------------------------------------------------------ omega tail (omega.cuh)
 // STAGE 2: accumulate sums of u (GroupNorm-2);  STAGE 3: sums of v (GroupNorm-3).  grid = (blocks, S).
 template <int STAGE>
 __global__ void __launch_bounds__(256) omega_stats_kernel(const float* __restrict__ t0, size_t P, const __grid_constant__ OmegaTail q,

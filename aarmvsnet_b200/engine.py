@@ -135,8 +135,8 @@ class Engine:
         return w
 
     # ------------------------------------------------------------------------------------------ workspace
-    def _workspace(self, H, W, N, D, device, keep_cost, with_loss=False):
-        key = (H, W, N, D, str(device), keep_cost, with_loss)
+    def _workspace(self, H, W, N, D, device, keep_cost, with_loss=False, with_state=False):
+        key = (H, W, N, D, str(device), keep_cost, with_loss, with_state)
         ws = self._ws.get(key)
         if ws is not None:
             self._ws.move_to_end(key)
@@ -169,7 +169,9 @@ class Engine:
             ws["up0p"] = torch.empty(2, 2, P // 4, 8, **f16)
             ws["up1p"] = torch.empty(2, 2, P, 8, **f16)
             ws["c"] = [torch.empty(self.lib.aarmvs_cell_state_floats(H // s, W // s, ch), **f32) for ch, s in zip(_HID, _SCALE)]
-            ws["h"] = [None] * 5              # no fp32 copies of h: deconvolutions and the head read the planes too
+            # no fp32 copies of h on the inference path (deconvolutions and the head read the planes too); the training forward
+            # asks the cells for them (h_f32_pair) because the backward pass snapshots the recurrent state of every plane
+            ws["h"] = ([torch.empty(2, P // (s * s), ch, **f32) for ch, s in zip(_HID, _SCALE)] if with_state else [None] * 5)
         else:
             ws["h"] = [torch.empty(2, P // (s * s), ch, **f32) for ch, s in zip(_HID, _SCALE)]
             ws["c"] = [torch.empty(P // (s * s), ch, **f32) for ch, s in zip(_HID, _SCALE)]
@@ -283,10 +285,12 @@ class Engine:
         capi.check(self.lib.aarmvs_split_planes(ctypes.byref(src), H, W, _ptr(planes), stream), "aarmvs_split_planes")
 
     # ------------------------------------------------------------------------------------------ one plane
-    def _batch(self, ws, w, stream, nplanes, marks=None):
+    def _batch(self, ws, w, stream, nplanes, marks=None, after_plane=None):
         """Enqueue the kernel chain of `nplanes` consecutive depth planes starting at the plane index held in
         ws['plane'] (device memory): passes A-D once for the whole batch, then the recurrence plane by plane.
-        marks: optional list collecting (stage name, CUDA event) after each stage (bench.py's per-kernel timing)."""
+        marks: optional list collecting (stage name, CUDA event) after each stage (bench.py's per-kernel timing).
+        after_plane: optional callable(k) run after the launches of the batch's k-th plane (eager mode only: the training
+        forward snapshots the recurrent state there)."""
         lib, H, W, N = self.lib, ws["H"], ws["W"], ws["N"]
 
         def mark(name):
@@ -398,6 +402,8 @@ class Engine:
             else:
                 capi.check(lib.aarmvs_next_plane(dptr, _ptr(s_up0), 8, stream), "aarmvs_next_plane")
             mark("head_wta")
+            if after_plane is not None:
+                after_plane(k)
 
     # ------------------------------------------------------------------------------------------ one depth map
     @staticmethod
@@ -422,6 +428,48 @@ class Engine:
             stream = ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
             self.feature_map(img.to(torch.float32).contiguous(), out, fs, w, stream)
             return out
+
+    def forward_saving_state(self, imgs, proj_matrices, depth_values):
+        """The training-phase forward of ONE sample (models/drmvsnet.py:272-287) on the tensor-core kernels, launched eagerly,
+        keeping what the backward pass needs: the features of the N views, the regularised cost of every plane and a snapshot
+        of the recurrent state (h, c of the five cells) after every plane -- 66 floats per full-resolution pixel and plane;
+        everything else is recomputed per plane by the backward (aarmvsnet_b200/backward.py).
+        Returns {"cost": [D,P], "feat": [N,P,32], "h": 5 x [D,P_i,Ch_i], "c": 5 x [D, blocked floats], ...}."""
+        device = imgs.device
+        if device.type != "cuda":
+            raise RuntimeError("aarmvsnet_b200 has no CPU path: inputs must live on a CUDA device")
+        if self.cell_math != "tc":
+            raise RuntimeError("the training forward runs on the tensor-core kernels (cell_math='tc')")
+        with torch.cuda.device(device):
+            N, _, H, W = imgs.shape
+            D = depth_values.shape[0]
+            w = self._weights(device)
+            ws = self._workspace(H, W, N, D, device, True, False, True)
+            stream = ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+            imgs = imgs.to(torch.float32).contiguous()
+            for v in range(N):
+                self.feature_map(imgs[v], ws["feat"][v], ws, w, stream)
+            cams = self.relative_cameras(proj_matrices)
+            ws["cams"].copy_(cams, non_blocking=True)
+            ws["depths"].copy_(depth_values.to(torch.float32), non_blocking=True)
+            ws["plane"].zero_()
+            ws["psums"].zero_()
+            f32 = dict(device=device, dtype=torch.float32)
+            saved = {"H": H, "W": W, "N": N, "D": D, "imgs": imgs, "cams": ws["cams"].clone(),
+                     "depths_host": [float(x) for x in depth_values.detach().cpu().tolist()],
+                     "h": [torch.empty((D,) + tuple(t.shape[1:]), **f32) for t in ws["h"]],
+                     "c": [torch.empty(D, t.numel(), **f32) for t in ws["c"]]}
+            K = ws["K"]
+            for d0 in range(0, D, K):
+                def snapshot(k, d0=d0):
+                    d = d0 + k
+                    for i in range(5):
+                        saved["h"][i][d].copy_(ws["h"][i][d & 1])
+                        saved["c"][i][d].copy_(ws["c"][i])
+                self._batch(ws, w, stream, min(K, D - d0), after_plane=snapshot)
+            saved["feat"] = ws["feat"].clone()
+            saved["cost"] = ws["cost_volume"].clone()
+            return saved
 
     @staticmethod
     def nearest_hypothesis(depth_values, depth_gt, mask):

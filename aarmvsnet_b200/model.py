@@ -100,6 +100,34 @@ class UNetConvLSTM(nn.Module):
         self.conv_0 = nn.Conv2d(8, 1, 3, 1, padding=1)
 
 
+class _RegularisedCostVolume(torch.autograd.Function):
+    """The differentiable training-phase forward (models/drmvsnet.py:272-289): imgs, cameras, depth hypotheses and the 90
+    parameters -> regularised cost volume [B,D,H,W] (the softmax over D stays a torch op on top).  forward = the tensor-core
+    engine with per-plane state snapshots; backward = aarmvsnet_b200/backward.py (reverse sweep over the planes with per-plane
+    recompute).  Gradients go to the parameters only: the reference builds the sampling grid under no_grad (module.py:15-34)
+    and images carry no gradient in training."""
+
+    @staticmethod
+    def forward(ctx, model, imgs, proj_matrices, depth_values, *params):
+        eng = model._engine
+        B, _, _, H, W = imgs.shape
+        saved = [eng.forward_saving_state(imgs[b], proj_matrices[b], depth_values[b]) for b in range(B)]
+        ctx.model, ctx.saved = model, saved
+        return torch.stack([s["cost"].view(-1, H, W) for s in saved])
+
+    @staticmethod
+    def backward(ctx, dcost):
+        from .backward import Backward
+        model, saved = ctx.model, ctx.saved
+        bwd = Backward(model._engine, dcost.device)
+        with torch.cuda.device(dcost.device):
+            for b, s in enumerate(saved):
+                bwd.sample(s, dcost[b].reshape(s["D"], -1).to(torch.float32))
+        grads = bwd.parameter_gradients()
+        ctx.saved = None
+        return (None, None, None, None) + tuple(grads[name].to(p.dtype) for name, p in model.named_parameters())
+
+
 class EMVSNet(nn.Module):
     """Same constructor as models/drmvsnet.py:235.  `disparity_level` only parameterised the evidential head and is
     accepted and ignored; `max_h * image_scale` x `max_w * image_scale` must equal the tensor size in the reference
@@ -133,6 +161,10 @@ class EMVSNet(nn.Module):
             raise RuntimeError(f"depth_values must be [B,D], got {tuple(depth_values.shape)}")
         if self.strict_size and (H, W) != self.input_size:
             raise RuntimeError(f"input {H}x{W} does not match max_h*image_scale x max_w*image_scale = {self.input_size}")
+        if not self.return_depth and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            # training phase with autograd (train.py:297-306): loss.backward() reaches every parameter
+            cost = _RegularisedCostVolume.apply(self, imgs, proj_matrices, depth_values, *self.parameters())
+            return torch.softmax(cost, dim=1), None, None
         keep_cost = not self.return_depth
         outs = []
         with torch.no_grad():

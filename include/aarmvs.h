@@ -264,6 +264,89 @@ int aarmvs_tc_selftest(const void* a_f16, int a_rows, const void* b_f16, float* 
  * with 8-row groups `group_rows` rows apart, start row advancing by a_shift_rows per instruction) on `grid` CTAs. */
 int aarmvs_tc_mma_bench(int N, int group_rows, int reps, int a_shift_rows, int grid, long long* out, void* stream);
 
+/* ---- backward pass (BASELINE config 5: train.py:288-307 loss.backward() through models/drmvsnet.py:272-295) ---------
+ * fp32 NHWC primitives; the host side (aarmvsnet_b200/backward.py) walks the depth planes in reverse, recomputes each
+ * plane's intermediates from the stored recurrent state and chains these calls.  Gradient buffers marked "+=" are
+ * accumulated into (zero them first); nothing here allocates. */
+
+/* One channel segment of a concatenated (inputs) or split (outputs) NHWC operand: [H][W][channels] fp32. */
+typedef struct aarmvs_seg {
+    float* ptr;
+    int channels;
+    int accumulate;            /* outputs only: 0 = store, 1 = add to what is there */
+} aarmvs_seg;
+
+/* Direct convolution over the channel concat of `in` (replaces torch.cat, module.py:80), written to / added into the channel
+ * split `out`:
+ *   transposed == 0:  out(Y,X)[co] = bias[co] + sum in(stride*Y - pad + ky, stride*X - pad + kx)[ci] * weight[ky*k+kx][ci][co]
+ *   transposed == 1:  out(Y,X)[co] = bias[co] + sum in((Y + pad - ky) / stride, (X + pad - kx) / stride)[ci] * weight[..][ci][co]
+ *                     over the taps where the divisions are exact;  pad = (k - 1) / 2, zero outside the input.
+ * Used for: gate pre-activations recomputed per plane (module.py:82), dX of every Conv2d (transposed, weight =
+ * W[co][ci][ky][kx] read as [tap][co][ci]), ConvTranspose2d forward (module.py:281: transposed, stride 2) and its dX
+ * (plain, stride 2), the 1x1 layers.  weight: [k*k][cin][cout]; bias: [cout] or NULL; k in {1, 3}; stride in {1, 2}. */
+int aarmvs_conv_nhwc(const aarmvs_seg* in, int nin, int Hin, int Win, const aarmvs_seg* out, int nout, int Hout, int Wout,
+                     int cin, int cout, int ksize, int stride, int transposed, const float* weight, const float* bias,
+                     void* stream);
+
+/* dweight[ky*k+kx][ci][co] += sum_{Y,X} x(stride*Y - pad + ky, stride*X - pad + kx)[ci] * dy(Y,X)[co];  dbias[co] += sum dy.
+ * x: channel concat [Hx][Wx][cx]; dy: [Hy][Wy][cy], cy <= 64.  For a Conv2d x is its input and dy its output gradient; for
+ * the ConvTranspose2d x is the OUTPUT gradient and dy the input (the result is then indexed [tap][co][ci]). */
+int aarmvs_conv_bwd_weight(const aarmvs_seg* x, int nx, int Hx, int Wx, const float* dy, int Hy, int Wy, int cx, int cy,
+                           int ksize, int stride, float* dweight, float* dbias, void* stream);
+
+/* GroupNorm of x [P][C] (groups of C / groups channels over all P pixels; module.py:101,284): sums [groups][2] += (sum, sum
+ * of squares);  y = [ReLU](gamma * (x - mean) * rstd + beta). */
+int aarmvs_gn_sums(const float* x, size_t P, int C, int groups, double* sums, void* stream);
+int aarmvs_gn_relu_apply(const float* x, size_t P, int C, int groups, const double* sums, const float* gamma, const float* beta,
+                         int relu, float* y, void* stream);
+/* Backward of the same: stage 1 accumulates chan_sums [C][2] (zero before) = (sum_p dz * xhat, sum_p dz), dz = dy * [y > 0];
+ * stage 2 writes dx (may alias dy), adds the affine gradients to dgamma / dbeta and, if dx_chan_sum != NULL, sum_p dx to it
+ * (the bias gradient of the convolution that produced x).  C divides 256. */
+int aarmvs_gn_relu_bwd(int stage, const float* x, const float* dy, size_t P, int C, int groups, const double* sums,
+                       const float* gamma, const float* beta, int relu, double* chan_sums, float* dx, float* dgamma,
+                       float* dbeta, float* dx_chan_sum, void* stream);
+
+/* ConvLSTMCell backward, point-wise part (module.py:83-90).  gates [P][4*hidden]: the conv output incl. bias, channel blocks
+ * i | f | o | g; c_prev (NULL at plane 0) / c_new [P][hidden]; dh = dL/dh_d; dc: in dL/dc_d (from plane d+1), out dL/dc_{d-1};
+ * dgates [P][4*hidden] = dL/d(conv output). */
+int aarmvs_lstm_gates_bwd(const float* gates, const float* c_prev, const float* c_new, const float* dh, float* dc, float* dgates,
+                          size_t P, int hidden, void* stream);
+
+/* MaxPool2d(2, 2) (drmvsnet.py:148,152) and its backward (dx += dout at the first maximum of each window). */
+int aarmvs_maxpool2(const float* x, int H, int W, int C, float* out, void* stream);
+int aarmvs_maxpool2_bwd(const float* x, const float* dout, int H, int W, int C, float* dx, void* stream);
+
+/* Aggregation backward (drmvsnet.py:311-319): cost = -(1/S) sum_v (1 + omega_v) c_v  ->
+ *   dcostv[v][p][:] = -(1 + reweight[v][p]) / S * dcost[p][:],   dreweight[v][p] = -(1/S) sum_ch costv[v][p][ch] * dcost[p][ch]. */
+int aarmvs_aggregate_bwd(const float* dcost, const float* costv, const float* reweight, int S, size_t P, float* dcostv,
+                         float* dreweight, void* stream);
+
+/* Backward of omega's point-wise tail (drmvsnet.py:31-34 after the stem conv), four passes because each of its three
+ * GroupNorms needs two sums over the whole map: stage 3, 2, 1 accumulate bstats[v][stage-1][2] (zero before stage 3) and the
+ * parameter gradients dtail[aarmvs_omega_tail_floats()] (fp64, +=, OmegaTail order); stage 0 writes dt0 [S][P][4] = dL/d(stem
+ * conv output).  t0, stats, tail_host as in aarmvs_omega_stats (one plane); dreweight from aarmvs_aggregate_bwd. */
+int aarmvs_omega_bwd(int stage, const float* t0, const float* dreweight, int H, int W, int S, const float* tail_host,
+                     const double* stats, double* bstats, double* dtail, float* dt0, void* stream);
+
+/* Warp backward (module.py:6-38; the grid is built under no_grad, so only the features receive gradients): with
+ * c_v = (warp_v - ref)^2:  g = 2 (warp_v - ref) * dcostv[v];  dref[p] -= sum_v g;  dsrc[v][tap] += w_tap * g for the four
+ * bilinear taps (red.global.add.v4.f32).  cams: device [S][12]; dsrc: S maps `view_stride` floats apart. */
+int aarmvs_warp_bwd(const float* ref, const float* src, size_t view_stride, int H, int W, int S, const float* cams, float depth,
+                    int align_corners, const float* dcostv, float* dref, float* dsrc, void* stream);
+
+/* IntraViewAAModule tail backward (drmvsnet.py:19-24): dfeature [H][W][32] -> gradients w.r.t. the GroupNorm+ReLU'd 1x1
+ * outputs: dm0 [H][W][16] (stored), dm1 [H/2][W/2][8] and dm2 [H/4][W/4][8] (+=, atomics: zero before). */
+int aarmvs_feat_assemble_bwd(const float* dfeature, int H, int W, float* dm0, float* dm1, float* dm2, void* stream);
+
+/* DeformConv2d backward (module.py:133-189), with the 9x32 -> 32 contraction done by aarmvs_conv_nhwc / _bwd_weight (k = 1):
+ * aarmvs_deform_sample: x [H][W][32] (already GroupNorm+ReLU'd), offmask as in aarmvs_deform_conv ->
+ *     samp [P][9][32] (bilinear samples before the modulation) and samp_m = samp * sigmoid(m)  (the contraction's input);
+ * aarmvs_deform_bwd: dsamp_m [P][9][32] -> dx [H][W][32] (+=, atomics) and doffmask [P][32] (row / column offsets through the
+ *     bilinear weights -- floor() is detached, module.py:150 -- and modulation logits; channels 27-31 = 0). */
+int aarmvs_deform_sample(const float* x, int H, int W, const float* offmask, float* samp, float* samp_m, void* stream);
+int aarmvs_deform_bwd(const float* x, int H, int W, const float* offmask, const float* samp, const float* dsamp_m, float* dx,
+                      float* doffmask, void* stream);
+
 /* ---- debug hooks: only in libraries built with -DAARMVS_DEBUG (AARMVS_NVCC_EXTRA=-DAARMVS_DEBUG python -m
  * aarmvsnet_b200.build --force); the product library has no process-global state and does not export them. */
 #ifdef AARMVS_DEBUG
