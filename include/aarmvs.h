@@ -347,6 +347,11 @@ int aarmvs_deform_sample(const float* x, int H, int W, const float* offmask, flo
 int aarmvs_deform_bwd(const float* x, int H, int W, const float* offmask, const float* samp, const float* dsamp_m, float* dx,
                       float* doffmask, void* stream);
 
+/* Adam step (train.py:180,307; torch.optim.Adam semantics, no amsgrad) over one flat fp32 buffer holding every parameter:
+ * param, grad, exp_avg, exp_avg_sq [n]; step = 1 for the first update. */
+int aarmvs_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t n, float lr, float beta1,
+                     float beta2, float eps, float weight_decay, int step, void* stream);
+
 /* ---- debug hooks: only in libraries built with -DAARMVS_DEBUG (AARMVS_NVCC_EXTRA=-DAARMVS_DEBUG python -m
  * aarmvsnet_b200.build --force); the product library has no process-global state and does not export them. */
 #ifdef AARMVS_DEBUG
