@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """bench.py -- depth maps/s and ms per depth plane of the AA-RMVSNet cost-volume pipeline on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg4|cfg1|tiny]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg4|cfg1|tiny|cfg3|cfg5]
+    (cfg3 = one 49-view scan partitioned over the ranks, strong scaling; cfg5 = the training step, forward + backward + Adam)
 
 One "step" = one whole depth map of the workload BASELINE.json quotes the metric on (cfg2: 1600x1184, N=7 views,
 D=512 planes, model_dtu_v2.ckpt, synthetic images/cameras): FeatNet on the 7 views + 512 depth planes.
@@ -392,16 +393,314 @@ def run_ours(args):
     return line
 
 
+# ------------------------------------------------------------------------------------------------- cfg5: training step
+TRAIN = {"H": 128, "W": 160, "N": 3, "D": 192, "B": 4, "ckpt": "model_dtu_v2.ckpt"}       # BASELINE config 5
+
+
+def train_config():
+    c = TRAIN
+    return {"workload": f"cfg5: AA-RMVSNet training step (train.py:288-307: forward + mvsnet_cls_loss + backward + Adam), network tensors "
+                        f"{c['W']}x{c['H']} (640x512 images at image_scale 0.25), N={c['N']} views, D={c['D']} inverse depth planes, batch "
+                        f"{c['B']} per GPU, {c['ckpt']}, synthetic N(0,1) images + ring cameras + random ground truth",
+            "height": c["H"], "width": c["W"], "views": c["N"], "planes": c["D"], "batch": c["B"], "checkpoint": c["ckpt"],
+            "l2": "saved recurrent state 4 x 1.0 GB + per-plane recompute buffers exceed the 126 MB L2"}
+
+
+def train_batch(seed, batch):
+    from aarmvsnet_b200 import synth
+    c = TRAIN
+    s = synth.make_sample(c["H"], c["W"], c["N"], c["D"], seed=seed, batch=batch, depth_mode="inverse")
+    g = torch.Generator().manual_seed(seed + 1)
+    s["depth_gt"] = 425.0 + 510.0 * torch.rand(batch, c["H"], c["W"], generator=g)
+    s["mask"] = (torch.rand(batch, c["H"], c["W"], generator=g) > 0.2).float()
+    return s
+
+
+def cpu_train_sample(threads=None):
+    """The reference's training step on the host cores, bounded sample: forward + mvsnet_cls_loss + backward of the UNMODIFIED
+    reference (oracle/_ref; the oracle port if absent) at the cfg5 tensor size with B = 1 and D = 2 / D = 6 planes; the
+    difference gives the per-plane cost, extrapolated to B x D.  -> (seconds per step, cores, kind, how)."""
+    import contextlib
+    from oracle import aarmvs_oracle as orc, ref_runner
+    c = TRAIN
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    sd = load_sd(c["ckpt"])
+    s = train_batch(0, 1)
+    runs = []
+    with contextlib.redirect_stdout(sys.stderr):
+        if ref_runner.available():
+            m = ref_runner.load_reference(sd, c["H"], c["W"], return_depth=False)
+            m.train()
+            from models.drmvsnet import mvsnet_cls_loss as ref_loss
+            kind = "reference"
+        else:
+            kind = "port"
+        for it, nd in enumerate((2, 2, 6)):            # the first run warms the allocator / thread pool up and is dropped
+            t0 = time.perf_counter()
+            dv = s["depth_values"][:, :nd]
+            if kind == "reference":
+                m.zero_grad()
+                prob, _, _ = m(s["imgs"], s["proj_matrices"], dv)
+                loss, _ = ref_loss(prob, s["depth_gt"], s["mask"], dv)
+            else:
+                sdg = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+                loss, _ = orc.cls_loss(orc.forward_train(sdg, s["imgs"], s["proj_matrices"], dv), s["depth_gt"], s["mask"], dv)
+            loss.backward()
+            if it:
+                runs.append(time.perf_counter() - t0)
+    t_plane = max(runs[1] - runs[0], 0.0) / 4
+    t_fixed = max(runs[0] - 2 * t_plane, 0.0)
+    total = c["B"] * (t_fixed + c["D"] * t_plane)
+    how = (f"{'unmodified reference (oracle/_ref)' if kind == 'reference' else 'oracle port'} forward + mvsnet_cls_loss + backward, PyTorch "
+           f"{torch.__version__} CPU fp32, {threads} threads, {c['W']}x{c['H']} N={c['N']} B=1: D=2 {runs[0]:.2f} s, D=6 {runs[1]:.2f} s -> "
+           f"{t_plane:.3f} s/plane + {t_fixed:.2f} s fixed, extrapolated to B={c['B']} x D={c['D']} (optimizer step not included)")
+    return total, threads, kind, how
+
+
+def run_train(args):
+    """--workload cfg5: one step = one optimisation step on a batch of B samples (forward with state snapshots, loss, reverse
+    plane sweep, FeatNet backward, flat Adam).  value = training samples/s; e2e = the same with the batch copied from pinned
+    host memory and the loss read back every step."""
+    import torch.distributed as dist
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    c = TRAIN
+    if args.impl == "reference":
+        if rank == 0:
+            total, cores, kind, how = cpu_train_sample()
+            val = c["B"] / total
+            print(json.dumps({"impl": "reference", "metric": "training samples/sec (forward+backward)", "value": val, "unit": "samples/s",
+                              "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total * 1e3,
+                              "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                              "config": train_config(),
+                              "cpu_baseline": {"value": val, "unit": "samples/s", "cores": cores, "kind": kind, "sample": how},
+                              "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+    import aarmvsnet_b200 as aa
+    from aarmvsnet_b200.training import TrainStep
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    model = aa.EMVSNet(disparity_level=32, image_scale=1.0, max_h=c["H"], max_w=c["W"], return_depth=False)
+    model.load_state_dict(load_sd(c["ckpt"]), strict=True)
+    model = model.to(dev).train()
+    step = TrainStep(model, lr=1e-4)
+    keys = ("imgs", "proj_matrices", "depth_values", "depth_gt", "mask")
+    batches = [train_batch(100 * rank + i, c["B"]) for i in range(2)]
+    host = [{k: b[k].pin_memory() for k in keys} for b in batches]
+    resident = [{k: (v if k == "proj_matrices" else v.to(dev)) for k, v in h.items()} for h in host]
+    h2d = sum(host[0][k].numel() * 4 for k in keys if k != "proj_matrices")
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn):
+        for i in range(args.warmup):
+            fn(i)
+        barrier()
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(args.steps):
+            fn(args.warmup + i)
+        e1.record()
+        barrier()
+        clocks = sampler.stop() if rank == 0 else None
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item(), clocks
+
+    losses = []
+
+    def step_resident(i):
+        r = resident[i % 2]
+        losses.append(step(*[r[k] for k in keys])[0])
+
+    loss_host = torch.empty(1).pin_memory()
+
+    def step_e2e(i):
+        h = host[i % 2]
+        args_ = [h[k] if k == "proj_matrices" else h[k].to(dev, non_blocking=True) for k in keys]
+        loss_host.copy_(step(*args_)[0].reshape(1), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    ms_total, clocks = timed(step_resident)
+    ms_e2e, _ = timed(step_e2e)
+    if world > 1:            # data-parallel replicas: the gradient all-reduce of train.py's (unused) DataParallel is not on this path
+        dist.barrier()
+    if rank == 0:
+        pk = peaks()
+        # phase split of one more step, CUDA events (eager launches; the host enqueues ahead only where it can)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        r = resident[0]
+        step.opt.zero_grad()
+        ev[0].record()
+        prob, _, _ = model(r["imgs"], r["proj_matrices"], r["depth_values"])
+        loss, _ = aa.mvsnet_cls_loss(prob, r["depth_gt"], r["mask"], r["depth_values"])
+        ev[1].record()
+        loss.backward()
+        ev[2].record()
+        step.opt.step()
+        ev[3].record()
+        torch.cuda.synchronize()
+        phases = {"forward_and_loss_ms": ev[0].elapsed_time(ev[1]), "backward_ms": ev[1].elapsed_time(ev[2]),
+                  "adam_ms": ev[2].elapsed_time(ev[3])}
+        P = c["H"] * c["W"]
+        # useful FLOPs of the recurrence: forward 105 264 / px / plane, backward 2x (dX and dW); the backward's recompute of the
+        # gate pre-activations (another 1x) is not counted
+        flops = 3 * FLOP_PER_PX_PLANE * P * c["D"] * c["B"]
+        ms_step = ms_total / args.steps
+        ach = flops / (ms_step * 1e-3) / 1e12
+        cpu = None
+        if not args.no_cpu_baseline and world == 1:
+            total, cores, kind, how = cpu_train_sample()
+            cpu = {"value": c["B"] / total, "unit": "samples/s", "cores": cores, "kind": kind, "sample": how}
+        launches_fwd = c["B"] * (c["N"] * 16 + -(-c["D"] // 8) * 4 + c["D"] * 11)
+        launches_bwd = c["B"] * (c["D"] * (4 + 2 + 6 + 5 + 2 + 15 + 10 + 2 + 1 + 4 + 2 * (c["N"] - 1) + 1) + c["N"] * (16 + 75))
+        line = {"metric": "training samples/sec (forward+backward+Adam)", "value": world * c["B"] * args.steps / (ms_total * 1e-3),
+                "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+                "ms_per_plane": ms_step / (c["B"] * c["D"]), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic", "config": train_config(), "clocks": clocks,
+                "e2e": {"value": world * c["B"] * args.steps / (ms_e2e * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": h2d,
+                        "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
+                "gpu_launches": args.steps * (launches_fwd + launches_bwd + 1),
+                "roofline": {"kernel": "whole step (the backward's kernels are fp32 CUDA-core FMA, ~50 launches per plane and sample)",
+                             "bound": "tensor", "achieved": ach, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                             "frac": ach / pk["bf16_tflops_sustained"], "traffic": None,
+                             "algorithmic_flops_per_step": flops,
+                             "note": "useful recurrence FLOPs (forward 1x + backward 2x) over the step time; the step is bound by launch "
+                                     "count and host enqueue (eager, per-plane recompute), not by the tensor pipe or HBM"},
+                "phases_ms": phases, "loss_first_last": [float(losses[0]), float(losses[-1])], "cpu_baseline": cpu}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------- cfg3: one scan, partitioned
+def run_scan(args):
+    """--workload cfg3: ONE synthetic 49-view scan (1600x1184, N=7, D=512) partitioned by reference view over the ranks
+    (scan.shard_views, contiguous slices; eval.py:105-113 walks the same units one by one).  A step = the whole scan: every
+    rank runs FeatNet once per image it needs (per-scan feature cache, as eval_scan.py --cache_features) and the plane sweep
+    of its reference views; makespan = the slowest rank.  Strong scaling: value = 49 depth maps / makespan, next to the
+    ceiling 49 / ceil(49 / G)."""
+    import torch.distributed as dist
+    import aarmvsnet_b200 as aa
+    from aarmvsnet_b200 import scan as scan_mod
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    H, W, N, D, ckpt, mode = WORKLOADS["cfg2"]
+    V = args.scan_views
+    model = aa.EMVSNet(disparity_level=32, image_scale=1.0, max_h=H, max_w=W, return_depth=True)
+    model.load_state_dict(load_sd(ckpt), strict=True)
+    model = model.to(dev).eval()
+    eng = model._engine
+    # the scan: V images (generated on the device, seeded per view id) and a ring of cameras; view i pairs with its 6 neighbours
+    cams = aa.synth.make_sample(8, 8, V, 2, seed=7)["proj_matrices"][0].clone()        # [V,4,4] extrinsics pattern, re-intrinsic'd below
+    ring = aa.synth.make_sample(H, W, N, D, seed=7, depth_mode=mode)
+    depth_values = ring["depth_values"][0].to(dev)
+
+    def image(v):
+        g = torch.Generator(device=dev).manual_seed(1000 + v)
+        return torch.randn(3, H, W, device=dev, generator=g)
+
+    def neighbours(i):
+        order = sorted((u for u in range(V) if u != i), key=lambda u: (abs(u - i), u))
+        return order[: N - 1]
+
+    mine = list(scan_mod.shard_views(V, world, rank))
+    maps = torch.empty(len(mine), 2, H, W, device=dev)
+
+    def run_share(cache_features):
+        cache = {}
+        for j, i in enumerate(mine):
+            ids = [i] + neighbours(i)
+            feats = None
+            if cache_features:
+                for v in ids:
+                    if v not in cache:
+                        cache[v] = eng.features(image(v))
+                    if len(cache) > 2 * N + 2:                           # bounded: neighbours are local in a contiguous slice
+                        cache.pop(min(cache))
+                feats = [cache[v] for v in ids]
+                imgs = torch.empty(N, 3, H, W, device=dev)               # unused by the engine when features are given
+            else:
+                imgs = torch.stack([image(v) for v in ids])
+            o = eng.depth_map(imgs, ring["proj_matrices"][0], depth_values, features=feats)
+            maps[j, 0].copy_(o["depth"]); maps[j, 1].copy_(o["photometric_confidence"])
+
+    def makespan(cache_features):
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        run_share(cache_features)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item()
+
+    # warm-up: three depth maps (graph capture, clocks), then the scan with and without the feature cache
+    for _ in range(max(3, args.warmup)):
+        eng.depth_map(torch.stack([image(v) for v in range(N)]), ring["proj_matrices"][0], depth_values)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms_cached = min(makespan(True) for _ in range(max(1, args.steps)))
+    clocks = sampler.stop() if rank == 0 else None
+    ms_plain = makespan(False)
+    gathered = scan_mod.gather_maps(maps, V) if world > 1 else maps       # the one end-of-scan gather (SURVEY.md §8e)
+    if rank == 0:
+        share = scan_mod.max_share(V, world)
+        line = {"metric": "depth maps/sec (one scan partitioned by reference view)", "value": V / (ms_cached * 1e-3), "unit": "depth maps/s",
+                "n_gpus": world, "steps": max(1, args.steps), "warmup": max(3, args.warmup), "ms_per_step": ms_cached,
+                "ms_per_plane": ms_cached / (share * D), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic",
+                "config": {"workload": f"cfg3: one synthetic DTU scan, {V} reference views, {W}x{H}, N={N}, D={D}, model_dtu_v2.ckpt, partitioned "
+                                       f"by reference view over {world} GPU(s) (contiguous slices, per-scan FeatNet cache)", "height": H,
+                           "width": W, "views": N, "planes": D, "scan_views": V,
+                           "l2": "per-step working set exceeds the 126 MB L2"},
+                "clocks": clocks, "makespan_s_feature_cache": ms_cached * 1e-3, "makespan_s_no_cache": ms_plain * 1e-3,
+                "max_share": share, "ceiling_speedup": V / share, "gathered_maps": list(gathered.shape),
+                "gpu_launches": len(mine) * (-(-D // eng.plane_batch) * 4 + D * 11) + 16 * (len(mine) + N - 1)}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS) + ["cfg3", "cfg5"])
+    ap.add_argument("--scan-views", type=int, default=49, help="cfg3: reference views of the synthetic scan")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--plane-batch", type=int, default=8, help="depth planes per launch of passes A-D (1..16)")
     args = ap.parse_args()
+    if args.workload == "cfg5":
+        return run_train(args)
+    if args.workload == "cfg3" and args.impl == "ours":
+        return run_scan(args)
+    if args.workload == "cfg3":
+        args.workload = "cfg2"            # the CPU arm of one depth map is the unit a scan repeats
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -410,13 +410,14 @@ def test_training_step_gradients_match_reference():
     assert not bad, "\n".join(bad)
 
 
-def test_batch_of_two_against_oracle_autograd(sd_dtu):
+@pytest.mark.parametrize("B,D", [(1, 7), (2, 7), (1, 11)])
+def test_batch_against_oracle_autograd(sd_dtu, B, D):
     """B = 2, D = 7 (a partial last plane batch) at 24x32: loss and a sample of parameter gradients against autograd through
     the oracle's training forward + loss on the CPU (the oracle's autograd is pinned to the reference's gradients in
     tests/test_oracle_golden.py::test_training_gradients)."""
     import aarmvsnet_b200 as aa
     from oracle import aarmvs_oracle as orc
-    H, W, N, D, B = 24, 32, 3, 7, 2
+    H, W, N = 24, 32, 3
     s = aa.synth.make_sample(H, W, N, D, seed=17, batch=B, depth_mode="inverse")
     g = torch.Generator().manual_seed(18)
     depth_gt = 425.0 + 510.0 * torch.rand(B, H, W, generator=g)
@@ -432,16 +433,17 @@ def test_batch_of_two_against_oracle_autograd(sd_dtu):
     loss, _ = aa.mvsnet_cls_loss(p2, depth_gt.cuda(), mask.cuda(), s["depth_values"].cuda())
     torch.testing.assert_close(loss.detach().cpu(), loss_ref.detach(), rtol=2e-4, atol=1e-6)
     loss.backward()
-    worst = 0.0
+    rels = []
     for name, p in m.named_parameters():
         want = sd[name].grad
         scale = want.abs().max().item()
         if scale < 1e-6:
             continue
-        rel = (p.grad.cpu() - want).abs().max().item() / scale
-        worst = max(worst, rel)
-        assert rel <= 3e-4, f"{name}: {rel:.2e}"
-    print(f"B=2 D=7: worst max-error / max-gradient over the parameters = {worst:.2e}")
+        rels.append(((p.grad.cpu() - want).abs().max().item() / scale, name))
+    rels.sort(reverse=True)
+    print(f"B={B} D={D}: worst max-error / max-gradient over the parameters = {rels[0][0]:.2e}; top: " +
+          ", ".join(f"{n} {r:.1e}" for r, n in rels[:6]))
+    assert rels[0][0] <= 3e-4, rels[:6]
 
 
 def test_flat_adam_matches_torch_adam_and_training_step_lowers_the_loss():
