@@ -113,9 +113,9 @@ def homo_warp(src_fea, src_proj, ref_proj, depth_value):
     align_corners=False although the grid is normalised with the (W-1)/2 formula."""
     b, c, h, w = src_fea.shape
     rot, trans = relative_projection(src_proj, ref_proj)
-    ys, xs = torch.meshgrid(torch.arange(h, dtype=torch.float32), torch.arange(w, dtype=torch.float32),
-                            indexing="ij")
-    xyz = torch.stack((xs.reshape(-1), ys.reshape(-1), torch.ones(h * w))).unsqueeze(0).repeat(b, 1, 1)
+    dt = src_fea.dtype                 # fp32 like the reference; fp64 only for the tests' noise-floor measurements
+    ys, xs = torch.meshgrid(torch.arange(h, dtype=dt), torch.arange(w, dtype=dt), indexing="ij")
+    xyz = torch.stack((xs.reshape(-1), ys.reshape(-1), torch.ones(h * w, dtype=dt))).unsqueeze(0).repeat(b, 1, 1)
     p = torch.matmul(rot, xyz) * depth_value.view(b, 1, 1) + trans.view(b, 3, 1)
     z = p[:, 2:3, :]
     z = torch.where(z == 0, z + 0.0001, z)                        # module.py:29
@@ -168,9 +168,9 @@ HIDDEN_DIMS = (16, 16, 16, 16, 8)          # models/drmvsnet.py:242
 STATE_SCALES = (1, 2, 4, 2, 1)             # models/drmvsnet.py:91
 
 
-def init_state(batch, height, width):
+def init_state(batch, height, width, dtype=torch.float32):
     """models/drmvsnet.py:202-206 + module.py:94-96 (zeros; the reference's hard .cuda() dropped)."""
-    return [(torch.zeros(batch, ch, height // s, width // s), torch.zeros(batch, ch, height // s, width // s))
+    return [(torch.zeros(batch, ch, height // s, width // s, dtype=dtype), torch.zeros(batch, ch, height // s, width // s, dtype=dtype))
             for ch, s in zip(HIDDEN_DIMS, STATE_SCALES)]
 
 
@@ -226,7 +226,7 @@ def forward_train(sd, imgs, proj_matrices, depth_values):
     b, n = imgs.shape[:2]
     feats = [feat_net(imgs[:, v], sd) for v in range(n)]
     h, w = feats[0].shape[2:]
-    state = init_state(b, h, w)
+    state = init_state(b, h, w, feats[0].dtype)
     costs = []
     for d in range(depth_values.shape[1]):
         var = aggregate_plane(feats[0], feats[1:], proj_matrices[:, 0],

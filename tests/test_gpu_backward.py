@@ -412,9 +412,10 @@ def test_training_step_gradients_match_reference():
 
 @pytest.mark.parametrize("B,D", [(1, 7), (2, 7), (1, 11)])
 def test_batch_against_oracle_autograd(sd_dtu, B, D):
-    """B = 2, D = 7 (a partial last plane batch) at 24x32: loss and a sample of parameter gradients against autograd through
-    the oracle's training forward + loss on the CPU (the oracle's autograd is pinned to the reference's gradients in
-    tests/test_oracle_golden.py::test_training_gradients)."""
+    """B samples, D planes (partial plane batches) at 24x32: loss and all parameter gradients against autograd through the
+    oracle's training forward + loss on the CPU in fp64 (the oracle's autograd is pinned to the reference's gradients in
+    tests/test_oracle_golden.py::test_training_gradients).  The same oracle in fp32 -- i.e. what the reference itself computes --
+    is measured against fp64 too: that is the noise floor of these sums (two samples' gradients partly cancel)."""
     import aarmvsnet_b200 as aa
     from oracle import aarmvs_oracle as orc
     H, W, N = 24, 32, 3
@@ -422,28 +423,37 @@ def test_batch_against_oracle_autograd(sd_dtu, B, D):
     g = torch.Generator().manual_seed(18)
     depth_gt = 425.0 + 510.0 * torch.rand(B, H, W, generator=g)
     mask = (torch.rand(B, H, W, generator=g) > 0.25).float()
-    sd = {k: v.clone().requires_grad_(True) for k, v in sd_dtu.items()}
-    prob = orc.forward_train(sd, s["imgs"], s["proj_matrices"], s["depth_values"])
-    loss_ref, _ = orc.cls_loss(prob, depth_gt, mask, s["depth_values"])
-    loss_ref.backward()
+
+    def oracle_grads(dtype):
+        sd = {k: v.to(dtype).clone().requires_grad_(True) for k, v in sd_dtu.items()}
+        prob = orc.forward_train(sd, s["imgs"].to(dtype), s["proj_matrices"].to(dtype), s["depth_values"].to(dtype))
+        loss, _ = orc.cls_loss(prob, depth_gt.to(dtype), mask.to(dtype), s["depth_values"].to(dtype))
+        loss.backward()
+        return loss.detach(), {k: v.grad for k, v in sd.items()}
+
+    loss64, g64 = oracle_grads(torch.float64)
+    loss32, g32 = oracle_grads(torch.float32)
     m = aa.EMVSNet(disparity_level=32, image_scale=1.0, max_h=H, max_w=W, return_depth=False)
     m.load_state_dict(sd_dtu, strict=True)
     m = m.cuda().train()
     p2, _, _ = m(s["imgs"].cuda(), s["proj_matrices"].cuda(), s["depth_values"].cuda())
     loss, _ = aa.mvsnet_cls_loss(p2, depth_gt.cuda(), mask.cuda(), s["depth_values"].cuda())
-    torch.testing.assert_close(loss.detach().cpu(), loss_ref.detach(), rtol=2e-4, atol=1e-6)
+    print(f"B={B} D={D}: loss ours {loss.item():.7f}, oracle fp32 {loss32.item():.7f}, oracle fp64 {loss64.item():.7f}")
+    torch.testing.assert_close(loss.detach().cpu().double(), loss64, rtol=5e-5, atol=1e-6)
     loss.backward()
-    rels = []
+    ours, floor = [], []
     for name, p in m.named_parameters():
-        want = sd[name].grad
+        want = g64[name]
         scale = want.abs().max().item()
         if scale < 1e-6:
             continue
-        rels.append(((p.grad.cpu() - want).abs().max().item() / scale, name))
-    rels.sort(reverse=True)
-    print(f"B={B} D={D}: worst max-error / max-gradient over the parameters = {rels[0][0]:.2e}; top: " +
-          ", ".join(f"{n} {r:.1e}" for r, n in rels[:6]))
-    assert rels[0][0] <= 3e-4, rels[:6]
+        ours.append(((p.grad.cpu().double() - want).abs().max().item() / scale, name))
+        floor.append(((g32[name].double() - want).abs().max().item() / scale, name))
+    ours.sort(reverse=True)
+    floor.sort(reverse=True)
+    print(f"B={B} D={D}: worst max-error / max-gradient vs fp64: ours {ours[0][0]:.2e} ({ours[0][1]}), the fp32 oracle {floor[0][0]:.2e} "
+          f"({floor[0][1]}); ours top: " + ", ".join(f"{n} {r:.1e}" for r, n in ours[:5]))
+    assert ours[0][0] <= max(2e-4, 3.0 * floor[0][0]), ours[:6]
 
 
 def test_flat_adam_matches_torch_adam_and_training_step_lowers_the_loss():
