@@ -3,7 +3,8 @@ models/drmvsnet.py:272-295): host-side chaining of the fp32 backward kernels beh
 
 Strategy: the forward (Engine.forward_saving_state, tensor-core kernels) keeps the features, the regularised
 costs and a snapshot of the recurrent state (h, c of the five ConvLSTM cells) after every depth plane.  The backward walks
-the planes in REVERSE; for plane d it recomputes that plane's intermediates from the snapshots of planes d-1 and d
+the planes in REVERSE (one CUDA graph of ~60 launches, replayed per plane); for plane d it recomputes that plane's
+intermediates from the snapshots of planes d-1 and d
 (per-view cost, omega's t0 and statistics, aggregated cost, pooled / deconvolved inputs, gate pre-activations), runs the
 U-Net's backward against them and carries dL/dh_{d-1}, dL/dc_{d-1} of the five cells to the next iteration.  The warp
 backward scatters into per-view feature gradients that are accumulated over all planes; FeatNet's backward then runs once
@@ -21,7 +22,6 @@ import torch
 
 from . import capi, pack
 from .engine import _HID, _SCALE, _ptr, _src
-from .ops import _unblock_state
 
 _CELL_IN = (32, 16, 16, 32, 32)           # input channels of the five cells (models/drmvsnet.py:241)
 _FS_OFF = {"init0": 0, "init1": 2, "conv0": 6, "conv1": 14, "conv2": 22, "dc0": 30, "dc1": 38, "dc2": 46,
@@ -47,8 +47,9 @@ def _taps_inverse(dw, cout, cin, k):
 class Backward:
     """Gradient accumulation for one optimisation step of one EMVSNet (all samples of the batch, all planes)."""
 
-    def __init__(self, engine, device):
+    def __init__(self, engine, device, use_graph=True):
         self.eng = engine
+        self.use_graph = use_graph
         self.lib = engine.lib
         self.dev = device
         self.sd = {k: v.detach().to(device=device, dtype=torch.float32) for k, v in engine.module.state_dict().items()}
@@ -136,13 +137,19 @@ class Backward:
         b["dh"] = [torch.zeros(Pi[i], _HID[i], **f32) for i in range(5)]
         b["dhprev"] = [torch.zeros(Pi[i], _HID[i], **f32) for i in range(5)]
         b["dc"] = [torch.zeros(Pi[i], _HID[i], **f32) for i in range(5)]
-        b["zero"] = [torch.zeros(Pi[i], _HID[i], **f32) for i in range(5)]
         b["dcost"] = torch.empty(P, 32, **f32)
         b["dcostv"] = torch.empty(S, P, 32, **f32)
         b["drew"] = torch.empty(S, P, **f32)
         b["dt0"] = torch.empty(S, P, 4, **f32)
         b["dfeat"] = torch.zeros(N, P, 32, **f32)
-        b["depth1"] = torch.zeros(1, **f32)
+        # staging of one plane: the state records after planes d-1 and d (Engine.state_layout), dL/dcost_reg[d], the plane index
+        lay, rec = self.eng.state_layout(H, W)
+        b["rec2"] = torch.zeros(2, rec, **f32)
+        for r, (hn, cn) in enumerate((("hp", "cp"), ("h", "c"))):
+            b[hn] = [b["rec2"][r][lay[i][0]:lay[i][0] + lay[i][2]].view(Pi[i], _HID[i]) for i in range(5)]
+            b[cn] = [b["rec2"][r][lay[i][1]:lay[i][1] + lay[i][2]].view(Pi[i], _HID[i]) for i in range(5)]
+        b["dcr"] = torch.zeros(P, **f32)
+        b["plane"] = torch.zeros(1, device=dev, dtype=torch.int32)
         self._ws = b
         return b
 
@@ -176,102 +183,118 @@ class Backward:
 
     # ------------------------------------------------------------------------------------------ one sample
     def sample(self, saved, dcost_volume):
-        """saved: Engine.forward_saving_state's dict; dcost_volume [D, P] = dL / d(regularised cost).  Accumulates into self.g."""
-        lib, eng, w, bw, g = self.lib, self.eng, self.w, self.bw, self.g
+        """saved: Engine.forward_saving_state's dict; dcost_volume [D, P] = dL / d(regularised cost).  Accumulates into self.g.
+
+        The body of one plane works on FIXED buffers: the two state records it needs (after planes d-1 and d) and its row of
+        dcost_volume are staged into them, the plane index lives in device memory -- so the ~60 launches of a plane are captured
+        once as a CUDA graph and replayed for every other plane (three small staging ops + one graph launch per plane)."""
+        eng = self.eng
         H, W, N, D = saved["H"], saved["W"], saved["N"], saved["D"]
-        P, S = H * W, N - 1
-        H2, W2, H4, W4 = H // 2, W // 2, H // 4, W // 4
-        hw = [(H // s, W // s) for s in _SCALE]
         b = self._workspace(H, W, N)
-        st = self._st()
-        feat = saved["feat"]
-        ref, src = _ptr(feat), _ptr(feat, P * 32)
-        ac = int(eng.align_corners)
-        depths_dev = torch.tensor(saved["depths_host"], device=self.dev, dtype=torch.float32)
         for t in b["dh"] + b["dc"] + b["dhprev"]:
             t.zero_()
         b["dfeat"].zero_()
         dcost_volume = dcost_volume.contiguous()
-
+        state = saved["state"]
+        graph = None
         for d in range(D - 1, -1, -1):
-            h = [saved["h"][i][d] for i in range(5)]
-            c = [_unblock_state(saved["c"][i][d], hw[i][0], hw[i][1], _HID[i]) for i in range(5)]
-            if d > 0:
-                hp = [saved["h"][i][d - 1] for i in range(5)]
-                cp = [_unblock_state(saved["c"][i][d - 1], hw[i][0], hw[i][1], _HID[i]) for i in range(5)]
+            b["rec2"].copy_(state[d:d + 2])                   # [0] = state entering plane d, [1] = state after it
+            b["dcr"].copy_(dcost_volume[d])
+            b["plane"].fill_(d)
+            if d == D - 1 or not self.use_graph:
+                self._plane(saved, b)                         # eager: also sets the kernels' launch attributes
+                if self.use_graph and D > 1:
+                    torch.cuda.synchronize(self.dev)
+                    graph = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(graph):
+                        self._plane(saved, b)
             else:
-                hp, cp = b["zero"], [None] * 5
-            # ---------------- recompute the plane's forward intermediates
-            b["stats"].zero_()
-            eng.cost_stem(ref, src, P * 32, H, W, S, _ptr(saved["cams"]), w, _ptr(depths_dev), d, None, 1, _ptr(b["t0"]), _ptr(b["stats"]),
-                          st, _ptr(b["costv"]))
-            for stage in (2, 3):
-                capi.check(lib.aarmvs_omega_stats(stage, _ptr(b["t0"]), H, W, S, 1, w["tail_host"], _ptr(b["stats"]), st), "aarmvs_omega_stats")
-            capi.check(lib.aarmvs_aggregate(ref, src, P * 32, H, W, S, _ptr(saved["cams"]), w["tail_host"], _ptr(depths_dev), d, None, 1, ac,
-                                            _ptr(b["t0"]), _ptr(b["stats"]), _ptr(b["costv"]), _ptr(b["cost"]), None, _ptr(b["rew"]), st),
-                       "aarmvs_aggregate")
-            capi.check(lib.aarmvs_maxpool2(_ptr(h[0]), H, W, 16, _ptr(b["pool0"]), st), "aarmvs_maxpool2")
-            capi.check(lib.aarmvs_maxpool2(_ptr(h[1]), H2, W2, 16, _ptr(b["pool1"]), st), "aarmvs_maxpool2")
-            for i, (hin, win, src_h) in enumerate(((H4, W4, h[2]), (H2, W2, h[3]))):
-                self.conv([_seg(src_h, 16)], hin, win, [_seg(b[f"up{i}raw"], 16)], 2 * hin, 2 * win, 3, 2, True, bw[f"deconv{i}.w"],
-                          bw[f"deconv{i}.b"])
-                b[f"gsum{i}"].zero_()
-                capi.check(lib.aarmvs_gn_sums(_ptr(b[f"up{i}raw"]), 4 * hin * win, 16, 2, _ptr(b[f"gsum{i}"]), st), "aarmvs_gn_sums")
-                self.gn_apply(b[f"up{i}raw"], 4 * hin * win, 16, 2, b[f"gsum{i}"], bw[f"deconv{i}.gn"], b[f"up{i}"])
-            xin = [[_seg(b["cost"], 32)], [_seg(b["pool0"], 16)], [_seg(b["pool1"], 16)], [_seg(b["up0"], 16), _seg(h[1], 16)],
-                   [_seg(b["up1"], 16), _seg(h[0], 16)]]
-            for i in range(5):
-                self.conv(xin[i] + [_seg(hp[i], _HID[i])], hw[i][0], hw[i][1], [_seg(b["gates"][i], 4 * _HID[i])], hw[i][0], hw[i][1], 3, 1,
-                          False, bw[f"cell{i}.w"], bw[f"cell{i}.b"])
-
-            # ---------------- backward of the plane.  b["dh"][i] enters holding dL/dh_i^d from plane d+1 (cell i's h_prev input)
-            dh, dhp, dc = b["dh"], b["dhprev"], b["dc"]
-            dcr = dcost_volume[d]                                           # [P] = [P][1]
-            self.conv([_seg(dcr, 1)], H, W, [_seg(dh[4], 8, 1)], H, W, 3, 1, True, bw["head.wT"])
-            self.wgrad([_seg(h[4], 8)], H, W, dcr, H, W, 1, 3, 1, g["head.w"], g["head.b"])
-
-            def cell_bwd(i, outs):
-                capi.check(lib.aarmvs_lstm_gates_bwd(_ptr(b["gates"][i]), _ptr(cp[i]) if cp[i] is not None else None, _ptr(c[i]), _ptr(dh[i]),
-                                                     _ptr(dc[i]), _ptr(b["dgates"][i]), hw[i][0] * hw[i][1], _HID[i], st), "aarmvs_lstm_gates_bwd")
-                self.conv([_seg(b["dgates"][i], 4 * _HID[i])], hw[i][0], hw[i][1], outs + [_seg(dhp[i], _HID[i])], hw[i][0], hw[i][1], 3, 1, True,
-                          bw[f"cell{i}.wT"])
-                self.wgrad(xin[i] + [_seg(hp[i], _HID[i])], hw[i][0], hw[i][1], b["dgates"][i], hw[i][0], hw[i][1], 4 * _HID[i], 3, 1,
-                           g[f"cell{i}.w"], g[f"cell{i}.b"])
-
-            def up_bwd(i, hin, win, src_h, dh_target):
-                pp = 4 * hin * win
-                self.gn_bwd(b[f"up{i}raw"], b[f"dup{i}"], pp, 16, 2, b[f"gsum{i}"], bw[f"deconv{i}.gn"], b[f"dup{i}"], g[f"deconv{i}.gamma"],
-                            g[f"deconv{i}.beta"], g[f"deconv{i}.b"])
-                self.conv([_seg(b[f"dup{i}"], 16)], 2 * hin, 2 * win, [_seg(dh_target, 16, 1)], hin, win, 3, 2, False, bw[f"deconv{i}.wT"])
-                self.wgrad([_seg(b[f"dup{i}"], 16)], 2 * hin, 2 * win, src_h, hin, win, 16, 3, 2, g[f"deconv{i}.wT"])
-
-            cell_bwd(4, [_seg(b["dup1"], 16), _seg(dh[0], 16, 1)])
-            up_bwd(1, H2, W2, h[3], dh[3])
-            cell_bwd(3, [_seg(b["dup0"], 16), _seg(dh[1], 16, 1)])
-            up_bwd(0, H4, W4, h[2], dh[2])
-            cell_bwd(2, [_seg(b["dpool1"], 16)])
-            capi.check(lib.aarmvs_maxpool2_bwd(_ptr(h[1]), _ptr(b["dpool1"]), H2, W2, 16, _ptr(dh[1]), st), "aarmvs_maxpool2_bwd")
-            cell_bwd(1, [_seg(b["dpool0"], 16)])
-            capi.check(lib.aarmvs_maxpool2_bwd(_ptr(h[0]), _ptr(b["dpool0"]), H, W, 16, _ptr(dh[0]), st), "aarmvs_maxpool2_bwd")
-            cell_bwd(0, [_seg(b["dcost"], 32)])
-
-            # ---------------- aggregation, omega, warp
-            capi.check(lib.aarmvs_aggregate_bwd(_ptr(b["dcost"]), _ptr(b["costv"]), _ptr(b["rew"]), S, P, _ptr(b["dcostv"]), _ptr(b["drew"]), st),
-                       "aarmvs_aggregate_bwd")
-            b["bstats"].zero_()
-            for stage in (3, 2, 1, 0):
-                capi.check(lib.aarmvs_omega_bwd(stage, _ptr(b["t0"]), _ptr(b["drew"]), H, W, S, w["tail_host"], _ptr(b["stats"]),
-                                                _ptr(b["bstats"]), _ptr(g["tail"]), _ptr(b["dt0"]), st), "aarmvs_omega_bwd")
-            for v in range(S):
-                self.conv([_seg(b["dt0"][v], 4)], H, W, [_seg(b["dcostv"][v], 32, 1)], H, W, 3, 1, True, bw["stem.wT"])
-                self.wgrad([_seg(b["costv"][v], 32)], H, W, b["dt0"][v], H, W, 4, 3, 1, g["stem.w"], g["stem.b"])
-            capi.check(lib.aarmvs_warp_bwd(ref, src, P * 32, H, W, S, _ptr(saved["cams"]), saved["depths_host"][d], ac, _ptr(b["dcostv"]),
-                                           _ptr(b["dfeat"]), _ptr(b["dfeat"], P * 32), st), "aarmvs_warp_bwd")
-            # ---------------- carry: dL/dh_{d-1} becomes next iteration's starting dh; dc was updated in place
-            b["dh"], b["dhprev"] = b["dhprev"], b["dh"]
-
+                graph.replay()
         for v in range(N):
             self.featnet(saved["imgs"][v], b["dfeat"][v], H, W)
+
+    def _plane(self, saved, b):
+        """Backward of the plane whose index is in b["plane"], whose states are in b["rec2"] and whose dL/dcost_reg is b["dcr"]."""
+        lib, eng, w, bw, g = self.lib, self.eng, self.w, self.bw, self.g
+        H, W, N = saved["H"], saved["W"], saved["N"]
+        P, S = H * W, N - 1
+        H2, W2, H4, W4 = H // 2, W // 2, H // 4, W // 4
+        hw = [(H // s, W // s) for s in _SCALE]
+        st = self._st()
+        feat = saved["feat"]
+        ref, src = _ptr(feat), _ptr(feat, P * 32)
+        ac = int(eng.align_corners)
+        dptr = _ptr(b["plane"])
+        depths, cams = _ptr(saved["depths"]), _ptr(saved["cams"])
+        hp, cp, h, c = b["hp"], b["cp"], b["h"], b["c"]
+        # ---------------- recompute the plane's forward intermediates
+        b["stats"].zero_()
+        eng.cost_stem(ref, src, P * 32, H, W, S, cams, w, depths, 0, dptr, 1, _ptr(b["t0"]), _ptr(b["stats"]), st, _ptr(b["costv"]))
+        for stage in (2, 3):
+            capi.check(lib.aarmvs_omega_stats(stage, _ptr(b["t0"]), H, W, S, 1, w["tail_host"], _ptr(b["stats"]), st), "aarmvs_omega_stats")
+        capi.check(lib.aarmvs_aggregate(ref, src, P * 32, H, W, S, cams, w["tail_host"], depths, 0, dptr, 1, ac, _ptr(b["t0"]),
+                                        _ptr(b["stats"]), _ptr(b["costv"]), _ptr(b["cost"]), None, _ptr(b["rew"]), st), "aarmvs_aggregate")
+        capi.check(lib.aarmvs_maxpool2(_ptr(h[0]), H, W, 16, _ptr(b["pool0"]), st), "aarmvs_maxpool2")
+        capi.check(lib.aarmvs_maxpool2(_ptr(h[1]), H2, W2, 16, _ptr(b["pool1"]), st), "aarmvs_maxpool2")
+        for i, (hin, win, src_h) in enumerate(((H4, W4, h[2]), (H2, W2, h[3]))):
+            self.conv([_seg(src_h, 16)], hin, win, [_seg(b[f"up{i}raw"], 16)], 2 * hin, 2 * win, 3, 2, True, bw[f"deconv{i}.w"],
+                      bw[f"deconv{i}.b"])
+            b[f"gsum{i}"].zero_()
+            capi.check(lib.aarmvs_gn_sums(_ptr(b[f"up{i}raw"]), 4 * hin * win, 16, 2, _ptr(b[f"gsum{i}"]), st), "aarmvs_gn_sums")
+            self.gn_apply(b[f"up{i}raw"], 4 * hin * win, 16, 2, b[f"gsum{i}"], bw[f"deconv{i}.gn"], b[f"up{i}"])
+        xin = [[_seg(b["cost"], 32)], [_seg(b["pool0"], 16)], [_seg(b["pool1"], 16)], [_seg(b["up0"], 16), _seg(h[1], 16)],
+               [_seg(b["up1"], 16), _seg(h[0], 16)]]
+        for i in range(5):
+            self.conv(xin[i] + [_seg(hp[i], _HID[i])], hw[i][0], hw[i][1], [_seg(b["gates"][i], 4 * _HID[i])], hw[i][0], hw[i][1], 3, 1,
+                      False, bw[f"cell{i}.w"], bw[f"cell{i}.b"])
+
+        # ---------------- backward of the plane.  b["dh"][i] enters holding dL/dh_i^d from plane d+1 (cell i's h_prev input)
+        dh, dhp, dc = b["dh"], b["dhprev"], b["dc"]
+        dcr = b["dcr"]                                               # [P] = [P][1]
+        self.conv([_seg(dcr, 1)], H, W, [_seg(dh[4], 8, 1)], H, W, 3, 1, True, bw["head.wT"])
+        self.wgrad([_seg(h[4], 8)], H, W, dcr, H, W, 1, 3, 1, g["head.w"], g["head.b"])
+
+        def cell_bwd(i, outs):
+            # at plane 0 the staged previous state is the zero record: c_prev = h_prev = 0 (module.py:94-96)
+            capi.check(lib.aarmvs_lstm_gates_bwd(_ptr(b["gates"][i]), _ptr(cp[i]), _ptr(c[i]), _ptr(dh[i]), _ptr(dc[i]), _ptr(b["dgates"][i]),
+                                                 hw[i][0] * hw[i][1], _HID[i], st), "aarmvs_lstm_gates_bwd")
+            self.conv([_seg(b["dgates"][i], 4 * _HID[i])], hw[i][0], hw[i][1], outs + [_seg(dhp[i], _HID[i])], hw[i][0], hw[i][1], 3, 1, True,
+                      bw[f"cell{i}.wT"])
+            self.wgrad(xin[i] + [_seg(hp[i], _HID[i])], hw[i][0], hw[i][1], b["dgates"][i], hw[i][0], hw[i][1], 4 * _HID[i], 3, 1,
+                       g[f"cell{i}.w"], g[f"cell{i}.b"])
+
+        def up_bwd(i, hin, win, src_h, dh_target):
+            pp = 4 * hin * win
+            self.gn_bwd(b[f"up{i}raw"], b[f"dup{i}"], pp, 16, 2, b[f"gsum{i}"], bw[f"deconv{i}.gn"], b[f"dup{i}"], g[f"deconv{i}.gamma"],
+                        g[f"deconv{i}.beta"], g[f"deconv{i}.b"])
+            self.conv([_seg(b[f"dup{i}"], 16)], 2 * hin, 2 * win, [_seg(dh_target, 16, 1)], hin, win, 3, 2, False, bw[f"deconv{i}.wT"])
+            self.wgrad([_seg(b[f"dup{i}"], 16)], 2 * hin, 2 * win, src_h, hin, win, 16, 3, 2, g[f"deconv{i}.wT"])
+
+        cell_bwd(4, [_seg(b["dup1"], 16), _seg(dh[0], 16, 1)])
+        up_bwd(1, H2, W2, h[3], dh[3])
+        cell_bwd(3, [_seg(b["dup0"], 16), _seg(dh[1], 16, 1)])
+        up_bwd(0, H4, W4, h[2], dh[2])
+        cell_bwd(2, [_seg(b["dpool1"], 16)])
+        capi.check(lib.aarmvs_maxpool2_bwd(_ptr(h[1]), _ptr(b["dpool1"]), H2, W2, 16, _ptr(dh[1]), st), "aarmvs_maxpool2_bwd")
+        cell_bwd(1, [_seg(b["dpool0"], 16)])
+        capi.check(lib.aarmvs_maxpool2_bwd(_ptr(h[0]), _ptr(b["dpool0"]), H, W, 16, _ptr(dh[0]), st), "aarmvs_maxpool2_bwd")
+        cell_bwd(0, [_seg(b["dcost"], 32)])
+
+        # ---------------- aggregation, omega, warp
+        capi.check(lib.aarmvs_aggregate_bwd(_ptr(b["dcost"]), _ptr(b["costv"]), _ptr(b["rew"]), S, P, _ptr(b["dcostv"]), _ptr(b["drew"]), st),
+                   "aarmvs_aggregate_bwd")
+        b["bstats"].zero_()
+        for stage in (3, 2, 1, 0):
+            capi.check(lib.aarmvs_omega_bwd(stage, _ptr(b["t0"]), _ptr(b["drew"]), H, W, S, w["tail_host"], _ptr(b["stats"]),
+                                            _ptr(b["bstats"]), _ptr(g["tail"]), _ptr(b["dt0"]), st), "aarmvs_omega_bwd")
+        for v in range(S):
+            self.conv([_seg(b["dt0"][v], 4)], H, W, [_seg(b["dcostv"][v], 32, 1)], H, W, 3, 1, True, bw["stem.wT"])
+            self.wgrad([_seg(b["costv"][v], 32)], H, W, b["dt0"][v], H, W, 4, 3, 1, g["stem.w"], g["stem.b"])
+        capi.check(lib.aarmvs_warp_bwd(ref, src, P * 32, H, W, S, cams, depths, 0, dptr, ac, _ptr(b["dcostv"]), _ptr(b["dfeat"]),
+                                       _ptr(b["dfeat"], P * 32), st), "aarmvs_warp_bwd")
+        # ---------------- carry: dL/dh_{d-1} is the next (lower) plane's starting dh; dc was updated in place
+        for i in range(5):
+            dh[i].copy_(dhp[i])
 
     # ------------------------------------------------------------------------------------------ FeatNet of one view
     def featnet(self, img, dfeat, H, W):

@@ -95,7 +95,7 @@ PROTOTYPES = {
     "aarmvs_maxpool2_bwd": (_I, [_P, _P, _I, _I, _I, _P, _P]),
     "aarmvs_aggregate_bwd": (_I, [_P, _P, _P, _I, _SZ, _P, _P, _P]),
     "aarmvs_omega_bwd": (_I, [_I, _P, _P, _I, _I, _I, c_float_p, _P, _P, _P, _P, _P]),
-    "aarmvs_warp_bwd": (_I, [_P, _P, _SZ, _I, _I, _I, _P, _F, _I, _P, _P, _P, _P]),
+    "aarmvs_warp_bwd": (_I, [_P, _P, _SZ, _I, _I, _I, _P, _P, _I, _P, _I, _P, _P, _P, _P]),
     "aarmvs_feat_assemble_bwd": (_I, [_P, _I, _I, _P, _P, _P, _P]),
     "aarmvs_deform_sample": (_I, [_P, _I, _I, _P, _P, _P, _P]),
     "aarmvs_deform_bwd": (_I, [_P, _I, _I, _P, _P, _P, _P, _P, _P]),

@@ -225,11 +225,14 @@ __global__ void __launch_bounds__(256) omega_bwd_kernel(const __grid_constant__ 
 
 // ------------------------------------------------------------------------------------------------ warp
 __global__ void __launch_bounds__(256) warp_bwd_kernel(const float* __restrict__ ref, const float* __restrict__ src, size_t view_stride,
-                                                       int H, int W, int S, const float* __restrict__ cams, float depth, int align_corners,
-                                                       const float* __restrict__ dcostv, float* __restrict__ dref, float* __restrict__ dsrc) {
+                                                       int H, int W, int S, const float* __restrict__ cams,
+                                                       const float* __restrict__ depth_values, int d_host, const int* __restrict__ d_dev,
+                                                       int align_corners, const float* __restrict__ dcostv, float* __restrict__ dref,
+                                                       float* __restrict__ dsrc) {
     __shared__ float scam[AARMVS_MAX_SRC * 12];
     for (int i = threadIdx.x; i < S * 12; i += blockDim.x) scam[i] = cams[i];
     __syncthreads();
+    const float depth = depth_values[plane_index(d_host, d_dev)];
     const size_t P = (size_t)H * W;
     const int sub = threadIdx.x & 7;
     for (size_t p = (size_t)blockIdx.x * 32 + (threadIdx.x >> 3); p < P; p += (size_t)gridDim.x * 32) {
@@ -286,11 +289,13 @@ extern "C" int aarmvs_omega_bwd(int stage, const float* t0, const float* dreweig
     AARMVS_LAUNCH_RESULT();
 }
 
-extern "C" int aarmvs_warp_bwd(const float* ref, const float* src, size_t view_stride, int H, int W, int S, const float* cams, float depth,
-                               int align_corners, const float* dcostv, float* dref, float* dsrc, void* stream) {
-    AARMVS_CHECK_ARG(ref && src && cams && dcostv && dref && dsrc && H > 0 && W > 0 && S >= 1 && S <= AARMVS_MAX_SRC);
+extern "C" int aarmvs_warp_bwd(const float* ref, const float* src, size_t view_stride, int H, int W, int S, const float* cams,
+                               const float* depth_values, int d_host, const int* d_dev, int align_corners, const float* dcostv, float* dref,
+                               float* dsrc, void* stream) {
+    AARMVS_CHECK_ARG(ref && src && cams && depth_values && dcostv && dref && dsrc && H > 0 && W > 0 && S >= 1 && S <= AARMVS_MAX_SRC);
     const size_t blocks = ((size_t)H * W + 31) / 32;
-    warp_bwd_kernel<<<(int)(blocks < 148 * 16 ? blocks : 148 * 16), 256, 0, (cudaStream_t)stream>>>(ref, src, view_stride, H, W, S, cams, depth,
-                                                                                                 align_corners, dcostv, dref, dsrc);
+    warp_bwd_kernel<<<(int)(blocks < 148 * 16 ? blocks : 148 * 16), 256, 0, (cudaStream_t)stream>>>(ref, src, view_stride, H, W, S, cams,
+                                                                                                 depth_values, d_host, d_dev, align_corners,
+                                                                                                 dcostv, dref, dsrc);
     AARMVS_LAUNCH_RESULT();
 }

@@ -429,12 +429,34 @@ class Engine:
             self.feature_map(img.to(torch.float32).contiguous(), out, fs, w, stream)
             return out
 
+    @staticmethod
+    def state_layout(H, W):
+        """Offsets (floats) of h_i and c_i, i = 0..4, inside one per-plane state record [h0 | c0 | h1 | c1 | ...], NHWC fp32,
+        and the record length: 66 floats per full-resolution pixel."""
+        off, lay = 0, []
+        for ch, s in zip(_HID, _SCALE):
+            n = (H // s) * (W // s) * ch
+            lay.append((off, off + n, n))
+            off += 2 * n
+        return lay, off
+
+    @staticmethod
+    def _unblock_into(dst, cb, H, W, ch):
+        """Tile-blocked cell state (include/aarmvs.h: aarmvs_cell_state_floats) -> dst [H*W*ch] NHWC."""
+        ty, tx = (H + 15) // 16, (W + 7) // 8
+        src = cb.view(ty, tx, 4, 16, 8, ch // 4).permute(0, 3, 1, 4, 2, 5)              # [ty][16][tx][8][4][ch/4]
+        if H % 16 == 0 and W % 8 == 0:
+            dst.view(ty, 16, tx, 8, 4, ch // 4).copy_(src)                               # one strided copy
+        else:
+            dst.view(H, W, ch).copy_(src.reshape(ty * 16, tx * 8, ch)[:H, :W])
+
     def forward_saving_state(self, imgs, proj_matrices, depth_values):
         """The training-phase forward of ONE sample (models/drmvsnet.py:272-287) on the tensor-core kernels, launched eagerly,
         keeping what the backward pass needs: the features of the N views, the regularised cost of every plane and a snapshot
-        of the recurrent state (h, c of the five cells) after every plane -- 66 floats per full-resolution pixel and plane;
-        everything else is recomputed per plane by the backward (aarmvsnet_b200/backward.py).
-        Returns {"cost": [D,P], "feat": [N,P,32], "h": 5 x [D,P_i,Ch_i], "c": 5 x [D, blocked floats], ...}."""
+        of the recurrent state (h, c of the five cells) after every plane -- one flat record of 66 floats per full-resolution
+        pixel and plane (state_layout), record 0 = the zero state before plane 0; everything else is recomputed per plane by
+        the backward (aarmvsnet_b200/backward.py).
+        Returns {"cost": [D,P], "feat": [N,P,32], "state": [D+1, record], ...}."""
         device = imgs.device
         if device.type != "cuda":
             raise RuntimeError("aarmvsnet_b200 has no CPU path: inputs must live on a CUDA device")
@@ -449,23 +471,23 @@ class Engine:
             imgs = imgs.to(torch.float32).contiguous()
             for v in range(N):
                 self.feature_map(imgs[v], ws["feat"][v], ws, w, stream)
-            cams = self.relative_cameras(proj_matrices)
-            ws["cams"].copy_(cams, non_blocking=True)
+            ws["cams"].copy_(self.relative_cameras(proj_matrices), non_blocking=True)
             ws["depths"].copy_(depth_values.to(torch.float32), non_blocking=True)
             ws["plane"].zero_()
             ws["psums"].zero_()
-            f32 = dict(device=device, dtype=torch.float32)
-            saved = {"H": H, "W": W, "N": N, "D": D, "imgs": imgs, "cams": ws["cams"].clone(),
-                     "depths_host": [float(x) for x in depth_values.detach().cpu().tolist()],
-                     "h": [torch.empty((D,) + tuple(t.shape[1:]), **f32) for t in ws["h"]],
-                     "c": [torch.empty(D, t.numel(), **f32) for t in ws["c"]]}
+            lay, rec = self.state_layout(H, W)
+            state = torch.empty(D + 1, rec, device=device, dtype=torch.float32)
+            state[0].zero_()
+            saved = {"H": H, "W": W, "N": N, "D": D, "imgs": imgs, "cams": ws["cams"].clone(), "depths": ws["depths"].clone(),
+                     "state": state}
             K = ws["K"]
             for d0 in range(0, D, K):
                 def snapshot(k, d0=d0):
-                    d = d0 + k
+                    r = state[d0 + k + 1]
                     for i in range(5):
-                        saved["h"][i][d].copy_(ws["h"][i][d & 1])
-                        saved["c"][i][d].copy_(ws["c"][i])
+                        ho, co, n = lay[i]
+                        r[ho:ho + n].copy_(ws["h"][i][(d0 + k) & 1].reshape(-1))
+                        self._unblock_into(r[co:co + n], ws["c"][i], H // _SCALE[i], W // _SCALE[i], _HID[i])
                 self._batch(ws, w, stream, min(K, D - d0), after_plane=snapshot)
             saved["feat"] = ws["feat"].clone()
             saved["cost"] = ws["cost_volume"].clone()

@@ -330,9 +330,11 @@ int aarmvs_omega_bwd(int stage, const float* t0, const float* dreweight, int H, 
 
 /* Warp backward (module.py:6-38; the grid is built under no_grad, so only the features receive gradients): with
  * c_v = (warp_v - ref)^2:  g = 2 (warp_v - ref) * dcostv[v];  dref[p] -= sum_v g;  dsrc[v][tap] += w_tap * g for the four
- * bilinear taps (red.global.add.v4.f32).  cams: device [S][12]; dsrc: S maps `view_stride` floats apart. */
-int aarmvs_warp_bwd(const float* ref, const float* src, size_t view_stride, int H, int W, int S, const float* cams, float depth,
-                    int align_corners, const float* dcostv, float* dref, float* dsrc, void* stream);
+ * bilinear taps (red.global.add.v4.f32).  cams: device [S][12]; the plane's depth is depth_values[d] with d = *d_dev if d_dev
+ * is non-null (one captured graph serves every plane), else d_host; dsrc: S maps `view_stride` floats apart. */
+int aarmvs_warp_bwd(const float* ref, const float* src, size_t view_stride, int H, int W, int S, const float* cams,
+                    const float* depth_values, int d_host, const int* d_dev, int align_corners, const float* dcostv, float* dref,
+                    float* dsrc, void* stream);
 
 /* IntraViewAAModule tail backward (drmvsnet.py:19-24): dfeature [H][W][32] -> gradients w.r.t. the GroupNorm+ReLU'd 1x1
  * outputs: dm0 [H][W][16] (stored), dm1 [H/2][W/2][8] and dm2 [H/4][W/4][8] (+=, atomics: zero before). */
