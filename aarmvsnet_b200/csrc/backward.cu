@@ -37,7 +37,7 @@ static int convert_segs(const aarmvs_seg* in, int n, Seg* out, int& total) {
 }
 
 // ------------------------------------------------------------------------------------------------ generic conv
-constexpr int GC_CO = 16, GC_THREADS = 128;
+constexpr int GC_THREADS = 128;     // one thread = one output pixel x GC_CO output channels (8 for small maps: twice the CTAs)
 
 struct GConvArgs {
     Seg in[3], out[3];
@@ -47,6 +47,7 @@ struct GConvArgs {
     const float* bias;     // [cout] or null
 };
 
+template <int GC_CO>
 __global__ void __launch_bounds__(GC_THREADS) conv_nhwc_kernel(const __grid_constant__ GConvArgs a) {
     extern __shared__ __align__(16) float sw[];          // [ks*ks][cin][GC_CO] of this output-channel tile, zero padded
     const int tid = threadIdx.x;
@@ -136,7 +137,11 @@ __global__ void __launch_bounds__(GC_THREADS) conv_nhwc_kernel(const __grid_cons
 }
 
 // ------------------------------------------------------------------------------------------------ weight gradient
-constexpr int WG_PX = 32, WG_CI = 16, WG_CO = 64, WG_THREADS = 64;
+// Block = 256 threads = 4 pixel groups x (4 input-channel quads x 16 output-channel quads): every thread owns a 4 x 4 block of
+// dW[tap][ci0 .. ci0 + 16][0 .. 64) for a quarter of the pixels of each staged tile; tiles of 64 pixels are staged by all 256
+// threads (16-byte loads where the channel counts allow), partial sums go to global memory with fp32 atomics at the end.
+// (The first version -- 64 threads, 512 pixels per block, scalar staging -- took ~100 us per call whatever the layer: latency.)
+constexpr int WG_PX = 64, WG_CI = 16, WG_CO = 64, WG_THREADS = 256;
 
 struct WGArgs {
     Seg x[3];
@@ -153,68 +158,96 @@ __global__ void __launch_bounds__(WG_THREADS) conv_wgrad_kernel(const __grid_con
     const int tid = threadIdx.x;
     const int tap = blockIdx.y, ky = tap / a.ks, kx = tap - ky * a.ks, pad = (a.ks - 1) / 2;
     const int ci0 = blockIdx.z * WG_CI;
-    const int ci4 = tid >> 4, co4 = tid & 15;
+    const int pg = tid >> 6, ci4 = (tid >> 4) & 3, co4 = tid & 15;
     const int P = a.Hy * a.Wy;
     const int p_begin = blockIdx.x * a.chunk, p_end = min(P, p_begin + a.chunk);
+    const int cy4 = (a.cy + 3) & ~3;                                     // output channels staged (zero padded to a quad)
+    const bool dy_vec = (a.cy & 3) == 0;
     float acc[4][4] = {};
     float bsum[4] = {0.f, 0.f, 0.f, 0.f};
+    const bool active = co4 * 4 < a.cy;
     const bool want_bias = a.db && tap == 0 && blockIdx.z == 0 && ci4 == 0;
+    // the segment (and channel inside it) this thread stages: constant over the tiles
+    const int sc = ci0 + (tid & 3) * 4;                                  // first of the 4 channels of this thread's staging quad
+    int sseg = 0, sbase = 0;
+    while (sseg < a.nx - 1 && sc >= sbase + a.x[sseg].ch) { sbase += a.x[sseg].ch; ++sseg; }
+    const bool x_vec = (a.x[sseg].ch & 3) == 0 && (sbase & 3) == 0 && sc + 3 < a.cx && (sc - sbase) + 3 < a.x[sseg].ch;
     for (int p0 = p_begin; p0 < p_end; p0 += WG_PX) {
-        // stage X[p + tap][ci0 .. ci0 + 16): one item = (pixel, channel)
-        for (int it = tid; it < WG_PX * WG_CI; it += WG_THREADS) {
-            const int px = it / WG_CI, c = ci0 + (it - px * WG_CI);
-            const int p = p0 + px;
-            float v = 0.f;
-            if (p < p_end && c < a.cx) {
+        {   // stage X[p + tap][ci0 .. ci0 + 16): thread = (pixel tid / 4, channel quad tid % 4)
+            const int px = tid >> 2, p = p0 + px;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p < p_end && sc < a.cx) {
                 const int Y = p / a.Wy, X = p - Y * a.Wy;
                 const int y = a.stride * Y - pad + ky, x = a.stride * X - pad + kx;
                 if (y >= 0 && y < a.Hx && x >= 0 && x < a.Wx) {
-                    int base = 0, s = 0;
-                    while (s < a.nx - 1 && c >= base + a.x[s].ch) { base += a.x[s].ch; ++s; }
-                    v = a.x[s].ptr[((size_t)y * a.Wx + x) * a.x[s].ch + (c - base)];
+                    const size_t pix = (size_t)y * a.Wx + x;
+                    if (x_vec) {
+                        v = ld4(a.x[sseg].ptr + pix * a.x[sseg].ch + (sc - sbase));
+                    } else {
+                        float e[4] = {0.f, 0.f, 0.f, 0.f};
+                        for (int k = 0; k < 4; ++k) {
+                            const int c = sc + k;
+                            if (c >= a.cx) break;
+                            int base = 0, sg = 0;
+                            while (sg < a.nx - 1 && c >= base + a.x[sg].ch) { base += a.x[sg].ch; ++sg; }
+                            e[k] = a.x[sg].ptr[pix * a.x[sg].ch + (c - base)];
+                        }
+                        v = make_float4(e[0], e[1], e[2], e[3]);
+                    }
                 }
             }
-            xs[px][it - px * WG_CI] = v;
+            *reinterpret_cast<float4*>(&xs[px][(tid & 3) * 4]) = v;
         }
-        for (int it = tid; it < WG_PX * WG_CO; it += WG_THREADS) {
-            const int px = it / WG_CO, c = it - px * WG_CO;
+        for (int it = tid; it < WG_PX * (cy4 >> 2); it += WG_THREADS) {  // stage dY[p][0 .. cy4)
+            const int px = it / (cy4 >> 2), q = it - px * (cy4 >> 2);
             const int p = p0 + px;
-            ds[px][c] = (p < p_end && c < a.cy) ? a.dy[(size_t)p * a.cy + c] : 0.f;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p < p_end) {
+                const float* dp = a.dy + (size_t)p * a.cy + q * 4;
+                if (dy_vec) v = ld4(dp);
+                else {
+                    float e[4] = {0.f, 0.f, 0.f, 0.f};
+                    for (int k = 0; k < 4 && q * 4 + k < a.cy; ++k) e[k] = dp[k];
+                    v = make_float4(e[0], e[1], e[2], e[3]);
+                }
+            }
+            *reinterpret_cast<float4*>(&ds[px][q * 4]) = v;
         }
         __syncthreads();
-        if (co4 * 4 < a.cy) {
+        if (active) {
 #pragma unroll 4
-            for (int px = 0; px < WG_PX; ++px) {
+            for (int j = 0; j < WG_PX / 4; ++j) {
+                const int px = pg * (WG_PX / 4) + j;
                 const float4 xv = *reinterpret_cast<const float4*>(&xs[px][ci4 * 4]);
                 const float4 dv = *reinterpret_cast<const float4*>(&ds[px][co4 * 4]);
                 const float xa[4] = {xv.x, xv.y, xv.z, xv.w}, da[4] = {dv.x, dv.y, dv.z, dv.w};
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(xa[i], da[j], acc[i][j]);
+                    for (int k = 0; k < 4; ++k) acc[i][k] = fmaf(xa[i], da[k], acc[i][k]);
                 if (want_bias) {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) bsum[j] += da[j];
+                    for (int k = 0; k < 4; ++k) bsum[k] += da[k];
                 }
             }
         }
         __syncthreads();
     }
-    if (co4 * 4 < a.cy) {
+    if (active) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const int ci = ci0 + ci4 * 4 + i;
             if (ci >= a.cx) continue;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int co = co4 * 4 + j;
-                if (co < a.cy) atomicAdd(a.dw + ((size_t)tap * a.cx + ci) * a.cy + co, acc[i][j]);
+            for (int k = 0; k < 4; ++k) {
+                const int co = co4 * 4 + k;
+                if (co < a.cy) atomicAdd(a.dw + ((size_t)tap * a.cx + ci) * a.cy + co, acc[i][k]);
             }
         }
         if (want_bias) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-                if (co4 * 4 + j < a.cy) atomicAdd(a.db + co4 * 4 + j, bsum[j]);
+            for (int k = 0; k < 4; ++k)
+                if (co4 * 4 + k < a.cy) atomicAdd(a.db + co4 * 4 + k, bsum[k]);
         }
     }
 }
@@ -425,13 +458,21 @@ extern "C" int aarmvs_conv_nhwc(const aarmvs_seg* in, int nin, int Hin, int Win,
     AARMVS_CHECK_ARG(ci == cin && co == cout);
     a.nin = nin; a.nout = nout; a.Hin = Hin; a.Win = Win; a.Hout = Hout; a.Wout = Wout; a.cin = cin; a.cout = cout;
     a.ks = ksize; a.stride = stride; a.transposed = transposed ? 1 : 0; a.w = weight; a.bias = bias;
-    const int smem = ksize * ksize * cin * GC_CO * (int)sizeof(float);
+    const int bx = grid_for((size_t)Hout * Wout, GC_THREADS);
+    const int co_tile = (bx * ((cout + 15) / 16) < 148 * 3 && cout > 8) ? 8 : 16;      // small maps: more, narrower CTAs
+    const int smem = ksize * ksize * cin * co_tile * (int)sizeof(float);
     AARMVS_CHECK_ARG(smem <= 200 * 1024);
-    static unsigned long long smem_ok = 0;
-    if (smem > 48 * 1024)
-        if (cudaError_t e = ensure_dyn_smem(conv_nhwc_kernel, 200 * 1024, smem_ok)) return (int)e;
-    dim3 grid(grid_for((size_t)Hout * Wout, GC_THREADS), (cout + GC_CO - 1) / GC_CO);
-    conv_nhwc_kernel<<<grid, GC_THREADS, smem, (cudaStream_t)stream>>>(a);
+    static unsigned long long smem_ok8 = 0, smem_ok16 = 0;
+    dim3 grid(bx, (cout + co_tile - 1) / co_tile);
+    if (co_tile == 8) {
+        if (smem > 48 * 1024)
+            if (cudaError_t e = ensure_dyn_smem(conv_nhwc_kernel<8>, 200 * 1024, smem_ok8)) return (int)e;
+        conv_nhwc_kernel<8><<<grid, GC_THREADS, smem, (cudaStream_t)stream>>>(a);
+    } else {
+        if (smem > 48 * 1024)
+            if (cudaError_t e = ensure_dyn_smem(conv_nhwc_kernel<16>, 200 * 1024, smem_ok16)) return (int)e;
+        conv_nhwc_kernel<16><<<grid, GC_THREADS, smem, (cudaStream_t)stream>>>(a);
+    }
     AARMVS_LAUNCH_RESULT();
 }
 
@@ -446,9 +487,11 @@ extern "C" int aarmvs_conv_bwd_weight(const aarmvs_seg* x, int nx, int Hx, int W
     a.nx = nx; a.dy = dy; a.Hx = Hx; a.Wx = Wx; a.Hy = Hy; a.Wy = Wy; a.cx = cx; a.cy = cy; a.ks = ksize; a.stride = stride;
     a.dw = dweight; a.db = dbias;
     const int P = Hy * Wy;
-    int chunks = (P + 511) / 512;                                  // >= 512 pixels per block: few atomics per weight
+    // pixels per block: enough blocks to fill the machine a few times over (the kernel is short), few enough that the fp32
+    // atomics at the end stay a small part of it
     const int per_chunk = ksize * ksize * ((cx + WG_CI - 1) / WG_CI);
-    while (chunks > 1 && chunks * per_chunk > 148 * 32) chunks = (chunks + 1) / 2;
+    int chunks = (P + 4 * WG_PX - 1) / (4 * WG_PX);
+    while (chunks > 1 && chunks * per_chunk > 148 * 16) chunks = (chunks + 1) / 2;
     a.chunk = ((P + chunks - 1) / chunks + WG_PX - 1) / WG_PX * WG_PX;
     chunks = (P + a.chunk - 1) / a.chunk;
     dim3 grid(chunks, ksize * ksize, (cx + WG_CI - 1) / WG_CI);
