@@ -150,6 +150,10 @@ class Backward:
             b[cn] = [b["rec2"][r][lay[i][1]:lay[i][1] + lay[i][2]].view(Pi[i], _HID[i]) for i in range(5)]
         b["dcr"] = torch.zeros(P, **f32)
         b["plane"] = torch.zeros(1, device=dev, dtype=torch.int32)
+        b["feat"] = torch.empty(N, P, 32, **f32)
+        b["cams"] = torch.empty(S, 12, **f32)
+        b["depths"] = torch.empty(0, **f32)
+        b["graph"] = None
         self._ws = b
         return b
 
@@ -196,36 +200,41 @@ class Backward:
         b["dfeat"].zero_()
         dcost_volume = dcost_volume.contiguous()
         state = saved["state"]
-        graph = None
+        # per-sample constants go to fixed buffers as well, so that ONE captured graph serves every sample of the step
+        b["feat"].copy_(saved["feat"])
+        b["cams"].copy_(saved["cams"])
+        if b["depths"].numel() != D:
+            b["depths"], b["graph"] = torch.empty(D, device=self.dev, dtype=torch.float32), None
+        b["depths"].copy_(saved["depths"])
         for d in range(D - 1, -1, -1):
             b["rec2"].copy_(state[d:d + 2])                   # [0] = state entering plane d, [1] = state after it
             b["dcr"].copy_(dcost_volume[d])
             b["plane"].fill_(d)
-            if d == D - 1 or not self.use_graph:
-                self._plane(saved, b)                         # eager: also sets the kernels' launch attributes
-                if self.use_graph and D > 1:
-                    torch.cuda.synchronize(self.dev)
-                    graph = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(graph):
-                        self._plane(saved, b)
-            else:
-                graph.replay()
+            if b["graph"] is not None:
+                b["graph"].replay()
+                continue
+            self._plane(H, W, N, b)                           # eager: also sets the kernels' launch attributes
+            if self.use_graph:
+                torch.cuda.synchronize(self.dev)
+                b["graph"] = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(b["graph"]):
+                    self._plane(H, W, N, b)
         for v in range(N):
             self.featnet(saved["imgs"][v], b["dfeat"][v], H, W)
 
-    def _plane(self, saved, b):
-        """Backward of the plane whose index is in b["plane"], whose states are in b["rec2"] and whose dL/dcost_reg is b["dcr"]."""
+    def _plane(self, H, W, N, b):
+        """Backward of the plane whose index is in b["plane"], whose states are in b["rec2"] and whose dL/dcost_reg is b["dcr"]
+        (features, cameras and depth hypotheses of the sample in b["feat"], b["cams"], b["depths"])."""
         lib, eng, w, bw, g = self.lib, self.eng, self.w, self.bw, self.g
-        H, W, N = saved["H"], saved["W"], saved["N"]
         P, S = H * W, N - 1
         H2, W2, H4, W4 = H // 2, W // 2, H // 4, W // 4
         hw = [(H // s, W // s) for s in _SCALE]
         st = self._st()
-        feat = saved["feat"]
+        feat = b["feat"]
         ref, src = _ptr(feat), _ptr(feat, P * 32)
         ac = int(eng.align_corners)
         dptr = _ptr(b["plane"])
-        depths, cams = _ptr(saved["depths"]), _ptr(saved["cams"])
+        depths, cams = _ptr(b["depths"]), _ptr(b["cams"])
         hp, cp, h, c = b["hp"], b["cp"], b["h"], b["c"]
         # ---------------- recompute the plane's forward intermediates
         b["stats"].zero_()

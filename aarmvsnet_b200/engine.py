@@ -131,7 +131,8 @@ class Engine:
         w = {k: (v.to(device) if torch.is_tensor(v) else tuple(t.to(device) for t in v) if isinstance(v, tuple) else v)
              for k, v in w.items()}
         self.w, self._wkey = w, key
-        self._ws.clear()                 # graphs bake host-side parameters: drop them with the old weights
+        for ws in self._ws.values():     # captured graphs bake host-side parameters: drop them with the old weights (the
+            ws["graph"] = None           # buffers stay: a training loop changes the weights every step)
         return w
 
     # ------------------------------------------------------------------------------------------ workspace
