@@ -117,3 +117,25 @@ def test_aggregate_plane_and_omega(ops_dtu, sd_dtu, model, model_fma, hw, math):
         c = (orc.homo_warp(feats[v + 1], pm[:, v + 1], pm[:, 0], dv) - feats[0]).pow(2)
         torch.testing.assert_close(rew[v].cpu(), orc.omega(c, sd_dtu)[0, 0], rtol=1e-4, atol=2e-5)
     torch.testing.assert_close(got.cpu(), want[0], rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.gpu
+def test_same_process_drives_two_devices(sd_dtu):
+    """One process, two GPUs: launch attributes (dynamic shared memory opt-in) and the SM count are per-device properties
+    (a process-wide flag made every large-smem conv fail on the second device)."""
+    import aarmvsnet_b200 as aa
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two CUDA devices")
+    s = aa.synth.make_sample(48, 64, 3, 6, seed=5)
+    outs = []
+    for dev in ("cuda:0", "cuda:1"):
+        m = aa.EMVSNet(32, image_scale=1.0, max_h=48, max_w=64, return_depth=True, cell_math="tc" if dev.endswith("0") else "fma")
+        m.load_state_dict(sd_dtu, strict=True)
+        m = m.to(dev).eval()
+        o = m(s["imgs"].to(dev), s["proj_matrices"].to(dev), s["depth_values"].to(dev))
+        outs.append(o["index"].cpu())
+        m2 = aa.EMVSNet(32, image_scale=1.0, max_h=48, max_w=64, return_depth=True, cell_math="fma" if dev.endswith("0") else "tc")
+        m2.load_state_dict(sd_dtu, strict=True)
+        outs.append(m2.to(dev).eval()(s["imgs"].to(dev), s["proj_matrices"].to(dev), s["depth_values"].to(dev))["index"].cpu())
+    for o in outs[1:]:
+        assert (o == outs[0]).float().mean().item() >= 0.999
