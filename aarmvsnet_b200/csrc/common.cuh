@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #define AARMVS_OK 0
 #define AARMVS_ERR_ARG 1000001   // bad argument (shape / alignment / null pointer)
@@ -27,6 +28,21 @@ static inline cudaError_t ensure_dyn_smem(K kern, int bytes, unsigned long long&
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     if (e == cudaSuccess && dev < 64) mask |= 1ull << dev;
     return e;
+}
+
+// Launch with programmatic stream serialization (see tc_common.cuh: pdl_wait).  AARMVS_NO_PDL=1 in the environment falls back
+// to a plain launch (A/B measurements).
+template <class Arg>
+static inline cudaError_t launch_pdl(void (*kern)(Arg), dim3 grid, dim3 block, size_t smem, cudaStream_t st, const Arg& arg) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    const char* off = getenv("AARMVS_NO_PDL");
+    cfg.attrs = attr;
+    cfg.numAttrs = (off && off[0] == '1') ? 0 : 1;
+    return cudaLaunchKernelEx(&cfg, kern, arg);
 }
 
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }

@@ -550,13 +550,18 @@ extern "C" int aarmvs_head_wta(const aarmvs_conv_src* h4, int H, int W, const fl
     AARMVS_LAUNCH_RESULT();
 }
 
-__global__ void next_plane_kernel(int* d_dev, double* sums, int nzero) {
+struct NextPlaneArgs { int* d_dev; double* sums; int nzero; };
+__global__ void next_plane_kernel(const NextPlaneArgs a) {
+    int* d_dev = a.d_dev; double* sums = a.sums; const int nzero = a.nzero;
+    asm volatile("griddepcontrol.wait;" ::: "memory");           // part of the per-plane PDL chain: the head kernel is complete
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     for (int i = threadIdx.x; i < nzero; i += blockDim.x) sums[i] = 0.0;
     if (threadIdx.x == 0 && d_dev) *d_dev += 1;
 }
 
 extern "C" int aarmvs_next_plane(int* d_dev, double* sums, int nzero, void* stream) {
     AARMVS_CHECK_ARG(nzero >= 0 && (nzero == 0 || sums));
-    next_plane_kernel<<<1, 128, 0, (cudaStream_t)stream>>>(d_dev, sums, nzero);
+    NextPlaneArgs a = {d_dev, sums, nzero};
+    if (cudaError_t e = launch_pdl(next_plane_kernel, dim3(1), dim3(128), 0, (cudaStream_t)stream, a)) return (int)e;
     AARMVS_LAUNCH_RESULT();
 }

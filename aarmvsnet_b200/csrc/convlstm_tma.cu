@@ -132,12 +132,9 @@ __global__ void __launch_bounds__(N_THREADS, 1) convlstm_tma_kernel(const __grid
     __shared__ float s_bias[NG];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int d = plane_index(a.d_host, a.d_dev);
 
-    // ---- one-time setup: barriers, TMEM, zeroed stages where no TMA will ever write (h_{-1} = 0 at plane 0,
-    //      module.py:94-96; K padding of cell 4)
-    if (d == 0 || a.need_zero)
-        for (int i = tid; i < NST * C::A_STAGE / 16; i += N_THREADS) reinterpret_cast<uint4*>(sA)[i] = make_uint4(0u, 0u, 0u, 0u);
+    // ---- setup that reads nothing a predecessor kernel writes: under programmatic dependent launch it runs while the
+    //      previous kernel of the plane chain drains (barriers, TMEM, tensor-map prefetch, the weight bulk load)
     if (tid < NG) s_bias[tid] = a.bias[tid];
     if (tid == 0) {
         for (int s = 0; s < NST; ++s) { tc::mbar_init(&full_a[s], 1); tc::mbar_init(&empty_a[s], 1); }
@@ -146,10 +143,24 @@ __global__ void __launch_bounds__(N_THREADS, 1) convlstm_tma_kernel(const __grid
         tc::mbar_fence_init();
     }
     if (warp == MMA_WARP) tc::tmem_alloc<C::TMEM_COLS>(&tmem_base_s);
-    tc::fence_async_smem();                  // the zero fill went through the generic proxy
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
+    if (warp == TMA_WARP && lane == 0) {
+        for (int s = 0; s < a.nsrc; ++s) tc::tma_prefetch_desc(&a.map[s]);
+        tc::mbar_arrive_expect_tx(&w_bar, C::B_BYTES);
+        for (int off = 0; off < C::B_BYTES; off += 32768)
+            tc::bulk_load_1d(sB + off, reinterpret_cast<const unsigned char*>(a.weight) + off, min(32768, C::B_BYTES - off), &w_bar);
+    }
+    tc::pdl_wait();                          // the predecessor (and, transitively, everything before it) is complete from here on
+    tc::pdl_launch_dependents();
+    const int d = plane_index(a.d_host, a.d_dev);
+    // zeroed stages where no TMA will ever write (h_{-1} = 0 at plane 0, module.py:94-96; K padding of cell 4)
+    if (d == 0 || a.need_zero) {
+        for (int i = tid; i < NST * C::A_STAGE / 16; i += N_THREADS) reinterpret_cast<uint4*>(sA)[i] = make_uint4(0u, 0u, 0u, 0u);
+        tc::fence_async_smem();              // the zero fill went through the generic proxy
+        __syncthreads();
+    }
     const uint32_t tmem_base = tmem_base_s;
 
     const int tiles_x = (a.W + TCOL - 1) / TCOL, tiles_y = (a.H + TR - 1) / TR;
@@ -171,13 +182,6 @@ __global__ void __launch_bounds__(N_THREADS, 1) convlstm_tma_kernel(const __grid
                     cb += a.chunks[s];
                 }
             }
-        }
-        if (lane == 0) {
-            for (int s = 0; s < a.nsrc; ++s) tc::tma_prefetch_desc(&a.map[s]);
-            tc::mbar_arrive_expect_tx(&w_bar, C::B_BYTES);
-            for (int off = 0; off < C::B_BYTES; off += 32768)
-                tc::bulk_load_1d(sB + off, reinterpret_cast<const unsigned char*>(a.weight) + off,
-                                 min(32768, C::B_BYTES - off), &w_bar);
         }
         int it = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
@@ -407,7 +411,7 @@ int launch_cell(const CellArgs& a, cudaStream_t stream) {
     const int ntiles = ((a.W + TCOL - 1) / TCOL) * ((a.H + TR - 1) / TR);
     const int sms = aarmvs_sm_count();
     if (sms <= 0) return AARMVS_ERR_ARG;
-    kern<<<ntiles < sms ? ntiles : sms, N_THREADS, C::SMEM, stream>>>(a);
+    if (cudaError_t e = launch_pdl(kern, dim3(ntiles < sms ? ntiles : sms), dim3(N_THREADS), C::SMEM, stream, a)) return (int)e;
     AARMVS_LAUNCH_RESULT();
 }
 

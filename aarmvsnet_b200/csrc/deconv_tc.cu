@@ -63,20 +63,9 @@ __global__ void __launch_bounds__(N_THREADS, 1) deconv_tc_kernel(const __grid_co
     __shared__ float s_scale[16], s_shift[16];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int d = plane_index(a.d_host, a.d_dev);
     const bool apply = a.out_planes != nullptr;
 
-    if (tid < 16) {
-        float sc = 1.f, sh = 0.f;
-        if (apply) {
-            float mean, rstd;
-            gn_mean_rstd(a.stats + (tid >> 3) * 2, a.count, mean, rstd);
-            sc = rstd * a.gamma[tid];
-            sh = a.beta[tid] - mean * sc;
-        }
-        s_scale[tid] = sc;
-        s_shift[tid] = sh;
-    }
+    // setup that reads nothing a predecessor writes (overlaps the previous kernel's drain under programmatic dependent launch)
     if (tid == 0) {
         for (int s = 0; s < NST; ++s) { tc::mbar_init(&full_a[s], 1); tc::mbar_init(&empty_a[s], 1); }
         for (int b = 0; b < 2; ++b) { tc::mbar_init(&tmem_full[b], 1); tc::mbar_init(&tmem_empty[b], N_EPI_WARPS * 32); }
@@ -87,6 +76,26 @@ __global__ void __launch_bounds__(N_THREADS, 1) deconv_tc_kernel(const __grid_co
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
+    if (warp == TMA_WARP && lane == 0) {
+        tc::tma_prefetch_desc(&a.map);
+        tc::mbar_arrive_expect_tx(&w_bar, B_BYTES);
+        tc::bulk_load_1d(sB, a.weight, B_BYTES, &w_bar);
+    }
+    tc::pdl_wait();
+    tc::pdl_launch_dependents();
+    const int d = plane_index(a.d_host, a.d_dev);
+    if (tid < 16) {          // GroupNorm scale / shift from the sums pass 1 (the predecessor) accumulated
+        float sc = 1.f, sh = 0.f;
+        if (apply) {
+            float mean, rstd;
+            gn_mean_rstd(a.stats + (tid >> 3) * 2, a.count, mean, rstd);
+            sc = rstd * a.gamma[tid];
+            sh = a.beta[tid] - mean * sc;
+        }
+        s_scale[tid] = sc;
+        s_shift[tid] = sh;
+    }
+    __syncthreads();
     const uint32_t tmem_base = tmem_base_s;
 
     const int tiles_x = (a.Win + TCOL - 1) / TCOL, tiles_y = (a.Hin + TR - 1) / TR;
@@ -94,11 +103,6 @@ __global__ void __launch_bounds__(N_THREADS, 1) deconv_tc_kernel(const __grid_co
 
     if (warp == TMA_WARP) {
         const int sel = a.pp_phase < 0 ? 0 : ((d + a.pp_phase) & 1);
-        if (lane == 0) {
-            tc::tma_prefetch_desc(&a.map);
-            tc::mbar_arrive_expect_tx(&w_bar, B_BYTES);
-            tc::bulk_load_1d(sB, a.weight, B_BYTES, &w_bar);
-        }
         int it = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
             const int st = it % NST;
@@ -228,6 +232,7 @@ extern "C" int aarmvs_deconv2x_tc(const aarmvs_plane_src* in, int Hin, int Win, 
     const int ntiles = ((Win + TCOL - 1) / TCOL) * ((Hin + TR - 1) / TR);
     const int sms = aarmvs_sm_count();
     if (sms <= 0) return AARMVS_ERR_ARG;
-    deconv_tc_kernel<<<ntiles < sms ? ntiles : sms, N_THREADS, SMEM, (cudaStream_t)stream>>>(a);
+    if (cudaError_t e = launch_pdl(deconv_tc_kernel, dim3(ntiles < sms ? ntiles : sms), dim3(N_THREADS), SMEM, (cudaStream_t)stream, a))
+        return (int)e;
     AARMVS_LAUNCH_RESULT();
 }

@@ -54,7 +54,7 @@ __global__ void __launch_bounds__(N_THREADS, CTAS_PER_SM) head_tc_kernel(const _
     __shared__ uint32_t tmem_base_s;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int d = plane_index(a.d_host, a.d_dev);
+    // setup that reads nothing a predecessor writes (overlaps cell 4's drain under programmatic dependent launch)
     if (tid == 0) {
         for (int s = 0; s < NST; ++s) { tc::mbar_init(&full_a[s], 1); tc::mbar_init(&empty_a[s], 1); }
         for (int b = 0; b < 2; ++b) { tc::mbar_init(&tmem_full[b], 1); tc::mbar_init(&tmem_empty[b], N_EPI_WARPS * 32); }
@@ -65,17 +65,20 @@ __global__ void __launch_bounds__(N_THREADS, CTAS_PER_SM) head_tc_kernel(const _
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
+    if (warp == TMA_WARP && lane == 0) {
+        tc::tma_prefetch_desc(&a.map);
+        tc::mbar_arrive_expect_tx(&w_bar, B_BYTES);
+        tc::bulk_load_1d(sB, a.weight, B_BYTES, &w_bar);
+    }
+    tc::pdl_wait();
+    tc::pdl_launch_dependents();
+    const int d = plane_index(a.d_host, a.d_dev);
     const uint32_t tmem_base = tmem_base_s;
     const int tiles_x = (a.W + TCOL - 1) / TCOL, tiles_y = (a.H + TR - 1) / TR;
     const int ntiles = tiles_x * tiles_y;
 
     if (warp == TMA_WARP) {
         const int sel = d & 1;                                   // h4 of the CURRENT plane
-        if (lane == 0) {
-            tc::tma_prefetch_desc(&a.map);
-            tc::mbar_arrive_expect_tx(&w_bar, B_BYTES);
-            tc::bulk_load_1d(sB, a.weight, B_BYTES, &w_bar);
-        }
         int it = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
             const int st = it % NST;
@@ -204,6 +207,6 @@ extern "C" int aarmvs_head_wta_tc(const void* h4_planes, int H, int W, const voi
     const int sms = aarmvs_sm_count();
     if (sms <= 0) return AARMVS_ERR_ARG;
     const int grid = ntiles < sms * CTAS_PER_SM ? ntiles : sms * CTAS_PER_SM;
-    head_tc_kernel<<<grid, N_THREADS, SMEM, (cudaStream_t)stream>>>(a);
+    if (cudaError_t e = launch_pdl(head_tc_kernel, dim3(grid), dim3(N_THREADS), SMEM, (cudaStream_t)stream, a)) return (int)e;
     AARMVS_LAUNCH_RESULT();
 }

@@ -13,6 +13,15 @@
 
 namespace tc {
 
+// Programmatic dependent launch (PTX griddepcontrol).  The kernels of the per-plane recurrence chain are launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization (common.cuh: launch_pdl): a kernel's CTAs may become resident while its
+// predecessor drains, run the part of their prologue that touches nothing a predecessor writes (barrier init, TMEM
+// allocation, tensor-map prefetch, the bulk load of the immutable weights), and only then wait for the predecessor's
+// completion (and memory flush).  launch_dependents is issued right AFTER the wait, so at most two kernels of the chain
+// overlap and "complete" is transitive.  Without the launch attribute both instructions are no-ops.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {

@@ -220,7 +220,11 @@ int aarmvs_head_wta(const aarmvs_conv_src* h4, int H, int W, const float* weight
  * for the tap pairs (0,1) (2,3) (4,5) (6,7) (8,-) of tap = ky * 3 + kx; other arguments as aarmvs_head_wta.
  * Optional fused training loss (mvsnet_cls_loss, models/drmvsnet.py:347-381, without the [D][H][W] probability volume):
  * gt_index [H*W] = hypothesis nearest to the ground truth (0 where gt_mask is 0), gt_mask [H*W], gt_cost [H*W] state;
- * at the last plane *loss_sum += sum_p gt_mask[p] * (log(sum_d exp(cost_d[p])) - cost_gt[p]).  All four NULL: no loss. */
+ * at the last plane *loss_sum += sum_p gt_mask[p] * (log(sum_d exp(cost_d[p])) - cost_gt[p]).  All four NULL: no loss.
+ * Range: the exp-sum is the winner-take-all update's own (drmvsnet.py:324 takes exp(cost) without subtracting a maximum), so
+ * like the reference's test phase it overflows for a regularised cost above ~88; the shipped weights produce costs in
+ * [-41, -17].  The differentiable training path (EMVSNet.forward under autograd, aarmvs_loss_grad) goes through
+ * a max-subtracted softmax and has no such bound.  Likewise the fp16 (hi, lo) operand split assumes |x| < 65 504. */
 int aarmvs_head_wta_tc(const void* h4_planes, int H, int W, const void* weight_f16, const float* bias_host,
                        const float* depth_values, int num_depth, int d_host, const int* d_dev, float* max_prob,
                        float* depth_map, float* exp_sum, int* index_map, float* conf, float* cost_volume,
