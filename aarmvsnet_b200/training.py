@@ -11,6 +11,7 @@ The evidential loss of the fork (train.py:304) is out of scope
 import ctypes
 
 import torch
+import torch.distributed as dist
 
 from . import capi
 from .engine import _ptr
@@ -60,6 +61,18 @@ class FlatAdam:
             self.model._engine._wkey = None
 
 
+def average_gradients(flat_grad, group=None):
+    """Data-parallel training over the GPUs of one box (one process per GPU, each with its own batch): ONE all-reduce of the
+    flat gradient buffer (187 203 floats = 0.75 MB; NCCL over NVLink, gloo in the CPU test) replaces the per-parameter
+    reductions of the nn.DataParallel the reference leaves commented out (train.py:129-150,173).  No-op for a single process."""
+    if dist.is_available() and dist.is_initialized():
+        world = dist.get_world_size(group)
+        if world > 1:
+            dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM, group=group)
+            flat_grad.div_(world)
+    return flat_grad
+
+
 class TrainStep:
     """train.py:288-307 for one batch: returns the loss (device scalar) and the winner-take-all depth map."""
 
@@ -72,5 +85,6 @@ class TrainStep:
         prob, _, _ = self.model(imgs, proj_matrices, depth_values)
         loss, depth = mvsnet_cls_loss(prob, depth_gt, mask, depth_values)
         loss.backward()
+        average_gradients(self.opt.grad)
         self.opt.step()
         return loss.detach(), depth

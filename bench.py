@@ -534,7 +534,7 @@ def run_train(args):
 
     ms_total, clocks = timed(step_resident)
     ms_e2e, _ = timed(step_e2e)
-    if world > 1:            # data-parallel replicas: the gradient all-reduce of train.py's (unused) DataParallel is not on this path
+    if world > 1:            # (data-parallel: TrainStep all-reduces the flat gradient buffer inside every timed step)
         dist.barrier()
     if rank == 0:
         pk = peaks()

@@ -58,3 +58,28 @@ def test_scan_gather_world2_gloo(n_views):
         out = mgr.dict()
         mp.spawn(_worker, args=(world, port, n_views, out), nprocs=world, join=True)
         assert dict(out) == {0: True, 1: True}
+
+
+def _grad_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from aarmvsnet_b200.training import average_gradients
+    flat = torch.arange(10.0) * (rank + 1)                  # rank 0: g, rank 1: 2g -> mean 1.5 g
+    average_gradients(flat)
+    out[rank] = bool(torch.allclose(flat, torch.arange(10.0) * 1.5))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_data_parallel_gradient_average_world2_gloo():
+    """The one collective of the data-parallel training step (aarmvsnet_b200.training.average_gradients): an all-reduce of
+    the flat gradient buffer, here over gloo with two CPU processes."""
+    world = 2
+    port = 31500 + (os.getpid() % 2000)
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_grad_worker, args=(world, port, out), nprocs=world, join=True)
+        assert dict(out) == {0: True, 1: True}
+    from aarmvsnet_b200.training import average_gradients
+    t = torch.ones(3)
+    assert average_gradients(t) is t and torch.equal(t, torch.ones(3))      # single process: untouched
