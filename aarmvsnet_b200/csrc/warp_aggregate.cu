@@ -203,7 +203,7 @@ aggregate_kernel(const float* __restrict__ ref, const float* __restrict__ src, s
                  const float* __restrict__ cams, const __grid_constant__ OmegaTail q,
                  const float* __restrict__ depth_values, int d_host, const int* __restrict__ d_dev, int align_corners,
                  const float* __restrict__ t0, const double* __restrict__ stats, float* __restrict__ cost,
-                 float* __restrict__ reweight_out) {
+                 __half* __restrict__ cost_planes, float* __restrict__ reweight_out) {
     __shared__ OmegaNorm norms_all[AARMVS_MAX_PLANES * AARMVS_MAX_SRC];
     __shared__ float scam[AARMVS_MAX_SRC * 12];
     for (int i = threadIdx.x; i < S * 12; i += blockDim.x) scam[i] = cams[i];
@@ -293,9 +293,22 @@ aggregate_kernel(const float* __restrict__ ref, const float* __restrict__ src, s
                     }
                 }
             }
-            if (valid)
-                st4(cost + ((size_t)k * P + p) * 32 + sub * 4, make_float4(-__fdiv_rn(acc.x, s_den), -__fdiv_rn(acc.y, s_den),
-                                                                           -__fdiv_rn(acc.z, s_den), -__fdiv_rn(acc.w, s_den)));
+            const float4 r = make_float4(-__fdiv_rn(acc.x, s_den), -__fdiv_rn(acc.y, s_den), -__fdiv_rn(acc.z, s_den), -__fdiv_rn(acc.w, s_den));
+            if (cost_planes) {       // fp16 (hi, lo) operand planes [K][2][4 chunks][P][8] of ConvLSTM cell 0, as aggregate_stream_kernel
+                uint2 hi, lo;
+                tc::split4_f16(r, hi, lo);
+                const bool odd = sub & 1;
+                const uint2 give = odd ? hi : lo;
+                uint2 got;
+                got.x = __shfl_xor_sync(0xffffffffu, give.x, 1);
+                got.y = __shfl_xor_sync(0xffffffffu, give.y, 1);
+                if (valid) {
+                    const size_t off = (((size_t)k * 8 + (odd ? 4 : 0) + (sub >> 1)) * P + p) * 8;
+                    *reinterpret_cast<uint4*>(cost_planes + off) = odd ? make_uint4(got.x, got.y, lo.x, lo.y) : make_uint4(hi.x, hi.y, got.x, got.y);
+                }
+            } else if (valid) {
+                st4(cost + ((size_t)k * P + p) * 32 + sub * 4, r);
+            }
             }
         }
     }
@@ -540,7 +553,7 @@ extern "C" int aarmvs_aggregate(const float* ref, const float* src, size_t view_
                                 const int* d_dev, int planes, int align_corners, const float* t0, const double* stats,
                                 const float* costv, float* cost, void* cost_planes, float* reweight_out, void* stream) {
     AARMVS_CHECK_ARG(t0 && stats && tail_host && H > 0 && W > 0);
-    AARMVS_CHECK_ARG(cost_planes ? (costv && ((uintptr_t)cost_planes & 15) == 0) : cost != nullptr);
+    AARMVS_CHECK_ARG(cost_planes ? ((uintptr_t)cost_planes & 15) == 0 : cost != nullptr);
     AARMVS_CHECK_ARG(S >= 1 && S <= AARMVS_MAX_SRC && planes >= 1 && planes <= AARMVS_MAX_PLANES);
     OmegaTail q;
     fill_tail(q, tail_host);
@@ -557,6 +570,6 @@ extern "C" int aarmvs_aggregate(const float* ref, const float* src, size_t view_
     const int ntiles = ((W + AG_TW - 1) / AG_TW) * ((H + AG_TH - 1) / AG_TH);
     const int blocks = ntiles < 148 * AGG_MINB ? ntiles : 148 * AGG_MINB;
     aggregate_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(ref, src, view_stride, H, W, S, planes, cams, q, depth_values, d_host,
-                                                              d_dev, align_corners, t0, stats, cost, reweight_out);
+                                                              d_dev, align_corners, t0, stats, cost, (__half*)cost_planes, reweight_out);
     AARMVS_LAUNCH_RESULT();
 }

@@ -159,7 +159,7 @@ class Engine:
         tc = self.cell_math == "tc"
         # (warp - ref)^2 kept by pass A so that pass D streams instead of gathering again (tensor-core path only)
         ws["costv"] = torch.empty(K, S, P, 32, **f32) if tc and self.keep_costv else None
-        ws["cost"] = torch.empty(K, P, 32, **f32) if ws["costv"] is None else None
+        ws["cost"] = torch.empty(K, P, 32, **f32) if not tc else None
         if tc:
             # everything the cells read is kept as fp16 (hi, lo) operand planes [2][C/8][H][W][8] (include/aarmvs.h):
             # cost (pass D), h ping-pong pairs and max-pooled h (cell epilogues), GroupNorm+ReLU'd deconv outputs
@@ -315,15 +315,12 @@ class Engine:
                        "aarmvs_omega_stats")
         mark("omega_stats")
         tc = self.cell_math == "tc"
-        # tensor-core cells: pass D writes the cost straight into cell 0's operand planes
-        direct = tc and costv is not None
+        # tensor-core cells: pass D (streaming or gathering) writes the cost straight into cell 0's operand planes
+        direct = tc
         capi.check(lib.aarmvs_aggregate(ref, src, P * 32, H, W, S, _ptr(ws["cams"]), w["tail_host"], _ptr(ws["depths"]), 0,
                                         dptr, nplanes, ac, _ptr(ws["t0"]), _ptr(ps), costv,
                                         None if direct else _ptr(ws["cost"]), _ptr(ws["costp"]) if direct else None, None,
                                         stream), "aarmvs_aggregate")
-        if tc and not direct:
-            for k in range(nplanes):
-                self.split_planes(_src(ws["cost"][k], 32), H, W, ws["costp"][k], stream)
         mark("aggregate")
         h, c = ws["h"], ws["c"]
 

@@ -219,7 +219,8 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     H, W, N, D, ckpt, mode = WORKLOADS[args.workload]
-    model = aa.EMVSNet(disparity_level=32, image_scale=1.0, max_h=H, max_w=W, return_depth=True, plane_batch=args.plane_batch)
+    model = aa.EMVSNet(disparity_level=32, image_scale=1.0, max_h=H, max_w=W, return_depth=True, plane_batch=args.plane_batch,
+                       keep_costv=not args.no_costv)
     model.load_state_dict(load_sd(ckpt), strict=True)
     model = model.to(dev).eval()
     eng = model._engine
@@ -694,6 +695,7 @@ def main():
     ap.add_argument("--scan-views", type=int, default=49, help="cfg3: reference views of the synthetic scan")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--plane-batch", type=int, default=8, help="depth planes per launch of passes A-D (1..16)")
+    ap.add_argument("--no-costv", action="store_true", help="A/B: pass D gathers again instead of streaming pass A's stored per-view cost")
     args = ap.parse_args()
     if args.workload == "cfg5":
         return run_train(args)

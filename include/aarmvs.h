@@ -131,8 +131,8 @@ int aarmvs_omega_stats(int stage, const float* t0, int H, int W, int S, int plan
 /* Pass D: cost[p][c] = -(sum_v (omega_v(p) + 1) * (warp_v - ref)^2) / S  (models/drmvsnet.py:311-319), the input
  * of the recurrent regulariser.  costv: NULL = gather again; else pass A's costv_out, read back as a pure stream (ref, src,
  * cams, depth_values are then unused).  reweight_out: optional omega maps (operator seam / tests), may be NULL.
- * cost_planes (needs costv): write the result as fp16 (hi, lo) operand planes [planes][2][4][H][W][8] (see
- * aarmvs_plane_src) instead of fp32 `cost`, which may then be NULL. */
+ * cost_planes: write the result as fp16 (hi, lo) operand planes [planes][2][4][H][W][8] (see aarmvs_plane_src) instead of
+ * fp32 `cost`, which may then be NULL. */
 int aarmvs_aggregate(const float* ref, const float* src, size_t view_stride, int H, int W, int S, const float* cams,
                      const float* tail_host, const float* depth_values, int d_host, const int* d_dev, int planes,
                      int align_corners, const float* t0, const double* stats, const float* costv, float* cost,
