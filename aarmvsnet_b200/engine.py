@@ -58,11 +58,16 @@ class Engine:
 
     MAX_WORKSPACES = 2        # per-shape workspaces (and their captured graphs) kept alive; least recently used is dropped
 
-    def __init__(self, module, align_corners=False, use_graph=True, cell_math="tc", plane_batch=8, keep_costv=True):
+    def __init__(self, module, align_corners=False, use_graph=True, cell_math="tc", plane_batch=8, keep_costv=False):
         # cell_math "fma" (fp32 CUDA-core kernels) is a precision reference for the tests, not a product path
         if cell_math not in ("tc", "fma"):
             raise ValueError("cell_math must be 'tc' (tcgen05, split-fp16 operands) or 'fma' (fp32 CUDA cores)")
         self.cell_math = cell_math
+        # keep_costv=True: pass A also stores the per-view cost (warp - ref)^2 of a plane batch (11.6 GB at cfg2) and pass D streams
+        # it back instead of gathering a second time.  Round 1's default; same-box A/B in round 2 (profiles/r02l_*.json): 0.8712 /
+        # 0.8697 depth maps/s at 1 751 MHz under the power cap WITH the slab, 0.8736 / 0.8719 at 1 942 MHz WITHOUT it -- the
+        # second gather costs about what the 3 GB/plane of extra DRAM traffic costs in clock, so the default is the variant that
+        # never lets a per-view cost reach HBM (BASELINE.json north_star (2)).
         self.keep_costv = keep_costv
         if not 1 <= plane_batch <= 16:
             raise ValueError("plane_batch must be in 1..16")
@@ -157,7 +162,7 @@ class Engine:
         # plane sweep
         ws["t0"] = torch.empty(K, S, P, 4, **f32)
         tc = self.cell_math == "tc"
-        # (warp - ref)^2 kept by pass A so that pass D streams instead of gathering again (tensor-core path only)
+        # optional: (warp - ref)^2 kept by pass A so that pass D streams instead of gathering again (keep_costv, see __init__)
         ws["costv"] = torch.empty(K, S, P, 32, **f32) if tc and self.keep_costv else None
         ws["cost"] = torch.empty(K, P, 32, **f32) if not tc else None
         if tc:

@@ -135,7 +135,7 @@ class EMVSNet(nn.Module):
     a non-default max_h/max_w raises the same way the reference's torch.cat would."""
 
     def __init__(self, disparity_level=32, image_scale=0.25, max_h=960, max_w=480, return_depth=False,
-                 align_corners=False, use_graph=True, strict_size=False, cell_math="tc", plane_batch=8, keep_costv=True):
+                 align_corners=False, use_graph=True, strict_size=False, cell_math="tc", plane_batch=8, keep_costv=False):
         super().__init__()
         self.feature = FeatNet()
         self.cost_regularization = UNetConvLSTM()

@@ -36,6 +36,9 @@ WORKLOADS = {
     "tiny": (64, 96, 3, 8, "model_dtu_v2.ckpt", "uniform"),
 }
 FLOP_PER_PX_PLANE = 105264            # ConvLSTM U-Net, SURVEY.md §8d
+# dram__bytes_read.sum + dram__bytes_write.sum per 8-plane launch at cfg2 without the per-view cost slab (ncu --set full,
+# profiles/r02_stage_kernels.txt); None until captured
+TRAFFIC_NO_COSTV = {"cost_stem": None, "aggregate": None}
 CELL_FLOP_PER_PX = {"cell0": 55296, "cell1": 9216, "cell2": 2304, "cell3": 13824, "cell4": 23040}
 
 
@@ -220,7 +223,7 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     H, W, N, D, ckpt, mode = WORKLOADS[args.workload]
     model = aa.EMVSNet(disparity_level=32, image_scale=1.0, max_h=H, max_w=W, return_depth=True, plane_batch=args.plane_batch,
-                       keep_costv=not args.no_costv)
+                       keep_costv=args.costv)
     model.load_state_dict(load_sd(ckpt), strict=True)
     model = model.to(dev).eval()
     eng = model._engine
@@ -329,10 +332,11 @@ def run_ours(args):
         # the slowest kernel of the plane chain against ITS bound (algorithmic bytes / FLOPs as listed in DESIGN.md §3)
         kernels = {
             # pass A: the (warp-ref)^2 store for pass D (128*P*S, see `traffic`) is a design choice, not algorithmic work
-            "cost_stem": ("cost_stem_tc_kernel (pass A: gather + (warp-ref)^2 + omega stem conv on tcgen05, stores costv)", "hbm",
-                          128 * P * (S + 1) + 16 * P * S),
-            "aggregate": ("aggregate_stream_kernel (pass D: omega tail + weighted sum over the stored (warp-ref)^2)", "hbm",
-                          (128 + 16) * P * S + 128 * P),
+            "cost_stem": ("cost_stem_tc_kernel (pass A: gather + (warp-ref)^2 + omega stem conv on tcgen05" +
+                          (", stores costv)" if args.costv else ")"), "hbm", 128 * P * (S + 1) + 16 * P * S),
+            "aggregate": ("aggregate_stream_kernel (pass D: omega tail + weighted sum over the stored (warp-ref)^2)" if args.costv else
+                          "aggregate_kernel (pass D: second gather + omega tail + weighted sum -> cell 0's operand planes)", "hbm",
+                          ((128 + 16) * P * S + 128 * P) if args.costv else (128 * P * (S + 1) + 16 * P * S + 128 * P)),
             "omega_stats": ("omega_stats_kernel<2>+<3> (passes B, C)", "hbm", 2 * 16 * P * S),
             "head_wta": ("head_tc_kernel (conv_0 on tcgen05 + winner-take-all update)", "hbm", 44 * P),
         }
@@ -346,11 +350,14 @@ def run_ours(args):
         # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu captures (cfg2 only)
         traffic_cfg2 = {"cost_stem": 14.961e9, "aggregate": 15.028e9, "omega_stats": 2.92e9, "cell0": 0.721e9, "cell1": 0.114e9,
                         "cell2": 0.023e9, "cell3": 0.145e9, "cell4": 0.462e9, "head_wta": 0.082e9}   # profiles/r01x_pass_a, r01k_passes_AD, r01t_recurrence
+        if not args.costv:          # no per-view cost slab: profiles/r02_stage_kernels.txt
+            traffic_cfg2.update(TRAFFIC_NO_COSTV)
         roofline = {"kernel": kname, "bound": bound, "planes_per_launch": per_launch, "ms_per_launch": st[top] * per_launch,
                     "algorithmic_work_per_launch": work * per_launch,
                     "traffic": traffic_cfg2.get(top) if args.workload == "cfg2" else None,
-                    "traffic_source": "ncu --set full, profiles/r01x_pass_a.txt / r01k_passes_AD.txt / r01t_recurrence.txt (pass A includes the 11.6 GB "
-                                      "costv store per 8-plane launch that replaces pass D's second gather)"}
+                    "traffic_source": ("ncu --set full, profiles/r01x_pass_a.txt / r01k_passes_AD.txt / r01t_recurrence.txt (pass A includes the 11.6 GB "
+                                       "costv store per 8-plane launch that replaces pass D's second gather)") if args.costv else
+                                      "ncu --set full, profiles/r02_stage_kernels.txt (no per-view cost slab) / r01t_recurrence.txt"}
         if bound == "hbm":
             roofline.update({"achieved": work / (st[top] * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
                              "peak_source": pk["source"] + ", STREAM-style copy"})
@@ -695,7 +702,8 @@ def main():
     ap.add_argument("--scan-views", type=int, default=49, help="cfg3: reference views of the synthetic scan")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--plane-batch", type=int, default=8, help="depth planes per launch of passes A-D (1..16)")
-    ap.add_argument("--no-costv", action="store_true", help="A/B: pass D gathers again instead of streaming pass A's stored per-view cost")
+    ap.add_argument("--costv", action="store_true", help="A/B: pass A stores the per-view cost of a plane batch and pass D streams it "
+                                                         "(round 1's default) instead of gathering a second time")
     args = ap.parse_args()
     if args.workload == "cfg5":
         return run_train(args)

@@ -22,13 +22,13 @@ def _model(g, return_depth=True, **kw):
 
 
 @pytest.mark.parametrize("name", CASES)
-@pytest.mark.parametrize("use_graph,cell_math,plane_batch", [(True, "tc", 8), (False, "tc", 5), (True, "fma", 1), (True, "tc", 3), (True, "tc-gather", 4)])
+@pytest.mark.parametrize("use_graph,cell_math,plane_batch", [(True, "tc", 8), (False, "tc", 5), (True, "fma", 1), (True, "tc", 3), (True, "tc-costv", 4), (False, "tc-costv", 8)])
 def test_forward_matches_reference(name, use_graph, cell_math, plane_batch):
     """plane_batch 8 / 5 / 3 / 1 against D = 8 / 24 / 12: full batches, a partial last batch, and no batching."""
     g = load_golden(name)
-    # tc: pass A gathers and stores costv, pass D streams it; tc-gather: both passes gather (no costv buffer);
-    # fma: the fp32 CUDA-core kernels kept as a precision reference
-    m = _model(g, use_graph=use_graph, cell_math=cell_math.split("-")[0], plane_batch=plane_batch, keep_costv=cell_math != "tc-gather")
+    # tc: both passes A and D gather (no per-view cost reaches HBM: the default); tc-costv: pass A stores the per-view cost of
+    # the plane batch and pass D streams it; fma: the fp32 CUDA-core kernels kept as a precision reference
+    m = _model(g, use_graph=use_graph, cell_math=cell_math.split("-")[0], plane_batch=plane_batch, keep_costv=cell_math == "tc-costv")
     for _ in range(2):           # second call replays the captured plane graph
         out = m(g["imgs"].cuda(), g["proj_matrices"].cuda(), g["depth_values"].cuda())
     idx, want = out["index"].cpu().long(), g["index"].long()
