@@ -37,8 +37,8 @@ WORKLOADS = {
 }
 FLOP_PER_PX_PLANE = 105264            # ConvLSTM U-Net, SURVEY.md §8d
 # dram__bytes_read.sum + dram__bytes_write.sum per 8-plane launch at cfg2 without the per-view cost slab (ncu --set full,
-# profiles/r02_stage_kernels.txt); None until captured
-TRAFFIC_NO_COSTV = {"cost_stem": None, "aggregate": None}
+# profiles/r02_stage_kernels.txt: pass A 1.58 read + 1.41 written, pass D 3.46 + 1.91)
+TRAFFIC_NO_COSTV = {"cost_stem": 2.989e9, "aggregate": 5.368e9}
 CELL_FLOP_PER_PX = {"cell0": 55296, "cell1": 9216, "cell2": 2304, "cell3": 13824, "cell4": 23040}
 
 
