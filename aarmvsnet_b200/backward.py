@@ -215,10 +215,17 @@ class Backward:
                 continue
             self._plane(H, W, N, b)                           # eager: also sets the kernels' launch attributes
             if self.use_graph:
-                torch.cuda.synchronize(self.dev)
-                b["graph"] = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(b["graph"]):
+                # capture on a side stream with the raw API: torch.cuda.graph()'s context manager would also run gc.collect(),
+                # empty the caching allocator and synchronise the device on every optimisation step (the body allocates nothing)
+                side = torch.cuda.Stream(self.dev)
+                side.wait_stream(torch.cuda.current_stream(self.dev))
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.stream(side):
+                    graph.capture_begin()
                     self._plane(H, W, N, b)
+                    graph.capture_end()
+                torch.cuda.current_stream(self.dev).wait_stream(side)
+                b["graph"] = graph
         for v in range(N):
             self.featnet(saved["imgs"][v], b["dfeat"][v], H, W)
 

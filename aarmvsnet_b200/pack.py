@@ -31,21 +31,24 @@ def lstm_gates(w, b):
 def lstm_gates_f16_steps(w, b):
     """The same operand arranged by K STEP, [steps][2 chunks][2 (hi, lo)][4*hidden][8] fp16, as csrc/convlstm_tma.cu issues
     them: per tap one step per 16 input channels; when cin % 16 == 8 (cell 4: 40 channels) the last chunk of taps
-    (0,1) (2,3) (4,5) (6,7) (8,-) shares one step each (9 * 2 + 5 = 23 steps instead of 27 zero-padded ones)."""
+    (0,1) (2,3) (4,5) (6,7) (8,-) shares one step each (9 * 2 + 5 = 23 steps instead of 27 zero-padded ones).
+    (A handful of whole-tensor ops: a training loop re-packs after every optimizer step.)"""
     taps, bias = lstm_gates(w, b)                    # [9][cin][n] fp32
     k, cin, n = taps.shape
     full = cin // 16
 
-    def chunk(t, c0):                                # [2 (hi, lo)][n][8] of channels c0 .. c0+8 of tap t (zeros for t < 0)
-        blk = taps.new_zeros(8, n) if t < 0 else taps[t, c0:c0 + 8]
+    def split(blk):                                  # [..., 8 channels, n] fp32 -> [..., 2 (hi, lo), n, 8] fp16
         hi = blk.half()
         lo = (blk - hi.float()).half()
-        return torch.stack([hi.t(), lo.t()])
+        return torch.stack([hi, lo], -3).transpose(-1, -2)
 
-    steps = [torch.stack([chunk(t, 16 * s), chunk(t, 16 * s + 8)]) for t in range(k) for s in range(full)]
+    # regular steps: tap t, 16-channel group s -> chunks (2s, 2s + 1)
+    steps = split(taps[:, :16 * full].reshape(k, full, 2, 8, n)).reshape(k * full, 2, 2, n, 8)
     if cin % 16:
-        steps += [torch.stack([chunk(t, 16 * full), chunk(t + 1 if t + 1 < k else -1, 16 * full)]) for t in range(0, k, 2)]
-    return torch.stack(steps).contiguous(), bias
+        tail = taps.new_zeros(k + 1, 8, n)           # chunk `2 * full` of every tap, plus a zero tap to pair tap 8 with
+        tail[:k] = taps[:, 16 * full:16 * full + 8]
+        steps = torch.cat([steps, split(tail.reshape((k + 1) // 2, 2, 8, n))], 0)
+    return steps.contiguous(), bias
 
 
 def taps_f16(taps, n_pad=None):
