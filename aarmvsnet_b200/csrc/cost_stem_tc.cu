@@ -118,46 +118,9 @@ struct __align__(16) TapRec {
     unsigned pad0, pad1;
 };
 
-// Packed fp32 pairs (Blackwell FFMA2 / FMUL2 / FADD2): IEEE round-to-nearest per lane, i.e. bit-identical to the scalar
-// __fmaf_rn / __fmul_rn / __fsub_rn chains they replace, at half the issue slots.
-__device__ __forceinline__ uint64_t pk2(float lo, float hi) {
-    uint64_t r;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-    return r;
-}
-__device__ __forceinline__ void upk2(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
-__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
-    uint64_t r;
-    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-    return r;
-}
-__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
-    uint64_t r;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
-    return r;
-}
-__device__ __forceinline__ uint64_t sub2(uint64_t a, uint64_t b) {
-    uint64_t r;
-    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-    return r;
-}
-
 __device__ __forceinline__ float4 ldg4b(const unsigned char* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ void sts64(uint32_t addr, uint2 v) {
     asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(v.x), "r"(v.y) : "memory");
-}
-
-// Sample position of pixel (x, y) in one source view at one depth -> the four bilinear weights (0 for corners outside the
-// image) and the byte offset of the clamped north-west line | column step | row step << 1 (TapRec.w / TapRec.base).
-__device__ __forceinline__ void make_recipe(const float* cam, int x, int y, float depth, int W, int H, bool align_corners,
-                                            float4& wts, unsigned& base) {
-    float ix, iy;
-    sweep_position(cam, (float)x, (float)y, depth, W, H, align_corners, ix, iy);
-    const Taps t = make_taps(ix, iy, W, H);
-    wts = make_float4(t.o_nw >= 0 ? t.w_nw : 0.f, t.o_ne >= 0 ? t.w_ne : 0.f, t.o_sw >= 0 ? t.w_sw : 0.f, t.o_se >= 0 ? t.w_se : 0.f);
-    const int xw = min(max(t.xi, 0), W - 1), xe = min(max(t.xi + 1, 0), W - 1);
-    const int yn = min(max(t.yi, 0), H - 1), ys = min(max(t.yi + 1, 0), H - 1);
-    base = (unsigned)(yn * W + xw) * 128u | (unsigned)(xe - xw) | ((unsigned)(ys - yn) << 1);
 }
 
 __global__ void __launch_bounds__(N_THREADS, 1) cost_stem_tc_kernel(const __grid_constant__ StemArgs a) {

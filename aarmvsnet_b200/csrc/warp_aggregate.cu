@@ -8,11 +8,13 @@
 //   pass B  omega_stats_kernel<2>   t0 -> GN1/ReLU -> 1x1 -> GroupNorm-2 sums          (reads t0 only)
 //   pass C  omega_stats_kernel<3>   ... -> GN2/ReLU -> 1x1 -> GroupNorm-3 sums         (reads t0 only)
 //   pass D  aggregate_kernel   re-gather, omega tail from t0 + the three statistics, sum_v (1 + w_v) c_v, * -1/S
-// The 5-D cost volume [B,32,D,H,W] never exists.  On the tensor-core path (cost_stem_tc.cu + aggregate_stream_kernel below)
-// the per-view 32-channel cost of the K planes of ONE batch does travel through HBM once -- pass A stores it (costv
-// [K][S][P][32], 11.6 GB at cfg2) and pass D streams it back -- because gathering a second time was measured slower
-// (0.56 vs 0.37 ms/plane); the gathering kernels of this file keep it on chip.  Layout: features NHWC fp32
-// (one pixel = 128 B = one cache line per bilinear tap); 8 lanes x float4 cover one pixel, a warp covers 4 pixels per load.
+// The 5-D cost volume [B,32,D,H,W] never exists, and by default no per-view cost reaches HBM either: pass A keeps only t0
+// (16 B per pixel and view) and pass D gathers a second time.  aggregate_stream_kernel below is round 1's alternative -- pass A
+// (cost_stem_tc.cu, costv_mode 1) stores the per-view cost of a plane batch (costv [K][S][P][32], 11.6 GB at cfg2) and pass D
+// streams it back; as whole jobs on the same box the two are equally fast (the second gather costs what 3 GB/plane of extra
+// DRAM traffic costs in clock under the board's power cap: DESIGN.md §3), so the variant without the slab is the default and
+// the streaming one stays as Engine(keep_costv=True).  Layout: features NHWC fp32 (one pixel = 128 B = one cache line per
+// bilinear tap); 8 lanes x float4 cover one pixel, a warp covers 4 pixels per load.
 #include "common.cuh"
 #include "tc_common.cuh"
 #include "omega.cuh"
@@ -191,6 +193,7 @@ __global__ void __launch_bounds__(256) omega_stats_kernel(const float* __restric
 // tap set and omega weight once, the group reads them back with shuffles, and the taps of three views (12 lines) are
 // requested before the first is used.
 constexpr int AG_TH = 8, AG_TW = 16;
+__device__ __forceinline__ float4 ldg4b(const unsigned char* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 #ifndef AGG_NBV
 #define AGG_NBV 1              // views whose taps are requested before the first is used
 #endif
@@ -220,6 +223,7 @@ aggregate_kernel(const float* __restrict__ ref, const float* __restrict__ src, s
     const int sub = threadIdx.x & 7, grp = threadIdx.x >> 3;
     const float* depths = depth_values + plane_index(d_host, d_dev);
     const float s_den = (float)S;
+    const unsigned row_bytes = (unsigned)W * 128u;
     const int tiles_x = (W + AG_TW - 1) / AG_TW, tiles_y = (H + AG_TH - 1) / AG_TH;
     for (int tile = blockIdx.x; tile < tiles_x * tiles_y; tile += gridDim.x) {
         const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
@@ -230,23 +234,22 @@ aggregate_kernel(const float* __restrict__ ref, const float* __restrict__ src, s
             const bool valid = y < H && x < W;
             const size_t p = valid ? (size_t)y * W + x : 0;
             const float4 rv = ldg4(ref + p * 32 + sub * 4);
+            const uint64_t rv01 = pk2(rv.x, rv.y), rv23 = pk2(rv.z, rv.w);
             // planes innermost: the source lines this pixel touches at plane k+1 are the ones just fetched for plane k
             for (int k = 0; k < K; ++k) {
             const float depth = depths[k];
             const OmegaNorm* norms = norms_all + k * S;
             const float* t0k = t0 + (size_t)k * S * P * 4;
-            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            uint64_t acc01 = 0ull, acc23 = 0ull;
             for (int v0 = 0; v0 < S; v0 += 8) {
-                // this lane's view: sample position, taps and reweight
+                // this lane's view: gather recipe (four weights, 0 for a corner outside the image = the skipped tap; byte offset of
+                // the clamped north-west line | column step | row step << 1, as in pass A) and reweight
                 const int mv = v0 + sub;
-                Taps tm;
-                tm.o_nw = tm.o_ne = tm.o_sw = tm.o_se = -1;
-                tm.w_nw = tm.w_ne = tm.w_sw = tm.w_se = 0.f;
+                float4 rw = make_float4(0.f, 0.f, 0.f, 0.f);
+                unsigned rb = 0u;
                 float wm = 0.f;
                 if (mv < S && valid) {
-                    float ix, iy;
-                    sweep_position(scam + mv * 12, (float)x, (float)y, depth, W, H, align_corners != 0, ix, iy);
-                    tm = make_taps(ix, iy, W, H);
+                    make_recipe(scam + mv * 12, x, y, depth, W, H, align_corners != 0, rw, rb);
                     float a1[4], u[4], vv[4];
                     omega_u(q, norms[mv], ldg4(t0k + ((size_t)mv * P + p) * 4), a1, u);
                     omega_v(q, norms[mv], u, vv);
@@ -254,45 +257,29 @@ aggregate_kernel(const float* __restrict__ ref, const float* __restrict__ src, s
                     if (reweight_out) reweight_out[((size_t)k * S + mv) * P + p] = wm;
                 }
                 const int nv = min(8, S - v0);
-                for (int kb = 0; kb < nv; kb += AGG_NBV) {
-                    float4 ta[AGG_NBV], tb[AGG_NBV], tcn[AGG_NBV], td[AGG_NBV];
-                    float w0[AGG_NBV], w1[AGG_NBV], w2[AGG_NBV], w3[AGG_NBV], wv[AGG_NBV];
-#pragma unroll
-                    for (int e = 0; e < AGG_NBV; ++e) {
-                        const int k = min(kb + e, 7);
-                        const int o0 = __shfl_sync(0xffffffffu, tm.o_nw, k, 8), o1 = __shfl_sync(0xffffffffu, tm.o_ne, k, 8);
-                        const int o2 = __shfl_sync(0xffffffffu, tm.o_sw, k, 8), o3 = __shfl_sync(0xffffffffu, tm.o_se, k, 8);
-                        w0[e] = __shfl_sync(0xffffffffu, tm.w_nw, k, 8); w1[e] = __shfl_sync(0xffffffffu, tm.w_ne, k, 8);
-                        w2[e] = __shfl_sync(0xffffffffu, tm.w_sw, k, 8); w3[e] = __shfl_sync(0xffffffffu, tm.w_se, k, 8);
-                        wv[e] = __shfl_sync(0xffffffffu, wm, k, 8) + 1.0f;
-                        if (o0 < 0) w0[e] = 0.f;
-                        if (o1 < 0) w1[e] = 0.f;
-                        if (o2 < 0) w2[e] = 0.f;
-                        if (o3 < 0) w3[e] = 0.f;
-                        const float* sv = src + (size_t)min(v0 + kb + e, S - 1) * view_stride + sub * 4;
-                        ta[e] = ldg4(sv + (size_t)max(o0, 0) * 32);
-                        tb[e] = ldg4(sv + (size_t)max(o1, 0) * 32);
-                        tcn[e] = ldg4(sv + (size_t)max(o2, 0) * 32);
-                        td[e] = ldg4(sv + (size_t)max(o3, 0) * 32);
-                    }
-#pragma unroll
-                    for (int e = 0; e < AGG_NBV; ++e) {
-                        if (kb + e >= nv) continue;
-                        const float gx = __fmaf_rn(td[e].x, w3[e], __fmaf_rn(tcn[e].x, w2[e], __fmaf_rn(tb[e].x, w1[e], __fmul_rn(ta[e].x, w0[e]))));
-                        const float gy = __fmaf_rn(td[e].y, w3[e], __fmaf_rn(tcn[e].y, w2[e], __fmaf_rn(tb[e].y, w1[e], __fmul_rn(ta[e].y, w0[e]))));
-                        const float gz = __fmaf_rn(td[e].z, w3[e], __fmaf_rn(tcn[e].z, w2[e], __fmaf_rn(tb[e].z, w1[e], __fmul_rn(ta[e].z, w0[e]))));
-                        const float gw = __fmaf_rn(td[e].w, w3[e], __fmaf_rn(tcn[e].w, w2[e], __fmaf_rn(tb[e].w, w1[e], __fmul_rn(ta[e].w, w0[e]))));
-                        const float dx = gx - rv.x, dy = gy - rv.y, dz = gz - rv.z, dw = gw - rv.w;
-                        const float cx = __fmul_rn(dx, dx), cy = __fmul_rn(dy, dy), cz = __fmul_rn(dz, dz), cw = __fmul_rn(dw, dw);
-                        if (v0 + kb + e == 0) {
-                            acc = make_float4(__fmul_rn(wv[e], cx), __fmul_rn(wv[e], cy), __fmul_rn(wv[e], cz), __fmul_rn(wv[e], cw));
-                        } else {   // the reference adds the rounded product (two ATen ops): keep mul and add separate
-                            acc.x = __fadd_rn(acc.x, __fmul_rn(wv[e], cx)); acc.y = __fadd_rn(acc.y, __fmul_rn(wv[e], cy));
-                            acc.z = __fadd_rn(acc.z, __fmul_rn(wv[e], cz)); acc.w = __fadd_rn(acc.w, __fmul_rn(wv[e], cw));
-                        }
-                    }
+                const unsigned char* sv = reinterpret_cast<const unsigned char*>(src + (size_t)v0 * view_stride) + sub * 16;
+                for (int e = 0; e < nv; ++e, sv += view_stride * sizeof(float)) {
+                    // six shuffles hand view e's recipe round the pixel's 8-lane group
+                    const unsigned base = __shfl_sync(0xffffffffu, rb, e, 8);
+                    const float w0 = __shfl_sync(0xffffffffu, rw.x, e, 8), w1 = __shfl_sync(0xffffffffu, rw.y, e, 8);
+                    const float w2 = __shfl_sync(0xffffffffu, rw.z, e, 8), w3 = __shfl_sync(0xffffffffu, rw.w, e, 8);
+                    const float wv = __shfl_sync(0xffffffffu, wm, e, 8) + 1.0f;
+                    const unsigned o0 = base & ~127u, o1 = o0 + ((base & 1u) << 7), od = (base & 2u) ? row_bytes : 0u;
+                    const float4 ta = ldg4b(sv + o0), tb = ldg4b(sv + o1), tcn = ldg4b(sv + (o0 + od)), td = ldg4b(sv + (o1 + od));
+                    // blend in ATen's order fma(se, w, fma(sw, w, fma(ne, w, nw * w))), (warp - ref)^2, * (1 + w_v): packed fp32 pairs,
+                    // IEEE per lane = bit-identical to the scalar chains
+                    const uint64_t p0 = pk2(w0, w0), p1 = pk2(w1, w1), p2 = pk2(w2, w2), p3 = pk2(w3, w3), pv = pk2(wv, wv);
+                    const uint64_t g01 = fma2(pk2(td.x, td.y), p3, fma2(pk2(tcn.x, tcn.y), p2, fma2(pk2(tb.x, tb.y), p1, mul2(pk2(ta.x, ta.y), p0))));
+                    const uint64_t g23 = fma2(pk2(td.z, td.w), p3, fma2(pk2(tcn.z, tcn.w), p2, fma2(pk2(tb.z, tb.w), p1, mul2(pk2(ta.z, ta.w), p0))));
+                    const uint64_t d01 = sub2(g01, rv01), d23 = sub2(g23, rv23);
+                    const uint64_t t01 = mul2(pv, mul2(d01, d01)), t23 = mul2(pv, mul2(d23, d23));
+                    if (v0 + e == 0) { acc01 = t01; acc23 = t23; }
+                    else { acc01 = add2(acc01, t01); acc23 = add2(acc23, t23); }    // the reference adds the rounded product (two ATen ops)
                 }
             }
+            float4 acc;
+            upk2(acc01, acc.x, acc.y);
+            upk2(acc23, acc.z, acc.w);
             const float4 r = make_float4(-__fdiv_rn(acc.x, s_den), -__fdiv_rn(acc.y, s_den), -__fdiv_rn(acc.z, s_den), -__fdiv_rn(acc.w, s_den));
             if (cost_planes) {       // fp16 (hi, lo) operand planes [K][2][4 chunks][P][8] of ConvLSTM cell 0, as aggregate_stream_kernel
                 uint2 hi, lo;
@@ -567,6 +554,7 @@ extern "C" int aarmvs_aggregate(const float* ref, const float* src, size_t view_
         AARMVS_LAUNCH_RESULT();
     }
     AARMVS_CHECK_ARG(ref && src && depth_values && cams);
+    AARMVS_CHECK_ARG((size_t)H * W * 128 < 0xFFFFFFFFull);          // the gather recipes hold 32-bit byte offsets
     const int ntiles = ((W + AG_TW - 1) / AG_TW) * ((H + AG_TH - 1) / AG_TH);
     const int blocks = ntiles < 148 * AGG_MINB ? ntiles : 148 * AGG_MINB;
     aggregate_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(ref, src, view_stride, H, W, S, planes, cams, q, depth_values, d_host,
