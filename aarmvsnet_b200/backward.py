@@ -55,7 +55,7 @@ class Backward:
         self.sd = {k: v.detach().to(device=device, dtype=torch.float32) for k, v in engine.module.state_dict().items()}
         self.w = engine._weights(device)
         self._pack()
-        self._ws = None
+        self._wss = {}                       # slot -> workspace: one per concurrently running sample (see batch())
         self.chan = torch.zeros(128, device=device, dtype=torch.float64)      # per-channel sums of one GroupNorm backward
 
     # ------------------------------------------------------------------------------------------ weights and accumulators
@@ -108,10 +108,11 @@ class Backward:
             g[f"dc{l}.beta"] = torch.zeros(32, **f32)
         self.bw, self.g = bw, g
 
-    def _workspace(self, H, W, N):
+    def _workspace(self, H, W, N, slot=0):
         key = (H, W, N)
-        if self._ws is not None and self._ws["key"] == key:
-            return self._ws
+        ws = self._wss.get(slot)
+        if ws is not None and ws["key"] == key:
+            return ws
         dev = self.dev
         f32 = dict(device=dev, dtype=torch.float32)
         P, S = H * W, N - 1
@@ -154,7 +155,8 @@ class Backward:
         b["cams"] = torch.empty(S, 12, **f32)
         b["depths"] = torch.empty(0, **f32)
         b["graph"] = None
-        self._ws = b
+        b["chan"] = torch.zeros(128, device=dev, dtype=torch.float64)      # per-channel sums of one GroupNorm backward
+        self._wss[slot] = b
         return b
 
     # ------------------------------------------------------------------------------------------ kernel wrappers
@@ -177,8 +179,8 @@ class Backward:
         capi.check(self.lib.aarmvs_gn_relu_apply(_ptr(x), P, C, groups, _ptr(sums), _ptr(gn[0]), _ptr(gn[1]), 1, _ptr(out), self._st()),
                    "aarmvs_gn_relu_apply")
 
-    def gn_bwd(self, x, dy, P, C, groups, sums, gn, dx, dgamma, dbeta, dbias=None):
-        chan = self.chan
+    def gn_bwd(self, x, dy, P, C, groups, sums, gn, dx, dgamma, dbeta, dbias=None, chan=None):
+        chan = self.chan if chan is None else chan
         chan.zero_()
         for stage in (1, 2):
             capi.check(self.lib.aarmvs_gn_relu_bwd(stage, _ptr(x), _ptr(dy), P, C, groups, _ptr(sums), _ptr(gn[0]), _ptr(gn[1]), 1,
@@ -186,15 +188,52 @@ class Backward:
                                                    _ptr(dbias) if dbias is not None else None, self._st()), "aarmvs_gn_relu_bwd")
 
     # ------------------------------------------------------------------------------------------ one sample
+    def batch(self, saved_list, dcost):
+        """All samples of a step: dcost [B, D, P].  The samples' reverse sweeps are independent chains of short kernels on small
+        maps (latency-bound one at a time), so each runs on its own stream with its own workspace and graph, interleaved plane by
+        plane; the gradient accumulators are shared (atomics).  FeatNet's backward follows on the calling stream."""
+        B = len(saved_list)
+        if B == 1:
+            return self.sample(saved_list[0], dcost[0])
+        main = torch.cuda.current_stream(self.dev)
+        streams = [torch.cuda.Stream(self.dev) for _ in range(B)]
+        sweeps = []
+        for i, (sv, st) in enumerate(zip(saved_list, streams)):
+            st.wait_stream(main)
+            with torch.cuda.stream(st):
+                sweeps.append(self._sweep(sv, dcost[i], slot=i))
+        alive = True
+        while alive:                              # round-robin: one plane of every sample per turn
+            alive = False
+            for sweep, st in zip(sweeps, streams):
+                with torch.cuda.stream(st):
+                    if next(sweep, "done") != "done":
+                        alive = True
+        for st in streams:
+            main.wait_stream(st)
+        for i, sv in enumerate(saved_list):
+            b = self._wss[i]
+            for v in range(sv["N"]):
+                self.featnet(sv["imgs"][v], b["dfeat"][v], sv["H"], sv["W"])
+
     def sample(self, saved, dcost_volume):
-        """saved: Engine.forward_saving_state's dict; dcost_volume [D, P] = dL / d(regularised cost).  Accumulates into self.g.
+        """One sample, on the calling stream: reverse sweep, then FeatNet's backward per view."""
+        for _ in self._sweep(saved, dcost_volume, slot=0):
+            pass
+        b = self._wss[0]
+        for v in range(saved["N"]):
+            self.featnet(saved["imgs"][v], b["dfeat"][v], saved["H"], saved["W"])
+
+    def _sweep(self, saved, dcost_volume, slot):
+        """Generator over the planes of one sample's reverse sweep (yields after enqueueing each plane).
+        saved: Engine.forward_saving_state's dict; dcost_volume [D, P] = dL / d(regularised cost).  Accumulates into self.g.
 
         The body of one plane works on FIXED buffers: the two state records it needs (after planes d-1 and d) and its row of
         dcost_volume are staged into them, the plane index lives in device memory -- so the ~60 launches of a plane are captured
         once as a CUDA graph and replayed for every other plane (three small staging ops + one graph launch per plane)."""
         eng = self.eng
         H, W, N, D = saved["H"], saved["W"], saved["N"], saved["D"]
-        b = self._workspace(H, W, N)
+        b = self._workspace(H, W, N, slot)
         for t in b["dh"] + b["dc"] + b["dhprev"]:
             t.zero_()
         b["dfeat"].zero_()
@@ -212,22 +251,23 @@ class Backward:
             b["plane"].fill_(d)
             if b["graph"] is not None:
                 b["graph"].replay()
+                yield d
                 continue
             self._plane(H, W, N, b)                           # eager: also sets the kernels' launch attributes
             if self.use_graph:
                 # capture on a side stream with the raw API: torch.cuda.graph()'s context manager would also run gc.collect(),
                 # empty the caching allocator and synchronise the device on every optimisation step (the body allocates nothing)
+                cur = torch.cuda.current_stream(self.dev)
                 side = torch.cuda.Stream(self.dev)
-                side.wait_stream(torch.cuda.current_stream(self.dev))
+                side.wait_stream(cur)
                 graph = torch.cuda.CUDAGraph()
                 with torch.cuda.stream(side):
                     graph.capture_begin()
                     self._plane(H, W, N, b)
                     graph.capture_end()
-                torch.cuda.current_stream(self.dev).wait_stream(side)
+                cur.wait_stream(side)
                 b["graph"] = graph
-        for v in range(N):
-            self.featnet(saved["imgs"][v], b["dfeat"][v], H, W)
+            yield d
 
     def _plane(self, H, W, N, b):
         """Backward of the plane whose index is in b["plane"], whose states are in b["rec2"] and whose dL/dcost_reg is b["dcr"]
@@ -282,7 +322,7 @@ class Backward:
         def up_bwd(i, hin, win, src_h, dh_target):
             pp = 4 * hin * win
             self.gn_bwd(b[f"up{i}raw"], b[f"dup{i}"], pp, 16, 2, b[f"gsum{i}"], bw[f"deconv{i}.gn"], b[f"dup{i}"], g[f"deconv{i}.gamma"],
-                        g[f"deconv{i}.beta"], g[f"deconv{i}.b"])
+                        g[f"deconv{i}.beta"], g[f"deconv{i}.b"], chan=b["chan"])
             self.conv([_seg(b[f"dup{i}"], 16)], 2 * hin, 2 * win, [_seg(dh_target, 16, 1)], hin, win, 3, 2, False, bw[f"deconv{i}.wT"])
             self.wgrad([_seg(b[f"dup{i}"], 16)], 2 * hin, 2 * win, src_h, hin, win, 16, 3, 2, g[f"deconv{i}.wT"])
 

@@ -372,8 +372,9 @@ __global__ void __launch_bounds__(256) gn_bwd_kernel(const __grid_constant__ GnB
             if (threadIdx.x < C) atomicAdd(a.dx_chan_sum + threadIdx.x, (float)s_acc[threadIdx.x * 2]);
         }
         if (blockIdx.x == 0 && threadIdx.x < C) {
-            a.dgamma[threadIdx.x] += (float)a.chan_sums[threadIdx.x * 2];
-            a.dbeta[threadIdx.x] += (float)a.chan_sums[threadIdx.x * 2 + 1];
+            // (atomics: the samples of a batch run their backward sweeps on concurrent streams into the same accumulators)
+            atomicAdd(a.dgamma + threadIdx.x, (float)a.chan_sums[threadIdx.x * 2]);
+            atomicAdd(a.dbeta + threadIdx.x, (float)a.chan_sums[threadIdx.x * 2 + 1]);
         }
     }
 }

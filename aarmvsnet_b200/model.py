@@ -121,8 +121,7 @@ class _RegularisedCostVolume(torch.autograd.Function):
         model, saved = ctx.model, ctx.saved
         bwd = Backward(model._engine, dcost.device)
         with torch.cuda.device(dcost.device):
-            for b, s in enumerate(saved):
-                bwd.sample(s, dcost[b].reshape(s["D"], -1).to(torch.float32))
+            bwd.batch(saved, dcost.reshape(len(saved), saved[0]["D"], -1).to(torch.float32).contiguous())
         grads = bwd.parameter_gradients()
         ctx.saved = None
         return (None, None, None, None) + tuple(grads[name].to(p.dtype) for name, p in model.named_parameters())
