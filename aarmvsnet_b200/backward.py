@@ -55,7 +55,14 @@ class Backward:
         self.sd = {k: v.detach().to(device=device, dtype=torch.float32) for k, v in engine.module.state_dict().items()}
         self.w = engine._weights(device)
         self._pack()
-        self._wss = {}                       # slot -> workspace: one per concurrently running sample (see batch())
+        # slot -> workspace and stream, one per concurrently running sample (see batch()).  They live on the engine and survive
+        # the optimisation step (this object does not: the weights it packs change every step), so that the caching allocator's
+        # per-stream pools are reused; only the captured graphs are per step (they bake the packed weights' addresses).
+        if not hasattr(engine, "_bwd_wss"):
+            engine._bwd_wss, engine._bwd_streams = {}, []
+        self._wss, self._streams = engine._bwd_wss, engine._bwd_streams
+        for ws in self._wss.values():
+            ws["graph"] = None
         self.chan = torch.zeros(128, device=device, dtype=torch.float64)      # per-channel sums of one GroupNorm backward
 
     # ------------------------------------------------------------------------------------------ weights and accumulators
@@ -196,7 +203,9 @@ class Backward:
         if B == 1:
             return self.sample(saved_list[0], dcost[0])
         main = torch.cuda.current_stream(self.dev)
-        streams = [torch.cuda.Stream(self.dev) for _ in range(B)]
+        while len(self._streams) < B:
+            self._streams.append(torch.cuda.Stream(self.dev))
+        streams = self._streams[:B]
         sweeps = []
         for i, (sv, st) in enumerate(zip(saved_list, streams)):
             st.wait_stream(main)

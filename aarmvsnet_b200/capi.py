@@ -99,6 +99,7 @@ PROTOTYPES = {
     "aarmvs_feat_assemble_bwd": (_I, [_P, _I, _I, _P, _P, _P, _P]),
     "aarmvs_deform_sample": (_I, [_P, _I, _I, _P, _P, _P, _P]),
     "aarmvs_deform_bwd": (_I, [_P, _I, _I, _P, _P, _P, _P, _P, _P]),
+    "aarmvs_snapshot_state": (_I, [_P, _P, _I, _I, _P, _SZ, _I, _P, _P]),
     "aarmvs_adam_step": (_I, [_P, _P, _P, _P, _SZ, _F, _F, _F, _F, _F, _I, _P]),
     "aarmvs_tc_mma_bench": (_I, [_I, _I, _I, _I, _I, _P, _P]),
     "aarmvs_tc_selftest": (_I, [_P, _I, _P, _P, _I, _I, _I, _P]),

@@ -73,3 +73,59 @@ extern "C" int aarmvs_split_planes(const aarmvs_conv_src* src, int H, int W, voi
     split_planes_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(a);
     AARMVS_LAUNCH_RESULT();
 }
+
+// ------------------------------------------------------------------------------------------------ state snapshot (training)
+// After plane d of the training forward: copy the recurrent state of the five cells -- h_i (the fp32 copies the cells write,
+// ping-pong half d & 1) and c_i (tile-blocked, private to the cell kernel) -- into record d + 1 of the per-sample state
+// history [D + 1][record] as plain NHWC fp32 (Engine.state_layout: [h0 | c0 | h1 | c1 | ...]).  One launch instead of ten
+// strided copies, and graph-friendly: the record index is read from the device-side plane counter (already incremented by
+// aarmvs_next_plane) and the history's base address from device memory (one captured graph serves every sample).
+namespace {
+struct SnapArgs {
+    const float* h[5];
+    const float* c[5];
+    int H, W;
+    float* const* state_pp;
+    size_t rec;
+    int d_host;
+    const int* d_dev;
+};
+__device__ constexpr int SNAP_CH[5] = {16, 16, 16, 16, 8}, SNAP_SCALE[5] = {1, 2, 4, 2, 1};
+
+__global__ void __launch_bounds__(256) snapshot_state_kernel(const SnapArgs a) {
+    const int r = plane_index(a.d_host, a.d_dev);            // record to write = planes completed so far
+    float* dst = *a.state_pp + (size_t)r * a.rec;
+    size_t off = 0;
+    for (int i = 0; i < 5; ++i) {
+        const int ch = SNAP_CH[i], h = a.H / SNAP_SCALE[i], w = a.W / SNAP_SCALE[i], q = ch / 4;
+        const size_t n = (size_t)h * w * ch;
+        const int tiles_x = (w + 7) / 8;
+        const float* hs = a.h[i] + (size_t)((r - 1) & 1) * n;
+        for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (size_t)gridDim.x * blockDim.x) {
+            dst[off + idx] = hs[idx];
+            const size_t p = idx / ch;
+            const int cn = (int)(idx - p * ch), y = (int)(p / w), x = (int)(p - (size_t)y * w);
+            const size_t tile = (size_t)(y >> 4) * tiles_x + (x >> 3);
+            const size_t src = ((tile * 4 + cn / q) * 128 + ((y & 15) * 8 + (x & 7))) * q + cn % q;
+            dst[off + n + idx] = a.c[i][src];
+        }
+        off += 2 * n;
+    }
+}
+}  // namespace
+
+extern "C" int aarmvs_snapshot_state(const float* const* h_f32_pairs, const float* const* c_blocked, int H, int W, float* const* state_pp,
+                                     size_t record_floats, int d_host, const int* d_dev, void* stream) {
+    AARMVS_CHECK_ARG(h_f32_pairs && c_blocked && state_pp && H > 0 && W > 0 && H % 4 == 0 && W % 4 == 0 && record_floats > 0);
+    SnapArgs a = {};
+    for (int i = 0; i < 5; ++i) {
+        AARMVS_CHECK_ARG(h_f32_pairs[i] && c_blocked[i]);
+        a.h[i] = h_f32_pairs[i];
+        a.c[i] = c_blocked[i];
+    }
+    a.H = H; a.W = W; a.state_pp = state_pp; a.rec = record_floats; a.d_host = d_host; a.d_dev = d_dev;
+    const size_t n = (size_t)H * W * 16;
+    const size_t blocks = (n + 255) / 256;
+    snapshot_state_kernel<<<(int)(blocks < 148 * 8 ? blocks : 148 * 8), 256, 0, (cudaStream_t)stream>>>(a);
+    AARMVS_LAUNCH_RESULT();
+}

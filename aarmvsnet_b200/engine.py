@@ -184,6 +184,12 @@ class Engine:
         if not tc:               # fp32 deconvolution outputs (the tensor-core path writes operand planes directly)
             ws["up0"] = torch.empty(P // 4, 16, **f32)
             ws["up1"] = torch.empty(P, 16, **f32)
+        if tc and with_state:
+            # training forward: where aarmvs_snapshot_state finds the cells' state, and the device cell holding the base address
+            # of the current sample's state history (so that one captured graph serves every sample)
+            ws["snap"] = {"h": (ctypes.c_void_p * 5)(*[t.data_ptr() for t in ws["h"]]),
+                          "c": (ctypes.c_void_p * 5)(*[t.data_ptr() for t in ws["c"]]),
+                          "state_pp": torch.zeros(1, device=device, dtype=torch.int64), "rec": self.state_layout(H, W)[1]}
         ws["psums"] = torch.zeros(K * S * 6 + 8, device=device, dtype=torch.float64)
         ws["plane"] = torch.zeros(1, device=device, dtype=torch.int32)
         ws["cams"] = torch.empty(S, 12, **f32)
@@ -291,12 +297,10 @@ class Engine:
         capi.check(self.lib.aarmvs_split_planes(ctypes.byref(src), H, W, _ptr(planes), stream), "aarmvs_split_planes")
 
     # ------------------------------------------------------------------------------------------ one plane
-    def _batch(self, ws, w, stream, nplanes, marks=None, after_plane=None):
+    def _batch(self, ws, w, stream, nplanes, marks=None):
         """Enqueue the kernel chain of `nplanes` consecutive depth planes starting at the plane index held in
         ws['plane'] (device memory): passes A-D once for the whole batch, then the recurrence plane by plane.
-        marks: optional list collecting (stage name, CUDA event) after each stage (bench.py's per-kernel timing).
-        after_plane: optional callable(k) run after the launches of the batch's k-th plane (eager mode only: the training
-        forward snapshots the recurrent state there)."""
+        marks: optional list collecting (stage name, CUDA event) after each stage (bench.py's per-kernel timing)."""
         lib, H, W, N = self.lib, ws["H"], ws["W"], ws["N"]
 
         def mark(name):
@@ -405,8 +409,42 @@ class Engine:
             else:
                 capi.check(lib.aarmvs_next_plane(dptr, _ptr(s_up0), 8, stream), "aarmvs_next_plane")
             mark("head_wta")
-            if after_plane is not None:
-                after_plane(k)
+            if ws.get("snap") is not None:          # training forward: record the recurrent state after this plane
+                sn = ws["snap"]
+                capi.check(lib.aarmvs_snapshot_state(sn["h"], sn["c"], H, W, _ptr(sn["state_pp"]), sn["rec"], 0, dptr, stream),
+                           "aarmvs_snapshot_state")
+
+    def _capture_batch(self, ws, w, device, nplanes):
+        """Capture the kernel chain of one plane batch as a CUDA graph (raw capture API on a side stream: nothing is allocated
+        inside, and torch.cuda.graph()'s context manager would flush the caching allocator and synchronise the device, which a
+        training loop -- one capture per optimisation step, the graph bakes host-side weights -- cannot afford)."""
+        cur = torch.cuda.current_stream(device)
+        side = torch.cuda.Stream(device)
+        side.wait_stream(cur)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.stream(side):
+            g.capture_begin()
+            self._batch(ws, w, ctypes.c_void_p(side.cuda_stream), nplanes)
+            g.capture_end()
+        cur.wait_stream(side)
+        return g
+
+    def _run_planes(self, ws, w, device, stream, D):
+        """All D planes of one sample: whole batches of K planes through the (lazily captured) graph, the rest eagerly."""
+        K = ws["K"]
+        full, rem = divmod(D, K)
+        start = 0
+        if self.use_graph and ws["graph"] is None and full > 0:
+            self._batch(ws, w, stream, K)         # first batch eagerly: also sets the kernels' launch attributes
+            start = 1
+            ws["graph"] = self._capture_batch(ws, w, device, K)
+        for _ in range(start, full):
+            if self.use_graph:
+                ws["graph"].replay()
+            else:
+                self._batch(ws, w, stream, K)
+        if rem:
+            self._batch(ws, w, stream, rem)       # last partial batch
 
     # ------------------------------------------------------------------------------------------ one depth map
     @staticmethod
@@ -443,19 +481,9 @@ class Engine:
             off += 2 * n
         return lay, off
 
-    @staticmethod
-    def _unblock_into(dst, cb, H, W, ch):
-        """Tile-blocked cell state (include/aarmvs.h: aarmvs_cell_state_floats) -> dst [H*W*ch] NHWC."""
-        ty, tx = (H + 15) // 16, (W + 7) // 8
-        src = cb.view(ty, tx, 4, 16, 8, ch // 4).permute(0, 3, 1, 4, 2, 5)              # [ty][16][tx][8][4][ch/4]
-        if H % 16 == 0 and W % 8 == 0:
-            dst.view(ty, 16, tx, 8, 4, ch // 4).copy_(src)                               # one strided copy
-        else:
-            dst.view(H, W, ch).copy_(src.reshape(ty * 16, tx * 8, ch)[:H, :W])
-
     def forward_saving_state(self, imgs, proj_matrices, depth_values):
-        """The training-phase forward of ONE sample (models/drmvsnet.py:272-287) on the tensor-core kernels, launched eagerly,
-        keeping what the backward pass needs: the features of the N views, the regularised cost of every plane and a snapshot
+        """The training-phase forward of ONE sample (models/drmvsnet.py:272-287) on the tensor-core kernels (the same graph-replayed
+        plane chain as inference, plus aarmvs_snapshot_state after every plane), keeping what the backward pass needs: the features of the N views, the regularised cost of every plane and a snapshot
         of the recurrent state (h, c of the five cells) after every plane -- one flat record of 66 floats per full-resolution
         pixel and plane (state_layout), record 0 = the zero state before plane 0; everything else is recomputed per plane by
         the backward (aarmvsnet_b200/backward.py).
@@ -483,15 +511,8 @@ class Engine:
             state[0].zero_()
             saved = {"H": H, "W": W, "N": N, "D": D, "imgs": imgs, "cams": ws["cams"].clone(), "depths": ws["depths"].clone(),
                      "state": state}
-            K = ws["K"]
-            for d0 in range(0, D, K):
-                def snapshot(k, d0=d0):
-                    r = state[d0 + k + 1]
-                    for i in range(5):
-                        ho, co, n = lay[i]
-                        r[ho:ho + n].copy_(ws["h"][i][(d0 + k) & 1].reshape(-1))
-                        self._unblock_into(r[co:co + n], ws["c"][i], H // _SCALE[i], W // _SCALE[i], _HID[i])
-                self._batch(ws, w, stream, min(K, D - d0), after_plane=snapshot)
+            ws["snap"]["state_pp"].fill_(state.data_ptr())
+            self._run_planes(ws, w, device, stream, D)
             saved["feat"] = ws["feat"].clone()
             saved["cost"] = ws["cost_volume"].clone()
             return saved
@@ -554,25 +575,7 @@ class Engine:
         ws["depths"].copy_(depth_values.to(torch.float32), non_blocking=True)
         ws["plane"].zero_()
         ws["psums"].zero_()
-        K = ws["K"]
-        full, rem = divmod(D, K)
-        start = 0
-        if self.use_graph and ws["graph"] is None and full > 0:
-            self._batch(ws, w, stream, K)         # first batch eagerly: also sets the kernels' launch attributes
-            start = 1
-            torch.cuda.synchronize(device)
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                cap = ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
-                self._batch(ws, w, cap, K)
-            ws["graph"] = g
-        for _ in range(start, full):
-            if self.use_graph:
-                ws["graph"].replay()
-            else:
-                self._batch(ws, w, stream, K)
-        if rem:
-            self._batch(ws, w, stream, rem)       # last partial batch
+        self._run_planes(ws, w, device, stream, D)
         out = {"depth": ws["depth"].view(H, W), "photometric_confidence": ws["conf"].view(H, W),
                "index": ws["index"].view(H, W)}
         if keep_cost:

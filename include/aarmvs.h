@@ -353,6 +353,15 @@ int aarmvs_deform_sample(const float* x, int H, int W, const float* offmask, flo
 int aarmvs_deform_bwd(const float* x, int H, int W, const float* offmask, const float* samp, const float* dsamp_m, float* dx,
                       float* doffmask, void* stream);
 
+/* Training forward: after plane d, copy the recurrent state of the five cells -- h_i (the fp32 copies written by
+ * aarmvs_convlstm_cell_tc, two [P_i][Ch_i] halves each; half d & 1 is read) and c_i (tile-blocked, aarmvs_cell_state_floats) --
+ * into record r of the state history [D + 1][record_floats] as NHWC fp32 [h0 | c0 | h1 | c1 | h2 | c2 | h3 | c3 | h4 | c4]
+ * (hidden 16, 16, 16, 16, 8 at scales 1, 2, 4, 2, 1: 66 floats per full-resolution pixel).  r = *d_dev if d_dev is non-null
+ * (the plane counter AFTER aarmvs_next_plane, i.e. d + 1), else d_host; *state_pp (device memory) is the history's base, so one
+ * captured graph serves every sample.  h_f32_pairs / c_blocked: HOST arrays of five device pointers. */
+int aarmvs_snapshot_state(const float* const* h_f32_pairs, const float* const* c_blocked, int H, int W, float* const* state_pp,
+                          size_t record_floats, int d_host, const int* d_dev, void* stream);
+
 /* Adam step (train.py:180,307; torch.optim.Adam semantics, no amsgrad) over one flat fp32 buffer holding every parameter:
  * param, grad, exp_avg, exp_avg_sq [n]; step = 1 for the first update. */
 int aarmvs_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t n, float lr, float beta1,
