@@ -66,6 +66,10 @@ constexpr int TAP_BYTES = NPX * 32;                                      // one 
 #endif
 constexpr int TAP_SLOTS = STEM_AHEAD ? 2 : 1;
 constexpr int SMEM_FIXED = B_BYTES + G * (A_STAGE + TAP_SLOTS * TAP_BYTES) + 1024;    // + G * 4 warps * planes * S * 8 bytes of GroupNorm partial sums
+#ifndef STEM_STAT_SHARED
+#define STEM_STAT_SHARED 1      // 1: one GroupNorm partial-sum slot per worker GROUP (shared-memory float atomics of its four warps)
+#endif                          //    instead of one per warp: 3/4 less shared memory for the sums (what a sixth group needs)
+constexpr int STAT_ROWS = STEM_STAT_SHARED ? STEM_GROUPS : STEM_GROUPS * 4 * STEM_NBLK;
 #ifndef STEM_ACC_STRIDE
 #define STEM_ACC_STRIDE 32
 #endif
@@ -140,7 +144,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) cost_stem_tc_kernel(const __grid
     for (int i = tid; i < B_BYTES / 16; i += N_THREADS)
         reinterpret_cast<uint4*>(sB)[i] = __ldg(reinterpret_cast<const uint4*>(a.weight) + i);
     for (int i = tid; i < a.S * 12; i += N_THREADS) scam[i] = a.cams[i];
-    for (int i = tid; i < G * 4 * NBLK * SK; i += N_THREADS) sstat[i] = make_float2(0.f, 0.f);
+    for (int i = tid; i < STAT_ROWS * SK; i += N_THREADS) sstat[i] = make_float2(0.f, 0.f);
     if (tid == 0) {
         for (int s = 0; s < G; ++s) { tc::mbar_init(&full_a[s], GROUP_THREADS); tc::mbar_init(&done_a[s], 1); }
         tc::mbar_fence_init();
@@ -409,9 +413,14 @@ __global__ void __launch_bounds__(N_THREADS, 1) cost_stem_tc_kernel(const __grid
                 ss += __shfl_xor_sync(0xffffffffu, ss, off);
             }
             if (lane == 0) {       // this warp's private accumulator: a tile contributes 32 pixels x 4 values, ~100 tiles per slot
+#if STEM_STAT_SHARED
+                atomicAdd(&sstat[g * SK + slot].x, s);
+                atomicAdd(&sstat[g * SK + slot].y, ss);
+#else
                 float2 acc = sstat[(warp - 1) * SK + slot];
                 acc.x += s; acc.y += ss;
                 sstat[(warp - 1) * SK + slot] = acc;
+#endif
             }
             if (pf) pp[6] = clock64();
             tl = tl2; v = v2; k = k2; ty = ty2; tx = tx2;
@@ -422,7 +431,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) cost_stem_tc_kernel(const __grid
     if (warp == 0) tc::tmem_dealloc<TMEM_COLS>(tmem_base);
     if (tid < a.K * a.S) {                                                   // stats[k][v][GN1][sum, sumsq]
         double s = 0.0, ss = 0.0;
-        for (int w = 0; w < G * 4 * NBLK; ++w) { s += (double)sstat[w * SK + tid].x; ss += (double)sstat[w * SK + tid].y; }
+        for (int w = 0; w < STAT_ROWS; ++w) { s += (double)sstat[w * SK + tid].x; ss += (double)sstat[w * SK + tid].y; }
         atomicAdd(a.stats + tid * 6 + 0, s);
         atomicAdd(a.stats + tid * 6 + 1, ss);
     }
@@ -440,7 +449,7 @@ extern "C" void aarmvs_debug_flags(int flags) { g_dbg = flags; }
 extern "C" void aarmvs_debug_stem_profile_buffer(void* buf) { g_stem_prof = (unsigned long long*)buf; }
 #endif
 
-extern "C" int aarmvs_cost_stem_tc_max_slots(void) { return (227 * 1024 - 2048 - SMEM_FIXED) / (G * 4 * NBLK * 8); }
+extern "C" int aarmvs_cost_stem_tc_max_slots(void) { return (227 * 1024 - 2048 - SMEM_FIXED) / (STAT_ROWS * 8); }
 
 namespace {
 int launch_cost_stem_tc(const float* ref, const float* src, size_t view_stride, int H, int W, int S, const float* cams,
@@ -465,9 +474,9 @@ int launch_cost_stem_tc(const float* ref, const float* src, size_t view_stride, 
 #endif
     static unsigned long long smem_ok = 0;
     constexpr int SMEM_CAP = 227 * 1024 - 2048;      // the kernel also has ~1 KB of static shared memory
-    static_assert(SMEM_FIXED + G * 4 * NBLK * 8 * 8 <= SMEM_CAP, "shared memory budget");
+    static_assert(SMEM_FIXED + STAT_ROWS * 8 * 8 <= SMEM_CAP, "shared memory budget");
     if (cudaError_t e = ensure_dyn_smem(cost_stem_tc_kernel, SMEM_CAP, smem_ok)) return (int)e;
-    const int SMEM = SMEM_FIXED + G * 4 * NBLK * planes * S * 8;
+    const int SMEM = SMEM_FIXED + STAT_ROWS * planes * S * 8;
     AARMVS_CHECK_ARG(SMEM <= SMEM_CAP);          // planes * S <= aarmvs_cost_stem_tc_max_slots()
     const int ntiles = ((W + TCOL - 1) / TCOL) * ((H + TR - 1) / TR);
     const int sms = aarmvs_sm_count();
