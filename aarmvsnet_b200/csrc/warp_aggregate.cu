@@ -19,7 +19,6 @@
 #include "tc_common.cuh"
 #include "omega.cuh"
 #include <string.h>
-#include <stdlib.h>
 
 struct StemParams {            // omega.reweight_network.0.0 repacked [tap][cin][cout] + bias; lives in the
     float w[9 * 32 * 4];       // kernel parameter (constant) bank, so the 1152 FMAs per pixel take their
@@ -302,173 +301,6 @@ aggregate_kernel(const float* __restrict__ ref, const float* __restrict__ src, s
     }
 }
 
-// ------------------------------------------------------------------------------------------------ pass D, column walk
-// Same result as aggregate_kernel (bit for bit), organised like pass A's gather (cost_stem_tc.cu) instead of "8 lanes per
-// pixel, shuffles hand the recipes round": a persistent CTA of WG independent groups of 128 threads; a group takes one
-// (16 x 8 tile, plane) item at a time and loops over the source views:
-//   1. one THREAD per pixel evaluates the view's gather recipe (bit-exact homography, four weights zeroed for corners outside
-//      the image, byte offset of the clamped north-west line | step flags) and its reweight 1 + omega (from t0 and the three
-//      GroupNorm statistics) -> 32-byte record in shared memory (two slots: one group barrier per view);
-//   2. 8 lanes per pixel gather; each 8-lane team walks ONE COLUMN SEGMENT of eight vertically adjacent pixels and keeps a
-//      pixel's south lines as the north lines of the pixel below when the addresses coincide (any homography: an address
-//      comparison), blends in ATen's order with packed fp32 pairs, (warp - ref)^2, and accumulates (1 + w) c over the views in
-//      registers (eight float4 per thread);
-//   3. after the last view: -acc / S -> cell 0's fp16 (hi, lo) operand planes (or fp32).
-// Against aggregate_kernel: no per-view shuffles / selects / 64-bit address pairs, the recipe and omega arithmetic of a
-// (pixel, view) is issued once per 32 lanes instead of once per 8-lane group pass, ~40 % fewer line reads.
-constexpr int WK_TR = 16, WK_TC = 8, WK_GROUP = 128;
-#ifndef WALK_GROUPS
-#define WALK_GROUPS 5
-#endif
-constexpr int WK_G = WALK_GROUPS, WK_THREADS = WK_G * WK_GROUP;
-
-struct __align__(16) WalkRec {
-    float w[4];                // bilinear weights (0 = corner outside the image)
-    unsigned base;             // byte offset of the clamped north-west line | column step | row step << 1
-    float wv;                  // 1 + omega_v(p)
-    unsigned pad0, pad1;
-};
-
-struct WalkArgs {
-    const float* ref;
-    const float* src;
-    size_t view_stride;
-    int H, W, S, K;
-    const float* cams;
-    OmegaTail q;
-    const float* depth_values;
-    int d_host;
-    const int* d_dev;
-    int align_corners;
-    const float* t0;
-    const double* stats;
-    float* cost;
-    __half* cost_planes;
-    float* reweight_out;
-};
-
-__global__ void __launch_bounds__(WK_THREADS, 1) aggregate_walk_kernel(const __grid_constant__ WalkArgs a) {
-    __shared__ WalkRec recs[WK_G][2][WK_GROUP];
-    __shared__ OmegaNorm norms_all[AARMVS_MAX_PLANES * AARMVS_MAX_SRC];
-    __shared__ float scam[AARMVS_MAX_SRC * 12];
-    const int tid = threadIdx.x;
-    const int S = a.S, K = a.K, W = a.W, H = a.H;
-    const size_t P = (size_t)H * W;
-    for (int i = tid; i < S * 12; i += WK_THREADS) scam[i] = a.cams[i];
-    if (tid < S * K) {
-        OmegaNorm n;
-        const double cnt = 4.0 * (double)P;
-        gn_mean_rstd(a.stats + tid * 6 + 0, cnt, n.m1, n.r1);
-        gn_mean_rstd(a.stats + tid * 6 + 2, cnt, n.m2, n.r2);
-        gn_mean_rstd(a.stats + tid * 6 + 4, cnt, n.m3, n.r3);
-        norms_all[tid] = n;
-    }
-    __syncthreads();
-    const int g = tid / WK_GROUP, lt = tid - g * WK_GROUP;
-    const uint32_t bar_id = 1 + g;
-    const float* depths = a.depth_values + plane_index(a.d_host, a.d_dev);
-    const float s_den = (float)S;
-    const unsigned row_bytes = (unsigned)W * 128u;
-    const int tiles_x = (W + WK_TC - 1) / WK_TC, tiles_y = (H + WK_TR - 1) / WK_TR;
-    const int ntiles = tiles_x * tiles_y;
-    const int my_tiles = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-    const int total = my_tiles * K;                    // items of this CTA: (tile slot, plane), planes innermost
-    // recipe role: this thread's pixel of the tile; gather role: 8-lane team `team`, channels 4 sub .. 4 sub + 3
-    const int rr = lt >> 3, rc = lt & 7;               // recipe pixel (row, column) = tile-local index lt
-    const int team = lt >> 3, sub = lt & 7;
-    const int tcol = team & 7, trow0 = (team >> 3) * 8; // the team's column segment: rows trow0 .. trow0 + 7 of column tcol
-    const unsigned char* refb = reinterpret_cast<const unsigned char*>(a.ref) + sub * 16;
-    for (int it = g; it < total; it += WK_G) {
-        const int tl = it / K, k = it - tl * K;
-        const int tile = (int)blockIdx.x + tl * (int)gridDim.x;
-        const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
-        const float depth = depths[k];
-        const int y = ty * WK_TR + rr, x = tx * WK_TC + rc;
-        const bool valid = y < H && x < W;
-        const size_t p = valid ? (size_t)y * W + x : 0;
-        uint64_t acc01[8], acc23[8];
-#pragma unroll 1
-        for (int v = 0; v < S; ++v) {
-            // ---- 1. recipe + reweight of (my pixel, view v)
-            WalkRec rec;
-            rec.w[0] = rec.w[1] = rec.w[2] = rec.w[3] = 0.f;
-            rec.base = 0u; rec.wv = 1.0f; rec.pad0 = rec.pad1 = 0u;
-            if (valid) {
-                float4 wts;
-                make_recipe(scam + v * 12, x, y, depth, W, H, a.align_corners != 0, wts, rec.base);
-                rec.w[0] = wts.x; rec.w[1] = wts.y; rec.w[2] = wts.z; rec.w[3] = wts.w;
-                const OmegaNorm nm = norms_all[k * S + v];
-                float a1[4], u[4], vv[4];
-                omega_u(a.q, nm, ldg4(a.t0 + ((size_t)(k * S + v) * P + p) * 4), a1, u);
-                omega_v(a.q, nm, u, vv);
-                const float wm = omega_w(a.q, nm, a1, vv);
-                if (a.reweight_out) a.reweight_out[((size_t)k * S + v) * P + p] = wm;
-                rec.wv = wm + 1.0f;
-            }
-            WalkRec* slot = recs[g][v & 1];
-            slot[lt] = rec;
-            asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(WK_GROUP) : "memory");
-            // ---- 2. gather the team's column segment (eight pixels), south lines kept as the next pixel's north lines
-            const unsigned char* svb = reinterpret_cast<const unsigned char*>(a.src + (size_t)v * a.view_stride) + sub * 16;
-            float4 pc = make_float4(0.f, 0.f, 0.f, 0.f), pd = pc;
-            unsigned want = 2u;                                     // (north-west line | column step) the registers hold; bit 1 = none
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const WalkRec* rp = slot + (trow0 + j) * WK_TC + tcol;
-                const float4 wq = *reinterpret_cast<const float4*>(rp->w);
-                const uint2 bw = *reinterpret_cast<const uint2*>(&rp->base);
-                const float wv = __uint_as_float(bw.y);
-                const unsigned o0 = bw.x & ~127u, o1 = o0 + ((bw.x & 1u) << 7), od = (bw.x & 2u) ? row_bytes : 0u;
-                const bool reuse = (bw.x & ~2u) == want;
-                float4 ta = pc, tb = pd;
-                if (!reuse) { ta = ldg4b(svb + o0); tb = ldg4b(svb + o1); }
-                const float4 tcn = ldg4b(svb + (o0 + od)), td = ldg4b(svb + (o1 + od));
-                const int yy = ty * WK_TR + trow0 + j, xx = tx * WK_TC + tcol;
-                const unsigned roff = (yy < H && xx < W) ? (unsigned)(yy * W + xx) * 128u : 0u;
-                const float4 rv = ldg4b(refb + roff);
-                const uint64_t p0 = pk2(wq.x, wq.x), p1 = pk2(wq.y, wq.y), p2 = pk2(wq.z, wq.z), p3 = pk2(wq.w, wq.w), pv = pk2(wv, wv);
-                const uint64_t g01 = fma2(pk2(td.x, td.y), p3, fma2(pk2(tcn.x, tcn.y), p2, fma2(pk2(tb.x, tb.y), p1, mul2(pk2(ta.x, ta.y), p0))));
-                const uint64_t g23 = fma2(pk2(td.z, td.w), p3, fma2(pk2(tcn.z, tcn.w), p2, fma2(pk2(tb.z, tb.w), p1, mul2(pk2(ta.z, ta.w), p0))));
-                const uint64_t d01 = sub2(g01, pk2(rv.x, rv.y)), d23 = sub2(g23, pk2(rv.z, rv.w));
-                const uint64_t t01 = mul2(pv, mul2(d01, d01)), t23 = mul2(pv, mul2(d23, d23));
-                if (v == 0) { acc01[j] = t01; acc23[j] = t23; }
-                else { acc01[j] = add2(acc01[j], t01); acc23[j] = add2(acc23[j], t23); }      // the reference adds the rounded product
-                pc = tcn; pd = td;
-                want = (o0 + od) | (bw.x & 1u);
-            }
-        }
-        // ---- 3. -acc / S -> operand planes (or fp32)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int yy = ty * WK_TR + trow0 + j, xx = tx * WK_TC + tcol;
-            const bool ok = yy < H && xx < W;
-            const size_t pp = ok ? (size_t)yy * W + xx : 0;
-            float4 acc;
-            upk2(acc01[j], acc.x, acc.y);
-            upk2(acc23[j], acc.z, acc.w);
-            const float4 r = make_float4(-__fdiv_rn(acc.x, s_den), -__fdiv_rn(acc.y, s_den), -__fdiv_rn(acc.z, s_den), -__fdiv_rn(acc.w, s_den));
-            if (a.cost_planes) {
-                uint2 hi, lo;
-                tc::split4_f16(r, hi, lo);
-                const bool odd = sub & 1;
-                const uint2 give = odd ? hi : lo;
-                uint2 got;
-                got.x = __shfl_xor_sync(0xffffffffu, give.x, 1);
-                got.y = __shfl_xor_sync(0xffffffffu, give.y, 1);
-                if (ok) {
-                    const size_t off = (((size_t)k * 8 + (odd ? 4 : 0) + (sub >> 1)) * P + pp) * 8;
-                    *reinterpret_cast<uint4*>(a.cost_planes + off) = odd ? make_uint4(got.x, got.y, lo.x, lo.y) : make_uint4(hi.x, hi.y, got.x, got.y);
-                }
-            } else if (ok) {
-                st4(a.cost + ((size_t)k * P + pp) * 32 + sub * 4, r);
-            }
-        }
-        // the next item's first recipe write goes to slot 0: every thread of the group must have finished reading slot 0 (views
-        // S-2 or S-1) -- with S == 1 or 2 the slots of consecutive items collide without this barrier
-        asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(WK_GROUP) : "memory");
-    }
-}
-
 // ------------------------------------------------------------------------------------------------ pass A1: warp cost
 // costv[k][v][p][c] = (warp_v(p; depth k)[c] - ref(p)[c])^2 for every pixel, view and plane of the batch, written once;
 // the omega stem conv (cost_stem_tc_kernel in stream mode) and pass D then read it back as plain streams, so the gather --
@@ -723,21 +555,13 @@ extern "C" int aarmvs_aggregate(const float* ref, const float* src, size_t view_
     }
     AARMVS_CHECK_ARG(ref && src && depth_values && cams);
     AARMVS_CHECK_ARG((size_t)H * W * 128 < 0xFFFFFFFFull);          // the gather recipes hold 32-bit byte offsets
-    const char* legacy = getenv("AARMVS_AGG_LEGACY");           // A/B switch: the 8-lanes-per-pixel kernel with shuffled recipes
-    if (legacy && legacy[0] == '1') {
-        const int ntiles = ((W + AG_TW - 1) / AG_TW) * ((H + AG_TH - 1) / AG_TH);
-        const int blocks = ntiles < 148 * AGG_MINB ? ntiles : 148 * AGG_MINB;
-        aggregate_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(ref, src, view_stride, H, W, S, planes, cams, q, depth_values, d_host,
-                                                                  d_dev, align_corners, t0, stats, cost, (__half*)cost_planes, reweight_out);
-        AARMVS_LAUNCH_RESULT();
-    }
-    WalkArgs wa = {};
-    wa.ref = ref; wa.src = src; wa.view_stride = view_stride; wa.H = H; wa.W = W; wa.S = S; wa.K = planes; wa.cams = cams; wa.q = q;
-    wa.depth_values = depth_values; wa.d_host = d_host; wa.d_dev = d_dev; wa.align_corners = align_corners; wa.t0 = t0; wa.stats = stats;
-    wa.cost = cost; wa.cost_planes = (__half*)cost_planes; wa.reweight_out = reweight_out;
-    const int wtiles = ((W + WK_TC - 1) / WK_TC) * ((H + WK_TR - 1) / WK_TR);
-    const int sms = aarmvs_sm_count();
-    if (sms <= 0) return AARMVS_ERR_ARG;
-    aggregate_walk_kernel<<<wtiles < sms ? wtiles : sms, WK_THREADS, 0, (cudaStream_t)stream>>>(wa);
+    // (a column-walking variant organised like pass A's gather -- one thread per pixel for the recipe and the reweight, 8-lane
+    //  teams walking eight-pixel column segments with line reuse and register accumulation over the views, bit-identical -- was
+    //  measured SLOWER, 0.68 vs 0.57 ms/plane at cfg2: 96-128 registers, one barrier per view and at most 24 resident warps against
+    //  this kernel's 32 barrier-free ones; profiles/r02_stage_variants.log)
+    const int ntiles = ((W + AG_TW - 1) / AG_TW) * ((H + AG_TH - 1) / AG_TH);
+    const int blocks = ntiles < 148 * AGG_MINB ? ntiles : 148 * AGG_MINB;
+    aggregate_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(ref, src, view_stride, H, W, S, planes, cams, q, depth_values, d_host,
+                                                              d_dev, align_corners, t0, stats, cost, (__half*)cost_planes, reweight_out);
     AARMVS_LAUNCH_RESULT();
 }
