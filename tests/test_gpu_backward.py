@@ -411,15 +411,17 @@ def test_training_step_gradients_match_reference():
     assert not bad, "\n".join(bad)
 
 
-@pytest.mark.parametrize("B,D", [(1, 7), (2, 7), (1, 11)])
-def test_batch_against_oracle_autograd(sd_dtu, B, D):
-    """B samples, D planes (partial plane batches) at 24x32: loss and all parameter gradients against autograd through the
+@pytest.mark.parametrize("H,W,B,D", [(24, 32, 1, 7), (24, 32, 2, 7), (24, 32, 1, 11), (128, 160, 1, 3), (72, 104, 2, 4)])
+def test_batch_against_oracle_autograd(sd_dtu, H, W, B, D):
+    """B samples, D planes (partial plane batches) at 24x32, at BASELINE config 5's tensor size 128x160 (every backward kernel with
+    many CTAs, several weight-gradient chunks, multi-block GroupNorm reductions) and at a ragged 72x104 with two samples on
+    concurrent streams: loss and all parameter gradients against autograd through the
     oracle's training forward + loss on the CPU in fp64 (the oracle's autograd is pinned to the reference's gradients in
     tests/test_oracle_golden.py::test_training_gradients).  The same oracle in fp32 -- i.e. what the reference itself computes --
     is measured against fp64 too: that is the noise floor of these sums (two samples' gradients partly cancel)."""
     import aarmvsnet_b200 as aa
     from oracle import aarmvs_oracle as orc
-    H, W, N = 24, 32, 3
+    N = 3
     s = aa.synth.make_sample(H, W, N, D, seed=17, batch=B, depth_mode="inverse")
     g = torch.Generator().manual_seed(18)
     depth_gt = 425.0 + 510.0 * torch.rand(B, H, W, generator=g)
@@ -439,7 +441,7 @@ def test_batch_against_oracle_autograd(sd_dtu, B, D):
     m = m.cuda().train()
     p2, _, _ = m(s["imgs"].cuda(), s["proj_matrices"].cuda(), s["depth_values"].cuda())
     loss, _ = aa.mvsnet_cls_loss(p2, depth_gt.cuda(), mask.cuda(), s["depth_values"].cuda())
-    print(f"B={B} D={D}: loss ours {loss.item():.7f}, oracle fp32 {loss32.item():.7f}, oracle fp64 {loss64.item():.7f}")
+    print(f"{H}x{W} B={B} D={D}: loss ours {loss.item():.7f}, oracle fp32 {loss32.item():.7f}, oracle fp64 {loss64.item():.7f}")
     torch.testing.assert_close(loss.detach().cpu().double(), loss64, rtol=5e-5, atol=1e-6)
     loss.backward()
     ours, floor = [], []
@@ -452,7 +454,7 @@ def test_batch_against_oracle_autograd(sd_dtu, B, D):
         floor.append(((g32[name].double() - want).abs().max().item() / scale, name))
     ours.sort(reverse=True)
     floor.sort(reverse=True)
-    print(f"B={B} D={D}: worst max-error / max-gradient vs fp64: ours {ours[0][0]:.2e} ({ours[0][1]}), the fp32 oracle {floor[0][0]:.2e} "
+    print(f"{H}x{W} B={B} D={D}: worst max-error / max-gradient vs fp64: ours {ours[0][0]:.2e} ({ours[0][1]}), the fp32 oracle {floor[0][0]:.2e} "
           f"({floor[0][1]}); ours top: " + ", ".join(f"{n} {r:.1e}" for r, n in ours[:5]))
     assert ours[0][0] <= max(2e-4, 4.0 * floor[0][0]), ours[:6]
 
