@@ -42,7 +42,7 @@ struct alignas(64) HeadTcArgs {
     // optional fused training loss (mvsnet_cls_loss, models/drmvsnet.py:347-381, without the [D][H][W] probability volume)
     const int* gt_index;        // [H*W] hypothesis nearest to the ground truth (0 where the mask is 0)
     const float* mask;          // [H*W]
-    float* gt_cost;             // [H*W] state: regularised cost at the ground-truth plane
+    float* gt_cost;             // [3][H*W] state: regularised cost at the ground-truth plane | running max | rescaled exp-sum
     double* loss_sum;           // += sum over pixels of mask * (log(sum_d exp(cost_d)) - cost_gt) at the last plane
 };
 
@@ -151,11 +151,20 @@ __global__ void __launch_bounds__(N_THREADS, CTAS_PER_SM) head_tc_kernel(const _
             tc::mbar_arrive(&tmem_empty[ab]);
             if (!valid) continue;
             const float acc = (__uint_as_float(r[0]) + __uint_as_float(r[8])) + a.bias;
-            float gc = 0.f;
+            float gc = 0.f, lse = 0.f;
             if (a.gt_index) {
                 const int gi = a.gt_index[p];
                 if (d == gi) { gc = acc; a.gt_cost[p] = acc; }
                 else if (d == a.num_depth - 1) gc = a.gt_cost[p];
+                // log-sum-exp of the costs as an online softmax (running max + rescaled sum), like the stable F.softmax of the
+                // reference's loss path (drmvsnet.py:291): the winner-take-all exp-sum below may overflow, this cannot
+                const float m0 = d == 0 ? -INFINITY : a.gt_cost[n + p];
+                const float s0 = d == 0 ? 0.f : a.gt_cost[2 * n + p];
+                const float m1 = fmaxf(m0, acc);
+                const float s1 = s0 * expf(m0 - m1) + expf(acc - m1);
+                a.gt_cost[n + p] = m1;
+                a.gt_cost[2 * n + p] = s1;
+                lse = m1 + logf(s1);
             }
             if (a.cost_volume) a.cost_volume[(size_t)d * n + p] = acc;
             const float prob = expf(acc);
@@ -172,7 +181,7 @@ __global__ void __launch_bounds__(N_THREADS, CTAS_PER_SM) head_tc_kernel(const _
             if (d == a.num_depth - 1) {
                 a.conf[p] = __fdiv_rn(mp, es);
                 // -log softmax(cost)[gt] = log(sum_d exp(cost_d)) - cost_gt, times the mask (drmvsnet.py:366-369)
-                if (a.gt_index) ce_sum += a.mask[p] * (logf(es) - gc);
+                if (a.gt_index) ce_sum += a.mask[p] * (lse - gc);
             }
         }
         if (a.gt_index && d == a.num_depth - 1) {

@@ -201,7 +201,7 @@ class Engine:
         ws["index"] = torch.empty(P, device=device, dtype=torch.int32)
         ws["cost_volume"] = torch.empty(D, P, **f32) if keep_cost else None
         # fused training loss (tensor-core path): nearest-hypothesis index, mask, cost at that plane, loss accumulator
-        ws["gt"] = ((torch.zeros(P, device=device, dtype=torch.int32), torch.zeros(P, **f32), torch.zeros(P, **f32),
+        ws["gt"] = ((torch.zeros(P, device=device, dtype=torch.int32), torch.zeros(P, **f32), torch.zeros(3, P, **f32),
                      torch.zeros(1, device=device, dtype=torch.float64)) if with_loss else None)
         self._ws[key] = ws
         return ws

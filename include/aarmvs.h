@@ -219,12 +219,13 @@ int aarmvs_head_wta(const aarmvs_conv_src* h4, int H, int W, const float* weight
  * read): two taps per K = 16 MMA.  weight_f16: DEVICE [5 pairs][2 taps][16 rows][8] fp16 with row 0 = hi(w), row 8 = lo(w)
  * for the tap pairs (0,1) (2,3) (4,5) (6,7) (8,-) of tap = ky * 3 + kx; other arguments as aarmvs_head_wta.
  * Optional fused training loss (mvsnet_cls_loss, models/drmvsnet.py:347-381, without the [D][H][W] probability volume):
- * gt_index [H*W] = hypothesis nearest to the ground truth (0 where gt_mask is 0), gt_mask [H*W], gt_cost [H*W] state;
- * at the last plane *loss_sum += sum_p gt_mask[p] * (log(sum_d exp(cost_d[p])) - cost_gt[p]).  All four NULL: no loss.
- * Range: the exp-sum is the winner-take-all update's own (drmvsnet.py:324 takes exp(cost) without subtracting a maximum), so
- * like the reference's test phase it overflows for a regularised cost above ~88; the shipped weights produce costs in
- * [-41, -17].  The differentiable training path (EMVSNet.forward under autograd, aarmvs_loss_grad) goes through
- * a max-subtracted softmax and has no such bound.  Likewise the fp16 (hi, lo) operand split assumes |x| < 65 504. */
+ * gt_index [H*W] = hypothesis nearest to the ground truth (0 where gt_mask is 0), gt_mask [H*W], gt_cost [3][H*W] state (cost
+ * at the ground-truth plane | running max | rescaled exp-sum); at the last plane
+ * *loss_sum += sum_p gt_mask[p] * (log(sum_d exp(cost_d[p])) - cost_gt[p]), the log-sum-exp evaluated as an online softmax, so
+ * the loss stays finite where the reference's F.softmax does.  All four NULL: no loss.
+ * Range of the winner-take-all part: drmvsnet.py:324 takes exp(cost) without subtracting a maximum, so like the reference's
+ * test phase max_prob / exp_sum overflow for a regularised cost above ~88; the shipped weights produce costs in [-41, -17]
+ * (SURVEY.md §7).  The fp16 (hi, lo) operand split of the tensor-core kernels assumes |x| < 65 504. */
 int aarmvs_head_wta_tc(const void* h4_planes, int H, int W, const void* weight_f16, const float* bias_host,
                        const float* depth_values, int num_depth, int d_host, const int* d_dev, float* max_prob,
                        float* depth_map, float* exp_sum, int* index_map, float* conf, float* cost_volume,

@@ -135,3 +135,24 @@ def test_loss_gradient_wrt_cost_matches_autograd():
     scale = cost.grad.abs().max().item()
     torch.testing.assert_close(got, cost.grad, rtol=1e-4, atol=1e-5 * scale)
     assert (got[:, g["mask"][0] == 0] == 0).all()                                           # masked pixels carry no gradient
+
+
+def test_fused_loss_is_shift_invariant_and_finite_where_exp_overflows():
+    """The fused cross entropy is a log-sum-exp evaluated as an online softmax: adding 130 to every regularised cost (conv_0's
+    bias) overflows exp() -- the winner-take-all exp-sum becomes inf, as it would in the reference's test phase -- but leaves
+    the loss finite and unchanged, like the reference's F.softmax-based loss."""
+    import aarmvsnet_b200 as aa
+    g = load_golden("train_32x40_n3_d6.pt")
+    sd = {k: v.clone() for k, v in load_weights(g["ckpt"]).items()}
+    args = [g[k].cuda() for k in ("imgs", "proj_matrices", "depth_values")]
+    losses = []
+    for shift in (0.0, 130.0):
+        m = aa.EMVSNet(disparity_level=32, image_scale=1.0, max_h=32, max_w=40, return_depth=False)
+        sd2 = dict(sd)
+        sd2["cost_regularization.conv_0.bias"] = sd["cost_regularization.conv_0.bias"] + shift
+        m.load_state_dict(sd2, strict=True)
+        loss, _ = m.cuda().eval().forward_loss(*args, g["depth_gt"].cuda(), g["mask"].cuda())
+        losses.append(loss.item())
+    assert all(torch.isfinite(torch.tensor(losses)))
+    assert abs(losses[1] - losses[0]) <= 2e-4 * abs(losses[0]), losses
+    assert abs(losses[0] - float(g["loss"])) <= 2e-4 * float(g["loss"])
