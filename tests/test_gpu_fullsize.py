@@ -187,3 +187,16 @@ def test_cfg2_full_resolution_few_planes_against_oracle():
     assert mismatch <= MISMATCH_BAR
     assert (out["depth"].cpu()[same] == ref["depth"][same]).all()
     torch.testing.assert_close(out["photometric_confidence"].cpu()[same], ref["photometric_confidence"][same], rtol=1e-3, atol=1e-3)
+
+
+def test_cfg4_full_resolution_few_planes_against_oracle():
+    """BASELINE cfg4's image size, view count and weights (1920x1056, N=7, model_blended_v2.ckpt, inverse depths) with D=4 planes
+    against the CPU oracle on the box's host cores (~45 s): the full D=512 run is only property-checked."""
+    from aarmvsnet_b200 import synth
+    from oracle import aarmvs_oracle as orc
+    H, W, N, D = 1056, 1920, 7, 4
+    s = synth.make_sample(H, W, N, D, seed=6, depth_mode="inverse", smooth=True)
+    out = _run(_model(H, W, ckpt="model_blended_v2.ckpt"), s)
+    ref = orc.forward_test(load_weights("model_blended_v2.ckpt"), s["imgs"], s["proj_matrices"], s["depth_values"], return_index=True,
+                           return_cost=True)
+    _compare("cfg4 resolution 1920x1056 N=7 D=4 (blended)", out, ref, s)
