@@ -158,7 +158,7 @@ class Backward:
             b[cn] = [b["rec2"][r][lay[i][1]:lay[i][1] + lay[i][2]].view(Pi[i], _HID[i]) for i in range(5)]
         b["dcr"] = torch.zeros(P, **f32)
         b["plane"] = torch.zeros(1, device=dev, dtype=torch.int32)
-        b["feat"] = torch.empty(N, P, 32, **f32)
+        b["feat"] = self.eng.feature_buffer(N, H, W, dev)
         b["cams"] = torch.empty(S, 12, **f32)
         b["depths"] = torch.empty(0, **f32)
         b["graph"] = None

@@ -193,15 +193,23 @@ __device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
     return r;
 }
 
-// Sample position of pixel (x, y) in one source view at one depth -> the four bilinear weights (0 for corners outside the
-// image) and the byte offset of the clamped north-west line | column step | row step << 1 (TapRec.w / TapRec.base).
+// Gather recipe of pixel (x, y) in one source view at one depth: the four bilinear weights in tap order north-west, north-east,
+// south-west, south-east and the byte offset `base` of the north-west line.  The taps are read at base, base + 128,
+// base + 128 W and base + 128 W + 128 -- fixed steps, so the three neighbours are immediate / one-add addresses -- and a
+// corner outside the image has weight 0, which reproduces ATen's skipped tap exactly (its line is still read: the caller
+// guarantees (W + 1) * 128 readable, finite bytes behind the last source map).  On the low side nothing is read before a map:
+// with the west (north) column (row) outside, the two valid taps move into the west (north) weight slots and the base is
+// clamped to column (row) 0; the blend fma(se, w, fma(sw, w, fma(ne, w, nw * w))) only gains exact +-0 terms that way, the
+// result is bit-identical.
 __device__ __forceinline__ void make_recipe(const float* cam, int x, int y, float depth, int W, int H, bool align_corners,
                                             float4& wts, unsigned& base) {
     float ix, iy;
     sweep_position(cam, (float)x, (float)y, depth, W, H, align_corners, ix, iy);
     const Taps t = make_taps(ix, iy, W, H);
-    wts = make_float4(t.o_nw >= 0 ? t.w_nw : 0.f, t.o_ne >= 0 ? t.w_ne : 0.f, t.o_sw >= 0 ? t.w_sw : 0.f, t.o_se >= 0 ? t.w_se : 0.f);
-    const int xw = min(max(t.xi, 0), W - 1), xe = min(max(t.xi + 1, 0), W - 1);
-    const int yn = min(max(t.yi, 0), H - 1), ys = min(max(t.yi + 1, 0), H - 1);
-    base = (unsigned)(yn * W + xw) * 128u | (unsigned)(xe - xw) | ((unsigned)(ys - yn) << 1);
+    float w0 = t.o_nw >= 0 ? t.w_nw : 0.f, w1 = t.o_ne >= 0 ? t.w_ne : 0.f, w2 = t.o_sw >= 0 ? t.w_sw : 0.f, w3 = t.o_se >= 0 ? t.w_se : 0.f;
+    int xi = t.xi, yi = t.yi;                       // north-west corner: -1 .. size-1 on each axis (0 when no corner is inside)
+    if (xi < 0) { w0 = w1; w1 = 0.f; w2 = w3; w3 = 0.f; xi = 0; }
+    if (yi < 0) { w0 = w2; w1 = w3; w2 = 0.f; w3 = 0.f; yi = 0; }
+    wts = make_float4(w0, w1, w2, w3);
+    base = (unsigned)(yi * W + xi) * 128u;
 }

@@ -111,10 +111,9 @@ struct StemArgs {
 #endif
 
 // Gather recipe of one staged pixel (32 bytes; the L1 data pipe bounds this kernel, so the record is kept to two loads):
-// the four bilinear weights (0 for corners outside the image, which reproduces the skipped tap exactly), the BYTE offset
-// of the clamped north-west line with the clamped column / row steps in bits 0 / 1 (a zero-weight corner may read any
-// valid line), and the byte offset of the reference pixel with the "this fill owns the pixel's costv line" flag in
-// bit 0 (-1: the pixel lies outside the image, its cost is the conv's zero padding).
+// the four bilinear weights and the BYTE offset of the north-west line (common.cuh: make_recipe -- fixed +128 / +row steps,
+// weight 0 for a corner outside the image), and the byte offset of the reference pixel with the "this fill owns the pixel's
+// costv line" flag in bit 0 (-1: the pixel lies outside the image, its cost is the conv's zero padding).
 struct __align__(16) TapRec {
     float w[4];
     unsigned base;
@@ -127,6 +126,9 @@ __device__ __forceinline__ void sts64(uint32_t addr, uint2 v) {
     asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(v.x), "r"(v.y) : "memory");
 }
 
+// KEEP_CV: also store (warp - ref)^2 of the tile's interior pixels to a.costv (the training backward's per-plane recompute and
+// Engine(keep_costv=True)); a template parameter so that the default kernel carries none of its predicated-off instructions.
+template <bool KEEP_CV>
 __global__ void __launch_bounds__(N_THREADS, 1) cost_stem_tc_kernel(const __grid_constant__ StemArgs a) {
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* sB = smem;
@@ -208,7 +210,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) cost_stem_tc_kernel(const __grid
         // a thread always handles the same 16-byte slice (4 channels) of its pixels: item j is pixel px0 + (GROUP_THREADS / 8) j
         const int c4i = lt & 7, px0 = lt >> 3;
         const uint32_t st_thread = tc::smem_u32(stage) + (uint32_t)((c4i >> 1) * AROWS * 16 + (c4i & 1) * 8);
-        const bool keep_cv = a.costv_mode == 1;
+        constexpr bool keep_cv = KEEP_CV;
         const unsigned row_bytes = (unsigned)a.W * 128u;
         // fill it = g, g + G, ... decoded incrementally as (tile slot tl, view v, plane k): it = (tl * S + v) * K + k
         int tl = g / SK, v = (g % SK) / a.K, k = g % a.K, n = 0;
@@ -229,7 +231,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) cost_stem_tc_kernel(const __grid
                     {   // the gather of this fill starts thousands of cycles from now (after the current fill's MMAs): pull its
                         // source lines towards L1 meanwhile (ncu: 40 % of the warp stalls are the gather's first use of a load)
                         const unsigned char* sb = reinterpret_cast<const unsigned char*>(a.src + (size_t)v_ * a.view_stride);
-                        const unsigned o0 = rec.base & ~127u, ox = (rec.base & 1u) << 7, od = (rec.base & 2u) ? (unsigned)a.W * 128u : 0u;
+                        const unsigned o0 = rec.base, ox = 128u, od = (unsigned)a.W * 128u;
                         asm volatile("prefetch.global.L1 [%0];" ::"l"(sb + o0));
                         if (od) asm volatile("prefetch.global.L1 [%0];" ::"l"(sb + (o0 + od)));
                         if (ox && (cc == HC - 1 || STEM_PREFETCH > 1)) {      // the east lines are the next pixel's west lines, except in the last column
@@ -259,7 +261,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) cost_stem_tc_kernel(const __grid
             if (pf) pp[1] = clock64();
             // ---- 2. gather, (warp - ref)^2, split, stage
             const float* sv = a.src + (size_t)v * a.view_stride;
-            float* costv_slot = a.costv ? a.costv + ((size_t)(k * a.S + v) * P) * 32 : nullptr;
+            float* costv_slot = KEEP_CV ? a.costv + ((size_t)(k * a.S + v) * P) * 32 : nullptr;
             {
                 const unsigned char* svb = reinterpret_cast<const unsigned char*>(sv) + c4i * 16;
                 const unsigned char* refb = reinterpret_cast<const unsigned char*>(a.ref) + c4i * 16;
@@ -308,7 +310,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) cost_stem_tc_kernel(const __grid
                     const int ut = u / HC;
                     int pxr = ut * (UROWS - 1) * HC + u;                  // (row ut * UROWS, column u - ut * HC)
                     float4 pc = make_float4(0.f, 0.f, 0.f, 0.f), pd = pc;
-                    unsigned want = 2u;                                   // (north-west line | column step) the registers hold; bit 1 = none
+                    unsigned want = 1u;                                   // north-west line offset the registers hold (odd = none: offsets are multiples of 128)
 #pragma unroll 1
                     for (int jb = 0; jb < UROWS; jb += 2, pxr += 2 * HC) {
                         // (written out for two rows: all loads of both rows are issued before the first use; a generic
@@ -318,23 +320,27 @@ __global__ void __launch_bounds__(N_THREADS, 1) cost_stem_tc_kernel(const __grid
                         const TapRec* rec1 = rec0 + HC;
                         const float4 wq0 = *reinterpret_cast<const float4*>(rec0->w), wq1 = *reinterpret_cast<const float4*>(rec1->w);
                         const uint2 br0 = *reinterpret_cast<const uint2*>(&rec0->base), br1 = *reinterpret_cast<const uint2*>(&rec1->base);
-                        const unsigned a0 = br0.x & ~127u, a1 = a0 + ((br0.x & 1u) << 7), ad = (br0.x & 2u) ? row_bytes : 0u;
-                        const unsigned b0 = br1.x & ~127u, b1 = b0 + ((br1.x & 1u) << 7), bd = (br1.x & 2u) ? row_bytes : 0u;
-                        // a pixel's north lines (and column step) = the south lines of the pixel above: taken from registers
-                        const bool ra = (br0.x & ~2u) == want;
-                        const bool rb = (br1.x & ~2u) == ((a0 + ad) | (br0.x & 1u));
+                        // the four lines of a pixel: north-west at svb + base, the others at fixed steps (+128, +row, +row + 128):
+                        // one 64-bit add per row, the column step is an immediate of the load
+                        const unsigned char* n0 = svb + br0.x;
+                        const unsigned char* s0 = n0 + row_bytes;
+                        const unsigned char* n1 = svb + br1.x;
+                        const unsigned char* s1 = n1 + row_bytes;
+                        // a pixel's north lines = the south lines of the pixel above: taken from registers
+                        const bool ra = br0.x == want;
+                        const bool rb = br1.x == br0.x + row_bytes;
                         float4 ta0 = pc, tb0 = pd, ta1, tb1;
-                        if (!ra) { ta0 = ldg4b(svb + a0); tb0 = ldg4b(svb + a1); }
-                        const float4 tc0 = ldg4b(svb + (a0 + ad)), td0 = ldg4b(svb + (a1 + ad));
-                        if (!rb) { ta1 = ldg4b(svb + b0); tb1 = ldg4b(svb + b1); }
-                        const float4 tc1 = ldg4b(svb + (b0 + bd)), td1 = ldg4b(svb + (b1 + bd));
+                        if (!ra) { ta0 = ldg4b(n0); tb0 = ldg4b(n0 + 128); }
+                        const float4 tc0 = ldg4b(s0), td0 = ldg4b(s0 + 128);
+                        if (!rb) { ta1 = ldg4b(n1); tb1 = ldg4b(n1 + 128); }
+                        const float4 tc1 = ldg4b(s1), td1 = ldg4b(s1 + 128);
                         const float4 rv0 = ldg4b(refb + ((unsigned)max((int)br0.y, 0) & ~127u));
                         const float4 rv1 = ldg4b(refb + ((unsigned)max((int)br1.y, 0) & ~127u));
                         if (rb) { ta1 = tc0; tb1 = td0; }
                         finish(ta0, tb0, tc0, td0, rv0, wq0, (int)br0.y, pxr, true);          // units never leave the staged tile
                         finish(ta1, tb1, tc1, td1, rv1, wq1, (int)br1.y, pxr + HC, true);
                         pc = tc1; pd = td1;
-                        want = (b0 + bd) | (br1.x & 1u);
+                        want = br1.x + row_bytes;
                     }
                 }
 #else
@@ -348,7 +354,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) cost_stem_tc_kernel(const __grid
                         wq[j] = *reinterpret_cast<const float4*>(rec->w);
                         const uint2 br = *reinterpret_cast<const uint2*>(&rec->base);
                         rk[j] = (int)br.y;
-                        const unsigned o0 = br.x & ~127u, o1 = o0 + ((br.x & 1u) << 7), od = (br.x & 2u) ? row_bytes : 0u;
+                        const unsigned o0 = br.x, o1 = o0 + 128u, od = row_bytes;
                         ta[j] = ldg4b(svb + o0);
                         tb[j] = ldg4b(svb + o1);
                         tcn[j] = ldg4b(svb + (o0 + od));
@@ -472,16 +478,18 @@ int launch_cost_stem_tc(const float* ref, const float* src, size_t view_stride, 
     a.dbg = g_dbg;
     a.prof = g_stem_prof;
 #endif
-    static unsigned long long smem_ok = 0;
+    static unsigned long long smem_ok0 = 0, smem_ok1 = 0;
     constexpr int SMEM_CAP = 227 * 1024 - 2048;      // the kernel also has ~1 KB of static shared memory
     static_assert(SMEM_FIXED + STAT_ROWS * 8 * 8 <= SMEM_CAP, "shared memory budget");
-    if (cudaError_t e = ensure_dyn_smem(cost_stem_tc_kernel, SMEM_CAP, smem_ok)) return (int)e;
+    if (cudaError_t e = costv_mode == 1 ? ensure_dyn_smem(cost_stem_tc_kernel<true>, SMEM_CAP, smem_ok1)
+                                        : ensure_dyn_smem(cost_stem_tc_kernel<false>, SMEM_CAP, smem_ok0)) return (int)e;
     const int SMEM = SMEM_FIXED + STAT_ROWS * planes * S * 8;
     AARMVS_CHECK_ARG(SMEM <= SMEM_CAP);          // planes * S <= aarmvs_cost_stem_tc_max_slots()
     const int ntiles = ((W + TCOL - 1) / TCOL) * ((H + TR - 1) / TR);
     const int sms = aarmvs_sm_count();
     if (sms <= 0) return AARMVS_ERR_ARG;
-    cost_stem_tc_kernel<<<ntiles < sms ? ntiles : sms, N_THREADS, SMEM, (cudaStream_t)stream>>>(a);
+    if (costv_mode == 1) cost_stem_tc_kernel<true><<<ntiles < sms ? ntiles : sms, N_THREADS, SMEM, (cudaStream_t)stream>>>(a);
+    else cost_stem_tc_kernel<false><<<ntiles < sms ? ntiles : sms, N_THREADS, SMEM, (cudaStream_t)stream>>>(a);
     AARMVS_LAUNCH_RESULT();
 }
 }  // namespace

@@ -243,7 +243,7 @@ aggregate_kernel(const float* __restrict__ ref, const float* __restrict__ src, s
             uint64_t acc01 = 0ull, acc23 = 0ull;
             for (int v0 = 0; v0 < S; v0 += 8) {
                 // this lane's view: gather recipe (four weights, 0 for a corner outside the image = the skipped tap; byte offset of
-                // the clamped north-west line | column step | row step << 1, as in pass A) and reweight
+                // the north-west line, as in pass A) and reweight
                 const int mv = v0 + sub;
                 float4 rw = make_float4(0.f, 0.f, 0.f, 0.f);
                 unsigned rb = 0u;
@@ -264,8 +264,9 @@ aggregate_kernel(const float* __restrict__ ref, const float* __restrict__ src, s
                     const float w0 = __shfl_sync(0xffffffffu, rw.x, e, 8), w1 = __shfl_sync(0xffffffffu, rw.y, e, 8);
                     const float w2 = __shfl_sync(0xffffffffu, rw.z, e, 8), w3 = __shfl_sync(0xffffffffu, rw.w, e, 8);
                     const float wv = __shfl_sync(0xffffffffu, wm, e, 8) + 1.0f;
-                    const unsigned o0 = base & ~127u, o1 = o0 + ((base & 1u) << 7), od = (base & 2u) ? row_bytes : 0u;
-                    const float4 ta = ldg4b(sv + o0), tb = ldg4b(sv + o1), tcn = ldg4b(sv + (o0 + od)), td = ldg4b(sv + (o1 + od));
+                    const unsigned char* nl = sv + base;                 // north-west line; the others at fixed steps (make_recipe)
+                    const unsigned char* sl = nl + row_bytes;
+                    const float4 ta = ldg4b(nl), tb = ldg4b(nl + 128), tcn = ldg4b(sl), td = ldg4b(sl + 128);
                     // blend in ATen's order fma(se, w, fma(sw, w, fma(ne, w, nw * w))), (warp - ref)^2, * (1 + w_v): packed fp32 pairs,
                     // IEEE per lane = bit-identical to the scalar chains
                     const uint64_t p0 = pk2(w0, w0), p1 = pk2(w1, w1), p2 = pk2(w2, w2), p3 = pk2(w3, w3), pv = pk2(wv, wv);

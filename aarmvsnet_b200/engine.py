@@ -157,7 +157,7 @@ class Engine:
         P, S = H * W, N - 1
         K = min(self.plane_batch, D)
         ws = {"H": H, "W": W, "N": N, "D": D, "K": K, "graph": None, "warm": False}
-        ws["feat"] = torch.empty(N, P, 32, **f32)
+        ws["feat"] = self.feature_buffer(N, H, W, device)
         ws.update(self._feat_scratch(H, W, device))
         # plane sweep
         ws["t0"] = torch.empty(K, S, P, 4, **f32)
@@ -205,6 +205,14 @@ class Engine:
                      torch.zeros(1, device=device, dtype=torch.float64)) if with_loss else None)
         self._ws[key] = ws
         return ws
+
+    @staticmethod
+    def feature_buffer(N, H, W, device):
+        """[N][H*W][32] fp32 feature maps followed by (W + 1) zeroed pixels: the gather kernels read a sample's four lines at
+        fixed steps from the north-west one, so a zero-weight east / south corner of the last map's last row may touch up to
+        (W + 1) * 128 bytes behind it (include/aarmvs.h: aarmvs_cost_stem_tc, aarmvs_aggregate)."""
+        flat = torch.zeros((N * H * W + W + 1) * 32, device=device, dtype=torch.float32)
+        return flat[: N * H * W * 32].view(N, H * W, 32)
 
     def _feat_scratch(self, H, W, device):
         """FeatNet scratch (reused for every view), separate from the sweep workspace so features() allocates only this."""

@@ -72,7 +72,8 @@ def aggregate_plane(model, ref_fea, src_feas, ref_proj, src_projs, depth_value, 
     w = eng._weights(dev)
     _, H, W = ref_fea.shape
     S, P = len(src_feas), H * W
-    feat = torch.stack([_nhwc(f.float()) for f in [ref_fea] + list(src_feas)])
+    feat = Engine.feature_buffer(S + 1, H, W, dev)               # with the readable slack the gather kernels require behind it
+    feat.copy_(torch.stack([_nhwc(f.float()) for f in [ref_fea] + list(src_feas)]))
     cams = Engine.relative_cameras(torch.stack([ref_proj] + list(src_projs))).to(dev)
     depths = torch.tensor([float(depth_value)], device=dev)
     t0 = torch.empty(S, P, 4, device=dev)

@@ -109,7 +109,10 @@ int aarmvs_cost_stem(const float* ref, const float* src, size_t view_stride, int
  * (others zero): per tile the conv is 9 taps x 2 K-steps x (A_hi, A_lo) MMAs with N = 16, taps addressed by descriptor.
  * costv [planes][S][H*W][32] fp32 = (warp - ref)^2; costv_mode 0: unused; 1: WRITTEN here (interior pixels of each tile)
  * so that aarmvs_aggregate can skip its gather -- the gather then runs exactly once per pixel, view and plane.
- * H * W * 128 < 2^31 (the gather recipes hold 32-bit byte offsets): larger images return AARMVS_ERR_ARG. */
+ * H * W * 128 < 2^31 (the gather recipes hold 32-bit byte offsets): larger images return AARMVS_ERR_ARG.
+ * The four lines of a bilinear sample are read at fixed steps from the north-west one (+128, +128 W, +128 W + 128 bytes), a
+ * corner outside the image with weight 0: every source map must be followed by (W + 1) * 128 readable bytes holding finite
+ * values (the next view's map, or zeroed slack behind the last one -- Engine.feature_buffer); nothing is read before a map. */
 int aarmvs_cost_stem_tc_max_slots(void);   /* upper bound of planes * S per launch (shared-memory GroupNorm partial sums) */
 int aarmvs_cost_stem_tc(const float* ref, const float* src, size_t view_stride, int H, int W, int S, const float* cams,
                         const void* stem_w_f16, const float* stem_b_host, const float* depth_values, int d_host,
@@ -129,8 +132,8 @@ int aarmvs_omega_stats(int stage, const float* t0, int H, int W, int S, int plan
                        double* stats, void* stream);
 
 /* Pass D: cost[p][c] = -(sum_v (omega_v(p) + 1) * (warp_v - ref)^2) / S  (models/drmvsnet.py:311-319), the input
- * of the recurrent regulariser.  costv: NULL = gather again; else pass A's costv_out, read back as a pure stream (ref, src,
- * cams, depth_values are then unused).  reweight_out: optional omega maps (operator seam / tests), may be NULL.
+ * of the recurrent regulariser.  costv: NULL = gather again (same readable-slack requirement behind the source maps as
+ * aarmvs_cost_stem_tc); else pass A's costv_out, read back as a pure stream (ref, src, cams, depth_values are then unused).  reweight_out: optional omega maps (operator seam / tests), may be NULL.
  * cost_planes: write the result as fp16 (hi, lo) operand planes [planes][2][4][H][W][8] (see aarmvs_plane_src) instead of
  * fp32 `cost`, which may then be NULL. */
 int aarmvs_aggregate(const float* ref, const float* src, size_t view_stride, int H, int W, int S, const float* cams,
