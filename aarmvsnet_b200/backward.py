@@ -140,7 +140,7 @@ class Backward:
             b[f"gsum{i}"] = torch.zeros(4, device=dev, dtype=torch.float64)
         b["dpool0"] = torch.empty(P // 4, 16, **f32)
         b["dpool1"] = torch.empty(P // 16, 16, **f32)
-        b["gates"] = [torch.empty(Pi[i], 4 * _HID[i], **f32) for i in range(5)]
+        b["gates_pp"] = torch.zeros(5, device=dev, dtype=torch.int64)     # bases of the sample's five gate histories (forward)
         b["dgates"] = [torch.empty(Pi[i], 4 * _HID[i], **f32) for i in range(5)]
         b["dh"] = [torch.zeros(Pi[i], _HID[i], **f32) for i in range(5)]
         b["dhprev"] = [torch.zeros(Pi[i], _HID[i], **f32) for i in range(5)]
@@ -254,6 +254,8 @@ class Backward:
         if b["depths"].numel() != D:
             b["depths"], b["graph"] = torch.empty(D, device=self.dev, dtype=torch.float32), None
         b["depths"].copy_(saved["depths"])
+        for i, gh in enumerate(saved["gates"]):
+            b["gates_pp"][i].fill_(gh.data_ptr())
         for d in range(D - 1, -1, -1):
             b["rec2"].copy_(state[d:d + 2])                   # [0] = state entering plane d, [1] = state after it
             b["dcr"].copy_(dcost_volume[d])
@@ -309,9 +311,7 @@ class Backward:
             self.gn_apply(b[f"up{i}raw"], 4 * hin * win, 16, 2, b[f"gsum{i}"], bw[f"deconv{i}.gn"], b[f"up{i}"])
         xin = [[_seg(b["cost"], 32)], [_seg(b["pool0"], 16)], [_seg(b["pool1"], 16)], [_seg(b["up0"], 16), _seg(h[1], 16)],
                [_seg(b["up1"], 16), _seg(h[0], 16)]]
-        for i in range(5):
-            self.conv(xin[i] + [_seg(hp[i], _HID[i])], hw[i][0], hw[i][1], [_seg(b["gates"][i], 4 * _HID[i])], hw[i][0], hw[i][1], 3, 1,
-                      False, bw[f"cell{i}.w"], bw[f"cell{i}.b"])
+        # (the cells' gates are not recomputed: the training forward stored them activated, saved["gates"])
 
         # ---------------- backward of the plane.  b["dh"][i] enters holding dL/dh_i^d from plane d+1 (cell i's h_prev input)
         dh, dhp, dc = b["dh"], b["dhprev"], b["dc"]
@@ -321,8 +321,8 @@ class Backward:
 
         def cell_bwd(i, outs):
             # at plane 0 the staged previous state is the zero record: c_prev = h_prev = 0 (module.py:94-96)
-            capi.check(lib.aarmvs_lstm_gates_bwd(_ptr(b["gates"][i]), _ptr(cp[i]), _ptr(c[i]), _ptr(dh[i]), _ptr(dc[i]), _ptr(b["dgates"][i]),
-                                                 hw[i][0] * hw[i][1], _HID[i], st), "aarmvs_lstm_gates_bwd")
+            capi.check(lib.aarmvs_lstm_gates_bwd_act(_ptr(b["gates_pp"], i), 0, dptr, _ptr(cp[i]), _ptr(c[i]), _ptr(dh[i]), _ptr(dc[i]),
+                                                     _ptr(b["dgates"][i]), hw[i][0] * hw[i][1], _HID[i], st), "aarmvs_lstm_gates_bwd_act")
             self.conv([_seg(b["dgates"][i], 4 * _HID[i])], hw[i][0], hw[i][1], outs + [_seg(dhp[i], _HID[i])], hw[i][0], hw[i][1], 3, 1, True,
                       bw[f"cell{i}.wT"])
             self.wgrad(xin[i] + [_seg(hp[i], _HID[i])], hw[i][0], hw[i][1], b["dgates"][i], hw[i][0], hw[i][1], 4 * _HID[i], 3, 1,

@@ -75,7 +75,7 @@ PROTOTYPES = {
     "aarmvs_split_planes": (_I, [_SRCP, _I, _I, _P, _P]),
     "aarmvs_cell_state_floats": (_SZ, [_I, _I, _I]),
     "aarmvs_convlstm_cell": (_I, [_SRCP, _I, _I, _I, _I, _I, _P, _P, _P, _P, _I, _P, _P]),
-    "aarmvs_convlstm_cell_tc": (_I, [_PLSP, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _I, _P, _P]),
+    "aarmvs_convlstm_cell_tc": (_I, [_PLSP, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P]),
     "aarmvs_deconv2x_tc": (_I, [_PLSP, _I, _I, _P, c_float_p, _P, _P, _P, _P, _I, _P, _P]),
     "aarmvs_deconv2x": (_I, [_SRCP, _I, _I, c_float_p, c_float_p, _P, _P, _I, _P, _P]),
     "aarmvs_head_wta": (_I, [_SRCP, _I, _I, c_float_p, c_float_p, _P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
@@ -91,6 +91,7 @@ PROTOTYPES = {
     "aarmvs_gn_relu_apply": (_I, [_P, _SZ, _I, _I, _P, _P, _P, _I, _P, _P]),
     "aarmvs_gn_relu_bwd": (_I, [_I, _P, _P, _SZ, _I, _I, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P]),
     "aarmvs_lstm_gates_bwd": (_I, [_P, _P, _P, _P, _P, _P, _SZ, _I, _P]),
+    "aarmvs_lstm_gates_bwd_act": (_I, [_P, _I, _P, _P, _P, _P, _P, _P, _SZ, _I, _P]),
     "aarmvs_maxpool2": (_I, [_P, _I, _I, _I, _P, _P]),
     "aarmvs_maxpool2_bwd": (_I, [_P, _P, _I, _I, _I, _P, _P]),
     "aarmvs_aggregate_bwd": (_I, [_P, _P, _P, _I, _SZ, _P, _P, _P]),

@@ -252,6 +252,220 @@ __global__ void __launch_bounds__(WG_THREADS) conv_wgrad_kernel(const __grid_con
     }
 }
 
+// ------------------------------------------------------------------------------------------------ weight gradient, 3x3 stride 1
+// The per-plane layers (the five cells, omega's stem): the same sum as conv_wgrad_kernel, organised for FMA issue instead of
+// shared-memory traffic.  A CTA stages a tile of 8 x 32 output pixels ONCE for all nine taps -- X with its halo, dY, both zero
+// padded outside the image so the inner loop has no predicates -- and each of its nine warps owns one tap: a lane accumulates
+// 4 input x 8 output channels, i.e. 32 FMAs per pixel against three LDS.128 (X: one line shared by the lanes of a channel
+// quad, dY: two lines of 16 bytes per lane, contiguous over the lanes).  LCO lanes sit along the output channels:
+// LCO = 8 / 4 / 2 covers 64 / 32 / 16 output x 16 / 32 / 64 input channels per CTA (blockIdx.y walks the input channel
+// blocks).  A CTA walks `gridDim.x`-strided tiles with its accumulators in registers; fp32 atomics once at the end.
+constexpr int W3_TH = 8, W3_TW = 32, W3_IH = W3_TH + 2, W3_IW = W3_TW + 2, W3_THREADS = 288;
+
+template <int LCO>
+__global__ void __launch_bounds__(W3_THREADS) conv_wgrad3_kernel(const __grid_constant__ WGArgs a) {
+    constexpr int CO = 8 * LCO, CI = 4 * (32 / LCO);
+    extern __shared__ __align__(16) float sm3[];
+    float* xs = sm3;                                     // [W3_IH][W3_IW][CI]
+    float* ds = sm3 + W3_IH * W3_IW * CI;                // [W3_TH * W3_TW][CO]
+    const int tid = threadIdx.x, lane = tid & 31, tap = tid >> 5;
+    const int ky = tap / 3, kx = tap - ky * 3;
+    const int ci4 = lane / LCO, co8 = lane % LCO;
+    const int ci0 = blockIdx.y * CI;
+    const int tiles_x = (a.Wy + W3_TW - 1) / W3_TW, tiles_y = (a.Hy + W3_TH - 1) / W3_TH;
+    const bool want_bias = a.db && tap == 0 && blockIdx.y == 0 && ci4 == 0;
+    float acc[4][8] = {};
+    float bsum[8] = {};
+    for (int tile = blockIdx.x; tile < tiles_x * tiles_y; tile += gridDim.x) {
+        const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+        const int oy0 = ty * W3_TH, ox0 = tx * W3_TW;
+        for (int it = tid; it < W3_IH * W3_IW * (CI / 4); it += W3_THREADS) {
+            const int pos = it / (CI / 4), c4 = it - pos * (CI / 4);
+            const int r = pos / W3_IW, cc = pos - r * W3_IW;
+            const int y = oy0 - 1 + r, x = ox0 - 1 + cc, c = ci0 + c4 * 4;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (y >= 0 && y < a.Hx && x >= 0 && x < a.Wx && c < a.cx) {
+                int base = 0, sg = 0;
+                while (sg < a.nx - 1 && c >= base + a.x[sg].ch) { base += a.x[sg].ch; ++sg; }
+                v = ld4(a.x[sg].ptr + ((size_t)y * a.Wx + x) * a.x[sg].ch + (c - base));
+            }
+            st4(xs + pos * CI + c4 * 4, v);
+        }
+        for (int it = tid; it < W3_TH * W3_TW * (CO / 4); it += W3_THREADS) {
+            const int px = it / (CO / 4), q = it - px * (CO / 4);
+            const int y = oy0 + px / W3_TW, x = ox0 + px % W3_TW;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (y < a.Hy && x < a.Wy && q * 4 < a.cy) v = ld4(a.dy + ((size_t)y * a.Wy + x) * a.cy + q * 4);
+            st4(ds + px * CO + q * 4, v);
+        }
+        __syncthreads();
+        const float* xt = xs + (ky * W3_IW + kx) * CI + ci4 * 4;
+        const float* dt = ds + co8 * 4;
+#pragma unroll 1
+        for (int r = 0; r < W3_TH; ++r) {
+#pragma unroll 4
+            for (int c = 0; c < W3_TW; ++c) {
+                const float4 xv = ld4(xt + (r * W3_IW + c) * CI);
+                const float4 d0 = ld4(dt + (r * W3_TW + c) * CO), d1 = ld4(dt + (r * W3_TW + c) * CO + CO / 2);
+                const float xa[4] = {xv.x, xv.y, xv.z, xv.w};
+                const float da[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) acc[i][k] = fmaf(xa[i], da[k], acc[i][k]);
+                if (want_bias) {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) bsum[k] += da[k];
+                }
+            }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int co = (k < 4 ? 0 : CO / 2) + co8 * 4 + (k & 3);
+        if (co >= a.cy) continue;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int ci = ci0 + ci4 * 4 + i;
+            if (ci < a.cx) atomicAdd(a.dw + ((size_t)tap * a.cx + ci) * a.cy + co, acc[i][k]);
+        }
+        if (want_bias) atomicAdd(a.db + co, bsum[k]);
+    }
+}
+
+template <int LCO>
+static int launch_wgrad3(const WGArgs& a, cudaStream_t stream) {
+    constexpr int CO = 8 * LCO, CI = 4 * (32 / LCO);
+    constexpr int smem = (W3_IH * W3_IW * CI + W3_TH * W3_TW * CO) * (int)sizeof(float);
+    static unsigned long long smem_ok = 0;
+    if (cudaError_t e = ensure_dyn_smem(conv_wgrad3_kernel<LCO>, smem, smem_ok)) return (int)e;
+    const int tiles = ((a.Wy + W3_TW - 1) / W3_TW) * ((a.Hy + W3_TH - 1) / W3_TH);
+    const int blocks_y = (a.cx + CI - 1) / CI;
+    // two tiles per CTA on the large maps: half the atomics, still one wave of the machine across the concurrent samples
+    int gx = tiles;
+    if (tiles * blocks_y > 148) gx = (tiles + 1) / 2;
+    conv_wgrad3_kernel<LCO><<<dim3(gx, blocks_y), W3_THREADS, smem, stream>>>(a);
+    AARMVS_LAUNCH_RESULT();
+}
+
+// ------------------------------------------------------------------------------------------------ data gradient, 3x3 stride 1
+// dX = dG (*) W^T of the five cells (the widest convolutions of the reverse sweep), register tiled like the forward's
+// conv_kernel (conv.cu): weights [tap][CIN][COUT] and an input tile + halo in shared memory, lane = tile column, a warp owns
+// TCO output channels and TPX tile rows per lane (TPX * TCO accumulators, weights are warp-broadcast LDS.128).
+// Out[Y][X][co] = sum_{ky,kx,ci} In[Y + 1 - ky][X + 1 - kx][ci] * w[ky * 3 + kx][ci][co]  (conv_nhwc_kernel's `transposed`
+// indexing at stride 1); the output channels are scattered to up to three tensors, stored or accumulated.
+struct DXArgs {
+    const float* in;       // [H][W][CIN]
+    Seg out[3];
+    int nout, H, W;
+    const float* w;        // [9][CIN][COUT]
+};
+
+template <int CIN, int COUT, int TCO, int TPX>
+struct DXCfg {
+    static constexpr int NWARPS = 8, NCG = COUT / TCO, PSETS = NWARPS / NCG;
+    static constexpr int TH = PSETS * TPX, TW = 32, IH = TH + 2, IW = TW + 2;
+    static constexpr int CPAD = ((CIN / 4) & 1) ? CIN : CIN + 4;     // odd number of 16-byte chunks: conflict-free LDS.128
+    static constexpr int W_FLOATS = 9 * CIN * COUT, IN_FLOATS = IH * IW * CPAD;
+    static constexpr int SMEM = (W_FLOATS + IN_FLOATS) * (int)sizeof(float);
+    static_assert(COUT % TCO == 0 && NWARPS % NCG == 0 && TCO % 4 == 0 && CIN % 4 == 0, "bad tiling");
+    static_assert(SMEM <= 227 * 1024, "tile does not fit");
+};
+
+template <int CIN, int COUT, int TCO, int TPX>
+__global__ void __launch_bounds__(256, 1) conv_dx3_kernel(const __grid_constant__ DXArgs a) {
+    using C = DXCfg<CIN, COUT, TCO, TPX>;
+    extern __shared__ __align__(16) float smx[];
+    float* sw = smx;
+    float* sin = smx + C::W_FLOATS;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int cg = warp % C::NCG, ps = warp / C::NCG;
+    const int co0 = cg * TCO;
+    for (int i = tid * 4; i < C::W_FLOATS; i += 256 * 4) st4(sw + i, ldg4(a.w + i));
+    const int tiles_x = (a.W + C::TW - 1) / C::TW, tiles_y = (a.H + C::TH - 1) / C::TH;
+    constexpr int CIN4 = CIN / 4;
+    for (int tile = blockIdx.x; tile < tiles_x * tiles_y; tile += gridDim.x) {
+        const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+        const int oy0 = ty * C::TH, ox0 = tx * C::TW;
+        for (int it = tid; it < C::IH * C::IW * CIN4; it += 256) {
+            const int pos = it / CIN4, c4 = it - pos * CIN4;
+            const int r = pos / C::IW, cc = pos - r * C::IW;
+            const int y = oy0 - 1 + r, x = ox0 - 1 + cc;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (y >= 0 && y < a.H && x >= 0 && x < a.W) v = ld4(a.in + ((size_t)y * a.W + x) * CIN + c4 * 4);
+            st4(sin + pos * C::CPAD + c4 * 4, v);
+        }
+        __syncthreads();
+        float acc[TPX][TCO];
+#pragma unroll
+        for (int p = 0; p < TPX; ++p)
+#pragma unroll
+            for (int k = 0; k < TCO; ++k) acc[p][k] = 0.f;
+#pragma unroll 1
+        for (int tap = 0; tap < 9; ++tap) {
+            const int ky = tap / 3, kx = tap - ky * 3;
+            const float* wt = sw + tap * CIN * COUT + co0;
+            const float* it = sin + ((ps * TPX + 2 - ky) * C::IW + lane + 2 - kx) * C::CPAD;
+#pragma unroll 2
+            for (int c4 = 0; c4 < CIN4; ++c4) {
+                float4 x[TPX];
+#pragma unroll
+                for (int p = 0; p < TPX; ++p) x[p] = ld4(it + p * C::IW * C::CPAD + c4 * 4);
+#pragma unroll
+                for (int ci = 0; ci < 4; ++ci) {
+                    float wv[TCO];
+#pragma unroll
+                    for (int k = 0; k < TCO; k += 4) {
+                        const float4 w4 = ld4(wt + (c4 * 4 + ci) * COUT + k);
+                        wv[k] = w4.x; wv[k + 1] = w4.y; wv[k + 2] = w4.z; wv[k + 3] = w4.w;
+                    }
+#pragma unroll
+                    for (int p = 0; p < TPX; ++p) {
+                        const float xv = ci == 0 ? x[p].x : ci == 1 ? x[p].y : ci == 2 ? x[p].z : x[p].w;
+#pragma unroll
+                        for (int k = 0; k < TCO; ++k) acc[p][k] = fmaf(xv, wv[k], acc[p][k]);
+                    }
+                }
+            }
+        }
+        const int ox = ox0 + lane;
+#pragma unroll
+        for (int p = 0; p < TPX; ++p) {
+            const int oy = oy0 + ps * TPX + p;
+            if (oy >= a.H || ox >= a.W) continue;
+            const size_t pix = (size_t)oy * a.W + ox;
+#pragma unroll
+            for (int k = 0; k < TCO; k += 4) {
+                const int co = co0 + k;
+                int base = 0, sg = 0;
+                while (sg < a.nout - 1 && co >= base + a.out[sg].ch) { base += a.out[sg].ch; ++sg; }
+                float* q = a.out[sg].ptr + pix * a.out[sg].ch + (co - base);
+                float4 o = make_float4(acc[p][k], acc[p][k + 1], acc[p][k + 2], acc[p][k + 3]);
+                if (a.out[sg].acc) {
+                    const float4 t = ld4(q);
+                    o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w;
+                }
+                st4(q, o);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+template <int CIN, int COUT, int TCO, int TPX>
+static int launch_dx3(const DXArgs& a, cudaStream_t stream) {
+    using C = DXCfg<CIN, COUT, TCO, TPX>;
+    auto kern = conv_dx3_kernel<CIN, COUT, TCO, TPX>;
+    static unsigned long long smem_ok = 0;
+    if (cudaError_t e = ensure_dyn_smem(kern, C::SMEM, smem_ok)) return (int)e;
+    const int tiles = ((a.W + C::TW - 1) / C::TW) * ((a.H + C::TH - 1) / C::TH);
+    const int sms = aarmvs_sm_count();
+    if (sms <= 0) return AARMVS_ERR_ARG;
+    kern<<<tiles < sms ? tiles : sms, 256, C::SMEM, stream>>>(a);
+    AARMVS_LAUNCH_RESULT();
+}
+
 // ------------------------------------------------------------------------------------------------ GroupNorm
 // x [P][C]; group g = channels [g * C / groups, (g + 1) * C / groups) over all P pixels; sums = fp64 (sum, sum of squares).
 __global__ void __launch_bounds__(256) gn_sums_kernel(const float* __restrict__ x, size_t n /* P * C */, int C, int groups,
@@ -404,6 +618,30 @@ __global__ void __launch_bounds__(256) lstm_gates_bwd_kernel(const float* __rest
     }
 }
 
+// The same from the activated gates stored by the training forward (no sigmoid / tanh of pre-activations, no conv recompute).
+__global__ void __launch_bounds__(256) lstm_gates_bwd_act_kernel(const float* const* __restrict__ hist, int d_host, const int* __restrict__ d_dev,
+                                                                 const float* __restrict__ c_prev, const float* __restrict__ c_new,
+                                                                 const float* __restrict__ dh, float* __restrict__ dc,
+                                                                 float* __restrict__ dgates, size_t P, int Ch) {
+    const float* gates = *hist + (size_t)plane_index(d_host, d_dev) * P * 4 * Ch;
+    const size_t n = P * (size_t)Ch;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t p = i / Ch;
+        const int c = (int)(i - p * Ch);
+        const float* gp = gates + p * 4 * Ch;
+        const float gi = gp[c], gf = gp[Ch + c], go = gp[2 * Ch + c], gg = gp[3 * Ch + c];
+        const float th = tanhf(c_new[i]);
+        const float dhv = dh[i];
+        const float dct = dc[i] + dhv * go * (1.f - th * th);
+        float* dg = dgates + p * 4 * Ch;
+        dg[c] = dct * gg * gi * (1.f - gi);
+        dg[Ch + c] = dct * c_prev[i] * gf * (1.f - gf);
+        dg[2 * Ch + c] = dhv * th * go * (1.f - go);
+        dg[3 * Ch + c] = dct * gi * (1.f - gg * gg);
+        dc[i] = dct * gf;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ max pool 2x2 / 2
 __global__ void __launch_bounds__(256) maxpool2_kernel(const float* __restrict__ x, int H, int W, int C, float* __restrict__ out) {
     const int Ho = H / 2, Wo = W / 2;
@@ -459,6 +697,18 @@ extern "C" int aarmvs_conv_nhwc(const aarmvs_seg* in, int nin, int Hin, int Win,
     AARMVS_CHECK_ARG(ci == cin && co == cout);
     a.nin = nin; a.nout = nout; a.Hin = Hin; a.Win = Win; a.Hout = Hout; a.Wout = Wout; a.cin = cin; a.cout = cout;
     a.ks = ksize; a.stride = stride; a.transposed = transposed ? 1 : 0; a.w = weight; a.bias = bias;
+    if (transposed && ksize == 3 && stride == 1 && nin == 1 && !a.in[0].acc && !bias && Hin == Hout && Win == Wout) {
+        bool quads = true;                               // the cells' data gradients: the register-tiled kernel
+        for (int s = 0; s < nout; ++s) quads = quads && a.out[s].ch % 4 == 0;
+        if (quads) {
+            DXArgs x = {};
+            x.in = a.in[0].ptr; x.nout = nout; x.H = Hout; x.W = Wout; x.w = weight;
+            for (int s = 0; s < nout; ++s) x.out[s] = a.out[s];
+            if (cin == 64 && cout == 48) return launch_dx3<64, 48, 12, 4>(x, (cudaStream_t)stream);      // cells 0, 3
+            if (cin == 64 && cout == 32) return launch_dx3<64, 32, 16, 2>(x, (cudaStream_t)stream);      // cells 1, 2
+            if (cin == 32 && cout == 40) return launch_dx3<32, 40, 20, 2>(x, (cudaStream_t)stream);      // cell 4
+        }
+    }
     const int bx = grid_for((size_t)Hout * Wout, GC_THREADS);
     const int co_tile = (bx * ((cout + 15) / 16) < 148 * 3 && cout > 8) ? 8 : 16;      // small maps: more, narrower CTAs
     const int smem = ksize * ksize * cin * co_tile * (int)sizeof(float);
@@ -487,6 +737,15 @@ extern "C" int aarmvs_conv_bwd_weight(const aarmvs_seg* x, int nx, int Hx, int W
     AARMVS_CHECK_ARG(c == cx);
     a.nx = nx; a.dy = dy; a.Hx = Hx; a.Wx = Wx; a.Hy = Hy; a.Wy = Wy; a.cx = cx; a.cy = cy; a.ks = ksize; a.stride = stride;
     a.dw = dweight; a.db = dbias;
+    if (ksize == 3 && stride == 1 && Hx == Hy && Wx == Wy && cy % 4 == 0) {
+        bool quads = true;
+        for (int s = 0; s < nx; ++s) quads = quads && a.x[s].ch % 4 == 0;
+        if (quads) {
+            if (cy > 32) return launch_wgrad3<8>(a, (cudaStream_t)stream);
+            if (cy > 16) return launch_wgrad3<4>(a, (cudaStream_t)stream);
+            return launch_wgrad3<2>(a, (cudaStream_t)stream);
+        }
+    }
     const int P = Hy * Wy;
     // pixels per block: enough blocks to fill the machine a few times over (the kernel is short), few enough that the fp32
     // atomics at the end stay a small part of it
@@ -530,6 +789,14 @@ extern "C" int aarmvs_lstm_gates_bwd(const float* gates, const float* c_prev, co
                                      float* dgates, size_t P, int hidden, void* stream) {
     AARMVS_CHECK_ARG(gates && c_new && dh && dc && dgates && P > 0 && hidden > 0);
     lstm_gates_bwd_kernel<<<grid_for(P * hidden, 256), 256, 0, (cudaStream_t)stream>>>(gates, c_prev, c_new, dh, dc, dgates, P, hidden);
+    AARMVS_LAUNCH_RESULT();
+}
+
+extern "C" int aarmvs_lstm_gates_bwd_act(const float* const* gates_history, int d_host, const int* d_dev, const float* c_prev, const float* c_new,
+                                         const float* dh, float* dc, float* dgates, size_t P, int hidden, void* stream) {
+    AARMVS_CHECK_ARG(gates_history && c_prev && c_new && dh && dc && dgates && P > 0 && hidden > 0);
+    lstm_gates_bwd_act_kernel<<<grid_for(P * hidden, 256), 256, 0, (cudaStream_t)stream>>>(gates_history, d_host, d_dev, c_prev, c_new, dh,
+                                                                                           dc, dgates, P, hidden);
     AARMVS_LAUNCH_RESULT();
 }
 

@@ -54,6 +54,8 @@ struct alignas(64) CellArgs {
     float* c_blocked;           // [tiles][4 quarters][128][CH/4]
     float* h_f32;               // optional [2 ping-pong][H*W][CH] fp32 copy of h (deconvolution / head inputs, operator seam)
     __half* pooled;             // optional [2][CH/8][H/2][W/2][8]: operand planes of max_pool2d(h, 2)
+    float* const* gates_out;    // optional (training forward): device slot holding the base of the history [planes][H*W][4*CH] of the
+                                // ACTIVATED gates, blocks i | f | o | g
     int d_host;
     const int* d_dev;
 #ifdef AARMVS_DEBUG
@@ -120,7 +122,8 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
 __device__ __forceinline__ float exp_neg(float x) { return tc::ex2_approx(fminf(-1.4426950408889634f * x, 30.0f)); }
 __device__ __forceinline__ float exp_neg2(float x) { return tc::ex2_approx(fminf(-2.8853900817779268f * x, 30.0f)); }
 
-template <int KSTEPS, int NG, int NST>
+// SAVE: the training instantiation, which also stores the activated gates (CellArgs::gates_out); the inference one is unchanged.
+template <int KSTEPS, int NG, int NST, bool SAVE>
 __global__ void __launch_bounds__(N_THREADS, 1) convlstm_tma_kernel(const __grid_constant__ CellArgs a) {
     using C = Cfg<KSTEPS, NG, NST>;
     constexpr int CH = NG / 4, CHK = (CH + 7) / 8;
@@ -330,7 +333,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) convlstm_tma_kernel(const __grid
             // Gates with ONE reciprocal per hidden channel: with a = 1 + e^-i, b = 1 + e^-f, c = 1 + e^-o, d = 1 + e^-2g and
             // r = 1 / (abcd):  sigmoid(i) = r*cd*b, sigmoid(f) = r*cd*a, sigmoid(o) = r*ab*d, tanh(g) = 2*r*ab*c - 1
             // (MUFU.EX2 / MUFU.RCP are quarter-rate: 6.5 instead of 10 per channel; relative error a few ulp).
-            float ec[NHC], go[NHC];
+            float ec[NHC], go[NHC], gia[NHC], gfa[NHC], gga[NHC];
 #pragma unroll
             for (int j = 0; j < NHC; ++j) {
                 const float* bb = bias_r + j * 4;
@@ -338,6 +341,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) convlstm_tma_kernel(const __grid
                     cn[j] = (g[j * 4 + 0] + g2[j * 4 + 0]) + bb[0] + cprev[j];
                     go[j] = (g[j * 4 + 1] + g2[j * 4 + 1]) + (g[j * 4 + 2] + g2[j * 4 + 2]) + (g[j * 4 + 3] + g2[j * 4 + 3]);
                     ec[j] = 1.0f;
+                    if constexpr (SAVE) gia[j] = gfa[j] = gga[j] = 0.f;
                     continue;
                 }
                 const float pa = 1.0f + exp_neg((g[j * 4 + 0] + g2[j * 4 + 0]) + bb[0]);      // (hi*hi + lo*hi) + hi*lo, + bias
@@ -352,12 +356,27 @@ __global__ void __launch_bounds__(N_THREADS, 1) convlstm_tma_kernel(const __grid
                 const float gg = fmaf(2.0f, rcd * pc, -1.0f);
                 cn[j] = __fadd_rn(__fmul_rn(gf, cprev[j]), __fmul_rn(gi, gg));
                 ec[j] = 1.0f + exp_neg2(cn[j]);
+                if constexpr (SAVE) { gia[j] = gi; gfa[j] = gf; gga[j] = gg; }
             }
 #pragma unroll
             for (int j = 0; j < NHC; j += 2) {           // tanh(c') of two channels with one reciprocal
                 const float r = tc::rcp_approx(ec[j] * ec[j + 1]);
                 hn[j] = go[j] * fmaf(2.0f, r * ec[j + 1], -1.0f);
                 hn[j + 1] = go[j + 1] * fmaf(2.0f, r * ec[j], -1.0f);
+            }
+            if (SAVE && valid) {             // the gates exactly as this forward used them, for the backward pass (no recompute there)
+                float* gp = *a.gates_out + ((size_t)d * P + pix) * (4 * CH) + part * NHC;
+                if constexpr (NHC == 4) {
+                    st4(gp, make_float4(gia[0], gia[1], gia[2], gia[3]));
+                    st4(gp + CH, make_float4(gfa[0], gfa[1], gfa[2], gfa[3]));
+                    st4(gp + 2 * CH, make_float4(go[0], go[1], go[2], go[3]));
+                    st4(gp + 3 * CH, make_float4(gga[0], gga[1], gga[2], gga[3]));
+                } else {
+                    *reinterpret_cast<float2*>(gp) = make_float2(gia[0], gia[1]);
+                    *reinterpret_cast<float2*>(gp + CH) = make_float2(gfa[0], gfa[1]);
+                    *reinterpret_cast<float2*>(gp + 2 * CH) = make_float2(go[0], go[1]);
+                    *reinterpret_cast<float2*>(gp + 3 * CH) = make_float2(gga[0], gga[1]);
+                }
             }
             if (valid) {
                 if constexpr (NHC == 4) {
@@ -402,10 +421,10 @@ __global__ void __launch_bounds__(N_THREADS, 1) convlstm_tma_kernel(const __grid
     if (warp == MMA_WARP) tc::tmem_dealloc<C::TMEM_COLS>(tmem_base);
 }
 
-template <int KSTEPS, int NG, int NST>
-int launch_cell(const CellArgs& a, cudaStream_t stream) {
+template <int KSTEPS, int NG, int NST, bool SAVE>
+int launch_cell_as(const CellArgs& a, cudaStream_t stream) {
     using C = Cfg<KSTEPS, NG, NST>;
-    auto kern = convlstm_tma_kernel<KSTEPS, NG, NST>;
+    auto kern = convlstm_tma_kernel<KSTEPS, NG, NST, SAVE>;
     static unsigned long long smem_ok = 0;
     if (cudaError_t e = ensure_dyn_smem(kern, C::SMEM, smem_ok)) return (int)e;
     const int ntiles = ((a.W + TCOL - 1) / TCOL) * ((a.H + TR - 1) / TR);
@@ -413,6 +432,11 @@ int launch_cell(const CellArgs& a, cudaStream_t stream) {
     if (sms <= 0) return AARMVS_ERR_ARG;
     if (cudaError_t e = launch_pdl(kern, dim3(ntiles < sms ? ntiles : sms), dim3(N_THREADS), C::SMEM, stream, a)) return (int)e;
     AARMVS_LAUNCH_RESULT();
+}
+
+template <int KSTEPS, int NG, int NST>
+int launch_cell(const CellArgs& a, cudaStream_t stream) {
+    return a.gates_out ? launch_cell_as<KSTEPS, NG, NST, true>(a, stream) : launch_cell_as<KSTEPS, NG, NST, false>(a, stream);
 }
 
 #ifdef AARMVS_DEBUG
@@ -435,7 +459,8 @@ extern "C" size_t aarmvs_cell_state_floats(int H, int W, int hidden) {
 
 extern "C" int aarmvs_convlstm_cell_tc(const aarmvs_plane_src* src, int nsrc, int H, int W, int cin, int hidden,
                                        const void* weight_f16, const float* bias_packed, void* h_planes, float* c_blocked,
-                                       float* h_f32_pair, void* pooled_planes, int d_host, const int* d_dev, void* stream) {
+                                       float* h_f32_pair, void* pooled_planes, float* const* gates_out, int d_host, const int* d_dev,
+                                       void* stream) {
     AARMVS_CHECK_ARG(src && weight_f16 && bias_packed && h_planes && c_blocked && H > 0 && W > 0 && nsrc >= 1 && nsrc <= 2);
     AARMVS_CHECK_ARG(hidden == 16 || hidden == 8);
     AARMVS_CHECK_ARG(!pooled_planes || (hidden == 16 && H % 2 == 0 && W % 2 == 0));
@@ -461,7 +486,7 @@ extern "C" int aarmvs_convlstm_cell_tc(const aarmvs_plane_src* src, int nsrc, in
     AARMVS_CHECK_ARG(csum == cin && cin <= 48 && ((uintptr_t)h_planes & 15) == 0 && ((uintptr_t)weight_f16 & 15) == 0);
     a.need_zero = 0;          // K padding is never read: cell 4 packs its fifth chunk (see Cfg::PACK)
     a.H = H; a.W = W; a.weight = (const __half*)weight_f16; a.bias = bias_packed; a.h_planes = (__half*)h_planes;
-    a.c_blocked = c_blocked; a.h_f32 = h_f32_pair; a.pooled = (__half*)pooled_planes;
+    a.c_blocked = c_blocked; a.h_f32 = h_f32_pair; a.pooled = (__half*)pooled_planes; a.gates_out = gates_out;
     a.d_host = d_host; a.d_dev = d_dev;
 #ifdef AARMVS_DEBUG
     a.prof = g_prof; a.dbg = g_cell_dbg;

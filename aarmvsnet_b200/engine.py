@@ -189,7 +189,9 @@ class Engine:
             # of the current sample's state history (so that one captured graph serves every sample)
             ws["snap"] = {"h": (ctypes.c_void_p * 5)(*[t.data_ptr() for t in ws["h"]]),
                           "c": (ctypes.c_void_p * 5)(*[t.data_ptr() for t in ws["c"]]),
-                          "state_pp": torch.zeros(1, device=device, dtype=torch.int64), "rec": self.state_layout(H, W)[1]}
+                          "state_pp": torch.zeros(1, device=device, dtype=torch.int64), "rec": self.state_layout(H, W)[1],
+                          # per sample: base addresses of the five cells' gate histories (forward_saving_state)
+                          "gates_pp": torch.zeros(5, device=device, dtype=torch.int64)}
         ws["psums"] = torch.zeros(K * S * 6 + 8, device=device, dtype=torch.float64)
         ws["plane"] = torch.zeros(1, device=device, dtype=torch.int32)
         ws["cams"] = torch.empty(S, 12, **f32)
@@ -356,7 +358,9 @@ class Engine:
             capi.check(lib.aarmvs_convlstm_cell_tc(arr, len(srcs), hh, ww, cin, _HID[i], _ptr(w[f"cell{i}.wtc"]),
                                                    _ptr(w[f"cell{i}.b"]), _ptr(ws["hp"][i]), _ptr(c[i]),
                                                    _ptr(h[i]) if h[i] is not None else None,
-                                                   _ptr(pooled) if pooled is not None else None, 0, dptr, stream),
+                                                   _ptr(pooled) if pooled is not None else None,
+                                                   _ptr(ws["snap"]["gates_pp"], i) if ws.get("snap") is not None else None,
+                                                   0, dptr, stream),
                        f"aarmvs_convlstm_cell_tc[{i}]")
             mark(f"cell{i}")
 
@@ -520,6 +524,12 @@ class Engine:
             saved = {"H": H, "W": W, "N": N, "D": D, "imgs": imgs, "cams": ws["cams"].clone(), "depths": ws["depths"].clone(),
                      "state": state}
             ws["snap"]["state_pp"].fill_(state.data_ptr())
+            # the activated gates of every plane, as the cells used them: [D][P_i][4 Ch_i] per cell (132 floats per full-resolution
+            # pixel and plane); the kernels read the bases from device memory, so the captured plane graph serves every sample
+            saved["gates"] = [torch.empty(D, (H // sc) * (W // sc), 4 * ch, device=device, dtype=torch.float32)
+                              for ch, sc in zip(_HID, _SCALE)]
+            for i, g in enumerate(saved["gates"]):
+                ws["snap"]["gates_pp"][i].fill_(g.data_ptr())
             self._run_planes(ws, w, device, stream, D)
             saved["feat"] = ws["feat"].clone()
             saved["cost"] = ws["cost_volume"].clone()

@@ -131,7 +131,7 @@ def convlstm_cell(model, cell_index, x, h, c, math=None):
         cb = _block_state(cs, H, W)
         assert cb.numel() == lib.aarmvs_cell_state_floats(H, W, ch)
         capi.check(lib.aarmvs_convlstm_cell_tc(_psrc_array(_psrc(xp, cx)), 1, H, W, cx + ch, ch, _ptr(w[f"cell{cell_index}.wtc"]),
-                                               _ptr(w[f"cell{cell_index}.b"]), _ptr(hp), _ptr(cb), _ptr(h_pair), None, 1, None, st),
+                                               _ptr(w[f"cell{cell_index}.b"]), _ptr(hp), _ptr(cb), _ptr(h_pair), None, None, 1, None, st),
                    "aarmvs_convlstm_cell_tc")
         cs = _unblock_state(cb, H, W, ch)
     else:

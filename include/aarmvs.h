@@ -185,10 +185,15 @@ size_t aarmvs_cell_state_floats(int H, int W, int hidden);
  * where h = c = 0) and writes half d&1.  c_blocked: aarmvs_cell_state_floats() floats, in place.
  * h_f32_pair: optional fp32 copy of h, two [H*W][hidden] halves (half d&1 written) for the deconvolution / head kernels.
  * pooled_planes: optional operand planes [2][hidden/8][H/2][W/2][8] of max_pool2d(h, 2) (models/drmvsnet.py:148,152;
- * hidden == 16 only).  Supported (cin, hidden): (48,16) (32,16) (40,8). */
+ * hidden == 16 only).
+ * gates_out: optional (training forward); *gates_out (device memory, like aarmvs_snapshot_state's state_pp, so one captured
+ * graph serves every sample) is the base of a history [num planes][H*W][4*hidden] fp32 of the ACTIVATED gates in channel blocks
+ * sigmoid(i) | sigmoid(f) | sigmoid(o) | tanh(g) (module.py:83-88), record d written by plane d: the backward pass reads the
+ * gates exactly as the forward used them instead of recomputing the cell's convolution.
+ * Supported (cin, hidden): (48,16) (32,16) (40,8). */
 int aarmvs_convlstm_cell_tc(const aarmvs_plane_src* src, int nsrc, int H, int W, int cin, int hidden,
                             const void* weight_f16, const float* bias_packed, void* h_planes, float* c_blocked,
-                            float* h_f32_pair, void* pooled_planes, int d_host, const int* d_dev, void* stream);
+                            float* h_f32_pair, void* pooled_planes, float* const* gates_out, int d_host, const int* d_dev, void* stream);
 
 /* deConvGnReLU's ConvTranspose2d(16,16,k3,s2,p1,op1) (models/module.py:281): in [Hin][Win][16] (one conv source,
  * typically a ping-pong h) -> pre-norm out [2Hin][2Win][16] + GroupNorm sums (2 groups).
@@ -319,6 +324,11 @@ int aarmvs_gn_relu_bwd(int stage, const float* x, const float* dy, size_t P, int
  * dgates [P][4*hidden] = dL/d(conv output). */
 int aarmvs_lstm_gates_bwd(const float* gates, const float* c_prev, const float* c_new, const float* dh, float* dc, float* dgates,
                           size_t P, int hidden, void* stream);
+/* The same from the ACTIVATED gates the training forward stored (aarmvs_convlstm_cell_tc: gates_out): *gates_history (device
+ * memory) is the base of [planes][P][4*hidden]; record d = *d_dev if d_dev is non-null (one captured graph serves every plane
+ * and sample), else d_host. */
+int aarmvs_lstm_gates_bwd_act(const float* const* gates_history, int d_host, const int* d_dev, const float* c_prev, const float* c_new,
+                              const float* dh, float* dc, float* dgates, size_t P, int hidden, void* stream);
 
 /* MaxPool2d(2, 2) (drmvsnet.py:148,152) and its backward (dx += dout at the first maximum of each window). */
 int aarmvs_maxpool2(const float* x, int H, int W, int C, float* out, void* stream);

@@ -110,7 +110,30 @@ def test_conv_nhwc(ctx, case):
     _close(_nchw(out, H, W).cpu(), want, 2e-5, case)
 
 
-@pytest.mark.parametrize("case", ["s1_concat", "s2", "deconv", "k1_288", "cy1"])
+@pytest.mark.parametrize("cin,cout,splits", [(64, 48, (32, 16)), (64, 48, (16, 16, 16)), (64, 32, (16, 16)), (32, 40, (16, 16, 8))])
+@pytest.mark.parametrize("H,W", [(18, 22), (40, 72)])
+def test_cell_data_gradient_tiled(ctx, cin, cout, splits, H, W):
+    """The register-tiled dX kernel of the five cells (conv_dx3_kernel: dG (*) W^T scattered to the cell's inputs, the second
+    one accumulated) against autograd through F.conv2d in fp64; ragged tiles in both directions."""
+    from aarmvsnet_b200.backward import _seg
+    _, bw = ctx
+    g = torch.Generator().manual_seed(31)
+    dev = "cuda"
+    r = lambda *s: torch.randn(*s, generator=g, dtype=torch.float64)
+    x = r(cout, H, W).requires_grad_(True)                  # the cell's input (cout channels of dX)
+    wt = r(cin, cout, 3, 3)                                 # conv: cout input channels -> cin gate channels
+    y = F.conv2d(x[None], wt, None, padding=1)[0]
+    dy = r(*y.shape)
+    (want,) = torch.autograd.grad(y, x, dy)
+    wk = wt.permute(2, 3, 0, 1).reshape(9, cin, cout).float().contiguous().to(dev)         # [tap][gate][input] = W^T
+    dys = _nhwc(dy).float().to(dev)
+    outs = [torch.full((H * W, c), 1.0 if i == 1 else float("nan"), device=dev) for i, c in enumerate(splits)]
+    bw.conv([_seg(dys, cin)], H, W, [_seg(o, c, 1 if i == 1 else 0) for i, (o, c) in enumerate(zip(outs, splits))], H, W, 3, 1, True, wk)
+    outs[1] -= 1.0
+    _close(_nchw(torch.cat(outs, 1), H, W).cpu(), want, 2e-5, f"dx {cin}->{cout}")
+
+
+@pytest.mark.parametrize("case", ["s1_concat", "s2", "deconv", "k1_288", "cy1", "cell0", "cell4", "stem"])
 def test_conv_bwd_weight(ctx, case):
     from aarmvsnet_b200.backward import _seg
     _, bw = ctx
@@ -130,7 +153,10 @@ def test_conv_bwd_weight(ctx, case):
         got = dw.reshape(3, 3, 16, 16).permute(3, 2, 0, 1)
         _close(got.cpu(), want, 5e-5, case)
         return
-    cin, cout, k, s = {"s1_concat": (20, 24, 3, 1), "s2": (32, 32, 3, 2), "k1_288": (288, 32, 1, 1), "cy1": (8, 1, 3, 1)}[case]
+    cin, cout, k, s = {"s1_concat": (20, 24, 3, 1), "s2": (32, 32, 3, 2), "k1_288": (288, 32, 1, 1), "cy1": (8, 1, 3, 1),
+                       "cell0": (48, 64, 3, 1), "cell4": (40, 32, 3, 1), "stem": (32, 4, 3, 1)}[case]
+    if case in ("cell0", "cell4"):
+        H, W = (64, 200) if case == "cell0" else (40, 72)       # the tiled kernel: 56 tiles, two per CTA / 15 tiles; ragged right edge
     x = r(cin, H, W)
     wt = r(cout, cin, k, k).requires_grad_(True)
     b = r(cout).requires_grad_(True)
@@ -142,7 +168,7 @@ def test_conv_bwd_weight(ctx, case):
     db = torch.zeros(cout, device=dev)
     xs = _nhwc(x).float().to(dev)
     keep = [xs[:, :12].contiguous(), xs[:, 12:].contiguous()]
-    segs = [_seg(keep[0], 12), _seg(keep[1], cin - 12)] if case == "s1_concat" else [_seg(xs, cin)]
+    segs = [_seg(keep[0], 12), _seg(keep[1], cin - 12)] if case in ("s1_concat", "cell0", "cell4") else [_seg(xs, cin)]
     dys = _nhwc(dy).float().to(dev)
     bw.wgrad(segs, H, W, dys, ho, wo, cout, k, s, dw, db)
     _close(dw.reshape(k, k, cin, cout).permute(3, 2, 0, 1).cpu(), want_w, 5e-5, case + " dW")
@@ -202,6 +228,18 @@ def test_lstm_gates_and_maxpool_backward(ctx):
     capi.check(bw.lib.aarmvs_lstm_gates_bwd(_ptr(t_g), _ptr(t_cp), _ptr(t_cn), _ptr(t_dh), _ptr(dc), _ptr(dg), P, Ch, bw._st()), "lstm")
     _close(dg.cpu(), wg, 5e-5, "lstm dgates")
     _close(dc.cpu(), wc, 5e-5, "lstm dc_prev")
+    # the same from the activated gates a training forward stored: record 2 of a 3-plane history, plane index on the device
+    act = torch.cat([torch.sigmoid(gates[:, :3 * Ch]), torch.tanh(gates[:, 3 * Ch:])], dim=1).detach().float()
+    hist = torch.full((3, P, 4 * Ch), float("nan"), device=dev)
+    hist[2] = act.to(dev)
+    slot = torch.tensor([hist.data_ptr()], dtype=torch.int64).to(dev)
+    plane = torch.tensor([2], dtype=torch.int32).to(dev)
+    dc2 = dcn.float().to(dev).clone()
+    dg2 = torch.empty(P, 4 * Ch, device=dev)
+    capi.check(bw.lib.aarmvs_lstm_gates_bwd_act(_ptr(slot), 0, _ptr(plane), _ptr(t_cp), _ptr(t_cn), _ptr(t_dh), _ptr(dc2), _ptr(dg2), P, Ch,
+                                                bw._st()), "lstm act")
+    _close(dg2.cpu(), wg, 5e-5, "lstm dgates (stored activations)")
+    _close(dc2.cpu(), wc, 5e-5, "lstm dc_prev (stored activations)")
     # max pool
     H, W, C = 12, 20, 16
     x = torch.randn(C, H, W, generator=g, dtype=torch.float64).requires_grad_(True)
