@@ -162,6 +162,8 @@ class Backward:
         b["cams"] = torch.empty(S, 12, **f32)
         b["depths"] = torch.empty(0, **f32)
         b["graph"] = None
+        b["side"] = torch.cuda.Stream(dev)                                  # second branch of the plane (see _plane)
+        b["stage_ready"] = torch.cuda.Event()
         b["chan"] = torch.zeros(128, device=dev, dtype=torch.float64)      # per-channel sums of one GroupNorm backward
         self._wss[slot] = b
         return b
@@ -294,15 +296,31 @@ class Backward:
         dptr = _ptr(b["plane"])
         depths, cams = _ptr(b["depths"]), _ptr(b["cams"])
         hp, cp, h, c = b["hp"], b["cp"], b["h"], b["c"]
+        # Two branches (captured as a fork / join of the plane's graph): the MAIN stream carries the dependent chain of data
+        # gradients, the SIDE stream everything nothing downstream in the plane waits for -- the weight gradients (a third of the
+        # kernel time) and the recompute of the warp / omega / aggregation stage, which only cell 0's weight gradient and the
+        # aggregation backward at the very end need.
+        main, side = torch.cuda.current_stream(self.dev), b["side"]
+
+        def on_side(fn):
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                fn()
+
         # ---------------- recompute the plane's forward intermediates
-        b["stats"].zero_()
-        eng.cost_stem(ref, src, P * 32, H, W, S, cams, w, depths, 0, dptr, 1, _ptr(b["t0"]), _ptr(b["stats"]), st, _ptr(b["costv"]))
-        for stage in (2, 3):
-            capi.check(lib.aarmvs_omega_stats(stage, _ptr(b["t0"]), H, W, S, 1, w["tail_host"], _ptr(b["stats"]), st), "aarmvs_omega_stats")
-        capi.check(lib.aarmvs_aggregate(ref, src, P * 32, H, W, S, cams, w["tail_host"], depths, 0, dptr, 1, ac, _ptr(b["t0"]),
-                                        _ptr(b["stats"]), _ptr(b["costv"]), _ptr(b["cost"]), None, _ptr(b["rew"]), st), "aarmvs_aggregate")
-        capi.check(lib.aarmvs_maxpool2(_ptr(h[0]), H, W, 16, _ptr(b["pool0"]), st), "aarmvs_maxpool2")
-        capi.check(lib.aarmvs_maxpool2(_ptr(h[1]), H2, W2, 16, _ptr(b["pool1"]), st), "aarmvs_maxpool2")
+        def stage_recompute():
+            sst = self._st()
+            b["stats"].zero_()
+            eng.cost_stem(ref, src, P * 32, H, W, S, cams, w, depths, 0, dptr, 1, _ptr(b["t0"]), _ptr(b["stats"]), sst, _ptr(b["costv"]))
+            for stage in (2, 3):
+                capi.check(lib.aarmvs_omega_stats(stage, _ptr(b["t0"]), H, W, S, 1, w["tail_host"], _ptr(b["stats"]), sst), "aarmvs_omega_stats")
+            capi.check(lib.aarmvs_aggregate(ref, src, P * 32, H, W, S, cams, w["tail_host"], depths, 0, dptr, 1, ac, _ptr(b["t0"]),
+                                            _ptr(b["stats"]), _ptr(b["costv"]), _ptr(b["cost"]), None, _ptr(b["rew"]), sst), "aarmvs_aggregate")
+            b["stage_ready"].record(side)
+            capi.check(lib.aarmvs_maxpool2(_ptr(h[0]), H, W, 16, _ptr(b["pool0"]), sst), "aarmvs_maxpool2")
+            capi.check(lib.aarmvs_maxpool2(_ptr(h[1]), H2, W2, 16, _ptr(b["pool1"]), sst), "aarmvs_maxpool2")
+
+        on_side(stage_recompute)
         for i, (hin, win, src_h) in enumerate(((H4, W4, h[2]), (H2, W2, h[3]))):
             self.conv([_seg(src_h, 16)], hin, win, [_seg(b[f"up{i}raw"], 16)], 2 * hin, 2 * win, 3, 2, True, bw[f"deconv{i}.w"],
                       bw[f"deconv{i}.b"])
@@ -317,23 +335,23 @@ class Backward:
         dh, dhp, dc = b["dh"], b["dhprev"], b["dc"]
         dcr = b["dcr"]                                               # [P] = [P][1]
         self.conv([_seg(dcr, 1)], H, W, [_seg(dh[4], 8, 1)], H, W, 3, 1, True, bw["head.wT"])
-        self.wgrad([_seg(h[4], 8)], H, W, dcr, H, W, 1, 3, 1, g["head.w"], g["head.b"])
+        on_side(lambda: self.wgrad([_seg(h[4], 8)], H, W, dcr, H, W, 1, 3, 1, g["head.w"], g["head.b"]))
 
         def cell_bwd(i, outs):
             # at plane 0 the staged previous state is the zero record: c_prev = h_prev = 0 (module.py:94-96)
             capi.check(lib.aarmvs_lstm_gates_bwd_act(_ptr(b["gates_pp"], i), 0, dptr, _ptr(cp[i]), _ptr(c[i]), _ptr(dh[i]), _ptr(dc[i]),
                                                      _ptr(b["dgates"][i]), hw[i][0] * hw[i][1], _HID[i], st), "aarmvs_lstm_gates_bwd_act")
+            on_side(lambda: self.wgrad(xin[i] + [_seg(hp[i], _HID[i])], hw[i][0], hw[i][1], b["dgates"][i], hw[i][0], hw[i][1],
+                                       4 * _HID[i], 3, 1, g[f"cell{i}.w"], g[f"cell{i}.b"]))
             self.conv([_seg(b["dgates"][i], 4 * _HID[i])], hw[i][0], hw[i][1], outs + [_seg(dhp[i], _HID[i])], hw[i][0], hw[i][1], 3, 1, True,
                       bw[f"cell{i}.wT"])
-            self.wgrad(xin[i] + [_seg(hp[i], _HID[i])], hw[i][0], hw[i][1], b["dgates"][i], hw[i][0], hw[i][1], 4 * _HID[i], 3, 1,
-                       g[f"cell{i}.w"], g[f"cell{i}.b"])
 
         def up_bwd(i, hin, win, src_h, dh_target):
             pp = 4 * hin * win
             self.gn_bwd(b[f"up{i}raw"], b[f"dup{i}"], pp, 16, 2, b[f"gsum{i}"], bw[f"deconv{i}.gn"], b[f"dup{i}"], g[f"deconv{i}.gamma"],
                         g[f"deconv{i}.beta"], g[f"deconv{i}.b"], chan=b["chan"])
+            on_side(lambda: self.wgrad([_seg(b[f"dup{i}"], 16)], 2 * hin, 2 * win, src_h, hin, win, 16, 3, 2, g[f"deconv{i}.wT"]))
             self.conv([_seg(b[f"dup{i}"], 16)], 2 * hin, 2 * win, [_seg(dh_target, 16, 1)], hin, win, 3, 2, False, bw[f"deconv{i}.wT"])
-            self.wgrad([_seg(b[f"dup{i}"], 16)], 2 * hin, 2 * win, src_h, hin, win, 16, 3, 2, g[f"deconv{i}.wT"])
 
         cell_bwd(4, [_seg(b["dup1"], 16), _seg(dh[0], 16, 1)])
         up_bwd(1, H2, W2, h[3], dh[3])
@@ -346,20 +364,27 @@ class Backward:
         cell_bwd(0, [_seg(b["dcost"], 32)])
 
         # ---------------- aggregation, omega, warp
+        main.wait_event(b["stage_ready"])                            # costv, t0, stats, rew of the recompute branch
         capi.check(lib.aarmvs_aggregate_bwd(_ptr(b["dcost"]), _ptr(b["costv"]), _ptr(b["rew"]), S, P, _ptr(b["dcostv"]), _ptr(b["drew"]), st),
                    "aarmvs_aggregate_bwd")
         b["bstats"].zero_()
         for stage in (3, 2, 1, 0):
             capi.check(lib.aarmvs_omega_bwd(stage, _ptr(b["t0"]), _ptr(b["drew"]), H, W, S, w["tail_host"], _ptr(b["stats"]),
                                             _ptr(b["bstats"]), _ptr(g["tail"]), _ptr(b["dt0"]), st), "aarmvs_omega_bwd")
+
+        def stem_wgrads():
+            for v in range(S):
+                self.wgrad([_seg(b["costv"][v], 32)], H, W, b["dt0"][v], H, W, 4, 3, 1, g["stem.w"], g["stem.b"])
+
+        on_side(stem_wgrads)
         for v in range(S):
             self.conv([_seg(b["dt0"][v], 4)], H, W, [_seg(b["dcostv"][v], 32, 1)], H, W, 3, 1, True, bw["stem.wT"])
-            self.wgrad([_seg(b["costv"][v], 32)], H, W, b["dt0"][v], H, W, 4, 3, 1, g["stem.w"], g["stem.b"])
         capi.check(lib.aarmvs_warp_bwd(ref, src, P * 32, H, W, S, cams, depths, 0, dptr, ac, _ptr(b["dcostv"]), _ptr(b["dfeat"]),
                                        _ptr(b["dfeat"], P * 32), st), "aarmvs_warp_bwd")
         # ---------------- carry: dL/dh_{d-1} is the next (lower) plane's starting dh; dc was updated in place
         for i in range(5):
             dh[i].copy_(dhp[i])
+        main.wait_stream(side)                                       # join: the plane's buffers are free for the next plane
 
     # ------------------------------------------------------------------------------------------ FeatNet of one view
     def featnet(self, img, dfeat, H, W):
