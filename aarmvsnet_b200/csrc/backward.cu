@@ -13,6 +13,8 @@
 // The training shape is small (128 x 160 feature maps, B = 4, D = 192: SURVEY.md §8d cfg5), so the backward keeps whole
 // fp32 activations in HBM and is bound by launch count and FMA issue, not by the tensor pipe; the inference path's tcgen05
 // kernels are untouched.
+#include <type_traits>
+
 #include "common.cuh"
 #include "../../include/aarmvs.h"
 
@@ -259,8 +261,10 @@ __global__ void __launch_bounds__(WG_THREADS) conv_wgrad_kernel(const __grid_con
 // 4 input x 8 output channels, i.e. 32 FMAs per pixel against three LDS.128 (X: one line shared by the lanes of a channel
 // quad, dY: two lines of 16 bytes per lane, contiguous over the lanes).  LCO lanes sit along the output channels:
 // LCO = 8 / 4 / 2 covers 64 / 32 / 16 output x 16 / 32 / 64 input channels per CTA (blockIdx.y walks the input channel
-// blocks).  A CTA walks `gridDim.x`-strided tiles with its accumulators in registers; fp32 atomics once at the end.
-constexpr int W3_TH = 8, W3_TW = 32, W3_IH = W3_TH + 2, W3_IW = W3_TW + 2, W3_THREADS = 288;
+// blocks).  Two warps per tap (the upper and the lower four rows of the tile: 18 warps spread evenly over the four schedulers);
+// a CTA walks `gridDim.x`-strided tiles with its accumulators in registers, the two halves are added through shared memory and
+// leave as fp32 atomics once at the end.  Staging is cp.async (all loads of a tile in flight at once).
+constexpr int W3_TH = 8, W3_TW = 32, W3_IH = W3_TH + 2, W3_IW = W3_TW + 2, W3_THREADS = 576;
 
 template <int LCO>
 __global__ void __launch_bounds__(W3_THREADS) conv_wgrad3_kernel(const __grid_constant__ WGArgs a) {
@@ -268,12 +272,13 @@ __global__ void __launch_bounds__(W3_THREADS) conv_wgrad3_kernel(const __grid_co
     extern __shared__ __align__(16) float sm3[];
     float* xs = sm3;                                     // [W3_IH][W3_IW][CI]
     float* ds = sm3 + W3_IH * W3_IW * CI;                // [W3_TH * W3_TW][CO]
-    const int tid = threadIdx.x, lane = tid & 31, tap = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, tap = (tid >> 5) % 9, half = tid / 288;
     const int ky = tap / 3, kx = tap - ky * 3;
     const int ci4 = lane / LCO, co8 = lane % LCO;
     const int ci0 = blockIdx.y * CI;
     const int tiles_x = (a.Wy + W3_TW - 1) / W3_TW, tiles_y = (a.Hy + W3_TH - 1) / W3_TH;
-    const bool want_bias = a.db && tap == 0 && blockIdx.y == 0 && ci4 == 0;
+    const bool bias_warp = a.db && tap == 0 && blockIdx.y == 0;          // warp uniform
+    const bool want_bias = bias_warp && ci4 == 0;
     float acc[4][8] = {};
     float bsum[8] = {};
     for (int tile = blockIdx.x; tile < tiles_x * tiles_y; tile += gridDim.x) {
@@ -283,52 +288,68 @@ __global__ void __launch_bounds__(W3_THREADS) conv_wgrad3_kernel(const __grid_co
             const int pos = it / (CI / 4), c4 = it - pos * (CI / 4);
             const int r = pos / W3_IW, cc = pos - r * W3_IW;
             const int y = oy0 - 1 + r, x = ox0 - 1 + cc, c = ci0 + c4 * 4;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (y >= 0 && y < a.Hx && x >= 0 && x < a.Wx && c < a.cx) {
+            const bool ok = y >= 0 && y < a.Hx && x >= 0 && x < a.Wx && c < a.cx;
+            const float* gp = a.dy;
+            if (ok) {
                 int base = 0, sg = 0;
                 while (sg < a.nx - 1 && c >= base + a.x[sg].ch) { base += a.x[sg].ch; ++sg; }
-                v = ld4(a.x[sg].ptr + ((size_t)y * a.Wx + x) * a.x[sg].ch + (c - base));
+                gp = a.x[sg].ptr + ((size_t)y * a.Wx + x) * a.x[sg].ch + (c - base);
             }
-            st4(xs + pos * CI + c4 * 4, v);
+            cp_async16_zfill(xs + pos * CI + c4 * 4, gp, ok);
         }
         for (int it = tid; it < W3_TH * W3_TW * (CO / 4); it += W3_THREADS) {
             const int px = it / (CO / 4), q = it - px * (CO / 4);
             const int y = oy0 + px / W3_TW, x = ox0 + px % W3_TW;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (y < a.Hy && x < a.Wy && q * 4 < a.cy) v = ld4(a.dy + ((size_t)y * a.Wy + x) * a.cy + q * 4);
-            st4(ds + px * CO + q * 4, v);
+            const bool ok = y < a.Hy && x < a.Wy && q * 4 < a.cy;
+            cp_async16_zfill(ds + px * CO + q * 4, ok ? a.dy + ((size_t)y * a.Wy + x) * a.cy + q * 4 : a.dy, ok);
         }
+        cp_async_wait_all();
         __syncthreads();
         const float* xt = xs + (ky * W3_IW + kx) * CI + ci4 * 4;
         const float* dt = ds + co8 * 4;
+        auto sweep = [&](auto with_bias) {               // (the bias sum costs 8 issue slots per pixel: only the warps that own it)
 #pragma unroll 1
-        for (int r = 0; r < W3_TH; ++r) {
+            for (int r = half * (W3_TH / 2); r < (half + 1) * (W3_TH / 2); ++r) {
 #pragma unroll 4
-            for (int c = 0; c < W3_TW; ++c) {
-                const float4 xv = ld4(xt + (r * W3_IW + c) * CI);
-                const float4 d0 = ld4(dt + (r * W3_TW + c) * CO), d1 = ld4(dt + (r * W3_TW + c) * CO + CO / 2);
-                const float xa[4] = {xv.x, xv.y, xv.z, xv.w};
-                const float da[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+                for (int c = 0; c < W3_TW; ++c) {
+                    const float4 xv = ld4(xt + (r * W3_IW + c) * CI);
+                    const float4 d0 = ld4(dt + (r * W3_TW + c) * CO), d1 = ld4(dt + (r * W3_TW + c) * CO + CO / 2);
+                    const float xa[4] = {xv.x, xv.y, xv.z, xv.w};
+                    const float da[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
 #pragma unroll
-                for (int i = 0; i < 4; ++i)
+                    for (int i = 0; i < 4; ++i)
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) acc[i][k] = fmaf(xa[i], da[k], acc[i][k]);
-                if (want_bias) {
+                        for (int k = 0; k < 8; ++k) acc[i][k] = fmaf(xa[i], da[k], acc[i][k]);
+                    if constexpr (decltype(with_bias)::value) {
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) bsum[k] += da[k];
+                        for (int k = 0; k < 8; ++k) bsum[k] += da[k];
+                    }
                 }
             }
-        }
+        };
+        if (bias_warp) sweep(std::true_type{});
+        else sweep(std::false_type{});
         __syncthreads();
     }
+    // the lower half's sums join the upper half's through shared memory ([accumulator][tap][lane]: conflict free)
+    if (half == 1) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) sm3[(i * 8 + k) * 288 + tap * 32 + lane] = acc[i][k];
+    }
+    __syncthreads();
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
         const int co = (k < 4 ? 0 : CO / 2) + co8 * 4 + (k & 3);
         if (co >= a.cy) continue;
+        if (half == 0) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int ci = ci0 + ci4 * 4 + i;
-            if (ci < a.cx) atomicAdd(a.dw + ((size_t)tap * a.cx + ci) * a.cy + co, acc[i][k]);
+            for (int i = 0; i < 4; ++i) {
+                const int ci = ci0 + ci4 * 4 + i;
+                if (ci < a.cx)
+                    atomicAdd(a.dw + ((size_t)tap * a.cx + ci) * a.cy + co, acc[i][k] + sm3[(i * 8 + k) * 288 + tap * 32 + lane]);
+            }
         }
         if (want_bias) atomicAdd(a.db + co, bsum[k]);
     }
@@ -338,6 +359,7 @@ template <int LCO>
 static int launch_wgrad3(const WGArgs& a, cudaStream_t stream) {
     constexpr int CO = 8 * LCO, CI = 4 * (32 / LCO);
     constexpr int smem = (W3_IH * W3_IW * CI + W3_TH * W3_TW * CO) * (int)sizeof(float);
+    static_assert(smem >= 32 * 288 * (int)sizeof(float), "the tile buffers double as the reduction scratch");
     static unsigned long long smem_ok = 0;
     if (cudaError_t e = ensure_dyn_smem(conv_wgrad3_kernel<LCO>, smem, smem_ok)) return (int)e;
     const int tiles = ((a.Wy + W3_TW - 1) / W3_TW) * ((a.Hy + W3_TH - 1) / W3_TH);
@@ -346,6 +368,80 @@ static int launch_wgrad3(const WGArgs& a, cudaStream_t stream) {
     int gx = tiles;
     if (tiles * blocks_y > 148) gx = (tiles + 1) / 2;
     conv_wgrad3_kernel<LCO><<<dim3(gx, blocks_y), W3_THREADS, smem, stream>>>(a);
+    AARMVS_LAUNCH_RESULT();
+}
+
+// The same for a layer with 1 or 4 output channels (omega's stem conv: 32 -> 4; the head: 8 -> 1): lane = input channel, CY
+// accumulators per lane, one warp per tap.  The work is a hundredth of a cell's; the tiled kernel above would spend a full
+// 16 x 64 channel block on it.
+template <int CY>
+__global__ void __launch_bounds__(288) conv_wgrad3_narrow_kernel(const __grid_constant__ WGArgs a) {
+    __shared__ __align__(16) float xs[W3_IH * W3_IW * 32];
+    __shared__ __align__(16) float ds[W3_TH * W3_TW * CY];
+    const int tid = threadIdx.x, lane = tid & 31, tap = tid >> 5;
+    const int ky = tap / 3, kx = tap - ky * 3;
+    const int tiles_x = (a.Wy + W3_TW - 1) / W3_TW, tiles_y = (a.Hy + W3_TH - 1) / W3_TH;
+    const bool bias_warp = a.db && tap == 0;
+    float acc[CY] = {}, bsum[CY] = {};
+    for (int tile = blockIdx.x; tile < tiles_x * tiles_y; tile += gridDim.x) {
+        const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+        const int oy0 = ty * W3_TH, ox0 = tx * W3_TW;
+        for (int it = tid; it < W3_IH * W3_IW * 8; it += 288) {
+            const int pos = it >> 3, c = (it & 7) * 4;
+            const int r = pos / W3_IW, cc = pos - r * W3_IW;
+            const int y = oy0 - 1 + r, x = ox0 - 1 + cc;
+            const bool ok = y >= 0 && y < a.Hx && x >= 0 && x < a.Wx && c < a.cx;
+            const float* gp = a.dy;
+            if (ok) {
+                int base = 0, sg = 0;
+                while (sg < a.nx - 1 && c >= base + a.x[sg].ch) { base += a.x[sg].ch; ++sg; }
+                gp = a.x[sg].ptr + ((size_t)y * a.Wx + x) * a.x[sg].ch + (c - base);
+            }
+            cp_async16_zfill(xs + pos * 32 + c, gp, ok);
+        }
+        for (int px = tid; px < W3_TH * W3_TW; px += 288) {
+            const int y = oy0 + px / W3_TW, x = ox0 + px % W3_TW;
+            const bool ok = y < a.Hy && x < a.Wy;
+            const float* dp = a.dy + ((size_t)y * a.Wy + x) * CY;
+            if constexpr (CY == 4) cp_async16_zfill(ds + px * 4, ok ? dp : a.dy, ok);
+            else ds[px] = ok ? *dp : 0.f;
+        }
+        cp_async_wait_all();
+        __syncthreads();
+        const float* xt = xs + (ky * W3_IW + kx) * 32 + lane;
+#pragma unroll 1
+        for (int r = 0; r < W3_TH; ++r) {
+#pragma unroll 8
+            for (int c = 0; c < W3_TW; ++c) {
+                const float xv = xt[(r * W3_IW + c) * 32];
+                float da[CY];
+                if constexpr (CY == 4) {
+                    const float4 d = ld4(ds + (r * W3_TW + c) * 4);
+                    da[0] = d.x; da[1] = d.y; da[2] = d.z; da[3] = d.w;
+                } else {
+                    da[0] = ds[r * W3_TW + c];
+                }
+#pragma unroll
+                for (int k = 0; k < CY; ++k) acc[k] = fmaf(xv, da[k], acc[k]);
+                if (bias_warp) {
+#pragma unroll
+                    for (int k = 0; k < CY; ++k) bsum[k] += da[k];
+                }
+            }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int k = 0; k < CY; ++k) {
+        if (lane < a.cx) atomicAdd(a.dw + ((size_t)tap * a.cx + lane) * CY + k, acc[k]);
+        if (bias_warp && lane == 0) atomicAdd(a.db + k, bsum[k]);
+    }
+}
+
+template <int CY>
+static int launch_wgrad3_narrow(const WGArgs& a, cudaStream_t stream) {
+    const int tiles = ((a.Wy + W3_TW - 1) / W3_TW) * ((a.Hy + W3_TH - 1) / W3_TH);
+    conv_wgrad3_narrow_kernel<CY><<<tiles > 32 ? (tiles + 1) / 2 : tiles, 288, 0, stream>>>(a);
     AARMVS_LAUNCH_RESULT();
 }
 
@@ -382,7 +478,7 @@ __global__ void __launch_bounds__(256, 1) conv_dx3_kernel(const __grid_constant_
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int cg = warp % C::NCG, ps = warp / C::NCG;
     const int co0 = cg * TCO;
-    for (int i = tid * 4; i < C::W_FLOATS; i += 256 * 4) st4(sw + i, ldg4(a.w + i));
+    for (int i = tid * 4; i < C::W_FLOATS; i += 256 * 4) cp_async16_zfill(sw + i, a.w + i, true);     // lands with the first tile
     const int tiles_x = (a.W + C::TW - 1) / C::TW, tiles_y = (a.H + C::TH - 1) / C::TH;
     constexpr int CIN4 = CIN / 4;
     for (int tile = blockIdx.x; tile < tiles_x * tiles_y; tile += gridDim.x) {
@@ -392,10 +488,10 @@ __global__ void __launch_bounds__(256, 1) conv_dx3_kernel(const __grid_constant_
             const int pos = it / CIN4, c4 = it - pos * CIN4;
             const int r = pos / C::IW, cc = pos - r * C::IW;
             const int y = oy0 - 1 + r, x = ox0 - 1 + cc;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (y >= 0 && y < a.H && x >= 0 && x < a.W) v = ld4(a.in + ((size_t)y * a.W + x) * CIN + c4 * 4);
-            st4(sin + pos * C::CPAD + c4 * 4, v);
+            const bool ok = y >= 0 && y < a.H && x >= 0 && x < a.W;
+            cp_async16_zfill(sin + pos * C::CPAD + c4 * 4, ok ? a.in + ((size_t)y * a.W + x) * CIN + c4 * 4 : a.in, ok);
         }
+        cp_async_wait_all();
         __syncthreads();
         float acc[TPX][TCO];
 #pragma unroll
@@ -737,10 +833,12 @@ extern "C" int aarmvs_conv_bwd_weight(const aarmvs_seg* x, int nx, int Hx, int W
     AARMVS_CHECK_ARG(c == cx);
     a.nx = nx; a.dy = dy; a.Hx = Hx; a.Wx = Wx; a.Hy = Hy; a.Wy = Wy; a.cx = cx; a.cy = cy; a.ks = ksize; a.stride = stride;
     a.dw = dweight; a.db = dbias;
-    if (ksize == 3 && stride == 1 && Hx == Hy && Wx == Wy && cy % 4 == 0) {
+    if (ksize == 3 && stride == 1 && Hx == Hy && Wx == Wy && (cy % 4 == 0 || cy == 1)) {
         bool quads = true;
         for (int s = 0; s < nx; ++s) quads = quads && a.x[s].ch % 4 == 0;
-        if (quads) {
+        if (quads && cx <= 32 && cy == 4) return launch_wgrad3_narrow<4>(a, (cudaStream_t)stream);
+        if (quads && cx <= 32 && cy == 1) return launch_wgrad3_narrow<1>(a, (cudaStream_t)stream);
+        if (quads && cy % 4 == 0) {
             if (cy > 32) return launch_wgrad3<8>(a, (cudaStream_t)stream);
             if (cy > 16) return launch_wgrad3<4>(a, (cudaStream_t)stream);
             return launch_wgrad3<2>(a, (cudaStream_t)stream);

@@ -30,6 +30,17 @@ static inline cudaError_t ensure_dyn_smem(K kern, int bytes, unsigned long long&
     return e;
 }
 
+// 16-byte asynchronous global -> shared copy (no register round trip: a staging loop keeps all its loads in flight);
+// !pred writes 16 zero bytes instead (src is not read, but must be a valid address).
+__device__ __forceinline__ void cp_async16_zfill(float* smem_dst, const float* src, bool pred) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    const int bytes = pred ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+}
+
 // Launch with programmatic stream serialization (see tc_common.cuh: pdl_wait).  AARMVS_NO_PDL=1 in the environment falls back
 // to a plain launch (A/B measurements).
 template <class Arg>

@@ -141,14 +141,20 @@ class Engine:
         return w
 
     # ------------------------------------------------------------------------------------------ workspace
-    def _workspace(self, H, W, N, D, device, keep_cost, with_loss=False, with_state=False):
-        key = (H, W, N, D, str(device), keep_cost, with_loss, with_state)
+    def _workspace(self, H, W, N, D, device, keep_cost, with_loss=False, with_state=False, slot=0):
+        key = (H, W, N, D, str(device), keep_cost, with_loss, with_state, slot)
         ws = self._ws.get(key)
         if ws is not None:
             self._ws.move_to_end(key)
             return ws
-        while len(self._ws) >= self.MAX_WORKSPACES:          # a scan mixes view counts / shapes: do not let slabs pile up
-            self._ws.popitem(last=False)
+        # a scan mixes view counts / shapes: do not let slabs pile up.  The per-sample slots of one shape (training batches)
+        # count as one workspace and leave together.
+        bases = {k[:-1] for k in self._ws}
+        while key[:-1] not in bases and len(bases) >= self.MAX_WORKSPACES:
+            oldest = next(iter(self._ws))[:-1]
+            for k in [k for k in self._ws if k[:-1] == oldest]:
+                del self._ws[k]
+            bases.discard(oldest)
         if H % 4 or W % 4:
             raise RuntimeError(f"feature height and width must be multiples of 4, got {H}x{W} (models/drmvsnet.py:51-52, 148-160)")
         if not 2 <= N <= 16:
@@ -493,13 +499,17 @@ class Engine:
             off += 2 * n
         return lay, off
 
-    def forward_saving_state(self, imgs, proj_matrices, depth_values):
+    def forward_saving_state(self, imgs, proj_matrices, depth_values, slot=0, sweep_stream=None):
         """The training-phase forward of ONE sample (models/drmvsnet.py:272-287) on the tensor-core kernels (the same graph-replayed
-        plane chain as inference, plus aarmvs_snapshot_state after every plane), keeping what the backward pass needs: the features of the N views, the regularised cost of every plane and a snapshot
-        of the recurrent state (h, c of the five cells) after every plane -- one flat record of 66 floats per full-resolution
-        pixel and plane (state_layout), record 0 = the zero state before plane 0; everything else is recomputed per plane by
-        the backward (aarmvsnet_b200/backward.py).
-        Returns {"cost": [D,P], "feat": [N,P,32], "state": [D+1, record], ...}."""
+        plane chain as inference, plus aarmvs_snapshot_state after every plane), keeping what the backward pass needs: the features
+        of the N views, the regularised cost of every plane, a snapshot of the recurrent state (h, c of the five cells) after every
+        plane -- one flat record of 66 floats per full-resolution pixel and plane (state_layout), record 0 = the zero state before
+        plane 0 -- and the activated gates of every cell and plane (132 floats per pixel and plane); the rest is recomputed per
+        plane by the backward (aarmvsnet_b200/backward.py).
+        slot / sweep_stream: the samples of a batch are independent chains of short kernels on small maps, so a caller may run
+        each sample's plane sweep on its own stream with its own workspace (`slot`); FeatNet (shared scratch) and every
+        allocation stay on the calling stream, and the CALLER joins `sweep_stream` before it touches the results.
+        Returns {"cost": [D,P], "feat": [N,P,32], "state": [D+1, record], "gates": 5 x [D,P_i,4 Ch_i], ...}."""
         device = imgs.device
         if device.type != "cuda":
             raise RuntimeError("aarmvsnet_b200 has no CPU path: inputs must live on a CUDA device")
@@ -509,30 +519,39 @@ class Engine:
             N, _, H, W = imgs.shape
             D = depth_values.shape[0]
             w = self._weights(device)
-            ws = self._workspace(H, W, N, D, device, True, False, True)
-            stream = ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+            ws = self._workspace(H, W, N, D, device, True, False, True, slot)
+            main = torch.cuda.current_stream(device)
+            stream = ctypes.c_void_p(main.cuda_stream)
             imgs = imgs.to(torch.float32).contiguous()
             for v in range(N):
                 self.feature_map(imgs[v], ws["feat"][v], ws, w, stream)
-            ws["cams"].copy_(self.relative_cameras(proj_matrices), non_blocking=True)
-            ws["depths"].copy_(depth_values.to(torch.float32), non_blocking=True)
-            ws["plane"].zero_()
-            ws["psums"].zero_()
             lay, rec = self.state_layout(H, W)
-            state = torch.empty(D + 1, rec, device=device, dtype=torch.float32)
+            f32 = dict(device=device, dtype=torch.float32)
+            state = torch.empty(D + 1, rec, **f32)
             state[0].zero_()
-            saved = {"H": H, "W": W, "N": N, "D": D, "imgs": imgs, "cams": ws["cams"].clone(), "depths": ws["depths"].clone(),
-                     "state": state}
-            ws["snap"]["state_pp"].fill_(state.data_ptr())
-            # the activated gates of every plane, as the cells used them: [D][P_i][4 Ch_i] per cell (132 floats per full-resolution
-            # pixel and plane); the kernels read the bases from device memory, so the captured plane graph serves every sample
-            saved["gates"] = [torch.empty(D, (H // sc) * (W // sc), 4 * ch, device=device, dtype=torch.float32)
-                              for ch, sc in zip(_HID, _SCALE)]
-            for i, g in enumerate(saved["gates"]):
-                ws["snap"]["gates_pp"][i].fill_(g.data_ptr())
-            self._run_planes(ws, w, device, stream, D)
-            saved["feat"] = ws["feat"].clone()
-            saved["cost"] = ws["cost_volume"].clone()
+            cams_host = self.relative_cameras(proj_matrices)
+            saved = {"H": H, "W": W, "N": N, "D": D, "imgs": imgs, "state": state,
+                     "cams": torch.empty_like(ws["cams"]), "depths": torch.empty_like(ws["depths"]),
+                     "feat": torch.empty_like(ws["feat"]), "cost": torch.empty_like(ws["cost_volume"]),
+                     # the activated gates of every plane, as the cells used them: [D][P_i][4 Ch_i] per cell; the kernels read
+                     # the bases from device memory, so the captured plane graph serves every sample
+                     "gates": [torch.empty(D, (H // sc) * (W // sc), 4 * ch, **f32) for ch, sc in zip(_HID, _SCALE)]}
+            depth_values = depth_values.to(torch.float32)
+            if sweep_stream is not None:
+                sweep_stream.wait_stream(main)
+            with torch.cuda.stream(sweep_stream if sweep_stream is not None else main):
+                stream = ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+                ws["cams"].copy_(cams_host, non_blocking=True)
+                ws["depths"].copy_(depth_values, non_blocking=True)
+                ws["plane"].zero_()
+                ws["psums"].zero_()
+                ws["snap"]["state_pp"].fill_(state.data_ptr())
+                for i, g in enumerate(saved["gates"]):
+                    ws["snap"]["gates_pp"][i].fill_(g.data_ptr())
+                self._run_planes(ws, w, device, stream, D)
+                for k in ("cams", "depths", "feat"):
+                    saved[k].copy_(ws[k])
+                saved["cost"].copy_(ws["cost_volume"])
             return saved
 
     @staticmethod

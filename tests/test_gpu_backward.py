@@ -172,7 +172,10 @@ def test_conv_bwd_weight(ctx, case):
     dys = _nhwc(dy).float().to(dev)
     bw.wgrad(segs, H, W, dys, ho, wo, cout, k, s, dw, db)
     _close(dw.reshape(k, k, cin, cout).permute(3, 2, 0, 1).cpu(), want_w, 5e-5, case + " dW")
-    _close(db.cpu(), want_b, 5e-5, case + " db")
+    # sum_p dy cancels heavily (884+ summands of either sign, atomics in any order): measure against the summands' scale
+    err_b = (db.cpu().double() - want_b).abs().max().item()
+    print(f"{case} db: max |err| = {err_b:.2e}, sum |dy| = {dy.abs().sum((1, 2)).max().item():.1f}")
+    assert err_b <= 2e-7 * dy.abs().sum((1, 2)).max().item(), f"{case} db: {err_b:.2e}"
 
 
 @pytest.mark.parametrize("C,groups", [(4, 1), (16, 2), (32, 4), (8, 1)])
