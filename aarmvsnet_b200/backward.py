@@ -127,8 +127,13 @@ class Backward:
         b = {"key": key}
         b["costv"] = torch.empty(S, P, 32, **f32)
         b["t0"] = torch.empty(S, P, 4, **f32)
-        b["stats"] = torch.zeros(S * 6, device=dev, dtype=torch.float64)
-        b["bstats"] = torch.zeros(S * 6, device=dev, dtype=torch.float64)
+        # every fp64 accumulator a plane starts from zero, in one block (one fill per plane): omega's forward / backward sums,
+        # the two GroupNorms' sums and the per-channel sums of their backward passes
+        z = torch.zeros(2 * S * 6 + 2 * 4 + 2 * 128, device=dev, dtype=torch.float64)
+        b["zeros"] = z
+        b["stats"], b["bstats"] = z[:S * 6], z[S * 6:2 * S * 6]
+        o = 2 * S * 6
+        b["gsum0"], b["gsum1"], b["chan0"], b["chan1"] = z[o:o + 4], z[o + 4:o + 8], z[o + 8:o + 136], z[o + 136:o + 264]
         b["cost"] = torch.empty(P, 32, **f32)
         b["rew"] = torch.empty(S, P, **f32)
         b["pool0"] = torch.empty(P // 4, 16, **f32)
@@ -137,13 +142,11 @@ class Backward:
             b[f"up{i}raw"] = torch.empty(pp, 16, **f32)
             b[f"up{i}"] = torch.empty(pp, 16, **f32)
             b[f"dup{i}"] = torch.empty(pp, 16, **f32)
-            b[f"gsum{i}"] = torch.zeros(4, device=dev, dtype=torch.float64)
         b["dpool0"] = torch.empty(P // 4, 16, **f32)
         b["dpool1"] = torch.empty(P // 16, 16, **f32)
         b["gates_pp"] = torch.zeros(5, device=dev, dtype=torch.int64)     # bases of the sample's five gate histories (forward)
         b["dgates"] = [torch.empty(Pi[i], 4 * _HID[i], **f32) for i in range(5)]
         b["dh"] = [torch.zeros(Pi[i], _HID[i], **f32) for i in range(5)]
-        b["dhprev"] = [torch.zeros(Pi[i], _HID[i], **f32) for i in range(5)]
         b["dc"] = [torch.zeros(Pi[i], _HID[i], **f32) for i in range(5)]
         b["dcost"] = torch.empty(P, 32, **f32)
         b["dcostv"] = torch.empty(S, P, 32, **f32)
@@ -164,7 +167,6 @@ class Backward:
         b["graph"] = None
         b["side"] = torch.cuda.Stream(dev)                                  # second branch of the plane (see _plane)
         b["stage_ready"] = torch.cuda.Event()
-        b["chan"] = torch.zeros(128, device=dev, dtype=torch.float64)      # per-channel sums of one GroupNorm backward
         self._wss[slot] = b
         return b
 
@@ -189,8 +191,10 @@ class Backward:
                    "aarmvs_gn_relu_apply")
 
     def gn_bwd(self, x, dy, P, C, groups, sums, gn, dx, dgamma, dbeta, dbias=None, chan=None):
-        chan = self.chan if chan is None else chan
-        chan.zero_()
+        """chan: zeroed per-channel scratch of the caller (default: this object's, zeroed here)."""
+        if chan is None:
+            chan = self.chan
+            chan.zero_()
         for stage in (1, 2):
             capi.check(self.lib.aarmvs_gn_relu_bwd(stage, _ptr(x), _ptr(dy), P, C, groups, _ptr(sums), _ptr(gn[0]), _ptr(gn[1]), 1,
                                                    _ptr(chan), _ptr(dx), _ptr(dgamma), _ptr(dbeta),
@@ -245,7 +249,7 @@ class Backward:
         eng = self.eng
         H, W, N, D = saved["H"], saved["W"], saved["N"], saved["D"]
         b = self._workspace(H, W, N, slot)
-        for t in b["dh"] + b["dc"] + b["dhprev"]:
+        for t in b["dh"] + b["dc"]:
             t.zero_()
         b["dfeat"].zero_()
         dcost_volume = dcost_volume.contiguous()
@@ -308,9 +312,10 @@ class Backward:
                 fn()
 
         # ---------------- recompute the plane's forward intermediates
+        b["zeros"].zero_()
+
         def stage_recompute():
             sst = self._st()
-            b["stats"].zero_()
             eng.cost_stem(ref, src, P * 32, H, W, S, cams, w, depths, 0, dptr, 1, _ptr(b["t0"]), _ptr(b["stats"]), sst, _ptr(b["costv"]))
             for stage in (2, 3):
                 capi.check(lib.aarmvs_omega_stats(stage, _ptr(b["t0"]), H, W, S, 1, w["tail_host"], _ptr(b["stats"]), sst), "aarmvs_omega_stats")
@@ -324,7 +329,6 @@ class Backward:
         for i, (hin, win, src_h) in enumerate(((H4, W4, h[2]), (H2, W2, h[3]))):
             self.conv([_seg(src_h, 16)], hin, win, [_seg(b[f"up{i}raw"], 16)], 2 * hin, 2 * win, 3, 2, True, bw[f"deconv{i}.w"],
                       bw[f"deconv{i}.b"])
-            b[f"gsum{i}"].zero_()
             capi.check(lib.aarmvs_gn_sums(_ptr(b[f"up{i}raw"]), 4 * hin * win, 16, 2, _ptr(b[f"gsum{i}"]), st), "aarmvs_gn_sums")
             self.gn_apply(b[f"up{i}raw"], 4 * hin * win, 16, 2, b[f"gsum{i}"], bw[f"deconv{i}.gn"], b[f"up{i}"])
         xin = [[_seg(b["cost"], 32)], [_seg(b["pool0"], 16)], [_seg(b["pool1"], 16)], [_seg(b["up0"], 16), _seg(h[1], 16)],
@@ -332,7 +336,7 @@ class Backward:
         # (the cells' gates are not recomputed: the training forward stored them activated, saved["gates"])
 
         # ---------------- backward of the plane.  b["dh"][i] enters holding dL/dh_i^d from plane d+1 (cell i's h_prev input)
-        dh, dhp, dc = b["dh"], b["dhprev"], b["dc"]
+        dh, dc = b["dh"], b["dc"]
         dcr = b["dcr"]                                               # [P] = [P][1]
         self.conv([_seg(dcr, 1)], H, W, [_seg(dh[4], 8, 1)], H, W, 3, 1, True, bw["head.wT"])
         on_side(lambda: self.wgrad([_seg(h[4], 8)], H, W, dcr, H, W, 1, 3, 1, g["head.w"], g["head.b"]))
@@ -343,13 +347,15 @@ class Backward:
                                                      _ptr(b["dgates"][i]), hw[i][0] * hw[i][1], _HID[i], st), "aarmvs_lstm_gates_bwd_act")
             on_side(lambda: self.wgrad(xin[i] + [_seg(hp[i], _HID[i])], hw[i][0], hw[i][1], b["dgates"][i], hw[i][0], hw[i][1],
                                        4 * _HID[i], 3, 1, g[f"cell{i}.w"], g[f"cell{i}.b"]))
-            self.conv([_seg(b["dgates"][i], 4 * _HID[i])], hw[i][0], hw[i][1], outs + [_seg(dhp[i], _HID[i])], hw[i][0], hw[i][1], 3, 1, True,
+            # dL/dh_i^{d-1} replaces dh[i]: every contribution to dL/dh_i^d precedes this point of the plane, the ones of plane
+            # d-1 (skip connections, pooling, deconvolutions, the head) accumulate onto it in the next replay
+            self.conv([_seg(b["dgates"][i], 4 * _HID[i])], hw[i][0], hw[i][1], outs + [_seg(dh[i], _HID[i])], hw[i][0], hw[i][1], 3, 1, True,
                       bw[f"cell{i}.wT"])
 
         def up_bwd(i, hin, win, src_h, dh_target):
             pp = 4 * hin * win
             self.gn_bwd(b[f"up{i}raw"], b[f"dup{i}"], pp, 16, 2, b[f"gsum{i}"], bw[f"deconv{i}.gn"], b[f"dup{i}"], g[f"deconv{i}.gamma"],
-                        g[f"deconv{i}.beta"], g[f"deconv{i}.b"], chan=b["chan"])
+                        g[f"deconv{i}.beta"], g[f"deconv{i}.b"], chan=b[f"chan{i}"])
             on_side(lambda: self.wgrad([_seg(b[f"dup{i}"], 16)], 2 * hin, 2 * win, src_h, hin, win, 16, 3, 2, g[f"deconv{i}.wT"]))
             self.conv([_seg(b[f"dup{i}"], 16)], 2 * hin, 2 * win, [_seg(dh_target, 16, 1)], hin, win, 3, 2, False, bw[f"deconv{i}.wT"])
 
@@ -367,7 +373,6 @@ class Backward:
         main.wait_event(b["stage_ready"])                            # costv, t0, stats, rew of the recompute branch
         capi.check(lib.aarmvs_aggregate_bwd(_ptr(b["dcost"]), _ptr(b["costv"]), _ptr(b["rew"]), S, P, _ptr(b["dcostv"]), _ptr(b["drew"]), st),
                    "aarmvs_aggregate_bwd")
-        b["bstats"].zero_()
         for stage in (3, 2, 1, 0):
             capi.check(lib.aarmvs_omega_bwd(stage, _ptr(b["t0"]), _ptr(b["drew"]), H, W, S, w["tail_host"], _ptr(b["stats"]),
                                             _ptr(b["bstats"]), _ptr(g["tail"]), _ptr(b["dt0"]), st), "aarmvs_omega_bwd")
@@ -381,9 +386,7 @@ class Backward:
             self.conv([_seg(b["dt0"][v], 4)], H, W, [_seg(b["dcostv"][v], 32, 1)], H, W, 3, 1, True, bw["stem.wT"])
         capi.check(lib.aarmvs_warp_bwd(ref, src, P * 32, H, W, S, cams, depths, 0, dptr, ac, _ptr(b["dcostv"]), _ptr(b["dfeat"]),
                                        _ptr(b["dfeat"], P * 32), st), "aarmvs_warp_bwd")
-        # ---------------- carry: dL/dh_{d-1} is the next (lower) plane's starting dh; dc was updated in place
-        for i in range(5):
-            dh[i].copy_(dhp[i])
+        # (carry: dh now holds dL/dh_{d-1}, the next (lower) plane's starting point; dc was updated in place)
         main.wait_stream(side)                                       # join: the plane's buffers are free for the next plane
 
     # ------------------------------------------------------------------------------------------ FeatNet of one view
