@@ -2,12 +2,15 @@
 // models/drmvsnet.py:272-295).  Everything here is fp32 on NHWC tensors, CUDA-core FMA:
 //
 //   conv_nhwc_kernel      direct convolution / transposed convolution over a channel CONCAT of inputs, writing (or adding
-//                         to) a channel SPLIT of outputs.  One kernel covers the gate pre-activations recomputed per plane
-//                         (module.py:80-82), every data gradient dX = dY (*) W^T (stride 1 and 2; the deconvolution's is a
-//                         strided conv, module.py:281), the ConvTranspose forward itself, and the 1x1 layers of FeatNet.
+//                         to) a channel SPLIT of outputs.  One kernel covers the data gradients dX = dY (*) W^T of the small
+//                         and the strided layers (the deconvolution's is a strided conv, module.py:281), the ConvTranspose
+//                         forward itself, and the 1x1 layers of FeatNet.
+//   conv_dx3_kernel       the same sum for the five cells' 3x3 data gradients, register tiled (the widest convolutions).
 //   conv_wgrad_kernel     dW[tap][ci][co] += sum_p X[p + tap][ci] * dY[p][co] (+ bias gradient), fp32 atomics at the end.
+//   conv_wgrad3_kernel    the same for 3x3 stride-1 layers: one staged tile for all nine taps, a warp pair per tap;
+//   conv_wgrad3_narrow_   ... and for 1 / 4 output channels (head, omega's stem).
 //   gn_*                  GroupNorm (+ReLU) materialisation, statistics, and the two-pass backward (global sums, then dX).
-//   lstm_gates_bwd        module.py:83-90 backwards: d gates, d c_{d-1} from d h_d, d c_d.
+//   lstm_gates_bwd(_act)  module.py:83-90 backwards: d gates, d c_{d-1} from d h_d, d c_d (from the gates the forward stored).
 //   maxpool2 / _bwd       drmvsnet.py:148,152; the gradient goes to the first maximum of the window in scan order (ATen).
 //
 // The training shape is small (128 x 160 feature maps, B = 4, D = 192: SURVEY.md §8d cfg5), so the backward keeps whole

@@ -584,8 +584,9 @@ def run_train(args):
                              "bound": "tensor", "achieved": ach, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
                              "frac": ach / pk["bf16_tflops_sustained"], "traffic": None,
                              "algorithmic_flops_per_step": flops,
-                             "note": "useful recurrence FLOPs (forward 1x + backward 2x) over the step time; the step is bound by launch "
-                                     "count and host enqueue (eager, per-plane recompute), not by the tensor pipe or HBM"},
+                             "note": "useful recurrence FLOPs (forward 1x + backward 2x) over the step time; the backward is ~50 short fp32 "
+                                     "kernels per plane and sample (issue-bound FMA code and launch latency), not bound by the "
+                                     "tensor pipe or HBM"},
                 "phases_ms": phases, "loss_first_last": [float(losses[0]), float(losses[-1])], "cpu_baseline": cpu}
         print(json.dumps(line))
     if world > 1:
