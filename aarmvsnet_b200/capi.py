@@ -8,7 +8,7 @@ import os
 from . import build as _build
 
 ERR_ARG = 1000001
-ABI_VERSION = 4
+ABI_VERSION = 5
 SRC_PLAIN, SRC_GN_RELU, SRC_MAXPOOL2, SRC_NCHW = 0, 1, 2, 3
 
 c_float_p = ctypes.POINTER(ctypes.c_float)

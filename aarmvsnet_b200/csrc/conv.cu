@@ -275,7 +275,7 @@ static int sm_count() {
     return n;
 }
 
-extern "C" int aarmvs_version(void) { return 4; }
+extern "C" int aarmvs_version(void) { return 5; }
 extern "C" int aarmvs_sm_count(void) { return sm_count(); }
 
 template <int CIN, int COUT, int KS, int STRIDE, int TCO, int TPX, int EPI>

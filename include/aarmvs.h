@@ -23,7 +23,7 @@ extern "C" {
 #define AARMVS_MAX_SRC_VIEWS 15
 #define AARMVS_MAX_PLANES_PER_CALL 16
 
-int aarmvs_version(void);          /* ABI version, currently 4 */
+int aarmvs_version(void);          /* ABI version, currently 5 (5: aarmvs_convlstm_cell_tc gained gates_out; aarmvs_lstm_gates_bwd_act) */
 int aarmvs_sm_count(void);         /* multiprocessors of the current device (148 on B200), <0 on error */
 
 /* ---------------------------------------------------------------------------------------------------------
