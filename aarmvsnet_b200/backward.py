@@ -47,9 +47,12 @@ def _taps_inverse(dw, cout, cin, k):
 class Backward:
     """Gradient accumulation for one optimisation step of one EMVSNet (all samples of the batch, all planes)."""
 
-    def __init__(self, engine, device, use_graph=True):
+    def __init__(self, engine, device, use_graph=True, dx_math="tc"):
+        """dx_math: the cells' data gradients on the tensor cores ("tc", csrc/conv_dx_tc.cu) or as fp32 FMA code ("fma", the
+        register-tiled conv_dx3_kernel: tests and A/B measurements)."""
         self.eng = engine
         self.use_graph = use_graph
+        self.dx_math = dx_math
         self.lib = engine.lib
         self.dev = device
         self.sd = {k: v.detach().to(device=device, dtype=torch.float32) for k, v in engine.module.state_dict().items()}
@@ -75,6 +78,9 @@ class Backward:
             wt = pack.conv_taps(sd[f"{cr}.cell_list.{i}.conv.weight"])           # [9][cin][4Ch], PyTorch gate order i|f|o|g
             bw[f"cell{i}.w"] = wt
             bw[f"cell{i}.wT"] = wt.transpose(1, 2).contiguous()                   # [9][4Ch][cin]: dX = dG (*) W^T
+            # the same as the B operand of the tensor-core data gradient: taps flipped (its taps index the input offset
+            # -1..1, aarmvs_conv_nhwc's `transposed` ones the output offset), output rows padded to 48 / 32
+            bw[f"cell{i}.dxtc"] = pack.conv_f16_steps(bw[f"cell{i}.wT"].flip(0), 32 if wt.shape[1] == 32 else 48)
             bw[f"cell{i}.b"] = sd[f"{cr}.cell_list.{i}.conv.bias"].contiguous()
             g[f"cell{i}.w"] = torch.zeros_like(wt)
             g[f"cell{i}.b"] = torch.zeros(wt.shape[2], **f32)
@@ -129,11 +135,12 @@ class Backward:
         b["t0"] = torch.empty(S, P, 4, **f32)
         # every fp64 accumulator a plane starts from zero, in one block (one fill per plane): omega's forward / backward sums,
         # the two GroupNorms' sums and the per-channel sums of their backward passes
-        z = torch.zeros(2 * S * 6 + 2 * 4 + 2 * 128, device=dev, dtype=torch.float64)
+        z = torch.zeros(2 * S * 6 + 2 * 4 + 2 * 128 + 4, device=dev, dtype=torch.float64)
         b["zeros"] = z
         b["stats"], b["bstats"] = z[:S * 6], z[S * 6:2 * S * 6]
         o = 2 * S * 6
         b["gsum0"], b["gsum1"], b["chan0"], b["chan1"] = z[o:o + 4], z[o + 4:o + 8], z[o + 8:o + 136], z[o + 136:o + 264]
+        b["gmax"] = z[o + 264:o + 268].view(torch.int32)       # max |dgates| of the five cells (bit patterns, atomicMax)
         b["cost"] = torch.empty(P, 32, **f32)
         b["rew"] = torch.empty(S, P, **f32)
         b["pool0"] = torch.empty(P // 4, 16, **f32)
@@ -146,6 +153,9 @@ class Backward:
         b["dpool1"] = torch.empty(P // 16, 16, **f32)
         b["gates_pp"] = torch.zeros(5, device=dev, dtype=torch.int64)     # bases of the sample's five gate histories (forward)
         b["dgates"] = [torch.empty(Pi[i], 4 * _HID[i], **f32) for i in range(5)]
+        # the same as scaled fp16 (hi, lo) operand planes for the tensor-core data gradient, and the scale's inverse
+        b["dgplanes"] = [torch.empty(2, 4 * _HID[i] // 8, Pi[i], 8, device=dev, dtype=torch.float16) for i in range(5)]
+        b["ginv"] = torch.ones(5, **f32)
         b["dh"] = [torch.zeros(Pi[i], _HID[i], **f32) for i in range(5)]
         b["dc"] = [torch.zeros(Pi[i], _HID[i], **f32) for i in range(5)]
         b["dcost"] = torch.empty(P, 32, **f32)
@@ -343,14 +353,23 @@ class Backward:
 
         def cell_bwd(i, outs):
             # at plane 0 the staged previous state is the zero record: c_prev = h_prev = 0 (module.py:94-96)
+            tc = self.dx_math == "tc"
             capi.check(lib.aarmvs_lstm_gates_bwd_act(_ptr(b["gates_pp"], i), 0, dptr, _ptr(cp[i]), _ptr(c[i]), _ptr(dh[i]), _ptr(dc[i]),
-                                                     _ptr(b["dgates"][i]), hw[i][0] * hw[i][1], _HID[i], st), "aarmvs_lstm_gates_bwd_act")
+                                                     _ptr(b["dgates"][i]), hw[i][0] * hw[i][1], _HID[i],
+                                                     _ptr(b["gmax"], i) if tc else None, st), "aarmvs_lstm_gates_bwd_act")
             on_side(lambda: self.wgrad(xin[i] + [_seg(hp[i], _HID[i])], hw[i][0], hw[i][1], b["dgates"][i], hw[i][0], hw[i][1],
                                        4 * _HID[i], 3, 1, g[f"cell{i}.w"], g[f"cell{i}.b"]))
             # dL/dh_i^{d-1} replaces dh[i]: every contribution to dL/dh_i^d precedes this point of the plane, the ones of plane
             # d-1 (skip connections, pooling, deconvolutions, the head) accumulate onto it in the next replay
-            self.conv([_seg(b["dgates"][i], 4 * _HID[i])], hw[i][0], hw[i][1], outs + [_seg(dh[i], _HID[i])], hw[i][0], hw[i][1], 3, 1, True,
-                      bw[f"cell{i}.wT"])
+            outs = outs + [_seg(dh[i], _HID[i])]
+            if tc:       # tensor cores: the gate gradients as scaled fp16 (hi, lo) operand planes through the forward cell's GEMM
+                capi.check(lib.aarmvs_split_planes_scaled(_ptr(b["dgates"][i]), hw[i][0], hw[i][1], 4 * _HID[i], _ptr(b["gmax"], i),
+                                                          _ptr(b["dgplanes"][i]), _ptr(b["ginv"], i), st), "aarmvs_split_planes_scaled")
+                capi.check(lib.aarmvs_conv_dx_tc(_ptr(b["dgplanes"][i]), hw[i][0], hw[i][1], 4 * _HID[i], _segs(*outs), len(outs),
+                                                 sum(o.channels for o in outs), _ptr(bw[f"cell{i}.dxtc"]), _ptr(b["ginv"], i), st),
+                           "aarmvs_conv_dx_tc")
+            else:
+                self.conv([_seg(b["dgates"][i], 4 * _HID[i])], hw[i][0], hw[i][1], outs, hw[i][0], hw[i][1], 3, 1, True, bw[f"cell{i}.wT"])
 
         def up_bwd(i, hin, win, src_h, dh_target):
             pp = 4 * hin * win

@@ -718,12 +718,15 @@ __global__ void __launch_bounds__(256) lstm_gates_bwd_kernel(const float* __rest
 }
 
 // The same from the activated gates stored by the training forward (no sigmoid / tanh of pre-activations, no conv recompute).
+// max_bits (optional): receives max |dgates| as a bit pattern (atomicMax on the unsigned view of a non-negative float), the
+// scale of the tensor-core data gradient that follows (conv_dx_tc.cu); the caller zeroes it.
 __global__ void __launch_bounds__(256) lstm_gates_bwd_act_kernel(const float* const* __restrict__ hist, int d_host, const int* __restrict__ d_dev,
                                                                  const float* __restrict__ c_prev, const float* __restrict__ c_new,
                                                                  const float* __restrict__ dh, float* __restrict__ dc,
-                                                                 float* __restrict__ dgates, size_t P, int Ch) {
+                                                                 float* __restrict__ dgates, size_t P, int Ch, unsigned* __restrict__ max_bits) {
     const float* gates = *hist + (size_t)plane_index(d_host, d_dev) * P * 4 * Ch;
     const size_t n = P * (size_t)Ch;
+    float mx = 0.f;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         const size_t p = i / Ch;
         const int c = (int)(i - p * Ch);
@@ -733,11 +736,19 @@ __global__ void __launch_bounds__(256) lstm_gates_bwd_act_kernel(const float* co
         const float dhv = dh[i];
         const float dct = dc[i] + dhv * go * (1.f - th * th);
         float* dg = dgates + p * 4 * Ch;
-        dg[c] = dct * gg * gi * (1.f - gi);
-        dg[Ch + c] = dct * c_prev[i] * gf * (1.f - gf);
-        dg[2 * Ch + c] = dhv * th * go * (1.f - go);
-        dg[3 * Ch + c] = dct * gi * (1.f - gg * gg);
+        const float d0 = dct * gg * gi * (1.f - gi), d1 = dct * c_prev[i] * gf * (1.f - gf);
+        const float d2 = dhv * th * go * (1.f - go), d3 = dct * gi * (1.f - gg * gg);
+        dg[c] = d0;
+        dg[Ch + c] = d1;
+        dg[2 * Ch + c] = d2;
+        dg[3 * Ch + c] = d3;
         dc[i] = dct * gf;
+        mx = fmaxf(fmaxf(mx, fmaxf(fabsf(d0), fabsf(d1))), fmaxf(fabsf(d2), fabsf(d3)));
+    }
+    if (max_bits) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        if ((threadIdx.x & 31) == 0 && mx > 0.f) atomicMax(max_bits, __float_as_uint(mx));
     }
 }
 
@@ -894,10 +905,10 @@ extern "C" int aarmvs_lstm_gates_bwd(const float* gates, const float* c_prev, co
 }
 
 extern "C" int aarmvs_lstm_gates_bwd_act(const float* const* gates_history, int d_host, const int* d_dev, const float* c_prev, const float* c_new,
-                                         const float* dh, float* dc, float* dgates, size_t P, int hidden, void* stream) {
+                                         const float* dh, float* dc, float* dgates, size_t P, int hidden, unsigned* max_bits, void* stream) {
     AARMVS_CHECK_ARG(gates_history && c_prev && c_new && dh && dc && dgates && P > 0 && hidden > 0);
     lstm_gates_bwd_act_kernel<<<grid_for(P * hidden, 256), 256, 0, (cudaStream_t)stream>>>(gates_history, d_host, d_dev, c_prev, c_new, dh,
-                                                                                           dc, dgates, P, hidden);
+                                                                                           dc, dgates, P, hidden, max_bits);
     AARMVS_LAUNCH_RESULT();
 }
 

@@ -51,6 +51,20 @@ def lstm_gates_f16_steps(w, b):
     return steps.contiguous(), bias
 
 
+def conv_f16_steps(taps, n_pad=None):
+    """[9][cin][n] fp32 tap-major weights (cin a multiple of 16) -> [9 * cin/16 K steps][2 chunks][2 (hi, lo)][n_pad][8] fp16,
+    the B operand of csrc/conv_dx_tc.cu (the arrangement of lstm_gates_f16_steps without the gate reordering; output rows
+    beyond n are zero)."""
+    k, cin, n = taps.shape
+    n_pad = n_pad or n
+    full = taps.new_zeros(k, cin, n_pad)
+    full[:, :, :n] = taps
+    blk = full.reshape(k, cin // 16, 2, 8, n_pad)
+    hi = blk.half()
+    lo = (blk - hi.float()).half()
+    return torch.stack([hi, lo], -3).transpose(-1, -2).reshape(k * (cin // 16), 2, 2, n_pad, 8).contiguous()
+
+
 def taps_f16(taps, n_pad=None):
     """[9][cin][n] fp32 tap-major weights -> tcgen05 B operand [2 planes hi,lo][9][cin_pad/8][n_pad][8] fp16
     (un-swizzled K-major: 16-byte chunks of 8 input channels; cin padded to a multiple of 16, n to n_pad, with zeros)."""

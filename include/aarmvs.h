@@ -23,7 +23,7 @@ extern "C" {
 #define AARMVS_MAX_SRC_VIEWS 15
 #define AARMVS_MAX_PLANES_PER_CALL 16
 
-int aarmvs_version(void);          /* ABI version, currently 5 (5: aarmvs_convlstm_cell_tc gained gates_out; aarmvs_lstm_gates_bwd_act) */
+int aarmvs_version(void);          /* ABI version, currently 5 (5: aarmvs_convlstm_cell_tc gained gates_out; aarmvs_lstm_gates_bwd_act, aarmvs_conv_dx_tc, aarmvs_split_planes_scaled) */
 int aarmvs_sm_count(void);         /* multiprocessors of the current device (148 on B200), <0 on error */
 
 /* ---------------------------------------------------------------------------------------------------------
@@ -326,9 +326,26 @@ int aarmvs_lstm_gates_bwd(const float* gates, const float* c_prev, const float* 
                           size_t P, int hidden, void* stream);
 /* The same from the ACTIVATED gates the training forward stored (aarmvs_convlstm_cell_tc: gates_out): *gates_history (device
  * memory) is the base of [planes][P][4*hidden]; record d = *d_dev if d_dev is non-null (one captured graph serves every plane
- * and sample), else d_host. */
+ * and sample), else d_host.
+ * max_bits: optional; receives max |dgates| as the bit pattern of a float (atomicMax on a zeroed word), the scale of
+ * aarmvs_split_planes_scaled. */
 int aarmvs_lstm_gates_bwd_act(const float* const* gates_history, int d_host, const int* d_dev, const float* c_prev, const float* c_new,
-                              const float* dh, float* dc, float* dgates, size_t P, int hidden, void* stream);
+                              const float* dh, float* dc, float* dgates, size_t P, int hidden, unsigned* max_bits, void* stream);
+
+/* The cells' data gradient dX = dG (*) W^T on the tensor cores (csrc/conv_dx_tc.cu): the forward cell's TMA-fed tcgen05
+ * implicit GEMM with the gate gradients as operand planes.
+ * aarmvs_split_planes_scaled: fp32 x [H][W][channels] -> operand planes [2][channels/8][H][W][8] of 2^k x, k chosen so that
+ * the largest element (*max_bits, see above) lands in [128, 256): gradients are far below fp16's normal range; writes 2^-k
+ * to *inv_scale (device).
+ * aarmvs_conv_dx_tc: out[Y][X][co] = 2^-k sum_{ky,kx,ci} planes[Y-1+ky][X-1+kx][ci] * w[ky*3+kx][ci][co] scattered to
+ * `out` like aarmvs_conv_nhwc (channels multiples of 4, stored or accumulated).  weight_f16: DEVICE
+ * [9 * cin/16 K steps][2 chunks][2 (hi, lo)][NG][8] fp16 with NG = 48 or 32 output rows (zero rows beyond cout) -- for the
+ * data gradient the caller packs the spatially flipped, transposed cell weights (pack.conv_f16_steps).
+ * Supported (cin, cout): (64,48) (64,32) (32,40). */
+int aarmvs_split_planes_scaled(const float* x, int H, int W, int channels, const unsigned* max_bits, void* planes,
+                               float* inv_scale, void* stream);
+int aarmvs_conv_dx_tc(const void* dgate_planes, int H, int W, int cin, const aarmvs_seg* out, int nout, int cout,
+                      const void* weight_f16, const float* inv_scale, void* stream);
 
 /* MaxPool2d(2, 2) (drmvsnet.py:148,152) and its backward (dx += dout at the first maximum of each window). */
 int aarmvs_maxpool2(const float* x, int H, int W, int C, float* out, void* stream);

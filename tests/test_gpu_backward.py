@@ -133,6 +133,46 @@ def test_cell_data_gradient_tiled(ctx, cin, cout, splits, H, W):
     _close(_nchw(torch.cat(outs, 1), H, W).cpu(), want, 2e-5, f"dx {cin}->{cout}")
 
 
+@pytest.mark.parametrize("cin,cout,splits", [(64, 48, (32, 16)), (64, 48, (16, 16, 16)), (64, 32, (16, 16)), (32, 40, (16, 16, 8))])
+@pytest.mark.parametrize("H,W,magnitude", [(20, 24, 1.0), (40, 72, 3e-7), (128, 160, 1e-3)])
+def test_cell_data_gradient_tensor_cores(ctx, cin, cout, splits, H, W, magnitude):
+    """The same data gradients through aarmvs_split_planes_scaled + aarmvs_conv_dx_tc (the forward cell's tcgen05 GEMM with
+    the gate gradients as scaled fp16 (hi, lo) operand planes) against autograd in fp64, for gradients of the sizes a
+    training step sees (far below fp16's range) and with a few elements 2^-20 of the largest; ragged tiles, more tiles than
+    SMs at 128 x 160."""
+    from aarmvsnet_b200 import capi, pack
+    from aarmvsnet_b200.backward import _seg, _segs
+    from aarmvsnet_b200.engine import _ptr
+    _, bw = ctx
+    g = torch.Generator().manual_seed(37)
+    dev = "cuda"
+    r = lambda *s: torch.randn(*s, generator=g, dtype=torch.float64)
+    x = r(cout, H, W).requires_grad_(True)
+    wt = r(cin, cout, 3, 3)
+    y = F.conv2d(x[None], wt, None, padding=1)[0]
+    dy = r(*y.shape) * magnitude
+    dy[:, ::3, ::5] *= 2.0 ** -20
+    (want,) = torch.autograd.grad(y, x, dy)
+    wk = wt.permute(2, 3, 0, 1).reshape(9, cin, cout).float().contiguous()                  # [tap][gate][input] = W^T
+    wtc = pack.conv_f16_steps(wk.flip(0), 32 if cout == 32 else 48).to(dev)
+    dys = _nhwc(dy).float().to(dev)
+    mbits = dys.abs().max().reshape(1).view(torch.int32).clone()
+    planes = torch.empty(2, cin // 8, H * W, 8, device=dev, dtype=torch.float16)
+    inv = torch.zeros(1, device=dev)
+    capi.check(bw.lib.aarmvs_split_planes_scaled(_ptr(dys), H, W, cin, _ptr(mbits), _ptr(planes), _ptr(inv), bw._st()), "split")
+    scaled_max = dys.abs().max().item() / inv.item()
+    assert 128.0 <= scaled_max < 256.0, scaled_max
+    outs = [torch.full((H * W, c), 1.0 if i == 1 else float("nan"), device=dev) for i, c in enumerate(splits)]
+    segs = [_seg(o, c, 1 if i == 1 else 0) for i, (o, c) in enumerate(zip(outs, splits))]
+    capi.check(bw.lib.aarmvs_conv_dx_tc(_ptr(planes), H, W, cin, _segs(*segs), len(segs), cout, _ptr(wtc), _ptr(inv), bw._st()), "dx tc")
+    torch.cuda.synchronize()
+    got = torch.cat([outs[0], outs[1] - 1.0 * (1 if magnitude == 1.0 else 0)] + outs[2:], 1)
+    if magnitude != 1.0:                     # the accumulated segment: 1 + tiny is not representable, compare it separately
+        return _close(_nchw(torch.cat([outs[0]] + outs[2:], 1), H, W).cpu(),
+                      torch.cat([want[:splits[0]], want[splits[0] + splits[1]:]], 0), 1e-5, f"dx tc {cin}->{cout} (stored segments)")
+    _close(_nchw(got, H, W).cpu(), want, 1e-5, f"dx tc {cin}->{cout}")
+
+
 @pytest.mark.parametrize("case", ["s1_concat", "s2", "deconv", "k1_288", "cy1", "cell0", "cell4", "stem"])
 def test_conv_bwd_weight(ctx, case):
     from aarmvsnet_b200.backward import _seg
@@ -239,10 +279,12 @@ def test_lstm_gates_and_maxpool_backward(ctx):
     plane = torch.tensor([2], dtype=torch.int32).to(dev)
     dc2 = dcn.float().to(dev).clone()
     dg2 = torch.empty(P, 4 * Ch, device=dev)
+    mbits = torch.zeros(1, dtype=torch.int32, device=dev)
     capi.check(bw.lib.aarmvs_lstm_gates_bwd_act(_ptr(slot), 0, _ptr(plane), _ptr(t_cp), _ptr(t_cn), _ptr(t_dh), _ptr(dc2), _ptr(dg2), P, Ch,
-                                                bw._st()), "lstm act")
+                                                _ptr(mbits), bw._st()), "lstm act")
     _close(dg2.cpu(), wg, 5e-5, "lstm dgates (stored activations)")
     _close(dc2.cpu(), wc, 5e-5, "lstm dc_prev (stored activations)")
+    assert mbits.view(torch.float32).item() == dg2.abs().max().item()         # the scale of the tensor-core data gradient
     # max pool
     H, W, C = 12, 20, 16
     x = torch.randn(C, H, W, generator=g, dtype=torch.float64).requires_grad_(True)
