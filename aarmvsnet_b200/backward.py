@@ -156,6 +156,9 @@ class Backward:
         # the same as scaled fp16 (hi, lo) operand planes for the tensor-core data gradient, and the scale's inverse
         b["dgplanes"] = [torch.empty(2, 4 * _HID[i] // 8, Pi[i], 8, device=dev, dtype=torch.float16) for i in range(5)]
         b["ginv"] = torch.ones(5, **f32)
+        # ... and the cells' inputs [x | h_{d-1}] as operand planes for the tensor-core weight gradient
+        cxs = (48, 32, 32, 48, 40)
+        b["xplanes"] = [torch.empty(2, cxs[i] // 8, Pi[i], 8, device=dev, dtype=torch.float16) for i in range(5)]
         b["dh"] = [torch.zeros(Pi[i], _HID[i], **f32) for i in range(5)]
         b["dc"] = [torch.zeros(Pi[i], _HID[i], **f32) for i in range(5)]
         b["dcost"] = torch.empty(P, 32, **f32)
@@ -354,22 +357,35 @@ class Backward:
         def cell_bwd(i, outs):
             # at plane 0 the staged previous state is the zero record: c_prev = h_prev = 0 (module.py:94-96)
             tc = self.dx_math == "tc"
+            xs = xin[i] + [_seg(hp[i], _HID[i])]
+            ph, pw = hw[i]
             capi.check(lib.aarmvs_lstm_gates_bwd_act(_ptr(b["gates_pp"], i), 0, dptr, _ptr(cp[i]), _ptr(c[i]), _ptr(dh[i]), _ptr(dc[i]),
-                                                     _ptr(b["dgates"][i]), hw[i][0] * hw[i][1], _HID[i],
-                                                     _ptr(b["gmax"], i) if tc else None, st), "aarmvs_lstm_gates_bwd_act")
-            on_side(lambda: self.wgrad(xin[i] + [_seg(hp[i], _HID[i])], hw[i][0], hw[i][1], b["dgates"][i], hw[i][0], hw[i][1],
-                                       4 * _HID[i], 3, 1, g[f"cell{i}.w"], g[f"cell{i}.b"]))
+                                                     _ptr(b["dgates"][i]), ph * pw, _HID[i], _ptr(b["gmax"], i) if tc else None,
+                                                     _ptr(g[f"cell{i}.b"]) if tc else None, st), "aarmvs_lstm_gates_bwd_act")
             # dL/dh_i^{d-1} replaces dh[i]: every contribution to dL/dh_i^d precedes this point of the plane, the ones of plane
             # d-1 (skip connections, pooling, deconvolutions, the head) accumulate onto it in the next replay
             outs = outs + [_seg(dh[i], _HID[i])]
-            if tc:       # tensor cores: the gate gradients as scaled fp16 (hi, lo) operand planes through the forward cell's GEMM
-                capi.check(lib.aarmvs_split_planes_scaled(_ptr(b["dgates"][i]), hw[i][0], hw[i][1], 4 * _HID[i], _ptr(b["gmax"], i),
-                                                          _ptr(b["dgplanes"][i]), _ptr(b["ginv"], i), st), "aarmvs_split_planes_scaled")
-                capi.check(lib.aarmvs_conv_dx_tc(_ptr(b["dgplanes"][i]), hw[i][0], hw[i][1], 4 * _HID[i], _segs(*outs), len(outs),
-                                                 sum(o.channels for o in outs), _ptr(bw[f"cell{i}.dxtc"]), _ptr(b["ginv"], i), st),
-                           "aarmvs_conv_dx_tc")
-            else:
-                self.conv([_seg(b["dgates"][i], 4 * _HID[i])], hw[i][0], hw[i][1], outs, hw[i][0], hw[i][1], 3, 1, True, bw[f"cell{i}.wT"])
+            if not tc:   # fp32 FMA kernels (tests, A/B measurements)
+                on_side(lambda: self.wgrad(xs, ph, pw, b["dgates"][i], ph, pw, 4 * _HID[i], 3, 1, g[f"cell{i}.w"], g[f"cell{i}.b"]))
+                self.conv([_seg(b["dgates"][i], 4 * _HID[i])], ph, pw, outs, ph, pw, 3, 1, True, bw[f"cell{i}.wT"])
+                return
+            # tensor cores: the gate gradients as scaled fp16 (hi, lo) operand planes -- the A operand of the data gradient (the
+            # forward cell's implicit GEMM with the transposed weights) and, read as an MN-major operand, the B operand of the
+            # weight gradient (K = pixels; its A operand: the cell's inputs [x | h_{d-1}] as planes).  The bias gradient came
+            # from the gate kernel.
+            capi.check(lib.aarmvs_split_planes_scaled(_ptr(b["dgates"][i]), ph, pw, 4 * _HID[i], _ptr(b["gmax"], i), _ptr(b["dgplanes"][i]),
+                                                      _ptr(b["ginv"], i), st), "aarmvs_split_planes_scaled")
+
+            def dw_tc():
+                sst = self._st()
+                capi.check(lib.aarmvs_split_planes_cat(_segs(*xs), len(xs), ph, pw, _ptr(b["xplanes"][i]), sst), "aarmvs_split_planes_cat")
+                capi.check(lib.aarmvs_conv_dw_tc(_ptr(b["xplanes"][i]), _ptr(b["dgplanes"][i]), ph, pw, sum(x.channels for x in xs),
+                                                 4 * _HID[i], _ptr(b["ginv"], i), _ptr(g[f"cell{i}.w"]), sst), "aarmvs_conv_dw_tc")
+
+            on_side(dw_tc)
+            capi.check(lib.aarmvs_conv_dx_tc(_ptr(b["dgplanes"][i]), ph, pw, 4 * _HID[i], _segs(*outs), len(outs),
+                                             sum(o.channels for o in outs), _ptr(bw[f"cell{i}.dxtc"]), _ptr(b["ginv"], i), st),
+                       "aarmvs_conv_dx_tc")
 
         def up_bwd(i, hin, win, src_h, dh_target):
             pp = 4 * hin * win

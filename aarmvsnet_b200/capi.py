@@ -91,7 +91,9 @@ PROTOTYPES = {
     "aarmvs_gn_relu_apply": (_I, [_P, _SZ, _I, _I, _P, _P, _P, _I, _P, _P]),
     "aarmvs_gn_relu_bwd": (_I, [_I, _P, _P, _SZ, _I, _I, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P]),
     "aarmvs_lstm_gates_bwd": (_I, [_P, _P, _P, _P, _P, _P, _SZ, _I, _P]),
-    "aarmvs_lstm_gates_bwd_act": (_I, [_P, _I, _P, _P, _P, _P, _P, _P, _SZ, _I, _P, _P]),
+    "aarmvs_lstm_gates_bwd_act": (_I, [_P, _I, _P, _P, _P, _P, _P, _P, _SZ, _I, _P, _P, _P]),
+    "aarmvs_split_planes_cat": (_I, [_SEGP, _I, _I, _I, _P, _P]),
+    "aarmvs_conv_dw_tc": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P]),
     "aarmvs_split_planes_scaled": (_I, [_P, _I, _I, _I, _P, _P, _P, _P]),
     "aarmvs_conv_dx_tc": (_I, [_P, _I, _I, _I, _SEGP, _I, _I, _P, _P, _P]),
     "aarmvs_maxpool2": (_I, [_P, _I, _I, _I, _P, _P]),

@@ -723,10 +723,13 @@ __global__ void __launch_bounds__(256) lstm_gates_bwd_kernel(const float* __rest
 __global__ void __launch_bounds__(256) lstm_gates_bwd_act_kernel(const float* const* __restrict__ hist, int d_host, const int* __restrict__ d_dev,
                                                                  const float* __restrict__ c_prev, const float* __restrict__ c_new,
                                                                  const float* __restrict__ dh, float* __restrict__ dc,
-                                                                 float* __restrict__ dgates, size_t P, int Ch, unsigned* __restrict__ max_bits) {
+                                                                 float* __restrict__ dgates, size_t P, int Ch, unsigned* __restrict__ max_bits,
+                                                                 float* __restrict__ dbias) {
+    __shared__ float red[4][256];
     const float* gates = *hist + (size_t)plane_index(d_host, d_dev) * P * 4 * Ch;
     const size_t n = P * (size_t)Ch;
     float mx = 0.f;
+    float sb[4] = {0.f, 0.f, 0.f, 0.f};      // this thread's channel is fixed (256 % Ch == 0): sums of its four gates' gradients
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         const size_t p = i / Ch;
         const int c = (int)(i - p * Ch);
@@ -744,6 +747,18 @@ __global__ void __launch_bounds__(256) lstm_gates_bwd_act_kernel(const float* co
         dg[3 * Ch + c] = d3;
         dc[i] = dct * gf;
         mx = fmaxf(fmaxf(mx, fmaxf(fabsf(d0), fabsf(d1))), fmaxf(fabsf(d2), fabsf(d3)));
+        sb[0] += d0; sb[1] += d1; sb[2] += d2; sb[3] += d3;
+    }
+    if (dbias) {                              // the conv's bias gradient: sum over the pixels (the tensor-core dW has no bias term)
+#pragma unroll
+        for (int g = 0; g < 4; ++g) red[g][threadIdx.x] = sb[g];
+        __syncthreads();
+        if ((int)threadIdx.x < 4 * Ch) {
+            const int g = threadIdx.x / Ch, c = threadIdx.x - g * Ch;
+            float t = 0.f;
+            for (int j = c; j < 256; j += Ch) t += red[g][j];
+            atomicAdd(dbias + g * Ch + c, t);
+        }
     }
     if (max_bits) {
 #pragma unroll
@@ -905,10 +920,11 @@ extern "C" int aarmvs_lstm_gates_bwd(const float* gates, const float* c_prev, co
 }
 
 extern "C" int aarmvs_lstm_gates_bwd_act(const float* const* gates_history, int d_host, const int* d_dev, const float* c_prev, const float* c_new,
-                                         const float* dh, float* dc, float* dgates, size_t P, int hidden, unsigned* max_bits, void* stream) {
-    AARMVS_CHECK_ARG(gates_history && c_prev && c_new && dh && dc && dgates && P > 0 && hidden > 0);
+                                         const float* dh, float* dc, float* dgates, size_t P, int hidden, unsigned* max_bits,
+                                         float* dbias, void* stream) {
+    AARMVS_CHECK_ARG(gates_history && c_prev && c_new && dh && dc && dgates && P > 0 && hidden > 0 && 256 % hidden == 0 && hidden <= 64);
     lstm_gates_bwd_act_kernel<<<grid_for(P * hidden, 256), 256, 0, (cudaStream_t)stream>>>(gates_history, d_host, d_dev, c_prev, c_new, dh,
-                                                                                           dc, dgates, P, hidden, max_bits);
+                                                                                           dc, dgates, P, hidden, max_bits, dbias);
     AARMVS_LAUNCH_RESULT();
 }
 

@@ -23,7 +23,7 @@ extern "C" {
 #define AARMVS_MAX_SRC_VIEWS 15
 #define AARMVS_MAX_PLANES_PER_CALL 16
 
-int aarmvs_version(void);          /* ABI version, currently 5 (5: aarmvs_convlstm_cell_tc gained gates_out; aarmvs_lstm_gates_bwd_act, aarmvs_conv_dx_tc, aarmvs_split_planes_scaled) */
+int aarmvs_version(void);          /* ABI version, currently 5 (5: aarmvs_convlstm_cell_tc gained gates_out; aarmvs_lstm_gates_bwd_act, aarmvs_conv_dx_tc, aarmvs_conv_dw_tc, aarmvs_split_planes_scaled / _cat) */
 int aarmvs_sm_count(void);         /* multiprocessors of the current device (148 on B200), <0 on error */
 
 /* ---------------------------------------------------------------------------------------------------------
@@ -328,9 +328,10 @@ int aarmvs_lstm_gates_bwd(const float* gates, const float* c_prev, const float* 
  * memory) is the base of [planes][P][4*hidden]; record d = *d_dev if d_dev is non-null (one captured graph serves every plane
  * and sample), else d_host.
  * max_bits: optional; receives max |dgates| as the bit pattern of a float (atomicMax on a zeroed word), the scale of
- * aarmvs_split_planes_scaled. */
+ * aarmvs_split_planes_scaled.  dbias: optional [4*hidden], += sum_p dgates (the cell conv's bias gradient). */
 int aarmvs_lstm_gates_bwd_act(const float* const* gates_history, int d_host, const int* d_dev, const float* c_prev, const float* c_new,
-                              const float* dh, float* dc, float* dgates, size_t P, int hidden, unsigned* max_bits, void* stream);
+                              const float* dh, float* dc, float* dgates, size_t P, int hidden, unsigned* max_bits, float* dbias,
+                              void* stream);
 
 /* The cells' data gradient dX = dG (*) W^T on the tensor cores (csrc/conv_dx_tc.cu): the forward cell's TMA-fed tcgen05
  * implicit GEMM with the gate gradients as operand planes.
@@ -344,6 +345,15 @@ int aarmvs_lstm_gates_bwd_act(const float* const* gates_history, int d_host, con
  * Supported (cin, cout): (64,48) (64,32) (32,40). */
 int aarmvs_split_planes_scaled(const float* x, int H, int W, int channels, const unsigned* max_bits, void* planes,
                                float* inv_scale, void* stream);
+/* The cells' weight gradient dW[tap][ci][co] += 2^-k sum_p X[p + tap][ci] * dG[p][co] on the tensor cores
+ * (csrc/conv_dw_tc.cu): a K = pixels GEMM over the same operand planes read as MN-major operands, accumulated in TMEM over
+ * all tiles of a CTA.  x_planes: [2][cx/8][H][W][8], the channel concat [x | h_{d-1}] of the cell's inputs
+ * (aarmvs_split_planes_cat: up to three fp32 [H][W][ch] maps, channels multiples of 8, unscaled);
+ * dgate_planes / inv_scale: aarmvs_split_planes_scaled's.  dweight: [9][cx][cy] fp32, accumulated with atomics.
+ * Supported (cx, cy): (48,64) (32,64) (40,32).  The bias gradient is aarmvs_lstm_gates_bwd_act's dbias. */
+int aarmvs_split_planes_cat(const aarmvs_seg* x, int nx, int H, int W, void* planes, void* stream);
+int aarmvs_conv_dw_tc(const void* x_planes, const void* dgate_planes, int H, int W, int cx, int cy, const float* inv_scale,
+                      float* dweight, void* stream);
 int aarmvs_conv_dx_tc(const void* dgate_planes, int H, int W, int cin, const aarmvs_seg* out, int nout, int cout,
                       const void* weight_f16, const float* inv_scale, void* stream);
 

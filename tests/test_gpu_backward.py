@@ -173,6 +173,46 @@ def test_cell_data_gradient_tensor_cores(ctx, cin, cout, splits, H, W, magnitude
     _close(_nchw(got, H, W).cpu(), want, 1e-5, f"dx tc {cin}->{cout}")
 
 
+@pytest.mark.parametrize("splits,cy", [((32, 16), 64), ((16, 16), 64), ((16, 16, 16), 64), ((16, 16, 8), 32)])
+@pytest.mark.parametrize("H,W,magnitude", [(20, 24, 1.0), (40, 72, 3e-7), (128, 160, 1e-3)])
+def test_cell_weight_gradient_tensor_cores(ctx, splits, cy, H, W, magnitude):
+    """aarmvs_split_planes_cat + aarmvs_conv_dw_tc (a K = pixels tcgen05 GEMM over the operand planes read as MN-major
+    operands, accumulated in TMEM over all tiles of a CTA) against autograd in fp64; accumulates onto a non-zero dW."""
+    from aarmvsnet_b200 import capi
+    from aarmvsnet_b200.backward import _seg, _segs
+    from aarmvsnet_b200.engine import _ptr
+    _, bw = ctx
+    g = torch.Generator().manual_seed(41)
+    dev = "cuda"
+    r = lambda *s: torch.randn(*s, generator=g, dtype=torch.float64)
+    cx = sum(splits)
+    x = r(cx, H, W)
+    wt = r(cy, cx, 3, 3).requires_grad_(True)
+    y = F.conv2d(x[None], wt, None, padding=1)[0]
+    dy = r(*y.shape) * magnitude
+    dy[:, ::3, ::5] *= 2.0 ** -20
+    (want,) = torch.autograd.grad(y, wt, dy)                                               # [cy][cx][3][3]
+    xs = _nhwc(x).float().to(dev)
+    parts, o = [], 0
+    for c in splits:
+        parts.append(xs[:, o:o + c].contiguous())
+        o += c
+    xplanes = torch.empty(2, cx // 8, H * W, 8, device=dev, dtype=torch.float16)
+    segs = [_seg(t, c) for t, c in zip(parts, splits)]
+    capi.check(bw.lib.aarmvs_split_planes_cat(_segs(*segs), len(segs), H, W, _ptr(xplanes), bw._st()), "split cat")
+    dys = _nhwc(dy).float().to(dev)
+    mbits = dys.abs().max().reshape(1).view(torch.int32).clone()
+    gplanes = torch.empty(2, cy // 8, H * W, 8, device=dev, dtype=torch.float16)
+    inv = torch.zeros(1, device=dev)
+    capi.check(bw.lib.aarmvs_split_planes_scaled(_ptr(dys), H, W, cy, _ptr(mbits), _ptr(gplanes), _ptr(inv), bw._st()), "split")
+    start = magnitude * 0.5
+    dw = torch.full((9, cx, cy), start, device=dev)
+    capi.check(bw.lib.aarmvs_conv_dw_tc(_ptr(xplanes), _ptr(gplanes), H, W, cx, cy, _ptr(inv), _ptr(dw), bw._st()), "dw tc")
+    torch.cuda.synchronize()
+    got = (dw.double() - start).reshape(3, 3, cx, cy).permute(3, 2, 0, 1)
+    _close(got.cpu(), want, 1e-5, f"dW tc {cx}->{cy}")
+
+
 @pytest.mark.parametrize("case", ["s1_concat", "s2", "deconv", "k1_288", "cy1", "cell0", "cell4", "stem"])
 def test_conv_bwd_weight(ctx, case):
     from aarmvsnet_b200.backward import _seg
@@ -280,11 +320,14 @@ def test_lstm_gates_and_maxpool_backward(ctx):
     dc2 = dcn.float().to(dev).clone()
     dg2 = torch.empty(P, 4 * Ch, device=dev)
     mbits = torch.zeros(1, dtype=torch.int32, device=dev)
+    dbias = torch.zeros(4 * Ch, device=dev)
     capi.check(bw.lib.aarmvs_lstm_gates_bwd_act(_ptr(slot), 0, _ptr(plane), _ptr(t_cp), _ptr(t_cn), _ptr(t_dh), _ptr(dc2), _ptr(dg2), P, Ch,
-                                                _ptr(mbits), bw._st()), "lstm act")
+                                                _ptr(mbits), _ptr(dbias), bw._st()), "lstm act")
     _close(dg2.cpu(), wg, 5e-5, "lstm dgates (stored activations)")
     _close(dc2.cpu(), wc, 5e-5, "lstm dc_prev (stored activations)")
     assert mbits.view(torch.float32).item() == dg2.abs().max().item()         # the scale of the tensor-core data gradient
+    err_b = (dbias.cpu().double() - wg.sum(0)).abs().max().item()             # (cancelling sum: against the summands' scale)
+    assert err_b <= 2e-7 * wg.abs().sum(0).max().item(), f"sum_p dgates (the cell conv's bias gradient): {err_b:.2e}"
     # max pool
     H, W, C = 12, 20, 16
     x = torch.randn(C, H, W, generator=g, dtype=torch.float64).requires_grad_(True)
