@@ -1,5 +1,6 @@
 // Backward pass of the path, part 1: the dense primitives (BASELINE config 5; train.py:288-307 `loss.backward()` through
-// models/drmvsnet.py:272-295).  Everything here is fp32 on NHWC tensors, CUDA-core FMA:
+// models/drmvsnet.py:272-295).  Everything here is fp32 on NHWC tensors, CUDA-core FMA (the cells' data and weight gradients
+// run on the tensor cores: conv_dx_tc.cu, conv_dw_tc.cu; conv_dx3_kernel / conv_wgrad3_kernel below are their fp32 fallbacks):
 //
 //   conv_nhwc_kernel      direct convolution / transposed convolution over a channel CONCAT of inputs, writing (or adding
 //                         to) a channel SPLIT of outputs.  One kernel covers the data gradients dX = dY (*) W^T of the small
@@ -14,8 +15,7 @@
 //   maxpool2 / _bwd       drmvsnet.py:148,152; the gradient goes to the first maximum of the window in scan order (ATen).
 //
 // The training shape is small (128 x 160 feature maps, B = 4, D = 192: SURVEY.md §8d cfg5), so the backward keeps whole
-// fp32 activations in HBM and is bound by launch count and FMA issue, not by the tensor pipe; the inference path's tcgen05
-// kernels are untouched.
+// fp32 activations in HBM and is bound by the ~60 dependent launches of a plane, not by the tensor pipe or HBM.
 #include <type_traits>
 
 #include "common.cuh"

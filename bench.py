@@ -580,13 +580,13 @@ def run_train(args):
                 "e2e": {"value": world * c["B"] * args.steps / (ms_e2e * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": h2d,
                         "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": args.steps * (launches_fwd + launches_bwd + 1),
-                "roofline": {"kernel": "whole step (the backward's kernels are fp32 CUDA-core FMA, ~50 launches per plane and sample)",
+                "roofline": {"kernel": "whole step (cells' forward, data and weight gradients on tcgen05; ~60 launches per plane and sample in the backward)",
                              "bound": "tensor", "achieved": ach, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
                              "frac": ach / pk["bf16_tflops_sustained"], "traffic": None,
                              "algorithmic_flops_per_step": flops,
-                             "note": "useful recurrence FLOPs (forward 1x + backward 2x) over the step time; the backward is ~50 short fp32 "
-                                     "kernels per plane and sample (issue-bound FMA code and launch latency), not bound by the "
-                                     "tensor pipe or HBM"},
+                             "note": "useful recurrence FLOPs (forward 1x + backward 2x) over the step time; the backward is ~60 short "
+                                     "dependent kernels per plane and sample on 20 480-pixel maps (launch latency), not bound by "
+                                     "the tensor pipe or HBM"},
                 "phases_ms": phases, "loss_first_last": [float(losses[0]), float(losses[-1])], "cpu_baseline": cpu}
         print(json.dumps(line))
     if world > 1:
