@@ -28,7 +28,7 @@ constexpr int CHUNK_BYTES = NPX * 16;
 static_assert(HR == planemap::BOX_ROWS && HC == planemap::BOX_COLS, "the tensor-map box is the staged halo tile");
 constexpr int N_EPI_WARPS = 16, MMA_WARP = N_EPI_WARPS, TMA_WARP = MMA_WARP + 1;
 constexpr int N_THREADS = (N_EPI_WARPS + 2) * 32;                             // 576
-constexpr int DW_GROUPS = 16;
+constexpr int DW_GROUPS = 8;          // measured at cfg5: 4..8 groups 213 ms per step, 16: 217, 32: 228
 
 struct alignas(64) DwArgs {
     CUtensorMap xmap, gmap;     // X and gate-gradient operand planes, box (80, 18, chunks, 1, 1)
