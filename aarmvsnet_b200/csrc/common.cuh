@@ -30,6 +30,15 @@ static inline cudaError_t ensure_dyn_smem(K kern, int bytes, unsigned long long&
     return e;
 }
 
+// Grid of a persistent kernel with balanced rounds: the fewest CTAs that still finish in ceil(tiles / sms) rounds.  160 tiles on
+// 148 SMs: 80 CTAs x 2 tiles instead of 148 CTAs of which 12 take two -- the same latency on half the SMs, which the concurrent
+// streams of a training step use; large maps (thousands of tiles) keep one CTA per SM.
+static inline int balanced_grid(int tiles, int sms) {
+    if (tiles <= sms) return tiles;
+    const int rounds = (tiles + sms - 1) / sms;
+    return (tiles + rounds - 1) / rounds;
+}
+
 // 16-byte asynchronous global -> shared copy (no register round trip: a staging loop keeps all its loads in flight);
 // !pred writes 16 zero bytes instead (src is not read, but must be a valid address).
 __device__ __forceinline__ void cp_async16_zfill(float* smem_dst, const float* src, bool pred) {

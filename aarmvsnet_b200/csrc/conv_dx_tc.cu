@@ -209,7 +209,7 @@ int launch_dx(const DxArgs& a, cudaStream_t stream) {
     const int ntiles = ((a.W + TCOL - 1) / TCOL) * ((a.H + TR - 1) / TR);
     const int sms = aarmvs_sm_count();
     if (sms <= 0) return AARMVS_ERR_ARG;
-    kern<<<ntiles < sms ? ntiles : sms, N_THREADS, C::SMEM, stream>>>(a);
+    kern<<<balanced_grid(ntiles, sms), N_THREADS, C::SMEM, stream>>>(a);
     AARMVS_LAUNCH_RESULT();
 }
 

@@ -430,7 +430,7 @@ int launch_cell_as(const CellArgs& a, cudaStream_t stream) {
     const int ntiles = ((a.W + TCOL - 1) / TCOL) * ((a.H + TR - 1) / TR);
     const int sms = aarmvs_sm_count();
     if (sms <= 0) return AARMVS_ERR_ARG;
-    if (cudaError_t e = launch_pdl(kern, dim3(ntiles < sms ? ntiles : sms), dim3(N_THREADS), C::SMEM, stream, a)) return (int)e;
+    if (cudaError_t e = launch_pdl(kern, dim3(balanced_grid(ntiles, sms)), dim3(N_THREADS), C::SMEM, stream, a)) return (int)e;
     AARMVS_LAUNCH_RESULT();
 }
 

@@ -232,7 +232,7 @@ extern "C" int aarmvs_deconv2x_tc(const aarmvs_plane_src* in, int Hin, int Win, 
     const int ntiles = ((Win + TCOL - 1) / TCOL) * ((Hin + TR - 1) / TR);
     const int sms = aarmvs_sm_count();
     if (sms <= 0) return AARMVS_ERR_ARG;
-    if (cudaError_t e = launch_pdl(deconv_tc_kernel, dim3(ntiles < sms ? ntiles : sms), dim3(N_THREADS), SMEM, (cudaStream_t)stream, a))
+    if (cudaError_t e = launch_pdl(deconv_tc_kernel, dim3(balanced_grid(ntiles, sms)), dim3(N_THREADS), SMEM, (cudaStream_t)stream, a))
         return (int)e;
     AARMVS_LAUNCH_RESULT();
 }
