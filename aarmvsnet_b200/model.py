@@ -129,7 +129,7 @@ class _RegularisedCostVolume(torch.autograd.Function):
     def backward(ctx, dcost):
         from .backward import Backward
         model, saved = ctx.model, ctx.saved
-        bwd = Backward(model._engine, dcost.device)
+        bwd = Backward(model._engine, dcost.device, dx_math=getattr(model, "backward_math", "tc"))
         with torch.cuda.device(dcost.device):
             bwd.batch(saved, dcost.reshape(len(saved), saved[0]["D"], -1).to(torch.float32).contiguous())
         grads = bwd.parameter_gradients()

@@ -503,15 +503,18 @@ def test_deform_conv_and_assemble_backward(ctx, sd_dtu):
 
 
 # ------------------------------------------------------------------------------------------------ the whole training step
-def test_training_step_gradients_match_reference():
+@pytest.mark.parametrize("backward_math", ["tc", "fma"])
+def test_training_step_gradients_match_reference(backward_math):
     """train.py:288-300 on the train fixture: prob = model(...); loss = mvsnet_cls_loss(prob, ...); loss.backward() -- all 90
-    parameter gradients against the ones the UNMODIFIED reference computed (2e-4 of each tensor's largest gradient)."""
+    parameter gradients against the ones the UNMODIFIED reference computed (2e-4 of each tensor's largest gradient); with the
+    cells' data / weight gradients on the tensor cores (the product path) and on the fp32 fallback kernels."""
     import aarmvsnet_b200 as aa
     t = load_golden("train_32x40_n3_d6.pt")
     gold = load_golden("train_grads_32x40_n3_d6.pt")
     m = aa.EMVSNet(disparity_level=32, image_scale=1.0, max_h=32, max_w=40, return_depth=False)
     m.load_state_dict(load_weights(t["ckpt"]), strict=True)
     m = m.cuda().train()
+    m.backward_math = backward_math
     prob, _, _ = m(t["imgs"].cuda(), t["proj_matrices"].cuda(), t["depth_values"].cuda())
     assert prob.requires_grad
     loss, _ = aa.mvsnet_cls_loss(prob, t["depth_gt"].cuda(), t["mask"].cuda(), t["depth_values"].cuda())
@@ -533,7 +536,7 @@ def test_training_step_gradients_match_reference():
         worst = max(worst, rel)
         if rel > 2e-4:
             bad.append(f"{name}: {rel:.2e} (max |ref| {scale:.2e})")
-    print(f"90 parameter gradients: worst max-error / max-gradient = {worst:.2e}")
+    print(f"90 parameter gradients ({backward_math}): worst max-error / max-gradient = {worst:.2e}")
     assert not bad, "\n".join(bad)
 
 
