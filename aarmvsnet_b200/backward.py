@@ -61,9 +61,9 @@ class Backward:
         # slot -> workspace and stream, one per concurrently running sample (see batch()).  They live on the engine and survive
         # the optimisation step (this object does not: the weights it packs change every step), so that the caching allocator's
         # per-stream pools are reused; only the captured graphs are per step (they bake the packed weights' addresses).
-        if not hasattr(engine, "_bwd_wss"):
-            engine._bwd_wss, engine._bwd_streams = {}, []
-        self._wss, self._streams = engine._bwd_wss, engine._bwd_streams
+        if not hasattr(engine, "_bwd_state"):
+            engine._bwd_state = {}                      # per device: (workspaces by slot, streams)
+        self._wss, self._streams = engine._bwd_state.setdefault(str(device), ({}, []))
         for ws in self._wss.values():
             ws["graph"] = None
         self.chan = torch.zeros(128, device=device, dtype=torch.float64)      # per-channel sums of one GroupNorm backward

@@ -567,26 +567,37 @@ static int launch_dx3(const DXArgs& a, cudaStream_t stream) {
 
 // ------------------------------------------------------------------------------------------------ GroupNorm
 // x [P][C]; group g = channels [g * C / groups, (g + 1) * C / groups) over all P pixels; sums = fp64 (sum, sum of squares).
+// 256 % C == 0 (every layer of the path): a thread keeps its channel over the grid-stride loop, partial sums are combined per
+// channel through shared memory (no shared-memory fp64 atomics: those are CAS loops) and leave as 2 * groups atomics per block.
 __global__ void __launch_bounds__(256) gn_sums_kernel(const float* __restrict__ x, size_t n /* P * C */, int C, int groups,
                                                       double* __restrict__ sums) {
-    __shared__ double sh[8 * 2];       // up to 8 groups
-    if (threadIdx.x < 16) sh[threadIdx.x] = 0.0;
-    __syncthreads();
+    __shared__ double rs[256], rq[256];
     const int gch = C / groups;
-    double s[8] = {}, q[8] = {};
+    double s = 0.0, q = 0.0;
+    float fs = 0.f, fq = 0.f;
+    int it = 0;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        const int g = (int)(i % C) / gch;
-        const double v = (double)x[i];
-#pragma unroll
-        for (int k = 0; k < 8; ++k)
-            if (k == g) { s[k] += v; q[k] += v * v; }
+        const float v = x[i];
+        fs += v;
+        fq = fmaf(v, v, fq);
+        if (++it == 8) { s += fs; q += fq; fs = fq = 0.f; it = 0; }
     }
-    for (int k = 0; k < groups; ++k) {
-        const double a = warp_sum(s[k]), b = warp_sum(q[k]);
-        if ((threadIdx.x & 31) == 0) { atomicAdd(&sh[k * 2], a); atomicAdd(&sh[k * 2 + 1], b); }
+    rs[threadIdx.x] = s + fs;
+    rq[threadIdx.x] = q + fq;
+    __syncthreads();
+    if ((int)threadIdx.x < C) {                      // channel totals of the block (thread j held channel j % C)
+        double a = 0.0, b = 0.0;
+        for (int j = threadIdx.x; j < 256; j += C) { a += rs[j]; b += rq[j]; }
+        rs[threadIdx.x] = a;
+        rq[threadIdx.x] = b;
     }
     __syncthreads();
-    if (threadIdx.x < groups * 2) atomicAdd(sums + threadIdx.x, sh[threadIdx.x]);
+    if ((int)threadIdx.x < groups) {
+        double a = 0.0, b = 0.0;
+        for (int c = threadIdx.x * gch; c < (threadIdx.x + 1) * gch; ++c) { a += rs[c]; b += rq[c]; }
+        atomicAdd(sums + threadIdx.x * 2, a);
+        atomicAdd(sums + threadIdx.x * 2 + 1, b);
+    }
 }
 
 __global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__ x, size_t n, int C, int groups, size_t P,
@@ -630,7 +641,7 @@ struct GnBwdArgs {
 template <int STAGE>
 __global__ void __launch_bounds__(256) gn_bwd_kernel(const __grid_constant__ GnBwdArgs a) {
     __shared__ float s_mean[8], s_rstd[8], s_A[8], s_B[8];
-    __shared__ double s_acc[64 * 2];
+    __shared__ double r1[256], r2[256];
     const int C = a.C, gch = C / a.groups;
     const double M = (double)gch * (double)a.P;
     if (threadIdx.x < a.groups) {
@@ -648,7 +659,6 @@ __global__ void __launch_bounds__(256) gn_bwd_kernel(const __grid_constant__ GnB
             s_B[threadIdx.x] = (float)(B / M);
         }
     }
-    if (threadIdx.x < 2 * C) s_acc[threadIdx.x] = 0.0;
     __syncthreads();
     const size_t n = a.P * (size_t)C;
     // grid stride is a multiple of C (launcher), so a thread always meets the same channel
@@ -673,22 +683,26 @@ __global__ void __launch_bounds__(256) gn_bwd_kernel(const __grid_constant__ GnB
         if (++it == 16) { t1 += f1; t2 += f2; f1 = f2 = 0.f; it = 0; }
     }
     t1 += f1; t2 += f2;
-    if (STAGE == 1) {
-        atomicAdd(&s_acc[c * 2], t1);
-        atomicAdd(&s_acc[c * 2 + 1], t2);
+    // per-channel totals of the block through shared memory (thread j holds channel j % C), then one atomic per channel
+    if (STAGE == 1 || a.dx_chan_sum) {
+        r1[threadIdx.x] = t1;
+        r2[threadIdx.x] = t2;
         __syncthreads();
-        if (threadIdx.x < 2 * C) atomicAdd(a.chan_sums + threadIdx.x, s_acc[threadIdx.x]);
-    } else {
-        if (a.dx_chan_sum) {
-            atomicAdd(&s_acc[c * 2], t1);
-            __syncthreads();
-            if (threadIdx.x < C) atomicAdd(a.dx_chan_sum + threadIdx.x, (float)s_acc[threadIdx.x * 2]);
+        if ((int)threadIdx.x < C) {
+            double u = 0.0, v = 0.0;
+            for (int j = threadIdx.x; j < 256; j += C) { u += r1[j]; v += r2[j]; }
+            if (STAGE == 1) {
+                atomicAdd(a.chan_sums + threadIdx.x * 2, u);
+                atomicAdd(a.chan_sums + threadIdx.x * 2 + 1, v);
+            } else {
+                atomicAdd(a.dx_chan_sum + threadIdx.x, (float)u);
+            }
         }
-        if (blockIdx.x == 0 && threadIdx.x < C) {
-            // (atomics: the samples of a batch run their backward sweeps on concurrent streams into the same accumulators)
-            atomicAdd(a.dgamma + threadIdx.x, (float)a.chan_sums[threadIdx.x * 2]);
-            atomicAdd(a.dbeta + threadIdx.x, (float)a.chan_sums[threadIdx.x * 2 + 1]);
-        }
+    }
+    if (STAGE == 2 && blockIdx.x == 0 && (int)threadIdx.x < C) {
+        // (atomics: the samples of a batch run their backward sweeps on concurrent streams into the same accumulators)
+        atomicAdd(a.dgamma + threadIdx.x, (float)a.chan_sums[threadIdx.x * 2]);
+        atomicAdd(a.dbeta + threadIdx.x, (float)a.chan_sums[threadIdx.x * 2 + 1]);
     }
 }
 
@@ -801,6 +815,12 @@ __global__ void __launch_bounds__(256) maxpool2_bwd_kernel(const float* __restri
     }
 }
 
+// reductions that end in per-block atomics: two blocks per SM at most (a few elements per thread instead of one)
+static int reduce_grid(size_t n) {
+    const size_t b = (n + 255) / 256;
+    return (int)(b < 2 * 148 ? (b ? b : 1) : 2 * 148);
+}
+
 static int grid_for(size_t n, int threads) {
     size_t b = (n + threads - 1) / threads;
     const size_t cap = 148 * 16;
@@ -887,8 +907,8 @@ extern "C" int aarmvs_conv_bwd_weight(const aarmvs_seg* x, int nx, int Hx, int W
 }
 
 extern "C" int aarmvs_gn_sums(const float* x, size_t P, int C, int groups, double* sums, void* stream) {
-    AARMVS_CHECK_ARG(x && sums && P > 0 && C >= 1 && C <= 64 && groups >= 1 && groups <= 8 && C % groups == 0);
-    gn_sums_kernel<<<grid_for(P * C, 256), 256, 0, (cudaStream_t)stream>>>(x, P * C, C, groups, sums);
+    AARMVS_CHECK_ARG(x && sums && P > 0 && C >= 1 && C <= 64 && 256 % C == 0 && groups >= 1 && groups <= 8 && C % groups == 0);
+    gn_sums_kernel<<<reduce_grid(P * C), 256, 0, (cudaStream_t)stream>>>(x, P * C, C, groups, sums);
     AARMVS_LAUNCH_RESULT();
 }
 
@@ -906,7 +926,7 @@ extern "C" int aarmvs_gn_relu_bwd(int stage, const float* x, const float* dy, si
     AARMVS_CHECK_ARG(C >= 1 && C <= 64 && 256 % C == 0 && groups >= 1 && groups <= 8 && C % groups == 0);
     AARMVS_CHECK_ARG(stage == 1 || (dx && dgamma && dbeta));
     GnBwdArgs a = {x, dy, P, C, groups, relu, sums, gamma, beta, chan_sums, dx, dgamma, dbeta, dx_chan_sum};
-    const int grid = grid_for(P * C, 256);          // blockDim (256) is a multiple of C: every thread keeps its channel
+    const int grid = reduce_grid(P * C);            // blockDim (256) is a multiple of C: every thread keeps its channel
     if (stage == 1) gn_bwd_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(a);
     else gn_bwd_kernel<2><<<grid, 256, 0, (cudaStream_t)stream>>>(a);
     AARMVS_LAUNCH_RESULT();

@@ -499,6 +499,15 @@ class Engine:
             off += 2 * n
         return lay, off
 
+    def sweep_streams(self, device, n):
+        """n persistent streams of `device` for the concurrent plane sweeps of a training batch (forward_saving_state)."""
+        if not hasattr(self, "_sweep_streams"):
+            self._sweep_streams = {}
+        pool = self._sweep_streams.setdefault(str(device), [])
+        while len(pool) < n:
+            pool.append(torch.cuda.Stream(device))
+        return pool[:n]
+
     def forward_saving_state(self, imgs, proj_matrices, depth_values, slot=0, sweep_stream=None):
         """The training-phase forward of ONE sample (models/drmvsnet.py:272-287) on the tensor-core kernels (the same graph-replayed
         plane chain as inference, plus aarmvs_snapshot_state after every plane), keeping what the backward pass needs: the features

@@ -113,11 +113,8 @@ class _RegularisedCostVolume(torch.autograd.Function):
         B, _, _, H, W = imgs.shape
         # the samples' plane sweeps are independent, latency-bound chains: one stream and workspace per sample
         main = torch.cuda.current_stream(imgs.device)
-        if not hasattr(eng, "_fwd_streams"):
-            eng._fwd_streams = []
-        while len(eng._fwd_streams) < B:
-            eng._fwd_streams.append(torch.cuda.Stream(imgs.device))
-        streams = eng._fwd_streams[:B] if B > 1 else [None]
+        pool = eng.sweep_streams(imgs.device, B)
+        streams = pool if B > 1 else [None]
         saved = [eng.forward_saving_state(imgs[b], proj_matrices[b], depth_values[b], slot=b, sweep_stream=streams[b]) for b in range(B)]
         for st in streams:
             if st is not None:

@@ -308,7 +308,7 @@ int aarmvs_conv_bwd_weight(const aarmvs_seg* x, int nx, int Hx, int Wx, const fl
                            int ksize, int stride, float* dweight, float* dbias, void* stream);
 
 /* GroupNorm of x [P][C] (groups of C / groups channels over all P pixels; module.py:101,284): sums [groups][2] += (sum, sum
- * of squares);  y = [ReLU](gamma * (x - mean) * rstd + beta). */
+ * of squares);  y = [ReLU](gamma * (x - mean) * rstd + beta).  C divides 256 (4, 8, 16, 32, 64: every layer of the path). */
 int aarmvs_gn_sums(const float* x, size_t P, int C, int groups, double* sums, void* stream);
 int aarmvs_gn_relu_apply(const float* x, size_t P, int C, int groups, const double* sums, const float* gamma, const float* beta,
                          int relu, float* y, void* stream);

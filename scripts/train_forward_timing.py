@@ -26,13 +26,12 @@ mask = torch.ones(B, H, W, device="cuda")
 ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
 for rep in range(3):
     main = torch.cuda.current_stream()
-    while len(getattr(eng, "_fwd_streams", [])) < B:
-        eng._fwd_streams = getattr(eng, "_fwd_streams", []) + [torch.cuda.Stream()]
+    streams = eng.sweep_streams(imgs.device, B)
     torch.cuda.synchronize()
     ev[0].record()
-    saved = [eng.forward_saving_state(imgs[b], proj[b], dv[b], slot=b, sweep_stream=eng._fwd_streams[b]) for b in range(B)]
+    saved = [eng.forward_saving_state(imgs[b], proj[b], dv[b], slot=b, sweep_stream=streams[b]) for b in range(B)]
     ev[1].record()                                   # FeatNet of all samples done on the main stream
-    for st in eng._fwd_streams[:B]:
+    for st in streams:
         main.wait_stream(st)
     ev[2].record()
     cost = torch.stack([s["cost"].view(-1, H, W) for s in saved]).requires_grad_(True)
