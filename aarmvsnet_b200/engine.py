@@ -86,8 +86,12 @@ class Engine:
         key = (str(device),) + tuple((p.data_ptr(), p._version) for p in params)
         if key == self._wkey:
             return self.w
-        # re-pack on the HOST and upload each packed tensor once (a few dozen copies instead of ~1 000 tiny device kernels)
-        sd = {k: v.detach().to(device="cpu", dtype=torch.float32) for k, v in self.module.state_dict().items()}
+        # Inference: re-pack on the HOST and upload each packed tensor once (a few dozen copies instead of ~1 000 tiny device
+        # kernels in front of the first depth map).  Training re-packs after every optimizer step: there the tensors are packed
+        # on the device (no 90 device-to-host copies, no host arithmetic while the GPU idles) and only the few small layers
+        # whose parameters travel as kernel parameter banks are read back.
+        pack_dev = torch.device("cpu") if not self.module.training else device
+        sd = {k: v.detach().to(device=pack_dev, dtype=torch.float32) for k, v in self.module.state_dict().items()}
         w = {}
 
         def convgn(name, prefix, cin_pad=None):

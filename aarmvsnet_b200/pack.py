@@ -24,7 +24,7 @@ def lstm_gates(w, b):
     [k*k][cin][hidden*4] with channel order [hidden channel][i,f,o,g], and the bias likewise."""
     c4, cin, k, _ = w.shape
     hidden = c4 // 4
-    perm = torch.arange(c4).view(4, hidden).t().reshape(-1)      # new index hc*4+g <- old g*hidden+hc
+    perm = torch.arange(c4, device=w.device).view(4, hidden).t().reshape(-1)      # new index hc*4+g <- old g*hidden+hc
     return conv_taps(w[perm]), b[perm].contiguous()
 
 
