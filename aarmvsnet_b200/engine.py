@@ -549,9 +549,12 @@ class Engine:
                      # the activated gates of every plane, as the cells used them: [D][P_i][4 Ch_i] per cell; the kernels read
                      # the bases from device memory, so the captured plane graph serves every sample
                      "gates": [torch.empty(D, (H // sc) * (W // sc), 4 * ch, **f32) for ch, sc in zip(_HID, _SCALE)]}
-            depth_values = depth_values.to(torch.float32)
+            dv32 = depth_values.to(torch.float32)
             if sweep_stream is not None:
                 sweep_stream.wait_stream(main)
+                if dv32 is not depth_values:                 # a temporary of the calling stream, read on the sweep stream
+                    dv32.record_stream(sweep_stream)
+            depth_values = dv32
             with torch.cuda.stream(sweep_stream if sweep_stream is not None else main):
                 stream = ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
                 ws["cams"].copy_(cams_host, non_blocking=True)
