@@ -178,6 +178,7 @@ class Backward:
         b["cams"] = torch.empty(S, 12, **f32)
         b["depths"] = torch.empty(0, **f32)
         b["graph"] = None
+        b["fchan"] = torch.zeros(128, device=dev, dtype=torch.float64)      # GroupNorm-backward scratch of FeatNet's backward
         b["side"] = torch.cuda.Stream(dev)                                  # second branch of the plane (see _plane)
         b["stage_ready"] = torch.cuda.Event()
         self._wss[slot] = b
@@ -203,10 +204,11 @@ class Backward:
         capi.check(self.lib.aarmvs_gn_relu_apply(_ptr(x), P, C, groups, _ptr(sums), _ptr(gn[0]), _ptr(gn[1]), 1, _ptr(out), self._st()),
                    "aarmvs_gn_relu_apply")
 
-    def gn_bwd(self, x, dy, P, C, groups, sums, gn, dx, dgamma, dbeta, dbias=None, chan=None):
-        """chan: zeroed per-channel scratch of the caller (default: this object's, zeroed here)."""
+    def gn_bwd(self, x, dy, P, C, groups, sums, gn, dx, dgamma, dbeta, dbias=None, chan=None, zero=False):
+        """chan: per-channel fp64 scratch, zeroed by the caller unless `zero` (default: this object's, zeroed here)."""
         if chan is None:
-            chan = self.chan
+            chan, zero = self.chan, True
+        if zero:
             chan.zero_()
         for stage in (1, 2):
             capi.check(self.lib.aarmvs_gn_relu_bwd(stage, _ptr(x), _ptr(dy), P, C, groups, _ptr(sums), _ptr(gn[0]), _ptr(gn[1]), 1,
@@ -237,12 +239,15 @@ class Backward:
                 with torch.cuda.stream(st):
                     if next(sweep, "done") != "done":
                         alive = True
+        # FeatNet's backward (once per view; its forward is recomputed first) follows each sample's sweep on the sample's stream,
+        # with the sample's own FeatNet scratch: four chains of short kernels side by side instead of twelve views in a row
+        for i, (sv, st) in enumerate(zip(saved_list, streams)):
+            with torch.cuda.stream(st):
+                b = self._wss[i]
+                for v in range(sv["N"]):
+                    self.featnet(sv["imgs"][v], b["dfeat"][v], sv["H"], sv["W"], slot=i)
         for st in streams:
             main.wait_stream(st)
-        for i, sv in enumerate(saved_list):
-            b = self._wss[i]
-            for v in range(sv["N"]):
-                self.featnet(sv["imgs"][v], b["dfeat"][v], sv["H"], sv["W"])
 
     def sample(self, saved, dcost_volume):
         """One sample, on the calling stream: reverse sweep, then FeatNet's backward per view."""
@@ -425,14 +430,16 @@ class Backward:
         main.wait_stream(side)                                       # join: the plane's buffers are free for the next plane
 
     # ------------------------------------------------------------------------------------------ FeatNet of one view
-    def featnet(self, img, dfeat, H, W):
-        """img [3,H,W]; dfeat [P,32] = dL/d(feature map of this view)."""
+    def featnet(self, img, dfeat, H, W, slot=0):
+        """img [3,H,W]; dfeat [P,32] = dL/d(feature map of this view).  slot: which FeatNet scratch / reduction scratch to use
+        (concurrent samples)."""
         lib, eng, w, bw, g = self.lib, self.eng, self.w, self.bw, self.g
         st = self._st()
         dev = self.dev
         f32 = dict(device=dev, dtype=torch.float32)
         P = H * W
-        fs = eng._feat_scratch(H, W, dev)
+        fs = eng._feat_scratch(H, W, dev, slot)
+        chan = self._wss[slot]["fchan"] if slot in self._wss else self.chan
         scratch = torch.empty(P, 32, **f32)
         eng.feature_map(img, scratch, fs, w, st)               # recompute: raw activations + GroupNorm sums in fs
         sums = fs["fsums"]
@@ -459,14 +466,14 @@ class Backward:
             groups = max(1, ch // 8)
             # 1x1 head: GroupNorm+ReLU backward, then the conv
             self.gn_bwd(fs[f"m{l}"], dm[l], pl, ch, groups, sl(f"head{l}"), w[f"head{l}.gn"], dm[l], g[f"head{l}.gamma"], g[f"head{l}.beta"],
-                        g[f"head{l}.b"])
+                        g[f"head{l}.b"], chan=chan, zero=True)
             dcp = torch.empty(pl, 32, **f32)
             self.gn_apply(fs[f"dc{l}"], pl, 32, 4, sl(f"dc{l}"), w[f"dc{l}.gn"], dcp)
             ddc = torch.empty(pl, 32, **f32)
             self.conv([_seg(dm[l], ch)], hl, wl, [_seg(ddc, 32)], hl, wl, 1, 1, True, bw[f"head{l}.wT"])
             self.wgrad([_seg(dcp, 32)], hl, wl, dm[l], hl, wl, ch, 1, 1, g[f"head{l}.w"])
             # deformable conv: GroupNorm+ReLU backward, contraction backward, gather backward
-            self.gn_bwd(fs[f"dc{l}"], ddc, pl, 32, 4, sl(f"dc{l}"), w[f"dc{l}.gn"], ddc, g[f"dc{l}.gamma"], g[f"dc{l}.beta"], g[f"dc{l}.b"])
+            self.gn_bwd(fs[f"dc{l}"], ddc, pl, 32, 4, sl(f"dc{l}"), w[f"dc{l}.gn"], ddc, g[f"dc{l}.gamma"], g[f"dc{l}.beta"], g[f"dc{l}.b"], chan=chan, zero=True)
             samp, samp_m, dsamp_m = (torch.empty(pl, 288, **f32) for _ in range(3))
             capi.check(lib.aarmvs_deform_sample(_ptr(xp[l]), hl, wl, _ptr(fs[f"om{l}"]), _ptr(samp), _ptr(samp_m), st), "aarmvs_deform_sample")
             self.conv([_seg(ddc, 32)], hl, wl, [_seg(dsamp_m, 288)], hl, wl, 1, 1, False, bw[f"dc{l}.w288T"])
@@ -481,19 +488,19 @@ class Backward:
         for l in (2, 1):
             hl, wl = lv[l]
             self.gn_bwd(fs[f"x{l}"], dxp[l], hl * wl, 32, 4, sl(f"conv{l}"), w[f"conv{l}.gn"], dxp[l], g[f"conv{l}.gamma"], g[f"conv{l}.beta"],
-                        g[f"conv{l}.b"])
+                        g[f"conv{l}.b"], chan=chan, zero=True)
             hi, wi = lv[l - 1]
             self.conv([_seg(dxp[l], 32)], hl, wl, [_seg(dxp[l - 1], 32, 1)], hi, wi, 3, 2, True, bw[f"conv{l}.wT"])
             self.wgrad([_seg(xp[l - 1], 32)], hi, wi, dxp[l], hl, wl, 32, 3, 2, g[f"conv{l}.w"])
-        self.gn_bwd(fs["x0"], dxp[0], P, 32, 4, sl("conv0"), w["conv0.gn"], dxp[0], g["conv0.gamma"], g["conv0.beta"], g["conv0.b"])
+        self.gn_bwd(fs["x0"], dxp[0], P, 32, 4, sl("conv0"), w["conv0.gn"], dxp[0], g["conv0.gamma"], g["conv0.beta"], g["conv0.b"], chan=chan, zero=True)
         da2 = torch.empty(P, 16, **f32)
         self.conv([_seg(dxp[0], 32)], H, W, [_seg(da2, 16)], H, W, 3, 1, True, bw["conv0.wT"])
         self.wgrad([_seg(a2p, 16)], H, W, dxp[0], H, W, 32, 3, 1, g["conv0.w"])
-        self.gn_bwd(fs["a2"], da2, P, 16, 2, sl("init1"), w["init1.gn"], da2, g["init1.gamma"], g["init1.beta"], g["init1.b"])
+        self.gn_bwd(fs["a2"], da2, P, 16, 2, sl("init1"), w["init1.gn"], da2, g["init1.gamma"], g["init1.beta"], g["init1.b"], chan=chan, zero=True)
         da1 = torch.empty(P, 8, **f32)
         self.conv([_seg(da2, 16)], H, W, [_seg(da1, 8)], H, W, 3, 1, True, bw["init1.wT"])
         self.wgrad([_seg(a1p, 8)], H, W, da2, H, W, 16, 3, 1, g["init1.w"])
-        self.gn_bwd(fs["a1"], da1, P, 8, 1, sl("init0"), w["init0.gn"], da1, g["init0.gamma"], g["init0.beta"], g["init0.b"])
+        self.gn_bwd(fs["a1"], da1, P, 8, 1, sl("init0"), w["init0.gn"], da1, g["init0.gamma"], g["init0.beta"], g["init0.b"], chan=chan, zero=True)
         img4 = torch.zeros(P, 4, **f32)
         img4[:, :3] = img.reshape(3, P).t()
         self.wgrad([_seg(img4, 4)], H, W, da1, H, W, 8, 3, 1, g["init0.w"])

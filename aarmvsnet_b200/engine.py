@@ -226,17 +226,23 @@ class Engine:
         flat = torch.zeros((N * H * W + W + 1) * 32, device=device, dtype=torch.float32)
         return flat[: N * H * W * 32].view(N, H * W, 32)
 
-    def _feat_scratch(self, H, W, device):
-        """FeatNet scratch (reused for every view), separate from the sweep workspace so features() allocates only this."""
-        key = (H, W, str(device))
+    def _feat_scratch(self, H, W, device, slot=0):
+        """FeatNet scratch (reused for every view), separate from the sweep workspace so features() allocates only this.
+        slot: the samples of a training batch run FeatNet's backward (which recomputes its forward into this scratch) on
+        concurrent streams, each with its own copy; the slots of one shape count as one entry of the LRU."""
+        key = (H, W, str(device), slot)
         fs = self._fs.get(key)
         if fs is not None:
             self._fs.move_to_end(key)
             return fs
         if H % 4 or W % 4:
             raise RuntimeError(f"feature height and width must be multiples of 4, got {H}x{W} (models/drmvsnet.py:51-52, 148-160)")
-        while len(self._fs) >= self.MAX_WORKSPACES:
-            self._fs.popitem(last=False)
+        bases = {k[:-1] for k in self._fs}
+        while key[:-1] not in bases and len(bases) >= self.MAX_WORKSPACES:
+            oldest = next(iter(self._fs))[:-1]
+            for k in [k for k in self._fs if k[:-1] == oldest]:
+                del self._fs[k]
+            bases.discard(oldest)
         f32 = dict(device=device, dtype=torch.float32)
         P = H * W
         fs = {"H": H, "W": W, "a1": torch.empty(P, 8, **f32), "a2": torch.empty(P, 16, **f32)}
