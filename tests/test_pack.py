@@ -76,3 +76,27 @@ def test_deform_taps_layout():
                 _close(rec[t, s, c], w[:, c0:c0 + 8, ky, kx])
     # hi carries the value to fp16 precision, lo only the remainder
     assert (b[:, :, :, 32:].float().abs() <= b[:, :, :, :32].float().abs() * 2 ** -10 + 1e-7).all()
+
+
+def test_data_gradient_operand_reproduces_the_transposed_convolution():
+    """pack.conv_f16_steps of the spatially flipped W^T (the B operand of csrc/conv_dx_tc.cu): layout [9 * cin/16][2][2][n_pad][8],
+    hi + lo = weight, zero rows beyond n, and -- read as a regular 3x3 convolution of the gate gradients, which is what the
+    kernel computes -- it is the data gradient of the cell's convolution (autograd)."""
+    import torch.nn.functional as F
+    gen = torch.Generator().manual_seed(5)
+    for gates, cin_cell, n_pad in ((64, 48, 48), (64, 32, 32), (32, 40, 48)):
+        wt = torch.randn(gates, cin_cell, 3, 3, generator=gen, dtype=torch.float64)            # the cell's conv weight
+        wT = wt.permute(2, 3, 0, 1).reshape(9, gates, cin_cell).float()                        # [tap][gate][input]
+        steps = pack.conv_f16_steps(wT.flip(0), n_pad)
+        assert steps.shape == (9 * gates // 16, 2, 2, n_pad, 8) and steps.dtype == torch.float16
+        rec = steps[:, :, 0].float() + steps[:, :, 1].float()                                  # [steps][2 chunks][n_pad][8]
+        assert not rec[:, :, cin_cell:].any()
+        taps = rec.reshape(9, gates // 16, 2, n_pad, 8).permute(0, 1, 2, 4, 3).reshape(9, gates, n_pad)[:, :, :cin_cell]
+        _close(taps, wT.flip(0))
+        x = torch.randn(cin_cell, 7, 9, generator=gen, dtype=torch.float64, requires_grad=True)
+        y = F.conv2d(x[None], wt, None, padding=1)[0]
+        dy = torch.randn(*y.shape, generator=gen, dtype=torch.float64)
+        (want,) = torch.autograd.grad(y, x, dy)
+        as_conv = taps.double().reshape(3, 3, gates, cin_cell).permute(3, 2, 0, 1)             # [out = input ch][in = gate][ty][tx]
+        got = F.conv2d(dy[None], as_conv, None, padding=1)[0]
+        torch.testing.assert_close(got, want, rtol=0, atol=1e-5 * float(want.abs().max()))
